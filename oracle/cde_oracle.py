@@ -1,0 +1,729 @@
+"""CPU oracle for the Neural-CDE solve path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch restatement (plain PyTorch fp32/fp64 CPU ops + autograd) of the algorithms the
+reference implements in its vendored ``torchcde 0.2.0`` / ``torchdiffeq 0.2.1``.  It exists so the CUDA product
+path can be *checked*; nothing in the product (``online-neural-cdes_b200/``) may import it.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline / ``--impl reference`` legs use it.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the *real* reference (imported read-only from
+``/root/reference/modules``) on seeded inputs and stores inputs+outputs under ``tests/golden/*.pt``;
+``tests/test_oracle_golden.py`` checks every function here against those vectors and against the reference's own
+known-answer test (``modules/torchcde/test/test_linear_interpolation.py:124-145``).
+
+Reference citations are relative to /root/reference.  "tcde" = modules/torchcde/torchcde, "tdeq" =
+modules/torchdiffeq/torchdiffeq/_impl.
+"""
+import math
+import warnings
+
+import torch
+
+# ----------------------------------------------------------------------------------------------------------------
+# Interpolation constructors
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def forward_fill(x, fill_index=-2):
+    """Last-observation-carried-forward along ``fill_index``.  Follows tcde/misc.py:103-126."""
+    nan = torch.isnan(x)
+    if not nan.any():
+        return x
+    seen = (~nan).cumsum(dim=fill_index)
+    seen[nan] = 0
+    _, src = seen.cummax(dim=fill_index)
+    return x.gather(dim=fill_index, index=src)
+
+
+def default_times(x):
+    """t = 0, 1, ..., L-1 in x's dtype.  tcde/misc.py:78-79."""
+    return torch.linspace(0, x.size(-2) - 1, x.size(-2), dtype=x.dtype, device=x.device)
+
+
+def validate_path(x, t):
+    """Error behaviour of tcde/misc.py:70-100 (ValueError for every malformed input)."""
+    if not x.is_floating_point():
+        raise ValueError("X must both be floating point.")
+    if x.ndimension() < 2:
+        raise ValueError("X must have at least two dimensions, corresponding to time and channels.")
+    if t is None:
+        t = default_times(x)
+    if not t.is_floating_point():
+        raise ValueError("t must both be floating point.")
+    if t.ndimension() != 1:
+        raise ValueError("t must be one dimensional.")
+    if t.numel() > 1 and not bool((t[1:] > t[:-1]).all()):
+        raise ValueError("t must be monotonically increasing.")
+    if x.size(-2) != t.size(0):
+        raise ValueError("The time dimension of X must equal the length of t.")
+    if t.size(0) < 2:
+        raise ValueError("Must have a time dimension of size at least 2.")
+    return t
+
+
+def rectilinear_prepare(x, time_index):
+    """(…, L, C) -> (…, 2L-1, C): ffill, duplicate every row, advance the time column by one row, drop the last
+    row.  tcde/interpolation_linear.py:87-128."""
+    n_channels = x.size(-1)
+    assert isinstance(time_index, int) and 0 <= time_index < n_channels
+    assert not torch.isnan(x[..., time_index]).any(), "nan values in the time column"
+    filled = forward_fill(x)
+    doubled = filled.repeat_interleave(2, dim=-2)
+    doubled[..., :-1, time_index] = doubled[..., 1:, time_index]
+    return doubled[..., :-1, :]
+
+
+def _fill_missing_series(t, x):
+    """One scalar series (L,).  Restates tcde/interpolation_linear.py:13-72 without the Python index walk: for a
+    NaN at j, p = last observed index < j, n = first observed index > j (after the two end points were imputed
+    with the first / last observation), value = x[p] + ((t[j]-t[p])/(t[n]-t[p])) * (x[n]-x[p])."""
+    ok = ~torch.isnan(x)
+    obs = x[ok]
+    if obs.numel() == 0:
+        return torch.zeros_like(x)
+    if obs.numel() == x.numel():
+        return x
+    x = x.clone()
+    if torch.isnan(x[0]):
+        x[0] = obs[0]
+    if torch.isnan(x[-1]):
+        x[-1] = obs[-1]
+    ok = ~torch.isnan(x)
+    if bool(ok.all()):
+        return x
+    L = x.numel()
+    idx = torch.arange(L)
+    prev = torch.where(ok, idx, torch.zeros_like(idx)).cummax(0).values
+    nxt = torch.where(ok, idx, torch.full_like(idx, L - 1)).flip(0).cummin(0).values.flip(0)
+    miss = ~ok
+    p, n, j = prev[miss], nxt[miss], idx[miss]
+    ratio = (t[j] - t[p]) / (t[n] - t[p])
+    x[j] = x[p] + ratio * (x[n] - x[p])
+    return x
+
+
+def _fill_missing(t, x_channels_first):
+    """Recursion over leading dims; tcde/interpolation_linear.py:75-84."""
+    if x_channels_first.ndimension() == 1:
+        return _fill_missing_series(t, x_channels_first)
+    return torch.stack([_fill_missing(t, p) for p in x_channels_first.unbind(0)], 0)
+
+
+def linear_interpolation_coeffs(x, t=None, rectilinear=None, initial_value_if_nan=None, forward_fill_=False):
+    """tcde/interpolation_linear.py:131-180 (note: mutates x when initial_value_if_nan is given, :159-160)."""
+    if initial_value_if_nan is not None:
+        first = x[..., 0, :]
+        first[torch.isnan(first)] = initial_value_if_nan
+    if rectilinear is not None:
+        if torch.isnan(x[..., 0, :]).any():
+            warnings.warn("The data `x` begins with missing values in some channels; not causal.")
+        x = rectilinear_prepare(x, rectilinear)
+    if forward_fill_:
+        x = forward_fill(x)
+    t = validate_path(x, t)
+    if torch.isnan(x).any():
+        x = _fill_missing(t, x.transpose(-1, -2)).transpose(-1, -2)
+    return x
+
+
+def tridiagonal_solve(rhs, upper, diag, lower):
+    """Thomas algorithm, no pivoting, same operation order as tcde/misc.py:13-67.  rhs: (..., n)."""
+    n = rhs.size(-1)
+    upper = upper.expand(*rhs.shape[:-1], n - 1) if upper.ndimension() <= rhs.ndimension() else upper
+    lower = lower.expand(*rhs.shape[:-1], n - 1) if lower.ndimension() <= rhs.ndimension() else lower
+    diag = diag.expand(*rhs.shape[:-1], n) if diag.ndimension() <= rhs.ndimension() else diag
+    d = [None] * n
+    r = [None] * n
+    d[0] = diag[..., 0]
+    r[0] = rhs[..., 0]
+    for i in range(1, n):
+        w = lower[..., i - 1] / d[i - 1]
+        d[i] = diag[..., i] - w * upper[..., i - 1]
+        r[i] = rhs[..., i] - w * r[i - 1]
+    out = [None] * n
+    out[n - 1] = r[n - 1] / d[n - 1]
+    for i in range(n - 2, -1, -1):
+        out[i] = (r[i] - upper[..., i] * out[i + 1]) / d[i]
+    return torch.stack(out, dim=-1)
+
+
+def _cubic_pieces_dense(t, x):
+    """x: (..., L) with no NaN -> a, b, two_c, three_d each (..., L-1).  tcde/interpolation_cubic.py:7-53."""
+    L = x.size(-1)
+    if L < 2:
+        raise ValueError("Must have a time dimension of size at least 2.")
+    if L == 2:
+        a = x[..., :1]
+        b = (x[..., 1:] - x[..., :1]) / (t[..., 1:] - t[..., :1])
+        z = torch.zeros(*x.shape[:-1], 1, dtype=x.dtype, device=x.device)
+        return a, b, z, z.clone()
+    h_inv = (t[1:] - t[:-1]).reciprocal()
+    h_inv2 = h_inv ** 2
+    three_dx = 3 * (x[..., 1:] - x[..., :-1])
+    six_dx = 2 * three_dx
+    dx_scaled = three_dx * h_inv2
+    diag = torch.empty(L, dtype=x.dtype, device=x.device)
+    diag[:-1] = h_inv
+    diag[-1] = 0
+    diag[1:] += h_inv
+    diag *= 2
+    rhs = torch.empty_like(x)
+    rhs[..., :-1] = dx_scaled
+    rhs[..., -1] = 0
+    rhs[..., 1:] += dx_scaled
+    kd = tridiagonal_solve(rhs, h_inv, diag, h_inv)
+    a = x[..., :-1]
+    b = kd[..., :-1]
+    two_c = (six_dx * h_inv - 4 * kd[..., :-1] - 2 * kd[..., 1:]) * h_inv
+    three_d = (-six_dx * h_inv + 3 * (kd[..., :-1] + kd[..., 1:])) * h_inv2
+    return a, b, two_c, three_d
+
+
+def _cubic_pieces_missing_series(t, x, version):
+    """One scalar series with NaNs.  tcde/interpolation_cubic.py:78-167: spline through the observed points only,
+    then every original interval gets the polynomial of the observed-piece it lies in, re-centred at its own left
+    end (offset = left-observed-time - own time)."""
+    L = x.size(0)
+    nan = torch.isnan(x)
+    obs = x[~nan]
+    if obs.numel() == 0:
+        z = torch.zeros(L - 1, dtype=x.dtype, device=x.device)
+        return z, z.clone(), z.clone(), z.clone()
+    x = x.clone()
+    if version == 0:
+        if torch.isnan(x[0]):
+            x[0] = obs[0]
+        if torch.isnan(x[-1]):
+            x[-1] = obs[-1]
+    else:
+        where = torch.nonzero(~nan).flatten()
+        first, last = int(where[0]), int(where[-1])
+        x[:first] = x[first]
+        x[last + 1:] = x[last]
+    ok = ~torch.isnan(x)
+    t_obs = t[ok]
+    pa, pb, pc, pd = _cubic_pieces_dense(t_obs, x[ok])
+    # piece index for every original interval start t[i]: number of observed times <= t[i], minus one
+    piece = (torch.searchsorted(t_obs, t[:-1].contiguous(), right=True) - 1).clamp(0, pa.numel() - 1)
+    off = t_obs[piece] - t[:-1]
+    a_, b_, c_, d_ = pa[piece], pb[piece], pc[piece], pd[piece]
+    inner = (0.5 * c_ - d_ * off / 3) * off
+    a = a_ + (inner - b_) * off
+    b = b_ + (d_ * off - c_) * off
+    two_c = c_ - 2 * d_ * off
+    return a, b, two_c, d_
+
+
+def _cubic_pieces_missing(t, x, version):
+    if x.ndimension() == 1:
+        return _cubic_pieces_missing_series(t, x, version)
+    parts = [_cubic_pieces_missing(t, p, version) for p in x.unbind(0)]
+    return tuple(torch.stack([p[i] for p in parts], 0) for i in range(4))
+
+
+def natural_cubic_coeffs(x, t=None, _version=1):
+    """(…, L, C) -> (…, L-1, 4C) = cat[a, b, 2c, 3d].  tcde/interpolation_cubic.py:173-190, 233-265."""
+    t = validate_path(x, t)
+    xt = x.transpose(-1, -2)
+    if torch.isnan(x).any():
+        parts = _cubic_pieces_missing(t, xt, _version)
+    else:
+        parts = _cubic_pieces_dense(t, xt)
+    return torch.cat([p.transpose(-1, -2) for p in parts], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Paths
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def knot_index(t, knots, n_pieces):
+    """bucketize(t, knots) - 1 clamped to [0, n_pieces-1]: at an exact knot k >= 1 this is the LEFT piece k-1.
+    tcde/interpolation_linear.py:212-219, interpolation_cubic.py:315-322."""
+    return torch.bucketize(t.detach(), knots.detach()).sub(1).clamp(0, n_pieces - 1)
+
+
+class LinearPath(torch.nn.Module):
+    """tcde/interpolation_linear.py:183-234."""
+
+    def __init__(self, coeffs, t=None):
+        super().__init__()
+        if t is None:
+            t = torch.linspace(0, coeffs.size(-2) - 1, coeffs.size(-2), dtype=coeffs.dtype, device=coeffs.device)
+        self.t = t
+        self.coeffs = coeffs
+        self.derivs = (coeffs[..., 1:, :] - coeffs[..., :-1, :]) / (t[1:] - t[:-1]).unsqueeze(-1)
+
+    @property
+    def grid_points(self):
+        return self.t
+
+    @property
+    def interval(self):
+        return torch.stack([self.t[0], self.t[-1]])
+
+    def _locate(self, t):
+        t = torch.as_tensor(t, dtype=self.derivs.dtype, device=self.derivs.device)
+        i = knot_index(t, self.t, self.derivs.size(-2))
+        return t - self.t[i], i
+
+    def evaluate(self, t):
+        frac, i = self._locate(t)
+        frac = frac.unsqueeze(-1)
+        lo = self.coeffs[..., i, :]
+        hi = self.coeffs[..., i + 1, :]
+        width = self.t[i + 1] - self.t[i]
+        return lo + frac * (hi - lo) / width.unsqueeze(-1)
+
+    def derivative(self, t):
+        _, i = self._locate(t)
+        return self.derivs[..., i, :]
+
+
+class CubicPath(torch.nn.Module):
+    """tcde/interpolation_cubic.py:268-336."""
+
+    def __init__(self, coeffs, t=None):
+        super().__init__()
+        if t is None:
+            t = torch.linspace(0, coeffs.size(-2), coeffs.size(-2) + 1, dtype=coeffs.dtype, device=coeffs.device)
+        c = coeffs.size(-1) // 4
+        if 4 * c != coeffs.size(-1):
+            raise ValueError("Passed invalid coeffs.")
+        self.t = t
+        self.a, self.b = coeffs[..., :c], coeffs[..., c:2 * c]
+        self.two_c, self.three_d = coeffs[..., 2 * c:3 * c], coeffs[..., 3 * c:]
+
+    @property
+    def grid_points(self):
+        return self.t
+
+    @property
+    def interval(self):
+        return torch.stack([self.t[0], self.t[-1]])
+
+    def _locate(self, t):
+        t = torch.as_tensor(t, dtype=self.b.dtype, device=self.b.device)
+        i = knot_index(t, self.t, self.b.size(-2))
+        return t - self.t[i], i
+
+    def evaluate(self, t):
+        frac, i = self._locate(t)
+        frac = frac.unsqueeze(-1)
+        inner = 0.5 * self.two_c[..., i, :] + self.three_d[..., i, :] * frac / 3
+        inner = self.b[..., i, :] + inner * frac
+        return self.a[..., i, :] + inner * frac
+
+    def derivative(self, t):
+        frac, i = self._locate(t)
+        frac = frac.unsqueeze(-1)
+        inner = self.two_c[..., i, :] + self.three_d[..., i, :] * frac
+        return self.b[..., i, :] + inner * frac
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ODE solvers (restating tdeq)
+# ----------------------------------------------------------------------------------------------------------------
+
+_THIRD = 1 / 3
+_TWO_THIRDS = 2 / 3
+
+
+def _prev_float(x):
+    return torch.nextafter(x, torch.tensor(-math.inf, dtype=x.dtype))
+
+
+def _next_float(x):
+    return torch.nextafter(x, torch.tensor(math.inf, dtype=x.dtype))
+
+
+class _Timed:
+    """Casts t to the state dtype before calling f, with optional one-ulp nudge.  tdeq/misc.py:168-191."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __call__(self, t, y, nudge=0):
+        t = t.to(y.dtype)
+        if nudge > 0:
+            t = _next_float(t.detach()) + (t - t.detach())
+        elif nudge < 0:
+            t = _prev_float(t.detach()) + (t - t.detach())
+        return self.f(t, y)
+
+
+def fixed_grid(t, step_size):
+    """tdeq/solvers.py:77-88 — arange(ceil((t_end-t0)/h + 1)) * h + t0 with the last point snapped to t[-1]."""
+    if step_size is None:
+        return t
+    n = torch.ceil((t[-1] - t[0]) / step_size + 1).item()
+    grid = torch.arange(0, n, dtype=t.dtype, device=t.device) * step_size + t[0]
+    grid[-1] = t[-1]
+    return grid
+
+
+def _euler_increment(f, t0, dt, t1, y0):
+    """tdeq/fixed_grid.py:6-11."""
+    return dt * f(t0, y0)
+
+
+def _rk4_38_increment(f, t0, dt, t1, y0):
+    """The 3/8-rule RK4 that method='rk4' actually runs.  tdeq/fixed_grid.py:24-29, rk_common.py:106-114."""
+    k1 = f(t0, y0)
+    k2 = f(t0 + dt * _THIRD, y0 + dt * k1 * _THIRD)
+    k3 = f(t0 + dt * _TWO_THIRDS, y0 + dt * (k2 - k1 * _THIRD))
+    k4 = f(t1, y0 + dt * (k1 - k2 + k3))
+    return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+
+
+_FIXED = {"euler": _euler_increment, "rk4": _rk4_38_increment}
+
+
+def odeint_fixed(f, y0, t, method, step_size=None):
+    """tdeq/solvers.py:90-119 with linear output interpolation (:166-172)."""
+    f = _Timed(f)
+    grid = fixed_grid(t, step_size)
+    assert grid[0] == t[0] and grid[-1] == t[-1]
+    inc = _FIXED[method]
+    out = [y0]
+    j = 1
+    y = y0
+    for a, b in zip(grid[:-1], grid[1:]):
+        dt = b - a
+        y_next = y + inc(f, a, dt, b, y)
+        while j < len(t) and b >= t[j]:
+            if t[j] == a:
+                out.append(y)
+            elif t[j] == b:
+                out.append(y_next)
+            else:
+                slope = (t[j] - a) / (b - a)
+                out.append(y + slope * (y_next - y))
+            j += 1
+        y = y_next
+    return torch.stack(out, 0)
+
+
+# Dormand-Prince 5(4), tdeq/dopri5.py:5-30
+_DP_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_DP_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_DP_ERR = [35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+           -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1. / 60.]
+_DP_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+           187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+
+
+def rms_norm(x):
+    """tdeq/misc.py:18-19 — ONE scalar over the whole state, so the batch shares a step size."""
+    return x.pow(2).mean().sqrt()
+
+
+def _initial_step(f, t0, y0, order, rtol, atol, norm, f0):
+    """tdeq/misc.py:32-71 (Hairer II.4).  `order` is passed as solver.order - 1 = 4 (rk_common.py:167)."""
+    t_dtype = t0.dtype
+    t0 = t0.to(y0.dtype)
+    scale = atol + torch.abs(y0) * rtol
+    d0 = norm(y0 / scale)
+    d1 = norm(f0 / scale)
+    if d0 < 1e-5 or d1 < 1e-5:
+        h0 = torch.tensor(1e-6, dtype=y0.dtype)
+    else:
+        h0 = 0.01 * d0 / d1
+    f1 = f(t0 + h0, y0 + h0 * f0)
+    d2 = norm((f1 - f0) / scale) / h0
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = torch.max(torch.tensor(1e-6, dtype=y0.dtype), h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1. / float(order + 1))
+    return torch.min(100 * h0, h1).to(t_dtype)
+
+
+def _next_step_size(dt, ratio, safety, ifactor, dfactor, order):
+    """tdeq/misc.py:79-89."""
+    if ratio == 0:
+        return dt * ifactor
+    if ratio < 1:
+        dfactor = torch.ones((), dtype=dt.dtype)
+    ratio = ratio.to(dt.dtype)
+    exponent = torch.tensor(order, dtype=dt.dtype).reciprocal()
+    return dt * torch.min(ifactor, torch.max(safety / ratio ** exponent, dfactor))
+
+
+class Dopri5:
+    """Adaptive Dormand-Prince with dense output.  tdeq/rk_common.py:117-313, solvers.py:24-31, interp.py.
+
+    State is fp32 (y0.dtype), every time-like scalar fp64.  `stats` counts attempted / accepted steps and vector
+    field evaluations so the CUDA path's control flow can be compared exactly."""
+
+    order = 5
+
+    def __init__(self, f, y0, rtol, atol, norm=rms_norm, min_step=0, max_step=float("inf"), first_step=None,
+                 safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=torch.float64):
+        self.f = _Timed(f)
+        self.y0 = y0
+        self.norm = norm
+        dtype = torch.promote_types(dtype, y0.dtype)
+        as_t = lambda v: torch.as_tensor(v, dtype=dtype)
+        self.rtol, self.atol = as_t(rtol), as_t(atol)
+        self.min_step, self.max_step = as_t(min_step), as_t(max_step)
+        self.first_step = None if first_step is None else as_t(first_step)
+        self.safety, self.ifactor, self.dfactor = as_t(safety), as_t(ifactor), as_t(dfactor)
+        self.max_num_steps = max_num_steps
+        self.dtype = dtype
+        yd = y0.dtype
+        self.alpha = torch.tensor(_DP_ALPHA, dtype=torch.float64).to(yd)
+        self.beta = [torch.tensor(b, dtype=torch.float64).to(yd) for b in _DP_BETA]
+        self.c_err = torch.tensor(_DP_ERR, dtype=torch.float64).to(yd)
+        self.c_mid = torch.tensor(_DP_MID, dtype=torch.float64).to(yd)
+        self.stats = {"attempted": 0, "accepted": 0, "nfe": 0}
+
+    def _f(self, t, y, nudge=0):
+        self.stats["nfe"] += 1
+        return self.f(t, y, nudge=nudge)
+
+    def _rk_step(self, y0, f0, t0, dt, t1):
+        """tdeq/rk_common.py:41-86.  Stages with alpha == 1 are evaluated one ulp before t1."""
+        t0, dt, t1 = t0.to(y0.dtype), dt.to(y0.dtype), t1.to(y0.dtype)
+        k = [f0]
+        yi = None
+        for a, b in zip(self.alpha, self.beta):
+            if a == 1.:
+                ti, nudge = t1, -1
+            else:
+                ti, nudge = t0 + a * dt, 0
+            yi = y0 + torch.stack(k, -1).matmul(b * dt).view_as(f0)
+            k.append(self._f(ti, yi, nudge=nudge))
+        kk = torch.stack(k, -1)
+        return yi, k[-1], kk.matmul(dt * self.c_err), kk
+
+    def _fit(self, y0, y1, kk, dt):
+        """tdeq/rk_common.py:307-313 + interp.py:1-22."""
+        dt = dt.type_as(y0)
+        y_mid = y0 + kk.matmul(dt * self.c_mid).view_as(y0)
+        f0, f1 = kk[..., 0], kk[..., -1]
+        a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+        b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+        c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+        return [y0, dt * f0, c, b, a]
+
+    @staticmethod
+    def _dense(coeffs, t0, t1, t):
+        """tdeq/interp.py:25-48."""
+        assert (t0 <= t) & (t <= t1)
+        x = ((t - t0) / (t1 - t0)).to(coeffs[0].dtype)
+        total = coeffs[0] + x * coeffs[1]
+        xp = x
+        for c in coeffs[2:]:
+            xp = xp * x
+            total = total + xp * c
+        return total
+
+    def integrate(self, t):
+        out = [self.y0]
+        t = t.to(self.dtype)
+        f0 = self._f(t[0], self.y0)
+        if self.first_step is None:
+            dt = _initial_step(lambda tt, yy: self._f(tt, yy), t[0], self.y0, self.order - 1, self.rtol, self.atol,
+                               self.norm, f0)
+        else:
+            dt = self.first_step
+        y, f_cur, t_lo, t_hi, coeffs = self.y0, f0, t[0], t[0], [self.y0] * 5
+        for i in range(1, len(t)):
+            n = 0
+            while t[i] > t_hi:
+                assert n < self.max_num_steps, "max_num_steps exceeded"
+                # one adaptive attempt, tdeq/rk_common.py:216-305
+                t0 = t_hi
+                t1 = t0 + dt
+                assert t0 + dt > t0, "underflow in dt {}".format(dt.item())
+                assert torch.isfinite(y).all(), "non-finite values in state `y`"
+                y1, f1, err, kk = self._rk_step(y, f_cur, t0, dt, t1)
+                tol = self.atol + self.rtol * torch.max(y.abs(), y1.abs())
+                ratio = self.norm(err / tol)
+                accept = bool(ratio <= 1)
+                if dt > self.max_step:
+                    accept = False
+                if dt <= self.min_step:
+                    accept = True
+                self.stats["attempted"] += 1
+                if accept:
+                    self.stats["accepted"] += 1
+                    coeffs = self._fit(y, y1, kk, dt)
+                    y, f_cur, t_hi = y1, f1, t1
+                t_lo = t0
+                with torch.no_grad():
+                    dt = _next_step_size(dt, ratio, self.safety, self.ifactor, self.dfactor, self.order)
+                dt = dt.clamp(self.min_step, self.max_step)
+                n += 1
+            out.append(self._dense(coeffs, t_lo, t_hi, t[i]))
+        return torch.stack(out, 0)
+
+
+def odeint(f, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, options=None, stats=None):
+    """Tensor-state odeint for increasing or decreasing t.  tdeq/odeint.py:31-90, misc.py:194-305."""
+    options = dict(options or {})
+    if method is None:
+        method = "dopri5"
+    if method not in ("euler", "rk4", "dopri5"):
+        raise ValueError('Invalid method "{}".'.format(method))
+    if len(t) > 1 and t[0] > t[1]:
+        t = -t
+        g = f
+        f = lambda tt, yy: -g(-tt, yy)
+    assert bool((t[1:] > t[:-1]).all()), "t must be strictly increasing or decreasing"
+    if method in _FIXED:
+        return odeint_fixed(f, y0, t, method, step_size=options.get("step_size"))
+    options.setdefault("norm", rms_norm)
+    solver = Dopri5(f, y0, rtol, atol, **options)
+    sol = solver.integrate(t)
+    if stats is not None:
+        for k, v in solver.stats.items():
+            stats[k] = stats.get(k, 0) + v
+    return sol
+
+
+class _Adjoint(torch.autograd.Function):
+    """Continuous adjoint.  tdeq/adjoint.py:9-145: forward under no_grad; backward integrates the augmented
+    state (vjp_t, y, a_y, a_theta...) backwards over each output interval, flattened into one vector whose norm is
+    max(|t|, rms(y), rms(a_y), max_i rms(a_theta_i)) (:235-246)."""
+
+    @staticmethod
+    def forward(ctx, f, t, method, rtol, atol, options, adj_opts, stats, y0, *params):
+        ctx.f, ctx.method, ctx.adj_opts, ctx.stats = f, method, adj_opts, stats
+        with torch.no_grad():
+            y = odeint(f, y0, t, method, rtol, atol, options, stats)
+        ctx.save_for_backward(t, y, *params)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        f, method, stats = ctx.f, ctx.method, ctx.stats
+        rtol, atol, options = ctx.adj_opts
+        t, y, *params = ctx.saved_tensors
+        params = tuple(params)
+        shapes = [torch.Size(())] + [y[-1].shape, y[-1].shape] + [p.shape for p in params]
+        sizes = [s.numel() for s in shapes]
+
+        def unflat(v):
+            return [c.view(s) for c, s in zip(v.split(sizes), shapes)]
+
+        def flat(parts):
+            return torch.cat([p.reshape(-1) for p in parts])
+
+        def aug_norm(v):
+            parts = unflat(v)
+            vals = [parts[0].abs(), rms_norm(parts[1]), rms_norm(parts[2])]
+            if len(parts) > 3:
+                vals.append(max(rms_norm(p) for p in parts[3:]))
+            return max(vals)
+
+        timed = _Timed(f)
+
+        def aug(tt, v):
+            parts = unflat(v)
+            yy, a = parts[1], parts[2]
+            with torch.enable_grad():
+                # Quirk kept on purpose: tdeq/adjoint.py:80-81 does `t_ = t.detach(); t = t_.requires_grad_(True)`,
+                # which makes t_ require grad too, so vjp_t is ALWAYS computed (non-zero whenever dX/dt depends
+                # on t, i.e. cubic paths) and enters the adjoint error norm through |vjp_t|.
+                tt = tt.detach().requires_grad_(True)
+                yy = yy.detach().requires_grad_(True)
+                fe = timed(tt, yy)
+                vj = torch.autograd.grad(fe, (tt, yy) + params, -a, allow_unused=True)
+            vj = [torch.zeros_like(w) if g is None else g for g, w in zip(vj, (tt, yy) + params)]
+            return flat([vj[0], fe.detach(), vj[1]] + vj[2:])
+
+        with torch.no_grad():
+            state = [torch.zeros((), dtype=y.dtype), y[-1], grad_y[-1]] + [torch.zeros_like(p) for p in params]
+            opts = dict(options)
+            if method == "dopri5":
+                opts["norm"] = aug_norm
+            for i in range(len(t) - 1, 0, -1):
+                sol = odeint(aug, flat(state), t[i - 1:i + 1].flip(0), method, rtol, atol, opts, stats)
+                state = unflat(sol[1])
+                state[1] = y[i - 1]
+                state[2] = state[2] + grad_y[i - 1]
+        return (None,) * 8 + (state[2],) + tuple(state[3:])
+
+
+def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, options=None, stats=None):
+    """tcde/solver.py:140-238 for a single batch dimension, 'matmul' vector fields and tensor state:
+    g(t, z) = func(t, z) @ dX/dt(t); returns (B, len(t), H).  Defaults atol=1e-6 / rtol=1e-4 (:193-196);
+    adjoint_* default to the forward values with `norm` dropped (tdeq/adjoint.py:159-171)."""
+    atol = 1e-6 if atol is None else atol
+    rtol = 1e-4 if rtol is None else rtol
+
+    def g(tt, z):
+        return (func(tt, z) @ X.derivative(tt).unsqueeze(-1)).squeeze(-1)
+
+    if adjoint:
+        params = tuple(p for p in func.parameters() if p.requires_grad)
+        adj_options = {k: v for k, v in (options or {}).items() if k != "norm"}
+        out = _Adjoint.apply(g, t, method, rtol, atol, options, (rtol, atol, adj_options), stats, z0, *params)
+    else:
+        out = odeint(g, z0, t, method, rtol, atol, options, stats)
+    return out.transpose(0, 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Vector fields and the thin model wrapper used by the configs
+# ----------------------------------------------------------------------------------------------------------------
+
+
+class SharedMLPField(torch.nn.Module):
+    """src/ncde/vector_fields/base.py:64-69,83-104 — note the *same* Linear object is repeated for every middle
+    layer, so its weight gradient accumulates over the repeats."""
+
+    def __init__(self, input_dim, hidden_dim, hidden_hidden_dim, num_layers):
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        layers = [torch.nn.Linear(hidden_dim, hidden_hidden_dim), torch.nn.ReLU()]
+        if num_layers > 1:
+            layers += [torch.nn.Linear(hidden_hidden_dim, hidden_hidden_dim), torch.nn.ReLU()] * (num_layers - 1)
+        self.net_to_hh = torch.nn.Sequential(*layers)
+        self.tanh_output_layer = torch.nn.Sequential(torch.nn.Linear(hidden_hidden_dim, hidden_dim * input_dim),
+                                                     torch.nn.Tanh())
+        self.nfe = 0
+
+    def forward(self, t, h):
+        self.nfe += 1
+        return self.tanh_output_layer(self.net_to_hh(h)).view(-1, self.hidden_dim, self.input_dim)
+
+
+class ToyField(torch.nn.Module):
+    """experiments/sim_bm_toy_example.py:10-30."""
+
+    def __init__(self, input_channels, hidden_channels, width=128):
+        super().__init__()
+        self.input_channels, self.hidden_channels = input_channels, hidden_channels
+        self.linear0 = torch.nn.Linear(hidden_channels, hidden_channels)
+        self.linear1 = torch.nn.Linear(hidden_channels, width)
+        self.linear2 = torch.nn.Linear(width, input_channels * hidden_channels)
+
+    def forward(self, t, z):
+        z = self.linear0(z).relu()
+        z = self.linear1(z).relu()
+        z = self.linear2(z).tanh()
+        return z.view(z.size(0), self.hidden_channels, self.input_channels)
+
+
+def ncde_forward(coeffs, func, initial, readout, interpolation, method, adjoint, online, static=None,
+                 options=None, rtol=1e-3, atol=1e-5, stats=None):
+    """src/ncde/ncde.py:170-243: h0 = initial([static ⊕] X(0)); hidden = cdeint(...); readout; rectilinear online
+    outputs keep every other knot."""
+    X = CubicPath(coeffs) if interpolation == "cubic" else LinearPath(coeffs)
+    x0 = X.evaluate(0)
+    h0 = initial(x0 if static is None else torch.cat((static, x0), -1))
+    times = X.grid_points if online else X.interval
+    hidden = cdeint(X, func, h0, times, adjoint=adjoint, method=method, rtol=rtol, atol=atol, options=options,
+                    stats=stats)
+    if online:
+        out = readout(hidden)
+        return out[:, ::2] if interpolation == "rectilinear" else out
+    return readout(hidden[:, -1, :])
