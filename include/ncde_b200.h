@@ -1,0 +1,182 @@
+/*
+ * ncde_b200.h — C ABI of the B200-native Neural-CDE solve path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every pointer marked "device" is a
+ * CUDA device pointer on the current device; `stream` is a cudaStream_t passed as void*.  All entry points are
+ * asynchronous on `stream` (no host synchronisation inside) and return NCDE_OK or a negative error code;
+ * ncde_last_error() gives a thread-local message.  The caller owns every buffer.
+ *
+ * The reference (jambo6/online-neural-cdes) has no native layer: the functions replaced here are the Python
+ * hot path of its vendored torchcde 0.2.0 / torchdiffeq 0.2.1.  Each entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ */
+#ifndef NCDE_B200_H
+#define NCDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCDE_ABI_VERSION 1
+#define NCDE_MAX_LAYERS 8
+#define NCDE_MAX_STAGES 7
+
+enum ncde_status {
+    NCDE_OK = 0,
+    NCDE_ERR_INVALID = -1,      /* bad argument (maps to ValueError) */
+    NCDE_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+    NCDE_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels were built for */
+    NCDE_ERR_WORKSPACE = -4     /* caller-provided workspace too small */
+};
+
+enum ncde_dtype { NCDE_F32 = 0, NCDE_F64 = 1 };
+enum ncde_path_kind { NCDE_PATH_LINEAR = 0, NCDE_PATH_CUBIC = 1 };
+enum ncde_method { NCDE_EULER = 0, NCDE_RK4_38 = 1, NCDE_DOPRI5 = 2 };
+enum ncde_act { NCDE_ACT_NONE = 0, NCDE_ACT_RELU = 1, NCDE_ACT_TANH = 2 };
+/* arithmetic of the final (H*C-wide) layer: fp32 FFMA, or bf16 tcgen05 tensor-core tiles with fp32 accumulate */
+enum ncde_precision { NCDE_PREC_FP32 = 0, NCDE_PREC_BF16 = 1 };
+
+/* device status words written by kernels (read them after synchronising the stream) */
+enum ncde_flag_bits {
+    NCDE_FLAG_NAN_TIME = 1,       /* rectilinear: NaN in the time channel (AssertionError in the reference) */
+    NCDE_FLAG_NONFINITE = 2,      /* dopri5: non-finite state (rk_common.py:233) */
+    NCDE_FLAG_DT_UNDERFLOW = 4,   /* dopri5: t0 + dt == t0 (rk_common.py:232) */
+    NCDE_FLAG_MAX_STEPS = 8       /* dopri5: attempt budget exhausted before reaching t[-1] */
+};
+
+const char* ncde_version(void);
+const char* ncde_last_error(void);
+int ncde_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Interpolation constructors.  x is (n_series, L, C) contiguous, dtype f32 or f64.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Forward fill along the length axis.  Replaces torchcde.misc.forward_fill
+ * (modules/torchcde/torchcde/misc.py:103-126).  out may alias x. */
+int ncde_forward_fill(int dtype, const void* x, void* out, int64_t n_series, int64_t L, int64_t C, void* stream);
+
+/* Rectilinear preparation: ffill, duplicate rows, advance the time column, drop the last row ->
+ * out (n_series, 2L-1, C).  Replaces _prepare_rectilinear_interpolation
+ * (modules/torchcde/torchcde/interpolation_linear.py:87-128).  Sets NCDE_FLAG_NAN_TIME in *flags (device int32,
+ * caller zero-initialised) if the time channel holds a NaN. */
+int ncde_rectilinear_prepare(int dtype, const void* x, void* out, int64_t n_series, int64_t L, int64_t C,
+                             int time_index, int32_t* flags, void* stream);
+
+/* In-place linear fill of missing (NaN) values per (series, channel): ends imputed with the first / last
+ * observation, interior by linear interpolation in t, all-NaN channel -> zeros.  Replaces
+ * _linear_interpolation_coeffs_with_missing_values (modules/torchcde/torchcde/interpolation_linear.py:13-84).
+ * t: device (L). */
+int ncde_linear_fill_missing(int dtype, void* x, const void* t, int64_t n_series, int64_t L, int64_t C,
+                             void* stream);
+
+/* Natural cubic spline coefficients, out (n_series, L-1, 4C) = [a | b | 2c | 3d].  NaN-aware (version 0/1 end
+ * handling).  Replaces _natural_cubic_spline_coeffs (modules/torchcde/torchcde/interpolation_cubic.py:7-190) and
+ * tridiagonal_solve (modules/torchcde/torchcde/misc.py:13-67).  scratch: device, ncde_cubic_scratch_bytes(). */
+size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t L, int64_t C);
+int ncde_natural_cubic_coeffs(int dtype, const void* x, const void* t, void* out, int64_t n_series, int64_t L,
+                              int64_t C, int version, void* scratch, void* stream);
+
+/* derivs[s,i,c] = (coeffs[s,i+1,c]-coeffs[s,i,c]) / (t[i+1]-t[i]); the LinearInterpolation constructor
+ * (modules/torchcde/torchcde/interpolation_linear.py:198). */
+int ncde_linear_derivs(int dtype, const void* coeffs, const void* t, void* derivs, int64_t n_series, int64_t K,
+                       int64_t C, void* stream);
+
+/* Evaluate a path or its derivative at n_t query times (device array tq).  kind LINEAR: coeffs (n_series,K,C),
+ * derivs (n_series,K-1,C) (may be NULL when deriv == 0); kind CUBIC: coeffs (n_series,K-1,4C).
+ * out: (n_series, n_t, C).  index_out (device int64, n_t, nullable) receives the knot index
+ * bucketize(t, knots) - 1 clamped to [0, K-2].  Replaces LinearInterpolation / NaturalCubicSpline
+ * ._interpret_t/.evaluate/.derivative (interpolation_linear.py:212-234, interpolation_cubic.py:315-336). */
+int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, const void* knots,
+                   int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv, void* out,
+                   int64_t* index_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The solve: z_t = z_0 + int f_theta(z_s) dX_s, replacing torchcde.cdeint -> torchdiffeq.odeint[_adjoint]
+ * (modules/torchcde/torchcde/solver.py:102-238; modules/torchdiffeq/torchdiffeq/_impl/solvers.py:48-119,
+ * fixed_grid.py:6-29, rk_common.py:41-313, adjoint.py:9-215).  fp32 state, fp64 step control.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* f_theta: a chain of Linear layers; layer l maps in_dim[l] -> out_dim[l] with activation act[l].  The last
+ * layer has out_dim == H*C and its output row h*C + c is the (h, c) entry of the vector-field matrix
+ * (src/ncde/vector_fields/base.py:83-104).  Layers with equal slot[] share one weight/bias tensor (the
+ * reference's list-multiplication of one nn.Linear, base.py:64-69): give them the same W/bias pointers; their
+ * gradients accumulate into the same gW/gbias. */
+typedef struct ncde_mlp {
+    int32_t n_layers;
+    int32_t in_dim[NCDE_MAX_LAYERS];
+    int32_t out_dim[NCDE_MAX_LAYERS];
+    int32_t act[NCDE_MAX_LAYERS];
+    int32_t slot[NCDE_MAX_LAYERS];
+    const float* W[NCDE_MAX_LAYERS];    /* device, (out_dim, in_dim) row-major — torch.nn.Linear layout */
+    const float* bias[NCDE_MAX_LAYERS]; /* device, (out_dim) or NULL */
+} ncde_mlp_t;
+
+typedef struct ncde_path {
+    int32_t kind;        /* ncde_path_kind */
+    int64_t K;           /* number of knots */
+    const float* knots;  /* device (K) */
+    const float* coeffs; /* device; LINEAR (B,K,C), CUBIC (B,K-1,4C) */
+    const float* derivs; /* device; LINEAR (B,K-1,C) precomputed by ncde_linear_derivs, or NULL; CUBIC NULL */
+} ncde_path_t;
+
+/* Fixed-grid schedule, built by the host exactly as torchdiffeq does (solvers.py:77-119): everything here lives
+ * in HOST memory and is consumed while enqueuing. */
+typedef struct ncde_fixed_grid {
+    int64_t n_steps;
+    const float* stage_t; /* (n_steps, n_stages) stage times after the cast to the state dtype (misc.py:181) */
+    const float* dt;      /* (n_steps) t1 - t0 rounded to fp32 */
+    int64_t n_out;        /* number of output times T (t[0] included) */
+    const int64_t* out_step; /* (T) grid step whose interval emits output j; out_step[0] is ignored */
+    const int32_t* out_mode; /* (T) 0: state at step start, 1: state at step end, 2: linear interpolation */
+    const float* out_slope;  /* (T) (t[j]-t0)/(t1-t0) for mode 2 */
+} ncde_fixed_grid_t;
+
+/* dopri5 controller parameters (rk_common.py:122-160; misc.py:32-89). */
+typedef struct ncde_adaptive {
+    double rtol, atol, min_step, max_step, first_step /* < 0: select automatically */, safety, ifactor, dfactor;
+    int64_t max_attempts; /* attempt budget enqueued without host sync */
+    int64_t n_out;        /* T */
+    const double* out_t;  /* HOST (T) increasing output times */
+} ncde_adaptive_t;
+
+typedef struct ncde_problem {
+    int64_t B;
+    int32_t H, C;
+    int32_t method;    /* ncde_method */
+    int32_t precision; /* ncde_precision */
+    ncde_mlp_t mlp;
+    ncde_path_t path;
+    ncde_fixed_grid_t grid;   /* EULER / RK4_38 */
+    ncde_adaptive_t adaptive; /* DOPRI5 */
+} ncde_problem_t;
+
+/* Byte sizes of the two caller-provided device buffers: `saved` carries what the backward pass needs (stage
+ * inputs, hidden activations, path derivatives per stage) and must stay alive until ncde_solve_bwd;
+ * `workspace` is scratch valid for one call. */
+size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad);
+size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward);
+
+/* Forward.  z0 (B,H) device; z_out (T,B,H) device (torchdiffeq's layout; cdeint returns its (B,T,H) permuted
+ * view, solver.py:227-229).  saved may be NULL when need_grad == 0.  flags: device int32 (nullable).
+ * stats (device int64[4], nullable): attempted steps, accepted steps, vector-field evaluations, kernels launched.
+ * launches (host, nullable): number of kernels this call enqueued. */
+int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void* saved, int need_grad,
+                   void* workspace, size_t workspace_bytes, int32_t* flags, int64_t* stats, int64_t* launches,
+                   void* stream);
+
+/* Backward of the fixed-grid solve (discretise-then-optimise: the exact gradient autograd produces through the
+ * reference's step loop).  grad_out (T,B,H).  Writes grad_z0 (B,H); ACCUMULATES into gW[l]/gbias[l] (torch
+ * layout, one pointer per layer; layers sharing a slot must pass the same pointer).  grad_coeffs (nullable):
+ * gradient w.r.t. path.coeffs, same shape, accumulated. */
+int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, const void* saved, float* grad_z0,
+                   float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
+                   size_t workspace_bytes, int64_t* launches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCDE_B200_H */

@@ -1,0 +1,372 @@
+// Interpolation constructors and evaluators as sm_100a CUDA.
+//
+// These are HBM-bound copy / scan kernels: one thread owns one (series, channel) scalar series and walks the
+// length axis; consecutive threads own consecutive channels, so every step of the walk is a coalesced row access.
+// Compiled with -fmad=false: the reference evaluates each torch op with its own rounding (no fused
+// multiply-add), and matching that is what makes the outputs bit-identical to the reference on the same inputs.
+#include "common.cuh"
+
+namespace ncde {
+
+template <typename T>
+__device__ __forceinline__ bool is_nan(T v) { return v != v; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward fill — torchcde/misc.py:103-126
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void forward_fill_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n_series, int64_t L,
+                                    int64_t C) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    int64_t s = tid / C, c = tid % C;
+    const T* xs = x + s * L * C + c;
+    T* os = out + s * L * C + c;
+    T last = xs[0];  // stays NaN until the first observation, like the gather through cummax index 0
+    for (int64_t i = 0; i < L; ++i) {
+        T v = xs[i * C];
+        if (!is_nan(v)) last = v;
+        os[i * C] = last;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rectilinear preparation — torchcde/interpolation_linear.py:87-128
+//   value channels: out[2i] = out[2i+1] = ffill(x)[i]        time channel: out[2i] = t[i], out[2i+1] = t[i+1]
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rectilinear_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n_series, int64_t L,
+                                   int64_t C, int time_index, int32_t* __restrict__ flags) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    int64_t s = tid / C, c = tid % C;
+    const T* xs = x + s * L * C + c;
+    T* os = out + s * (2 * L - 1) * C + c;
+    const bool is_time = (c == time_index);
+    T last = xs[0];
+    bool bad_time = false;
+    for (int64_t i = 0; i < L; ++i) {
+        T v = xs[i * C];
+        if (is_nan(v)) bad_time = bad_time || is_time; else last = v;
+        if (is_time) {
+            os[(2 * i) * C] = last;
+            if (i > 0) os[(2 * i - 1) * C] = last;
+        } else {
+            os[(2 * i) * C] = last;
+            if (i < L - 1) os[(2 * i + 1) * C] = last;
+        }
+    }
+    if (bad_time && flags) atomicOr(flags, NCDE_FLAG_NAN_TIME);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// linear fill of missing values, in place — torchcde/interpolation_linear.py:13-84
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void linear_fill_kernel(T* __restrict__ x, const T* __restrict__ t, int64_t n_series, int64_t L,
+                                   int64_t C) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    int64_t s = tid / C, c = tid % C;
+    T* xs = x + s * L * C + c;
+    int64_t first = -1, last = -1;
+    for (int64_t i = 0; i < L; ++i) {
+        if (!is_nan(xs[i * C])) { if (first < 0) first = i; last = i; }
+    }
+    if (first < 0) {  // nothing observed: constant zero path
+        for (int64_t i = 0; i < L; ++i) xs[i * C] = T(0);
+        return;
+    }
+    if (first == 0 && last == L - 1) {
+        bool any = false;
+        for (int64_t i = 0; i < L; ++i) any = any || is_nan(xs[i * C]);
+        if (!any) return;
+    }
+    // impute the two ends with the first / last observation, then interpolate interior gaps between the
+    // surrounding observed (or imputed) points
+    if (first > 0) xs[0] = xs[first * C];
+    if (last < L - 1) xs[(L - 1) * C] = xs[last * C];
+    int64_t p = 0;
+    int64_t i = 1;
+    while (i < L) {
+        if (!is_nan(xs[i * C])) { p = i; ++i; continue; }
+        int64_t n = i + 1;
+        while (is_nan(xs[n * C])) ++n;  // terminates: xs[L-1] is observed
+        const T xp = xs[p * C], xn = xs[n * C], tp = t[p], tn = t[n];
+        for (int64_t j = i; j < n; ++j) {
+            T ratio = (t[j] - tp) / (tn - tp);
+            xs[j * C] = xp + ratio * (xn - xp);
+        }
+        p = n;
+        i = n + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// linear derivs — LinearInterpolation.__init__, torchcde/interpolation_linear.py:198
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void linear_derivs_kernel(const T* __restrict__ coeffs, const T* __restrict__ t, T* __restrict__ derivs,
+                                     int64_t n_series, int64_t K, int64_t C) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = n_series * (K - 1) * C;
+    if (tid >= total) return;
+    int64_t c = tid % C;
+    int64_t i = (tid / C) % (K - 1);
+    int64_t s = tid / (C * (K - 1));
+    const T* cs = coeffs + s * K * C;
+    derivs[tid] = (cs[(i + 1) * C + c] - cs[i * C + c]) / (t[i + 1] - t[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// evaluate / derivative — interpolation_linear.py:212-234, interpolation_cubic.py:315-336
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void path_eval_kernel(int kind, const T* __restrict__ coeffs, const T* __restrict__ derivs,
+                                 const T* __restrict__ knots, int64_t n_series, int64_t K, int64_t C,
+                                 const T* __restrict__ tq, int64_t n_t, int deriv, T* __restrict__ out,
+                                 int64_t* __restrict__ index_out) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = n_series * n_t * C;
+    if (tid >= total) return;
+    int64_t c = tid % C;
+    int64_t q = (tid / C) % n_t;
+    int64_t s = tid / (C * n_t);
+    const T t = tq[q];
+    const int idx = knot_index<T>(knots, (int)K, t);
+    if (index_out && s == 0 && c == 0) index_out[q] = idx;
+    const T frac = t - knots[idx];
+    T r;
+    if (kind == NCDE_PATH_LINEAR) {
+        if (deriv) {
+            r = derivs[(s * (K - 1) + idx) * C + c];
+        } else {
+            const T lo = coeffs[(s * K + idx) * C + c];
+            const T hi = coeffs[(s * K + idx + 1) * C + c];
+            const T width = knots[idx + 1] - knots[idx];
+            r = lo + frac * (hi - lo) / width;
+        }
+    } else {
+        const T* row = coeffs + (s * (K - 1) + idx) * 4 * C;
+        const T a = row[c], b = row[C + c], two_c = row[2 * C + c], three_d = row[3 * C + c];
+        if (deriv) {
+            T inner = two_c + three_d * frac;
+            r = b + inner * frac;
+        } else {
+            T inner = T(0.5) * two_c + three_d * frac / T(3);
+            inner = b + inner * frac;
+            r = a + inner * frac;
+        }
+    }
+    out[tid] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// natural cubic spline coefficients — interpolation_cubic.py:7-190, misc.py:13-67 (Thomas algorithm)
+// One thread per scalar series; scratch arrays are laid out [L][n_threads] so every sweep step is coalesced.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cubic_coeffs_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out,
+                                    int64_t n_series, int64_t L, int64_t C, int version, T* __restrict__ s_x,
+                                    T* __restrict__ s_d, T* __restrict__ s_r, int32_t* __restrict__ s_i) {
+    const int64_t N = n_series * C;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= N) return;
+    int64_t s = tid / C, c = tid % C;
+    const T* xs = x + s * L * C + c;
+    T* os = out + s * (L - 1) * 4 * C + c;
+#define SX(i) s_x[(int64_t)(i) * N + tid]
+#define SD(i) s_d[(int64_t)(i) * N + tid]
+#define SR(i) s_r[(int64_t)(i) * N + tid]
+#define SI(i) s_i[(int64_t)(i) * N + tid]
+    // 1. observed points after end imputation (version 0: ends only; version 1: fill outward from first/last)
+    int64_t first = -1, last = -1;
+    for (int64_t i = 0; i < L; ++i) {
+        if (!is_nan(xs[i * C])) { if (first < 0) first = i; last = i; }
+    }
+    if (first < 0) {
+        for (int64_t i = 0; i < L - 1; ++i) {
+            os[i * 4 * C] = T(0); os[i * 4 * C + C] = T(0); os[i * 4 * C + 2 * C] = T(0); os[i * 4 * C + 3 * C] = T(0);
+        }
+        return;
+    }
+    const T x_first = xs[first * C], x_last = xs[last * C];
+    int m = 0;
+    for (int64_t i = 0; i < L; ++i) {
+        T v = xs[i * C];
+        bool have = !is_nan(v);
+        if (!have) {
+            if (version == 0) {
+                if (i == 0) { v = x_first; have = true; }
+                else if (i == L - 1) { v = x_last; have = true; }
+            } else {
+                if (i < first) { v = x_first; have = true; }
+                else if (i > last) { v = x_last; have = true; }
+            }
+        }
+        if (have) { SX(m) = v; SI(m) = (int32_t)i; ++m; }
+    }
+    // 2. knot derivatives kd (stored back into s_r) on the observed grid
+    if (m > 2) {
+        // forward sweep
+        T hinv_prev = T(0), dxs_prev = T(0);
+        T d_prev = T(0), r_prev = T(0);
+        for (int i = 0; i < m; ++i) {
+            T hinv = T(0), dxs = T(0);
+            if (i < m - 1) {
+                hinv = T(1) / (t[SI(i + 1)] - t[SI(i)]);
+                T three_dx = T(3) * (SX(i + 1) - SX(i));
+                dxs = three_dx * (hinv * hinv);
+            }
+            T diag = (i == 0) ? hinv : (hinv + hinv_prev);
+            diag = diag * T(2);
+            T rhs = (i == 0) ? dxs : (dxs + dxs_prev);
+            T d, r;
+            if (i == 0) { d = diag; r = rhs; }
+            else {
+                T w = hinv_prev / d_prev;       // lower[i-1] / d[i-1]
+                d = diag - w * hinv_prev;        // diag[i] - w * upper[i-1]
+                r = rhs - w * r_prev;
+            }
+            SD(i) = d; SR(i) = r;
+            d_prev = d; r_prev = r; hinv_prev = hinv; dxs_prev = dxs;
+        }
+        // back substitution (kd overwrites r)
+        T nxt = SR(m - 1) / SD(m - 1);
+        SR(m - 1) = nxt;
+        for (int i = m - 2; i >= 0; --i) {
+            T upper = T(1) / (t[SI(i + 1)] - t[SI(i)]);
+            nxt = (SR(i) - upper * nxt) / SD(i);
+            SR(i) = nxt;
+        }
+    }
+    // 3. every original interval takes the polynomial of the observed piece it lies in, re-centred at its own
+    //    left end (offset = observed-left-time - own time)
+    int j = 0;  // current observed piece [SI(j), SI(j+1)]
+    for (int64_t i = 0; i < L - 1; ++i) {
+        while (j < m - 2 && (int64_t)SI(j + 1) <= i) ++j;
+        const T tl = t[SI(j)], tr = t[SI(j + 1)];
+        const T xl = SX(j), xr = SX(j + 1);
+        T pa, pb, pc, pd;
+        if (m == 2) {
+            pa = xl; pb = (xr - xl) / (tr - tl); pc = T(0); pd = T(0);
+        } else {
+            const T hinv = T(1) / (tr - tl);
+            const T hinv2 = hinv * hinv;
+            const T six_dx = T(2) * (T(3) * (xr - xl));
+            const T kl = SR(j), kr = SR(j + 1);
+            pa = xl; pb = kl;
+            pc = (six_dx * hinv - T(4) * kl - T(2) * kr) * hinv;
+            pd = (-six_dx * hinv + T(3) * (kl + kr)) * hinv2;
+        }
+        const T off = tl - t[i];
+        const T inner = (T(0.5) * pc - pd * off / T(3)) * off;
+        os[i * 4 * C] = pa + (inner - pb) * off;
+        os[i * 4 * C + C] = pb + (pd * off - pc) * off;
+        os[i * 4 * C + 2 * C] = pc - T(2) * pd * off;
+        os[i * 4 * C + 3 * C] = pd;
+    }
+#undef SX
+#undef SD
+#undef SR
+#undef SI
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)ceil_div(n, block); }
+
+}  // namespace ncde
+
+using namespace ncde;
+
+#define DISPATCH_DTYPE(dtype, ...)                                                    \
+    if ((dtype) == NCDE_F32) { typedef float T; __VA_ARGS__; }                        \
+    else if ((dtype) == NCDE_F64) { typedef double T; __VA_ARGS__; }                  \
+    else { set_error("unsupported dtype %d", (int)(dtype)); return NCDE_ERR_INVALID; }
+
+extern "C" int ncde_forward_fill(int dtype, const void* x, void* out, int64_t n_series, int64_t L, int64_t C,
+                                 void* stream) {
+    NCDE_REQUIRE(x && out && n_series >= 0 && L >= 1 && C >= 1, NCDE_ERR_INVALID, "forward_fill: bad arguments");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (forward_fill_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(
+                              (const T*)x, (T*)out, n_series, L, C)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_rectilinear_prepare(int dtype, const void* x, void* out, int64_t n_series, int64_t L,
+                                        int64_t C, int time_index, int32_t* flags, void* stream) {
+    NCDE_REQUIRE(x && out && n_series >= 0 && L >= 1 && C >= 1, NCDE_ERR_INVALID, "rectilinear: bad arguments");
+    NCDE_REQUIRE(time_index >= 0 && time_index < C, NCDE_ERR_INVALID, "Time index must be in [0, %lld], was given %d.",
+                 (long long)C - 1, time_index);
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (rectilinear_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(
+                              (const T*)x, (T*)out, n_series, L, C, time_index, flags)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_linear_fill_missing(int dtype, void* x, const void* t, int64_t n_series, int64_t L, int64_t C,
+                                        void* stream) {
+    NCDE_REQUIRE(x && t && n_series >= 0 && L >= 2 && C >= 1, NCDE_ERR_INVALID, "linear_fill_missing: bad arguments");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (linear_fill_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(
+                              (T*)x, (const T*)t, n_series, L, C)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_linear_derivs(int dtype, const void* coeffs, const void* t, void* derivs, int64_t n_series,
+                                  int64_t K, int64_t C, void* stream) {
+    NCDE_REQUIRE(coeffs && t && derivs && K >= 2 && C >= 1, NCDE_ERR_INVALID, "linear_derivs: bad arguments");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (linear_derivs_kernel<T><<<grid_for(n_series * (K - 1) * C, 256), 256, 0, st>>>(
+                              (const T*)coeffs, (const T*)t, (T*)derivs, n_series, K, C)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, const void* knots,
+                              int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv,
+                              void* out, int64_t* index_out, void* stream) {
+    NCDE_REQUIRE(coeffs && knots && tq && out && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval: bad arguments");
+    NCDE_REQUIRE(kind == NCDE_PATH_LINEAR || kind == NCDE_PATH_CUBIC, NCDE_ERR_INVALID, "path_eval: bad kind");
+    NCDE_REQUIRE(!(kind == NCDE_PATH_LINEAR && deriv && !derivs), NCDE_ERR_INVALID,
+                 "path_eval: linear derivative needs derivs");
+    if (n_series == 0 || n_t == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (path_eval_kernel<T><<<grid_for(n_series * n_t * C, 256), 256, 0, st>>>(
+                              kind, (const T*)coeffs, (const T*)derivs, (const T*)knots, n_series, K, C,
+                              (const T*)tq, n_t, deriv, (T*)out, index_out)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t L, int64_t C) {
+    size_t el = dtype == NCDE_F64 ? 8 : 4;
+    size_t n = (size_t)n_series * (size_t)C * (size_t)L;
+    return 3 * n * el + n * sizeof(int32_t) + 1024;
+}
+
+extern "C" int ncde_natural_cubic_coeffs(int dtype, const void* x, const void* t, void* out, int64_t n_series,
+                                         int64_t L, int64_t C, int version, void* scratch, void* stream) {
+    NCDE_REQUIRE(x && t && out && scratch, NCDE_ERR_INVALID, "natural_cubic_coeffs: null pointer");
+    NCDE_REQUIRE(L >= 2 && C >= 1 && (version == 0 || version == 1), NCDE_ERR_INVALID,
+                 "Must have a time dimension of size at least 2.");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n = (size_t)n_series * (size_t)C * (size_t)L;
+    DISPATCH_DTYPE(dtype, {
+        T* sx = (T*)scratch;
+        T* sd = sx + n;
+        T* sr = sd + n;
+        int32_t* si = (int32_t*)(sr + n);
+        cubic_coeffs_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>((const T*)x, (const T*)t, (T*)out,
+                                                                             n_series, L, C, version, sx, sd, sr, si);
+    });
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}

@@ -1,0 +1,834 @@
+// Device kernels of the fixed-grid CDE solve (fp32 arithmetic).  See DESIGN.md §3 for the decomposition.
+//
+// Internal state layout is FEATURE-MAJOR: y, k_i, stage inputs, activations and dX/dt are all stored [feature][Bp]
+// with the batch index contiguous (Bp = B rounded up to 64), so that
+//   * batch-split kernels ("hidden") read/write R consecutive rows of every feature as one segment, and
+//   * weight-stationary kernels ("field") stream 64-row chunks of every feature with 16-byte loads.
+#pragma once
+#include "common.cuh"
+
+namespace ncde {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 64;   // batch rows per field-kernel chunk
+constexpr int kGnStride = 68;  // padded row of the n-major G tile (bank-conflict-free float4 stores)
+
+// ---------------------------------------------------------------------------------------------------------------
+// argument blocks (passed by value as __grid_constant__)
+// ---------------------------------------------------------------------------------------------------------------
+struct PathArgs {
+    int kind;
+    int K;
+    const float* knots;
+    const float* coeffs;
+    const float* derivs;
+    float t;  // stage time, already cast to fp32 (torchdiffeq/_impl/misc.py:181)
+};
+
+struct HiddenFwdArgs {
+    int B, Bp, H, C, Cp, R, F, Dmax;
+    int D[NCDE_MAX_LAYERS + 1];   // D[l] = input width of layer l (D[0] = H, D[F] = input of the final layer)
+    int ldw[NCDE_MAX_LAYERS];     // leading dimension (padded out width) of WT[l]
+    int act[NCDE_MAX_LAYERS];
+    const float* WT[NCDE_MAX_LAYERS];  // [D[l]][ldw[l]]  k-major
+    const float* bp[NCDE_MAX_LAYERS];  // [ldw[l]]
+    // stage input: see combine_stage_input()
+    int combine;
+    float dt;
+    float coef[NCDE_MAX_STAGES];
+    const float* yT;
+    const float* kT[NCDE_MAX_STAGES];
+    float* actT[NCDE_MAX_LAYERS + 1];  // actT[l] = [D[l] (padded to 4)][Bp], l = 0..F, for THIS stage
+    float* dXT;                        // [Cp][Bp]
+    PathArgs path;
+};
+
+struct FieldArgs {
+    int B, Bp, H, Cp, DF, DFP, S, Hg, n_hg, Np, Bt;
+    const float* W3T;   // [DF][Np]    k-major, n = h*Cp + c
+    const float* W3R;   // [Np][DFP]   n-major (backward only)
+    const float* b3p;   // [Np]
+    const float* actT;  // [DF(pad4)][Bp] input of the final layer
+    const float* dXT;   // [Cp][Bp]
+    float* koutT;       // [H][Bp]            (forward)
+    const float* gkT;   // [H][Bp]            (backward) dL/dk for this stage
+    float* P;           // [n_hg][B][DFP]     (backward) per-h-group partial of dL/d(act)
+    float* dW3acc;      // [n_bt][Np][DFP]    (backward) accumulated across stages
+    float* db3acc;      // [n_bt][Np]
+    float* gdXT;        // [Cp][Bp] or null   (backward) dL/d(dX/dt) partials are not supported yet
+};
+
+struct AdvanceArgs {
+    int B, Bp, H, method;
+    float dt;
+    const float* yT;
+    float* ynewT;
+    const float* kT[NCDE_MAX_STAGES];
+    int n_emit;
+    float* emit_ptr[4];  // (B,H) row-major slices of z_out
+    int emit_mode[4];
+    float emit_slope[4];
+};
+
+struct HiddenBwdArgs {
+    int B, Bp, H, R, F, Dmax, DFP, n_hg;
+    int D[NCDE_MAX_LAYERS + 1];
+    int act[NCDE_MAX_LAYERS];
+    const float* W[NCDE_MAX_LAYERS];       // torch layout [D[l+1]][D[l]]
+    const float* P;                         // [n_hg][B][DFP]
+    const float* actT[NCDE_MAX_LAYERS + 1]; // saved activations of this stage
+    float* dpreT[NCDE_MAX_LAYERS];          // [D[l+1] pad4][Bp] scratch, consumed by hidden_wgrad
+    float* gyT;                             // [H][Bp]  += dzs
+    int n_k;                                // number of earlier-stage k gradients to update
+    float* gkT[NCDE_MAX_STAGES];
+    float kcoef[NCDE_MAX_STAGES];           // gk_j += kcoef[j] * dzs
+};
+
+struct WgradArgs {
+    int B, Bp, n_slots;
+    int tile_begin[NCDE_MAX_LAYERS + 1];
+    int Dout[NCDE_MAX_LAYERS], Din[NCDE_MAX_LAYERS];
+    int n_lay[NCDE_MAX_LAYERS];
+    int lay[NCDE_MAX_LAYERS][NCDE_MAX_LAYERS];
+    const float* dpreT[NCDE_MAX_LAYERS];  // per layer
+    const float* actT[NCDE_MAX_LAYERS];   // per layer: its input
+    float* gW[NCDE_MAX_LAYERS];           // per slot
+    float* gb[NCDE_MAX_LAYERS];           // per slot, nullable
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == NCDE_ACT_RELU) return v > 0.f ? v : 0.f;   // clamp_min(0): NaN stays NaN either way is irrelevant here
+    if (act == NCDE_ACT_TANH) return tanhf(v);
+    return v;
+}
+__device__ __forceinline__ float act_grad_from_output(float out, int act) {
+    if (act == NCDE_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+    if (act == NCDE_ACT_TANH) return 1.f - out * out;
+    return 1.f;
+}
+
+enum { COMBINE_Y = 0, COMBINE_RK4_S2 = 1, COMBINE_RK4_S3 = 2, COMBINE_RK4_S4 = 3, COMBINE_LINEAR = 4 };
+
+// Stage input of the RK scheme with the reference's operation order and no FMA contraction
+// (torchdiffeq/_impl/rk_common.py:106-114; _one_third / _two_thirds are rounded to fp32 by the tensor multiply).
+__device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int64_t off) {
+    const float y = a.yT[off];
+    const float third = 0.3333333432674408f;  // float32(1/3)
+    switch (a.combine) {
+        case COMBINE_Y: return y;
+        case COMBINE_RK4_S2:  // y0 + dt * k1 * (1/3)
+            return __fadd_rn(y, __fmul_rn(__fmul_rn(a.dt, a.kT[0][off]), third));
+        case COMBINE_RK4_S3:  // y0 + dt * (k2 - k1 * (1/3))
+            return __fadd_rn(y, __fmul_rn(a.dt, __fsub_rn(a.kT[1][off], __fmul_rn(a.kT[0][off], third))));
+        case COMBINE_RK4_S4:  // y0 + dt * (k1 - k2 + k3)
+            return __fadd_rn(y, __fmul_rn(a.dt, __fadd_rn(__fsub_rn(a.kT[0][off], a.kT[1][off]), a.kT[2][off])));
+        default: {            // y0 + sum_j k_j * coef_j
+            float acc = 0.f;
+            for (int j = 0; j < NCDE_MAX_STAGES; ++j)
+                if (a.coef[j] != 0.f) acc = fmaf(a.kT[j][off], a.coef[j], acc);
+            return y + acc;
+        }
+    }
+}
+
+// dX/dt for one (row, channel) at the stage time — LinearInterpolation.derivative / NaturalCubicSpline.derivative
+// (torchcde/interpolation_linear.py:231-234, interpolation_cubic.py:331-336)
+__device__ __forceinline__ float path_derivative(const PathArgs& p, int idx, float frac, int64_t b, int c, int C) {
+    if (p.kind == NCDE_PATH_LINEAR) {
+        if (p.derivs) return p.derivs[((int64_t)b * (p.K - 1) + idx) * C + c];
+        const float* cs = p.coeffs + (int64_t)b * p.K * C;
+        return __fdiv_rn(__fsub_rn(cs[(int64_t)(idx + 1) * C + c], cs[(int64_t)idx * C + c]),
+                         __fsub_rn(p.knots[idx + 1], p.knots[idx]));
+    }
+    const float* row = p.coeffs + ((int64_t)b * (p.K - 1) + idx) * 4 * C;
+    const float bb = row[C + c], two_c = row[2 * C + c], three_d = row[3 * C + c];
+    const float inner = __fadd_rn(two_c, __fmul_rn(three_d, frac));
+    return __fadd_rn(bb, __fmul_rn(inner, frac));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------------------------
+// hidden layer: WT[k*ld + o] = W[o*Din + k]; bp[o] = bias[o] (0 when absent / padded)
+__global__ void pack_hidden_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ WT,
+                                   float* __restrict__ bp, int Dout, int Din, int ld) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < Din * ld) {
+        int k = idx / ld, o = idx % ld;
+        WT[idx] = (o < Dout) ? W[(int64_t)o * Din + k] : 0.f;
+    }
+    if (idx < ld) bp[idx] = (bias && idx < Dout) ? bias[idx] : 0.f;
+}
+
+// final layer: n = h*Cp + c (c padded to Cp, h padded to n_hg*Hg); W3T[k*Np + n], W3R[n*DFP + k], b3p[n]
+__global__ void pack_final_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ W3T,
+                                  float* __restrict__ W3R, float* __restrict__ b3p, int H, int C, int Cp, int DF,
+                                  int DFP, int Np) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)Np * DFP;
+    if (idx < total) {
+        int n = (int)(idx / DFP), k = (int)(idx % DFP);
+        int h = n / Cp, c = n % Cp;
+        float v = (h < H && c < C && k < DF) ? W[((int64_t)h * C + c) * DF + k] : 0.f;
+        if (W3R) W3R[idx] = v;
+        if (k < DF) W3T[(int64_t)k * Np + n] = v;
+    }
+    if (idx < Np) {
+        int h = (int)idx / Cp, c = (int)idx % Cp;
+        b3p[idx] = (bias && h < H && c < C) ? bias[(int64_t)h * C + c] : 0.f;
+    }
+}
+
+// (B,H) row-major <-> [H][Bp] feature-major
+__global__ void to_feature_major_kernel(const float* __restrict__ src, float* __restrict__ dstT, int B, int Bp, int H) {
+    __shared__ float tile[32][33];
+    int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int b = b0 + i, h = h0 + threadIdx.x;
+        tile[i][threadIdx.x] = (b < B && h < H) ? src[(int64_t)b * H + h] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int h = h0 + i, b = b0 + threadIdx.x;
+        if (h < H && b < Bp) dstT[(int64_t)h * Bp + b] = tile[threadIdx.x][i];
+    }
+}
+
+// dst (B,H) row-major  (=|+=)  scale * srcT [H][Bp]   (+ add (B,H) if given)
+__global__ void from_feature_major_kernel(const float* __restrict__ srcT, const float* __restrict__ add,
+                                          float* __restrict__ dst, int B, int Bp, int H) {
+    __shared__ float tile[32][33];
+    int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int h = h0 + i, b = b0 + threadIdx.x;
+        tile[i][threadIdx.x] = (h < H && b < B) ? srcT[(int64_t)h * Bp + b] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int b = b0 + i, h = h0 + threadIdx.x;
+        if (b < B && h < H) {
+            float v = tile[threadIdx.x][i];
+            if (add) v += add[(int64_t)b * H + h];
+            dst[(int64_t)b * H + h] = v;
+        }
+    }
+}
+
+// gyT[h][b] += scale * g[b][h]     (output-gradient injection in the backward sweep)
+__global__ void add_out_grad_kernel(float* __restrict__ gyT, const float* __restrict__ g, float scale, int B, int Bp,
+                                    int H) {
+    __shared__ float tile[32][33];
+    int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int b = b0 + i, h = h0 + threadIdx.x;
+        tile[i][threadIdx.x] = (b < B && h < H) ? g[(int64_t)b * H + h] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int h = h0 + i, b = b0 + threadIdx.x;
+        if (h < H && b < B) gyT[(int64_t)h * Bp + b] += scale * tile[threadIdx.x][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hidden_fwd: batch-split.  One CTA owns R rows: forms the RK stage input, evaluates dX/dt at the stage time
+// (knot lookup + gather / Horner) and runs the hidden Linear+activation layers.  Everything is written
+// feature-major for the field kernel and for the backward pass.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_constant__ HiddenFwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int R = a.R;
+    const int64_t b0 = (int64_t)blockIdx.x * R;
+    float* buf0 = sm;
+    float* buf1 = sm + (size_t)a.Dmax * R;
+
+    // 1. stage input  zs[h][r]
+    for (int idx = tid; idx < a.H * R; idx += kThreads) {
+        const int h = idx / R, r = idx % R;
+        const int64_t b = b0 + r;
+        float v = 0.f;
+        if (b < a.B) {
+            const int64_t off = (int64_t)h * a.Bp + b;
+            v = combine_stage_input(a, off);
+            a.actT[0][off] = v;
+        }
+        buf0[h * R + r] = v;
+    }
+    // 2. dX/dt at the stage time -> dXT[c][b] (zero in the padded channels)
+    {
+        const int idxk = knot_index<float>(a.path.knots, a.path.K, a.path.t);
+        const float frac = __fsub_rn(a.path.t, a.path.knots[idxk]);
+        float* tmp = buf1;  // [Cp][R]
+        for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
+            const int r = idx / a.Cp, c = idx % a.Cp;
+            const int64_t b = b0 + r;
+            float v = 0.f;
+            if (b < a.B && c < a.C) v = path_derivative(a.path, idxk, frac, b, c, a.C);
+            tmp[c * R + r] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
+            const int c = idx / R, r = idx % R;
+            const int64_t b = b0 + r;
+            if (b < a.B) a.dXT[(int64_t)c * a.Bp + b] = tmp[c * R + r];
+        }
+    }
+    __syncthreads();
+    // 3. hidden layers
+    const int RQ = R / 4;
+    for (int l = 0; l < a.F; ++l) {
+        const float* in = (l & 1) ? buf1 : buf0;
+        float* out = (l & 1) ? buf0 : buf1;
+        const int Din = a.D[l], Dout = a.D[l + 1], ld = a.ldw[l];
+        const float* __restrict__ WT = a.WT[l];
+        const float* __restrict__ bp = a.bp[l];
+        for (int item = tid; item < Dout * RQ; item += kThreads) {
+            const int o = item % Dout, q = item / Dout;
+            const float bias = bp[o];
+            float4 acc = make_float4(bias, bias, bias, bias);
+#pragma unroll 8
+            for (int k = 0; k < Din; ++k) {
+                const float w = __ldg(WT + (size_t)k * ld + o);
+                const float4 x = *reinterpret_cast<const float4*>(in + k * R + q * 4);
+                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
+                acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+            }
+            const int act = a.act[l];
+            acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
+            acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+            *reinterpret_cast<float4*>(out + o * R + q * 4) = acc;
+        }
+        __syncthreads();
+        float* __restrict__ g = a.actT[l + 1];
+        for (int idx = tid; idx < Dout * R; idx += kThreads) {
+            const int o = idx / R, r = idx % R;
+            const int64_t b = b0 + r;
+            if (b < a.B) g[(int64_t)o * a.Bp + b] = out[o * R + r];
+        }
+        // `out` is read-only until the next layer finishes writing the other buffer: no extra barrier needed
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// field_fwd: weight-stationary.  CTA (g, bt) keeps the W3 slice of h-group g in shared memory and streams the
+// rows of batch tile bt through it in 64-row chunks:
+//     k[b, h] = sum_c tanh( act[b,:] . W3[(h,c),:] + b3[(h,c)] ) * dX[b, c]
+// The (B, H*C) matrix of the reference (src/ncde/vector_fields/base.py:99-104, torchcde/solver.py:132) is never
+// materialised.  Thread (nt, mt) owns 4 consecutive n (= 4 channels of one h) x TM rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_constant__ FieldArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int S = a.S, DF = a.DF;
+    const int NT = S / 4;
+    constexpr int MT = kChunk / TM;
+    const int nt = tid % NT, mt = tid / NT;
+    const bool active = mt < MT;
+    const int g = blockIdx.x, bt = blockIdx.y;
+    float* Ws = sm;                       // [DF][S]
+    float* As = Ws + (size_t)DF * S;      // [DF][64]
+    float* red = As + (size_t)DF * kChunk;  // [NT][64]
+
+    for (int idx = tid; idx < DF * NT; idx += kThreads) {
+        const int k = idx / NT, j = idx % NT;
+        reinterpret_cast<float4*>(Ws)[idx] =
+            __ldg(reinterpret_cast<const float4*>(a.W3T + (size_t)k * a.Np + (size_t)g * S) + j);
+    }
+    float bias[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias[j] = active ? a.b3p[(size_t)g * S + nt * 4 + j] : 0.f;
+    const int c0 = (nt * 4) % a.Cp;
+
+    const int64_t row_begin = (int64_t)bt * a.Bt;
+    const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
+    for (int64_t b0 = row_begin; b0 < row_end; b0 += kChunk) {
+        for (int idx = tid; idx < DF * (kChunk / 4); idx += kThreads) {
+            const int k = idx / (kChunk / 4), j = idx % (kChunk / 4);
+            reinterpret_cast<float4*>(As)[idx] =
+                __ldg(reinterpret_cast<const float4*>(a.actT + (size_t)k * a.Bp + b0) + j);
+        }
+        __syncthreads();
+        if (active) {
+            float acc[TM][4];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < DF; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + k * S + nt * 4);
+                float av[TM];
+#pragma unroll
+                for (int i4 = 0; i4 < TM / 4; ++i4) {
+                    const float4 x = *reinterpret_cast<const float4*>(As + k * kChunk + mt * TM + i4 * 4);
+                    av[i4 * 4 + 0] = x.x; av[i4 * 4 + 1] = x.y; av[i4 * 4 + 2] = x.z; av[i4 * 4 + 3] = x.w;
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    acc[i][0] = fmaf(av[i], w.x, acc[i][0]); acc[i][1] = fmaf(av[i], w.y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], w.z, acc[i][2]); acc[i][3] = fmaf(av[i], w.w, acc[i][3]);
+                }
+            }
+            // epilogue: tanh, multiply by dX/dt, reduce this thread's 4 channels
+            float part[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) part[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* dxrow = a.dXT + (size_t)(c0 + j) * a.Bp + b0 + mt * TM;
+#pragma unroll
+                for (int i4 = 0; i4 < TM / 4; ++i4) {
+                    const float4 dx = __ldg(reinterpret_cast<const float4*>(dxrow) + i4);
+                    part[i4 * 4 + 0] = fmaf(tanhf(acc[i4 * 4 + 0][j] + bias[j]), dx.x, part[i4 * 4 + 0]);
+                    part[i4 * 4 + 1] = fmaf(tanhf(acc[i4 * 4 + 1][j] + bias[j]), dx.y, part[i4 * 4 + 1]);
+                    part[i4 * 4 + 2] = fmaf(tanhf(acc[i4 * 4 + 2][j] + bias[j]), dx.z, part[i4 * 4 + 2]);
+                    part[i4 * 4 + 3] = fmaf(tanhf(acc[i4 * 4 + 3][j] + bias[j]), dx.w, part[i4 * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int i4 = 0; i4 < TM / 4; ++i4)
+                *reinterpret_cast<float4*>(red + nt * kChunk + mt * TM + i4 * 4) =
+                    make_float4(part[i4 * 4], part[i4 * 4 + 1], part[i4 * 4 + 2], part[i4 * 4 + 3]);
+        }
+        __syncthreads();
+        const int Cq = a.Cp / 4;
+        for (int idx = tid; idx < a.Hg * kChunk; idx += kThreads) {
+            const int hl = idx / kChunk, m = idx % kChunk;
+            float s = 0.f;
+            for (int q = 0; q < Cq; ++q) s += red[(hl * Cq + q) * kChunk + m];
+            const int64_t b = b0 + m;
+            const int h = g * a.Hg + hl;
+            if (b < a.B && h < a.H) a.koutT[(size_t)h * a.Bp + b] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// advance: y_{n+1} from the stage derivatives (fixed_grid.py:6-29, rk_common.py:114) + output emission
+// (solvers.py:106-117,166-172).  Elementwise on feature-major state; emits (B,H) row-major slices of z_out.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void advance_kernel(const __grid_constant__ AdvanceArgs a) {
+    __shared__ float t_old[32][33];
+    __shared__ float t_new[32][33];
+    const int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int h = h0 + i, b = b0 + threadIdx.x;
+        float y = 0.f, yn = 0.f;
+        if (h < a.H && b < a.B) {
+            const size_t off = (size_t)h * a.Bp + b;
+            y = a.yT[off];
+            if (a.method == NCDE_RK4_38) {
+                // (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+                float s = __fadd_rn(a.kT[0][off], __fmul_rn(3.f, __fadd_rn(a.kT[1][off], a.kT[2][off])));
+                s = __fadd_rn(s, a.kT[3][off]);
+                yn = __fadd_rn(y, __fmul_rn(__fmul_rn(s, a.dt), 0.125f));
+            } else {  // Euler: y0 + dt * f0
+                yn = __fadd_rn(y, __fmul_rn(a.dt, a.kT[0][off]));
+            }
+            a.ynewT[off] = yn;
+        }
+        t_old[i][threadIdx.x] = y;
+        t_new[i][threadIdx.x] = yn;
+    }
+    if (a.n_emit == 0) return;
+    __syncthreads();
+    for (int e = 0; e < a.n_emit; ++e) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int b = b0 + i, h = h0 + threadIdx.x;
+            if (b < a.B && h < a.H) {
+                const float y = t_old[threadIdx.x][i], yn = t_new[threadIdx.x][i];
+                float v;
+                if (a.emit_mode[e] == 0) v = y;
+                else if (a.emit_mode[e] == 1) v = yn;
+                else v = __fadd_rn(y, __fmul_rn(a.emit_slope[e], __fsub_rn(yn, y)));  // _linear_interp
+                a.emit_ptr[e][(size_t)b * a.H + h] = v;
+            }
+        }
+    }
+}
+
+// backward: gk_i = c_i * dt * gy1   (derivative of the RK increment w.r.t. each stage derivative)
+__global__ void rk_bwd_begin_kernel(const float* __restrict__ gyT, float* gk0, float* gk1, float* gk2, float* gk3,
+                                    int method, float dt, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = gyT[i];
+    if (method == NCDE_RK4_38) {
+        const float c1 = dt * 0.125f, c3 = 3.f * (dt * 0.125f);
+        gk0[i] = g * c1; gk1[i] = g * c3; gk2[i] = g * c3; gk3[i] = g * c1;
+    } else {
+        gk0[i] = g * dt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// field_bwd: weight-stationary backward of the final layer + contraction, for one RK stage.
+//   pre = act . W3^T + b3 ; T = tanh(pre) ; G[b,(h,c)] = gk[b,h] * dX[b,c] * (1 - T^2)
+//   dW3[(h,c),:] += sum_b G * act[b,:]      (register accumulators across all chunks, then += into dW3acc)
+//   db3[(h,c)]   += sum_b G
+//   P_g[b,:]      = sum_{(h,c) in group} G * W3[(h,c),:]   (partial of dL/d act; summed over groups by hidden_bwd)
+// ---------------------------------------------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ FieldArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int S = a.S, DF = a.DF, DFP = a.DFP;
+    const int NT = S / 4;
+    constexpr int MT = kChunk / TM;
+    const int nt = tid % NT, mt = tid / NT;
+    const bool gemm_active = mt < MT;
+    const int g = blockIdx.x, bt = blockIdx.y;
+    const int ARS = DFP + 4;  // row stride of the row-major activation tile
+
+    float* Ws = sm;                              // [DF][S]        k-major slice
+    float* Wr = Ws + (size_t)DF * S;             // [S][DFP]       n-major slice
+    float* As = Wr + (size_t)S * DFP;            // [DF][64]       k-major chunk
+    float* Ar = As + (size_t)DF * kChunk;        // [64][DFP+4]    row-major chunk
+    float* Gn = Ar + (size_t)kChunk * ARS;       // [S][68]        n-major G
+    float* Gm = Gn + (size_t)S * kGnStride;      // [64][S]        m-major G
+    float* gks = Gm + (size_t)kChunk * S;        // [Hg][64]
+
+    for (int idx = tid; idx < DF * NT; idx += kThreads) {
+        const int k = idx / NT, j = idx % NT;
+        reinterpret_cast<float4*>(Ws)[idx] =
+            __ldg(reinterpret_cast<const float4*>(a.W3T + (size_t)k * a.Np + (size_t)g * S) + j);
+    }
+    for (int idx = tid; idx < S * (DFP / 4); idx += kThreads)
+        reinterpret_cast<float4*>(Wr)[idx] =
+            __ldg(reinterpret_cast<const float4*>(a.W3R + (size_t)g * S * DFP) + idx);
+    // zero the K padding of Ar once (columns DF..DFP-1 never change afterwards)
+    for (int idx = tid; idx < kChunk * ARS; idx += kThreads) Ar[idx] = 0.f;
+
+    float bias[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias[j] = gemm_active ? a.b3p[(size_t)g * S + nt * 4 + j] : 0.f;
+    const int c0 = (nt * 4) % a.Cp;
+    const int hl_of_nt = (nt * 4) / a.Cp;
+
+    // wgrad mapping: thread (nt, kw) owns 4 n x 16 k, k = q*(DFP/4) + kw*4 + j
+    const int KW = DFP / 16;
+    const int kw = tid / NT;
+    const bool wg_active = kw < KW;
+    float accw[4][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) accw[j][q] = 0.f;
+    float accb[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // dgrad mapping: thread (kd, md) owns 4 m x 8 k, k = {kd*4+j} U {DFP/2 + kd*4 + j}
+    const int KD = DFP / 8;
+    const int kd = tid % KD, md = tid / KD;
+    const bool dg_active = md < kChunk / 4;
+
+    const int64_t row_begin = (int64_t)bt * a.Bt;
+    const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
+    for (int64_t b0 = row_begin; b0 < row_end; b0 += kChunk) {
+        for (int idx = tid; idx < DF * (kChunk / 4); idx += kThreads) {
+            const int k = idx / (kChunk / 4), j = idx % (kChunk / 4);
+            reinterpret_cast<float4*>(As)[idx] =
+                __ldg(reinterpret_cast<const float4*>(a.actT + (size_t)k * a.Bp + b0) + j);
+        }
+        for (int idx = tid; idx < a.Hg * kChunk; idx += kThreads) {
+            const int hl = idx / kChunk, m = idx % kChunk;
+            const int h = g * a.Hg + hl;
+            const int64_t b = b0 + m;
+            gks[idx] = (h < a.H && b < a.B) ? a.gkT[(size_t)h * a.Bp + b] : 0.f;
+        }
+        __syncthreads();
+        // row-major copy of the chunk for the weight-gradient product
+        for (int idx = tid; idx < DF * kChunk; idx += kThreads) {
+            const int k = idx / kChunk, m = idx % kChunk;
+            Ar[m * ARS + k] = As[idx];
+        }
+        if (gemm_active) {
+            float acc[TM][4];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < DF; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + k * S + nt * 4);
+                float av[TM];
+#pragma unroll
+                for (int i4 = 0; i4 < TM / 4; ++i4) {
+                    const float4 x = *reinterpret_cast<const float4*>(As + k * kChunk + mt * TM + i4 * 4);
+                    av[i4 * 4 + 0] = x.x; av[i4 * 4 + 1] = x.y; av[i4 * 4 + 2] = x.z; av[i4 * 4 + 3] = x.w;
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    acc[i][0] = fmaf(av[i], w.x, acc[i][0]); acc[i][1] = fmaf(av[i], w.y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], w.z, acc[i][2]); acc[i][3] = fmaf(av[i], w.w, acc[i][3]);
+                }
+            }
+            // G = gk * dX * (1 - tanh^2), zero outside the batch
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* dxrow = a.dXT + (size_t)(c0 + j) * a.Bp + b0 + mt * TM;
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const int m = mt * TM + i;
+                    const float t = tanhf(acc[i][j] + bias[j]);
+                    const float gk = gks[hl_of_nt * kChunk + m];
+                    float gv = gk * __ldg(dxrow + i) * (1.f - t * t);
+                    if (b0 + m >= a.B) gv = 0.f;
+                    acc[i][j] = gv;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i4 = 0; i4 < TM / 4; ++i4)
+                    *reinterpret_cast<float4*>(Gn + (nt * 4 + j) * kGnStride + mt * TM + i4 * 4) =
+                        make_float4(acc[i4 * 4][j], acc[i4 * 4 + 1][j], acc[i4 * 4 + 2][j], acc[i4 * 4 + 3][j]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+                *reinterpret_cast<float4*>(Gm + (mt * TM + i) * S + nt * 4) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        // weight gradient: accw[j][q*4+jj] += G[m][n0+j] * act[m][k]
+        if (wg_active) {
+            const int QS = DFP / 4;
+#pragma unroll 2
+            for (int m = 0; m < kChunk; ++m) {
+                const float4 gv = *reinterpret_cast<const float4*>(Gm + m * S + nt * 4);
+                const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
+                if (kw == 0) { accb[0] += gv.x; accb[1] += gv.y; accb[2] += gv.z; accb[3] += gv.w; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x = *reinterpret_cast<const float4*>(Ar + m * ARS + q * QS + kw * 4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        accw[j][q * 4 + 0] = fmaf(gj[j], x.x, accw[j][q * 4 + 0]);
+                        accw[j][q * 4 + 1] = fmaf(gj[j], x.y, accw[j][q * 4 + 1]);
+                        accw[j][q * 4 + 2] = fmaf(gj[j], x.z, accw[j][q * 4 + 2]);
+                        accw[j][q * 4 + 3] = fmaf(gj[j], x.w, accw[j][q * 4 + 3]);
+                    }
+                }
+            }
+        }
+        // input gradient partial: P[b][k] = sum_n G[n][m] * W3[n][k]
+        if (dg_active) {
+            float accp[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) accp[i][q] = 0.f;
+#pragma unroll 2
+            for (int n = 0; n < S; ++n) {
+                const float4 gv = *reinterpret_cast<const float4*>(Gn + n * kGnStride + md * 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wr + n * DFP + kd * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wr + n * DFP + DFP / 2 + kd * 4);
+                const float gi[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    accp[i][0] = fmaf(gi[i], w0.x, accp[i][0]); accp[i][1] = fmaf(gi[i], w0.y, accp[i][1]);
+                    accp[i][2] = fmaf(gi[i], w0.z, accp[i][2]); accp[i][3] = fmaf(gi[i], w0.w, accp[i][3]);
+                    accp[i][4] = fmaf(gi[i], w1.x, accp[i][4]); accp[i][5] = fmaf(gi[i], w1.y, accp[i][5]);
+                    accp[i][6] = fmaf(gi[i], w1.z, accp[i][6]); accp[i][7] = fmaf(gi[i], w1.w, accp[i][7]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t b = b0 + md * 4 + i;
+                if (b < a.B) {
+                    float* prow = a.P + ((size_t)g * a.B + b) * DFP;
+                    *reinterpret_cast<float4*>(prow + kd * 4) = make_float4(accp[i][0], accp[i][1], accp[i][2], accp[i][3]);
+                    *reinterpret_cast<float4*>(prow + DFP / 2 + kd * 4) =
+                        make_float4(accp[i][4], accp[i][5], accp[i][6], accp[i][7]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // accumulate this stage's weight gradient into the per-(bt) accumulator (exclusively owned by this CTA)
+    if (wg_active) {
+        const int QS = DFP / 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* wrow = a.dW3acc + ((size_t)bt * a.Np + (size_t)g * S + nt * 4 + j) * DFP;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4* p = reinterpret_cast<float4*>(wrow + q * QS + kw * 4);
+                float4 v = *p;
+                v.x += accw[j][q * 4 + 0]; v.y += accw[j][q * 4 + 1]; v.z += accw[j][q * 4 + 2]; v.w += accw[j][q * 4 + 3];
+                *p = v;
+            }
+        }
+        if (kw == 0) {
+            float4* p = reinterpret_cast<float4*>(a.db3acc + (size_t)bt * a.Np + (size_t)g * S + nt * 4);
+            float4 v = *p;
+            v.x += accb[0]; v.y += accb[1]; v.z += accb[2]; v.w += accb[3];
+            *p = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hidden_bwd: batch-split.  Sums the per-group partials, walks the hidden layers backwards, stores each layer's
+// pre-activation gradient feature-major for hidden_wgrad, and applies the RK adjoint update
+//     gy0 += dzs ;  gk_j += kcoef[j] * dzs  (j = earlier stages feeding this stage's input).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_constant__ HiddenBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int R = a.R;
+    const int RQ = R / 4;
+    const int64_t b0 = (int64_t)blockIdx.x * R;
+    float* buf0 = sm;
+    float* buf1 = sm + (size_t)a.Dmax * R;
+
+    // 1. dL/d(final-layer input)[k][r] = sum_g P[g][b][k]
+    {
+        const int DF = a.D[a.F];
+        for (int idx = tid; idx < R * DF; idx += kThreads) {
+            const int r = idx / DF, k = idx % DF;
+            const int64_t b = b0 + r;
+            float s = 0.f;
+            if (b < a.B) {
+                const float* p = a.P + (size_t)b * a.DFP + k;
+                const size_t gs = (size_t)a.B * a.DFP;
+#pragma unroll 8
+                for (int g = 0; g < a.n_hg; ++g) s += __ldg(p + (size_t)g * gs);
+            }
+            buf0[k * R + r] = s;
+        }
+    }
+    __syncthreads();
+    // 2. hidden layers, last to first.  cur = gradient w.r.t. the OUTPUT of layer l (post-activation)
+    float* cur = buf0;
+    float* nxt = buf1;
+    for (int l = a.F - 1; l >= 0; --l) {
+        const int Din = a.D[l], Dout = a.D[l + 1];
+        // dpre = cur * act'(out), in place in `cur`, and feature-major to global for the weight gradient
+        const float* __restrict__ outT = a.actT[l + 1];
+        float* __restrict__ dpreT = a.dpreT[l];
+        const int act = a.act[l];
+        for (int idx = tid; idx < Dout * R; idx += kThreads) {
+            const int o = idx / R, r = idx % R;
+            const int64_t b = b0 + r;
+            float v = 0.f;
+            if (b < a.B) {
+                v = cur[idx] * act_grad_from_output(outT[(size_t)o * a.Bp + b], act);
+                dpreT[(size_t)o * a.Bp + b] = v;
+            }
+            cur[idx] = v;
+        }
+        __syncthreads();
+        // d(in)[i][r] = sum_o dpre[o][r] * W[o][i]
+        const float* __restrict__ W = a.W[l];
+        for (int item = tid; item < Din * RQ; item += kThreads) {
+            const int i = item % Din, q = item / Din;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int o = 0; o < Dout; ++o) {
+                const float w = __ldg(W + (size_t)o * Din + i);
+                const float4 x = *reinterpret_cast<const float4*>(cur + o * R + q * 4);
+                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
+                acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(nxt + i * R + q * 4) = acc;
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    // 3. RK adjoint update with dzs = cur[h][r]
+    for (int idx = tid; idx < a.H * R; idx += kThreads) {
+        const int h = idx / R, r = idx % R;
+        const int64_t b = b0 + r;
+        if (b < a.B) {
+            const size_t off = (size_t)h * a.Bp + b;
+            const float d = cur[idx];
+            a.gyT[off] += d;
+            for (int j = 0; j < a.n_k; ++j)
+                if (a.kcoef[j] != 0.f) a.gkT[j][off] = fmaf(a.kcoef[j], d, a.gkT[j][off]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hidden_wgrad: weight-stationary.  CTA owns a 32x32 tile of one hidden weight matrix and reduces over the batch:
+//     gW[o][i] += sum_b dpre[o][b] * in[i][b] ;  gb[o] += sum_b dpre[o][b]
+// Layers that share a slot (the reference's repeated nn.Linear) are folded into the same tile, so the
+// accumulation into the shared gradient is race-free and ordered.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) hidden_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+    __shared__ float dS[32][kChunk + 1];
+    __shared__ float aS[32][kChunk + 1];
+    const int tid = threadIdx.x;
+    int slot = 0;
+    while (slot + 1 < a.n_slots && (int)blockIdx.x >= a.tile_begin[slot + 1]) ++slot;
+    const int tile = blockIdx.x - a.tile_begin[slot];
+    const int Dout = a.Dout[slot], Din = a.Din[slot];
+    const int tiles_i = (Din + 31) / 32;
+    const int o0 = (tile / tiles_i) * 32, i0 = (tile % tiles_i) * 32;
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float accb[2] = {0.f, 0.f};
+    for (int li = 0; li < a.n_lay[slot]; ++li) {
+        const int l = a.lay[slot][li];
+        const float* __restrict__ dT = a.dpreT[l];
+        const float* __restrict__ xT = a.actT[l];
+        for (int bc = 0; bc < a.B; bc += kChunk) {
+            for (int idx = tid; idx < 32 * kChunk; idx += kThreads) {
+                const int rr = idx / kChunk, bb = idx % kChunk;
+                const int b = bc + bb;
+                dS[rr][bb] = (o0 + rr < Dout && b < a.B) ? dT[(size_t)(o0 + rr) * a.Bp + b] : 0.f;
+                aS[rr][bb] = (i0 + rr < Din && b < a.B) ? xT[(size_t)(i0 + rr) * a.Bp + b] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int bb = 0; bb < kChunk; ++bb) {
+                const float d0 = dS[ty * 2][bb], d1 = dS[ty * 2 + 1][bb];
+                const float x0 = aS[tx * 2][bb], x1 = aS[tx * 2 + 1][bb];
+                acc[0][0] = fmaf(d0, x0, acc[0][0]); acc[0][1] = fmaf(d0, x1, acc[0][1]);
+                acc[1][0] = fmaf(d1, x0, acc[1][0]); acc[1][1] = fmaf(d1, x1, acc[1][1]);
+                accb[0] += d0; accb[1] += d1;
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int o = o0 + ty * 2 + u;
+        if (o >= Dout) continue;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = i0 + tx * 2 + v;
+            if (i < Din) a.gW[slot][(size_t)o * Din + i] += acc[u][v];
+        }
+        if (a.gb[slot] && i0 == 0 && tx == 0) a.gb[slot][o] += accb[u];
+    }
+}
+
+// final-layer gradient: gW[(h*C+c)*DF + k] += sum_bt dW3acc[bt][(h*Cp+c)*DFP + k]; same for the bias
+__global__ void unpack_final_grad_kernel(const float* __restrict__ dW3acc, const float* __restrict__ db3acc,
+                                         float* __restrict__ gW, float* __restrict__ gb, int H, int C, int Cp, int DF,
+                                         int DFP, int Np, int n_bt) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)H * C * DF;
+    if (idx < total) {
+        const int k = (int)(idx % DF);
+        const int hc = (int)(idx / DF);
+        const int h = hc / C, c = hc % C;
+        float s = 0.f;
+        for (int bt = 0; bt < n_bt; ++bt) s += dW3acc[((size_t)bt * Np + (size_t)h * Cp + c) * DFP + k];
+        gW[idx] += s;
+    }
+    if (gb && idx < (int64_t)H * C) {
+        const int h = (int)idx / C, c = (int)idx % C;
+        float s = 0.f;
+        for (int bt = 0; bt < n_bt; ++bt) s += db3acc[(size_t)bt * Np + (size_t)h * Cp + c];
+        gb[idx] += s;
+    }
+}
+
+}  // namespace ncde

@@ -1,0 +1,184 @@
+"""Lower a vector-field ``func`` (an nn.Module mapping z:(B,H) -> (B,H,C)) to the MLP descriptor the CUDA kernels run.
+
+The fused solve cannot call back into Python per stage, so ``func`` must be a chain of Linear layers with ReLU /
+tanh / identity activations ending in ``tanh`` and a ``view(-1, H, C)`` — which is what every vector field on the
+reference's hot path is (src/ncde/vector_fields/base.py:64-104 ``OriginalVectorField``,
+experiments/sim_bm_toy_example.py:10-30 ``CDEFunc``, modules/torchcde/example/example.py:20-52).  Anything else raises:
+there is no eager fallback.
+
+Recognition order:
+  1. ``func.ncde_mlp_spec()`` if the module provides it -> list of (weight, bias, activation) tuples;
+  2. the ``net_to_hh`` + ``tanh_output_layer`` structure of the reference's vector fields;
+  3. a torch.fx trace of ``func.forward(t, z)`` that is a straight Linear/activation chain.
+Layers that reuse the same nn.Linear object (the reference repeats one Linear for all middle layers, base.py:65-68)
+share a slot, so their weight gradient accumulates into one tensor.
+"""
+import torch
+import torch.fx
+
+from . import _capi
+
+_ACT = {"none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "tanh": _capi.ACT_TANH}
+
+
+class MlpSpec:
+    """layers: list of (weight, bias_or_None, activation_code); slot[i] identifies shared parameters."""
+
+    def __init__(self, layers):
+        if not 1 <= len(layers) <= _capi.MAX_LAYERS:
+            raise NotImplementedError("vector fields with {} Linear layers are not supported (max {})".format(
+                len(layers), _capi.MAX_LAYERS))
+        self.weights = [l[0] for l in layers]
+        self.biases = [l[1] for l in layers]
+        self.acts = [l[2] for l in layers]
+        seen = {}
+        self.slots = []
+        for w in self.weights:
+            self.slots.append(seen.setdefault(id(w), len(seen)))
+        for i in range(1, len(layers)):
+            if self.weights[i].shape[1] != self.weights[i - 1].shape[0]:
+                raise ValueError("vector field layer {} takes {} inputs but the previous layer produces {}".format(
+                    i, self.weights[i].shape[1], self.weights[i - 1].shape[0]))
+
+    @property
+    def unique_params(self):
+        """Parameters in first-use order without duplicates: [(tensor, kind, layer_index)]"""
+        out, seen = [], set()
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            if id(w) not in seen:
+                seen.add(id(w))
+                out.append((w, "W", i))
+                if b is not None:
+                    out.append((b, "b", i))
+        return out
+
+    def reference_forward(self, z, hidden, channels):
+        """The same map written with torch ops; used only to validate a lowering once, never on the solve path."""
+        for w, b, a in zip(self.weights, self.biases, self.acts):
+            z = torch.nn.functional.linear(z, w, b)
+            if a == _capi.ACT_RELU:
+                z = z.relu()
+            elif a == _capi.ACT_TANH:
+                z = z.tanh()
+        return z.view(-1, hidden, channels)
+
+
+def _from_sequential(mods):
+    layers = []
+    for m in mods:
+        if isinstance(m, torch.nn.Linear):
+            layers.append([m.weight, m.bias, _capi.ACT_NONE])
+        elif isinstance(m, torch.nn.ReLU):
+            layers[-1][2] = _capi.ACT_RELU
+        elif isinstance(m, torch.nn.Tanh):
+            layers[-1][2] = _capi.ACT_TANH
+        elif isinstance(m, torch.nn.Identity):
+            pass
+        else:
+            raise NotImplementedError("unsupported module {} in vector field".format(type(m).__name__))
+    return layers
+
+
+def _from_fx(func):
+    try:
+        gm = torch.fx.symbolic_trace(func)
+    except Exception as e:  # noqa: BLE001
+        raise NotImplementedError("could not trace the vector field ({}); provide func.ncde_mlp_spec()".format(e))
+    layers = []
+    placeholders = [n for n in gm.graph.nodes if n.op == "placeholder"]
+    if len(placeholders) < 2:
+        raise NotImplementedError("vector field must have signature forward(t, z)")
+    cur = placeholders[1]
+    mods = dict(gm.named_modules())
+
+    def set_act(code):
+        if not layers or layers[-1][2] != _capi.ACT_NONE:
+            raise NotImplementedError("activation without a preceding Linear layer")
+        layers[-1][2] = code
+
+    for node in gm.graph.nodes:
+        if node.op in ("placeholder", "get_attr"):
+            continue
+        if node.op == "output":
+            break
+        inputs = [a for a in node.args if isinstance(a, torch.fx.Node)]
+        tname = getattr(node.target, "__name__", str(node.target))
+        # size()/getitem nodes used to build the final view are ignored
+        if node.op == "call_method" and node.target in ("size", "dim"):
+            continue
+        if node.op == "call_function" and tname in ("getitem", "mul", "add", "neg", "floordiv"):
+            if cur not in inputs:
+                continue
+        if cur not in inputs:
+            raise NotImplementedError("vector field is not a straight chain (node {})".format(node.name))
+        if node.op == "call_module":
+            m = mods[node.target]
+            if isinstance(m, torch.nn.Linear):
+                layers.append([m.weight, m.bias, _capi.ACT_NONE])
+            elif isinstance(m, torch.nn.ReLU):
+                set_act(_capi.ACT_RELU)
+            elif isinstance(m, torch.nn.Tanh):
+                set_act(_capi.ACT_TANH)
+            elif isinstance(m, torch.nn.Identity):
+                pass
+            else:
+                raise NotImplementedError("unsupported module {} in vector field".format(type(m).__name__))
+        elif node.op == "call_method" and node.target in ("relu", "tanh"):
+            set_act(_ACT[node.target])
+        elif node.op == "call_function" and tname in ("relu", "tanh"):
+            set_act(_ACT[tname])
+        elif (node.op == "call_method" and node.target in ("view", "reshape", "contiguous")) or \
+                (node.op == "call_function" and tname in ("reshape",)):
+            pass
+        else:
+            raise NotImplementedError("unsupported operation {} {} in vector field".format(node.op, node.target))
+        cur = node
+    return layers
+
+
+_CACHE = {}
+
+
+def lower(func, hidden, channels):
+    """Return the MlpSpec of ``func``; validated once per module object against func itself."""
+    key = id(func)
+    hit = _CACHE.get(key)
+    if hit is not None and hit[0]() is func and hit[2] == (hidden, channels):
+        return hit[1]
+    nfe_before = getattr(func, "nfe", None)
+    if hasattr(func, "ncde_mlp_spec"):
+        layers = [[w, b, _ACT[a] if isinstance(a, str) else a] for (w, b, a) in func.ncde_mlp_spec()]
+    elif isinstance(getattr(func, "net_to_hh", None), torch.nn.Sequential) and \
+            isinstance(getattr(func, "tanh_output_layer", None), torch.nn.Sequential):
+        if getattr(func, "vector_field_type", "matmul") != "matmul":
+            raise NotImplementedError("only vector_field_type='matmul' vector fields are supported")
+        layers = _from_sequential(list(func.net_to_hh) + list(func.tanh_output_layer))
+    elif isinstance(func, torch.nn.Module):
+        layers = _from_fx(func)
+    else:
+        raise NotImplementedError("func must be an nn.Module that is a Linear/activation chain (no eager fallback)")
+    if not layers:
+        raise NotImplementedError("vector field has no Linear layer")
+    spec = MlpSpec([tuple(l) for l in layers])
+    if spec.weights[0].shape[1] != hidden or spec.weights[-1].shape[0] != hidden * channels:
+        raise ValueError("vector field maps {} -> {} but the solve needs {} -> {}*{}".format(
+            spec.weights[0].shape[1], spec.weights[-1].shape[0], hidden, hidden, channels))
+    if spec.acts[-1] != _capi.ACT_TANH:
+        raise NotImplementedError("the vector field must end in tanh (as every vector field of the reference does)")
+    # one-off structural validation on three probe rows
+    with torch.no_grad():
+        w0 = spec.weights[0]
+        probe = torch.linspace(-1.0, 1.0, 3 * hidden, dtype=w0.dtype, device=w0.device).view(3, hidden)
+        want = func(torch.zeros((), dtype=w0.dtype, device=w0.device), probe)
+        got = spec.reference_forward(probe, hidden, channels)
+        if want.shape != got.shape or not torch.allclose(want, got, rtol=1e-4, atol=1e-5):
+            raise NotImplementedError("vector field could not be lowered to a Linear/activation chain faithfully")
+    if nfe_before is not None:
+        func.nfe = nfe_before
+    import weakref
+    try:
+        ref = weakref.ref(func)
+    except TypeError:
+        ref = (lambda f: (lambda: f))(func)
+    _CACHE[key] = (ref, spec, (hidden, channels))
+    return spec

@@ -1,0 +1,320 @@
+"""``cdeint``: drop-in for ``torchcde.cdeint`` (reference: modules/torchcde/torchcde/solver.py:140-238) whose every
+integration step runs inside libncde_b200 (hand-written sm_100a CUDA).
+
+The host side only (a) lowers ``func`` to an MLP descriptor, (b) builds the time grid exactly as
+``torchdiffeq`` does (modules/torchdiffeq/torchdiffeq/_impl/solvers.py:77-119) and (c) wires the result into
+autograd.  There is no eager / CPU fallback: unsupported inputs raise.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import lowering
+from . import misc
+from .interpolation_cubic import NaturalCubicSpline
+from .interpolation_linear import LinearInterpolation
+
+_METHODS = {"euler": _capi.EULER, "rk4": _capi.RK4_38, "dopri5": _capi.DOPRI5}
+_ALL_TORCHDIFFEQ_METHODS = ("dopri8", "dopri5", "bosh3", "fehlberg2", "adaptive_heun", "euler", "midpoint", "rk4",
+                            "explicit_adams", "implicit_adams", "fixed_adams", "scipy_solver")
+_PRECISIONS = {"fp32": _capi.PREC_FP32, "bf16": _capi.PREC_BF16}
+
+_THIRD = 1 / 3
+_TWO_THIRDS = 2 / 3
+
+# default arithmetic of the final-layer tiles; override per call with options={'precision': ...}
+default_precision = "fp32"
+
+
+class FixedSchedule:
+    """Host arrays describing the fixed grid, stage times and output map (kept alive while kernels are enqueued)."""
+
+    def __init__(self, t_host, method, step_size, grid_constructor, func, z0):
+        t = t_host
+        if step_size is None:
+            grid = t if grid_constructor is None else grid_constructor(func, z0, t)
+        else:
+            if grid_constructor is not None:
+                raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
+            # solvers.py:77-88, same torch ops in t's dtype so the grid is bit-identical
+            niters = torch.ceil((t[-1] - t[0]) / step_size + 1).item()
+            grid = torch.arange(0, niters, dtype=t.dtype) * step_size + t[0]
+            grid[-1] = t[-1]
+        grid = torch.as_tensor(grid).detach().cpu()
+        assert grid[0] == t[0] and grid[-1] == t[-1]
+        g0, g1 = grid[:-1], grid[1:]
+        dt = g1 - g0
+        if method == "rk4":
+            # rk_common.py:111-113; the cast to the state dtype is _PerturbFunc's (misc.py:181)
+            stages = torch.stack([g0, g0 + dt * _THIRD, g0 + dt * _TWO_THIRDS, g1], dim=1)
+        else:
+            stages = g0.unsqueeze(1)
+        self.n_steps = int(dt.numel())
+        self.n_stages = int(stages.shape[1]) if self.n_steps else (4 if method == "rk4" else 1)
+        self.stage_t = np.ascontiguousarray(stages.to(torch.float32).numpy())
+        self.dt = np.ascontiguousarray(dt.to(torch.float32).numpy())
+        # output map (solvers.py:106-117, 166-172)
+        T = int(t.numel())
+        tn, gn = t.numpy(), grid.numpy()
+        out_step = np.zeros(T, dtype=np.int64)
+        out_mode = np.zeros(T, dtype=np.int32)
+        out_slope = np.zeros(T, dtype=np.float32)
+        if T > 1:
+            step = np.searchsorted(gn[1:], tn[1:], side="left")
+            a, b = gn[step], gn[step + 1]
+            out_step[1:] = step
+            mode = np.where(tn[1:] == a, 0, np.where(tn[1:] == b, 1, 2))
+            out_mode[1:] = mode
+            with np.errstate(all="ignore"):
+                out_slope[1:] = ((tn[1:] - a) / (b - a)).astype(np.float32)
+        self.out_step, self.out_mode, self.out_slope = out_step, out_mode, out_slope
+        self.n_out = T
+
+
+_SCHEDULE_CACHE = {}
+
+
+def _schedule(t_host, method, options, func, z0):
+    step_size = options.get("step_size")
+    gc = options.get("grid_constructor")
+    if gc is None:
+        key = (t_host.dtype, t_host.numpy().tobytes(), method, None if step_size is None else float(step_size))
+        hit = _SCHEDULE_CACHE.get(key)
+        if hit is None:
+            if len(_SCHEDULE_CACHE) > 64:
+                _SCHEDULE_CACHE.clear()
+            hit = _SCHEDULE_CACHE[key] = FixedSchedule(t_host, method, step_size, None, func, z0)
+        return hit
+    return FixedSchedule(t_host, method, step_size, gc, func, z0)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _build_problem(X, spec, B, H, C, method, precision, sched):
+    p = _capi.Problem()
+    p.B, p.H, p.C = B, H, C
+    p.method = _METHODS[method]
+    p.precision = precision
+    m = p.mlp
+    m.n_layers = len(spec.weights)
+    keep = []
+    for i, (w, b, a, s) in enumerate(zip(spec.weights, spec.biases, spec.acts, spec.slots)):
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        keep.append(wd)
+        m.in_dim[i], m.out_dim[i], m.act[i], m.slot[i] = wd.shape[1], wd.shape[0], a, s
+        m.W[i] = wd.data_ptr()
+        if b is not None:
+            bd = b.detach().contiguous()
+            keep.append(bd)
+            m.bias[i] = bd.data_ptr()
+        else:
+            m.bias[i] = None
+    if isinstance(X, LinearInterpolation):
+        p.path.kind = _capi.PATH_LINEAR
+        coeffs = X._coeffs.detach().contiguous()
+        derivs = X._derivs.detach().contiguous()
+        p.path.K = coeffs.size(-2)
+        p.path.derivs = derivs.data_ptr()
+        keep.append(derivs)
+    else:
+        p.path.kind = _capi.PATH_CUBIC
+        coeffs = X._coeffs.detach().contiguous()
+        p.path.K = coeffs.size(-2) + 1
+        p.path.derivs = None
+    knots = X._t.detach().to(torch.float32).contiguous()
+    keep += [coeffs, knots]
+    p.path.knots = knots.data_ptr()
+    p.path.coeffs = coeffs.data_ptr()
+    g = p.grid
+    g.n_steps = sched.n_steps
+    g.stage_t, g.dt = _np_ptr(sched.stage_t), _np_ptr(sched.dt)
+    g.n_out = sched.n_out
+    g.out_step, g.out_mode, g.out_slope = _np_ptr(sched.out_step), _np_ptr(sched.out_mode), _np_ptr(sched.out_slope)
+    return p, keep
+
+
+# counters for bench / tests: kernels enqueued by the last forward / backward call
+last_launches = {"fwd": 0, "bwd": 0}
+
+
+class _FixedSolve(torch.autograd.Function):
+    """Forward: ncde_solve_fwd.  Backward: ncde_solve_bwd — the exact gradient of the discrete step loop, i.e. what
+    autograd computes through the reference when adjoint=False."""
+
+    @staticmethod
+    def forward(ctx, X, spec, method, precision, sched, z0, coeffs_for_graph, *params):
+        B, H = z0.shape
+        C = spec.weights[-1].shape[0] // H
+        dev = z0.device
+        problem, keep = _build_problem(X, spec, B, H, C, method, precision, sched)
+        L = _capi.lib()
+        need_grad = any(ctx.needs_input_grad[5:])
+        z0c = z0.detach().contiguous()
+        z_out = torch.empty(sched.n_out, B, H, dtype=torch.float32, device=dev)
+        saved = None
+        if need_grad:
+            nbytes = L.ncde_solve_saved_bytes(ctypes.byref(problem), 1)
+            saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 0)
+        if wbytes == 0:
+            # let the library produce the precise error
+            _capi.check(L.ncde_solve_fwd(ctypes.byref(problem), z0c.data_ptr(), z_out.data_ptr(), None, 0, None, 0,
+                                         None, None, None, _capi.stream_ptr(dev)))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        launches = ctypes.c_int64(0)
+        _capi.check(L.ncde_solve_fwd(ctypes.byref(problem), z0c.data_ptr(), z_out.data_ptr(), _capi.ptr(saved),
+                                     int(need_grad), work.data_ptr(), wbytes, None, None, ctypes.byref(launches),
+                                     _capi.stream_ptr(dev)))
+        last_launches["fwd"] = launches.value
+        ctx.X, ctx.spec, ctx.method, ctx.precision, ctx.sched = X, spec, method, precision, sched
+        ctx.saved_buf = saved
+        ctx.shape = (B, H, C)
+        ctx.n_params = len(params)
+        return z_out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, H, C = ctx.shape
+        spec = ctx.spec
+        dev = grad_out.device
+        if ctx.needs_input_grad[6]:
+            raise NotImplementedError("gradients with respect to the control path coefficients are not implemented")
+        problem, keep = _build_problem(ctx.X, spec, B, H, C, ctx.method, ctx.precision, ctx.sched)
+        L = _capi.lib()
+        g = grad_out.contiguous()
+        grad_z0 = torch.empty(B, H, dtype=torch.float32, device=dev)
+        # one gradient tensor per unique parameter, in the order the params were passed to apply()
+        uniq = spec.unique_params
+        grads = [torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p, _, _ in uniq]
+        by_layer_w, by_layer_b = {}, {}
+        for gt, (_, kind, layer) in zip(grads, uniq):
+            (by_layer_w if kind == "W" else by_layer_b)[layer] = gt
+        n = len(spec.weights)
+        gW = (ctypes.c_void_p * _capi.MAX_LAYERS)()
+        gb = (ctypes.c_void_p * _capi.MAX_LAYERS)()
+        first_of_slot = {}
+        for i in range(n):
+            j = first_of_slot.setdefault(spec.slots[i], i)
+            gW[i] = by_layer_w[j].data_ptr()
+            gb[i] = by_layer_b[j].data_ptr() if j in by_layer_b else None
+        wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 1)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        launches = ctypes.c_int64(0)
+        _capi.check(L.ncde_solve_bwd(ctypes.byref(problem), g.data_ptr(), ctx.saved_buf.data_ptr(), grad_z0.data_ptr(),
+                                     gW, gb, None, work.data_ptr(), wbytes, ctypes.byref(launches),
+                                     _capi.stream_ptr(dev)))
+        last_launches["bwd"] = launches.value
+        ctx.saved_buf = None
+        return (None, None, None, None, None, grad_z0, None) + tuple(grads)
+
+
+def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
+    r"""Solves z_t = z_{t_0} + \int_{t_0}^t f(s, z_s) dX_s on the GPU.
+
+    Same signature, argument meaning, defaults and return layout ``(..., len(t), hidden_channels)`` as the
+    reference's ``torchcde.cdeint`` (modules/torchcde/torchcde/solver.py:140-238).  ``kwargs`` are the torchdiffeq
+    solver arguments (``method``, ``rtol``, ``atol``, ``options``, ``adjoint_*``).  One extra option is understood:
+    ``options['precision']`` in {'fp32', 'bf16'} selects the arithmetic of the final-layer tiles.
+
+    Differences, all loud: ``X`` must be a ``LinearInterpolation`` or ``NaturalCubicSpline`` of this package,
+    ``func`` must lower to a Linear/activation chain (see ``lowering``), ``vector_field_type`` must be 'matmul',
+    tensors must live on a CUDA device.
+    """
+    if vector_field_type not in ['matmul', 'evaluate', 'derivative']:
+        raise ValueError("vector_field_type string not recognised")
+    if vector_field_type != 'matmul':
+        raise NotImplementedError("vector_field_type='{}' is not implemented by the fused solve".format(vector_field_type))
+    if not isinstance(X, (LinearInterpolation, NaturalCubicSpline)):
+        raise NotImplementedError("X must be a torchcde_b200 LinearInterpolation or NaturalCubicSpline")
+    if not isinstance(z0, torch.Tensor):
+        raise NotImplementedError("tuple state is not supported (it is dead code in the reference fork as well)")
+    _capi.require_cuda(z0, X._coeffs)
+    if z0.dtype != torch.float32 or X._coeffs.dtype != torch.float32:
+        raise NotImplementedError("the fused solve runs an fp32 state; got z0 {} / coeffs {}".format(
+            z0.dtype, X._coeffs.dtype))
+
+    # solver.py:193-196
+    if 'atol' not in kwargs:
+        kwargs['atol'] = 1e-6
+    if 'rtol' not in kwargs:
+        kwargs['rtol'] = 1e-4
+    method = kwargs.pop('method', None)
+    options = dict(kwargs.pop('options', None) or {})
+    if method is None:
+        method = 'dopri5'  # misc.py:222-223
+    if method not in _ALL_TORCHDIFFEQ_METHODS:
+        raise ValueError('Invalid method "{}". Must be one of {}'.format(
+            method, '{"' + '", "'.join(_ALL_TORCHDIFFEQ_METHODS) + '"}.'))
+    if method not in _METHODS:
+        raise NotImplementedError("method '{}' is not implemented by the fused solve (euler, rk4, dopri5 are)".format(method))
+    precision = options.pop('precision', default_precision)
+    if precision not in _PRECISIONS:
+        raise ValueError("options['precision'] must be one of {}".format(sorted(_PRECISIONS)))
+
+    if not isinstance(t, torch.Tensor):
+        raise AssertionError("t must be a torch.Tensor")
+    if not t.is_floating_point():
+        raise TypeError('`t` must be a floating point Tensor but is a {}'.format(t.type()))
+    assert t.ndimension() == 1, "t must be one dimensional"
+    if t.requires_grad:
+        raise NotImplementedError("gradients with respect to t are not implemented")
+    t_host = misc.host_values(t)
+    diff = t_host[1:] > t_host[:-1]
+    assert bool(diff.all()) or bool((~diff).all()), 't must be strictly increasing or decreasing'
+    if len(t_host) > 1 and bool(t_host[0] > t_host[1]):
+        raise NotImplementedError("decreasing integration times are not implemented")
+
+    batch_shape = z0.shape[:-1]
+    H = z0.shape[-1]
+    coeffs = X._coeffs
+    if coeffs.shape[:-2] != batch_shape:
+        raise ValueError("batch dimensions of z0 {} and of the control path {} differ".format(
+            tuple(batch_shape), tuple(coeffs.shape[:-2])))
+    C = coeffs.shape[-1] // (4 if isinstance(X, NaturalCubicSpline) else 1)
+    spec = lowering.lower(func, H, C)
+    for w in spec.weights:
+        _capi.require_cuda(w)
+        if w.dtype != torch.float32:
+            raise NotImplementedError("vector field parameters must be float32")
+
+    if method == 'dopri5':
+        from . import adaptive
+        out = adaptive.solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs)
+    else:
+        unused = {k: v for k, v in options.items() if k not in ('step_size', 'grid_constructor', 'perturb', 'interp')}
+        if options.get('interp', 'linear') != 'linear':
+            raise NotImplementedError("only interp='linear' is implemented for fixed-grid output")
+        if options.get('perturb', False):
+            raise NotImplementedError("perturb=True is not implemented")
+        if unused:
+            warnings.warn('{}: Unexpected arguments {}'.format('RK4' if method == 'rk4' else 'Euler', unused))
+        if adjoint:
+            raise NotImplementedError("adjoint=True with a fixed-grid solver is not implemented yet; every "
+                                      "configuration of the reference uses adjoint=False (SURVEY F6)")
+        z0f = z0.reshape(-1, H)
+        sched = _schedule(t_host, method, options, func, z0f)
+        params = [p for p, _, _ in spec.unique_params]
+        Xf = X
+        if len(batch_shape) != 1:
+            Xf = _flatten_path(X)
+        out = _FixedSolve.apply(Xf, spec, method, _PRECISIONS[precision], sched, z0f, coeffs, *params)
+        if hasattr(func, "nfe"):
+            func.nfe += sched.n_steps * sched.n_stages
+        out = out.reshape(sched.n_out, *batch_shape, H)
+
+    # solver.py:227-229: (T, ..., H) -> (..., T, H)
+    batch_dims = range(1, len(out.shape) - 1)
+    return out.permute(*batch_dims, 0, -1)
+
+
+def _flatten_path(X):
+    """View of X with all leading batch dimensions merged into one."""
+    coeffs = X._coeffs.reshape(-1, *X._coeffs.shape[-2:])
+    return type(X)(coeffs, misc.attach_host(X._t, X._t_host))
