@@ -176,6 +176,19 @@ int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, const void* s
                    float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
                    size_t workspace_bytes, int64_t* launches, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-kernel timing with CUDA events on the launching stream (measurement support for bench.py; no reference
+ * counterpart).  While enabled, every launch of the kernel classes in `class_mask` is bracketed by an event
+ * pair.  ncde_profile_read synchronises on the recorded events, sums elapsed milliseconds and launch counts per
+ * class into ms[NCDE_PROF_CLASSES] / count[NCDE_PROF_CLASSES], and clears the record.
+ * ---------------------------------------------------------------------------------------------------------- */
+enum ncde_prof_class {
+    NCDE_PROF_HIDDEN_FWD = 0, NCDE_PROF_FIELD_FWD = 1, NCDE_PROF_FIELD_BWD = 2, NCDE_PROF_HIDDEN_BWD = 3,
+    NCDE_PROF_HIDDEN_WGRAD = 4, NCDE_PROF_OTHER = 5, NCDE_PROF_CLASSES = 6
+};
+int ncde_profile_enable(int class_mask);
+int ncde_profile_read(double* ms, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,21 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- optional per-kernel event timing ------------------------------------------------------------------------
+struct ProfRecord { int cls; cudaEvent_t a, b; };
+static int g_prof_mask = 0;
+static std::vector<ProfRecord> g_prof;
+
+struct ProfScope {
+    int cls; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    ProfScope(int c, cudaStream_t s) : cls(c), st(s), on((g_prof_mask >> c) & 1) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); g_prof.push_back({cls, a, b}); }
+    }
+};
+
 constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr int kNumSMs = 148;
 
@@ -222,6 +237,25 @@ extern "C" const char* ncde_version(void) { return "ncde_b200 0.1.0 (sm_100a)"; 
 extern "C" const char* ncde_last_error(void) { return ncde::g_error; }
 extern "C" int ncde_abi_version(void) { return NCDE_ABI_VERSION; }
 
+extern "C" int ncde_profile_enable(int class_mask) {
+    ncde::g_prof_mask = class_mask;
+    return NCDE_OK;
+}
+
+extern "C" int ncde_profile_read(double* ms, int64_t* count) {
+    NCDE_REQUIRE(ms && count, NCDE_ERR_INVALID, "profile_read: null pointer");
+    for (int c = 0; c < NCDE_PROF_CLASSES; ++c) { ms[c] = 0.0; count[c] = 0; }
+    for (auto& r : ncde::g_prof) {
+        NCDE_CUDA_OK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        NCDE_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cls] += t; count[r.cls] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    ncde::g_prof.clear();
+    return NCDE_OK;
+}
+
 extern "C" size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad) {
     Plan pl;
     if (!p || !need_grad || make_plan(p, &pl) != NCDE_OK) return 0;
@@ -305,19 +339,25 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
             ha.dXT = stage + pl.dx_off;
             ha.path.t = g.stage_t[s * NS + i];
-            hidden_fwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(ha);
+            {
+                ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
+                hidden_fwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(ha);
+            }
             ++launches;
             fa.actT = stage + pl.act_off[pl.F];
             fa.dXT = stage + pl.dx_off;
             fa.koutT = kT[i];
-            if (use_tc) {
-                rc = tc_field_fwd(p, fa, st, &launches);
-                if (rc != NCDE_OK) return rc;
-            } else {
-                const dim3 fg(pl.n_hg, pl.n_bt);
-                if (pl.TM == 8) field_fwd_kernel<8><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
-                else field_fwd_kernel<4><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
-                ++launches;
+            {
+                ProfScope ps(NCDE_PROF_FIELD_FWD, st);
+                if (use_tc) {
+                    rc = tc_field_fwd(p, fa, st, &launches);
+                    if (rc != NCDE_OK) return rc;
+                } else {
+                    const dim3 fg(pl.n_hg, pl.n_bt);
+                    if (pl.TM == 8) field_fwd_kernel<8><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
+                    else field_fwd_kernel<4><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
+                    ++launches;
+                }
             }
         }
         AdvanceArgs aa;
@@ -454,14 +494,17 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             fa.actT = stage + pl.act_off[pl.F];
             fa.dXT = stage + pl.dx_off;
             fa.gkT = gkT[i];
-            if (use_tc) {
-                rc = tc_field_bwd(p, fa, st, &launches);
-                if (rc != NCDE_OK) return rc;
-            } else {
-                const dim3 fg(pl.n_hg, pl.n_bt);
-                if (pl.TM == 8) field_bwd_kernel<8><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
-                else field_bwd_kernel<4><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
-                ++launches;
+            {
+                ProfScope ps(NCDE_PROF_FIELD_BWD, st);
+                if (use_tc) {
+                    rc = tc_field_bwd(p, fa, st, &launches);
+                    if (rc != NCDE_OK) return rc;
+                } else {
+                    const dim3 fg(pl.n_hg, pl.n_bt);
+                    if (pl.TM == 8) field_bwd_kernel<8><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
+                    else field_bwd_kernel<4><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
+                    ++launches;
+                }
             }
             for (int l = 0; l <= pl.F; ++l) hb.actT[l] = stage + pl.act_off[l];
             // d(stage input)/d(k_j): rk_common.py:111-113
@@ -473,11 +516,17 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 if (i == 3) { hb.n_k = 3; hb.kcoef[0] = dt; hb.kcoef[1] = -dt; hb.kcoef[2] = dt; }
                 for (int j = 0; j < hb.n_k; ++j) hb.gkT[j] = gkT[j];
             }
-            hidden_bwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(hb);
+            {
+                ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
+                hidden_bwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(hb);
+            }
             ++launches;
             if (pl.F > 0) {
                 for (int l = 0; l < pl.F; ++l) wa.actT[l] = stage + pl.act_off[l];
-                hidden_wgrad_kernel<<<total_tiles, kThreads, 0, st>>>(wa);
+                {
+                    ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
+                    hidden_wgrad_kernel<<<total_tiles, kThreads, 0, st>>>(wa);
+                }
                 ++launches;
             }
         }

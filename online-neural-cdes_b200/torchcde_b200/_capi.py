@@ -72,7 +72,9 @@ _lib = None
 SYMBOLS = ["ncde_version", "ncde_last_error", "ncde_abi_version", "ncde_forward_fill", "ncde_rectilinear_prepare",
            "ncde_linear_fill_missing", "ncde_cubic_scratch_bytes", "ncde_natural_cubic_coeffs", "ncde_linear_derivs",
            "ncde_path_eval", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
-           "ncde_solve_bwd"]
+           "ncde_solve_bwd", "ncde_profile_enable", "ncde_profile_read"]
+
+PROF_CLASSES = ["hidden_fwd", "field_fwd", "field_bwd", "hidden_bwd", "hidden_wgrad", "other"]
 
 
 def lib():
@@ -105,6 +107,8 @@ def lib():
                                  ctypes.POINTER(ctypes.c_int64), vp]
     L.ncde_solve_bwd.argtypes = [ctypes.POINTER(Problem), vp, vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp,
                                  sz, ctypes.POINTER(ctypes.c_int64), vp]
+    L.ncde_profile_enable.argtypes = [i32]
+    L.ncde_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("ncde_abi_version",):
@@ -152,3 +156,19 @@ def stream_ptr(device):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def profile_enable(classes):
+    """Bracket every launch of the named kernel classes with CUDA events (bench.py's live kernel timing)."""
+    mask = 0
+    for c in classes:
+        mask |= 1 << PROF_CLASSES.index(c)
+    check(lib().ncde_profile_enable(mask))
+
+
+def profile_read():
+    """-> {class: (total_ms, launches)}; synchronises on the recorded events and clears them."""
+    ms = (ctypes.c_double * len(PROF_CLASSES))()
+    cnt = (ctypes.c_int64 * len(PROF_CLASSES))()
+    check(lib().ncde_profile_read(ms, cnt))
+    return {c: (ms[i], cnt[i]) for i, c in enumerate(PROF_CLASSES)}
