@@ -39,14 +39,21 @@ struct Plan {
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
+    int tc, Npad, KP;         // tensor-core path: columns per h-group padded to 16, K padded to 64
     int R, n_rt;
     int n_stages;
     size_t stage_floats;      // saved floats per RK stage
     size_t act_off[NCDE_MAX_LAYERS + 1];
-    size_t dx_off;
+    size_t dx_off, abf_off;
     size_t fwd_smem, bwd_smem, hid_smem;
-    size_t off_WT[NCDE_MAX_LAYERS], off_bp[NCDE_MAX_LAYERS], off_W3T, off_W3R, off_b3p, wpack_floats;
-    int ldw[NCDE_MAX_LAYERS];
+    size_t off_WT[NCDE_MAX_LAYERS], off_WR[NCDE_MAX_LAYERS], off_bp[NCDE_MAX_LAYERS], off_W3T, off_W3R, off_b3p,
+        wpack_floats;
+    int ldw[NCDE_MAX_LAYERS], ldi[NCDE_MAX_LAYERS];
+    int first_of_slot[NCDE_MAX_LAYERS];  // first layer that uses the same parameters as layer l
+    size_t wt_floats, wr_floats;         // contiguous packed hidden weights (k-major / row-major), unique slots only
+    int w_in_smem;
+    size_t hid_smem_fwd, hid_smem_bwd;
+    int wg_tiles, wg_split, wg_rows;     // hidden weight-gradient grid
 };
 
 static size_t bwd_smem_floats(int DF, int DFP, int S, int Hg) {
@@ -67,7 +74,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38, NCDE_ERR_UNSUPPORTED,
                  "solve: method %d is not a fixed-grid method", p->method);
     pl->B = (int)p->B; pl->H = p->H; pl->C = p->C;
-    pl->Bp = (int)round_up(p->B, kChunk);
+    pl->Bp = (int)round_up(p->B, kTcM);
     pl->Cp = (int)round_up(p->C, 4);
     pl->F = m.n_layers - 1;
     pl->n_stages = p->method == NCDE_RK4_38 ? 4 : 1;
@@ -95,33 +102,67 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     NCDE_REQUIRE(dmax <= 1024, NCDE_ERR_UNSUPPORTED, "solve: layer width %d > 1024 not supported", dmax);
     pl->Dmax = dmax;
 
-    // field tiling: h-groups x batch tiles
-    double best = -1.0;
-    const int hg_max = pl->H < 128 / pl->Cp ? pl->H : 128 / pl->Cp;
-    for (int hg = hg_max; hg >= 1; --hg) {
-        const int S = hg * pl->Cp, NT = S / 4;
-        if (bwd_smem_floats(pl->DF, pl->DFP, S, hg) * 4 > kSmemLimit) continue;
-        if (NT * (pl->DFP / 16) > kThreads) continue;
-        const int n_hg = (int)ceil_div(pl->H, hg);
-        int n_bt = kNumSMs / n_hg;
-        const int max_bt = (int)ceil_div(pl->B, kChunk);
-        n_bt = n_bt < 1 ? 1 : (n_bt > max_bt ? max_bt : n_bt);
-        const int TM = NT > 16 ? 8 : 4;
-        const int thr = NT * (kChunk / TM);
-        const double util = (thr > kThreads ? kThreads : thr) / (double)kThreads;
-        const int ctas = n_hg * n_bt;
-        const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * util;
-        if (score > best + 1e-9) {
-            best = score;
-            pl->Hg = hg; pl->S = S; pl->n_hg = n_hg; pl->TM = TM;
-            pl->Bt = (int)round_up(ceil_div(pl->B, n_bt), kChunk);
-            pl->n_bt = (int)ceil_div(pl->B, pl->Bt);
+    pl->tc = p->precision == NCDE_PREC_BF16;
+    if (!pl->tc) {
+        // field tiling (fp32 kernels): h-groups x batch tiles
+        double best = -1.0;
+        const int hg_max = pl->H < 128 / pl->Cp ? pl->H : 128 / pl->Cp;
+        for (int hg = hg_max; hg >= 1; --hg) {
+            const int S = hg * pl->Cp, NT = S / 4;
+            if (bwd_smem_floats(pl->DF, pl->DFP, S, hg) * 4 > kSmemLimit) continue;
+            if (NT * (pl->DFP / 16) > kThreads) continue;
+            const int n_hg = (int)ceil_div(pl->H, hg);
+            int n_bt = kNumSMs / n_hg;
+            const int max_bt = (int)ceil_div(pl->B, kChunk);
+            n_bt = n_bt < 1 ? 1 : (n_bt > max_bt ? max_bt : n_bt);
+            const int TM = NT > 16 ? 8 : 4;
+            const int thr = NT * (kChunk / TM);
+            const double util = (thr > kThreads ? kThreads : thr) / (double)kThreads;
+            const int ctas = n_hg * n_bt;
+            const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * util;
+            if (score > best + 1e-9) {
+                best = score;
+                pl->Hg = hg; pl->S = S; pl->n_hg = n_hg; pl->TM = TM;
+                pl->Bt = (int)round_up(ceil_div(pl->B, n_bt), kChunk);
+                pl->n_bt = (int)ceil_div(pl->B, pl->Bt);
+            }
         }
+        NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve: no field tiling fits shared memory (C=%d, width=%d)", p->C, pl->DF);
+        pl->Npad = pl->S;
+        pl->KP = pl->DFP;
+        pl->fwd_smem = fwd_smem_floats(pl->DF, pl->S) * 4;
+        pl->bwd_smem = bwd_smem_floats(pl->DF, pl->DFP, pl->S, pl->Hg) * 4;
+    } else {
+        // tensor-core tiling: h-group columns padded to a multiple of 16 (UMMA N), K padded to 64 (one swizzle block)
+        // K is padded to 128 so that the weight-gradient MMA (M = K) always runs the M = 128 shape
+        pl->KP = 128;
+        pl->DFP = pl->KP;  // gradient buffers share the padded K
+        double best = -1.0;
+        const int n_mt = (int)ceil_div(pl->B, kTcM);
+        for (int hg = 8; hg >= 1; --hg) {
+            if (hg > pl->H) continue;
+            const int npad = (int)round_up(hg * pl->Cp, 16);
+            if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
+            if (tc_bwd_smem_bytes(npad, pl->KP, hg, pl->Cp) > kSmemLimit) continue;
+            const int n_hg = (int)ceil_div(pl->H, hg);
+            int n_bt = kNumSMs / n_hg;
+            n_bt = n_bt < 1 ? 1 : (n_bt > n_mt ? n_mt : n_bt);
+            const int ctas = n_hg * n_bt;
+            const double waste = (double)(hg * pl->Cp) / npad;
+            const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * waste + 1e-4 * hg;
+            if (score > best + 1e-9) {
+                best = score;
+                pl->Hg = hg; pl->S = hg * pl->Cp; pl->Npad = npad; pl->n_hg = n_hg;
+                pl->Bt = (int)round_up(ceil_div(pl->B, n_bt), kTcM);
+                pl->n_bt = (int)ceil_div(pl->B, pl->Bt);
+            }
+        }
+        NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve: no tensor-core tiling fits (C=%d, width=%d)", p->C, pl->DF);
+        pl->TM = 8;
+        pl->fwd_smem = tc_fwd_smem_bytes(pl->Npad, pl->KP, pl->Hg, pl->Cp);
+        pl->bwd_smem = tc_bwd_smem_bytes(pl->Npad, pl->KP, pl->Hg, pl->Cp);
     }
-    NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve: no field tiling fits shared memory (C=%d, width=%d)", p->C, pl->DF);
-    pl->Np = pl->n_hg * pl->S;
-    pl->fwd_smem = fwd_smem_floats(pl->DF, pl->S) * 4;
-    pl->bwd_smem = bwd_smem_floats(pl->DF, pl->DFP, pl->S, pl->Hg) * 4;
+    pl->Np = pl->n_hg * pl->Npad;
 
     // hidden tiling
     int R = (int)round_up(ceil_div(pl->B, kNumSMs), 4);
@@ -130,20 +171,59 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     pl->n_rt = (int)ceil_div(pl->B, R);
     pl->hid_smem = (size_t)2 * pl->Dmax * R * 4;
     NCDE_REQUIRE(pl->hid_smem <= 48 * 1024, NCDE_ERR_UNSUPPORTED, "solve: hidden tile too large");
+    for (int l = 0; l < pl->F; ++l) {
+        pl->first_of_slot[l] = l;
+        for (int j = 0; j < l; ++j)
+            if (m.slot[j] == m.slot[l] && m.W[j] == m.W[l]) { pl->first_of_slot[l] = j; break; }
+        if (pl->first_of_slot[l] != l)
+            NCDE_REQUIRE(m.in_dim[l] == m.in_dim[pl->first_of_slot[l]] && m.out_dim[l] == m.out_dim[pl->first_of_slot[l]],
+                         NCDE_ERR_INVALID, "solve: layers sharing a slot must have the same shape");
+    }
 
     // saved-per-stage layout
     size_t off = 0;
     for (int l = 0; l <= pl->F; ++l) { pl->act_off[l] = off; off += (size_t)pl->Dp4[l] * pl->Bp; }
     pl->dx_off = off; off += (size_t)pl->Cp * pl->Bp;
+    pl->abf_off = off;
+    if (pl->tc) off += (size_t)pl->Bp * pl->KP / 2;  // bf16 copy of the final-layer input
     pl->stage_floats = off;
 
     // packed weights
     off = 0;
-    for (int l = 0; l < pl->F; ++l) {
+    for (int l = 0; l < pl->F; ++l) {  // k-major copies, unique slots, contiguous
         pl->ldw[l] = (int)round_up(m.out_dim[l], 4);
-        pl->off_WT[l] = off; off += round_up((size_t)pl->D[l] * pl->ldw[l], 64);
-        pl->off_bp[l] = off; off += round_up(pl->ldw[l], 64);
+        pl->ldi[l] = (int)round_up(m.in_dim[l], 4);
+        if (pl->first_of_slot[l] == l) { pl->off_WT[l] = off; off += (size_t)pl->D[l] * pl->ldw[l]; }
+        else pl->off_WT[l] = pl->off_WT[pl->first_of_slot[l]];
     }
+    pl->wt_floats = off;
+    off = round_up(off, 64);
+    const size_t wr_begin = off;
+    for (int l = 0; l < pl->F; ++l) {  // row-major copies for the backward pass
+        if (pl->first_of_slot[l] == l) { pl->off_WR[l] = off; off += (size_t)m.out_dim[l] * pl->ldi[l]; }
+        else pl->off_WR[l] = pl->off_WR[pl->first_of_slot[l]];
+    }
+    pl->wr_floats = off - wr_begin;
+    off = round_up(off, 64);
+    for (int l = 0; l < pl->F; ++l) { pl->off_bp[l] = off; off += round_up(pl->ldw[l], 64); }
+    {
+        const size_t wmax = pl->wt_floats > pl->wr_floats ? pl->wt_floats : pl->wr_floats;
+        pl->w_in_smem = pl->F > 0 && (pl->hid_smem + wmax * 4) <= 200 * 1024;
+        pl->hid_smem_fwd = pl->hid_smem + (pl->w_in_smem ? round_up(pl->wt_floats, 4) * 4 : 0);
+        pl->hid_smem_bwd = pl->hid_smem + (pl->w_in_smem ? round_up(pl->wr_floats, 4) * 4 : 0);
+    }
+    {
+        int tiles = 0;
+        for (int l = 0; l < pl->F; ++l)
+            if (pl->first_of_slot[l] == l) tiles += (int)(ceil_div(m.out_dim[l], kWgTile) * ceil_div(m.in_dim[l], kWgTile));
+        pl->wg_tiles = tiles;
+        int split = tiles > 0 ? kNumSMs / tiles : 1;
+        const int max_split = (int)ceil_div(pl->B, kWgRows);
+        split = split < 1 ? 1 : (split > max_split ? max_split : split);
+        pl->wg_rows = (int)round_up(ceil_div(pl->B, split), kWgRows);
+        pl->wg_split = (int)ceil_div(pl->B, pl->wg_rows);
+    }
+    // fp32 path: W3T [DF][Np] + W3R [Np][DFP]; tensor-core path: bf16 [Np][KP] stored in the W3T slot
     pl->off_W3T = off; off += round_up((size_t)pl->DF * pl->Np, 64);
     pl->off_W3R = off; off += round_up((size_t)pl->Np * pl->DFP, 64);
     pl->off_b3p = off; off += round_up(pl->Np, 64);
@@ -176,6 +256,7 @@ static size_t bwd_workspace_floats(const Plan& pl) {
     for (int l = 0; l < pl.F; ++l) n += (size_t)pl.Dp4[l + 1] * pl.Bp + per;
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
     n += (size_t)pl.n_bt * pl.Np + per;
+    n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
     return n;
 }
 
@@ -183,16 +264,25 @@ static int pack_weights(const ncde_problem_t* p, const Plan& pl, float* wpack, i
                         int64_t* launches) {
     const ncde_mlp_t& m = p->mlp;
     for (int l = 0; l < pl.F; ++l) {
-        const int n = pl.D[l] * pl.ldw[l];
-        pack_hidden_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(m.W[l], m.bias[l], wpack + pl.off_WT[l],
-                                                                      wpack + pl.off_bp[l], m.out_dim[l], pl.D[l],
-                                                                      pl.ldw[l]);
+        int n = pl.D[l] * pl.ldw[l];
+        const int nr = m.out_dim[l] * pl.ldi[l];
+        n = n > nr ? n : nr;
+        pack_hidden_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+            m.W[l], m.bias[l], wpack + pl.off_WT[l], wpack + pl.off_bp[l], with_rowmajor ? wpack + pl.off_WR[l] : nullptr,
+            m.out_dim[l], pl.D[l], pl.ldw[l], pl.ldi[l]);
         ++*launches;
     }
-    const int64_t n = (int64_t)pl.Np * pl.DFP;
-    pack_final_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
-        m.W[pl.F], m.bias[pl.F], wpack + pl.off_W3T, with_rowmajor ? wpack + pl.off_W3R : nullptr,
-        wpack + pl.off_b3p, pl.H, pl.C, pl.Cp, pl.DF, pl.DFP, pl.Np);
+    if (pl.tc) {
+        const int64_t n = (int64_t)pl.Np * pl.KP;
+        pack_final_bf16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+            m.W[pl.F], m.bias[pl.F], (__nv_bfloat16*)(wpack + pl.off_W3T), wpack + pl.off_b3p, pl.H, pl.C, pl.Cp, pl.Hg,
+            pl.n_hg, pl.Npad, pl.KP, pl.DF);
+    } else {
+        const int64_t n = (int64_t)pl.Np * pl.DFP;
+        pack_final_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+            m.W[pl.F], m.bias[pl.F], wpack + pl.off_W3T, with_rowmajor ? wpack + pl.off_W3R : nullptr,
+            wpack + pl.off_b3p, pl.H, pl.C, pl.Cp, pl.DF, pl.DFP, pl.Np);
+    }
     ++*launches;
     NCDE_CUDA_OK(cudaGetLastError());
     return NCDE_OK;
@@ -220,6 +310,14 @@ template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) NCDE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return NCDE_OK;
+}
+
+static void fill_tc_args(TcFieldArgs& ta, const Plan& pl, const float* wpack) {
+    memset(&ta, 0, sizeof(ta));
+    ta.B = pl.B; ta.Bp = pl.Bp; ta.H = pl.H; ta.Cp = pl.Cp; ta.Hg = pl.Hg; ta.n_hg = pl.n_hg; ta.Npad = pl.Npad;
+    ta.KP = pl.KP; ta.DF = pl.DF; ta.Bt = pl.Bt; ta.DFP = pl.DFP;
+    ta.Wbf = (const __nv_bfloat16*)(wpack + pl.off_W3T);
+    ta.b3 = wpack + pl.off_b3p;
 }
 
 static void fill_field_args(FieldArgs& fa, const Plan& pl, const float* wpack) {
@@ -298,12 +396,10 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     rc = pack_weights(p, pl, wpack, 0, st, &launches);
     if (rc != NCDE_OK) return rc;
 
-    const bool use_tc = p->precision == NCDE_PREC_BF16;
-    if (use_tc) {
-        rc = tc_prepare(p, pl.H, pl.C, pl.Cp, pl.DF, pl.Bp);
-        if (rc != NCDE_OK) return rc;
-    }
-    if (pl.TM == 8) rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); else rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem);
+    const bool use_tc = pl.tc != 0;
+    if (use_tc) rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem);
+    else if (pl.TM == 8) rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem);
+    else rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem);
     if (rc != NCDE_OK) return rc;
 
     const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
@@ -318,13 +414,20 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     for (int l = 0; l < pl.F; ++l) {
         ha.ldw[l] = pl.ldw[l]; ha.act[l] = p->mlp.act[l];
         ha.WT[l] = wpack + pl.off_WT[l]; ha.bp[l] = wpack + pl.off_bp[l];
+        ha.wsm_off[l] = (int)(pl.off_WT[l] - pl.off_WT[0]);
     }
+    ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
+    rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
+    if (rc != NCDE_OK) return rc;
     ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
     ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
     for (int i = 0; i < NS; ++i) ha.kT[i] = kT[i];
 
     FieldArgs fa;
     fill_field_args(fa, pl, wpack);
+    TcFieldArgs ta;
+    fill_tc_args(ta, pl, wpack);
+    ha.KP = pl.KP;
 
     static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
     int cur = 0;
@@ -338,10 +441,11 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             ha.yT = yT[cur];
             for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
             ha.dXT = stage + pl.dx_off;
+            ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
             ha.path.t = g.stage_t[s * NS + i];
             {
                 ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
-                hidden_fwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(ha);
+                hidden_fwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem_fwd, st>>>(ha);
             }
             ++launches;
             fa.actT = stage + pl.act_off[pl.F];
@@ -350,8 +454,11 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             {
                 ProfScope ps(NCDE_PROF_FIELD_FWD, st);
                 if (use_tc) {
-                    rc = tc_field_fwd(p, fa, st, &launches);
-                    if (rc != NCDE_OK) return rc;
+                    ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
+                    ta.dXT = stage + pl.dx_off;
+                    ta.koutT = kT[i];
+                    tc_field_fwd_kernel<<<dim3(pl.n_hg, pl.n_bt), kTcThreads, pl.fwd_smem, st>>>(ta);
+                    ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
                     if (pl.TM == 8) field_fwd_kernel<8><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
@@ -424,9 +531,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
 
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
-    if (pl.TM == 8) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); else rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
+    const bool use_tc = pl.tc != 0;
+    if (use_tc) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem);
+    else if (pl.TM == 8) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem);
+    else rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
     if (rc != NCDE_OK) return rc;
-    const bool use_tc = p->precision == NCDE_PREC_BF16;
 
     NCDE_CUDA_OK(cudaMemsetAsync(gyT, 0, nHB * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, (size_t)pl.n_bt * pl.Np * pl.DFP * 4, st));
@@ -435,18 +544,27 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     FieldArgs fa;
     fill_field_args(fa, pl, wpack);
     fa.P = P; fa.dW3acc = dW3acc; fa.db3acc = db3acc;
+    TcFieldArgs ta;
+    fill_tc_args(ta, pl, wpack);
+    ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc;
 
     HiddenBwdArgs hb;
     memset(&hb, 0, sizeof(hb));
     hb.B = pl.B; hb.Bp = pl.Bp; hb.H = pl.H; hb.R = pl.R; hb.F = pl.F; hb.Dmax = pl.Dmax; hb.DFP = pl.DFP; hb.n_hg = pl.n_hg;
     for (int l = 0; l <= pl.F; ++l) hb.D[l] = pl.D[l];
-    for (int l = 0; l < pl.F; ++l) { hb.act[l] = m.act[l]; hb.W[l] = m.W[l]; hb.dpreT[l] = dpreT[l]; }
+    for (int l = 0; l < pl.F; ++l) {
+        hb.act[l] = m.act[l]; hb.W[l] = wpack + pl.off_WR[l]; hb.ldi[l] = pl.ldi[l]; hb.dpreT[l] = dpreT[l];
+        hb.wsm_off[l] = (int)(pl.off_WR[l] - pl.off_WR[0]);
+    }
+    hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
     hb.P = P; hb.gyT = gyT;
+    rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
+    if (rc != NCDE_OK) return rc;
 
     // weight-gradient tiles grouped by slot
     WgradArgs wa;
     memset(&wa, 0, sizeof(wa));
-    wa.B = pl.B; wa.Bp = pl.Bp;
+    wa.B = pl.B; wa.Bp = pl.Bp; wa.n_split = pl.wg_split; wa.rows_per_split = pl.wg_rows;
     int total_tiles = 0;
     for (int l = 0; l < pl.F; ++l) {
         int sidx = -1;
@@ -466,9 +584,15 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     }
     for (int s2 = 0; s2 < wa.n_slots; ++s2) {
         wa.tile_begin[s2] = total_tiles;
-        total_tiles += (int)(ceil_div(wa.Dout[s2], 32) * ceil_div(wa.Din[s2], 32));
+        total_tiles += (int)(ceil_div(wa.Dout[s2], kWgTile) * ceil_div(wa.Din[s2], kWgTile));
+        const size_t nW = (size_t)pl.wg_split * wa.Dout[s2] * wa.Din[s2], nb = (size_t)pl.wg_split * wa.Dout[s2];
+        wa.gWp[s2] = cv.take(nW);
+        wa.gbp[s2] = cv.take(nb);
+        NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, nW * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, nb * 4, st));
     }
     wa.tile_begin[wa.n_slots] = total_tiles;
+    NCDE_REQUIRE(cv.used <= workspace_bytes, NCDE_ERR_WORKSPACE, "solve_bwd: workspace accounting error");
     NCDE_REQUIRE(gW[pl.F] != nullptr, NCDE_ERR_INVALID, "solve_bwd: gW of the final layer is null");
 
     const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
@@ -497,8 +621,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             {
                 ProfScope ps(NCDE_PROF_FIELD_BWD, st);
                 if (use_tc) {
-                    rc = tc_field_bwd(p, fa, st, &launches);
-                    if (rc != NCDE_OK) return rc;
+                    ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
+                    ta.dXT = stage + pl.dx_off;
+                    ta.gkT = gkT[i];
+                    tc_field_bwd_kernel<<<dim3(pl.n_hg, pl.n_bt), kTcThreads, pl.bwd_smem, st>>>(ta);
+                    ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
                     if (pl.TM == 8) field_bwd_kernel<8><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
@@ -518,14 +645,14 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             }
             {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
-                hidden_bwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem, st>>>(hb);
+                hidden_bwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem_bwd, st>>>(hb);
             }
             ++launches;
             if (pl.F > 0) {
                 for (int l = 0; l < pl.F; ++l) wa.actT[l] = stage + pl.act_off[l];
                 {
                     ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
-                    hidden_wgrad_kernel<<<total_tiles, kThreads, 0, st>>>(wa);
+                    hidden_wgrad_kernel<<<dim3(total_tiles, pl.wg_split), kThreads, 0, st>>>(wa);
                 }
                 ++launches;
             }
@@ -539,13 +666,20 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         }
         j_hi = j_lo;
     }
+    if (pl.F > 0) {
+        int nmax = 0;
+        for (int s2 = 0; s2 < wa.n_slots; ++s2) nmax = wa.Dout[s2] * wa.Din[s2] > nmax ? wa.Dout[s2] * wa.Din[s2] : nmax;
+        hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, st>>>(wa);
+        ++launches;
+    }
     // solution[0] = y0 (solvers.py:95): its gradient flows straight to z0
     from_feature_major_kernel<<<tg, tb, 0, st>>>(gyT, grad_out, grad_z0, pl.B, pl.Bp, pl.H);
     ++launches;
     {
         const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
         unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[pl.F], gbias[pl.F], pl.H,
-                                                                             pl.C, pl.Cp, pl.DF, pl.DFP, pl.Np, pl.n_bt);
+                                                                             pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF, pl.DFP,
+                                                                             pl.Np, pl.n_bt);
         ++launches;
     }
     NCDE_CUDA_OK(cudaGetLastError());

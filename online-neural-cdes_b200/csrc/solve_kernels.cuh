@@ -5,6 +5,8 @@
 //   * batch-split kernels ("hidden") read/write R consecutive rows of every feature as one segment, and
 //   * weight-stationary kernels ("field") stream 64-row chunks of every feature with 16-byte loads.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ncde {
@@ -40,6 +42,11 @@ struct HiddenFwdArgs {
     const float* kT[NCDE_MAX_STAGES];
     float* actT[NCDE_MAX_LAYERS + 1];  // actT[l] = [D[l] (padded to 4)][Bp], l = 0..F, for THIS stage
     float* dXT;                        // [Cp][Bp]
+    __nv_bfloat16* abf;                // [Bp][KP] bf16 row-major copy of the final-layer input (tensor-core path) or null
+    int KP;
+    int w_in_smem;                     // hidden weights are staged in shared memory for the whole launch
+    int wsm_off[NCDE_MAX_LAYERS];      // float offset of layer l's weights inside the shared staging area
+    int wsm_floats;                    // total floats staged (layers sharing a slot share the copy)
     PathArgs path;
 };
 
@@ -74,7 +81,11 @@ struct HiddenBwdArgs {
     int B, Bp, H, R, F, Dmax, DFP, n_hg;
     int D[NCDE_MAX_LAYERS + 1];
     int act[NCDE_MAX_LAYERS];
-    const float* W[NCDE_MAX_LAYERS];       // torch layout [D[l+1]][D[l]]
+    const float* W[NCDE_MAX_LAYERS];       // row-major [D[l+1]][ldi[l]] (packed copy, ldi = D[l] padded to 4)
+    int ldi[NCDE_MAX_LAYERS];
+    int w_in_smem;
+    int wsm_off[NCDE_MAX_LAYERS];
+    int wsm_floats;
     const float* P;                         // [n_hg][B][DFP]
     const float* actT[NCDE_MAX_LAYERS + 1]; // saved activations of this stage
     float* dpreT[NCDE_MAX_LAYERS];          // [D[l+1] pad4][Bp] scratch, consumed by hidden_wgrad
@@ -84,15 +95,20 @@ struct HiddenBwdArgs {
     float kcoef[NCDE_MAX_STAGES];           // gk_j += kcoef[j] * dzs
 };
 
+constexpr int kWgTile = 64;    // weight-gradient CTA tile (out x in)
+constexpr int kWgRows = 64;    // batch rows per staging chunk
+
 struct WgradArgs {
-    int B, Bp, n_slots;
+    int B, Bp, n_slots, n_split, rows_per_split;
     int tile_begin[NCDE_MAX_LAYERS + 1];
     int Dout[NCDE_MAX_LAYERS], Din[NCDE_MAX_LAYERS];
     int n_lay[NCDE_MAX_LAYERS];
     int lay[NCDE_MAX_LAYERS][NCDE_MAX_LAYERS];
     const float* dpreT[NCDE_MAX_LAYERS];  // per layer
     const float* actT[NCDE_MAX_LAYERS];   // per layer: its input
-    float* gW[NCDE_MAX_LAYERS];           // per slot
+    float* gWp[NCDE_MAX_LAYERS];          // per slot: [n_split][Dout][Din] partial accumulators (this CTA's split only)
+    float* gbp[NCDE_MAX_LAYERS];          // per slot: [n_split][Dout]
+    float* gW[NCDE_MAX_LAYERS];           // per slot: caller's gradient (torch layout), used by the final reduction
     float* gb[NCDE_MAX_LAYERS];           // per slot, nullable
 };
 
@@ -154,14 +170,24 @@ __device__ __forceinline__ float path_derivative(const PathArgs& p, int idx, flo
 // ---------------------------------------------------------------------------------------------------------------
 // hidden layer: WT[k*ld + o] = W[o*Din + k]; bp[o] = bias[o] (0 when absent / padded)
 __global__ void pack_hidden_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ WT,
-                                   float* __restrict__ bp, int Dout, int Din, int ld) {
+                                   float* __restrict__ bp, float* __restrict__ WR, int Dout, int Din, int ld, int ldi) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < Din * ld) {
         int k = idx / ld, o = idx % ld;
         WT[idx] = (o < Dout) ? W[(int64_t)o * Din + k] : 0.f;
     }
+    if (WR && idx < Dout * ldi) {
+        int o = idx / ldi, i = idx % ldi;
+        WR[idx] = (i < Din) ? W[(int64_t)o * Din + i] : 0.f;
+    }
     if (idx < ld) bp[idx] = (bias && idx < Dout) ? bias[idx] : 0.f;
 }
+
+// asynchronous 16-byte global->shared copy
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // final layer: n = h*Cp + c (c padded to Cp, h padded to n_hg*Hg); W3T[k*Np + n], W3R[n*DFP + k], b3p[n]
 __global__ void pack_final_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ W3T,
@@ -245,6 +271,13 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
     const int64_t b0 = (int64_t)blockIdx.x * R;
     float* buf0 = sm;
     float* buf1 = sm + (size_t)a.Dmax * R;
+    float* wsm = buf1 + (size_t)a.Dmax * R;
+    if (a.w_in_smem) {
+        // every distinct hidden weight matrix is copied once (asynchronously, overlapping steps 1-2 below); the packed
+        // matrices of the hidden layers are contiguous in the workspace, so this is one flat copy
+        const float* src = a.WT[0];
+        for (int i = tid * 4; i < a.wsm_floats; i += kThreads * 4) cp_async_16(wsm + i, src + i);
+    }
 
     // 1. stage input  zs[h][r]
     for (int idx = tid; idx < a.H * R; idx += kThreads) {
@@ -277,6 +310,7 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             if (b < a.B) a.dXT[(int64_t)c * a.Bp + b] = tmp[c * R + r];
         }
     }
+    if (a.w_in_smem) cp_async_wait_all_();
     __syncthreads();
     // 3. hidden layers
     const int RQ = R / 4;
@@ -284,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         const float* in = (l & 1) ? buf1 : buf0;
         float* out = (l & 1) ? buf0 : buf1;
         const int Din = a.D[l], Dout = a.D[l + 1], ld = a.ldw[l];
-        const float* __restrict__ WT = a.WT[l];
+        const float* __restrict__ WT = a.w_in_smem ? wsm + a.wsm_off[l] : a.WT[l];
         const float* __restrict__ bp = a.bp[l];
         for (int item = tid; item < Dout * RQ; item += kThreads) {
             const int o = item % Dout, q = item / Dout;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             float4 acc = make_float4(bias, bias, bias, bias);
 #pragma unroll 8
             for (int k = 0; k < Din; ++k) {
-                const float w = __ldg(WT + (size_t)k * ld + o);
+                const float w = WT[(size_t)k * ld + o];
                 const float4 x = *reinterpret_cast<const float4*>(in + k * R + q * 4);
                 acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
                 acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
@@ -310,6 +344,16 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             if (b < a.B) g[(int64_t)o * a.Bp + b] = out[o * R + r];
         }
         // `out` is read-only until the next layer finishes writing the other buffer: no extra barrier needed
+    }
+    if (a.abf) {
+        // bf16 row-major copy [b][k] (k padded with zeros to KP) for the tensor-core final layer
+        const float* last = (a.F & 1) ? buf1 : buf0;
+        const int DF = a.D[a.F];
+        for (int idx = tid; idx < R * a.KP; idx += kThreads) {
+            const int r = idx / a.KP, k = idx % a.KP;
+            const int64_t b = b0 + r;
+            if (b < a.B) a.abf[(size_t)b * a.KP + k] = __float2bfloat16(k < DF ? last[k * R + r] : 0.f);
+        }
     }
 }
 
@@ -532,8 +576,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     for (int64_t b0 = row_begin; b0 < row_end; b0 += kChunk) {
         for (int idx = tid; idx < DF * (kChunk / 4); idx += kThreads) {
             const int k = idx / (kChunk / 4), j = idx % (kChunk / 4);
-            reinterpret_cast<float4*>(As)[idx] =
-                __ldg(reinterpret_cast<const float4*>(a.actT + (size_t)k * a.Bp + b0) + j);
+            float4 x = __ldg(reinterpret_cast<const float4*>(a.actT + (size_t)k * a.Bp + b0) + j);
+            // batch padding holds uninitialised memory: zero it so that 0 * garbage cannot poison the weight gradient
+            const int64_t bb = b0 + j * 4;
+            if (bb + 0 >= a.B) x.x = 0.f;
+            if (bb + 1 >= a.B) x.y = 0.f;
+            if (bb + 2 >= a.B) x.z = 0.f;
+            if (bb + 3 >= a.B) x.w = 0.f;
+            reinterpret_cast<float4*>(As)[idx] = x;
         }
         for (int idx = tid; idx < a.Hg * kChunk; idx += kThreads) {
             const int hl = idx / kChunk, m = idx % kChunk;
@@ -685,23 +735,37 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
     const int64_t b0 = (int64_t)blockIdx.x * R;
     float* buf0 = sm;
     float* buf1 = sm + (size_t)a.Dmax * R;
+    float* wsm = buf1 + (size_t)a.Dmax * R;
+    if (a.w_in_smem) {
+        const float* src = a.W[0];
+        for (int i = tid * 4; i < a.wsm_floats; i += kThreads * 4) cp_async_16(wsm + i, src + i);
+    }
 
-    // 1. dL/d(final-layer input)[k][r] = sum_g P[g][b][k]
+    // 1. dL/d(final-layer input)[k][r] = sum_g P[g][b][k]: one float4 of k per thread, groups streamed 8 deep
     {
         const int DF = a.D[a.F];
-        for (int idx = tid; idx < R * DF; idx += kThreads) {
-            const int r = idx / DF, k = idx % DF;
+        const int K4 = a.DFP / 4;
+        for (int idx = tid; idx < R * K4; idx += kThreads) {
+            const int r = idx / K4, k4 = idx % K4;
             const int64_t b = b0 + r;
-            float s = 0.f;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b < a.B) {
-                const float* p = a.P + (size_t)b * a.DFP + k;
-                const size_t gs = (size_t)a.B * a.DFP;
+                const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)b * a.DFP) + k4;
+                const size_t gs = (size_t)a.B * a.DFP / 4;
 #pragma unroll 8
-                for (int g = 0; g < a.n_hg; ++g) s += __ldg(p + (size_t)g * gs);
+                for (int g = 0; g < a.n_hg; ++g) {
+                    const float4 v = __ldg(p + (size_t)g * gs);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
             }
-            buf0[k * R + r] = s;
+            const int k = k4 * 4;
+            if (k + 0 < DF) buf0[(k + 0) * R + r] = s.x;
+            if (k + 1 < DF) buf0[(k + 1) * R + r] = s.y;
+            if (k + 2 < DF) buf0[(k + 2) * R + r] = s.z;
+            if (k + 3 < DF) buf0[(k + 3) * R + r] = s.w;
         }
     }
+    if (a.w_in_smem) cp_async_wait_all_();
     __syncthreads();
     // 2. hidden layers, last to first.  cur = gradient w.r.t. the OUTPUT of layer l (post-activation)
     float* cur = buf0;
@@ -724,13 +788,14 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
         }
         __syncthreads();
         // d(in)[i][r] = sum_o dpre[o][r] * W[o][i]
-        const float* __restrict__ W = a.W[l];
+        const float* __restrict__ W = a.w_in_smem ? wsm + a.wsm_off[l] : a.W[l];
+        const int ldi = a.ldi[l];
         for (int item = tid; item < Din * RQ; item += kThreads) {
             const int i = item % Din, q = item / Din;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
             for (int o = 0; o < Dout; ++o) {
-                const float w = __ldg(W + (size_t)o * Din + i);
+                const float w = W[(size_t)o * ldi + i];
                 const float4 x = *reinterpret_cast<const float4*>(cur + o * R + q * 4);
                 acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
                 acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
@@ -755,78 +820,117 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// hidden_wgrad: weight-stationary.  CTA owns a 32x32 tile of one hidden weight matrix and reduces over the batch:
-//     gW[o][i] += sum_b dpre[o][b] * in[i][b] ;  gb[o] += sum_b dpre[o][b]
-// Layers that share a slot (the reference's repeated nn.Linear) are folded into the same tile, so the
-// accumulation into the shared gradient is race-free and ordered.
+// hidden_wgrad: weight-stationary and batch-split.  CTA (tile, split) owns a 64x64 tile of one hidden weight matrix
+// and the batch rows of one split:
+//     gWp[split][o][i] += sum_{b in split} dpre[o][b] * in[i][b] ;  gbp[split][o] += sum_b dpre[o][b]
+// Thread = 4 out x 4 in.  Layers that share a slot (the reference's repeated nn.Linear) are folded into the
+// same tile, so the accumulation into the shared gradient is race-free and ordered.  The per-split accumulators live in
+// the workspace across all stages (each is owned by exactly one CTA) and are summed once by hidden_wgrad_reduce.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) hidden_wgrad_kernel(const __grid_constant__ WgradArgs a) {
-    __shared__ float dS[32][kChunk + 1];
-    __shared__ float aS[32][kChunk + 1];
+    __shared__ __align__(16) float dS[kWgRows][kWgTile + 4];  // [b][o]
+    __shared__ __align__(16) float aS[kWgRows][kWgTile + 4];  // [b][i]
     const int tid = threadIdx.x;
     int slot = 0;
     while (slot + 1 < a.n_slots && (int)blockIdx.x >= a.tile_begin[slot + 1]) ++slot;
     const int tile = blockIdx.x - a.tile_begin[slot];
+    const int split = blockIdx.y;
     const int Dout = a.Dout[slot], Din = a.Din[slot];
-    const int tiles_i = (Din + 31) / 32;
-    const int o0 = (tile / tiles_i) * 32, i0 = (tile % tiles_i) * 32;
-    const int ty = tid / 16, tx = tid % 16;
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    float accb[2] = {0.f, 0.f};
+    const int tiles_i = (Din + kWgTile - 1) / kWgTile;
+    const int o0 = (tile / tiles_i) * kWgTile, i0 = (tile % tiles_i) * kWgTile;
+    const int ty = tid / 16, tx = tid % 16;  // 16 x 16 threads, each 4 x 4
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    float accb[4] = {0.f, 0.f, 0.f, 0.f};
+    const int row_begin = split * a.rows_per_split;
+    const int row_end = min(a.B, row_begin + a.rows_per_split);
     for (int li = 0; li < a.n_lay[slot]; ++li) {
         const int l = a.lay[slot][li];
         const float* __restrict__ dT = a.dpreT[l];
         const float* __restrict__ xT = a.actT[l];
-        for (int bc = 0; bc < a.B; bc += kChunk) {
-            for (int idx = tid; idx < 32 * kChunk; idx += kThreads) {
-                const int rr = idx / kChunk, bb = idx % kChunk;
+        for (int bc = row_begin; bc < row_end; bc += kWgRows) {
+            // global reads are coalesced along the batch; the tiles are stored transposed ([b][feature])
+            for (int idx = tid; idx < kWgTile * kWgRows; idx += kThreads) {
+                const int f = idx / kWgRows, bb = idx % kWgRows;
                 const int b = bc + bb;
-                dS[rr][bb] = (o0 + rr < Dout && b < a.B) ? dT[(size_t)(o0 + rr) * a.Bp + b] : 0.f;
-                aS[rr][bb] = (i0 + rr < Din && b < a.B) ? xT[(size_t)(i0 + rr) * a.Bp + b] : 0.f;
+                const bool in_rows = b < row_end;
+                dS[bb][f] = (in_rows && o0 + f < Dout) ? dT[(size_t)(o0 + f) * a.Bp + b] : 0.f;
+                aS[bb][f] = (in_rows && i0 + f < Din) ? xT[(size_t)(i0 + f) * a.Bp + b] : 0.f;
             }
             __syncthreads();
 #pragma unroll 8
-            for (int bb = 0; bb < kChunk; ++bb) {
-                const float d0 = dS[ty * 2][bb], d1 = dS[ty * 2 + 1][bb];
-                const float x0 = aS[tx * 2][bb], x1 = aS[tx * 2 + 1][bb];
-                acc[0][0] = fmaf(d0, x0, acc[0][0]); acc[0][1] = fmaf(d0, x1, acc[0][1]);
-                acc[1][0] = fmaf(d1, x0, acc[1][0]); acc[1][1] = fmaf(d1, x1, acc[1][1]);
-                accb[0] += d0; accb[1] += d1;
+            for (int bb = 0; bb < kWgRows; ++bb) {
+                const float4 d = *reinterpret_cast<const float4*>(&dS[bb][ty * 4]);
+                const float4 x = *reinterpret_cast<const float4*>(&aS[bb][tx * 4]);
+                const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[u][0] = fmaf(dv[u], x.x, acc[u][0]); acc[u][1] = fmaf(dv[u], x.y, acc[u][1]);
+                    acc[u][2] = fmaf(dv[u], x.z, acc[u][2]); acc[u][3] = fmaf(dv[u], x.w, acc[u][3]);
+                    accb[u] += dv[u];
+                }
             }
             __syncthreads();
         }
     }
+    float* gWp = a.gWp[slot] + (size_t)split * Dout * Din;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int o = o0 + ty * 2 + u;
+    for (int u = 0; u < 4; ++u) {
+        const int o = o0 + ty * 4 + u;
         if (o >= Dout) continue;
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int i = i0 + tx * 2 + v;
-            if (i < Din) a.gW[slot][(size_t)o * Din + i] += acc[u][v];
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + tx * 4 + v;
+            if (i < Din) gWp[(size_t)o * Din + i] += acc[u][v];
         }
-        if (a.gb[slot] && i0 == 0 && tx == 0) a.gb[slot][o] += accb[u];
+        if (i0 == 0 && tx == 0) a.gbp[slot][(size_t)split * Dout + o] += accb[u];
     }
 }
 
-// final-layer gradient: gW[(h*C+c)*DF + k] += sum_bt dW3acc[bt][(h*Cp+c)*DFP + k]; same for the bias
+// gW[slot] += sum_split gWp[slot][split] (once per backward pass)
+__global__ void hidden_wgrad_reduce_kernel(const __grid_constant__ WgradArgs a) {
+    const int slot = blockIdx.y;
+    const int n = a.Dout[slot] * a.Din[slot];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) {
+        float s = 0.f;
+        for (int sp = 0; sp < a.n_split; ++sp) s += a.gWp[slot][(size_t)sp * n + idx];
+        a.gW[slot][idx] += s;
+    }
+    if (a.gb[slot] && idx < a.Dout[slot]) {
+        float s = 0.f;
+        for (int sp = 0; sp < a.n_split; ++sp) s += a.gbp[slot][(size_t)sp * a.Dout[slot] + idx];
+        a.gb[slot][idx] += s;
+    }
+}
+
+// packed row index of (h, c): h-groups of Hg rows-of-Cp, each group padded to Npad rows
+__host__ __device__ inline int64_t packed_n(int h, int c, int Cp, int Hg, int Npad) {
+    return (int64_t)(h / Hg) * Npad + (int64_t)(h % Hg) * Cp + c;
+}
+
 __global__ void unpack_final_grad_kernel(const float* __restrict__ dW3acc, const float* __restrict__ db3acc,
-                                         float* __restrict__ gW, float* __restrict__ gb, int H, int C, int Cp, int DF,
-                                         int DFP, int Np, int n_bt) {
+                                         float* __restrict__ gW, float* __restrict__ gb, int H, int C, int Cp, int Hg,
+                                         int Npad, int DF, int DFP, int Np, int n_bt) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)H * C * DF;
     if (idx < total) {
         const int k = (int)(idx % DF);
         const int hc = (int)(idx / DF);
         const int h = hc / C, c = hc % C;
+        const int64_t n = packed_n(h, c, Cp, Hg, Npad);
         float s = 0.f;
-        for (int bt = 0; bt < n_bt; ++bt) s += dW3acc[((size_t)bt * Np + (size_t)h * Cp + c) * DFP + k];
+        for (int bt = 0; bt < n_bt; ++bt) s += dW3acc[((size_t)bt * Np + n) * DFP + k];
         gW[idx] += s;
     }
     if (gb && idx < (int64_t)H * C) {
         const int h = (int)idx / C, c = (int)idx % C;
+        const int64_t n = packed_n(h, c, Cp, Hg, Npad);
         float s = 0.f;
-        for (int bt = 0; bt < n_bt; ++bt) s += db3acc[(size_t)bt * Np + (size_t)h * Cp + c];
+        for (int bt = 0; bt < n_bt; ++bt) s += db3acc[(size_t)bt * Np + n];
         gb[idx] += s;
     }
 }
