@@ -80,6 +80,36 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldw<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -197,6 +227,20 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_sa
     }
 }
 
+// sum_j tanh(D[row][col0 + j] + b3[j]) * dX[j][row] over W consecutive channels; dx points at dXs[c0][row]
+template <int W>
+__device__ __forceinline__ float fwd_chunk(uint32_t taddr, const float* __restrict__ b3, const float* __restrict__ dx) {
+    float v[W];
+    tmem_ldw<W>(taddr, v);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; j += 2) {
+        acc0 = fmaf(tanh_fast(v[j] + b3[j]), dx[j * kTcM], acc0);
+        acc1 = fmaf(tanh_fast(v[j + 1] + b3[j + 1]), dx[(j + 1) * kTcM], acc1);
+    }
+    return acc0 + acc1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward:  k[b, h] = sum_c tanh( a[b,:] . W3[(h,c),:] + b3[(h,c)] ) * dX[b, c]
 // CTA (g, bt): W slice of h-group g resident in shared memory; 128-row tiles of the batch stream through.
@@ -232,11 +276,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
 
     const int wg = warp >> 2;                    // warp-group 0/1
     const int row = (warp & 3) * 32 + lane;      // TMEM lane == row inside the tile
-    const int S = a.Hg * a.Cp;                   // valid columns
-    // column range of this warp-group: whole h's when Hg is even, else split the channel range of the single h
-    int col_begin, col_end;
-    if (a.Hg >= 2) { col_begin = (a.Hg / 2) * a.Cp * wg; col_end = wg == 0 ? (a.Hg / 2) * a.Cp : S; }
-    else { const int half = ((a.Cp / 2 + 3) / 4) * 4; col_begin = wg == 0 ? 0 : half; col_end = wg == 0 ? half : S; }
+    // share of this warp-group: a set of whole h's when Hg >= 2, else half of the channels of the single h
+    int h_begin, h_end, c_begin, c_end;
+    if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
+    else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
 
     uint32_t phase = 0;
     const int64_t row_begin = (int64_t)bt * a.Bt;
@@ -257,26 +300,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
         phase ^= 1;
         tc_fence_after();
 
-        // epilogue
+        // epilogue: per h of this warp-group, a branch-free sweep over its channels (static smem offsets -> ILP)
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        int hl = col_begin / a.Cp, c = col_begin % a.Cp;
-        float acc = 0.f;
-        for (int n0 = col_begin; n0 < col_end; n0 += 16) {
-            float v[16];
-            tmem_ld16(lane_addr + (uint32_t)n0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + j;
-                if (n < col_end) {
-                    acc = fmaf(tanh_fast(v[j] + b3s[n]), dXs[c * kTcM + row], acc);
-                    if (++c == a.Cp) {  // end of this h: publish the partial sum
-                        part[(wg * a.Hg + hl) * kTcM + row] = acc;
-                        acc = 0.f; c = 0; ++hl;
-                    }
-                }
-            }
+        for (int hl = h_begin; hl < h_end; ++hl) {
+            float acc = 0.f;
+            const int colbase = hl * a.Cp;
+            int c0 = c_begin;
+            for (; c0 + 32 <= c_end; c0 += 32) acc += fwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row);
+            for (; c0 + 8 <= c_end; c0 += 8) acc += fwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row);
+            part[(wg * a.Hg + hl) * kTcM + row] = acc;
         }
-        if (c != 0) part[(wg * a.Hg + hl) * kTcM + row] = acc;  // Hg == 1: each warp-group holds half of the channels
         tc_fence_before();
         __syncthreads();
         // combine and write k^T[h][b]
@@ -311,6 +344,68 @@ static inline size_t tc_fwd_smem_bytes(int Npad, int KP, int Hg, int Cp) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kTcDwCol = 256;
 
+// Column sums of a W-column x 32-row (lane) block by recursive halving: after log2(W) exchange steps every lane holds
+// one column summed over a lane subset, the remaining levels are plain xor-reductions.  W + log2(32/W) shuffles
+// instead of 5 W.  dst points at the first of the W columns of this warp's accumulator row.
+template <int W>
+__device__ __forceinline__ void colsum_butterfly(float (&v)[W], int lane, float* dst) {
+    const uint32_t full = 0xffffffffu;
+    int col = 0;
+    int bit = 16;
+#pragma unroll
+    for (int width = W; width > 1; width >>= 1) {
+        const int half = width >> 1;
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = up ? v[j] : v[j + half];
+            const float keep = up ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, bit);
+        }
+        col += up ? half : 0;
+        bit >>= 1;
+    }
+    int low = 0;
+#pragma unroll
+    for (; bit >= 1; bit >>= 1) { v[0] += __shfl_xor_sync(full, v[0], bit); low |= bit; }
+    if ((lane & low) == 0) dst[col] += v[0];
+}
+
+// One W-column chunk of epilogue 1 for TMEM lane `row`: G = gk * dX * sech^2(pre + b3) -> bf16 into the swizzled G
+// tile (16-byte stores, n0 is a multiple of 8) and column sums for the bias gradient.
+template <int W>
+__device__ __forceinline__ void bwd_chunk(uint32_t taddr, const float* __restrict__ b3, const float* __restrict__ dx,
+                                          float gk, bool row_ok, uint8_t* Gs, int row, int n0, float* bsum_row, int lane) {
+    float v[W];
+    tmem_ldw<W>(taddr, v);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        float t, q;
+        tanh_sech2(v[j] + b3[j], t, q);
+        const float gv = gk * dx[j * kTcM] * q;
+        v[j] = row_ok ? gv : 0.f;   // select, not multiply: padded rows hold uninitialised dX
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < W / 8; ++j8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(Gs + sw128_off(row, (n0 >> 3) + j8, kTcM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if constexpr (W == 32) {
+        float lo[16], hi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { lo[j] = v[j]; hi[j] = v[16 + j]; }
+        colsum_butterfly<16>(lo, lane, bsum_row + n0);
+        colsum_butterfly<16>(hi, lane, bsum_row + n0 + 16);
+    } else {
+        colsum_butterfly<W>(v, lane, bsum_row + n0);
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -342,11 +437,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int S = a.Hg * a.Cp;
-    const int split = (Npad / 2) & ~15;                 // column split between the warp-groups, multiple of 16
+    const int S = a.Hg * a.Cp;                          // valid columns (multiple of 8); [S, Npad) is zero padding
+    int h_begin, h_end, c_begin, c_end;
+    if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
+    else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+    // column split of the final dW^T read-out (16-column chunks)
+    const int split = (Npad / 2) & ~15;
     const int col_begin = wg == 0 ? 0 : split;
     const int col_end = wg == 0 ? split : Npad;
-    const uint32_t full = 0xffffffffu;
+    if (S < Npad && tid < kTcM) *reinterpret_cast<uint4*>(Gs + sw128_off(tid, S >> 3, kTcM)) = make_uint4(0, 0, 0, 0);
 
     uint32_t phase = 0;
     bool first_tile = true;
@@ -367,70 +466,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
         phase ^= 1;
         tc_fence_after();
 
-        // ---- epilogue 1: G tile + bias-gradient column sums ----
+        // ---- epilogue 1: G tile + bias-gradient column sums; per h, branch-free over the channels ----
         const int64_t b = b0 + row;
         const bool row_ok = b < a.B;
-        {
-            int hl = col_begin / a.Cp, c = col_begin % a.Cp;
-            int h = g * a.Hg + hl;
-            float gk = (row_ok && hl < a.Hg && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
-            for (int n0 = col_begin; n0 < col_end; n0 += 16) {
-                float v[16];
-                tmem_ld16(lane_addr + (uint32_t)n0, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + j;
-                    float gv = 0.f;
-                    if (n < S) {
-                        float t, q;
-                        tanh_sech2(v[j] + b3s[n], t, q);
-                        gv = gk * dXs[c * kTcM + row] * q;
-                        if (++c == a.Cp) {
-                            c = 0; ++hl; h = g * a.Hg + hl;
-                            gk = (row_ok && hl < a.Hg && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
-                        }
-                    }
-                    v[j] = row_ok ? gv : 0.f;
-                }
-                // bf16 pack, two 16-byte stores into the swizzled G tile
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                    pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                *reinterpret_cast<uint4*>(Gs + sw128_off(row, n0 >> 3, kTcM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(Gs + sw128_off(row, (n0 >> 3) + 1, kTcM)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                // column sums over the 32 rows of this warp: halving butterfly, 16 shuffles
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float send = (lane & 16) ? v[j] : v[j + 8];
-                    const float keep = (lane & 16) ? v[j + 8] : v[j];
-                    v[j] = keep + __shfl_xor_sync(full, send, 16);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float send = (lane & 8) ? v[j] : v[j + 4];
-                    const float keep = (lane & 8) ? v[j + 4] : v[j];
-                    v[j] = keep + __shfl_xor_sync(full, send, 8);
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float send = (lane & 4) ? v[j] : v[j + 2];
-                    const float keep = (lane & 4) ? v[j + 2] : v[j];
-                    v[j] = keep + __shfl_xor_sync(full, send, 4);
-                }
-                {
-                    const float send = (lane & 2) ? v[0] : v[1];
-                    const float keep = (lane & 2) ? v[1] : v[0];
-                    v[0] = keep + __shfl_xor_sync(full, send, 2);
-                }
-                v[0] += __shfl_xor_sync(full, v[0], 1);
-                if ((lane & 1) == 0) {
-                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    bsum[warp * Npad + n0 + col] += v[0];
-                }
-            }
+        for (int hl = h_begin; hl < h_end; ++hl) {
+            const int h = g * a.Hg + hl;
+            const float gk = (row_ok && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
+            const int colbase = hl * a.Cp;
+            int c0 = c_begin;
+            for (; c0 + 32 <= c_end; c0 += 32)
+                bwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row, gk, row_ok, Gs, row,
+                              colbase + c0, bsum + warp * Npad, lane);
+            for (; c0 + 8 <= c_end; c0 += 8)
+                bwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row, gk, row_ok, Gs, row,
+                             colbase + c0, bsum + warp * Npad, lane);
         }
         fence_async_smem();
         tc_fence_before();
@@ -490,8 +539,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
                 tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
+                    // exactly one thread ever adds to this element in this launch: a reduction without return value is
+                    // deterministic and does not stall on the read
                     float* p = a.dW3acc + (((size_t)bt * a.n_hg + g) * Npad + n0 + j) * a.DFP + k;
-                    *p += v[j];
+                    atomicAdd(p, v[j]);
                 }
             }
         }
@@ -499,7 +550,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) s += bsum[w * Npad + n];
-            a.db3acc[((size_t)bt * a.n_hg + g) * Npad + n] += s;
+            atomicAdd(a.db3acc + ((size_t)bt * a.n_hg + g) * Npad + n, s);
         }
     }
     tc_fence_before();

@@ -75,7 +75,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
                  "solve: method %d is not a fixed-grid method", p->method);
     pl->B = (int)p->B; pl->H = p->H; pl->C = p->C;
     pl->Bp = (int)round_up(p->B, kTcM);
-    pl->Cp = (int)round_up(p->C, 4);
+    // channels padded to 4 (float4 epilogues) or 8 (tensor-core path: 16-byte bf16 chunks per h)
+    pl->Cp = (int)round_up(p->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
     pl->F = m.n_layers - 1;
     pl->n_stages = p->method == NCDE_RK4_38 ? 4 : 1;
     NCDE_REQUIRE(m.in_dim[0] == p->H, NCDE_ERR_INVALID, "solve: first layer must take H=%d inputs, takes %d", p->H,
@@ -210,7 +211,10 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
         const size_t wmax = pl->wt_floats > pl->wr_floats ? pl->wt_floats : pl->wr_floats;
         pl->w_in_smem = pl->F > 0 && (pl->hid_smem + wmax * 4) <= 200 * 1024;
         pl->hid_smem_fwd = pl->hid_smem + (pl->w_in_smem ? round_up(pl->wt_floats, 4) * 4 : 0);
-        pl->hid_smem_bwd = pl->hid_smem + (pl->w_in_smem ? round_up(pl->wr_floats, 4) * 4 : 0);
+        const size_t acts_bytes = (size_t)pl->F * pl->Dmax * R * 4;
+        if (pl->hid_smem + acts_bytes + wmax * 4 > 200 * 1024) pl->w_in_smem = 0;
+        pl->hid_smem_fwd = pl->hid_smem + (pl->w_in_smem ? round_up(pl->wt_floats, 4) * 4 : 0);
+        pl->hid_smem_bwd = pl->hid_smem + acts_bytes + (pl->w_in_smem ? round_up(pl->wr_floats, 4) * 4 : 0);
     }
     {
         int tiles = 0;
@@ -246,6 +250,12 @@ static size_t fwd_workspace_floats(const Plan& pl, int need_saved_scratch) {
     size_t n = pl.wpack_floats + per;
     n += (size_t)(2 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
     if (need_saved_scratch) n += pl.stage_floats + per;
+    return n;
+}
+static size_t fwd_workspace_extra_floats(const Plan& pl, int64_t n_steps, int need_saved_scratch) {
+    size_t per = 256 / 4;
+    size_t n = (size_t)n_steps * pl.n_stages + per;                                  // device copy of the stage times
+    if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * pl.Cp * pl.Bp + per;  // dX/dt of every stage
     return n;
 }
 static size_t bwd_workspace_floats(const Plan& pl) {
@@ -363,7 +373,8 @@ extern "C" size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad)
 extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward) {
     Plan pl;
     if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
-    size_t fl = backward ? bwd_workspace_floats(pl) : fwd_workspace_floats(pl, 1);
+    size_t fl = backward ? bwd_workspace_floats(pl)
+                         : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
 }
 
@@ -378,8 +389,9 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     if (rc != NCDE_OK) return rc;
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
-    NCDE_REQUIRE(workspace_bytes >= fwd_workspace_floats(pl, !need_grad) * 4, NCDE_ERR_WORKSPACE,
-                 "solve_fwd: workspace of %zu bytes is too small", workspace_bytes);
+    NCDE_REQUIRE(workspace_bytes >= (fwd_workspace_floats(pl, !need_grad) +
+                                     fwd_workspace_extra_floats(pl, p->grid.n_steps, !need_grad)) * 4,
+                 NCDE_ERR_WORKSPACE, "solve_fwd: workspace of %zu bytes is too small", workspace_bytes);
     NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 || p->precision == NCDE_PREC_BF16, NCDE_ERR_INVALID, "solve_fwd: bad precision");
     cudaStream_t st = (cudaStream_t)stream;
     int64_t launches = 0;
@@ -392,6 +404,9 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     float* kT[NCDE_MAX_STAGES] = {};
     for (int i = 0; i < NS; ++i) kT[i] = cv.take((size_t)pl.H * pl.Bp);
     float* scratch_stage = need_grad ? nullptr : cv.take(pl.stage_floats);
+    const int64_t n_st_total = g.n_steps * NS;
+    float* d_stage_t = cv.take((size_t)(n_st_total > 0 ? n_st_total : 1));
+    float* dx_all = need_grad ? nullptr : cv.take((size_t)n_st_total * pl.Cp * pl.Bp);
 
     rc = pack_weights(p, pl, wpack, 0, st, &launches);
     if (rc != NCDE_OK) return rc;
@@ -429,6 +444,21 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     fill_tc_args(ta, pl, wpack);
     ha.KP = pl.KP;
 
+    // dX/dt for every stage of the grid in one launch (off the sequential chain)
+    if (n_st_total > 0) {
+        NCDE_CUDA_OK(cudaMemcpyAsync(d_stage_t, g.stage_t, (size_t)n_st_total * 4, cudaMemcpyHostToDevice, st));
+        DxAllArgs da;
+        memset(&da, 0, sizeof(da));
+        da.B = pl.B; da.Bp = pl.Bp; da.C = pl.C; da.Cp = pl.Cp;
+        da.path = ha.path;
+        da.stage_t = d_stage_t;
+        da.dx_base = need_grad ? (float*)saved + pl.dx_off : dx_all;
+        da.stage_stride = need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp;
+        NCDE_REQUIRE(n_st_total <= 2147483647 && ceil_div(pl.B, 32) <= 65535, NCDE_ERR_UNSUPPORTED, "solve_fwd: grid too large");
+        dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
+        ++launches;
+    }
+
     static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
     int cur = 0;
     int64_t j_out = 1;
@@ -440,7 +470,8 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             ha.dt = dt;
             ha.yT = yT[cur];
             for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
-            ha.dXT = stage + pl.dx_off;
+            float* dx_stage = need_grad ? stage + pl.dx_off : dx_all + (size_t)(s * NS + i) * pl.Cp * pl.Bp;
+            ha.dXT = nullptr;  // precomputed by dx_all_kernel
             ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
             ha.path.t = g.stage_t[s * NS + i];
             {
@@ -449,13 +480,13 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             }
             ++launches;
             fa.actT = stage + pl.act_off[pl.F];
-            fa.dXT = stage + pl.dx_off;
+            fa.dXT = dx_stage;
             fa.koutT = kT[i];
             {
                 ProfScope ps(NCDE_PROF_FIELD_FWD, st);
                 if (use_tc) {
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
-                    ta.dXT = stage + pl.dx_off;
+                    ta.dXT = dx_stage;
                     ta.koutT = kT[i];
                     tc_field_fwd_kernel<<<dim3(pl.n_hg, pl.n_bt), kTcThreads, pl.fwd_smem, st>>>(ta);
                     ++launches;

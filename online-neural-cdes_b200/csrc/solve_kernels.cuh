@@ -166,6 +166,56 @@ __device__ __forceinline__ float path_derivative(const PathArgs& p, int idx, flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// dx_all: dX/dt at EVERY stage time of the fixed grid in one launch (it depends on the path only, not on the state,
+// so it is taken off the sequential stage chain).  CTA (stage, 32-row tile): knot lookup once (bucketize - 1 clamp,
+// interpolation_linear.py:216), gather / Horner, transpose through shared memory so that both the read (channels
+// contiguous) and the write (batch contiguous, feature-major) are coalesced.
+// ---------------------------------------------------------------------------------------------------------------
+struct DxAllArgs {
+    int B, Bp, C, Cp;
+    PathArgs path;             // path.t unused
+    const float* stage_t;      // device [n_stages_total]
+    float* dx_base;            // first stage's dXT
+    size_t stage_stride;       // floats between consecutive stages' dXT
+};
+
+__global__ void __launch_bounds__(256) dx_all_kernel(const __grid_constant__ DxAllArgs a) {
+    __shared__ float tile[32][129];
+    __shared__ int s_idx;
+    __shared__ float s_frac;
+    const int st = blockIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.y * 32;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const float t = a.stage_t[st];
+        const int idx = knot_index<float>(a.path.knots, a.path.K, t);
+        s_idx = idx;
+        s_frac = __fsub_rn(t, a.path.knots[idx]);
+    }
+    __syncthreads();
+    const int idxk = s_idx;
+    const float frac = s_frac;
+    float* out = a.dx_base + (size_t)st * a.stage_stride;
+    for (int c0 = 0; c0 < a.Cp; c0 += 128) {
+        const int cw = min(128, a.Cp - c0);
+        for (int i = tid; i < 32 * cw; i += 256) {
+            const int r = i / cw, c = c0 + i % cw;
+            const int64_t b = b0 + r;
+            float v = 0.f;
+            if (b < a.B && c < a.C) v = path_derivative(a.path, idxk, frac, b, c, a.C);
+            tile[r][c - c0] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < 32 * cw; i += 256) {
+            const int c = i / 32, r = i % 32;
+            const int64_t b = b0 + r;
+            if (b < a.B) out[(size_t)(c0 + c) * a.Bp + b] = tile[r][c];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weight packing
 // ---------------------------------------------------------------------------------------------------------------
 // hidden layer: WT[k*ld + o] = W[o*Din + k]; bp[o] = bias[o] (0 when absent / padded)
@@ -259,6 +309,39 @@ __global__ void add_out_grad_kernel(float* __restrict__ gyT, const float* __rest
     }
 }
 
+// acc[0..3] += sum_k w[k * ldk] * x[k * R .. +3]: one output feature for four batch rows.  Loads are issued in batches
+// of 8 before the FMAs, two accumulator sets halve the dependent chain.  SMEM selects shared vs read-only global
+// weights at compile time (a runtime pointer select would degrade every load to a generic LD).
+template <bool SMEM>
+__device__ __forceinline__ float4 matvec4(const float* __restrict__ w, int ldk, const float* __restrict__ x, int R, int n,
+                                          float4 acc) {
+    float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= n; k += 8) {
+        float wv[8];
+        float4 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            wv[u] = SMEM ? w[(size_t)(k + u) * ldk] : __ldg(w + (size_t)(k + u) * ldk);
+            xv[u] = *reinterpret_cast<const float4*>(x + (k + u) * R);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            acc.x = fmaf(wv[u], xv[u].x, acc.x); acc.y = fmaf(wv[u], xv[u].y, acc.y);
+            acc.z = fmaf(wv[u], xv[u].z, acc.z); acc.w = fmaf(wv[u], xv[u].w, acc.w);
+            acc2.x = fmaf(wv[u + 1], xv[u + 1].x, acc2.x); acc2.y = fmaf(wv[u + 1], xv[u + 1].y, acc2.y);
+            acc2.z = fmaf(wv[u + 1], xv[u + 1].z, acc2.z); acc2.w = fmaf(wv[u + 1], xv[u + 1].w, acc2.w);
+        }
+    }
+    for (; k < n; ++k) {
+        const float wk = SMEM ? w[(size_t)k * ldk] : __ldg(w + (size_t)k * ldk);
+        const float4 xk = *reinterpret_cast<const float4*>(x + k * R);
+        acc.x = fmaf(wk, xk.x, acc.x); acc.y = fmaf(wk, xk.y, acc.y);
+        acc.z = fmaf(wk, xk.z, acc.z); acc.w = fmaf(wk, xk.w, acc.w);
+    }
+    return make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // hidden_fwd: batch-split.  One CTA owns R rows: forms the RK stage input, evaluates dX/dt at the stage time
 // (knot lookup + gather / Horner) and runs the hidden Linear+activation layers.  Everything is written
@@ -291,8 +374,8 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         }
         buf0[h * R + r] = v;
     }
-    // 2. dX/dt at the stage time -> dXT[c][b] (zero in the padded channels)
-    {
+    // 2. dX/dt at the stage time -> dXT[c][b] (zero in the padded channels); skipped when dx_all_kernel already did it
+    if (a.dXT) {
         const int idxk = knot_index<float>(a.path.knots, a.path.K, a.path.t);
         const float frac = __fsub_rn(a.path.t, a.path.knots[idxk]);
         float* tmp = buf1;  // [Cp][R]
@@ -318,19 +401,13 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         const float* in = (l & 1) ? buf1 : buf0;
         float* out = (l & 1) ? buf0 : buf1;
         const int Din = a.D[l], Dout = a.D[l + 1], ld = a.ldw[l];
-        const float* __restrict__ WT = a.w_in_smem ? wsm + a.wsm_off[l] : a.WT[l];
         const float* __restrict__ bp = a.bp[l];
         for (int item = tid; item < Dout * RQ; item += kThreads) {
             const int o = item % Dout, q = item / Dout;
             const float bias = bp[o];
             float4 acc = make_float4(bias, bias, bias, bias);
-#pragma unroll 8
-            for (int k = 0; k < Din; ++k) {
-                const float w = WT[(size_t)k * ld + o];
-                const float4 x = *reinterpret_cast<const float4*>(in + k * R + q * 4);
-                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
-                acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
-            }
+            if (a.w_in_smem) acc = matvec4<true>(wsm + a.wsm_off[l] + o, ld, in + q * 4, R, Din, acc);
+            else acc = matvec4<false>(a.WT[l] + o, ld, in + q * 4, R, Din, acc);
             const int act = a.act[l];
             acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
             acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
@@ -707,17 +784,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
             float* wrow = a.dW3acc + ((size_t)bt * a.Np + (size_t)g * S + nt * 4 + j) * DFP;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float4* p = reinterpret_cast<float4*>(wrow + q * QS + kw * 4);
-                float4 v = *p;
-                v.x += accw[j][q * 4 + 0]; v.y += accw[j][q * 4 + 1]; v.z += accw[j][q * 4 + 2]; v.w += accw[j][q * 4 + 3];
-                *p = v;
+                // single writer per element: reductions without return value (no stall on the read, deterministic)
+                float* p = wrow + q * QS + kw * 4;
+                atomicAdd(p + 0, accw[j][q * 4 + 0]); atomicAdd(p + 1, accw[j][q * 4 + 1]);
+                atomicAdd(p + 2, accw[j][q * 4 + 2]); atomicAdd(p + 3, accw[j][q * 4 + 3]);
             }
         }
         if (kw == 0) {
-            float4* p = reinterpret_cast<float4*>(a.db3acc + (size_t)bt * a.Np + (size_t)g * S + nt * 4);
-            float4 v = *p;
-            v.x += accb[0]; v.y += accb[1]; v.z += accb[2]; v.w += accb[3];
-            *p = v;
+            float* p = a.db3acc + (size_t)bt * a.Np + (size_t)g * S + nt * 4;
+            atomicAdd(p + 0, accb[0]); atomicAdd(p + 1, accb[1]); atomicAdd(p + 2, accb[2]); atomicAdd(p + 3, accb[3]);
         }
     }
 }
@@ -735,13 +810,39 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
     const int64_t b0 = (int64_t)blockIdx.x * R;
     float* buf0 = sm;
     float* buf1 = sm + (size_t)a.Dmax * R;
-    float* wsm = buf1 + (size_t)a.Dmax * R;
+    float* acts = buf1 + (size_t)a.Dmax * R;            // [F][Dmax][R] saved layer outputs of these rows
+    float* wsm = acts + (size_t)a.F * a.Dmax * R;
+    // everything this kernel will need from global memory is requested up front (asynchronously):
+    //   the saved outputs of every hidden layer (for act'), the weights, and (below) gy / gk for the final update
+    for (int l = 0; l < a.F; ++l) {
+        const float* __restrict__ src = a.actT[l + 1];
+        const int Dout = a.D[l + 1];
+        for (int i = tid; i < Dout * (R / 4); i += kThreads) {
+            const int o = i / (R / 4), q = i % (R / 4);
+            if (b0 + q * 4 < a.Bp) cp_async_16(acts + ((size_t)l * a.Dmax + o) * R + q * 4, src + (size_t)o * a.Bp + b0 + q * 4);
+        }
+    }
     if (a.w_in_smem) {
         const float* src = a.W[0];
         for (int i = tid * 4; i < a.wsm_floats; i += kThreads * 4) cp_async_16(wsm + i, src + i);
     }
+    // gy / gk elements this thread updates at the end (fast path: at most 4 per thread)
+    const bool few = a.H * R <= 4 * kThreads;
+    float pre_gy[4], pre_gk[4][3];
+    if (few) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * kThreads;
+            const int h = idx / R, r = idx % R;
+            const bool ok = idx < a.H * R && b0 + r < a.B;
+            const size_t off = (size_t)h * a.Bp + b0 + r;
+            pre_gy[e] = ok ? a.gyT[off] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) pre_gk[e][j] = (ok && j < a.n_k && a.kcoef[j] != 0.f) ? a.gkT[j][off] : 0.f;
+        }
+    }
 
-    // 1. dL/d(final-layer input)[k][r] = sum_g P[g][b][k]: one float4 of k per thread, groups streamed 8 deep
+    // 1. dL/d(final-layer input)[k][r] = sum_g P[g][b][k]: one float4 of k per thread, groups streamed 16 deep
     {
         const int DF = a.D[a.F];
         const int K4 = a.DFP / 4;
@@ -752,7 +853,7 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
             if (b < a.B) {
                 const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)b * a.DFP) + k4;
                 const size_t gs = (size_t)a.B * a.DFP / 4;
-#pragma unroll 8
+#pragma unroll 16
                 for (int g = 0; g < a.n_hg; ++g) {
                     const float4 v = __ldg(p + (size_t)g * gs);
                     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -765,7 +866,7 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
             if (k + 3 < DF) buf0[(k + 3) * R + r] = s.w;
         }
     }
-    if (a.w_in_smem) cp_async_wait_all_();
+    cp_async_wait_all_();
     __syncthreads();
     // 2. hidden layers, last to first.  cur = gradient w.r.t. the OUTPUT of layer l (post-activation)
     float* cur = buf0;
@@ -773,7 +874,7 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
     for (int l = a.F - 1; l >= 0; --l) {
         const int Din = a.D[l], Dout = a.D[l + 1];
         // dpre = cur * act'(out), in place in `cur`, and feature-major to global for the weight gradient
-        const float* __restrict__ outT = a.actT[l + 1];
+        const float* __restrict__ outs = acts + (size_t)l * a.Dmax * R;
         float* __restrict__ dpreT = a.dpreT[l];
         const int act = a.act[l];
         for (int idx = tid; idx < Dout * R; idx += kThreads) {
@@ -781,31 +882,41 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
             const int64_t b = b0 + r;
             float v = 0.f;
             if (b < a.B) {
-                v = cur[idx] * act_grad_from_output(outT[(size_t)o * a.Bp + b], act);
+                v = cur[idx] * act_grad_from_output(outs[idx], act);
                 dpreT[(size_t)o * a.Bp + b] = v;
             }
             cur[idx] = v;
         }
         __syncthreads();
         // d(in)[i][r] = sum_o dpre[o][r] * W[o][i]
-        const float* __restrict__ W = a.w_in_smem ? wsm + a.wsm_off[l] : a.W[l];
         const int ldi = a.ldi[l];
         for (int item = tid; item < Din * RQ; item += kThreads) {
             const int i = item % Din, q = item / Din;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-            for (int o = 0; o < Dout; ++o) {
-                const float w = W[(size_t)o * ldi + i];
-                const float4 x = *reinterpret_cast<const float4*>(cur + o * R + q * 4);
-                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
-                acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
-            }
+            if (a.w_in_smem) acc = matvec4<true>(wsm + a.wsm_off[l] + i, ldi, cur + q * 4, R, Dout, acc);
+            else acc = matvec4<false>(a.W[l] + i, ldi, cur + q * 4, R, Dout, acc);
             *reinterpret_cast<float4*>(nxt + i * R + q * 4) = acc;
         }
         __syncthreads();
         float* t = cur; cur = nxt; nxt = t;
     }
     // 3. RK adjoint update with dzs = cur[h][r]
+    if (few) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * kThreads;
+            const int h = idx / R, r = idx % R;
+            if (idx < a.H * R && b0 + r < a.B) {
+                const size_t off = (size_t)h * a.Bp + b0 + r;
+                const float d = cur[idx];
+                a.gyT[off] = pre_gy[e] + d;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < a.n_k && a.kcoef[j] != 0.f) a.gkT[j][off] = fmaf(a.kcoef[j], d, pre_gk[e][j]);
+            }
+        }
+        return;
+    }
     for (int idx = tid; idx < a.H * R; idx += kThreads) {
         const int h = idx / R, r = idx % R;
         const int64_t b = b0 + r;
