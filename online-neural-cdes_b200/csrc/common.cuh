@@ -46,4 +46,27 @@ __device__ __forceinline__ int knot_index(const T* __restrict__ knots, int K, T 
     return idx;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl may begin (prologue: shared-memory carve-up,
+// TMEM allocation, staging of the packed weights) while its predecessor on the stream is still draining; it must
+// execute pdl_wait() before touching anything a previous kernel produced.  pdl_trigger() lets the successor start
+// its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ncde

@@ -131,10 +131,31 @@ __device__ __forceinline__ void tanh_sech2(float x, float& t, float& sech2) {
     t = copysignf((1.f - s) * r, x);
     sech2 = 4.f * s * r * r;
 }
+// The pre-activation of the bf16 path carries ~1e-2 absolute error from operand rounding, so MUFU.TANH (2^-11) is
+// noise here and costs one SFU op instead of two plus ten FP ops.  NCDE_TC_EXACT_TANH=1 builds the ex2/rcp variant.
+#ifndef NCDE_TC_EXACT_TANH
+#define NCDE_TC_EXACT_TANH 0
+#endif
 __device__ __forceinline__ float tanh_fast(float x) {
+#if NCDE_TC_EXACT_TANH
     float t, q;
     tanh_sech2(x, t, q);
     return t;
+#else
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+__device__ __forceinline__ float sech2_fast(float x) {
+#if NCDE_TC_EXACT_TANH
+    float t, q;
+    tanh_sech2(x, t, q);
+    return q;
+#else
+    const float t = tanh_fast(x);
+    return fmaf(-t, t, 1.f);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -273,6 +294,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // the activation tiles come from hidden_fwd
 
     const int wg = warp >> 2;                    // warp-group 0/1
     const int row = (warp & 3) * 32 + lane;      // TMEM lane == row inside the tile
@@ -380,9 +403,7 @@ __device__ __forceinline__ void bwd_chunk(uint32_t taddr, const float* __restric
     tmem_ldw<W>(taddr, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        float t, q;
-        tanh_sech2(v[j] + b3[j], t, q);
-        const float gv = gk * dx[j * kTcM] * q;
+        const float gv = gk * dx[j * kTcM] * sech2_fast(v[j] + b3[j]);
         v[j] = row_ok ? gv : 0.f;   // select, not multiply: padded rows hold uninitialised dX
     }
 #pragma unroll
@@ -433,6 +454,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // gk comes from the previous kernels
 
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;

@@ -263,7 +263,7 @@ static size_t bwd_workspace_floats(const Plan& pl) {
     size_t n = pl.wpack_floats + per;
     n += (size_t)(1 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
     n += (size_t)pl.n_hg * pl.B * pl.DFP + per;
-    for (int l = 0; l < pl.F; ++l) n += (size_t)pl.Dp4[l + 1] * pl.Bp + per;
+    for (int l = 0; l < pl.F; ++l) n += (size_t)pl.n_stages * ((size_t)pl.Dp4[l + 1] * pl.Bp + per);
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
     n += (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
@@ -476,7 +476,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             ha.path.t = g.stage_t[s * NS + i];
             {
                 ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
-                hidden_fwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem_fwd, st>>>(ha);
+                NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
             }
             ++launches;
             fa.actT = stage + pl.act_off[pl.F];
@@ -488,12 +488,12 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = dx_stage;
                     ta.koutT = kT[i];
-                    tc_field_fwd_kernel<<<dim3(pl.n_hg, pl.n_bt), kTcThreads, pl.fwd_smem, st>>>(ta);
+                    NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
                     ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) field_fwd_kernel<8><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
-                    else field_fwd_kernel<4><<<fg, kThreads, pl.fwd_smem, st>>>(fa);
+                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                    else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
                     ++launches;
                 }
             }
@@ -512,7 +512,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                 aa.emit_slope[aa.n_emit] = g.out_slope[j_out];
                 ++aa.n_emit; ++j_out;
             }
-            advance_kernel<<<tg, tb, 0, st>>>(aa);
+            NCDE_CUDA_OK(launch_pdl(advance_kernel, tg, tb, 0, st, aa));
             ++launches;
             first = false;
         }
@@ -555,8 +555,9 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     float* gkT[NCDE_MAX_STAGES] = {};
     for (int i = 0; i < NS; ++i) gkT[i] = cv.take(nHB);
     float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
-    float* dpreT[NCDE_MAX_LAYERS] = {};
-    for (int l = 0; l < pl.F; ++l) dpreT[l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
+    float* dpreT[NCDE_MAX_STAGES][NCDE_MAX_LAYERS] = {};
+    for (int i = 0; i < NS; ++i)
+        for (int l = 0; l < pl.F; ++l) dpreT[i][l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
     float* dW3acc = cv.take((size_t)pl.n_bt * pl.Np * pl.DFP);
     float* db3acc = cv.take((size_t)pl.n_bt * pl.Np);
 
@@ -584,7 +585,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     hb.B = pl.B; hb.Bp = pl.Bp; hb.H = pl.H; hb.R = pl.R; hb.F = pl.F; hb.Dmax = pl.Dmax; hb.DFP = pl.DFP; hb.n_hg = pl.n_hg;
     for (int l = 0; l <= pl.F; ++l) hb.D[l] = pl.D[l];
     for (int l = 0; l < pl.F; ++l) {
-        hb.act[l] = m.act[l]; hb.W[l] = wpack + pl.off_WR[l]; hb.ldi[l] = pl.ldi[l]; hb.dpreT[l] = dpreT[l];
+        hb.act[l] = m.act[l]; hb.W[l] = wpack + pl.off_WR[l]; hb.ldi[l] = pl.ldi[l];
         hb.wsm_off[l] = (int)(pl.off_WR[l] - pl.off_WR[0]);
     }
     hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
@@ -611,7 +612,6 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                          NCDE_ERR_INVALID, "solve_bwd: layers sharing a gradient buffer must share a slot and shape");
         }
         wa.lay[sidx][wa.n_lay[sidx]++] = l;
-        wa.dpreT[l] = dpreT[l];
     }
     for (int s2 = 0; s2 < wa.n_slots; ++s2) {
         wa.tile_begin[s2] = total_tiles;
@@ -638,11 +638,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         for (int64_t j = j_lo; j < j_hi; ++j) {
             const float sc = g.out_mode[j] == 1 ? 1.f : (g.out_mode[j] == 2 ? g.out_slope[j] : 0.f);
             if (sc != 0.f) {
-                add_out_grad_kernel<<<tg, tb, 0, st>>>(gyT, grad_out + (size_t)j * pl.B * pl.H, sc, pl.B, pl.Bp, pl.H);
+                NCDE_CUDA_OK(launch_pdl(add_out_grad_kernel, tg, tb, 0, st, gyT, grad_out + (size_t)j * pl.B * pl.H, sc, pl.B, pl.Bp, pl.H));
                 ++launches;
             }
         }
-        rk_bwd_begin_kernel<<<ew_grid, 256, 0, st>>>(gyT, gkT[0], gkT[1], gkT[2], gkT[3], p->method, dt, (int64_t)nHB);
+        NCDE_CUDA_OK(launch_pdl(rk_bwd_begin_kernel, dim3(ew_grid), dim3(256), 0, st, (const float*)gyT, gkT[0], gkT[1], gkT[2], gkT[3], (int)p->method, dt, (int64_t)nHB));
         ++launches;
         for (int i = NS - 1; i >= 0; --i) {
             const float* stage = (const float*)saved + (size_t)(s * NS + i) * pl.stage_floats;
@@ -655,16 +655,17 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = stage + pl.dx_off;
                     ta.gkT = gkT[i];
-                    tc_field_bwd_kernel<<<dim3(pl.n_hg, pl.n_bt), kTcThreads, pl.bwd_smem, st>>>(ta);
+                    NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta));
                     ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) field_bwd_kernel<8><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
-                    else field_bwd_kernel<4><<<fg, kThreads, pl.bwd_smem, st>>>(fa);
+                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+                    else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
                     ++launches;
                 }
             }
             for (int l = 0; l <= pl.F; ++l) hb.actT[l] = stage + pl.act_off[l];
+            for (int l = 0; l < pl.F; ++l) hb.dpreT[l] = dpreT[i][l];
             // d(stage input)/d(k_j): rk_common.py:111-113
             hb.n_k = 0;
             for (int j = 0; j < NCDE_MAX_STAGES; ++j) { hb.gkT[j] = nullptr; hb.kcoef[j] = 0.f; }
@@ -676,22 +677,27 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             }
             {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
-                hidden_bwd_kernel<<<pl.n_rt, kThreads, pl.hid_smem_bwd, st>>>(hb);
+                NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
             }
             ++launches;
-            if (pl.F > 0) {
-                for (int l = 0; l < pl.F; ++l) wa.actT[l] = stage + pl.act_off[l];
-                {
-                    ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
-                    hidden_wgrad_kernel<<<dim3(total_tiles, pl.wg_split), kThreads, 0, st>>>(wa);
-                }
-                ++launches;
+        }
+        if (pl.F > 0) {
+            // hidden weight gradients of all stages of this step in one launch (off the sequential chain)
+            wa.n_stage = NS;
+            for (int i = 0; i < NS; ++i) {
+                const float* stage = (const float*)saved + (size_t)(s * NS + i) * pl.stage_floats;
+                for (int l = 0; l < pl.F; ++l) { wa.actT[i][l] = stage + pl.act_off[l]; wa.dpreT[i][l] = dpreT[i][l]; }
             }
+            {
+                ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
+                NCDE_CUDA_OK(launch_pdl(hidden_wgrad_kernel, dim3(total_tiles, pl.wg_split), dim3(kThreads), 0, st, wa));
+            }
+            ++launches;
         }
         for (int64_t j = j_lo; j < j_hi; ++j) {
             const float sc = g.out_mode[j] == 0 ? 1.f : (g.out_mode[j] == 2 ? 1.f - g.out_slope[j] : 0.f);
             if (sc != 0.f) {
-                add_out_grad_kernel<<<tg, tb, 0, st>>>(gyT, grad_out + (size_t)j * pl.B * pl.H, sc, pl.B, pl.Bp, pl.H);
+                NCDE_CUDA_OK(launch_pdl(add_out_grad_kernel, tg, tb, 0, st, gyT, grad_out + (size_t)j * pl.B * pl.H, sc, pl.B, pl.Bp, pl.H));
                 ++launches;
             }
         }

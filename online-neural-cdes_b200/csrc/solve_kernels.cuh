@@ -104,8 +104,9 @@ struct WgradArgs {
     int Dout[NCDE_MAX_LAYERS], Din[NCDE_MAX_LAYERS];
     int n_lay[NCDE_MAX_LAYERS];
     int lay[NCDE_MAX_LAYERS][NCDE_MAX_LAYERS];
-    const float* dpreT[NCDE_MAX_LAYERS];  // per layer
-    const float* actT[NCDE_MAX_LAYERS];   // per layer: its input
+    int n_stage;                                            // RK stages folded into this launch
+    const float* dpreT[NCDE_MAX_STAGES][NCDE_MAX_LAYERS];   // per stage, per layer
+    const float* actT[NCDE_MAX_STAGES][NCDE_MAX_LAYERS];    // per stage, per layer: its input
     float* gWp[NCDE_MAX_LAYERS];          // per slot: [n_split][Dout][Din] partial accumulators (this CTA's split only)
     float* gbp[NCDE_MAX_LAYERS];          // per slot: [n_split][Dout]
     float* gW[NCDE_MAX_LAYERS];           // per slot: caller's gradient (torch layout), used by the final reduction
@@ -297,6 +298,8 @@ __global__ void from_feature_major_kernel(const float* __restrict__ srcT, const 
 __global__ void add_out_grad_kernel(float* __restrict__ gyT, const float* __restrict__ g, float scale, int B, int Bp,
                                     int H) {
     __shared__ float tile[32][33];
+    pdl_trigger();
+    pdl_wait();
     int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int b = b0 + i, h = h0 + threadIdx.x;
@@ -361,6 +364,8 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         const float* src = a.WT[0];
         for (int i = tid * 4; i < a.wsm_floats; i += kThreads * 4) cp_async_16(wsm + i, src + i);
     }
+    pdl_trigger();
+    pdl_wait();  // y and k_i come from the previous kernels
 
     // 1. stage input  zs[h][r]
     for (int idx = tid; idx < a.H * R; idx += kThreads) {
@@ -464,6 +469,8 @@ __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_consta
 #pragma unroll
     for (int j = 0; j < 4; ++j) bias[j] = active ? a.b3p[(size_t)g * S + nt * 4 + j] : 0.f;
     const int c0 = (nt * 4) % a.Cp;
+    pdl_trigger();
+    pdl_wait();  // activations come from hidden_fwd
 
     const int64_t row_begin = (int64_t)bt * a.Bt;
     const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
@@ -537,6 +544,8 @@ __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_consta
 __global__ void advance_kernel(const __grid_constant__ AdvanceArgs a) {
     __shared__ float t_old[32][33];
     __shared__ float t_new[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int h = h0 + i, b = b0 + threadIdx.x;
@@ -577,6 +586,8 @@ __global__ void advance_kernel(const __grid_constant__ AdvanceArgs a) {
 // backward: gk_i = c_i * dt * gy1   (derivative of the RK increment w.r.t. each stage derivative)
 __global__ void rk_bwd_begin_kernel(const float* __restrict__ gyT, float* gk0, float* gk1, float* gk2, float* gk3,
                                     int method, float dt, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float g = gyT[i];
@@ -647,6 +658,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     const int KD = DFP / 8;
     const int kd = tid % KD, md = tid / KD;
     const bool dg_active = md < kChunk / 4;
+    pdl_trigger();
+    pdl_wait();  // gk comes from the previous kernels
 
     const int64_t row_begin = (int64_t)bt * a.Bt;
     const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
@@ -826,6 +839,8 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
         const float* src = a.W[0];
         for (int i = tid * 4; i < a.wsm_floats; i += kThreads * 4) cp_async_16(wsm + i, src + i);
     }
+    pdl_trigger();
+    pdl_wait();  // P, gy, gk come from the previous kernels
     // gy / gk elements this thread updates at the end (fast path: at most 4 per thread)
     const bool few = a.H * R <= 4 * kThreads;
     float pre_gy[4], pre_gk[4][3];
@@ -941,6 +956,8 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
 __global__ void __launch_bounds__(kThreads) hidden_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     __shared__ __align__(16) float dS[kWgRows][kWgTile + 4];  // [b][o]
     __shared__ __align__(16) float aS[kWgRows][kWgTile + 4];  // [b][i]
+    pdl_trigger();
+    pdl_wait();  // dpre comes from hidden_bwd
     const int tid = threadIdx.x;
     int slot = 0;
     while (slot + 1 < a.n_slots && (int)blockIdx.x >= a.tile_begin[slot + 1]) ++slot;
@@ -958,10 +975,11 @@ __global__ void __launch_bounds__(kThreads) hidden_wgrad_kernel(const __grid_con
     float accb[4] = {0.f, 0.f, 0.f, 0.f};
     const int row_begin = split * a.rows_per_split;
     const int row_end = min(a.B, row_begin + a.rows_per_split);
-    for (int li = 0; li < a.n_lay[slot]; ++li) {
-        const int l = a.lay[slot][li];
-        const float* __restrict__ dT = a.dpreT[l];
-        const float* __restrict__ xT = a.actT[l];
+    for (int sl = 0; sl < a.n_stage * a.n_lay[slot]; ++sl) {
+        const int sg = sl / a.n_lay[slot];
+        const int l = a.lay[slot][sl % a.n_lay[slot]];
+        const float* __restrict__ dT = a.dpreT[sg][l];
+        const float* __restrict__ xT = a.actT[sg][l];
         for (int bc = row_begin; bc < row_end; bc += kWgRows) {
             // global reads are coalesced along the batch; the tiles are stored transposed ([b][feature])
             for (int idx = tid; idx < kWgTile * kWgRows; idx += kThreads) {
