@@ -168,6 +168,17 @@ int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void*
                    void* workspace, size_t workspace_bytes, int32_t* flags, int64_t* stats, int64_t* launches,
                    void* stream);
 
+/* dopri5 forward (NCDE_DOPRI5).  Error norm, accept/reject, next step size, initial step selection and dense output
+ * all run on a control block in device memory (replaces RKAdaptiveStepsizeODESolver, rk_common.py:117-313,
+ * misc.py:32-89, interp.py).  The host enqueues attempts in chunks of 32 and, between chunks, reads a completion
+ * flag the GPU wrote one chunk earlier, so the device never waits for the host; at most adaptive.max_attempts
+ * attempts are enqueued (NCDE_FLAG_MAX_STEPS if that was not enough).  stats (device int64[200], nullable):
+ * attempted steps, accepted steps, vector-field evaluations, ncde_flag_bits, then the selected initial step (fp64
+ * bits) and h0, d0, d1, d2 of its selection (fp32 bits), then (dt, error ratio, accepted) as fp64 for the first 64 attempts.  No saved state: gradients of the
+ * adaptive solve are not implemented in this revision. */
+int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void* workspace,
+                            size_t workspace_bytes, int64_t* stats, int64_t* launches, void* stream);
+
 /* Backward of the fixed-grid solve (discretise-then-optimise: the exact gradient autograd produces through the
  * reference's step loop).  grad_out (T,B,H).  Writes grad_z0 (B,H); ACCUMULATES into gW[l]/gbias[l] (torch
  * layout, one pointer per layer; layers sharing a slot must pass the same pointer).  grad_coeffs (nullable):

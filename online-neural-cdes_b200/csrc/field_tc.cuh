@@ -30,6 +30,7 @@ struct TcFieldArgs {
     float* dW3acc;             // [n_bt][Np][DFP]
     float* db3acc;             // [n_bt][Np]
     int DFP;
+    const AdaptCtrl* ctrl;     // adaptive solver: skip all work once ctrl->done
 };
 
 __host__ __device__ inline uint32_t tc_tmem_cols(int need) {
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
 
     uint32_t phase = 0;
     const int64_t row_begin = (int64_t)bt * a.Bt;
-    const int64_t row_end = min((int64_t)a.Bp, row_begin + a.Bt);
+    const int64_t row_end = (a.ctrl && a.ctrl->done) ? row_begin : min((int64_t)a.Bp, row_begin + a.Bt);
     for (int64_t b0 = row_begin; b0 < row_end && b0 < a.B; b0 += kTcM) {
         // asynchronous fills: activation tile (MMA operand) and dX/dt of these 128 rows (epilogue operand)
         load_tile_sw128(As, a.abf + (size_t)b0 * KP, kTcM, KP, (int)min((int64_t)kTcM, (int64_t)a.B - b0), tid, kTcThreads);
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
+    cp_async_wait_all();  // the weight tile copy must have landed before the CTA may exit
     if (warp == 0) tmem_dealloc(tmem_base, ncols);
 }
 

@@ -5,6 +5,7 @@
 
 #include "solve_kernels.cuh"
 #include "field_tc.cuh"
+#include "adaptive_kernels.cuh"
 
 namespace ncde {
 
@@ -71,14 +72,14 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     NCDE_REQUIRE(p->B < (1ll << 30), NCDE_ERR_UNSUPPORTED, "solve: batch too large");
     NCDE_REQUIRE(m.n_layers >= 1 && m.n_layers <= NCDE_MAX_LAYERS, NCDE_ERR_INVALID, "solve: 1..%d layers",
                  NCDE_MAX_LAYERS);
-    NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38, NCDE_ERR_UNSUPPORTED,
-                 "solve: method %d is not a fixed-grid method", p->method);
+    NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38 || p->method == NCDE_DOPRI5, NCDE_ERR_UNSUPPORTED,
+                 "solve: unknown method %d", p->method);
     pl->B = (int)p->B; pl->H = p->H; pl->C = p->C;
     pl->Bp = (int)round_up(p->B, kTcM);
     // channels padded to 4 (float4 epilogues) or 8 (tensor-core path: 16-byte bf16 chunks per h)
     pl->Cp = (int)round_up(p->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
     pl->F = m.n_layers - 1;
-    pl->n_stages = p->method == NCDE_RK4_38 ? 4 : 1;
+    pl->n_stages = p->method == NCDE_RK4_38 ? 4 : (p->method == NCDE_DOPRI5 ? 7 : 1);
     NCDE_REQUIRE(m.in_dim[0] == p->H, NCDE_ERR_INVALID, "solve: first layer must take H=%d inputs, takes %d", p->H,
                  m.in_dim[0]);
     for (int l = 0; l < m.n_layers; ++l) {
@@ -370,9 +371,19 @@ extern "C" size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad)
     return (size_t)p->grid.n_steps * pl.n_stages * pl.stage_floats * 4 + 256;
 }
 
+static size_t adaptive_workspace_floats(const Plan& pl, int64_t n_out) {
+    size_t per = 256 / 4;
+    size_t n = pl.wpack_floats + per;
+    n += (size_t)(2 + 7) * ((size_t)pl.H * pl.Bp + per);   // y, y1, k0..k6
+    n += pl.stage_floats + per;                             // one stage of scratch activations / dX / bf16 copy
+    n += sizeof(AdaptCtrl) / 4 + per + 2 * 256 + per + (size_t)n_out * 2 + per;
+    return n;
+}
+
 extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward) {
     Plan pl;
     if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
+    if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
     size_t fl = backward ? bwd_workspace_floats(pl)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
@@ -387,6 +398,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     Plan pl;
     int rc = make_plan(p, &pl);
     if (rc != NCDE_OK) return rc;
+    NCDE_REQUIRE(p->method != NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_fwd: use ncde_solve_adaptive_fwd for dopri5");
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
     NCDE_REQUIRE(workspace_bytes >= (fwd_workspace_floats(pl, !need_grad) +
@@ -718,6 +730,186 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                                                                              pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF, pl.DFP,
                                                                              pl.Np, pl.n_bt);
         ++launches;
+    }
+    NCDE_CUDA_OK(cudaGetLastError());
+    if (launches_out) *launches_out = launches;
+    return NCDE_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// dopri5 forward.  Step control runs on the device (adaptive_kernels.cuh); the host enqueues attempts in chunks and,
+// between chunks, looks at a completion flag that the GPU wrote one chunk earlier (so the GPU never waits for the
+// host).  stats (device int64[4], nullable) receives attempted, accepted, nfe, flags.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void* workspace,
+                                       size_t workspace_bytes, int64_t* stats, int64_t* launches_out, void* stream) {
+    NCDE_REQUIRE(p && z0 && z_out && workspace, NCDE_ERR_INVALID, "solve_adaptive_fwd: null pointer");
+    NCDE_REQUIRE(p->method == NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_adaptive_fwd: method must be dopri5");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc != NCDE_OK) return rc;
+    const ncde_adaptive_t& ad = p->adaptive;
+    NCDE_REQUIRE(ad.n_out >= 1 && ad.out_t, NCDE_ERR_INVALID, "solve_adaptive_fwd: output times missing");
+    for (int64_t j = 1; j < ad.n_out; ++j)
+        NCDE_REQUIRE(ad.out_t[j] > ad.out_t[j - 1], NCDE_ERR_INVALID, "t must be strictly increasing");
+    NCDE_REQUIRE(ad.max_attempts >= 1, NCDE_ERR_INVALID, "solve_adaptive_fwd: max_attempts must be positive");
+    NCDE_REQUIRE(p->path.K >= 2 && p->path.knots && p->path.coeffs, NCDE_ERR_INVALID, "solve: bad path");
+    NCDE_REQUIRE(workspace_bytes >= adaptive_workspace_floats(pl, ad.n_out) * 4, NCDE_ERR_WORKSPACE,
+                 "solve_adaptive_fwd: workspace of %zu bytes is too small", workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t launches = 0;
+    const size_t nHB = (size_t)pl.H * pl.Bp;
+
+    Carver cv{(char*)workspace, 0, workspace_bytes};
+    float* wpack = cv.take(pl.wpack_floats);
+    float* yT = cv.take(nHB);
+    float* y1T = cv.take(nHB);
+    float* kT[7];
+    for (int i = 0; i < 7; ++i) kT[i] = cv.take(nHB);
+    float* stage = cv.take(pl.stage_floats);
+    AdaptCtrl* ctrl = (AdaptCtrl*)cv.take(sizeof(AdaptCtrl) / 4 + 1);
+    const int nblocks = 128;
+    double* partials = (double*)cv.take(2 * nblocks * 2);
+    double* d_out_t = (double*)cv.take((size_t)ad.n_out * 2);
+
+    rc = pack_weights(p, pl, wpack, 0, st, &launches);
+    if (rc != NCDE_OK) return rc;
+    const bool use_tc = pl.tc != 0;
+    if (use_tc) rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem);
+    else if (pl.TM == 8) rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem);
+    else rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem);
+    if (rc != NCDE_OK) return rc;
+
+    const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
+    to_feature_major_kernel<<<tg, tb, 0, st>>>(z0, yT, pl.B, pl.Bp, pl.H);
+    ++launches;
+    NCDE_CUDA_OK(cudaMemcpyAsync(z_out, z0, (size_t)pl.B * pl.H * 4, cudaMemcpyDeviceToDevice, st));
+    NCDE_CUDA_OK(cudaMemcpyAsync(d_out_t, ad.out_t, (size_t)ad.n_out * 8, cudaMemcpyHostToDevice, st));
+
+    AdaptParams ap;
+    ap.t0 = ad.out_t[0]; ap.rtol = ad.rtol; ap.atol = ad.atol; ap.min_step = ad.min_step; ap.max_step = ad.max_step;
+    ap.first_step = ad.first_step; ap.safety = ad.safety; ap.ifactor = ad.ifactor; ap.dfactor = ad.dfactor;
+    ap.max_attempts = ad.max_attempts; ap.n_out = (int)ad.n_out;
+    adapt_init_kernel<<<1, 32, 0, st>>>(ctrl, ap);
+    ++launches;
+
+    HiddenFwdArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.B = pl.B; ha.Bp = pl.Bp; ha.H = pl.H; ha.C = pl.C; ha.Cp = pl.Cp; ha.R = pl.R; ha.F = pl.F; ha.Dmax = pl.Dmax;
+    for (int l = 0; l <= pl.F; ++l) ha.D[l] = pl.D[l];
+    for (int l = 0; l < pl.F; ++l) {
+        ha.ldw[l] = pl.ldw[l]; ha.act[l] = p->mlp.act[l];
+        ha.WT[l] = wpack + pl.off_WT[l]; ha.bp[l] = wpack + pl.off_bp[l];
+        ha.wsm_off[l] = (int)(pl.off_WT[l] - pl.off_WT[0]);
+    }
+    ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
+    rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
+    if (rc != NCDE_OK) return rc;
+    ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
+    ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    for (int i = 0; i < 7; ++i) ha.kT[i] = kT[i];
+    ha.combine = COMBINE_LINEAR;
+    ha.yT = yT;
+    ha.ctrl = ctrl;
+    ha.KP = pl.KP;
+    for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
+    ha.dXT = stage + pl.dx_off;
+    ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
+
+    FieldArgs fa;
+    fill_field_args(fa, pl, wpack);
+    fa.actT = stage + pl.act_off[pl.F]; fa.dXT = stage + pl.dx_off; fa.ctrl = ctrl;
+    TcFieldArgs ta;
+    fill_tc_args(ta, pl, wpack);
+    ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off; ta.ctrl = ctrl;
+
+    // one vector-field evaluation: stage input from tab[tab_index], result into kT[k_out]
+    auto eval = [&](int tab_index, int k_out, float* stage_input_T) -> int {
+        ha.tab_index = tab_index;
+        ha.actT[0] = stage_input_T ? stage_input_T : stage + pl.act_off[0];
+        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+        if (pl.F == 0) fa.actT = ha.actT[0];
+        if (use_tc) {
+            ta.koutT = kT[k_out];
+            NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
+        } else {
+            fa.koutT = kT[k_out];
+            const dim3 fg(pl.n_hg, pl.n_bt);
+            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+        }
+        launches += 2;
+        return NCDE_OK;
+    };
+
+    // f0 = f(t0, y0)
+    rc = eval(0, 0, nullptr);
+    if (rc != NCDE_OK) return rc;
+    const double n_elems = (double)pl.B * pl.H;
+    if (!(ad.first_step > 0)) {
+        // _select_initial_step (misc.py:32-71)
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, 0, (const float*)yT,
+                                (const float*)kT[0], (const float*)kT[0], pl.B, pl.Bp, pl.H, partials));
+        NCDE_CUDA_OK(launch_pdl(adapt_init_step1_kernel, dim3(1), dim3(32), 0, st, ctrl, (const double*)partials, nblocks, n_elems));
+        launches += 2;
+        rc = eval(NCDE_MAX_STAGES, 1, nullptr);
+        if (rc != NCDE_OK) return rc;
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, 1, (const float*)yT,
+                                (const float*)kT[0], (const float*)kT[1], pl.B, pl.Bp, pl.H, partials));
+        NCDE_CUDA_OK(launch_pdl(adapt_init_step2_kernel, dim3(1), dim3(32), 0, st, ctrl, (const double*)partials, nblocks, n_elems));
+        launches += 2;
+    }
+
+    DopriArgs da;
+    memset(&da, 0, sizeof(da));
+    da.ctrl = ctrl; da.B = pl.B; da.Bp = pl.Bp; da.H = pl.H; da.yT = yT; da.y1T = y1T;
+    for (int i = 0; i < 7; ++i) da.kT[i] = kT[i];
+    da.out_t = d_out_t; da.z_out = z_out; da.partials = partials; da.nblocks = nblocks;
+
+    // completion polling: pinned flag + event per chunk, always one chunk of look-ahead
+    static int* h_done = nullptr;
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!h_done) {
+        NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, 2 * sizeof(int), cudaHostAllocDefault));
+        NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    }
+    h_done[0] = h_done[1] = 0;
+    const int64_t chunk = 32;
+    int64_t enq = 0;
+    int n_chunks = 0;
+    while (enq < ad.max_attempts) {
+        const int64_t upto = enq + chunk < ad.max_attempts ? enq + chunk : ad.max_attempts;
+        for (; enq < upto; ++enq) {
+            for (int i = 1; i <= 6; ++i) {
+                rc = eval(i, i, i == 6 ? y1T : nullptr);
+                if (rc != NCDE_OK) return rc;
+            }
+            NCDE_CUDA_OK(launch_pdl(dopri_err_kernel, dim3(nblocks), dim3(256), 0, st, da));
+            NCDE_CUDA_OK(launch_pdl(dopri_ctrl_kernel, dim3(1), dim3(32), 0, st, da));
+            NCDE_CUDA_OK(launch_pdl(dopri_accept_kernel, tg, tb, 0, st, da));
+            launches += 3;
+        }
+        const int slot = n_chunks & 1;
+        if (n_chunks >= 1) {
+            // wait for the flag written at the end of the PREVIOUS chunk (the chunk just enqueued keeps the GPU busy)
+            NCDE_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
+            if (h_done[slot ^ 1]) break;
+        }
+        NCDE_CUDA_OK(cudaMemcpyAsync(&h_done[slot], &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NCDE_CUDA_OK(cudaEventRecord(ev[slot], st));
+        ++n_chunks;
+    }
+    if (stats) {
+        // attempted, accepted, nfe are consecutive int64 fields of the control block; flags follows max_attempts
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats, &ctrl->attempted, 3 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(stats + 3, 0, sizeof(int64_t), st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 3, &ctrl->flags, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        // stats[4] = initial step size (double bits), stats[5..6] = h0, d0, d1, d2 (float bits) of its selection
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 4, &ctrl->dt_init, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 5, &ctrl->h0, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 8, &ctrl->trace[0][0], 64 * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     NCDE_CUDA_OK(cudaGetLastError());
     if (launches_out) *launches_out = launches;

@@ -27,6 +27,27 @@ struct PathArgs {
     float t;  // stage time, already cast to fp32 (torchdiffeq/_impl/misc.py:181)
 };
 
+// ---- adaptive (dopri5) control state, resident in device memory; every time-like scalar is fp64 like the
+// reference (torchdiffeq/_impl/rk_common.py:139-160) ----
+struct StageTab {
+    float t;                        // stage time after the cast to fp32 (and the one-ulp nudge for alpha == 1)
+    float coef[NCDE_MAX_STAGES];    // beta_ij * dt in fp32
+};
+struct AdaptCtrl {
+    double t0, dt;                  // end of the last accepted step (= start of the next attempt), next step size
+    double t_lo, t_hi;              // interval of the last accepted step (dense output domain)
+    double step_dt;                 // dt of the attempt in flight
+    double acc_dt;                  // dt of the last accepted step (dense-output coefficients)
+    double rtol, atol, min_step, max_step, safety, ifactor, dfactor;
+    int accept, done, j_begin, j_end, j_out, n_out;
+    long long attempted, accepted, nfe, max_attempts;
+    int flags;
+    float h0, d0, d1, d2;           // initial-step selection scratch (misc.py:32-71)
+    double dt_init;
+    double trace[64][3];            // first 64 attempts: dt, error ratio, accepted (diagnostics)
+    StageTab tab[NCDE_MAX_STAGES + 1];
+};
+
 struct HiddenFwdArgs {
     int B, Bp, H, C, Cp, R, F, Dmax;
     int D[NCDE_MAX_LAYERS + 1];   // D[l] = input width of layer l (D[0] = H, D[F] = input of the final layer)
@@ -48,6 +69,9 @@ struct HiddenFwdArgs {
     int wsm_off[NCDE_MAX_LAYERS];      // float offset of layer l's weights inside the shared staging area
     int wsm_floats;                    // total floats staged (layers sharing a slot share the copy)
     PathArgs path;
+    // adaptive solver: stage time and combine coefficients come from device memory; nothing runs once ctrl->done
+    const AdaptCtrl* ctrl;
+    int tab_index;
 };
 
 struct FieldArgs {
@@ -63,6 +87,7 @@ struct FieldArgs {
     float* dW3acc;      // [n_bt][Np][DFP]    (backward) accumulated across stages
     float* db3acc;      // [n_bt][Np]
     float* gdXT;        // [Cp][Bp] or null   (backward) dL/d(dX/dt) partials are not supported yet
+    const AdaptCtrl* ctrl;  // adaptive solver: skip all work once ctrl->done
 };
 
 struct AdvanceArgs {
@@ -131,7 +156,7 @@ enum { COMBINE_Y = 0, COMBINE_RK4_S2 = 1, COMBINE_RK4_S3 = 2, COMBINE_RK4_S4 = 3
 
 // Stage input of the RK scheme with the reference's operation order and no FMA contraction
 // (torchdiffeq/_impl/rk_common.py:106-114; _one_third / _two_thirds are rounded to fp32 by the tensor multiply).
-__device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int64_t off) {
+__device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int64_t off, const float* coef) {
     const float y = a.yT[off];
     const float third = 0.3333333432674408f;  // float32(1/3)
     switch (a.combine) {
@@ -145,7 +170,7 @@ __device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int
         default: {            // y0 + sum_j k_j * coef_j
             float acc = 0.f;
             for (int j = 0; j < NCDE_MAX_STAGES; ++j)
-                if (a.coef[j] != 0.f) acc = fmaf(a.kT[j][off], a.coef[j], acc);
+                if (coef[j] != 0.f) acc = fmaf(a.kT[j][off], coef[j], acc);
             return y + acc;
         }
     }
@@ -366,6 +391,18 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
     }
     pdl_trigger();
     pdl_wait();  // y and k_i come from the previous kernels
+    float coef[NCDE_MAX_STAGES];
+    float t_stage = a.path.t;
+    if (a.ctrl) {
+        if (a.ctrl->done) return;
+        const StageTab& tb = a.ctrl->tab[a.tab_index];
+        t_stage = tb.t;
+#pragma unroll
+        for (int j = 0; j < NCDE_MAX_STAGES; ++j) coef[j] = tb.coef[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < NCDE_MAX_STAGES; ++j) coef[j] = a.coef[j];
+    }
 
     // 1. stage input  zs[h][r]
     for (int idx = tid; idx < a.H * R; idx += kThreads) {
@@ -374,15 +411,15 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         float v = 0.f;
         if (b < a.B) {
             const int64_t off = (int64_t)h * a.Bp + b;
-            v = combine_stage_input(a, off);
+            v = combine_stage_input(a, off, coef);
             a.actT[0][off] = v;
         }
         buf0[h * R + r] = v;
     }
     // 2. dX/dt at the stage time -> dXT[c][b] (zero in the padded channels); skipped when dx_all_kernel already did it
     if (a.dXT) {
-        const int idxk = knot_index<float>(a.path.knots, a.path.K, a.path.t);
-        const float frac = __fsub_rn(a.path.t, a.path.knots[idxk]);
+        const int idxk = knot_index<float>(a.path.knots, a.path.K, t_stage);
+        const float frac = __fsub_rn(t_stage, a.path.knots[idxk]);
         float* tmp = buf1;  // [Cp][R]
         for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
             const int r = idx / a.Cp, c = idx % a.Cp;
@@ -471,6 +508,7 @@ __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_consta
     const int c0 = (nt * 4) % a.Cp;
     pdl_trigger();
     pdl_wait();  // activations come from hidden_fwd
+    if (a.ctrl && a.ctrl->done) return;
 
     const int64_t row_begin = (int64_t)bt * a.Bt;
     const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
