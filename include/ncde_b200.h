@@ -187,6 +187,17 @@ int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, const void* s
                    float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
                    size_t workspace_bytes, int64_t* launches, void* stream);
 
+/* Continuous adjoint with a fixed-grid adjoint method (NCDE_EULER / NCDE_RK4_38); replaces OdeintAdjointMethod.backward
+ * (modules/torchdiffeq/torchdiffeq/_impl/adjoint.py:36-145).  p->grid describes the BACKWARD schedule, interval by
+ * interval from the last output interval to the first: n_steps = total steps, dt = step sizes (> 0, reversed time),
+ * stage_t = the stage times expressed in forward time (already negated back and cast to fp32).  interval_steps
+ * (host, n_out - 1 entries, same order) gives the number of steps of each interval.  y_out, grad_out: (T,B,H)
+ * forward outputs and their gradients.  Writes grad_z0; ACCUMULATES into gW / gbias like ncde_solve_bwd. */
+size_t ncde_solve_adjoint_workspace_bytes(const ncde_problem_t* p);
+int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* interval_steps, int64_t n_out, const float* y_out,
+                           const float* grad_out, float* grad_z0, float* const* gW, float* const* gbias,
+                           void* workspace, size_t workspace_bytes, int64_t* launches, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Per-kernel timing with CUDA events on the launching stream (measurement support for bench.py; no reference
  * counterpart).  While enabled, every launch of the kernel classes in `class_mask` is bracketed by an event

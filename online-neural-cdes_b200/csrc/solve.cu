@@ -915,3 +915,283 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     if (launches_out) *launches_out = launches;
     return NCDE_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Continuous adjoint with a fixed-grid method (torchdiffeq/_impl/adjoint.py:36-145 with adjoint_method euler / rk4).
+// For every output interval [t_{i-1}, t_i], last to first, the augmented state (y, a, g_theta) is integrated in
+// reversed time with the same scheme as the forward pass; every augmented evaluation is
+//     hidden_fwd(y) -> field_fwd (f)  and  field_bwd(gk = a) -> hidden_bwd (a^T df/dy) -> hidden_wgrad (a^T df/dtheta).
+// The time-gradient component of the reference's augmented state never influences a fixed-grid solve and is omitted.
+// ---------------------------------------------------------------------------------------------------------------
+struct ThetaLayout {
+    int n_slots;                       // unique hidden parameter sets
+    size_t off_W[NCDE_MAX_LAYERS], off_b[NCDE_MAX_LAYERS];   // per layer (shared layers share offsets); off_b = SIZE_MAX if no bias
+    size_t total;
+};
+
+static void theta_layout(const ncde_problem_t* p, const Plan& pl, float* const* gW, float* const* gbias, ThetaLayout* tl) {
+    size_t off = 0;
+    const int n = pl.F + 1;
+    for (int l = 0; l < n; ++l) {
+        int first = l;
+        for (int j = 0; j < l; ++j) if (gW[j] == gW[l]) { first = j; break; }
+        if (first != l) { tl->off_W[l] = tl->off_W[first]; tl->off_b[l] = tl->off_b[first]; continue; }
+        tl->off_W[l] = off; off += round_up((size_t)p->mlp.out_dim[l] * p->mlp.in_dim[l], 64);
+        if (gbias[l]) { tl->off_b[l] = off; off += round_up((size_t)p->mlp.out_dim[l], 64); } else tl->off_b[l] = (size_t)-1;
+    }
+    tl->total = off;
+}
+
+static size_t adjoint_workspace_floats(const ncde_problem_t* p, const Plan& pl) {
+    size_t per = 256 / 4;
+    const size_t nHB = (size_t)pl.H * pl.Bp;
+    size_t n = pl.wpack_floats + per;
+    n += (size_t)(3 + 2 * 4) * (nHB + per);            // y, a, a_stage, kf[4], ka[4]
+    n += pl.stage_floats + per;
+    n += (size_t)pl.n_hg * pl.B * pl.DFP + per;
+    for (int l = 0; l < pl.F; ++l) n += (size_t)pl.Dp4[l + 1] * pl.Bp + per;
+    n += (size_t)pl.n_bt * pl.Np * pl.DFP + per + (size_t)pl.n_bt * pl.Np + per;
+    n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
+    size_t ntheta = 0;
+    for (int l = 0; l <= pl.F; ++l) ntheta += round_up((size_t)p->mlp.out_dim[l] * p->mlp.in_dim[l], 64) + round_up(p->mlp.out_dim[l], 64);
+    n += 5 * (ntheta + per);
+    return n;
+}
+
+extern "C" size_t ncde_solve_adjoint_workspace_bytes(const ncde_problem_t* p) {
+    Plan pl;
+    if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
+    return adjoint_workspace_floats(p, pl) * 4 + 4096;
+}
+
+extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* interval_steps, int64_t n_out,
+                                      const float* y_out, const float* grad_out, float* grad_z0, float* const* gW,
+                                      float* const* gbias, void* workspace, size_t workspace_bytes, int64_t* launches_out,
+                                      void* stream) {
+    NCDE_REQUIRE(p && interval_steps && y_out && grad_out && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID,
+                 "solve_adjoint_bwd: null pointer");
+    NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38, NCDE_ERR_UNSUPPORTED,
+                 "solve_adjoint_bwd: only fixed-grid adjoint methods (euler, rk4) are implemented");
+    NCDE_REQUIRE(n_out >= 1, NCDE_ERR_INVALID, "solve_adjoint_bwd: no outputs");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc != NCDE_OK) return rc;
+    NCDE_REQUIRE(workspace_bytes >= adjoint_workspace_floats(p, pl) * 4, NCDE_ERR_WORKSPACE,
+                 "solve_adjoint_bwd: workspace of %zu bytes is too small", workspace_bytes);
+    NCDE_REQUIRE(p->path.K >= 2 && p->path.knots && p->path.coeffs, NCDE_ERR_INVALID, "solve: bad path");
+    const ncde_fixed_grid_t& g = p->grid;
+    int64_t total_steps = 0;
+    for (int64_t i = 0; i + 1 < n_out; ++i) { NCDE_REQUIRE(interval_steps[i] >= 0, NCDE_ERR_INVALID, "bad interval"); total_steps += interval_steps[i]; }
+    NCDE_REQUIRE(total_steps == g.n_steps && (g.n_steps == 0 || (g.stage_t && g.dt)), NCDE_ERR_INVALID,
+                 "solve_adjoint_bwd: schedule does not match the intervals");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t launches = 0;
+    const ncde_mlp_t& m = p->mlp;
+    const int NS = pl.n_stages;
+    const size_t nHB = (size_t)pl.H * pl.Bp;
+    for (int l = 0; l <= pl.F; ++l) NCDE_REQUIRE(gW[l] != nullptr, NCDE_ERR_INVALID, "solve_adjoint_bwd: gW[%d] is null", l);
+
+    Carver cv{(char*)workspace, 0, workspace_bytes};
+    float* wpack = cv.take(pl.wpack_floats);
+    float* yT = cv.take(nHB);
+    float* aT = cv.take(nHB);
+    float* a_stage = cv.take(nHB);
+    float* kf[4]; float* ka[4];
+    for (int i = 0; i < 4; ++i) { kf[i] = cv.take(nHB); ka[i] = cv.take(nHB); }
+    float* stage = cv.take(pl.stage_floats);
+    float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
+    float* dpreT[NCDE_MAX_LAYERS] = {};
+    for (int l = 0; l < pl.F; ++l) dpreT[l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
+    const size_t nW3 = (size_t)pl.n_bt * pl.Np * pl.DFP, nb3 = (size_t)pl.n_bt * pl.Np;
+    float* dW3acc = cv.take(nW3);
+    float* db3acc = cv.take(nb3);
+    ThetaLayout tl;
+    theta_layout(p, pl, gW, gbias, &tl);
+    float* theta = cv.take(tl.total);
+    float* ktheta[4];
+    for (int i = 0; i < 4; ++i) ktheta[i] = cv.take(tl.total);
+
+    rc = pack_weights(p, pl, wpack, 1, st, &launches);
+    if (rc != NCDE_OK) return rc;
+    const bool use_tc = pl.tc != 0;
+    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem); }
+    else if (pl.TM == 8) { rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); }
+    else { rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem); }
+    if (rc == NCDE_OK) rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
+    if (rc == NCDE_OK) rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
+    if (rc != NCDE_OK) return rc;
+
+    // ---- argument blocks ----
+    HiddenFwdArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.B = pl.B; ha.Bp = pl.Bp; ha.H = pl.H; ha.C = pl.C; ha.Cp = pl.Cp; ha.R = pl.R; ha.F = pl.F; ha.Dmax = pl.Dmax;
+    for (int l = 0; l <= pl.F; ++l) ha.D[l] = pl.D[l];
+    for (int l = 0; l < pl.F; ++l) {
+        ha.ldw[l] = pl.ldw[l]; ha.act[l] = m.act[l];
+        ha.WT[l] = wpack + pl.off_WT[l]; ha.bp[l] = wpack + pl.off_bp[l];
+        ha.wsm_off[l] = (int)(pl.off_WT[l] - pl.off_WT[0]);
+    }
+    ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
+    ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
+    ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    for (int i = 0; i < NS; ++i) ha.kT[i] = kf[i];
+    ha.yT = yT; ha.KP = pl.KP; ha.comb_sign = -1.f;
+    for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
+    ha.dXT = stage + pl.dx_off;
+    ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
+
+    FieldArgs fa;
+    fill_field_args(fa, pl, wpack);
+    fa.actT = stage + pl.act_off[pl.F]; fa.dXT = stage + pl.dx_off;
+    fa.P = P; fa.dW3acc = dW3acc; fa.db3acc = db3acc; fa.gkT = a_stage;
+    TcFieldArgs ta;
+    fill_tc_args(ta, pl, wpack);
+    ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off;
+    ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc; ta.gkT = a_stage;
+
+    HiddenBwdArgs hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.B = pl.B; hb.Bp = pl.Bp; hb.H = pl.H; hb.R = pl.R; hb.F = pl.F; hb.Dmax = pl.Dmax; hb.DFP = pl.DFP; hb.n_hg = pl.n_hg;
+    for (int l = 0; l <= pl.F; ++l) { hb.D[l] = pl.D[l]; hb.actT[l] = stage + pl.act_off[l]; }
+    for (int l = 0; l < pl.F; ++l) {
+        hb.act[l] = m.act[l]; hb.W[l] = wpack + pl.off_WR[l]; hb.ldi[l] = pl.ldi[l]; hb.dpreT[l] = dpreT[l];
+        hb.wsm_off[l] = (int)(pl.off_WR[l] - pl.off_WR[0]);
+    }
+    hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
+    hb.P = P;
+
+    WgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.B = pl.B; wa.Bp = pl.Bp; wa.n_split = pl.wg_split; wa.rows_per_split = pl.wg_rows; wa.n_stage = 1;
+    int total_tiles = 0;
+    int slot_layer[NCDE_MAX_LAYERS];
+    for (int l = 0; l < pl.F; ++l) {
+        int sidx = -1;
+        for (int s2 = 0; s2 < wa.n_slots; ++s2) if (slot_layer[s2] >= 0 && gW[slot_layer[s2]] == gW[l]) sidx = s2;
+        if (sidx < 0) {
+            sidx = wa.n_slots++;
+            slot_layer[sidx] = l;
+            wa.Dout[sidx] = m.out_dim[l]; wa.Din[sidx] = m.in_dim[l];
+        }
+        wa.lay[sidx][wa.n_lay[sidx]++] = l;
+        wa.dpreT[0][l] = dpreT[l];
+        wa.actT[0][l] = stage + pl.act_off[l];
+    }
+    size_t gwp_floats[NCDE_MAX_LAYERS], gbp_floats[NCDE_MAX_LAYERS];
+    for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+        wa.tile_begin[s2] = total_tiles;
+        total_tiles += (int)(ceil_div(wa.Dout[s2], kWgTile) * ceil_div(wa.Din[s2], kWgTile));
+        gwp_floats[s2] = (size_t)pl.wg_split * wa.Dout[s2] * wa.Din[s2];
+        gbp_floats[s2] = (size_t)pl.wg_split * wa.Dout[s2];
+        wa.gWp[s2] = cv.take(gwp_floats[s2]);
+        wa.gbp[s2] = cv.take(gbp_floats[s2]);
+    }
+    wa.tile_begin[wa.n_slots] = total_tiles;
+    NCDE_REQUIRE(cv.used <= workspace_bytes, NCDE_ERR_WORKSPACE, "solve_adjoint_bwd: workspace accounting error");
+
+    const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
+    const unsigned ew_grid = (unsigned)ceil_div((int64_t)nHB, 256);
+    const unsigned th_grid = (unsigned)ceil_div((int64_t)tl.total, 256);
+    static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
+
+    // initial augmented state: y = y(t_T), a = dL/dy(t_T), g_theta = 0
+    to_feature_major_kernel<<<tg, tb, 0, st>>>(y_out + (size_t)(n_out - 1) * pl.B * pl.H, yT, pl.B, pl.Bp, pl.H);
+    to_feature_major_kernel<<<tg, tb, 0, st>>>(grad_out + (size_t)(n_out - 1) * pl.B * pl.H, aT, pl.B, pl.Bp, pl.H);
+    launches += 2;
+    NCDE_CUDA_OK(cudaMemsetAsync(theta, 0, tl.total * 4, st));
+
+    int64_t step_idx = 0;
+    for (int64_t iv = 0; iv + 1 < n_out; ++iv) {
+        const int64_t i_hi = n_out - 1 - iv;  // interval [t_{i_hi-1}, t_{i_hi}]
+        for (int64_t s = 0; s < interval_steps[iv]; ++s, ++step_idx) {
+            const float dt = g.dt[step_idx];
+            for (int sg = 0; sg < NS; ++sg) {
+                const int mode = p->method == NCDE_RK4_38 ? rk4_combine[sg] : COMBINE_Y;
+                // y stage input (reversed time: k_y = -f) -> activations, dX/dt at the stage time, f
+                ha.combine = mode; ha.dt = dt; ha.path.t = g.stage_t[step_idx * NS + sg];
+                NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+                if (use_tc) {
+                    ta.koutT = kf[sg];
+                    NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
+                } else {
+                    fa.koutT = kf[sg];
+                    const dim3 fg(pl.n_hg, pl.n_bt);
+                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                    else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                }
+                // adjoint stage input a_s = a + increment(ka)
+                AugCombineArgs ca;
+                memset(&ca, 0, sizeof(ca));
+                ca.n = (int64_t)nHB; ca.combine = mode; ca.dt = dt; ca.sign = 1.f; ca.base = aT; ca.out = a_stage;
+                for (int j = 0; j < 4; ++j) ca.k[j] = ka[j];
+                NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(ew_grid), dim3(256), 0, st, ca));
+                launches += 3;
+                // vector-Jacobian products with a_s
+                NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, nW3 * 4, st));
+                NCDE_CUDA_OK(cudaMemsetAsync(db3acc, 0, nb3 * 4, st));
+                NCDE_CUDA_OK(cudaMemsetAsync(ktheta[sg], 0, tl.total * 4, st));
+                for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+                    NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, gwp_floats[s2] * 4, st));
+                    NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
+                }
+                if (use_tc) NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta));
+                else {
+                    const dim3 fg(pl.n_hg, pl.n_bt);
+                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+                    else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+                }
+                hb.dz_out = ka[sg];
+                NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
+                launches += 2;
+                if (pl.F > 0) {
+                    for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+                        const int l0 = slot_layer[s2];
+                        wa.gW[s2] = ktheta[sg] + tl.off_W[l0];
+                        wa.gb[s2] = tl.off_b[l0] == (size_t)-1 ? nullptr : ktheta[sg] + tl.off_b[l0];
+                    }
+                    NCDE_CUDA_OK(launch_pdl(hidden_wgrad_kernel, dim3(total_tiles, pl.wg_split), dim3(kThreads), 0, st, wa));
+                    int nmax = 0;
+                    for (int s2 = 0; s2 < wa.n_slots; ++s2) nmax = wa.Dout[s2] * wa.Din[s2] > nmax ? wa.Dout[s2] * wa.Din[s2] : nmax;
+                    hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, st>>>(wa);
+                    launches += 2;
+                }
+                {
+                    const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
+                    unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+                        dW3acc, db3acc, ktheta[sg] + tl.off_W[pl.F],
+                        tl.off_b[pl.F] == (size_t)-1 ? nullptr : ktheta[sg] + tl.off_b[pl.F], pl.H, pl.C, pl.Cp, pl.Hg, pl.Npad,
+                        pl.DF, pl.DFP, pl.Np, pl.n_bt);
+                    ++launches;
+                }
+            }
+            // advance the augmented state over this step
+            aug_advance_kernel<<<ew_grid, 256, 0, st>>>(yT, kf[0], kf[1], kf[2], kf[3], p->method, dt, -1.f, (int64_t)nHB);
+            aug_advance_kernel<<<ew_grid, 256, 0, st>>>(aT, ka[0], ka[1], ka[2], ka[3], p->method, dt, 1.f, (int64_t)nHB);
+            aug_advance_kernel<<<th_grid, 256, 0, st>>>(theta, ktheta[0], ktheta[1], ktheta[2], ktheta[3], p->method, dt, 1.f,
+                                                       (int64_t)tl.total);
+            launches += 3;
+        }
+        // adjoint.py:131-133: restart from the stored forward state, add the gradient arriving at t_{i-1}
+        to_feature_major_kernel<<<tg, tb, 0, st>>>(y_out + (size_t)(i_hi - 1) * pl.B * pl.H, yT, pl.B, pl.Bp, pl.H);
+        add_out_grad_kernel<<<tg, tb, 0, st>>>(aT, grad_out + (size_t)(i_hi - 1) * pl.B * pl.H, 1.f, pl.B, pl.Bp, pl.H);
+        launches += 2;
+    }
+    from_feature_major_kernel<<<tg, tb, 0, st>>>(aT, nullptr, grad_z0, pl.B, pl.Bp, pl.H);
+    ++launches;
+    for (int l = 0; l <= pl.F; ++l) {
+        bool first = true;
+        for (int j = 0; j < l; ++j) if (gW[j] == gW[l]) first = false;
+        if (!first) continue;
+        const int64_t nw = (int64_t)m.out_dim[l] * m.in_dim[l];
+        axpy_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, st>>>(gW[l], theta + tl.off_W[l], nw);
+        ++launches;
+        if (gbias[l]) {
+            axpy_kernel<<<(unsigned)ceil_div((int64_t)m.out_dim[l], 256), 256, 0, st>>>(gbias[l], theta + tl.off_b[l], m.out_dim[l]);
+            ++launches;
+        }
+    }
+    NCDE_CUDA_OK(cudaGetLastError());
+    if (launches_out) *launches_out = launches;
+    return NCDE_OK;
+}

@@ -72,6 +72,9 @@ struct HiddenFwdArgs {
     // adaptive solver: stage time and combine coefficients come from device memory; nothing runs once ctrl->done
     const AdaptCtrl* ctrl;
     int tab_index;
+    // continuous adjoint: the state is integrated in reversed time, its stage derivative is -f, so the increment of the
+    // stage-input combination is subtracted (comb_sign = -1)
+    float comb_sign;
 };
 
 struct FieldArgs {
@@ -112,6 +115,7 @@ struct HiddenBwdArgs {
     int wsm_off[NCDE_MAX_LAYERS];
     int wsm_floats;
     const float* P;                         // [n_hg][B][DFP]
+    float* dz_out;                          // adjoint: write dL/d(stage input) here [H][Bp] instead of the RK update
     const float* actT[NCDE_MAX_LAYERS + 1]; // saved activations of this stage
     float* dpreT[NCDE_MAX_LAYERS];          // [D[l+1] pad4][Bp] scratch, consumed by hidden_wgrad
     float* gyT;                             // [H][Bp]  += dzs
@@ -156,23 +160,68 @@ enum { COMBINE_Y = 0, COMBINE_RK4_S2 = 1, COMBINE_RK4_S3 = 2, COMBINE_RK4_S4 = 3
 
 // Stage input of the RK scheme with the reference's operation order and no FMA contraction
 // (torchdiffeq/_impl/rk_common.py:106-114; _one_third / _two_thirds are rounded to fp32 by the tensor multiply).
-__device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int64_t off, const float* coef) {
-    const float y = a.yT[off];
+// increment of an RK stage input from the earlier stage derivatives (reference operation order, no FMA contraction)
+__device__ __forceinline__ float stage_increment(int combine, float dt, const float* const* kT, const float* coef, int64_t off) {
     const float third = 0.3333333432674408f;  // float32(1/3)
-    switch (a.combine) {
-        case COMBINE_Y: return y;
-        case COMBINE_RK4_S2:  // y0 + dt * k1 * (1/3)
-            return __fadd_rn(y, __fmul_rn(__fmul_rn(a.dt, a.kT[0][off]), third));
-        case COMBINE_RK4_S3:  // y0 + dt * (k2 - k1 * (1/3))
-            return __fadd_rn(y, __fmul_rn(a.dt, __fsub_rn(a.kT[1][off], __fmul_rn(a.kT[0][off], third))));
-        case COMBINE_RK4_S4:  // y0 + dt * (k1 - k2 + k3)
-            return __fadd_rn(y, __fmul_rn(a.dt, __fadd_rn(__fsub_rn(a.kT[0][off], a.kT[1][off]), a.kT[2][off])));
-        default: {            // y0 + sum_j k_j * coef_j
+    switch (combine) {
+        case COMBINE_Y: return 0.f;
+        case COMBINE_RK4_S2:  // dt * k1 * (1/3)
+            return __fmul_rn(__fmul_rn(dt, kT[0][off]), third);
+        case COMBINE_RK4_S3:  // dt * (k2 - k1 * (1/3))
+            return __fmul_rn(dt, __fsub_rn(kT[1][off], __fmul_rn(kT[0][off], third)));
+        case COMBINE_RK4_S4:  // dt * (k1 - k2 + k3)
+            return __fmul_rn(dt, __fadd_rn(__fsub_rn(kT[0][off], kT[1][off]), kT[2][off]));
+        default: {            // sum_j k_j * coef_j
             float acc = 0.f;
             for (int j = 0; j < NCDE_MAX_STAGES; ++j)
-                if (coef[j] != 0.f) acc = fmaf(a.kT[j][off], coef[j], acc);
-            return y + acc;
+                if (coef[j] != 0.f) acc = fmaf(kT[j][off], coef[j], acc);
+            return acc;
         }
+    }
+}
+__device__ __forceinline__ float combine_stage_input(const HiddenFwdArgs& a, int64_t off, const float* coef) {
+    const float y = a.yT[off];
+    if (a.combine == COMBINE_Y) return y;
+    const float inc = stage_increment(a.combine, a.dt, a.kT, coef, off);
+    return a.comb_sign < 0.f ? __fsub_rn(y, inc) : __fadd_rn(y, inc);
+}
+
+// generic elementwise pieces of the augmented (adjoint) RK scheme -------------------------------------------------
+struct AugCombineArgs {
+    int64_t n;
+    int combine;
+    float dt, sign;
+    const float* base;
+    const float* k[NCDE_MAX_STAGES];
+    float coef[NCDE_MAX_STAGES];
+    float* out;
+};
+// out = base + sign * increment(combine, k...)
+__global__ void aug_combine_kernel(const __grid_constant__ AugCombineArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float b = a.base[i];
+        if (a.combine == COMBINE_Y) { a.out[i] = b; continue; }
+        const float inc = stage_increment(a.combine, a.dt, a.k, a.coef, i);
+        a.out[i] = a.sign < 0.f ? __fsub_rn(b, inc) : __fadd_rn(b, inc);
+    }
+}
+// s += sign * (k1 + 3 (k2 + k3) + k4) * dt * 0.125   (rk4)   |   s += sign * dt * k1   (euler)
+__global__ void aug_advance_kernel(float* __restrict__ s, const float* k0, const float* k1, const float* k2, const float* k3,
+                                   int method, float dt, float sign, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float inc;
+        if (method == NCDE_RK4_38) {
+            float q = __fadd_rn(k0[i], __fmul_rn(3.f, __fadd_rn(k1[i], k2[i])));
+            q = __fadd_rn(q, k3[i]);
+            inc = __fmul_rn(__fmul_rn(q, dt), 0.125f);
+        } else {
+            inc = __fmul_rn(dt, k0[i]);
+        }
+        s[i] = sign < 0.f ? __fsub_rn(s[i], inc) : __fadd_rn(s[i], inc);
     }
 }
 
@@ -880,7 +929,7 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
     pdl_trigger();
     pdl_wait();  // P, gy, gk come from the previous kernels
     // gy / gk elements this thread updates at the end (fast path: at most 4 per thread)
-    const bool few = a.H * R <= 4 * kThreads;
+    const bool few = a.dz_out == nullptr && a.H * R <= 4 * kThreads;
     float pre_gy[4], pre_gk[4][3];
     if (few) {
 #pragma unroll
@@ -953,7 +1002,14 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
         __syncthreads();
         float* t = cur; cur = nxt; nxt = t;
     }
-    // 3. RK adjoint update with dzs = cur[h][r]
+    // 3. RK adjoint update with dzs = cur[h][r]  (or, for the continuous adjoint, just hand dzs out)
+    if (a.dz_out) {
+        for (int idx = tid; idx < a.H * R; idx += kThreads) {
+            const int h = idx / R, r = idx % R;
+            if (b0 + r < a.B) a.dz_out[(size_t)h * a.Bp + b0 + r] = cur[idx];
+        }
+        return;
+    }
     if (few) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -1072,6 +1128,11 @@ __global__ void hidden_wgrad_reduce_kernel(const __grid_constant__ WgradArgs a) 
         for (int sp = 0; sp < a.n_split; ++sp) s += a.gbp[slot][(size_t)sp * a.Dout[slot] + idx];
         a.gb[slot][idx] += s;
     }
+}
+
+// dst[i] += src[i]
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
 // packed row index of (h, c): h-groups of Hg rows-of-Cp, each group padded to Npad rows

@@ -215,6 +215,86 @@ class _FixedSolve(torch.autograd.Function):
         return (None, None, None, None, None, grad_z0, None) + tuple(grads)
 
 
+class _AdjointFixedSolve(torch.autograd.Function):
+    """adjoint=True with a fixed-grid method: forward without saving anything but the outputs, backward by integrating
+    the augmented system (y, a, g_theta) backwards over every output interval (ncde_solve_adjoint_bwd) — the continuous
+    adjoint of modules/torchdiffeq/torchdiffeq/_impl/adjoint.py:36-145."""
+
+    @staticmethod
+    def forward(ctx, X, spec, method, precision, sched, adj, t_host, z0, coeffs_for_graph, *params):
+        B, H = z0.shape
+        C = spec.weights[-1].shape[0] // H
+        dev = z0.device
+        problem, keep = _build_problem(X, spec, B, H, C, method, precision, sched)
+        L = _capi.lib()
+        z0c = z0.detach().contiguous()
+        z_out = torch.empty(sched.n_out, B, H, dtype=torch.float32, device=dev)
+        wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 0)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
+        launches = ctypes.c_int64(0)
+        _capi.check(L.ncde_solve_fwd(ctypes.byref(problem), z0c.data_ptr(), z_out.data_ptr(), None, 0, work.data_ptr(),
+                                     wbytes, None, None, ctypes.byref(launches), _capi.stream_ptr(dev)))
+        last_launches["fwd"] = launches.value
+        ctx.X, ctx.spec, ctx.precision, ctx.adj, ctx.t_host = X, spec, precision, adj, t_host
+        ctx.shape = (B, H, C)
+        ctx.save_for_backward(z_out)
+        return z_out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (z_out,) = ctx.saved_tensors
+        B, H, C = ctx.shape
+        spec, t_host = ctx.spec, ctx.t_host
+        adj_method, adj_options = ctx.adj
+        dev = grad_out.device
+        if ctx.needs_input_grad[8]:
+            raise NotImplementedError("gradients with respect to the control path coefficients are not implemented")
+        # backward schedule, last interval first, built in reversed time exactly like _check_inputs does (misc.py:262-283)
+        T = int(t_host.numel())
+        scheds = []
+        for i in range(T - 1, 0, -1):
+            tau = -t_host[i - 1:i + 1].flip(0)
+            scheds.append(FixedSchedule(tau, adj_method, adj_options.get("step_size"), None, None, None))
+        NS = 4 if adj_method == "rk4" else 1
+
+        class _Grid:
+            n_steps = sum(sc.n_steps for sc in scheds)
+            n_out = T
+            stage_t = np.ascontiguousarray(np.concatenate([-sc.stage_t.reshape(-1, NS) for sc in scheds]).astype(np.float32)) \
+                if scheds else np.zeros((1, NS), dtype=np.float32)
+            dt = np.ascontiguousarray(np.concatenate([sc.dt for sc in scheds]).astype(np.float32)) if scheds \
+                else np.zeros(1, dtype=np.float32)
+            out_step = np.zeros(1, dtype=np.int64)
+            out_mode = np.zeros(1, dtype=np.int32)
+            out_slope = np.zeros(1, dtype=np.float32)
+        interval_steps = np.ascontiguousarray(np.array([sc.n_steps for sc in scheds] + [0], dtype=np.int64))
+        problem, keep = _build_problem(ctx.X, spec, B, H, C, adj_method, ctx.precision, _Grid)
+        L = _capi.lib()
+        g = grad_out.contiguous()
+        grad_z0 = torch.empty(B, H, dtype=torch.float32, device=dev)
+        uniq = spec.unique_params
+        grads = [torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p, _, _ in uniq]
+        by_layer_w, by_layer_b = {}, {}
+        for gt, (_, kind, layer) in zip(grads, uniq):
+            (by_layer_w if kind == "W" else by_layer_b)[layer] = gt
+        gW = (ctypes.c_void_p * _capi.MAX_LAYERS)()
+        gb = (ctypes.c_void_p * _capi.MAX_LAYERS)()
+        first_of_slot = {}
+        for i in range(len(spec.weights)):
+            j = first_of_slot.setdefault(spec.slots[i], i)
+            gW[i] = by_layer_w[j].data_ptr()
+            gb[i] = by_layer_b[j].data_ptr() if j in by_layer_b else None
+        wbytes = L.ncde_solve_adjoint_workspace_bytes(ctypes.byref(problem))
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
+        launches = ctypes.c_int64(0)
+        _capi.check(L.ncde_solve_adjoint_bwd(ctypes.byref(problem), _np_ptr(interval_steps), T, z_out.data_ptr(),
+                                             g.data_ptr(), grad_z0.data_ptr(), gW, gb, work.data_ptr(), wbytes,
+                                             ctypes.byref(launches), _capi.stream_ptr(dev)))
+        last_launches["bwd"] = launches.value
+        ctx.nfe_bwd = _Grid.n_steps * NS
+        return (None, None, None, None, None, None, None, grad_z0, None) + tuple(grads)
+
+
 def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
     r"""Solves z_t = z_{t_0} + \int_{t_0}^t f(s, z_s) dX_s on the GPU.
 
@@ -295,16 +375,26 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
             raise NotImplementedError("perturb=True is not implemented")
         if unused:
             warnings.warn('{}: Unexpected arguments {}'.format('RK4' if method == 'rk4' else 'Euler', unused))
-        if adjoint:
-            raise NotImplementedError("adjoint=True with a fixed-grid solver is not implemented yet; every "
-                                      "configuration of the reference uses adjoint=False (SURVEY F6)")
         z0f = z0.reshape(-1, H)
         sched = _schedule(t_host, method, options, func, z0f)
         params = [p for p, _, _ in spec.unique_params]
         Xf = X
         if len(batch_shape) != 1:
             Xf = _flatten_path(X)
-        out = _FixedSolve.apply(Xf, spec, method, _PRECISIONS[precision], sched, z0f, coeffs, *params)
+        if adjoint:
+            # adjoint.py:159-171: adjoint_* default to the forward method / options (minus `norm`)
+            adj_method = kwargs.get('adjoint_method') or method
+            adj_options = kwargs.get('adjoint_options')
+            if adj_options is None:
+                adj_options = {k: v for k, v in options.items() if k != 'norm'}
+            if adj_method not in ('euler', 'rk4'):
+                raise NotImplementedError("adjoint_method '{}' is not implemented (euler, rk4 are)".format(adj_method))
+            if adj_options.get('grid_constructor') is not None:
+                raise NotImplementedError("grid_constructor is not implemented for the adjoint pass")
+            out = _AdjointFixedSolve.apply(Xf, spec, method, _PRECISIONS[precision], sched, (adj_method, dict(adj_options)),
+                                           t_host, z0f, coeffs, *params)
+        else:
+            out = _FixedSolve.apply(Xf, spec, method, _PRECISIONS[precision], sched, z0f, coeffs, *params)
         if hasattr(func, "nfe"):
             func.nfe += sched.n_steps * sched.n_stages
         out = out.reshape(sched.n_out, *batch_shape, H)
