@@ -198,6 +198,17 @@ int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* interval_step
                            const float* grad_out, float* grad_z0, float* const* gW, float* const* gbias,
                            void* workspace, size_t workspace_bytes, int64_t* launches, void* stream);
 
+/* Continuous adjoint with dopri5 as the adjoint method.  p->adaptive carries the ADJOINT tolerances / options and the
+ * forward output times (host).  One device-controlled adaptive solve of the augmented state (y, a, g_theta) per output
+ * interval in reversed time, with the reference's mixed error norm max(|vjp_t|, rms(y), rms(a), max_p rms(g_theta_p))
+ * (adjoint.py:235-246; vjp_t, the time-gradient scalar, is integrated for cubic paths and is exactly zero for linear ones).  The host reads a completion flag after
+ * every chunk of 4 attempts (one stream synchronisation per chunk).  stats: device int64[200] = attempted, accepted,
+ * evaluations, flags summed over the intervals, [8..199] = (dt, error ratio, accepted) as doubles for the first 64 attempts. */
+size_t ncde_solve_adjoint_adaptive_workspace_bytes(const ncde_problem_t* p);
+int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const float* y_out, const float* grad_out, float* grad_z0,
+                                    float* const* gW, float* const* gbias, void* workspace, size_t workspace_bytes,
+                                    int64_t* stats, int64_t* launches, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Per-kernel timing with CUDA events on the launching stream (measurement support for bench.py; no reference
  * counterpart).  While enabled, every launch of the kernel classes in `class_mask` is bracketed by an event

@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     uint32_t phase = 0;
     bool first_tile = true;
     const int64_t row_begin = (int64_t)bt * a.Bt;
-    const int64_t row_end = min((int64_t)a.Bp, row_begin + a.Bt);
+    const int64_t row_end = (a.ctrl && a.ctrl->done) ? row_begin : min((int64_t)a.Bp, row_begin + a.Bt);
     for (int64_t b0 = row_begin; b0 < row_end && b0 < a.B; b0 += kTcM) {
         load_tile_sw128(As, a.abf + (size_t)b0 * KP, kTcM, KP, (int)min((int64_t)kTcM, (int64_t)a.B - b0), tid, kTcThreads);
         load_dx_tile(dXs, a.dXT, a.Cp, a.Bp, b0, tid, kTcThreads);
@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
+    cp_async_wait_all();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 

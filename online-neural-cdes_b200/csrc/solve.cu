@@ -790,7 +790,7 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     AdaptParams ap;
     ap.t0 = ad.out_t[0]; ap.rtol = ad.rtol; ap.atol = ad.atol; ap.min_step = ad.min_step; ap.max_step = ad.max_step;
     ap.first_step = ad.first_step; ap.safety = ad.safety; ap.ifactor = ad.ifactor; ap.dfactor = ad.dfactor;
-    ap.max_attempts = ad.max_attempts; ap.n_out = (int)ad.n_out;
+    ap.max_attempts = ad.max_attempts; ap.n_out = (int)ad.n_out; ap.time_sign = 1; ap.keep_counters = 0;
     adapt_init_kernel<<<1, 32, 0, st>>>(ctrl, ap);
     ++launches;
 
@@ -1190,6 +1190,429 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
             axpy_kernel<<<(unsigned)ceil_div((int64_t)m.out_dim[l], 256), 256, 0, st>>>(gbias[l], theta + tl.off_b[l], m.out_dim[l]);
             ++launches;
         }
+    }
+    NCDE_CUDA_OK(cudaGetLastError());
+    if (launches_out) *launches_out = launches;
+    return NCDE_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Continuous adjoint with dopri5 (adjoint.py:36-145 with adjoint_method = dopri5).  One adaptive solve of the augmented
+// state per output interval, last interval first, in reversed time; the controller (adaptive_kernels.cuh) uses the
+// reference's mixed norm over (y, a, every parameter-gradient tensor).  p->adaptive holds the ADJOINT tolerances and
+// options and the forward output times.  The host polls a completion flag after every chunk of 4 attempts.
+// ---------------------------------------------------------------------------------------------------------------
+static size_t adjoint_adaptive_workspace_floats(const ncde_problem_t* p, const Plan& pl, int64_t n_out) {
+    size_t per = 256 / 4;
+    const size_t nHB = (size_t)pl.H * pl.Bp;
+    size_t n = adjoint_workspace_floats(p, pl);
+    n += (size_t)(2 + 2 * 3) * (nHB + per);    // y1, a_out, extra kf[3], ka[3]
+    size_t ntheta = 0;
+    for (int l = 0; l <= pl.F; ++l) ntheta += round_up((size_t)p->mlp.out_dim[l] * p->mlp.in_dim[l], 64) + round_up(p->mlp.out_dim[l], 64);
+    n += 5 * (ntheta + per);                   // ktheta[4..6], theta1, theta_out
+    n += sizeof(AdaptCtrl) / 4 + per + (size_t)(kMaxSeg + 1) * 2 * 128 * 2 + per + (size_t)n_out * 4 + per;
+    n += nHB + (size_t)pl.Cp * pl.Bp + 3 * per;   // time-gradient component: q, d2X/dt2, scalars
+    return n;
+}
+
+extern "C" size_t ncde_solve_adjoint_adaptive_workspace_bytes(const ncde_problem_t* p) {
+    Plan pl;
+    if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
+    return adjoint_adaptive_workspace_floats(p, pl, p->adaptive.n_out) * 4 + 4096;
+}
+
+extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const float* y_out, const float* grad_out,
+                                               float* grad_z0, float* const* gW, float* const* gbias, void* workspace,
+                                               size_t workspace_bytes, int64_t* stats, int64_t* launches_out, void* stream) {
+    NCDE_REQUIRE(p && y_out && grad_out && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID,
+                 "solve_adjoint_adaptive_bwd: null pointer");
+    NCDE_REQUIRE(p->method == NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_adjoint_adaptive_bwd: method must be dopri5");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc != NCDE_OK) return rc;
+    const ncde_adaptive_t& ad = p->adaptive;
+    const int64_t n_out = ad.n_out;
+    NCDE_REQUIRE(n_out >= 1 && ad.out_t && ad.max_attempts >= 1, NCDE_ERR_INVALID, "solve_adjoint_adaptive_bwd: bad adaptive block");
+    NCDE_REQUIRE(workspace_bytes >= adjoint_adaptive_workspace_floats(p, pl, n_out) * 4, NCDE_ERR_WORKSPACE,
+                 "solve_adjoint_adaptive_bwd: workspace of %zu bytes is too small", workspace_bytes);
+    NCDE_REQUIRE(p->path.K >= 2 && p->path.knots && p->path.coeffs, NCDE_ERR_INVALID, "solve: bad path");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t launches = 0;
+    const ncde_mlp_t& m = p->mlp;
+    const size_t nHB = (size_t)pl.H * pl.Bp;
+    for (int l = 0; l <= pl.F; ++l) NCDE_REQUIRE(gW[l] != nullptr, NCDE_ERR_INVALID, "solve_adjoint_adaptive_bwd: gW[%d] is null", l);
+
+    Carver cv{(char*)workspace, 0, workspace_bytes};
+    float* wpack = cv.take(pl.wpack_floats);
+    float* yT = cv.take(nHB);
+    float* y1T = cv.take(nHB);
+    float* aT = cv.take(nHB);
+    float* a_stage = cv.take(nHB);
+    float* a_out = cv.take(nHB);
+    float* kf[7]; float* ka[7];
+    for (int i = 0; i < 7; ++i) { kf[i] = cv.take(nHB); ka[i] = cv.take(nHB); }
+    float* stage = cv.take(pl.stage_floats);
+    float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
+    float* dpreT[NCDE_MAX_LAYERS] = {};
+    for (int l = 0; l < pl.F; ++l) dpreT[l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
+    const size_t nW3 = (size_t)pl.n_bt * pl.Np * pl.DFP, nb3 = (size_t)pl.n_bt * pl.Np;
+    float* dW3acc = cv.take(nW3);
+    float* db3acc = cv.take(nb3);
+    ThetaLayout tl;
+    theta_layout(p, pl, gW, gbias, &tl);
+    float* theta = cv.take(tl.total);
+    float* theta1 = cv.take(tl.total);
+    float* theta_out = cv.take(tl.total);
+    float* ktheta[7];
+    for (int i = 0; i < 7; ++i) ktheta[i] = cv.take(tl.total);
+    AdaptCtrl* ctrl = (AdaptCtrl*)cv.take(sizeof(AdaptCtrl) / 4 + 1);
+    const int nblocks = 128;
+    double* partials = (double*)cv.take((size_t)(kMaxSeg + 1) * 2 * nblocks * 2);
+    double* d_tau = (double*)cv.take((size_t)n_out * 4);
+    // time-gradient component vjp_t of the augmented state (adjoint.py:64,80-100).  The reference always integrates it
+    // and it enters the error norm as |.|; dX/dt of a linear path does not depend on t, so it stays exactly zero there.
+    const bool has_vt = p->path.kind != NCDE_PATH_LINEAR;
+    float* qT = cv.take(nHB);
+    float* ddXT = cv.take((size_t)pl.Cp * pl.Bp);
+    float* vts = cv.take(64);   // [0] vt, [1] candidate, [2] dense output at the interval end, [8..14] stage derivatives
+    float* kvt[7];
+    for (int i = 0; i < 7; ++i) kvt[i] = vts + 8 + i;
+
+    rc = pack_weights(p, pl, wpack, 1, st, &launches);
+    if (rc != NCDE_OK) return rc;
+    const bool use_tc = pl.tc != 0;
+    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem); }
+    else if (pl.TM == 8) { rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); }
+    else { rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem); }
+    if (rc == NCDE_OK) rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
+    if (rc == NCDE_OK) rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
+    if (rc != NCDE_OK) return rc;
+
+    HiddenFwdArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.B = pl.B; ha.Bp = pl.Bp; ha.H = pl.H; ha.C = pl.C; ha.Cp = pl.Cp; ha.R = pl.R; ha.F = pl.F; ha.Dmax = pl.Dmax;
+    for (int l = 0; l <= pl.F; ++l) ha.D[l] = pl.D[l];
+    for (int l = 0; l < pl.F; ++l) {
+        ha.ldw[l] = pl.ldw[l]; ha.act[l] = m.act[l];
+        ha.WT[l] = wpack + pl.off_WT[l]; ha.bp[l] = wpack + pl.off_bp[l];
+        ha.wsm_off[l] = (int)(pl.off_WT[l] - pl.off_WT[0]);
+    }
+    ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
+    ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
+    ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    for (int i = 0; i < 7; ++i) ha.kT[i] = kf[i];
+    ha.yT = yT; ha.KP = pl.KP; ha.comb_sign = -1.f; ha.combine = COMBINE_LINEAR; ha.ctrl = ctrl;
+    for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
+    ha.dXT = stage + pl.dx_off;
+    ha.ddXT = has_vt ? ddXT : nullptr;
+    ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
+
+    FieldArgs fa;
+    fill_field_args(fa, pl, wpack);
+    fa.actT = stage + pl.act_off[pl.F]; fa.dXT = stage + pl.dx_off;
+    fa.P = P; fa.dW3acc = dW3acc; fa.db3acc = db3acc; fa.gkT = a_stage; fa.ctrl = ctrl;
+    TcFieldArgs ta;
+    fill_tc_args(ta, pl, wpack);
+    ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off;
+    ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc; ta.gkT = a_stage; ta.ctrl = ctrl;
+
+    HiddenBwdArgs hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.B = pl.B; hb.Bp = pl.Bp; hb.H = pl.H; hb.R = pl.R; hb.F = pl.F; hb.Dmax = pl.Dmax; hb.DFP = pl.DFP; hb.n_hg = pl.n_hg;
+    for (int l = 0; l <= pl.F; ++l) { hb.D[l] = pl.D[l]; hb.actT[l] = stage + pl.act_off[l]; }
+    for (int l = 0; l < pl.F; ++l) {
+        hb.act[l] = m.act[l]; hb.W[l] = wpack + pl.off_WR[l]; hb.ldi[l] = pl.ldi[l]; hb.dpreT[l] = dpreT[l];
+        hb.wsm_off[l] = (int)(pl.off_WR[l] - pl.off_WR[0]);
+    }
+    hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
+    hb.P = P; hb.ctrl = ctrl;
+
+    WgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.B = pl.B; wa.Bp = pl.Bp; wa.n_split = pl.wg_split; wa.rows_per_split = pl.wg_rows; wa.n_stage = 1; wa.ctrl = ctrl;
+    int total_tiles = 0;
+    int slot_layer[NCDE_MAX_LAYERS];
+    for (int l = 0; l < pl.F; ++l) {
+        int sidx = -1;
+        for (int s2 = 0; s2 < wa.n_slots; ++s2) if (gW[slot_layer[s2]] == gW[l]) sidx = s2;
+        if (sidx < 0) {
+            sidx = wa.n_slots++;
+            slot_layer[sidx] = l;
+            wa.Dout[sidx] = m.out_dim[l]; wa.Din[sidx] = m.in_dim[l];
+        }
+        wa.lay[sidx][wa.n_lay[sidx]++] = l;
+        wa.dpreT[0][l] = dpreT[l];
+        wa.actT[0][l] = stage + pl.act_off[l];
+    }
+    size_t gwp_floats[NCDE_MAX_LAYERS], gbp_floats[NCDE_MAX_LAYERS];
+    for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+        wa.tile_begin[s2] = total_tiles;
+        total_tiles += (int)(ceil_div(wa.Dout[s2], kWgTile) * ceil_div(wa.Din[s2], kWgTile));
+        gwp_floats[s2] = (size_t)pl.wg_split * wa.Dout[s2] * wa.Din[s2];
+        gbp_floats[s2] = (size_t)pl.wg_split * wa.Dout[s2];
+        wa.gWp[s2] = cv.take(gwp_floats[s2]);
+        wa.gbp[s2] = cv.take(gbp_floats[s2]);
+    }
+    wa.tile_begin[wa.n_slots] = total_tiles;
+    NCDE_REQUIRE(cv.used <= workspace_bytes, NCDE_ERR_WORKSPACE, "solve_adjoint_adaptive_bwd: workspace accounting error");
+
+    // segments of the mixed norm: y, a, then every parameter-gradient tensor
+    struct Seg { size_t off; int64_t n; };
+    std::vector<Seg> tsegs;
+    for (int l = 0; l <= pl.F; ++l) {
+        bool first = true;
+        for (int j = 0; j < l; ++j) if (gW[j] == gW[l]) first = false;
+        if (!first) continue;
+        tsegs.push_back({tl.off_W[l], (int64_t)m.out_dim[l] * m.in_dim[l]});
+        if (tl.off_b[l] != (size_t)-1) tsegs.push_back({tl.off_b[l], (int64_t)m.out_dim[l]});
+    }
+    const int n_seg = 2 + (int)tsegs.size() + (has_vt ? 1 : 0);   // the time-gradient scalar is the last segment
+    NCDE_REQUIRE(n_seg <= kMaxSeg, NCDE_ERR_UNSUPPORTED, "too many parameter tensors");
+    AugCtrlArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.ctrl = ctrl; ca.partials = partials; ca.nblocks = nblocks; ca.n_seg = n_seg;
+    ca.count[0] = ca.count[1] = (double)pl.B * pl.H;
+    for (size_t i = 0; i < tsegs.size(); ++i) ca.count[2 + i] = (double)tsegs[i].n;
+    if (has_vt) ca.count[n_seg - 1] = 1.0;
+
+    const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
+    const unsigned ew_grid = (unsigned)ceil_div((int64_t)nHB, 256);
+    const unsigned th_grid = (unsigned)ceil_div((int64_t)tl.total, 256);
+
+    // one augmented evaluation: stage inputs from ctrl->tab[tab_index]; results into kf/ka/ktheta[k_out]
+    auto aeval = [&](int tab_index, int k_out, float* y_stage_T) -> int {
+        ha.tab_index = tab_index;
+        ha.actT[0] = y_stage_T ? y_stage_T : stage + pl.act_off[0];
+        hb.actT[0] = ha.actT[0];
+        wa.actT[0][0] = ha.actT[0];   // the first hidden layer's input is the stage input itself
+        if (pl.F == 0) { fa.actT = ha.actT[0]; }
+        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+        const dim3 fg(pl.n_hg, pl.n_bt);
+        if (use_tc) {
+            ta.koutT = kf[k_out];
+            NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, fg, dim3(kTcThreads), pl.fwd_smem, st, ta));
+        } else {
+            fa.koutT = kf[k_out];
+            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+        }
+        if (has_vt) {
+            // q[b,h] = sum_c F(z)[b,h,c] d2X/dt2[b,c]: the same field kernel with the second path derivative
+            if (use_tc) {
+                ta.koutT = qT; ta.dXT = ddXT;
+                NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, fg, dim3(kTcThreads), pl.fwd_smem, st, ta));
+                ta.dXT = stage + pl.dx_off;
+            } else {
+                fa.koutT = qT; fa.dXT = ddXT;
+                if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                fa.dXT = stage + pl.dx_off;
+            }
+            ++launches;
+        }
+        AugCombineArgs cb;
+        memset(&cb, 0, sizeof(cb));
+        cb.n = (int64_t)nHB; cb.combine = COMBINE_LINEAR; cb.sign = 1.f; cb.base = aT; cb.out = a_stage;
+        for (int j = 0; j < 7; ++j) cb.k[j] = ka[j];
+        cb.ctrl = ctrl; cb.tab_index = tab_index;
+        NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(ew_grid), dim3(256), 0, st, cb));
+        if (has_vt) {
+            // d(vjp_t)/dtau = sum_{b,h} a[b,h] q[b,h]
+            NCDE_CUDA_OK(launch_pdl(aug_dot_kernel, dim3(1), dim3(1024), 0, st, (const AdaptCtrl*)ctrl, (const float*)a_stage,
+                                    (const float*)qT, pl.B, pl.Bp, pl.H, kvt[k_out]));
+            ++launches;
+        }
+        NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, nW3 * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(db3acc, 0, nb3 * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(ktheta[k_out], 0, tl.total * 4, st));
+        for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+            NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, gwp_floats[s2] * 4, st));
+            NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
+        }
+        if (use_tc) NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, fg, dim3(kTcThreads), pl.bwd_smem, st, ta));
+        else if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+        else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+        hb.dz_out = ka[k_out];
+        NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
+        launches += 5;
+        if (pl.F > 0) {
+            for (int s2 = 0; s2 < wa.n_slots; ++s2) {
+                const int l0 = slot_layer[s2];
+                wa.gW[s2] = ktheta[k_out] + tl.off_W[l0];
+                wa.gb[s2] = tl.off_b[l0] == (size_t)-1 ? nullptr : ktheta[k_out] + tl.off_b[l0];
+            }
+            NCDE_CUDA_OK(launch_pdl(hidden_wgrad_kernel, dim3(total_tiles, pl.wg_split), dim3(kThreads), 0, st, wa));
+            int nmax = 0;
+            for (int s2 = 0; s2 < wa.n_slots; ++s2) nmax = wa.Dout[s2] * wa.Din[s2] > nmax ? wa.Dout[s2] * wa.Din[s2] : nmax;
+            hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, st>>>(wa);
+            launches += 2;
+        }
+        const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
+        unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+            dW3acc, db3acc, ktheta[k_out] + tl.off_W[pl.F],
+            tl.off_b[pl.F] == (size_t)-1 ? nullptr : ktheta[k_out] + tl.off_b[pl.F], pl.H, pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF,
+            pl.DFP, pl.Np, pl.n_bt);
+        ++launches;
+        return NCDE_OK;
+    };
+    // mixed-norm partial sums of the initial-step selection: mode 0 -> (s0, f0), mode 1 -> (f0, f1)
+    auto norms = [&](int mode, int kb) -> int {
+        const int kb0 = 0;
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)yT,
+                                (const float*)kf[kb0], (const float*)kf[kb], pl.B, pl.Bp, pl.H, partials + (size_t)0 * 2 * nblocks));
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)aT,
+                                (const float*)ka[kb0], (const float*)ka[kb], pl.B, pl.Bp, pl.H, partials + (size_t)1 * 2 * nblocks));
+        for (size_t i = 0; i < tsegs.size(); ++i)
+            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode,
+                                    (const float*)(theta + tsegs[i].off), (const float*)(ktheta[kb0] + tsegs[i].off),
+                                    (const float*)(ktheta[kb] + tsegs[i].off), (int)tsegs[i].n, (int)tsegs[i].n, 1,
+                                    partials + (size_t)(2 + i) * 2 * nblocks));
+        if (has_vt)
+            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)vts,
+                                    (const float*)kvt[kb0], (const float*)kvt[kb], 1, 1, 1, partials + (size_t)(n_seg - 1) * 2 * nblocks));
+        launches += n_seg;
+        return NCDE_OK;
+    };
+
+    // reversed output times tau_j = -t_j, per interval [tau_start, tau_target]
+    std::vector<double> h_tau((size_t)2 * (n_out > 1 ? n_out - 1 : 1));
+    for (int64_t iv = 0; iv + 1 < n_out; ++iv) {
+        const int64_t i_hi = n_out - 1 - iv;
+        h_tau[2 * iv] = -ad.out_t[i_hi];
+        h_tau[2 * iv + 1] = -ad.out_t[i_hi - 1];
+        NCDE_REQUIRE(h_tau[2 * iv + 1] > h_tau[2 * iv], NCDE_ERR_INVALID, "t must be strictly increasing");
+    }
+    if (n_out > 1) NCDE_CUDA_OK(cudaMemcpy(d_tau, h_tau.data(), h_tau.size() * 8, cudaMemcpyHostToDevice));
+
+    to_feature_major_kernel<<<tg, tb, 0, st>>>(y_out + (size_t)(n_out - 1) * pl.B * pl.H, yT, pl.B, pl.Bp, pl.H);
+    to_feature_major_kernel<<<tg, tb, 0, st>>>(grad_out + (size_t)(n_out - 1) * pl.B * pl.H, aT, pl.B, pl.Bp, pl.H);
+    launches += 2;
+    NCDE_CUDA_OK(cudaMemsetAsync(theta, 0, tl.total * 4, st));
+    NCDE_CUDA_OK(cudaMemsetAsync(vts, 0, 64 * 4, st));
+    NCDE_CUDA_OK(cudaMemsetAsync(ctrl, 0, sizeof(AdaptCtrl), st));
+
+    static int* h_done = nullptr;
+    if (!h_done) NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, sizeof(int), cudaHostAllocDefault));
+
+    for (int64_t iv = 0; iv + 1 < n_out; ++iv) {
+        const int64_t i_hi = n_out - 1 - iv;
+        const double* out_tau = d_tau + 2 * iv;
+        ca.out_t = out_tau;
+        AdaptParams ap;
+        ap.t0 = h_tau[2 * iv]; ap.rtol = ad.rtol; ap.atol = ad.atol; ap.min_step = ad.min_step; ap.max_step = ad.max_step;
+        ap.first_step = ad.first_step; ap.safety = ad.safety; ap.ifactor = ad.ifactor; ap.dfactor = ad.dfactor;
+        ap.max_attempts = ad.max_attempts; ap.n_out = 2; ap.time_sign = -1; ap.keep_counters = iv > 0 ? 1 : 0;
+        adapt_init_kernel<<<1, 32, 0, st>>>(ctrl, ap);
+        ++launches;
+        // f0 of the augmented system at the interval start
+        rc = aeval(0, 0, nullptr);
+        if (rc != NCDE_OK) return rc;
+        if (!(ad.first_step > 0)) {
+            rc = norms(0, 0);
+            if (rc != NCDE_OK) return rc;
+            NCDE_CUDA_OK(launch_pdl(aug_init_step1_kernel, dim3(1), dim3(32), 0, st, ca));
+            rc = aeval(NCDE_MAX_STAGES, 1, nullptr);
+            if (rc != NCDE_OK) return rc;
+            rc = norms(1, 1);
+            if (rc != NCDE_OK) return rc;
+            NCDE_CUDA_OK(launch_pdl(aug_init_step2_kernel, dim3(1), dim3(32), 0, st, ca));
+            launches += 2;
+        }
+        int64_t enq = 0;
+        bool finished = false;
+        while (enq < ad.max_attempts && !finished) {
+            for (int c4 = 0; c4 < 4 && enq < ad.max_attempts; ++c4, ++enq) {
+                for (int i = 1; i <= 6; ++i) {
+                    rc = aeval(i, i, i == 6 ? y1T : nullptr);
+                    if (rc != NCDE_OK) return rc;
+                }
+                // theta candidate = theta + sum_j beta_6j dt ktheta_j (the 7th stage input of the parameter component)
+                AugCombineArgs cb;
+                memset(&cb, 0, sizeof(cb));
+                cb.n = (int64_t)tl.total; cb.combine = COMBINE_LINEAR; cb.sign = 1.f; cb.base = theta; cb.out = theta1;
+                for (int j = 0; j < 7; ++j) cb.k[j] = ktheta[j];
+                cb.ctrl = ctrl; cb.tab_index = 6;
+                NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(th_grid), dim3(256), 0, st, cb));
+                if (has_vt) {
+                    cb.n = 1; cb.base = vts; cb.out = vts + 1;
+                    for (int j = 0; j < 7; ++j) cb.k[j] = kvt[j];
+                    NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(1), dim3(32), 0, st, cb));
+                    ++launches;
+                }
+                // error ratio per segment
+                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)yT,
+                                        (const float*)y1T, (const float*)kf[0], (const float*)kf[1], (const float*)kf[2],
+                                        (const float*)kf[3], (const float*)kf[4], (const float*)kf[5], (const float*)kf[6],
+                                        (int64_t)nHB, pl.Bp, pl.B, partials));
+                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)aT,
+                                        (const float*)a_stage, (const float*)ka[0], (const float*)ka[1], (const float*)ka[2],
+                                        (const float*)ka[3], (const float*)ka[4], (const float*)ka[5], (const float*)ka[6],
+                                        (int64_t)nHB, pl.Bp, pl.B, partials + (size_t)1 * 2 * nblocks));
+                for (size_t i = 0; i < tsegs.size(); ++i) {
+                    const size_t o = tsegs[i].off;
+                    NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl,
+                                            (const float*)(theta + o), (const float*)(theta1 + o), (const float*)(ktheta[0] + o),
+                                            (const float*)(ktheta[1] + o), (const float*)(ktheta[2] + o), (const float*)(ktheta[3] + o),
+                                            (const float*)(ktheta[4] + o), (const float*)(ktheta[5] + o), (const float*)(ktheta[6] + o),
+                                            tsegs[i].n, 0, 0, partials + (size_t)(2 + i) * 2 * nblocks));
+                }
+                if (has_vt)
+                    NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)vts,
+                                            (const float*)(vts + 1), (const float*)kvt[0], (const float*)kvt[1], (const float*)kvt[2],
+                                            (const float*)kvt[3], (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6],
+                                            (int64_t)1, 0, 0, partials + (size_t)(n_seg - 1) * 2 * nblocks));
+                NCDE_CUDA_OK(launch_pdl(aug_ctrl_kernel, dim3(1), dim3(32), 0, st, ca));
+                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, yT, (const float*)y1T,
+                                        kf[0], (const float*)kf[1], (const float*)kf[2], (const float*)kf[3], (const float*)kf[4],
+                                        (const float*)kf[5], (const float*)kf[6], (float*)nullptr, (int64_t)nHB, out_tau));
+                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, aT, (const float*)a_stage,
+                                        ka[0], (const float*)ka[1], (const float*)ka[2], (const float*)ka[3], (const float*)ka[4],
+                                        (const float*)ka[5], (const float*)ka[6], a_out, (int64_t)nHB, out_tau));
+                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(th_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, theta, (const float*)theta1,
+                                        ktheta[0], (const float*)ktheta[1], (const float*)ktheta[2], (const float*)ktheta[3],
+                                        (const float*)ktheta[4], (const float*)ktheta[5], (const float*)ktheta[6], theta_out,
+                                        (int64_t)tl.total, out_tau));
+                if (has_vt) {
+                    NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(1), dim3(32), 0, st, (const AdaptCtrl*)ctrl, vts, (const float*)(vts + 1),
+                                            kvt[0], (const float*)kvt[1], (const float*)kvt[2], (const float*)kvt[3],
+                                            (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6], vts + 2, (int64_t)1, out_tau));
+                    ++launches;
+                }
+                launches += 7 + n_seg;
+            }
+            NCDE_CUDA_OK(cudaMemcpyAsync(h_done, &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            NCDE_CUDA_OK(cudaStreamSynchronize(st));
+            finished = *h_done != 0;
+        }
+        // interval end (adjoint.py:131-133): adjoint and parameter gradients from the dense output at t_{i-1}, the state
+        // from the stored forward solution, plus the gradient arriving at t_{i-1}
+        NCDE_CUDA_OK(cudaMemcpyAsync(aT, a_out, nHB * 4, cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(theta, theta_out, tl.total * 4, cudaMemcpyDeviceToDevice, st));
+        if (has_vt) NCDE_CUDA_OK(cudaMemcpyAsync(vts, vts + 2, 4, cudaMemcpyDeviceToDevice, st));
+        to_feature_major_kernel<<<tg, tb, 0, st>>>(y_out + (size_t)(i_hi - 1) * pl.B * pl.H, yT, pl.B, pl.Bp, pl.H);
+        add_out_grad_kernel<<<tg, tb, 0, st>>>(aT, grad_out + (size_t)(i_hi - 1) * pl.B * pl.H, 1.f, pl.B, pl.Bp, pl.H);
+        launches += 2;
+    }
+    from_feature_major_kernel<<<tg, tb, 0, st>>>(aT, nullptr, grad_z0, pl.B, pl.Bp, pl.H);
+    ++launches;
+    for (int l = 0; l <= pl.F; ++l) {
+        bool first = true;
+        for (int j = 0; j < l; ++j) if (gW[j] == gW[l]) first = false;
+        if (!first) continue;
+        const int64_t nw = (int64_t)m.out_dim[l] * m.in_dim[l];
+        axpy_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, st>>>(gW[l], theta + tl.off_W[l], nw);
+        ++launches;
+        if (gbias[l]) {
+            axpy_kernel<<<(unsigned)ceil_div((int64_t)m.out_dim[l], 256), 256, 0, st>>>(gbias[l], theta + tl.off_b[l], m.out_dim[l]);
+            ++launches;
+        }
+    }
+    if (stats) {
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats, &ctrl->attempted, 3 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(stats + 3, 0, sizeof(int64_t), st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 3, &ctrl->flags, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(stats + 8, &ctrl->trace[0][0], 64 * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     NCDE_CUDA_OK(cudaGetLastError());
     if (launches_out) *launches_out = launches;

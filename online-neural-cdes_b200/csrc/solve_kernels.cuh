@@ -40,6 +40,7 @@ struct AdaptCtrl {
     double acc_dt;                  // dt of the last accepted step (dense-output coefficients)
     double rtol, atol, min_step, max_step, safety, ifactor, dfactor;
     int accept, done, j_begin, j_end, j_out, n_out;
+    int time_sign;                  // +1 forward solve; -1 adjoint (controller runs in reversed time, paths are evaluated at -tau)
     long long attempted, accepted, nfe, max_attempts;
     int flags;
     float h0, d0, d1, d2;           // initial-step selection scratch (misc.py:32-71)
@@ -63,6 +64,7 @@ struct HiddenFwdArgs {
     const float* kT[NCDE_MAX_STAGES];
     float* actT[NCDE_MAX_LAYERS + 1];  // actT[l] = [D[l] (padded to 4)][Bp], l = 0..F, for THIS stage
     float* dXT;                        // [Cp][Bp]
+    float* ddXT;                       // [Cp][Bp] or null: d2X/dt2 (cubic paths; time-gradient component of the adjoint)
     __nv_bfloat16* abf;                // [Bp][KP] bf16 row-major copy of the final-layer input (tensor-core path) or null
     int KP;
     int w_in_smem;                     // hidden weights are staged in shared memory for the whole launch
@@ -116,6 +118,7 @@ struct HiddenBwdArgs {
     int wsm_floats;
     const float* P;                         // [n_hg][B][DFP]
     float* dz_out;                          // adjoint: write dL/d(stage input) here [H][Bp] instead of the RK update
+    const AdaptCtrl* ctrl;                  // adaptive adjoint: no-op once ctrl->done
     const float* actT[NCDE_MAX_LAYERS + 1]; // saved activations of this stage
     float* dpreT[NCDE_MAX_LAYERS];          // [D[l+1] pad4][Bp] scratch, consumed by hidden_wgrad
     float* gyT;                             // [H][Bp]  += dzs
@@ -140,6 +143,7 @@ struct WgradArgs {
     float* gbp[NCDE_MAX_LAYERS];          // per slot: [n_split][Dout]
     float* gW[NCDE_MAX_LAYERS];           // per slot: caller's gradient (torch layout), used by the final reduction
     float* gb[NCDE_MAX_LAYERS];           // per slot, nullable
+    const AdaptCtrl* ctrl;                // adaptive adjoint: no-op once ctrl->done
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -195,11 +199,19 @@ struct AugCombineArgs {
     const float* k[NCDE_MAX_STAGES];
     float coef[NCDE_MAX_STAGES];
     float* out;
+    const AdaptCtrl* ctrl;   // adaptive: coefficients from ctrl->tab[tab_index]; no-op once ctrl->done
+    int tab_index;
 };
 // out = base + sign * increment(combine, k...)
-__global__ void aug_combine_kernel(const __grid_constant__ AugCombineArgs a) {
+__global__ void aug_combine_kernel(const __grid_constant__ AugCombineArgs a0) {
     pdl_trigger();
     pdl_wait();
+    AugCombineArgs a = a0;
+    if (a.ctrl) {
+        if (a.ctrl->done) return;
+#pragma unroll
+        for (int j = 0; j < NCDE_MAX_STAGES; ++j) a.coef[j] = a.ctrl->tab[a.tab_index].coef[j];
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
         const float b = a.base[i];
         if (a.combine == COMBINE_Y) { a.out[i] = b; continue; }
@@ -483,6 +495,19 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             const int64_t b = b0 + r;
             if (b < a.B) a.dXT[(int64_t)c * a.Bp + b] = tmp[c * R + r];
         }
+        if (a.ddXT) {
+            // d/dt of NaturalCubicSpline.derivative (interpolation_cubic.py:331-336): 2c + 2 (3d) frac; zero for linear paths
+            for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
+                const int r = idx / a.Cp, c = idx % a.Cp;
+                const int64_t b = b0 + r;
+                float v = 0.f;
+                if (b < a.B && c < a.C && a.path.kind != NCDE_PATH_LINEAR) {
+                    const float* row = a.path.coeffs + ((int64_t)b * (a.path.K - 1) + idxk) * 4 * a.C;
+                    v = __fadd_rn(row[2 * a.C + c], __fmul_rn(2.f, __fmul_rn(row[3 * a.C + c], frac)));
+                }
+                if (b < a.B) a.ddXT[(int64_t)c * a.Bp + b] = v;
+            }
+        }
     }
     if (a.w_in_smem) cp_async_wait_all_();
     __syncthreads();
@@ -747,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     const bool dg_active = md < kChunk / 4;
     pdl_trigger();
     pdl_wait();  // gk comes from the previous kernels
+    if (a.ctrl && a.ctrl->done) return;
 
     const int64_t row_begin = (int64_t)bt * a.Bt;
     const int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
@@ -928,6 +954,7 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
     }
     pdl_trigger();
     pdl_wait();  // P, gy, gk come from the previous kernels
+    if (a.ctrl && a.ctrl->done) { cp_async_wait_all_(); return; }
     // gy / gk elements this thread updates at the end (fast path: at most 4 per thread)
     const bool few = a.dz_out == nullptr && a.H * R <= 4 * kThreads;
     float pre_gy[4], pre_gk[4][3];
@@ -1052,6 +1079,7 @@ __global__ void __launch_bounds__(kThreads) hidden_wgrad_kernel(const __grid_con
     __shared__ __align__(16) float aS[kWgRows][kWgTile + 4];  // [b][i]
     pdl_trigger();
     pdl_wait();  // dpre comes from hidden_bwd
+    if (a.ctrl && a.ctrl->done) return;
     const int tid = threadIdx.x;
     int slot = 0;
     while (slot + 1 < a.n_slots && (int)blockIdx.x >= a.tile_begin[slot + 1]) ++slot;

@@ -73,7 +73,8 @@ SYMBOLS = ["ncde_version", "ncde_last_error", "ncde_abi_version", "ncde_forward_
            "ncde_linear_fill_missing", "ncde_cubic_scratch_bytes", "ncde_natural_cubic_coeffs", "ncde_linear_derivs",
            "ncde_path_eval", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
            "ncde_solve_bwd", "ncde_solve_adaptive_fwd", "ncde_solve_adjoint_workspace_bytes",
-           "ncde_solve_adjoint_bwd", "ncde_profile_enable", "ncde_profile_read"]
+           "ncde_solve_adjoint_bwd", "ncde_solve_adjoint_adaptive_workspace_bytes",
+           "ncde_solve_adjoint_adaptive_bwd", "ncde_profile_enable", "ncde_profile_read"]
 
 PROF_CLASSES = ["hidden_fwd", "field_fwd", "field_bwd", "hidden_bwd", "hidden_wgrad", "other"]
 
@@ -113,6 +114,10 @@ def lib():
     L.ncde_solve_adjoint_workspace_bytes.restype = sz
     L.ncde_solve_adjoint_bwd.argtypes = [ctypes.POINTER(Problem), vp, i64, vp, vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                          vp, sz, ctypes.POINTER(ctypes.c_int64), vp]
+    L.ncde_solve_adjoint_adaptive_workspace_bytes.argtypes = [ctypes.POINTER(Problem)]
+    L.ncde_solve_adjoint_adaptive_workspace_bytes.restype = sz
+    L.ncde_solve_adjoint_adaptive_bwd.argtypes = [ctypes.POINTER(Problem), vp, vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                  vp, sz, vp, ctypes.POINTER(ctypes.c_int64), vp]
     L.ncde_profile_enable.argtypes = [i32]
     L.ncde_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     for name in SYMBOLS:

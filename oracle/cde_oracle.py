@@ -552,6 +552,7 @@ class Dopri5:
                 if dt <= self.min_step:
                     accept = True
                 self.stats["attempted"] += 1
+                self.stats.setdefault("trace", []).append((float(dt), float(ratio), bool(accept)))
                 if accept:
                     self.stats["accepted"] += 1
                     coeffs = self._fit(y, y1, kk, dt)
@@ -584,7 +585,7 @@ def odeint(f, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, options=None, stats=
     sol = solver.integrate(t)
     if stats is not None:
         for k, v in solver.stats.items():
-            stats[k] = stats.get(k, 0) + v
+            stats[k] = stats.get(k, [] if k == "trace" else 0) + v
     return sol
 
 
@@ -621,6 +622,8 @@ class _Adjoint(torch.autograd.Function):
             vals = [parts[0].abs(), rms_norm(parts[1]), rms_norm(parts[2])]
             if len(parts) > 3:
                 vals.append(max(rms_norm(p) for p in parts[3:]))
+            if stats is not None and stats.get("record_norms"):
+                stats.setdefault("norm_vals", []).append([float(v) for v in vals])
             return max(vals)
 
         timed = _Timed(f)
@@ -652,7 +655,8 @@ class _Adjoint(torch.autograd.Function):
         return (None,) * 8 + (state[2],) + tuple(state[3:])
 
 
-def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, options=None, stats=None):
+def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, options=None, stats=None,
+           adjoint_rtol=None, adjoint_atol=None, adjoint_options=None):
     """tcde/solver.py:140-238 for a single batch dimension, 'matmul' vector fields and tensor state:
     g(t, z) = func(t, z) @ dX/dt(t); returns (B, len(t), H).  Defaults atol=1e-6 / rtol=1e-4 (:193-196);
     adjoint_* default to the forward values with `norm` dropped (tdeq/adjoint.py:159-171)."""
@@ -664,8 +668,14 @@ def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, opti
 
     if adjoint:
         params = tuple(p for p in func.parameters() if p.requires_grad)
-        adj_options = {k: v for k, v in (options or {}).items() if k != "norm"}
-        out = _Adjoint.apply(g, t, method, rtol, atol, options, (rtol, atol, adj_options), stats, z0, *params)
+        # tdeq/adjoint.py:159-171
+        adj_rtol = rtol if adjoint_rtol is None else adjoint_rtol
+        adj_atol = atol if adjoint_atol is None else adjoint_atol
+        if adjoint_options is None:
+            adj_options = {k: v for k, v in (options or {}).items() if k != "norm"}
+        else:
+            adj_options = dict(adjoint_options)
+        out = _Adjoint.apply(g, t, method, rtol, atol, options, (adj_rtol, adj_atol, adj_options), stats, z0, *params)
     else:
         out = odeint(g, z0, t, method, rtol, atol, options, stats)
     return out.transpose(0, 1)
