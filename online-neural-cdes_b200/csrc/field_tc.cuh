@@ -9,21 +9,26 @@
 // Tiles are filled with ordinary 16-byte stores (the operands are produced or converted in the kernel anyway),
 // followed by fence.proxy.async so the tensor-core (async proxy) reads see them.
 #pragma once
+#include <cuda.h>        // CUtensorMap (types only; the encoder is resolved at run time, nothing links against libcuda)
 #include <cuda_bf16.h>
 
 #include "solve_kernels.cuh"
 
 namespace ncde {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcEpiThreads = 256;             // 8 epilogue warps: thread = TMEM lane (batch row), two warp-groups split the columns
+constexpr int kTcThreads = kTcEpiThreads + 32; // + one producer warp: TMA loads and every tcgen05.mma are issued by its lane 0
 constexpr int kTcM = 128;  // batch rows per MMA tile (= TMEM lanes)
+constexpr int kTcKP = 128; // K of the final layer padded to two 64-column swizzle blocks
 
 struct TcFieldArgs {
     int B, Bp, H, Cp, Hg, n_hg, Npad, KP, DF, Bt;
+    int CpB;                   // floats per dX/dt row in shared memory (Cp padded so that CpB/4 is odd: conflict-free LDS.128)
+    int rec_a, rec_x;          // record (RK stage) index inside the activation / dX tensor maps
     const __nv_bfloat16* Wbf;  // [n_hg][Npad][KP]
     const float* b3;           // [n_hg][Npad]
-    const __nv_bfloat16* abf;  // [Bp][KP] final-layer input, bf16 row-major
-    const float* dXT;          // [Cp][Bp]
+    const __nv_bfloat16* abf;  // [Bp][KP] final-layer input, bf16 row-major            (read through TMA map A)
+    const float* dXT;          // [Bp][Cp] dX/dt, ROW-major on the tensor-core path      (read through TMA map X)
     float* koutT;              // [H][Bp]            forward
     const float* gkT;          // [H][Bp]            backward
     float* P;                  // [n_hg][B][DFP]     backward
@@ -32,6 +37,10 @@ struct TcFieldArgs {
     int DFP;
     const AdaptCtrl* ctrl;     // adaptive solver: skip all work once ctrl->done
 };
+
+// TMA descriptors of one launch: W = packed final-layer weights {k, n} box {64, Npad}; A = bf16 activations {k, b, rec}
+// box {64, 128, 1}; X = dX/dt {c, b, rec} box {CpB, 128, 1}.  A and W use the 128-byte swizzle (the UMMA canonical layout).
+struct TcMaps { CUtensorMap W, A, X; };
 
 __host__ __device__ inline uint32_t tc_tmem_cols(int need) {
     return need <= 32 ? 32u : (need <= 64 ? 64u : (need <= 128 ? 128u : (need <= 256 ? 256u : 512u)));
@@ -69,6 +78,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA tile loads (cp.async.bulk.tensor): completion is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // tcgen05.commit: the mbarrier receives one arrival when every previously issued MMA of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -104,6 +139,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue-only variants: the registers are valid after tmem_wait_ld(...) on the same array
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// tcgen05.wait::ld, tied to the destination registers so that no use of them can be scheduled above the wait
+template <int W>
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[W]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < W; i += 8)
+        asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]), "+r"(r[i + 6]),
+                          "+r"(r[i + 7]));
+}
+template <int W>
+__device__ __forceinline__ void tmem_ldw_issue(uint32_t taddr, uint32_t (&r)[W]);
+template <>
+__device__ __forceinline__ void tmem_ldw_issue<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8_issue(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ldw_issue<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_issue(taddr, r); }
+
 template <int W>
 __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[W]);
 template <>
@@ -210,33 +277,6 @@ __global__ void pack_final_bf16_kernel(const float* __restrict__ W, const float*
     }
 }
 
-// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes == 0 zero-fills the destination
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// cooperative asynchronous copy of a [rows][KP] bf16 row-major global tile into the swizzled shared layout; rows >=
-// valid_rows are zero-filled (batch padding must not reach the weight-gradient reduction: 0 * garbage could be NaN)
-__device__ __forceinline__ void load_tile_sw128(uint8_t* smem_tile, const __nv_bfloat16* __restrict__ g, int rows, int KP,
-                                                int valid_rows, int tid, int nthreads) {
-    const int cpr = KP / 8;  // 16-byte chunks per row
-    for (int idx = tid; idx < rows * cpr; idx += nthreads) {
-        const int r = idx / cpr, ch = idx % cpr;
-        const bool ok = r < valid_rows;
-        cp_async16(smem_tile + sw128_off(r, ch, rows), g + (size_t)(ok ? r : 0) * KP + ch * 8, ok ? 16 : 0);
-    }
-}
-
-// dXs[c][r] = dXT[c][b0 + r] for the 128 rows of a tile
-__device__ __forceinline__ void load_dx_tile(float* dXs, const float* __restrict__ dXT, int Cp, int Bp, int64_t b0, int tid,
-                                             int nthreads) {
-    for (int idx = tid; idx < Cp * (kTcM / 4); idx += nthreads) {
-        const int c = idx / (kTcM / 4), q = idx % (kTcM / 4);
-        cp_async16(dXs + (size_t)idx * 4, dXT + (size_t)c * Bp + b0 + q * 4, 16);
-    }
-}
-
 // D[128 x N] (+)= A[128 x K] . B[N x K]^T, both operands K-major swizzled tiles; one thread issues
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_saddr, int a_rows, uint32_t b_saddr, int b_rows,
                                                   int N, int K, bool accumulate_first) {
@@ -249,164 +289,219 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_sa
     }
 }
 
-// sum_j tanh(D[row][col0 + j] + b3[j]) * dX[j][row] over W consecutive channels; dx points at dXs[c0][row]
+// sum_j tanh(D[row][col0 + j] + b3[j]) * dX[row][j] over W consecutive channels.  b3_s / dx_s are shared-memory byte
+// addresses (16-byte aligned); both are read as LDS.128 while the TMEM load is in flight.
 template <int W>
-__device__ __forceinline__ float fwd_chunk(uint32_t taddr, const float* __restrict__ b3, const float* __restrict__ dx) {
-    float v[W];
-    tmem_ldw<W>(taddr, v);
-    float acc0 = 0.f, acc1 = 0.f;
+__device__ __forceinline__ float fwd_chunk(uint32_t taddr, uint32_t b3_s, uint32_t dx_s) {
+    uint32_t r[W];
+    tmem_ldw_issue<W>(taddr, r);
+    float4 bb[W / 4], dd[W / 4];
 #pragma unroll
-    for (int j = 0; j < W; j += 2) {
-        acc0 = fmaf(tanh_fast(v[j] + b3[j]), dx[j * kTcM], acc0);
-        acc1 = fmaf(tanh_fast(v[j + 1] + b3[j + 1]), dx[(j + 1) * kTcM], acc1);
+    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(b3_s + 16u * q); dd[q] = lds128(dx_s + 16u * q); }
+    tmem_wait_ld<W>(r);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        acc0 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 0]) + bb[q].x), dd[q].x, acc0);
+        acc1 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 1]) + bb[q].y), dd[q].y, acc1);
+        acc2 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 2]) + bb[q].z), dd[q].z, acc2);
+        acc3 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 3]) + bb[q].w), dd[q].w, acc3);
     }
-    return acc0 + acc1;
+    return (acc0 + acc1) + (acc2 + acc3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward:  k[b, h] = sum_c tanh( a[b,:] . W3[(h,c),:] + b3[(h,c)] ) * dX[b, c]
-// CTA (g, bt): W slice of h-group g resident in shared memory; 128-row tiles of the batch stream through.
+// CTA (g, bt): the W3 slice of h-group g stays in shared memory; the 128-row tiles of the batch stream through a
+// warp-specialised pipeline.  Warp 8 (one elected lane) is the producer: TMA loads of the bf16 activation tile and of the
+// dX/dt tile (both double-buffered) and the tcgen05.mma of tile i+1 into the second TMEM accumulator, all while warps
+// 0-7 run the epilogue of tile i (the CUDA-core-bound part: one MUFU.TANH per element).  Hand-offs are mbarriers only:
+//   full_a[b] / full_x[b]  TMA -> MMA / epilogue        mma[b]  MMA complete -> epilogue, activation buffer free
+//   done[b]                epilogue finished (8 warp arrivals) -> accumulator b and dX buffer b free
 // Epilogue: thread = one TMEM lane (batch row); the two warp-groups split the columns.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __grid_constant__ TcFieldArgs a) {
+struct TcFwdSmem {   // byte offsets from the 1024-aligned base
+    uint32_t Ws, As, dXs, b3s, part, bars, total;
+};
+__host__ __device__ inline TcFwdSmem tc_fwd_layout(int Npad, int CpB) {
+    TcFwdSmem L;
+    uint32_t o = 0;
+    L.Ws = o; o += (uint32_t)Npad * kTcKP * 2;
+    L.As = o; o += 2u * kTcM * kTcKP * 2;
+    L.dXs = o; o += 2u * kTcM * (uint32_t)CpB * 4;
+    L.b3s = o; o += (uint32_t)Npad * 4;
+    L.part = o; o += kTcM * 4;
+    o = (o + 15u) & ~15u;
+    L.bars = o; o += 16 * 8;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __grid_constant__ TcFieldArgs a,
+                                                                     const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve (every operand tile 1024-byte aligned)
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int Npad = a.Npad, KP = a.KP;
-    uint8_t* Ws = smem;                                 // [Npad][KP] bf16 swizzled
-    uint8_t* As = Ws + (size_t)Npad * KP * 2;           // [128][KP]
-    float* b3s = reinterpret_cast<float*>(As + (size_t)kTcM * KP * 2);  // [Npad]
-    float* part = b3s + Npad;                           // [2][Hg][128] per-warp-group partial sums
-    float* dXs = part + 2 * a.Hg * kTcM;                // [Cp][128] dX/dt of the current row tile
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(dXs + (size_t)a.Cp * kTcM);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int Npad = a.Npad;
+    const TcFwdSmem L = tc_fwd_layout(Npad, a.CpB);
+    const uint32_t a_bytes = kTcM * kTcKP * 2, x_bytes = kTcM * (uint32_t)a.CpB * 4;
+    uint8_t* Ws = smem + L.Ws;
+    uint8_t* As = smem + L.As;
+    uint8_t* dXs = smem + L.dXs;
+    float* b3s = reinterpret_cast<float*>(smem + L.b3s);
+    float* part = reinterpret_cast<float*>(smem + L.part);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* full_a = bars;          // [2]
+    uint64_t* full_x = bars + 2;      // [2]
+    uint64_t* mma_bar = bars + 4;     // [2]
+    uint64_t* done = bars + 6;        // [2]
+    uint64_t* w_bar = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x, bt = blockIdx.y;
-    // power of two >= Npad + 16: the last 16-column epilogue load may start up to 15 columns before Npad
-    const uint32_t ncols = tc_tmem_cols(Npad + 16);
+    const uint32_t acc_stride = tc_tmem_cols(Npad);     // columns per accumulator (power of two >= 32)
 
-    if (warp == 0) tmem_alloc(tmem_slot, ncols);
-    if (tid == 0) mbar_init(mbar, 1);
-    load_tile_sw128(Ws, a.Wbf + (size_t)g * Npad * KP, Npad, KP, Npad, tid, kTcThreads);
+    if (warp == 0) tmem_alloc(tmem_slot, 2 * acc_stride);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full_a + i, 1); mbar_init(full_x + i, 1); mbar_init(mma_bar + i, 1); mbar_init(done + i, 8); }
+        mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < Npad; i += kTcThreads) b3s[i] = a.b3[(size_t)g * Npad + i];
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool producer = warp == 8 && lane == 0;
+    if (producer) {
+        // the packed weights were written long before the predecessor kernel started: safe to fetch ahead of the dependency
+        tma_prefetch_desc(&maps.A);
+        tma_prefetch_desc(&maps.X);
+        mbar_expect_tx(w_bar, (uint32_t)Npad * kTcKP * 2);
+        tma_load_3d(Ws, &maps.W, w_bar, 0, g * Npad, 0);
+        tma_load_3d(Ws + (size_t)Npad * 128, &maps.W, w_bar, 64, g * Npad, 0);
+    }
     pdl_trigger();
     pdl_wait();  // the activation tiles come from hidden_fwd
 
-    const int wg = warp >> 2;                    // warp-group 0/1
-    const int row = (warp & 3) * 32 + lane;      // TMEM lane == row inside the tile
-    // share of this warp-group: a set of whole h's when Hg >= 2, else half of the channels of the single h
-    int h_begin, h_end, c_begin, c_end;
-    if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
-    else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
-
-    uint32_t phase = 0;
     const int64_t row_begin = (int64_t)bt * a.Bt;
-    const int64_t row_end = (a.ctrl && a.ctrl->done) ? row_begin : min((int64_t)a.Bp, row_begin + a.Bt);
-    for (int64_t b0 = row_begin; b0 < row_end && b0 < a.B; b0 += kTcM) {
-        // asynchronous fills: activation tile (MMA operand) and dX/dt of these 128 rows (epilogue operand)
-        load_tile_sw128(As, a.abf + (size_t)b0 * KP, kTcM, KP, (int)min((int64_t)kTcM, (int64_t)a.B - b0), tid, kTcThreads);
-        load_dx_tile(dXs, a.dXT, a.Cp, a.Bp, b0, tid, kTcThreads);
-        cp_async_wait_all();
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue_gemm_kmajor(tmem_base, smem_u32(As), kTcM, smem_u32(Ws), Npad, Npad, KP, false);
-            umma_commit(mbar);
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
+    int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
+    if (a.ctrl && a.ctrl->done) row_end = row_begin;
+    const int nt = row_end > row_begin ? (int)((row_end - row_begin + kTcM - 1) / kTcM) : 0;
 
-        // epilogue: per h of this warp-group, a branch-free sweep over its channels (static smem offsets -> ILP)
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int hl = h_begin; hl < h_end; ++hl) {
-            float acc = 0.f;
-            const int colbase = hl * a.Cp;
-            int c0 = c_begin;
-            for (; c0 + 32 <= c_end; c0 += 32) acc += fwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row);
-            for (; c0 + 8 <= c_end; c0 += 8) acc += fwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row);
-            part[(wg * a.Hg + hl) * kTcM + row] = acc;
+    if (warp == 8) {
+        if (lane == 0 && nt > 0) {
+            auto load = [&](int i) {
+                const int b = i & 1;
+                const int b0 = (int)(row_begin + (int64_t)i * kTcM);
+                mbar_expect_tx(full_a + b, a_bytes);
+                tma_load_3d(As + (size_t)b * a_bytes, &maps.A, full_a + b, 0, b0, a.rec_a);
+                tma_load_3d(As + (size_t)b * a_bytes + a_bytes / 2, &maps.A, full_a + b, 64, b0, a.rec_a);
+                mbar_expect_tx(full_x + b, x_bytes);
+                tma_load_3d(dXs + (size_t)b * x_bytes, &maps.X, full_x + b, 0, b0, a.rec_x);
+            };
+            auto issue = [&](int i) {
+                const int b = i & 1;
+                mbar_wait(full_a + b, (uint32_t)(i >> 1) & 1u);
+                tc_fence_after();
+                issue_gemm_kmajor(tmem_base + (uint32_t)b * acc_stride, smem_u32(As + (size_t)b * a_bytes), kTcM, smem_u32(Ws), Npad, Npad,
+                                  kTcKP, false);
+                umma_commit(mma_bar + b);
+            };
+            load(0);
+            if (nt > 1) load(1);
+            mbar_wait(w_bar, 0);
+            issue(0);
+            for (int i = 0; i < nt; ++i) {
+                if (i + 1 < nt) issue(i + 1);      // accumulator (i+1)&1 is free: load(i+1) was issued after done(i-1)
+                if (i + 2 < nt) {
+                    mbar_wait(mma_bar + (i & 1), (uint32_t)(i >> 1) & 1u);   // MMA(i) complete: activation buffer free
+                    mbar_wait(done + (i & 1), (uint32_t)(i >> 1) & 1u);      // epilogue(i) complete: dX buffer and accumulator free
+                    load(i + 2);
+                }
+            }
         }
-        tc_fence_before();
-        __syncthreads();
-        // combine and write k^T[h][b]
-        for (int idx = tid; idx < a.Hg * kTcM; idx += kTcThreads) {
-            const int h_l = idx / kTcM, m = idx % kTcM;
-            float s;
-            if (a.Hg >= 2) s = part[((h_l < a.Hg / 2 ? 0 : 1) * a.Hg + h_l) * kTcM + m];
-            else s = part[m] + part[kTcM + m];
-            const int h = g * a.Hg + h_l;
-            if (h < a.H && b0 + m < a.B) a.koutT[(size_t)h * a.Bp + b0 + m] = s;
+    } else {
+        const int wg = warp >> 2;                    // warp-group 0/1
+        const int row = (warp & 3) * 32 + lane;      // TMEM lane == row inside the tile
+        // share of this warp-group: a set of whole h's when Hg >= 2, else half of the channels of the single h
+        int h_begin, h_end, c_begin, c_end;
+        if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
+        else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+        const uint32_t b3_s = smem_u32(b3s);
+        for (int i = 0; i < nt; ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int64_t b0 = row_begin + (int64_t)i * kTcM;
+            mbar_wait(full_x + b, ph);
+            mbar_wait(mma_bar + b, ph);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t dx_s = smem_u32(dXs) + (uint32_t)b * x_bytes + (uint32_t)row * (uint32_t)a.CpB * 4u;
+            for (int hl = h_begin; hl < h_end; ++hl) {
+                float acc = 0.f;
+                const int colbase = hl * a.Cp;
+                int c0 = c_begin;
+                for (; c0 + 32 <= c_end; c0 += 32) acc += fwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
+                for (; c0 + 8 <= c_end; c0 += 8) acc += fwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
+                if (a.Hg >= 2) {
+                    const int h = g * a.Hg + hl;
+                    if (h < a.H && b0 + row < a.B) a.koutT[(size_t)h * a.Bp + b0 + row] = acc;   // k^T[h][b], coalesced over the lanes
+                } else {
+                    if (wg == 0) part[row] = acc;
+                    named_bar_sync(1, kTcEpiThreads);
+                    if (wg == 1 && g < a.H && b0 + row < a.B) a.koutT[(size_t)g * a.Bp + b0 + row] = acc + part[row];
+                    named_bar_sync(1, kTcEpiThreads);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done + b);
         }
-        __syncthreads();
     }
     tc_fence_before();
+    __syncwarp();
     __syncthreads();
-    cp_async_wait_all();  // the weight tile copy must have landed before the CTA may exit
-    if (warp == 0) tmem_dealloc(tmem_base, ncols);
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * acc_stride);
 }
 
-static inline size_t tc_fwd_smem_bytes(int Npad, int KP, int Hg, int Cp) {
-    return 1024 + (size_t)Npad * KP * 2 + (size_t)kTcM * KP * 2 + (size_t)Npad * 4 + (size_t)2 * Hg * kTcM * 4 +
-           (size_t)Cp * kTcM * 4 + 64;
-}
+static inline size_t tc_fwd_smem_bytes(int Npad, int CpB) { return 1024 + tc_fwd_layout(Npad, CpB).total; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // backward of one RK stage:
 //   MMA1   pre[m][n]  = As . Ws^T                      (A, B K-major)                 -> TMEM cols [0, Npad)
-//   epi 1  G = gk * dX * (1 - tanh^2(pre + b3)) -> bf16 tile Gs[m][n];  per-warp column sums for db3
+//   epi 1  G = gk * dX * (1 - tanh^2(pre + b3)) -> bf16 tile Gs[m][n]
 //   dgrad  P[m][k]    = Gs . Ws        (A = Gs K-major over n, B = Ws MN-major)       -> TMEM cols [0, KP)
 //   wgrad  dW^T[k][n] += As^T . Gs     (A = As MN-major, B = Gs MN-major)             -> TMEM cols [256, 256+Npad)
-//   epi 2  P -> global partial of dL/d(act) for this h-group
+//   bias   db3[n]     += sum_m Gs[m][n]   column sums of the bf16 tile by the CUDA cores WHILE dgrad/wgrad run
+//   epi 2  P -> global partial of dL/d(act) for this h-group (waits for dgrad only; wgrad overlaps it)
 // dW^T stays in TMEM across all row tiles of the CTA and is added to the global accumulator once at the end.
+// Same warp specialisation as the forward kernel: warp 8 issues the TMA loads (the next dX/dt tile as soon as epilogue 1 is
+// done, the next activation tile as soon as wgrad is: it lands during epilogue 2) and every MMA; warps 0-7 run the
+// epilogues.  Barriers:
+//   full_a, full_x      TMA landed          pre_bar  MMA1 complete        g_ready  G tile written (8 warp arrivals)
+//   dg_bar  dgrad complete                  done2    epilogue 2 finished (8 warp arrivals)      fin_bar  last wgrad complete
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kTcDwCol = 256;
 
-// Column sums of a W-column x 32-row (lane) block by recursive halving: after log2(W) exchange steps every lane holds
-// one column summed over a lane subset, the remaining levels are plain xor-reductions.  W + log2(32/W) shuffles
-// instead of 5 W.  dst points at the first of the W columns of this warp's accumulator row.
-template <int W>
-__device__ __forceinline__ void colsum_butterfly(float (&v)[W], int lane, float* dst) {
-    const uint32_t full = 0xffffffffu;
-    int col = 0;
-    int bit = 16;
-#pragma unroll
-    for (int width = W; width > 1; width >>= 1) {
-        const int half = width >> 1;
-        const bool up = (lane & bit) != 0;
-#pragma unroll
-        for (int j = 0; j < half; ++j) {
-            const float send = up ? v[j] : v[j + half];
-            const float keep = up ? v[j + half] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, bit);
-        }
-        col += up ? half : 0;
-        bit >>= 1;
-    }
-    int low = 0;
-#pragma unroll
-    for (; bit >= 1; bit >>= 1) { v[0] += __shfl_xor_sync(full, v[0], bit); low |= bit; }
-    if ((lane & low) == 0) dst[col] += v[0];
-}
-
 // One W-column chunk of epilogue 1 for TMEM lane `row`: G = gk * dX * sech^2(pre + b3) -> bf16 into the swizzled G
-// tile (16-byte stores, n0 is a multiple of 8) and column sums for the bias gradient.
+// tile (16-byte stores, n0 is a multiple of 8).
 template <int W>
-__device__ __forceinline__ void bwd_chunk(uint32_t taddr, const float* __restrict__ b3, const float* __restrict__ dx,
-                                          float gk, bool row_ok, uint8_t* Gs, int row, int n0, float* bsum_row, int lane) {
-    float v[W];
-    tmem_ldw<W>(taddr, v);
+__device__ __forceinline__ void bwd_chunk(uint32_t taddr, uint32_t b3_s, uint32_t dx_s, float gk, uint32_t gs_s, int row, int n0) {
+    uint32_t r[W];
+    tmem_ldw_issue<W>(taddr, r);
+    float4 bb[W / 4], dd[W / 4];
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const float gv = gk * dx[j * kTcM] * sech2_fast(v[j] + b3[j]);
-        v[j] = row_ok ? gv : 0.f;   // select, not multiply: padded rows hold uninitialised dX
+    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(b3_s + 16u * q); dd[q] = lds128(dx_s + 16u * q); }
+    tmem_wait_ld<W>(r);
+    float v[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        // gk is zero for padded rows and dX/dt rows beyond the batch are zero-filled by TMA: no NaN can enter the G tile
+        v[4 * q + 0] = gk * dd[q].x * sech2_fast(__uint_as_float(r[4 * q + 0]) + bb[q].x);
+        v[4 * q + 1] = gk * dd[q].y * sech2_fast(__uint_as_float(r[4 * q + 1]) + bb[q].y);
+        v[4 * q + 2] = gk * dd[q].z * sech2_fast(__uint_as_float(r[4 * q + 2]) + bb[q].z);
+        v[4 * q + 3] = gk * dd[q].w * sech2_fast(__uint_as_float(r[4 * q + 3]) + bb[q].w);
     }
 #pragma unroll
     for (int j8 = 0; j8 < W / 8; ++j8) {
@@ -416,179 +511,259 @@ __device__ __forceinline__ void bwd_chunk(uint32_t taddr, const float* __restric
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1]);
             pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        *reinterpret_cast<uint4*>(Gs + sw128_off(row, (n0 >> 3) + j8, kTcM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-    if constexpr (W == 32) {
-        float lo[16], hi[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { lo[j] = v[j]; hi[j] = v[16 + j]; }
-        colsum_butterfly<16>(lo, lane, bsum_row + n0);
-        colsum_butterfly<16>(hi, lane, bsum_row + n0 + 16);
-    } else {
-        colsum_butterfly<W>(v, lane, bsum_row + n0);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + sw128_off(row, (n0 >> 3) + j8, kTcM)), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3]) : "memory");
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a) {
+struct TcBwdSmem {
+    uint32_t Ws, As, Gs, dXs, b3s, bsum, bars, total;
+};
+__host__ __device__ inline TcBwdSmem tc_bwd_layout(int Npad, int CpB) {
+    TcBwdSmem L;
+    const uint32_t NP64 = ((uint32_t)Npad + 63u) & ~63u;
+    uint32_t o = 0;
+    L.Ws = o; o += (uint32_t)Npad * kTcKP * 2;
+    L.As = o; o += kTcM * kTcKP * 2;
+    L.Gs = o; o += kTcM * NP64 * 2;
+    L.dXs = o; o += kTcM * (uint32_t)CpB * 4;
+    L.b3s = o; o += (uint32_t)Npad * 4;
+    L.bsum = o; o += 8u * (uint32_t)Npad * 4;
+    o = (o + 15u) & ~15u;
+    L.bars = o; o += 16 * 8;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a,
+                                                                     const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int Npad = a.Npad, KP = a.KP;
-    const int NP64 = (Npad + 63) & ~63;
-    uint8_t* Ws = smem;                                   // [Npad][KP]  bf16 swizzled (rows n, contiguous k)
-    uint8_t* As = Ws + (size_t)Npad * KP * 2;             // [128][KP]   (rows m, contiguous k)
-    uint8_t* Gs = As + (size_t)kTcM * KP * 2;             // [128][NP64] (rows m, contiguous n)
-    float* b3s = reinterpret_cast<float*>(Gs + (size_t)kTcM * NP64 * 2);  // [Npad]
-    float* bsum = b3s + Npad;                             // [8 warps][Npad]
-    float* dXs = bsum + 8 * Npad;                         // [Cp][128]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(dXs + (size_t)a.Cp * kTcM);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int Npad = a.Npad;
+    constexpr int KP = kTcKP;
+    const TcBwdSmem L = tc_bwd_layout(Npad, a.CpB);
+    const uint32_t a_bytes = kTcM * kTcKP * 2, x_bytes = kTcM * (uint32_t)a.CpB * 4;
+    uint8_t* Ws = smem + L.Ws;                            // [Npad][KP]  bf16 swizzled (rows n, contiguous k)
+    uint8_t* As = smem + L.As;                            // [128][KP]   (rows m, contiguous k)
+    uint8_t* Gs = smem + L.Gs;                            // [128][NP64] (rows m, contiguous n)
+    uint8_t* dXs = smem + L.dXs;                          // [128][CpB] fp32
+    float* b3s = reinterpret_cast<float*>(smem + L.b3s);  // [Npad]
+    float* bsum = reinterpret_cast<float*>(smem + L.bsum);  // [8 row slices][Npad]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* full_a = bars;
+    uint64_t* wg_bar = bars + 1;
+    uint64_t* full_x = bars + 2;
+    uint64_t* pre_bar = bars + 3;
+    uint64_t* g_ready = bars + 4;
+    uint64_t* dg_bar = bars + 5;
+    uint64_t* done2 = bars + 6;
+    uint64_t* fin_bar = bars + 7;
+    uint64_t* w_bar = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x, bt = blockIdx.y;
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
-    if (tid == 0) mbar_init(mbar, 1);
-    load_tile_sw128(Ws, a.Wbf + (size_t)g * Npad * KP, Npad, KP, Npad, tid, kTcThreads);
+    if (tid == 0) {
+        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(full_x, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, 8);
+        mbar_init(dg_bar, 1); mbar_init(done2, 8); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < Npad; i += kTcThreads) b3s[i] = a.b3[(size_t)g * Npad + i];
-    for (int i = tid; i < 8 * Npad; i += kTcThreads) bsum[i] = 0.f;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int S = a.Hg * a.Cp;                          // valid columns (multiple of 8); [S, Npad) is zero padding
+    if (S < Npad && tid < kTcM) *reinterpret_cast<uint4*>(Gs + sw128_off(tid, S >> 3, kTcM)) = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool producer = warp == 8 && lane == 0;
+    if (producer) {
+        tma_prefetch_desc(&maps.A);
+        tma_prefetch_desc(&maps.X);
+        mbar_expect_tx(w_bar, (uint32_t)Npad * kTcKP * 2);
+        tma_load_3d(Ws, &maps.W, w_bar, 0, g * Npad, 0);
+        tma_load_3d(Ws + (size_t)Npad * 128, &maps.W, w_bar, 64, g * Npad, 0);
+    }
     pdl_trigger();
     pdl_wait();  // gk comes from the previous kernels
 
-    const int wg = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int S = a.Hg * a.Cp;                          // valid columns (multiple of 8); [S, Npad) is zero padding
-    int h_begin, h_end, c_begin, c_end;
-    if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
-    else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
-    // column split of the final dW^T read-out (16-column chunks)
-    const int split = (Npad / 2) & ~15;
-    const int col_begin = wg == 0 ? 0 : split;
-    const int col_end = wg == 0 ? split : Npad;
-    if (S < Npad && tid < kTcM) *reinterpret_cast<uint4*>(Gs + sw128_off(tid, S >> 3, kTcM)) = make_uint4(0, 0, 0, 0);
-
-    uint32_t phase = 0;
-    bool first_tile = true;
     const int64_t row_begin = (int64_t)bt * a.Bt;
-    const int64_t row_end = (a.ctrl && a.ctrl->done) ? row_begin : min((int64_t)a.Bp, row_begin + a.Bt);
-    for (int64_t b0 = row_begin; b0 < row_end && b0 < a.B; b0 += kTcM) {
-        load_tile_sw128(As, a.abf + (size_t)b0 * KP, kTcM, KP, (int)min((int64_t)kTcM, (int64_t)a.B - b0), tid, kTcThreads);
-        load_dx_tile(dXs, a.dXT, a.Cp, a.Bp, b0, tid, kTcThreads);
-        cp_async_wait_all();
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue_gemm_kmajor(tmem_base, smem_u32(As), kTcM, smem_u32(Ws), Npad, Npad, KP, false);
-            umma_commit(mbar);
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
+    int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
+    if (a.ctrl && a.ctrl->done) row_end = row_begin;
+    const int nt = row_end > row_begin ? (int)((row_end - row_begin + kTcM - 1) / kTcM) : 0;
 
-        // ---- epilogue 1: G tile + bias-gradient column sums; per h, branch-free over the channels ----
-        const int64_t b = b0 + row;
-        const bool row_ok = b < a.B;
-        for (int hl = h_begin; hl < h_end; ++hl) {
-            const int h = g * a.Hg + hl;
-            const float gk = (row_ok && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
-            const int colbase = hl * a.Cp;
-            int c0 = c_begin;
-            for (; c0 + 32 <= c_end; c0 += 32)
-                bwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row, gk, row_ok, Gs, row,
-                              colbase + c0, bsum + warp * Npad, lane);
-            for (; c0 + 8 <= c_end; c0 += 8)
-                bwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3s + colbase + c0, dXs + c0 * kTcM + row, gk, row_ok, Gs, row,
-                             colbase + c0, bsum + warp * Npad, lane);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            // dgrad: D[128 x KP] = Gs (K-major over n) . Ws (MN-major: N = k contiguous, K = n rows)
-            {
-                const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
-                for (int ks = 0; ks < Npad / 16; ++ks) {
-                    const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                    const uint32_t b_off = (uint32_t)ks * 2048u;
-                    umma_bf16(tmem_base, make_sdesc(smem_u32(Gs) + a_off, 16, 1024),
-                              make_sdesc(smem_u32(Ws) + b_off, (uint32_t)Npad * 128u, 1024), idesc, ks > 0 ? 1u : 0u);
+    if (warp == 8) {
+        if (lane == 0 && nt > 0) {
+            auto load_A = [&](int i) {
+                const int b0 = (int)(row_begin + (int64_t)i * kTcM);
+                mbar_expect_tx(full_a, a_bytes);
+                tma_load_3d(As, &maps.A, full_a, 0, b0, a.rec_a);
+                tma_load_3d(As + a_bytes / 2, &maps.A, full_a, 64, b0, a.rec_a);
+            };
+            auto load_X = [&](int i) {
+                mbar_expect_tx(full_x, x_bytes);
+                tma_load_3d(dXs, &maps.X, full_x, 0, (int)(row_begin + (int64_t)i * kTcM), a.rec_x);
+            };
+            load_A(0);
+            load_X(0);
+            mbar_wait(w_bar, 0);
+            for (int i = 0; i < nt; ++i) {
+                const uint32_t ph = (uint32_t)i & 1u;
+                const uint32_t As_i = smem_u32(As);
+                mbar_wait(full_a, ph);
+                if (i > 0) mbar_wait(done2, ph ^ 1u);        // epilogue 2 of tile i-1 has read P out of the accumulator
+                tc_fence_after();
+                issue_gemm_kmajor(tmem_base, As_i, kTcM, smem_u32(Ws), Npad, Npad, KP, false);
+                umma_commit(pre_bar);
+                mbar_wait(g_ready, ph);                      // G tile of tile i written by all 8 warps; dX/dt tile no longer needed
+                tc_fence_after();
+                if (i + 1 < nt) load_X(i + 1);
+                // dgrad: D[128 x KP] = Gs (K-major over n) . Ws (MN-major: N = k contiguous, K = n rows)
+                {
+                    const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
+                    for (int ks = 0; ks < Npad / 16; ++ks) {
+                        const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
+                        const uint32_t b_off = (uint32_t)ks * 2048u;
+                        umma_bf16(tmem_base, make_sdesc(smem_u32(Gs) + a_off, 16, 1024),
+                                  make_sdesc(smem_u32(Ws) + b_off, (uint32_t)Npad * 128u, 1024), idesc, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(dg_bar);
+                // wgrad: D[KP x Npad] += As^T (MN-major: M = k contiguous, K = m rows) . Gs (MN-major: N = n contiguous)
+                {
+                    const uint32_t idesc = make_idesc(KP, Npad, 1, 1);
+                    for (int ks = 0; ks < kTcM / 16; ++ks) {
+                        const uint32_t off = (uint32_t)ks * 2048u;
+                        umma_bf16(tmem_base + kTcDwCol, make_sdesc(As_i + off, (uint32_t)kTcM * 128u, 1024),
+                                  make_sdesc(smem_u32(Gs) + off, (uint32_t)kTcM * 128u, 1024), idesc, (ks > 0 || i > 0) ? 1u : 0u);
+                    }
+                }
+                if (i + 1 < nt) {
+                    // the activation tile is free once wgrad(i) has completed; the next one lands during epilogue 2
+                    umma_commit(wg_bar);
+                    mbar_wait(wg_bar, ph);
+                    load_A(i + 1);
                 }
             }
-            // wgrad: D[KP x Npad] += As^T (MN-major: M = k contiguous, K = m rows) . Gs (MN-major: N = n contiguous)
-            {
-                const uint32_t idesc = make_idesc(KP, Npad, 1, 1);
-                for (int ks = 0; ks < kTcM / 16; ++ks) {
-                    const uint32_t off = (uint32_t)ks * 2048u;
-                    umma_bf16(tmem_base + kTcDwCol, make_sdesc(smem_u32(As) + off, (uint32_t)kTcM * 128u, 1024),
-                              make_sdesc(smem_u32(Gs) + off, (uint32_t)kTcM * 128u, 1024), idesc,
-                              (ks > 0 || !first_tile) ? 1u : 0u);
-                }
-            }
-            umma_commit(mbar);
+            umma_commit(fin_bar);
         }
-        first_tile = false;
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
+    } else {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int h_begin, h_end, c_begin, c_end;
+        if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
+        else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+        // column split of the final dW^T read-out (16-column chunks)
+        const int split = (Npad / 2) & ~15;
+        const int col_begin = wg == 0 ? 0 : split;
+        const int col_end = wg == 0 ? split : Npad;
+        // bias gradient: thread (chunk of 8 columns = lane, slice of 16 rows = warp) keeps its partial column sums in registers
+        const int n_chunk8 = Npad >> 3;                     // <= 30
+        float bacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+        const uint32_t b3_s = smem_u32(b3s), gs_s = smem_u32(Gs);
+        const uint32_t dx_s = smem_u32(dXs) + (uint32_t)row * (uint32_t)a.CpB * 4u;
 
-        // ---- epilogue 2: partial input gradient of this h-group ----
-        {
-            const int kb = wg * (KP / 2), ke = kb + KP / 2;
-            float* prow = a.P + ((size_t)g * a.B + (size_t)b) * a.DFP;
-            for (int k0 = kb; k0 < ke; k0 += 16) {
-                float v[16];
-                tmem_ld16(lane_addr + (uint32_t)k0, v);
-                if (row_ok) {
+        for (int i = 0; i < nt; ++i) {
+            const uint32_t ph = (uint32_t)i & 1u;
+            const int64_t b0 = row_begin + (int64_t)i * kTcM;
+            const int64_t b = b0 + row;
+            const bool row_ok = b < a.B;
+            mbar_wait(full_x, ph);
+            mbar_wait(pre_bar, ph);
+            tc_fence_after();
+            // ---- epilogue 1: G tile; per h, branch-free over the channels ----
+            for (int hl = h_begin; hl < h_end; ++hl) {
+                const int h = g * a.Hg + hl;
+                const float gk = (row_ok && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
+                const int colbase = hl * a.Cp;
+                int c0 = c_begin;
+                for (; c0 + 32 <= c_end; c0 += 32)
+                    bwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0, gk, gs_s, row, colbase + c0);
+                for (; c0 + 8 <= c_end; c0 += 8)
+                    bwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0, gk, gs_s, row, colbase + c0);
+            }
+            fence_async_smem();     // generic-proxy writes of G (and reads of dX/dt) before the async-proxy MMA / TMA
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_ready);
+            // bias gradient from the bf16 G tile while the tensor core works: every warp needs ALL rows -> epilogue-wide barrier
+            named_bar_sync(1, kTcEpiThreads);
+            if (lane < n_chunk8) {
+#pragma unroll 4
+                for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+                    uint32_t w4[4];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                                 : "r"(gs_s + sw128_off(r, lane, kTcM)));
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(prow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                        bacc[2 * j] += f.x;
+                        bacc[2 * j + 1] += f.y;
+                    }
                 }
             }
-        }
-        tc_fence_before();
-        __syncthreads();
-    }
-    // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [bt][g*Npad + n][k];  bias gradient ----
-    if (!first_tile) {
-        const int k = row;
-        if (k < KP) {
-            for (int n0 = col_begin; n0 < col_end; n0 += 16) {
-                float v[16];
-                tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
+            mbar_wait(dg_bar, ph);
+            tc_fence_after();
+            // ---- epilogue 2: partial input gradient of this h-group ----
+            {
+                const int kb = wg * (KP / 2), ke = kb + KP / 2;
+                float* prow = a.P + ((size_t)g * a.B + (size_t)b) * a.DFP;
+                for (int k0 = kb; k0 < ke; k0 += 16) {
+                    float v[16];
+                    tmem_ld16(lane_addr + (uint32_t)k0, v);
+                    if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    // exactly one thread ever adds to this element in this launch: a reduction without return value is
-                    // deterministic and does not stall on the read
-                    float* p = a.dW3acc + (((size_t)bt * a.n_hg + g) * Npad + n0 + j) * a.DFP + k;
-                    atomicAdd(p, v[j]);
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(prow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done2);
         }
-        for (int n = tid; n < Npad; n += kTcThreads) {
-            float s = 0.f;
+        // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [bt][g*Npad + n][k];  bias gradient ----
+        if (nt > 0) {
+            if (lane < n_chunk8) {
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += bsum[w * Npad + n];
-            atomicAdd(a.db3acc + ((size_t)bt * a.n_hg + g) * Npad + n, s);
+                for (int j = 0; j < 8; ++j) bsum[warp * Npad + lane * 8 + j] = bacc[j];
+            }
+            mbar_wait(fin_bar, 0);
+            tc_fence_after();
+            named_bar_sync(1, kTcEpiThreads);
+            const int k = row;
+            if (k < KP) {
+                for (int n0 = col_begin; n0 < col_end; n0 += 16) {
+                    float v[16];
+                    tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // exactly one thread ever adds to this element in this launch: a reduction without return value is
+                        // deterministic and does not stall on the read
+                        float* p = a.dW3acc + (((size_t)bt * a.n_hg + g) * Npad + n0 + j) * a.DFP + k;
+                        atomicAdd(p, v[j]);
+                    }
+                }
+            }
+            for (int n = tid; n < Npad; n += kTcEpiThreads) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += bsum[w * Npad + n];
+                atomicAdd(a.db3acc + ((size_t)bt * a.n_hg + g) * Npad + n, s);
+            }
         }
     }
     tc_fence_before();
+    __syncwarp();
     __syncthreads();
-    cp_async_wait_all();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-static inline size_t tc_bwd_smem_bytes(int Npad, int KP, int Hg, int Cp) {
-    (void)Hg;
-    const int NP64 = (Npad + 63) & ~63;
-    return 1024 + (size_t)Npad * KP * 2 + (size_t)kTcM * KP * 2 + (size_t)kTcM * NP64 * 2 + (size_t)Npad * 4 +
-           (size_t)8 * Npad * 4 + (size_t)Cp * kTcM * 4 + 64;
-}
+static inline size_t tc_bwd_smem_bytes(int Npad, int CpB) { return 1024 + tc_bwd_layout(Npad, CpB).total; }
 
 }  // namespace ncde

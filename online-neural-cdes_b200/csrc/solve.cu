@@ -1,5 +1,6 @@
 // Host orchestration of the fixed-grid CDE solve: tiling plan, workspace layout, per-stage launch sequence.
 // No host synchronisation anywhere: every call only enqueues work on the caller's stream.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -33,6 +34,50 @@ struct ProfScope {
 };
 
 constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+// ---- TMA descriptors (tensor-core path) -----------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the library has no link-time
+// dependency on libcuda (it must load on machines without a driver, e.g. for the symbol check of the CPU test suite).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int get_encoder(EncodeTiledFn* fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NCDE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        NCDE_REQUIRE(qres == cudaDriverEntryPointSuccess && ptr, NCDE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        cached = (EncodeTiledFn)ptr;
+    }
+    *fn = cached;
+    return NCDE_OK;
+}
+// rank-3 row-major tensor {inner, rows, recs}: element (c, r, k) at base + k*rec_stride + r*row_stride + c*elem
+static int make_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
+                    uint64_t recs, uint64_t row_stride_bytes, uint64_t rec_stride_bytes, uint32_t box_inner, uint32_t box_rows,
+                    CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc;
+    int rc = get_encoder(&enc);
+    if (rc != NCDE_OK) return rc;
+    const cuuint64_t dims[3] = {inner, rows, recs ? recs : 1};
+    // a single record still needs a legal (multiple of 16) stride
+    const cuuint64_t strides[2] = {row_stride_bytes, rec_stride_bytes ? rec_stride_bytes : row_stride_bytes * rows};
+    const cuuint32_t box[3] = {box_inner, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    NCDE_REQUIRE(((uintptr_t)base & 15) == 0 && (strides[0] & 15) == 0 && (strides[1] & 15) == 0 && ((uint64_t)box_inner * elem_bytes & 15) == 0,
+                 NCDE_ERR_INVALID, "TMA descriptor: misaligned tensor");
+    const CUresult r = enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NCDE_REQUIRE(r == CUDA_SUCCESS, NCDE_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return NCDE_OK;
+}
+// The activation / dX records of one solve sit at a fixed stride; launches address them by record index.
+struct TcMapSet {
+    TcMaps maps;
+    const char* base_a; size_t stride_a; int64_t n_a;
+    const char* base_x; size_t stride_x; int64_t n_x;
+};
 constexpr int kNumSMs = 148;
 
 struct Plan {
@@ -40,7 +85,7 @@ struct Plan {
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
-    int tc, Npad, KP;         // tensor-core path: columns per h-group padded to 16, K padded to 64
+    int tc, Npad, KP, CpB;    // tensor-core path: columns per h-group padded to 16, K padded to 128; dX row pitch in smem
     int R, n_rt;
     int n_stages;
     size_t stage_floats;      // saved floats per RK stage
@@ -137,34 +182,43 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     } else {
         // tensor-core tiling: h-group columns padded to a multiple of 16 (UMMA N), K padded to 64 (one swizzle block)
         // K is padded to 128 so that the weight-gradient MMA (M = K) always runs the M = 128 shape
-        pl->KP = 128;
+        pl->KP = kTcKP;
         pl->DFP = pl->KP;  // gradient buffers share the padded K
+        pl->CpB = pl->Cp + (((pl->Cp / 4) & 1) ? 0 : 4);   // CpB / 4 odd: per-row LDS.128 of consecutive lanes hit distinct banks
         double best = -1.0;
         const int n_mt = (int)ceil_div(pl->B, kTcM);
-        for (int hg = 8; hg >= 1; --hg) {
-            if (hg > pl->H) continue;
-            const int npad = (int)round_up(hg * pl->Cp, 16);
-            if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
-            if (tc_bwd_smem_bytes(npad, pl->KP, hg, pl->Cp) > kSmemLimit) continue;
-            const int n_hg = (int)ceil_div(pl->H, hg);
-            int n_bt = kNumSMs / n_hg;
-            n_bt = n_bt < 1 ? 1 : (n_bt > n_mt ? n_mt : n_bt);
-            const int ctas = n_hg * n_bt;
-            const double waste = (double)(hg * pl->Cp) / npad;
-            const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * waste + 1e-4 * hg;
-            if (score > best + 1e-9) {
-                best = score;
-                pl->Hg = hg; pl->S = hg * pl->Cp; pl->Npad = npad; pl->n_hg = n_hg;
-                pl->Bt = (int)round_up(ceil_div(pl->B, n_bt), kTcM);
-                pl->n_bt = (int)ceil_div(pl->B, pl->Bt);
+        // the padded dX/dt row pitch is dropped (bank conflicts instead of no fit) when shared memory is too tight for it
+        for (int attempt = 0; attempt < 2 && best < 0; ++attempt) {
+            if (attempt == 1) pl->CpB = pl->Cp;
+            for (int hg = 8; hg >= 1; --hg) {
+                if (hg > pl->H) continue;
+                const int npad = (int)round_up(hg * pl->Cp, 16);
+                if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
+                if (tc_bwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
+                if (tc_fwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
+                const int n_hg = (int)ceil_div(pl->H, hg);
+                int n_bt = kNumSMs / n_hg;
+                n_bt = n_bt < 1 ? 1 : (n_bt > n_mt ? n_mt : n_bt);
+                const int ctas = n_hg * n_bt;
+                const double waste = (double)(hg * pl->Cp) / npad;
+                const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * waste + 1e-4 * hg;
+                if (score > best + 1e-9) {
+                    best = score;
+                    pl->Hg = hg; pl->S = hg * pl->Cp; pl->Npad = npad; pl->n_hg = n_hg;
+                    pl->Bt = (int)round_up(ceil_div(pl->B, n_bt), kTcM);
+                    pl->n_bt = (int)ceil_div(pl->B, pl->Bt);
+                }
             }
         }
         NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve: no tensor-core tiling fits (C=%d, width=%d)", p->C, pl->DF);
         pl->TM = 8;
-        pl->fwd_smem = tc_fwd_smem_bytes(pl->Npad, pl->KP, pl->Hg, pl->Cp);
-        pl->bwd_smem = tc_bwd_smem_bytes(pl->Npad, pl->KP, pl->Hg, pl->Cp);
+        pl->fwd_smem = tc_fwd_smem_bytes(pl->Npad, pl->CpB);
+        pl->bwd_smem = tc_bwd_smem_bytes(pl->Npad, pl->CpB);
     }
     pl->Np = pl->n_hg * pl->Npad;
+    if (getenv("NCDE_DEBUG_PLAN"))
+        fprintf(stderr, "ncde plan: B=%d H=%d C=%d Cp=%d tc=%d Hg=%d Npad=%d n_hg=%d n_bt=%d Bt=%d fwd_smem=%zu bwd_smem=%zu\n", pl->B, pl->H,
+                pl->C, pl->Cp, pl->tc, pl->Hg, pl->Npad, pl->n_hg, pl->n_bt, pl->Bt, pl->fwd_smem, pl->bwd_smem);
 
     // hidden tiling
     int R = (int)round_up(ceil_div(pl->B, kNumSMs), 4);
@@ -320,15 +374,64 @@ static int validate_grid(const ncde_problem_t* p, const Plan& pl) {
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) NCDE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // Ask for exactly the shared-memory carve-out this kernel needs.  Without the hint the driver may leave the split of
+    // the previous kernel in place (the tensor-core kernels take 228 KB), which shrinks L1 for the latency-bound hidden-layer
+    // kernels that follow them.
+    static const bool hint = getenv("NCDE_NO_CARVEOUT_HINT") == nullptr;
+    if (hint) {
+        int pct = (int)((bytes + 1024 + 2327) * 100 / 233472);
+        pct = pct > 100 ? 100 : pct;
+        NCDE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     return NCDE_OK;
 }
 
 static void fill_tc_args(TcFieldArgs& ta, const Plan& pl, const float* wpack) {
     memset(&ta, 0, sizeof(ta));
     ta.B = pl.B; ta.Bp = pl.Bp; ta.H = pl.H; ta.Cp = pl.Cp; ta.Hg = pl.Hg; ta.n_hg = pl.n_hg; ta.Npad = pl.Npad;
-    ta.KP = pl.KP; ta.DF = pl.DF; ta.Bt = pl.Bt; ta.DFP = pl.DFP;
+    ta.KP = pl.KP; ta.DF = pl.DF; ta.Bt = pl.Bt; ta.DFP = pl.DFP; ta.CpB = pl.CpB;
     ta.Wbf = (const __nv_bfloat16*)(wpack + pl.off_W3T);
     ta.b3 = wpack + pl.off_b3p;
+}
+
+// Descriptors of one solve: weights, and the activation (bf16 [B][KP]) / dX (fp32 [B][Cp]) records at their strides.
+static int build_tc_maps(const Plan& pl, const float* wpack, TcMapSet* ms, const void* base_a, size_t stride_a_floats,
+                         int64_t n_a, const void* base_x, size_t stride_x_floats, int64_t n_x) {
+    memset(ms, 0, sizeof(*ms));
+    ms->base_a = (const char*)base_a; ms->stride_a = stride_a_floats * 4; ms->n_a = n_a < 1 ? 1 : n_a;
+    ms->base_x = (const char*)base_x; ms->stride_x = stride_x_floats * 4; ms->n_x = n_x < 1 ? 1 : n_x;
+    int rc = make_map(&ms->maps.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_W3T, kTcKP, (uint64_t)pl.n_hg * pl.Npad, 1,
+                      kTcKP * 2, 0, 64, (uint32_t)pl.Npad, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != NCDE_OK) return rc;
+    // rows beyond the batch are zero-filled by TMA (padding must not reach the weight-gradient reduction)
+    rc = make_map(&ms->maps.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base_a, kTcKP, (uint64_t)pl.B, (uint64_t)ms->n_a, kTcKP * 2,
+                  ms->n_a > 1 ? ms->stride_a : 0, 64, kTcM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != NCDE_OK) return rc;
+    return make_map(&ms->maps.X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base_x, (uint64_t)pl.Cp, (uint64_t)pl.B, (uint64_t)ms->n_x,
+                    (uint64_t)pl.Cp * 4, ms->n_x > 1 ? ms->stride_x : 0, (uint32_t)pl.CpB, kTcM, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+// record indices of this launch from the pointers the call site selected (ta.abf, ta.dXT)
+static int tc_records(TcFieldArgs& ta, const TcMapSet& ms) {
+    const size_t oa = (const char*)ta.abf - ms.base_a, ox = (const char*)ta.dXT - ms.base_x;
+    const int64_t ra = ms.n_a > 1 ? (int64_t)(oa / ms.stride_a) : 0, rx = ms.n_x > 1 ? (int64_t)(ox / ms.stride_x) : 0;
+    NCDE_REQUIRE((const char*)ta.abf >= ms.base_a && ra < ms.n_a && oa == (size_t)ra * (ms.n_a > 1 ? ms.stride_a : 0), NCDE_ERR_INVALID,
+                 "tensor-core launch: activation record outside the descriptor");
+    NCDE_REQUIRE((const char*)ta.dXT >= ms.base_x && rx < ms.n_x && ox == (size_t)rx * (ms.n_x > 1 ? ms.stride_x : 0), NCDE_ERR_INVALID,
+                 "tensor-core launch: dX record outside the descriptor");
+    ta.rec_a = (int)ra; ta.rec_x = (int)rx;
+    return NCDE_OK;
+}
+static int launch_tc_fwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cudaStream_t st) {
+    int rc = tc_records(ta, ms);
+    if (rc != NCDE_OK) return rc;
+    NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta, ms.maps));
+    return NCDE_OK;
+}
+static int launch_tc_bwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cudaStream_t st) {
+    int rc = tc_records(ta, ms);
+    if (rc != NCDE_OK) return rc;
+    NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta, ms.maps));
+    return NCDE_OK;
 }
 
 static void fill_field_args(FieldArgs& fa, const Plan& pl, const float* wpack) {
@@ -466,9 +569,18 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         da.stage_t = d_stage_t;
         da.dx_base = need_grad ? (float*)saved + pl.dx_off : dx_all;
         da.stage_stride = need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp;
+        da.row_major = use_tc ? 1 : 0;
         NCDE_REQUIRE(n_st_total <= 2147483647 && ceil_div(pl.B, 32) <= 65535, NCDE_ERR_UNSUPPORTED, "solve_fwd: grid too large");
         dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
         ++launches;
+    }
+
+    TcMapSet ms;
+    if (use_tc && n_st_total > 0) {
+        if (need_grad) rc = build_tc_maps(pl, wpack, &ms, (float*)saved + pl.abf_off, pl.stage_floats, n_st_total,
+                                          (float*)saved + pl.dx_off, pl.stage_floats, n_st_total);
+        else rc = build_tc_maps(pl, wpack, &ms, scratch_stage + pl.abf_off, 0, 1, dx_all, (size_t)pl.Cp * pl.Bp, n_st_total);
+        if (rc != NCDE_OK) return rc;
     }
 
     static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
@@ -500,7 +612,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = dx_stage;
                     ta.koutT = kT[i];
-                    NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
+                    { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
@@ -580,6 +692,12 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     else if (pl.TM == 8) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem);
     else rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
     if (rc != NCDE_OK) return rc;
+    TcMapSet ms;
+    if (use_tc && g.n_steps > 0) {
+        rc = build_tc_maps(pl, wpack, &ms, (const float*)saved + pl.abf_off, pl.stage_floats, g.n_steps * NS,
+                           (const float*)saved + pl.dx_off, pl.stage_floats, g.n_steps * NS);
+        if (rc != NCDE_OK) return rc;
+    }
 
     NCDE_CUDA_OK(cudaMemsetAsync(gyT, 0, nHB * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, (size_t)pl.n_bt * pl.Np * pl.DFP * 4, st));
@@ -603,6 +721,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
     hb.P = P; hb.gyT = gyT;
     rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
+    if (rc == NCDE_OK) rc = opt_in_smem(hidden_wgrad_kernel, 36 * 1024);
     if (rc != NCDE_OK) return rc;
 
     // weight-gradient tiles grouped by slot
@@ -667,7 +786,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = stage + pl.dx_off;
                     ta.gkT = gkT[i];
-                    NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta));
+                    { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
@@ -823,6 +942,12 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     TcFieldArgs ta;
     fill_tc_args(ta, pl, wpack);
     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off; ta.ctrl = ctrl;
+    ha.dx_row_major = use_tc ? 1 : 0;
+    TcMapSet ms;
+    if (use_tc) {
+        rc = build_tc_maps(pl, wpack, &ms, stage + pl.abf_off, 0, 1, stage + pl.dx_off, 0, 1);
+        if (rc != NCDE_OK) return rc;
+    }
 
     // one vector-field evaluation: stage input from tab[tab_index], result into kT[k_out]
     auto eval = [&](int tab_index, int k_out, float* stage_input_T) -> int {
@@ -832,7 +957,7 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
         if (pl.F == 0) fa.actT = ha.actT[0];
         if (use_tc) {
             ta.koutT = kT[k_out];
-            NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
+            { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
         } else {
             fa.koutT = kT[k_out];
             const dim3 fg(pl.n_hg, pl.n_bt);
@@ -1049,6 +1174,12 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     fill_tc_args(ta, pl, wpack);
     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off;
     ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc; ta.gkT = a_stage;
+    ha.dx_row_major = use_tc ? 1 : 0;
+    TcMapSet ms;
+    if (use_tc) {
+        rc = build_tc_maps(pl, wpack, &ms, stage + pl.abf_off, 0, 1, stage + pl.dx_off, 0, 1);
+        if (rc != NCDE_OK) return rc;
+    }
 
     HiddenBwdArgs hb;
     memset(&hb, 0, sizeof(hb));
@@ -1113,7 +1244,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                 NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
                 if (use_tc) {
                     ta.koutT = kf[sg];
-                    NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta));
+                    { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                 } else {
                     fa.koutT = kf[sg];
                     const dim3 fg(pl.n_hg, pl.n_bt);
@@ -1135,7 +1266,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                     NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, gwp_floats[s2] * 4, st));
                     NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
                 }
-                if (use_tc) NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta));
+                if (use_tc) { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                 else {
                     const dim3 fg(pl.n_hg, pl.n_bt);
                     if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
@@ -1316,6 +1447,13 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     fill_tc_args(ta, pl, wpack);
     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off); ta.dXT = stage + pl.dx_off;
     ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc; ta.gkT = a_stage; ta.ctrl = ctrl;
+    ha.dx_row_major = use_tc ? 1 : 0;
+    TcMapSet ms, ms_q;   // ms_q: the same activations with d2X/dt2 in place of dX/dt (time-gradient component)
+    if (use_tc) {
+        rc = build_tc_maps(pl, wpack, &ms, stage + pl.abf_off, 0, 1, stage + pl.dx_off, 0, 1);
+        if (rc == NCDE_OK) rc = build_tc_maps(pl, wpack, &ms_q, stage + pl.abf_off, 0, 1, ddXT, 0, 1);
+        if (rc != NCDE_OK) return rc;
+    }
 
     HiddenBwdArgs hb;
     memset(&hb, 0, sizeof(hb));
@@ -1391,7 +1529,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
         const dim3 fg(pl.n_hg, pl.n_bt);
         if (use_tc) {
             ta.koutT = kf[k_out];
-            NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, fg, dim3(kTcThreads), pl.fwd_smem, st, ta));
+            { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
         } else {
             fa.koutT = kf[k_out];
             if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
@@ -1401,7 +1539,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
             // q[b,h] = sum_c F(z)[b,h,c] d2X/dt2[b,c]: the same field kernel with the second path derivative
             if (use_tc) {
                 ta.koutT = qT; ta.dXT = ddXT;
-                NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, fg, dim3(kTcThreads), pl.fwd_smem, st, ta));
+                { const int rc_tc = launch_tc_fwd(pl, ta, ms_q, st); if (rc_tc != NCDE_OK) return rc_tc; }
                 ta.dXT = stage + pl.dx_off;
             } else {
                 fa.koutT = qT; fa.dXT = ddXT;
@@ -1430,7 +1568,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
             NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, gwp_floats[s2] * 4, st));
             NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
         }
-        if (use_tc) NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, fg, dim3(kTcThreads), pl.bwd_smem, st, ta));
+        if (use_tc) { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
         else if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
         else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
         hb.dz_out = ka[k_out];

@@ -63,7 +63,8 @@ struct HiddenFwdArgs {
     const float* yT;
     const float* kT[NCDE_MAX_STAGES];
     float* actT[NCDE_MAX_LAYERS + 1];  // actT[l] = [D[l] (padded to 4)][Bp], l = 0..F, for THIS stage
-    float* dXT;                        // [Cp][Bp]
+    float* dXT;                        // [Cp][Bp]  (tensor-core path, dx_row_major: [Bp][Cp])
+    int dx_row_major;
     float* ddXT;                       // [Cp][Bp] or null: d2X/dt2 (cubic paths; time-gradient component of the adjoint)
     __nv_bfloat16* abf;                // [Bp][KP] bf16 row-major copy of the final-layer input (tensor-core path) or null
     int KP;
@@ -264,6 +265,7 @@ struct DxAllArgs {
     const float* stage_t;      // device [n_stages_total]
     float* dx_base;            // first stage's dXT
     size_t stage_stride;       // floats between consecutive stages' dXT
+    int row_major;             // tensor-core path: [Bp][Cp] instead of [Cp][Bp]
 };
 
 __global__ void __launch_bounds__(256) dx_all_kernel(const __grid_constant__ DxAllArgs a) {
@@ -290,8 +292,10 @@ __global__ void __launch_bounds__(256) dx_all_kernel(const __grid_constant__ DxA
             const int64_t b = b0 + r;
             float v = 0.f;
             if (b < a.B && c < a.C) v = path_derivative(a.path, idxk, frac, b, c, a.C);
-            tile[r][c - c0] = v;
+            if (a.row_major) { if (b < a.B) out[(size_t)b * a.Cp + c] = v; }
+            else tile[r][c - c0] = v;
         }
+        if (a.row_major) continue;
         __syncthreads();
         for (int i = tid; i < 32 * cw; i += 256) {
             const int c = i / 32, r = i % 32;
@@ -487,13 +491,16 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             const int64_t b = b0 + r;
             float v = 0.f;
             if (b < a.B && c < a.C) v = path_derivative(a.path, idxk, frac, b, c, a.C);
-            tmp[c * R + r] = v;
+            if (a.dx_row_major) { if (b < a.B) a.dXT[(int64_t)b * a.Cp + c] = v; }
+            else tmp[c * R + r] = v;
         }
-        __syncthreads();
-        for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
-            const int c = idx / R, r = idx % R;
-            const int64_t b = b0 + r;
-            if (b < a.B) a.dXT[(int64_t)c * a.Bp + b] = tmp[c * R + r];
+        if (!a.dx_row_major) {
+            __syncthreads();
+            for (int idx = tid; idx < R * a.Cp; idx += kThreads) {
+                const int c = idx / R, r = idx % R;
+                const int64_t b = b0 + r;
+                if (b < a.B) a.dXT[(int64_t)c * a.Bp + b] = tmp[c * R + r];
+            }
         }
         if (a.ddXT) {
             // d/dt of NaturalCubicSpline.derivative (interpolation_cubic.py:331-336): 2c + 2 (3d) frac; zero for linear paths
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
                     const float* row = a.path.coeffs + ((int64_t)b * (a.path.K - 1) + idxk) * 4 * a.C;
                     v = __fadd_rn(row[2 * a.C + c], __fmul_rn(2.f, __fmul_rn(row[3 * a.C + c], frac)));
                 }
-                if (b < a.B) a.ddXT[(int64_t)c * a.Bp + b] = v;
+                if (b < a.B) a.ddXT[a.dx_row_major ? (int64_t)b * a.Cp + c : (int64_t)c * a.Bp + b] = v;
             }
         }
     }

@@ -20,7 +20,8 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-CASES = [(130, 4, 100, 128, 128, 3), (300, 6, 100, 128, 128, 3), (64, 5, 4, 64, 64, 3), (200, 5, 21, 64, 64, 2),
+# (1100, ...) and (700, ...): several 128-row tiles per CTA, so the double-buffered tile pipeline wraps around
+CASES = [(1100, 3, 100, 128, 128, 3), (700, 3, 30, 16, 64, 2), (130, 4, 100, 128, 128, 3), (300, 6, 100, 128, 128, 3), (64, 5, 4, 64, 64, 3), (200, 5, 21, 64, 64, 2),
          (96, 4, 14, 32, 128, 1), (33, 3, 2, 32, 128, 0)]
 
 

@@ -39,6 +39,8 @@ def run(B, L, C, H, HH, n, steps_note=""):
     return res
 
 if __name__ == "__main__":
+    run(1100, 3, 100, 128, 128, 3)
+    run(700, 3, 30, 16, 64, 2)
     run(130, 4, 100, 128, 128, 3)
     run(300, 6, 100, 128, 128, 3)
     run(64, 5, 4, 64, 64, 3)
