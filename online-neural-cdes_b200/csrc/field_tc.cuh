@@ -36,6 +36,13 @@ struct TcFieldArgs {
     float* db3acc;             // [n_bt][Np]
     int DFP;
     const AdaptCtrl* ctrl;     // adaptive solver: skip all work once ctrl->done
+    // all-tensor-core fixed-grid path: the forward epilogue also emits the NEXT stage's input y + increment(k...) as a bf16
+    // row-major record [Bp][128] (the operand tile of the tensor-core hidden layers)
+    __nv_bfloat16* zs_out;     // null: nothing to emit
+    const float* yT;           // [H][Bp]
+    const float* kT[NCDE_MAX_STAGES];   // stage derivatives incl. the one this launch writes (koutT)
+    int next_combine;
+    float dt;
 };
 
 // TMA descriptors of one launch: W = packed final-layer weights {k, n} box {64, Npad}; A = bf16 activations {k, b, rec}
@@ -446,11 +453,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
                 for (; c0 + 8 <= c_end; c0 += 8) acc += fwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
                 if (a.Hg >= 2) {
                     const int h = g * a.Hg + hl;
-                    if (h < a.H && b0 + row < a.B) a.koutT[(size_t)h * a.Bp + b0 + row] = acc;   // k^T[h][b], coalesced over the lanes
+                    if (h < a.H && b0 + row < a.B) {
+                        const size_t off = (size_t)h * a.Bp + b0 + row;
+                        a.koutT[off] = acc;   // k^T[h][b], coalesced over the lanes
+                        if (a.zs_out)   // this thread's store above is visible to its own loads
+                            a.zs_out[(size_t)(b0 + row) * 128 + h] =
+                                __float2bfloat16(__fadd_rn(a.yT[off], stage_increment(a.next_combine, a.dt, a.kT, nullptr, off)));
+                    }
                 } else {
                     if (wg == 0) part[row] = acc;
                     named_bar_sync(1, kTcEpiThreads);
-                    if (wg == 1 && g < a.H && b0 + row < a.B) a.koutT[(size_t)g * a.Bp + b0 + row] = acc + part[row];
+                    if (wg == 1 && g < a.H && b0 + row < a.B) {
+                        const size_t off = (size_t)g * a.Bp + b0 + row;
+                        a.koutT[off] = acc + part[row];
+                        if (a.zs_out)
+                            a.zs_out[(size_t)(b0 + row) * 128 + g] =
+                                __float2bfloat16(__fadd_rn(a.yT[off], stage_increment(a.next_combine, a.dt, a.kT, nullptr, off)));
+                    }
                     named_bar_sync(1, kTcEpiThreads);
                 }
             }

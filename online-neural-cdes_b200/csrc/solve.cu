@@ -6,6 +6,7 @@
 
 #include "solve_kernels.cuh"
 #include "field_tc.cuh"
+#include "hidden_tc.cuh"
 #include "adaptive_kernels.cuh"
 
 namespace ncde {
@@ -85,6 +86,9 @@ struct Plan {
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
+    int tc_hid;               // hidden layers on the tensor cores too (fixed-grid bf16 path): bf16 row-major activation records
+    size_t abl_off[NCDE_MAX_LAYERS + 1];   // tc_hid: record offset (floats) of the bf16 [Bp][128] input of layer l
+    size_t off_Wh, off_bh;    // tc_hid: packed bf16 hidden weights [F][128][128], fp32 biases [F][128]
     int tc, Npad, KP, CpB;    // tensor-core path: columns per h-group padded to 16, K padded to 128; dX row pitch in smem
     int R, n_rt;
     int n_stages;
@@ -110,7 +114,7 @@ static size_t fwd_smem_floats(int DF, int S) {
     return (size_t)DF * S + (size_t)DF * kChunk + (size_t)(S / 4) * kChunk;
 }
 
-static int make_plan(const ncde_problem_t* p, Plan* pl) {
+static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false) {
     memset(pl, 0, sizeof(*pl));
     const ncde_mlp_t& m = p->mlp;
     NCDE_REQUIRE(p->B >= 1 && p->H >= 1 && p->C >= 1, NCDE_ERR_INVALID, "solve: B, H, C must be positive");
@@ -243,6 +247,20 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     pl->abf_off = off;
     if (pl->tc) off += (size_t)pl->Bp * pl->KP / 2;  // bf16 copy of the final-layer input
     pl->stage_floats = off;
+    {
+        int wmax = pl->H;
+        for (int l = 0; l <= pl->F; ++l) wmax = pl->D[l] > wmax ? pl->D[l] : wmax;
+        static const bool enabled = getenv("NCDE_TC_HIDDEN") != nullptr;   // TODO default on once the backward kernels land
+        pl->tc_hid = fixed_path && pl->tc && wmax <= 128 && enabled;
+    }
+    if (pl->tc_hid) {
+        // records of the all-tensor-core path: bf16 [Bp][128] input of every layer (the last one feeds the final layer), dX/dt
+        off = 0;
+        for (int l = 0; l <= pl->F; ++l) { pl->abl_off[l] = off; off += (size_t)pl->Bp * 64; }
+        pl->abf_off = pl->abl_off[pl->F];
+        pl->dx_off = off; off += (size_t)pl->Cp * pl->Bp;
+        pl->stage_floats = off;
+    }
 
     // packed weights
     off = 0;
@@ -286,6 +304,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl) {
     pl->off_W3T = off; off += round_up((size_t)pl->DF * pl->Np, 64);
     pl->off_W3R = off; off += round_up((size_t)pl->Np * pl->DFP, 64);
     pl->off_b3p = off; off += round_up(pl->Np, 64);
+    pl->off_Wh = off; off += (size_t)pl->F * 128 * 64;
+    pl->off_bh = off; off += (size_t)pl->F * 128;
     pl->wpack_floats = off;
     return NCDE_OK;
 }
@@ -336,6 +356,13 @@ static int pack_weights(const ncde_problem_t* p, const Plan& pl, float* wpack, i
             m.W[l], m.bias[l], wpack + pl.off_WT[l], wpack + pl.off_bp[l], with_rowmajor ? wpack + pl.off_WR[l] : nullptr,
             m.out_dim[l], pl.D[l], pl.ldw[l], pl.ldi[l]);
         ++*launches;
+    }
+    if (pl.tc_hid) {
+        for (int l = 0; l < pl.F; ++l) {
+            pack_hidden_bf16_kernel<<<64, 256, 0, st>>>(m.W[l], m.bias[l], (__nv_bfloat16*)(wpack + pl.off_Wh) + (size_t)l * 128 * 128,
+                                                        wpack + pl.off_bh + (size_t)l * 128, m.out_dim[l], m.in_dim[l]);
+            ++*launches;
+        }
     }
     if (pl.tc) {
         const int64_t n = (int64_t)pl.Np * pl.KP;
@@ -427,6 +454,20 @@ static int launch_tc_fwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cu
     NCDE_CUDA_OK(launch_pdl(tc_field_fwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.fwd_smem, st, ta, ms.maps));
     return NCDE_OK;
 }
+// descriptors of the tensor-core hidden layers: packed weights and the bf16 activation records (rec0 = first record)
+static int build_hidden_maps(const Plan& pl, const float* wpack, TcHiddenMaps* hm, const float* rec0, size_t rec_stride_floats,
+                             int64_t n_rec) {
+    memset(hm, 0, sizeof(*hm));
+    int rc = NCDE_OK;
+    if (pl.F > 0)
+        rc = make_map(&hm->W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_Wh, 128, 128, (uint64_t)pl.F, 256, 128 * 256, 64, 128,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+    for (int l = 0; l <= pl.F && rc == NCDE_OK; ++l)
+        rc = make_map(&hm->act[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rec0 + pl.abl_off[l], 128, (uint64_t)pl.B,
+                      (uint64_t)(n_rec < 1 ? 1 : n_rec), 256, n_rec > 1 ? rec_stride_floats * 4 : 0, 64, kTcM, CU_TENSOR_MAP_SWIZZLE_128B);
+    return rc;
+}
+
 static int launch_tc_bwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cudaStream_t st) {
     int rc = tc_records(ta, ms);
     if (rc != NCDE_OK) return rc;
@@ -470,7 +511,7 @@ extern "C" int ncde_profile_read(double* ms, int64_t* count) {
 
 extern "C" size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad) {
     Plan pl;
-    if (!p || !need_grad || make_plan(p, &pl) != NCDE_OK) return 0;
+    if (!p || !need_grad || make_plan(p, &pl, true) != NCDE_OK) return 0;
     return (size_t)p->grid.n_steps * pl.n_stages * pl.stage_floats * 4 + 256;
 }
 
@@ -485,7 +526,7 @@ static size_t adaptive_workspace_floats(const Plan& pl, int64_t n_out) {
 
 extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward) {
     Plan pl;
-    if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
+    if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
     size_t fl = backward ? bwd_workspace_floats(pl)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
@@ -499,7 +540,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     NCDE_REQUIRE(p && z0 && z_out && workspace, NCDE_ERR_INVALID, "solve_fwd: null pointer");
     NCDE_REQUIRE(!need_grad || saved, NCDE_ERR_INVALID, "solve_fwd: need_grad requires a saved buffer");
     Plan pl;
-    int rc = make_plan(p, &pl);
+    int rc = make_plan(p, &pl, true);
     if (rc != NCDE_OK) return rc;
     NCDE_REQUIRE(p->method != NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_fwd: use ncde_solve_adaptive_fwd for dopri5");
     rc = validate_grid(p, pl);
@@ -582,6 +623,26 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         else rc = build_tc_maps(pl, wpack, &ms, scratch_stage + pl.abf_off, 0, 1, dx_all, (size_t)pl.Cp * pl.Bp, n_st_total);
         if (rc != NCDE_OK) return rc;
     }
+    // all-tensor-core path: hidden layers read / write bf16 row-major records; the stage inputs are produced by the previous
+    // final-layer kernel (or by `advance` / the initial conversion)
+    TcHiddenMaps hm;
+    TcHiddenArgs th;
+    memset(&th, 0, sizeof(th));
+    float* const rec0 = need_grad ? (float*)saved : scratch_stage;
+    const size_t rec_stride = need_grad ? pl.stage_floats : 0;
+    auto a0_of = [&](int64_t rec) { return (__nv_bfloat16*)(rec0 + (size_t)rec * rec_stride + pl.abl_off[0]); };
+    if (pl.tc_hid && n_st_total > 0) {
+        rc = build_hidden_maps(pl, wpack, &hm, rec0, pl.stage_floats, need_grad ? n_st_total : 1);
+        if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_fwd_kernel, tc_hid_smem_bytes());
+        if (rc != NCDE_OK) return rc;
+        th.B = pl.B; th.F = pl.F; th.bias = wpack + pl.off_bh;
+        for (int l = 0; l < pl.F; ++l) th.act[l] = p->mlp.act[l];
+        if (pl.H < 128)   // feature padding of the stage-input records must be zero, not whatever the buffer held
+            NCDE_CUDA_OK(cudaMemset2DAsync(rec0 + pl.abl_off[0], (need_grad ? pl.stage_floats : (size_t)pl.Bp * 64) * 4, 0,
+                                           (size_t)pl.Bp * 256, need_grad ? (size_t)n_st_total : 1, st));
+        to_bf16_rows_kernel<<<(unsigned)ceil_div((int64_t)pl.B * 128, 256), 256, 0, st>>>(z0, a0_of(0), pl.B, pl.H);
+        ++launches;
+    }
 
     static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
     int cur = 0;
@@ -598,11 +659,26 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             ha.dXT = nullptr;  // precomputed by dx_all_kernel
             ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
             ha.path.t = g.stage_t[s * NS + i];
-            {
+            if (pl.tc_hid) {
+                if (pl.F > 0) {
+                    ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
+                    th.rec = need_grad ? (int)(s * NS + i) : 0;
+                    NCDE_CUDA_OK(launch_pdl(tc_hidden_fwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads), tc_hid_smem_bytes(),
+                                            st, th, hm));
+                    ++launches;
+                }
+                // this stage's final-layer kernel emits the next stage's input record
+                const bool emit = i + 1 < NS;
+                ta.zs_out = emit ? a0_of(need_grad ? s * NS + i + 1 : 0) : nullptr;
+                ta.yT = yT[cur];
+                for (int j = 0; j < NS; ++j) ta.kT[j] = kT[j];
+                ta.next_combine = emit && p->method == NCDE_RK4_38 ? rk4_combine[i + 1] : COMBINE_Y;
+                ta.dt = dt;
+            } else {
                 ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
                 NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+                ++launches;
             }
-            ++launches;
             fa.actT = stage + pl.act_off[pl.F];
             fa.dXT = dx_stage;
             fa.koutT = kT[i];
@@ -627,6 +703,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         aa.B = pl.B; aa.Bp = pl.Bp; aa.H = pl.H; aa.method = p->method; aa.dt = dt;
         aa.yT = yT[cur]; aa.ynewT = yT[cur ^ 1];
         for (int i = 0; i < NS; ++i) aa.kT[i] = kT[i];
+        aa.ybf = (pl.tc_hid && s + 1 < g.n_steps) ? a0_of(need_grad ? (s + 1) * NS : 0) : nullptr;
         bool first = true;
         while (first || (j_out < g.n_out && g.out_step[j_out] == s)) {
             aa.n_emit = 0;

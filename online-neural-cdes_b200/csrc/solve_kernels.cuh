@@ -106,6 +106,7 @@ struct AdvanceArgs {
     float* emit_ptr[4];  // (B,H) row-major slices of z_out
     int emit_mode[4];
     float emit_slope[4];
+    __nv_bfloat16* ybf;  // all-tensor-core path: bf16 row-major [Bp][128] copy of y_{n+1} (input record of the next stage) or null
 };
 
 struct HiddenBwdArgs {
@@ -681,6 +682,7 @@ __global__ void advance_kernel(const __grid_constant__ AdvanceArgs a) {
                 yn = __fadd_rn(y, __fmul_rn(a.dt, a.kT[0][off]));
             }
             a.ynewT[off] = yn;
+            if (a.ybf) a.ybf[(size_t)b * 128 + h] = __float2bfloat16(yn);
         }
         t_old[i][threadIdx.x] = y;
         t_new[i][threadIdx.x] = yn;
