@@ -43,6 +43,14 @@ struct TcFieldArgs {
     const float* kT[NCDE_MAX_STAGES];   // stage derivatives incl. the one this launch writes (koutT)
     int next_combine;
     float dt;
+    // backward of the all-tensor-core path: dL/dk of this stage is formed on the fly from the gradient of the step result and
+    // the stage-input gradients of the LATER stages (rk_common.py:106-114 transposed), so no gk arrays are read-modify-written:
+    //     gk[b,h] = gcoef * gy1[b,h] + sum_q dzcoef[q] * dz_q[b,h]
+    const float* gy1T;         // [H][Bp] or null (then gkT is read)
+    float gcoef;
+    int n_dz;
+    const float* dzT[NCDE_MAX_STAGES];
+    float dzcoef[NCDE_MAX_STAGES];
 };
 
 // TMA descriptors of one launch: W = packed final-layer weights {k, n} box {64, Npad}; A = bf16 activations {k, b, rec}
@@ -698,7 +706,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             // ---- epilogue 1: G tile; per h, branch-free over the channels ----
             for (int hl = h_begin; hl < h_end; ++hl) {
                 const int h = g * a.Hg + hl;
-                const float gk = (row_ok && h < a.H) ? __ldg(a.gkT + (size_t)h * a.Bp + b) : 0.f;
+                float gk = 0.f;
+                if (row_ok && h < a.H) {
+                    const size_t off = (size_t)h * a.Bp + b;
+                    if (a.gy1T) {
+                        gk = a.gcoef * __ldg(a.gy1T + off);
+                        for (int q = 0; q < a.n_dz; ++q) gk = fmaf(a.dzcoef[q], __ldg(a.dzT[q] + off), gk);
+                    } else {
+                        gk = __ldg(a.gkT + off);
+                    }
+                }
                 const int colbase = hl * a.Cp;
                 int c0 = c_begin;
                 for (; c0 + 32 <= c_end; c0 += 32)

@@ -208,4 +208,327 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_fwd_kernel(const __gr
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the hidden layers.
+//
+// p_reduce: dL/d(a_F) = sum over the h-groups of the final-layer kernel's partials P[g][b][k], times act'(a_F), rounded to
+// a bf16 row-major record — the first operand tile of the tensor-core chain.  Batch-split over every SM (the 64-way sum is
+// 33 MB of L2 reads per stage: this part must not sit on 8 SMs).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad_bf(float out, int act) {
+    if (act == NCDE_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+    if (act == NCDE_ACT_TANH) return 1.f - out * out;
+    return 1.f;
+}
+
+struct PReduceArgs {
+    int B, n_hg, DFP, act;         // act: activation of the last hidden layer
+    const float* P;                // [n_hg][B][DFP], DFP == 128
+    const __nv_bfloat16* aF;       // [Bp][128] output of the last hidden layer (saved record)
+    __nv_bfloat16* dpre;           // [Bp][128]
+};
+
+__global__ void __launch_bounds__(256) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, float4 of k)
+    const int64_t b = idx >> 5;
+    const int k4 = (int)(idx & 31);
+    if (b >= a.B) return;
+    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)b * 128) + k4;
+    const size_t gs = (size_t)a.B * 32;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 16
+    for (int g = 0; g < a.n_hg; ++g) {
+        const float4 v = __ldg(p + (size_t)g * gs);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const uint2 ab = *reinterpret_cast<const uint2*>(a.aF + (size_t)b * 128 + k4 * 4);
+    const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ab.x));
+    const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ab.y));
+    s.x *= act_grad_bf(a01.x, a.act); s.y *= act_grad_bf(a01.y, a.act);
+    s.z *= act_grad_bf(a23.x, a.act); s.w *= act_grad_bf(a23.y, a.act);
+    __nv_bfloat162 o01 = __floats2bfloat162_rn(s.x, s.y), o23 = __floats2bfloat162_rn(s.z, s.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&o01);
+    o.y = *reinterpret_cast<uint32_t*>(&o23);
+    *reinterpret_cast<uint2*>(a.dpre + (size_t)b * 128 + k4 * 4) = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tc_hidden_bwd: CTA = one 128-row batch tile; for l = F-1 .. 0, with dpre_l (gradient w.r.t. the pre-activation of layer
+// l) and a_l (its input) as bf16 operand tiles in shared memory:
+//   dgrad   da_l[b][i]   = dpre_l . W_l           (A = dpre_l K-major, B = W_l MN-major)        -> TMEM cols [0, 128)
+//   wgrad   dW_l^T[i][o] = a_l^T . dpre_l         (both MN-major, K = batch rows)               -> TMEM cols [128 (l+1), +128)
+//   bias    db_l[o]      = column sums of the dpre_l tile (CUDA cores, while the tensor core works)
+//   epi     l > 0: dpre_{l-1} = da_l * act'(a_l) -> bf16 operand tile of the next level
+//           l = 0: dz = da_0 -> fp32 feature-major dL/d(stage input); the RK adjoint combination happens where it is consumed
+// The weight gradients stay in TMEM until the end of the CTA and are then added to the global accumulators with
+// reductions (layers sharing a parameter slot simply add into the same accumulator).  Warp 8 is the producer (TMA + MMA).
+// ---------------------------------------------------------------------------------------------------------------
+struct TcHiddenBwdMaps {
+    CUtensorMap W;                        // as in the forward kernel
+    CUtensorMap act[kTcHidMaxLayers];     // act[l]: saved input of layer l
+    CUtensorMap dpre;                     // {128, B, 1}: output of p_reduce
+};
+
+struct TcHiddenBwdArgs {
+    int B, Bp, H, F, rec;
+    int act[kTcHidMaxLayers];             // activation of layer l (act[l-1] is the one a_l went through)
+    float* dWacc[kTcHidMaxLayers];        // [128 out][128 in] fp32 accumulator of layer l's parameter slot
+    float* dbacc[kTcHidMaxLayers];        // [128]
+    float* dz_out;                        // [H][Bp] fp32: dL/d(stage input) of this stage
+};
+
+struct TcHidBwdSmem { uint32_t Wt, At, Dt, bsum, bars, total; };
+__host__ __device__ inline TcHidBwdSmem tc_hid_bwd_layout() {
+    TcHidBwdSmem L;
+    uint32_t o = 0;
+    L.Wt = o; o += 2 * kTcHidTile;
+    L.At = o; o += 2 * kTcHidTile;
+    L.Dt = o; o += 2 * kTcHidTile;
+    L.bsum = o; o += 8 * 128 * 4;
+    L.bars = o; o += 16 * 8;
+    L.total = o;
+    return L;
+}
+static inline size_t tc_hid_bwd_smem_bytes() { return 1024 + tc_hid_bwd_layout().total; }
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __grid_constant__ TcHiddenBwdArgs a,
+                                                                      const __grid_constant__ TcHiddenBwdMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const TcHidBwdSmem L = tc_hid_bwd_layout();
+    uint8_t* Wt = smem + L.Wt;     // weights of level l in buffer l & 1
+    uint8_t* At = smem + L.At;     // a_l in buffer l & 1
+    uint8_t* Dt = smem + L.Dt;     // dpre_l in buffer l & 1
+    float* bsum = reinterpret_cast<float*>(smem + L.bsum);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* w_full = bars;          // [2]
+    uint64_t* a_full = bars + 2;      // [2]
+    uint64_t* d_full = bars + 4;      // TMA: dpre_{F-1}
+    uint64_t* dg_bar = bars + 5;      // dgrad of the level complete
+    uint64_t* lvl_bar = bars + 6;     // every MMA of the level complete (operand buffers free)
+    uint64_t* dp_ready = bars + 7;    // epilogue -> producer: dpre_{l-1} tile written (8 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b0 = blockIdx.x * kTcM;
+    const int F = a.F;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(w_full + i, 1); mbar_init(a_full + i, 1); }
+        mbar_init(d_full, 1); mbar_init(dg_bar, 1); mbar_init(lvl_bar, 1); mbar_init(dp_ready, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto load_W = [&](int l) {
+        uint8_t* dst = Wt + (size_t)(l & 1) * kTcHidTile;
+        mbar_expect_tx(w_full + (l & 1), kTcHidTile);
+        tma_load_3d(dst, &maps.W, w_full + (l & 1), 0, 0, l);
+        tma_load_3d(dst + kTcHidTile / 2, &maps.W, w_full + (l & 1), 64, 0, l);
+    };
+    auto load_A = [&](int l) {   // saved records: written by the forward pass, older than every kernel of the backward pass
+        uint8_t* dst = At + (size_t)(l & 1) * kTcHidTile;
+        mbar_expect_tx(a_full + (l & 1), kTcHidTile);
+        tma_load_3d(dst, &maps.act[l], a_full + (l & 1), 0, b0, a.rec);
+        tma_load_3d(dst + kTcHidTile / 2, &maps.act[l], a_full + (l & 1), 64, b0, a.rec);
+    };
+    const bool producer = warp == 8 && lane == 0;
+    if (producer) {
+        tma_prefetch_desc(&maps.dpre);
+        load_W(F - 1); load_A(F - 1);
+        if (F > 1) { load_W(F - 2); load_A(F - 2); }
+    }
+    pdl_trigger();
+    pdl_wait();   // dpre_{F-1} comes from p_reduce; gy / gk from the previous kernels
+
+    // phase bookkeeping: level index n = F-1-l counts 0, 1, ... ; buffers are indexed by l & 1, barrier phases by use count
+    if (warp == 8) {
+        if (lane == 0) {
+            uint8_t* d_top = Dt + (size_t)((F - 1) & 1) * kTcHidTile;
+            mbar_expect_tx(d_full, kTcHidTile);
+            tma_load_3d(d_top, &maps.dpre, d_full, 0, b0, 0);
+            tma_load_3d(d_top + kTcHidTile / 2, &maps.dpre, d_full, 64, b0, 0);
+            uint32_t use_w[2] = {0, 0};
+            for (int l = F - 1, n = 0; l >= 0; --l, ++n) {
+                const int bf = l & 1;
+                if (n == 0) mbar_wait(d_full, 0);
+                else {
+                    mbar_wait(dp_ready, (uint32_t)(n - 1) & 1u);   // dpre_l written; every warp is done with a_{l+1}
+                    if (l - 1 >= 0) {
+                        // buffers of level l+1 are free once its MMAs have completed too: prefetch level l-1 into them
+                        mbar_wait(lvl_bar, (uint32_t)(n - 1) & 1u);
+                        load_W(l - 1); load_A(l - 1);
+                    }
+                }
+                mbar_wait(w_full + bf, use_w[bf] & 1u);
+                mbar_wait(a_full + bf, use_w[bf] & 1u);
+                ++use_w[bf];
+                tc_fence_after();
+                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile), w_s = smem_u32(Wt + (size_t)bf * kTcHidTile),
+                               a_s = smem_u32(At + (size_t)bf * kTcHidTile);
+                {   // dgrad: D[128 b x 128 i] = dpre_l (K-major over o) . W_l (MN-major: N = i contiguous, K = o rows)
+                    const uint32_t idesc = make_idesc(kTcM, 128, 0, 1);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
+                        umma_bf16(tmem_base, make_sdesc(d_s + a_off, 16, 1024), make_sdesc(w_s + (uint32_t)ks * 2048u, 128u * 128u, 1024), idesc,
+                                  ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(dg_bar);
+                {   // wgrad: D[128 i x 128 o] = a_l^T (MN-major: M = i contiguous, K = b rows) . dpre_l (MN-major: N = o contiguous)
+                    const uint32_t idesc = make_idesc(128, 128, 1, 1);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t off = (uint32_t)ks * 2048u;
+                        umma_bf16(tmem_base + 128u * (uint32_t)(l + 1), make_sdesc(a_s + off, 128u * 128u, 1024),
+                                  make_sdesc(d_s + off, 128u * 128u, 1024), idesc, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(lvl_bar);
+            }
+        }
+    } else {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const int64_t b = (int64_t)b0 + row;
+        const bool row_ok = b < a.B;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t use_a[2] = {0, 0};
+        for (int l = F - 1, n = 0; l >= 0; --l, ++n) {
+            const int bf = l & 1;
+            // ---- bias gradient: column sums of the dpre_l tile (16 chunks of 8 columns x 8 row slices of 16 rows) ----
+            if (n == 0) mbar_wait(d_full, 0);
+            else named_bar_sync(1, kTcEpiThreads);      // every warp has written its rows of dpre_l
+            if (lane < 16) {
+                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile);
+                float bacc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+#pragma unroll 4
+                for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+                    uint32_t w4[4];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                                 : "r"(d_s + sw128_off(r, lane, kTcM)));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                        bacc[2 * j] += f.x;
+                        bacc[2 * j + 1] += f.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[warp * 128 + lane * 8 + j] = bacc[j];
+            }
+            named_bar_sync(1, kTcEpiThreads);
+            if (tid < 128) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sacc += bsum[w * 128 + tid];
+                if (a.dbacc[l]) atomicAdd(a.dbacc[l] + tid, sacc);
+            }
+            // ---- epilogue of the level ----
+            mbar_wait(dg_bar, (uint32_t)n & 1u);
+            tc_fence_after();
+            if (l > 0) {
+                mbar_wait(a_full + bf, use_a[bf] & 1u);   // a_l landed (the producer waited on it too; this makes it visible here)
+                const uint32_t a_s = smem_u32(At + (size_t)bf * kTcHidTile);
+                const uint32_t dst = smem_u32(Dt + (size_t)((l - 1) & 1) * kTcHidTile);
+                const int act = a.act[l - 1];
+#pragma unroll
+                for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+                    uint32_t av[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(av[4 * q]), "=r"(av[4 * q + 1]), "=r"(av[4 * q + 2]),
+                                     "=r"(av[4 * q + 3]) : "r"(a_s + sw128_off(row, (c0 >> 3) + q, kTcM)));
+                    tmem_wait_ld<32>(r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 av2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[4 * q + j]));
+                            const float g0 = row_ok ? __uint_as_float(r[8 * q + 2 * j]) * act_grad_bf(av2.x, act) : 0.f;
+                            const float g1 = row_ok ? __uint_as_float(r[8 * q + 2 * j + 1]) * act_grad_bf(av2.y, act) : 0.f;
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + sw128_off(row, (c0 >> 3) + q, kTcM)), "r"(pk[0]),
+                                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    }
+                }
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dp_ready);
+            } else {
+                // dz, feature-major fp32: plain stores, coalesced over the lanes (= rows)
+#pragma unroll
+                for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+                    tmem_wait_ld<32>(r);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < a.H) a.dz_out[(size_t)(c0 + j) * a.Bp + b] = __uint_as_float(r[j]);
+                    }
+                }
+                tc_fence_before();
+            }
+            ++use_a[bf];
+        }
+        // ---- weight gradients: TMEM (lanes = i, columns = o) -> global accumulators [o][i] ----
+        mbar_wait(lvl_bar, (uint32_t)(F - 1) & 1u);
+        tc_fence_after();
+        for (int l = 0; l < F; ++l) {
+            float* acc = a.dWacc[l];
+            const int i = row;
+#pragma unroll
+            for (int o0 = wg * 64; o0 < wg * 64 + 64; o0 += 32) {
+                uint32_t r[32];
+                tmem_ld32_issue(lane_addr + 128u * (uint32_t)(l + 1) + (uint32_t)o0, r);
+                tmem_wait_ld<32>(r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(acc + (size_t)(o0 + j) * 128 + i, __uint_as_float(r[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// gW[o][i] += acc[o][i], gb[o] += accb[o] from the padded accumulators (launched once per layer, in order, so layers that
+// share a parameter tensor add into it one after the other)
+// gy += dz_0 + ... + dz_{n-1}: every stage input depends on y with unit Jacobian
+__global__ void gy_accumulate_kernel(float* __restrict__ gyT, const float* dz0, const float* dz1, const float* dz2, const float* dz3,
+                                     int n_dz, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = gyT[i] + dz0[i];
+    if (n_dz > 1) g += dz1[i];
+    if (n_dz > 2) g += dz2[i];
+    if (n_dz > 3) g += dz3[i];
+    gyT[i] = g;
+}
+
+__global__ void unpack_hidden_grad_kernel(const float* __restrict__ acc, const float* __restrict__ accb, float* __restrict__ gW,
+                                          float* __restrict__ gb, int Dout, int Din) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < Dout * Din) gW[idx] += acc[(size_t)(idx / Din) * 128 + idx % Din];
+    if (gb && idx < Dout) gb[idx] += accb[idx];
+}
+
 }  // namespace ncde

@@ -250,8 +250,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     {
         int wmax = pl->H;
         for (int l = 0; l <= pl->F; ++l) wmax = pl->D[l] > wmax ? pl->D[l] : wmax;
-        static const bool enabled = getenv("NCDE_TC_HIDDEN") != nullptr;   // TODO default on once the backward kernels land
-        pl->tc_hid = fixed_path && pl->tc && wmax <= 128 && enabled;
+        static const bool enabled = getenv("NCDE_NO_TC_HIDDEN") == nullptr;   // NCDE_NO_TC_HIDDEN=1: CUDA-core hidden layers (A/B runs)
+        pl->tc_hid = fixed_path && pl->tc && wmax <= 128 && pl->F <= 3 && enabled;
     }
     if (pl->tc_hid) {
         // records of the all-tensor-core path: bf16 [Bp][128] input of every layer (the last one feeds the final layer), dX/dt
@@ -342,6 +342,7 @@ static size_t bwd_workspace_floats(const Plan& pl) {
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
     n += (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
+    if (pl.tc_hid) n += (size_t)pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per;   // dpre record, weight-gradient accumulators
     return n;
 }
 
@@ -737,7 +738,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     NCDE_REQUIRE(p && grad_out && saved && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID, "solve_bwd: null pointer");
     NCDE_REQUIRE(grad_coeffs == nullptr, NCDE_ERR_UNSUPPORTED, "solve_bwd: gradient w.r.t. the control path is not implemented");
     Plan pl;
-    int rc = make_plan(p, &pl);
+    int rc = make_plan(p, &pl, true);
     if (rc != NCDE_OK) return rc;
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
@@ -761,6 +762,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         for (int l = 0; l < pl.F; ++l) dpreT[i][l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
     float* dW3acc = cv.take((size_t)pl.n_bt * pl.Np * pl.DFP);
     float* db3acc = cv.take((size_t)pl.n_bt * pl.Np);
+    // all-tensor-core path: one bf16 record for dL/d(pre-activation of the last hidden layer), padded fp32 accumulators
+    const bool tc_hid = pl.tc_hid && pl.F > 0;
+    float* dpre_rec = tc_hid ? cv.take((size_t)pl.Bp * 64) : nullptr;
+    float* dWh_acc = tc_hid ? cv.take((size_t)pl.F * 128 * 128) : nullptr;
+    float* dbh_acc = tc_hid ? cv.take((size_t)pl.F * 128) : nullptr;
 
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
@@ -797,6 +803,36 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     }
     hb.w_in_smem = pl.w_in_smem; hb.wsm_floats = (int)round_up(pl.wr_floats, 4);
     hb.P = P; hb.gyT = gyT;
+    TcHiddenBwdMaps hbm;
+    TcHiddenBwdArgs thb;
+    PReduceArgs pr;
+    memset(&thb, 0, sizeof(thb));
+    memset(&pr, 0, sizeof(pr));
+    if (tc_hid) {
+        NCDE_REQUIRE(pl.F <= 3, NCDE_ERR_UNSUPPORTED, "solve_bwd: at most 3 hidden layers on the tensor-core path");
+        memset(&hbm, 0, sizeof(hbm));
+        const int64_t n_rec = g.n_steps * NS;
+        rc = make_map(&hbm.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_Wh, 128, 128, (uint64_t)pl.F, 256, 128 * 256, 64, 128,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+        for (int l = 0; l < pl.F && rc == NCDE_OK; ++l)
+            rc = make_map(&hbm.act[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const float*)saved + pl.abl_off[l], 128, (uint64_t)pl.B,
+                          (uint64_t)(n_rec < 1 ? 1 : n_rec), 256, n_rec > 1 ? pl.stage_floats * 4 : 0, 64, kTcM, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == NCDE_OK)
+            rc = make_map(&hbm.dpre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dpre_rec, 128, (uint64_t)pl.B, 1, 256, 0, 64, kTcM,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_bwd_kernel, tc_hid_bwd_smem_bytes());
+        if (rc != NCDE_OK) return rc;
+        NCDE_CUDA_OK(cudaMemsetAsync(dWh_acc, 0, (size_t)pl.F * (128 * 128) * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(dbh_acc, 0, (size_t)pl.F * 128 * 4, st));
+        thb.B = pl.B; thb.Bp = pl.Bp; thb.H = pl.H; thb.F = pl.F;
+        for (int l = 0; l < pl.F; ++l) {
+            thb.act[l] = m.act[l];
+            // layers that share a parameter slot add into the accumulator of the first of them
+            thb.dWacc[l] = dWh_acc + (size_t)pl.first_of_slot[l] * 128 * 128;
+            thb.dbacc[l] = dbh_acc + (size_t)pl.first_of_slot[l] * 128;
+        }
+        pr.B = pl.B; pr.n_hg = pl.n_hg; pr.DFP = pl.DFP; pr.act = m.act[pl.F - 1]; pr.P = P; pr.dpre = (__nv_bfloat16*)dpre_rec;
+    }
     rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_wgrad_kernel, 36 * 1024);
     if (rc != NCDE_OK) return rc;
@@ -850,8 +886,10 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 ++launches;
             }
         }
-        NCDE_CUDA_OK(launch_pdl(rk_bwd_begin_kernel, dim3(ew_grid), dim3(256), 0, st, (const float*)gyT, gkT[0], gkT[1], gkT[2], gkT[3], (int)p->method, dt, (int64_t)nHB));
-        ++launches;
+        if (!tc_hid) {
+            NCDE_CUDA_OK(launch_pdl(rk_bwd_begin_kernel, dim3(ew_grid), dim3(256), 0, st, (const float*)gyT, gkT[0], gkT[1], gkT[2], gkT[3], (int)p->method, dt, (int64_t)nHB));
+            ++launches;
+        }
         for (int i = NS - 1; i >= 0; --i) {
             const float* stage = (const float*)saved + (size_t)(s * NS + i) * pl.stage_floats;
             fa.actT = stage + pl.act_off[pl.F];
@@ -863,6 +901,19 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = stage + pl.dx_off;
                     ta.gkT = gkT[i];
+                    if (tc_hid) {
+                        // dL/dk_i = c_i dt gy1 + sum over later stages q of d(stage input q)/dk_i * dz_q; the dz_q live in gkT[q]
+                        ta.gy1T = gyT;
+                        ta.n_dz = 0;
+                        if (p->method == NCDE_RK4_38) {
+                            ta.gcoef = (i == 0 || i == 3) ? dt * 0.125f : 3.f * (dt * 0.125f);
+                            const float c[4][4] = {{0, dt * third, -(dt * third), dt}, {0, 0, dt, -dt}, {0, 0, 0, dt}, {0, 0, 0, 0}};
+                            for (int q = i + 1; q < NS; ++q)
+                                if (c[i][q] != 0.f) { ta.dzT[ta.n_dz] = gkT[q]; ta.dzcoef[ta.n_dz] = c[i][q]; ++ta.n_dz; }
+                        } else {
+                            ta.gcoef = dt;
+                        }
+                    }
                     { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
@@ -883,13 +934,29 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 if (i == 3) { hb.n_k = 3; hb.kcoef[0] = dt; hb.kcoef[1] = -dt; hb.kcoef[2] = dt; }
                 for (int j = 0; j < hb.n_k; ++j) hb.gkT[j] = gkT[j];
             }
+            if (tc_hid) {
+                ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
+                pr.aF = (const __nv_bfloat16*)(stage + pl.abl_off[pl.F]);
+                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div((int64_t)pl.B * 32, 256)), dim3(256), 0, st, pr));
+                thb.rec = (int)(s * NS + i);
+                thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
+                NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads), tc_hid_bwd_smem_bytes(),
+                                        st, thb, hbm));
+                launches += 2;
+                continue;
+            }
             {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
             }
             ++launches;
         }
-        if (pl.F > 0) {
+        if (tc_hid) {
+            NCDE_CUDA_OK(launch_pdl(gy_accumulate_kernel, dim3(ew_grid), dim3(256), 0, st, gyT, (const float*)gkT[0], (const float*)gkT[1],
+                                    (const float*)gkT[2], (const float*)gkT[3], NS, (int64_t)nHB));
+            ++launches;
+        }
+        if (pl.F > 0 && !tc_hid) {
             // hidden weight gradients of all stages of this step in one launch (off the sequential chain)
             wa.n_stage = NS;
             for (int i = 0; i < NS; ++i) {
@@ -911,7 +978,15 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         }
         j_hi = j_lo;
     }
-    if (pl.F > 0) {
+    if (tc_hid) {
+        for (int l = 0; l < pl.F; ++l) {
+            if (pl.first_of_slot[l] != l) continue;   // the slot's accumulator already holds the sum over its layers
+            const int n = m.out_dim[l] * m.in_dim[l];
+            unpack_hidden_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dWh_acc + (size_t)l * 128 * 128, dbh_acc + (size_t)l * 128,
+                                                                                gW[l], gbias[l], m.out_dim[l], m.in_dim[l]);
+            ++launches;
+        }
+    } else if (pl.F > 0) {
         int nmax = 0;
         for (int s2 = 0; s2 < wa.n_slots; ++s2) nmax = wa.Dout[s2] * wa.Din[s2] > nmax ? wa.Dout[s2] * wa.Din[s2] : nmax;
         hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, st>>>(wa);
