@@ -546,7 +546,7 @@ __device__ __forceinline__ void bwd_chunk(uint32_t taddr, uint32_t b3_s, uint32_
 struct TcBwdSmem {
     uint32_t Ws, As, Gs, dXs, b3s, bsum, bars, total;
 };
-__host__ __device__ inline TcBwdSmem tc_bwd_layout(int Npad, int CpB) {
+__host__ __device__ inline TcBwdSmem tc_bwd_layout(int Npad, int CpB, int EW) {
     TcBwdSmem L;
     const uint32_t NP64 = ((uint32_t)Npad + 63u) & ~63u;
     uint32_t o = 0;
@@ -555,27 +555,32 @@ __host__ __device__ inline TcBwdSmem tc_bwd_layout(int Npad, int CpB) {
     L.Gs = o; o += kTcM * NP64 * 2;
     L.dXs = o; o += kTcM * (uint32_t)CpB * 4;
     L.b3s = o; o += (uint32_t)Npad * 4;
-    L.bsum = o; o += 8u * (uint32_t)Npad * 4;
+    L.bsum = o; o += (uint32_t)EW * (uint32_t)Npad * 4;
     o = (o + 15u) & ~15u;
     L.bars = o; o += 16 * 8;
     L.total = o;
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a,
-                                                                     const __grid_constant__ TcMaps maps) {
+// EW = number of epilogue warps (8 or 16; with 16, four warps share each TMEM lane quarter and split the columns).  Measured on
+// cfg 5: 8 warps 36.8 us per launch, 16 warps 40.6 us — the epilogue is not occupancy-bound, so 8 is the default (NCDE_BWD_EW=16
+// selects the other instantiation for A/B runs).
+template <int EW>
+__global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a,
+                                                                       const __grid_constant__ TcMaps maps) {
+    constexpr int kEpi = EW * 32, kAll = EW * 32 + 32, kCg = EW / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Npad = a.Npad;
     constexpr int KP = kTcKP;
-    const TcBwdSmem L = tc_bwd_layout(Npad, a.CpB);
+    const TcBwdSmem L = tc_bwd_layout(Npad, a.CpB, EW);
     const uint32_t a_bytes = kTcM * kTcKP * 2, x_bytes = kTcM * (uint32_t)a.CpB * 4;
     uint8_t* Ws = smem + L.Ws;                            // [Npad][KP]  bf16 swizzled (rows n, contiguous k)
     uint8_t* As = smem + L.As;                            // [128][KP]   (rows m, contiguous k)
     uint8_t* Gs = smem + L.Gs;                            // [128][NP64] (rows m, contiguous n)
     uint8_t* dXs = smem + L.dXs;                          // [128][CpB] fp32
     float* b3s = reinterpret_cast<float*>(smem + L.b3s);  // [Npad]
-    float* bsum = reinterpret_cast<float*>(smem + L.bsum);  // [8 row slices][Npad]
+    float* bsum = reinterpret_cast<float*>(smem + L.bsum);  // [EW row slices][Npad]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* full_a = bars;
     uint64_t* wg_bar = bars + 1;
@@ -593,11 +598,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(full_x, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, 8);
-        mbar_init(dg_bar, 1); mbar_init(done2, 8); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
+        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(full_x, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, EW);
+        mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < Npad; i += kTcThreads) b3s[i] = a.b3[(size_t)g * Npad + i];
+    for (int i = tid; i < Npad; i += kAll) b3s[i] = a.b3[(size_t)g * Npad + i];
     const int S = a.Hg * a.Cp;                          // valid columns (multiple of 8); [S, Npad) is zero padding
     if (S < Npad && tid < kTcM) *reinterpret_cast<uint4*>(Gs + sw128_off(tid, S >> 3, kTcM)) = make_uint4(0, 0, 0, 0);
     fence_async_smem();
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const bool producer = warp == 8 && lane == 0;
+    const bool producer = warp == EW && lane == 0;
     if (producer) {
         tma_prefetch_desc(&maps.A);
         tma_prefetch_desc(&maps.X);
@@ -621,7 +626,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     if (a.ctrl && a.ctrl->done) row_end = row_begin;
     const int nt = row_end > row_begin ? (int)((row_end - row_begin + kTcM - 1) / kTcM) : 0;
 
-    if (warp == 8) {
+    if (warp == EW) {
         if (lane == 0 && nt > 0) {
             auto load_A = [&](int i) {
                 const int b0 = (int)(row_begin + (int64_t)i * kTcM);
@@ -677,17 +682,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             umma_commit(fin_bar);
         }
     } else {
-        const int wg = warp >> 2;
+        const int cg = warp >> 2;                    // column group: the kCg warps of a TMEM lane quarter split the columns
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        int h_begin, h_end, c_begin, c_end;
-        if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
-        else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+        // columns are handed out as units (h, channel part): P parts per h when there are fewer h's than column groups
+        const int P = a.Hg >= kCg ? 1 : kCg / a.Hg;
+        const int U = a.Hg * P;
+        const int u_begin = cg * U / kCg, u_end = (cg + 1) * U / kCg;
+        const int cw = (((a.Cp + P - 1) / P) + 7) & ~7;
         // column split of the final dW^T read-out (16-column chunks)
-        const int split = (Npad / 2) & ~15;
-        const int col_begin = wg == 0 ? 0 : split;
-        const int col_end = wg == 0 ? split : Npad;
-        // bias gradient: thread (chunk of 8 columns = lane, slice of 16 rows = warp) keeps its partial column sums in registers
+        const int col_begin = (cg * Npad / kCg) & ~15;
+        const int col_end = cg == kCg - 1 ? Npad : (((cg + 1) * Npad / kCg) & ~15);
+        // bias gradient: thread (chunk of 8 columns = lane, slice of 128 / EW rows = warp) keeps its partial column sums in registers
         const int n_chunk8 = Npad >> 3;                     // <= 30
         float bacc[8];
 #pragma unroll
@@ -704,7 +710,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             mbar_wait(pre_bar, ph);
             tc_fence_after();
             // ---- epilogue 1: G tile; per h, branch-free over the channels ----
-            for (int hl = h_begin; hl < h_end; ++hl) {
+            for (int u = u_begin; u < u_end; ++u) {
+                const int hl = u / P, c_begin = (u % P) * cw, c_end = min(a.Cp, c_begin + cw);
                 const int h = g * a.Hg + hl;
                 float gk = 0.f;
                 if (row_ok && h < a.H) {
@@ -728,10 +735,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(g_ready);
             // bias gradient from the bf16 G tile while the tensor core works: every warp needs ALL rows -> epilogue-wide barrier
-            named_bar_sync(1, kTcEpiThreads);
+            named_bar_sync(1, kEpi);
             if (lane < n_chunk8) {
 #pragma unroll 4
-                for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+                for (int r = warp * (kTcM / EW); r < (warp + 1) * (kTcM / EW); ++r) {
                     uint32_t w4[4];
                     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
                                  : "r"(gs_s + sw128_off(r, lane, kTcM)));
@@ -747,7 +754,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             tc_fence_after();
             // ---- epilogue 2: partial input gradient of this h-group ----
             {
-                const int kb = wg * (KP / 2), ke = kb + KP / 2;
+                const int kb = cg * (KP / kCg), ke = kb + KP / kCg;
                 float* prow = a.P + ((size_t)g * a.B + (size_t)b) * a.DFP;
                 for (int k0 = kb; k0 < ke; k0 += 16) {
                     float v[16];
@@ -771,7 +778,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
             }
             mbar_wait(fin_bar, 0);
             tc_fence_after();
-            named_bar_sync(1, kTcEpiThreads);
+            named_bar_sync(1, kEpi);
             const int k = row;
             if (k < KP) {
                 for (int n0 = col_begin; n0 < col_end; n0 += 16) {
@@ -786,10 +793,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
                     }
                 }
             }
-            for (int n = tid; n < Npad; n += kTcEpiThreads) {
+            for (int n = tid; n < Npad; n += kEpi) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += bsum[w * Npad + n];
+                for (int w = 0; w < EW; ++w) s += bsum[w * Npad + n];
                 atomicAdd(a.db3acc + ((size_t)bt * a.n_hg + g) * Npad + n, s);
             }
         }
@@ -800,6 +807,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_bwd_kernel(const __gri
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-static inline size_t tc_bwd_smem_bytes(int Npad, int CpB) { return 1024 + tc_bwd_layout(Npad, CpB).total; }
+static inline size_t tc_bwd_smem_bytes(int Npad, int CpB, int EW) { return 1024 + tc_bwd_layout(Npad, CpB, EW).total; }
 
 }  // namespace ncde

@@ -89,6 +89,7 @@ struct Plan {
     int tc_hid;               // hidden layers on the tensor cores too (fixed-grid bf16 path): bf16 row-major activation records
     size_t abl_off[NCDE_MAX_LAYERS + 1];   // tc_hid: record offset (floats) of the bf16 [Bp][128] input of layer l
     size_t off_Wh, off_bh;    // tc_hid: packed bf16 hidden weights [F][128][128], fp32 biases [F][128]
+    int bwd_ew;               // epilogue warps of the tensor-core backward kernel (8 or 16)
     int tc, Npad, KP, CpB;    // tensor-core path: columns per h-group padded to 16, K padded to 128; dX row pitch in smem
     int R, n_rt;
     int n_stages;
@@ -187,6 +188,10 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
         // tensor-core tiling: h-group columns padded to a multiple of 16 (UMMA N), K padded to 64 (one swizzle block)
         // K is padded to 128 so that the weight-gradient MMA (M = K) always runs the M = 128 shape
         pl->KP = kTcKP;
+        {
+            static const char* ew = getenv("NCDE_BWD_EW");
+            pl->bwd_ew = (ew && atoi(ew) == 16) ? 16 : 8;   // measured: 16 epilogue warps are 10 % slower (40.6 vs 36.8 us per launch, cfg 5)
+        }
         pl->DFP = pl->KP;  // gradient buffers share the padded K
         pl->CpB = pl->Cp + (((pl->Cp / 4) & 1) ? 0 : 4);   // CpB / 4 odd: per-row LDS.128 of consecutive lanes hit distinct banks
         double best = -1.0;
@@ -198,7 +203,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
                 if (hg > pl->H) continue;
                 const int npad = (int)round_up(hg * pl->Cp, 16);
                 if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
-                if (tc_bwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
+                if (tc_bwd_smem_bytes(npad, pl->CpB, pl->bwd_ew) > kSmemLimit) continue;
                 if (tc_fwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
                 const int n_hg = (int)ceil_div(pl->H, hg);
                 int n_bt = kNumSMs / n_hg;
@@ -217,7 +222,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
         NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve: no tensor-core tiling fits (C=%d, width=%d)", p->C, pl->DF);
         pl->TM = 8;
         pl->fwd_smem = tc_fwd_smem_bytes(pl->Npad, pl->CpB);
-        pl->bwd_smem = tc_bwd_smem_bytes(pl->Npad, pl->CpB);
+        pl->bwd_smem = tc_bwd_smem_bytes(pl->Npad, pl->CpB, pl->bwd_ew);
     }
     pl->Np = pl->n_hg * pl->Npad;
     if (getenv("NCDE_DEBUG_PLAN"))
@@ -472,7 +477,10 @@ static int build_hidden_maps(const Plan& pl, const float* wpack, TcHiddenMaps* h
 static int launch_tc_bwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cudaStream_t st) {
     int rc = tc_records(ta, ms);
     if (rc != NCDE_OK) return rc;
-    NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel, dim3(pl.n_hg, pl.n_bt), dim3(kTcThreads), pl.bwd_smem, st, ta, ms.maps));
+    if (pl.bwd_ew == 16)
+        NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel<16>, dim3(pl.n_hg, pl.n_bt), dim3(16 * 32 + 32), pl.bwd_smem, st, ta, ms.maps));
+    else
+        NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel<8>, dim3(pl.n_hg, pl.n_bt), dim3(8 * 32 + 32), pl.bwd_smem, st, ta, ms.maps));
     return NCDE_OK;
 }
 
@@ -771,7 +779,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;
-    if (use_tc) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem);
+    if (use_tc) rc = (pl.bwd_ew == 16 ? opt_in_smem(tc_field_bwd_kernel<16>, pl.bwd_smem) : opt_in_smem(tc_field_bwd_kernel<8>, pl.bwd_smem));
     else if (pl.TM == 8) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem);
     else rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
     if (rc != NCDE_OK) return rc;
@@ -1292,7 +1300,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;
-    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem); }
+    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = (pl.bwd_ew == 16 ? opt_in_smem(tc_field_bwd_kernel<16>, pl.bwd_smem) : opt_in_smem(tc_field_bwd_kernel<8>, pl.bwd_smem)); }
     else if (pl.TM == 8) { rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); }
     else { rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem); }
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
@@ -1565,7 +1573,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;
-    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(tc_field_bwd_kernel, pl.bwd_smem); }
+    if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = (pl.bwd_ew == 16 ? opt_in_smem(tc_field_bwd_kernel<16>, pl.bwd_smem) : opt_in_smem(tc_field_bwd_kernel<8>, pl.bwd_smem)); }
     else if (pl.TM == 8) { rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); }
     else { rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem); }
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);

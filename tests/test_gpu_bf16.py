@@ -1,10 +1,11 @@
 """The tensor-core path (options={'precision': 'bf16'}: bf16 operand tiles, fp32 accumulate, fp32 state) against
 the oracle / the fp32 product path.  Stated bound (BASELINE.json north_star allows "a stated looser bound for
 TF32/bf16 MLP tiles"), relative max-norm:
-    short sequences (<= 11 knots):  hidden states 3e-3,  gradients 6e-2
+    short sequences (<= 11 knots):  hidden states 3e-3,  gradients 8e-2
     cfg-5 length (143 knots, 568 chained stages):  hidden states 1e-2,  gradients 1.5e-1
-bf16 rounds the final-layer operands to 8 mantissa bits (2^-9 relative), so the pre-activation of every vector-field
-evaluation carries ~1e-2 absolute error; nothing else in the path is reduced precision."""
+Every GEMM of the vector-field MLP (hidden layers and the final layer, forward and backward) takes bf16 operands —
+8 mantissa bits, 2^-9 relative rounding — so the pre-activation of every vector-field evaluation carries ~1e-2 absolute
+error; accumulation, the RK state, the path derivative and the parameter-gradient accumulators stay fp32."""
 import copy
 
 import pytest
@@ -22,7 +23,9 @@ def rel(a, b):
 
 # (1100, ...) and (700, ...): several 128-row tiles per CTA, so the double-buffered tile pipeline wraps around
 CASES = [(1100, 3, 100, 128, 128, 3), (700, 3, 30, 16, 64, 2), (130, 4, 100, 128, 128, 3), (300, 6, 100, 128, 128, 3), (64, 5, 4, 64, 64, 3), (200, 5, 21, 64, 64, 2),
-         (96, 4, 14, 32, 128, 1), (33, 3, 2, 32, 128, 0)]
+         (96, 4, 14, 32, 128, 1), (33, 3, 2, 32, 128, 0),
+         # 128 channels (unpadded dX/dt pitch, one hidden row per group); 4-layer field (3 hidden GEMMs chained in one kernel)
+         (200, 4, 128, 32, 64, 2), (150, 4, 10, 24, 48, 4)]
 
 
 @pytest.mark.parametrize("B,L,C,H,HH,n", CASES)
@@ -52,10 +55,41 @@ def test_bf16_short_sequences_against_oracle(B, L, C, H, HH, n):
     (out * w.cuda()).sum().backward()
     assert torch.isfinite(out).all()
     assert rel(out, oref) <= 3e-3
-    assert rel(z0d.grad, z0r.grad) <= 6e-2
+    assert rel(z0d.grad, z0r.grad) <= 8e-2
     for k, p in fd.named_parameters():
         assert torch.isfinite(p.grad).all(), k
-        assert rel(p.grad, gref[k]) <= 6e-2, k
+        assert rel(p.grad, gref[k]) <= 8e-2, k
+
+
+def test_bf16_euler_against_oracle():
+    """Euler on the all-tensor-core path (one stage per step: the next stage input always comes from `advance`)."""
+    import torchcde_b200 as tc
+    g = torch.Generator().manual_seed(11)
+    B, L, C, H, HH, n = 300, 6, 21, 64, 64, 2
+    x = torch.randn(B, L, C, generator=g)
+    x[..., 0] = torch.arange(L, dtype=torch.float32)
+    x[..., 1:] = x[..., 1:].cumsum(-2) * 0.2
+    torch.manual_seed(5)
+    func = O.SharedMLPField(C, H, HH, n)
+    z0 = torch.randn(B, H, generator=g) * 0.5
+    cref = O.natural_cubic_coeffs(x)
+    Xr = O.CubicPath(cref)
+    w = torch.randn(B, L, H, generator=g)
+    z0r = z0.clone().requires_grad_(True)
+    oref = O.cdeint(Xr, func, z0r, Xr.grid_points, adjoint=False, method="euler", options={"step_size": 0.5})
+    (oref * w).sum().backward()
+    gref = {k: p.grad.clone() for k, p in func.named_parameters()}
+    fd = copy.deepcopy(func).cuda()
+    for p in fd.parameters():
+        p.grad = None
+    X = tc.NaturalCubicSpline(cref.cuda())
+    z0d = z0.cuda().requires_grad_(True)
+    out = tc.cdeint(X, fd, z0d, X.grid_points, adjoint=False, method="euler", options={"step_size": 0.5, "precision": "bf16"})
+    (out * w.cuda()).sum().backward()
+    assert rel(out, oref) <= 3e-3
+    assert rel(z0d.grad, z0r.grad) <= 8e-2
+    for k, p in fd.named_parameters():
+        assert rel(p.grad, gref[k]) <= 8e-2, k
 
 
 def test_bf16_full_length_against_fp32_path():
