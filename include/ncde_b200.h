@@ -94,6 +94,15 @@ int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, 
                    int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv, void* out,
                    int64_t* index_out, void* stream);
 
+/* Log-ODE transform, depth 1 or 2: log-signatures of the piecewise-linear path x (n_series, Lp, d) over W windows
+ * (window w = rows idx[w]..idx[w+1], idx a device int32[W+1]), cumulatively summed, with the first row set to x[:,0,:] padded
+ * with zeros -> out (n_series, W+1, d + d(d-1)/2).  Channel order as Signatory's "words" mode.  wscale (device, W values of
+ * the same dtype, nullable) scales each window first.  Replaces the signatory.Logsignature / stack / cumsum part of
+ * torchcde.log_ode._logsignature_windows (modules/torchcde/torchcde/log_ode.py:49-70); the windowing and the linear fill
+ * (:15-47) stay on the host side / go through ncde_linear_fill_missing. */
+int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx, const void* wscale, void* out, int64_t n_series,
+                        int64_t Lp, int d, int depth, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * The solve: z_t = z_0 + int f_theta(z_s) dX_s, replacing torchcde.cdeint -> torchdiffeq.odeint[_adjoint]
  * (modules/torchcde/torchcde/solver.py:102-238; modules/torchdiffeq/torchdiffeq/_impl/solvers.py:48-119,

@@ -345,6 +345,71 @@ extern "C" int ncde_path_eval(int kind, int dtype, const void* coeffs, const voi
     return NCDE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Depth-<=2 log-signatures over windows of a piecewise-linear path, cumulatively summed (log-ODE transform).
+// Replaces the signatory.Logsignature(depth) + stack + cumsum part of torchcde.log_ode._logsignature_windows
+// (modules/torchcde/torchcde/log_ode.py:49-70).  x is the filled path (n_series, Lp, d); window w covers rows
+// idx[w] .. idx[w+1] inclusive.  Output row 0 is the "first increment" x[:, 0, :] padded with zeros (:53-55), row w+1 the
+// running sum of the window log-signatures.  Channel order = Signatory's default "words" mode: the d increments, then the
+// Levy areas of the Lyndon words (i, j), i < j, in lexicographic order:
+//     A_ij = 1/2 sum_k [ (x_k - x_0)_i (x_{k+1} - x_k)_j - (x_k - x_0)_j (x_{k+1} - x_k)_i ]
+// One thread per (series, output channel) walks the windows in order, so the cumulative sum needs no second pass.
+// wscale (device, W entries, nullable) multiplies each window's log-signature before the sum (_version 0: window duration).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void logsig_windows_kernel(const T* __restrict__ x, const int32_t* __restrict__ idx, const T* __restrict__ wscale,
+                                      T* __restrict__ out, int64_t n_series, int64_t Lp, int d, int depth, int W) {
+    const int ch = depth >= 2 ? d + d * (d - 1) / 2 : d;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * ch) return;
+    const int64_t s = tid / ch;
+    const int c = (int)(tid % ch);
+    const T* xs = x + s * Lp * d;
+    T* os = out + s * (int64_t)(W + 1) * ch;
+    int i = c, j = -1;
+    if (c >= d) {   // Lyndon word (i, j): c - d = i (2d - i - 1) / 2 + (j - i - 1)
+        int r = c - d;
+        i = 0;
+        while (r >= d - 1 - i) { r -= d - 1 - i; ++i; }
+        j = i + 1 + r;
+    }
+    T run = j < 0 ? xs[i] : (T)0;
+    os[c] = run;
+    for (int w = 0; w < W; ++w) {
+        const int lo = idx[w], hi = idx[w + 1];
+        T v;
+        if (j < 0) {
+            v = xs[(int64_t)hi * d + i] - xs[(int64_t)lo * d + i];
+        } else {
+            const T x0i = xs[(int64_t)lo * d + i], x0j = xs[(int64_t)lo * d + j];
+            T acc = 0;
+            T pi = x0i, pj = x0j;
+            for (int k = lo; k < hi; ++k) {
+                const T ni = xs[(int64_t)(k + 1) * d + i], nj = xs[(int64_t)(k + 1) * d + j];
+                acc += (pi - x0i) * (nj - pj) - (pj - x0j) * (ni - pi);
+                pi = ni; pj = nj;
+            }
+            v = (T)0.5 * acc;
+        }
+        if (wscale) v *= wscale[w];
+        run += v;
+        os[(int64_t)(w + 1) * ch + c] = run;
+    }
+}
+
+extern "C" int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx, const void* wscale, void* out, int64_t n_series,
+                                   int64_t Lp, int d, int depth, int W, void* stream) {
+    NCDE_REQUIRE(x && idx && out && Lp >= 1 && d >= 1 && W >= 0, NCDE_ERR_INVALID, "logsig_windows: bad arguments");
+    NCDE_REQUIRE(depth == 1 || depth == 2, NCDE_ERR_UNSUPPORTED, "logsig_windows: depth %d is not implemented (1 and 2 are)", depth);
+    if (n_series == 0) return NCDE_OK;
+    const int ch = depth >= 2 ? d + d * (d - 1) / 2 : d;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (logsig_windows_kernel<T><<<grid_for(n_series * ch, 128), 128, 0, st>>>(
+                              (const T*)x, idx, (const T*)wscale, (T*)out, n_series, Lp, d, depth, W)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
 extern "C" size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t L, int64_t C) {
     size_t el = dtype == NCDE_F64 ? 8 : 4;
     size_t n = (size_t)n_series * (size_t)C * (size_t)L;

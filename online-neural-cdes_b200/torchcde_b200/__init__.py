@@ -12,6 +12,7 @@ from .interpolation_base import InterpolationBase
 from .interpolation_cubic import (natural_cubic_spline_coeffs, natural_cubic_coeffs, NaturalCubicSpline,
                                   CubicSpline)
 from .interpolation_linear import linear_interpolation_coeffs, LinearInterpolation
+from .log_ode import logsig_windows, logsignature_windows, logsignature_channels
 from .misc import TupleControl, forward_fill
 from .solver import cdeint
 from . import distributed  # noqa: F401
