@@ -46,6 +46,7 @@ struct TcFieldArgs {
     // backward of the all-tensor-core path: dL/dk of this stage is formed on the fly from the gradient of the step result and
     // the stage-input gradients of the LATER stages (rk_common.py:106-114 transposed), so no gk arrays are read-modify-written:
     //     gk[b,h] = gcoef * gy1[b,h] + sum_q dzcoef[q] * dz_q[b,h]
+    int p_transposed;          // P is written as P^T[g][k][b] (coalesced; consumed by p_reduce) instead of [g][b][k]
     const float* gy1T;         // [H][Bp] or null (then gkT is read)
     float gcoef;
     int n_dz;
@@ -304,23 +305,38 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_sa
     }
 }
 
-// sum_j tanh(D[row][col0 + j] + b3[j]) * dX[row][j] over W consecutive channels.  b3_s / dx_s are shared-memory byte
-// addresses (16-byte aligned); both are read as LDS.128 while the TMEM load is in flight.
+// One W-column chunk of an epilogue for TMEM lane `row`: the accumulator values (tcgen05.ld in flight until
+// tmem_wait_ld), the biases and this row's dX/dt (both LDS.128 from 16-byte aligned shared addresses).  Chunks are software
+// pipelined: wait for chunk j, issue chunk j+1, then compute chunk j — tcgen05.wait::ld waits for every outstanding load of
+// the thread, so the next load is issued right after the wait and flies during the arithmetic.
 template <int W>
-__device__ __forceinline__ float fwd_chunk(uint32_t taddr, uint32_t b3_s, uint32_t dx_s) {
+struct TcChunk {
     uint32_t r[W];
-    tmem_ldw_issue<W>(taddr, r);
+    uint32_t b3_s, dx_s;   // shared-memory addresses of the chunk's biases and dX/dt values (read right before use: only the
+                           // TMEM registers are double-buffered, 2 x 32 of the 168 the launch bounds allow)
+};
+// chunk j (32 columns) of the unit that starts at column colbase + c_begin of this row; expects lane_addr, colbase, c_begin,
+// b3_s and dx_s in scope (a macro, not a lambda: a lambda taking the chunk by reference pushes it to local memory)
+#define issue32(k, j) chunk_issue<32>(k, lane_addr + (uint32_t)(colbase + c_begin + 32 * (j)), b3_s + 4u * (colbase + c_begin + 32 * (j)), \
+                                      dx_s + 4u * (c_begin + 32 * (j)))
+template <int W>
+__device__ __forceinline__ void chunk_issue(TcChunk<W>& k, uint32_t taddr, uint32_t b3_s, uint32_t dx_s) {
+    tmem_ldw_issue<W>(taddr, k.r);
+    k.b3_s = b3_s; k.dx_s = dx_s;
+}
+// sum_j tanh(D[row][col0 + j] + b3[j]) * dX[row][j] over the chunk (after tmem_wait_ld)
+template <int W>
+__device__ __forceinline__ float fwd_finish(const TcChunk<W>& k) {
     float4 bb[W / 4], dd[W / 4];
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(b3_s + 16u * q); dd[q] = lds128(dx_s + 16u * q); }
-    tmem_wait_ld<W>(r);
+    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(k.b3_s + 16u * q); dd[q] = lds128(k.dx_s + 16u * q); }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
-        acc0 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 0]) + bb[q].x), dd[q].x, acc0);
-        acc1 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 1]) + bb[q].y), dd[q].y, acc1);
-        acc2 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 2]) + bb[q].z), dd[q].z, acc2);
-        acc3 = fmaf(tanh_fast(__uint_as_float(r[4 * q + 3]) + bb[q].w), dd[q].w, acc3);
+        acc0 = fmaf(tanh_fast(__uint_as_float(k.r[4 * q + 0]) + bb[q].x), dd[q].x, acc0);
+        acc1 = fmaf(tanh_fast(__uint_as_float(k.r[4 * q + 1]) + bb[q].y), dd[q].y, acc1);
+        acc2 = fmaf(tanh_fast(__uint_as_float(k.r[4 * q + 2]) + bb[q].z), dd[q].z, acc2);
+        acc3 = fmaf(tanh_fast(__uint_as_float(k.r[4 * q + 3]) + bb[q].w), dd[q].w, acc3);
     }
     return (acc0 + acc1) + (acc2 + acc3);
 }
@@ -456,9 +472,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
             for (int hl = h_begin; hl < h_end; ++hl) {
                 float acc = 0.f;
                 const int colbase = hl * a.Cp;
-                int c0 = c_begin;
-                for (; c0 + 32 <= c_end; c0 += 32) acc += fwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
-                for (; c0 + 8 <= c_end; c0 += 8) acc += fwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
+                const int n32 = (c_end - c_begin) / 32;
+                {
+                    TcChunk<32> A, Bk;
+                    if (n32 > 0) issue32(A, 0);
+                    for (int j = 0; j < n32; j += 2) {
+                        tmem_wait_ld<32>(A.r);
+                        if (j + 1 < n32) issue32(Bk, j + 1);
+                        acc += fwd_finish<32>(A);
+                        if (j + 1 < n32) {
+                            tmem_wait_ld<32>(Bk.r);
+                            if (j + 2 < n32) issue32(A, j + 2);
+                            acc += fwd_finish<32>(Bk);
+                        }
+                    }
+                }
+                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
+                    TcChunk<8> T;
+                    chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
+                    tmem_wait_ld<8>(T.r);
+                    acc += fwd_finish<8>(T);
+                }
                 if (a.Hg >= 2) {
                     const int h = g * a.Hg + hl;
                     if (h < a.H && b0 + row < a.B) {
@@ -511,24 +545,19 @@ static inline size_t tc_fwd_smem_bytes(int Npad, int CpB) { return 1024 + tc_fwd
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kTcDwCol = 256;
 
-// One W-column chunk of epilogue 1 for TMEM lane `row`: G = gk * dX * sech^2(pre + b3) -> bf16 into the swizzled G
-// tile (16-byte stores, n0 is a multiple of 8).
+// One W-column chunk of epilogue 1 for TMEM lane `row` (after tmem_wait_ld): G = gk * dX * sech^2(pre + b3) -> bf16 into the
+// swizzled G tile (16-byte stores, n0 is a multiple of 8).
 template <int W>
-__device__ __forceinline__ void bwd_chunk(uint32_t taddr, uint32_t b3_s, uint32_t dx_s, float gk, uint32_t gs_s, int row, int n0) {
-    uint32_t r[W];
-    tmem_ldw_issue<W>(taddr, r);
-    float4 bb[W / 4], dd[W / 4];
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(b3_s + 16u * q); dd[q] = lds128(dx_s + 16u * q); }
-    tmem_wait_ld<W>(r);
+__device__ __forceinline__ void bwd_finish(const TcChunk<W>& k, float gk, uint32_t gs_s, int row, int n0) {
     float v[W];
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
+        const float4 bb = lds128(k.b3_s + 16u * q), dd = lds128(k.dx_s + 16u * q);
         // gk is zero for padded rows and dX/dt rows beyond the batch are zero-filled by TMA: no NaN can enter the G tile
-        v[4 * q + 0] = gk * dd[q].x * sech2_fast(__uint_as_float(r[4 * q + 0]) + bb[q].x);
-        v[4 * q + 1] = gk * dd[q].y * sech2_fast(__uint_as_float(r[4 * q + 1]) + bb[q].y);
-        v[4 * q + 2] = gk * dd[q].z * sech2_fast(__uint_as_float(r[4 * q + 2]) + bb[q].z);
-        v[4 * q + 3] = gk * dd[q].w * sech2_fast(__uint_as_float(r[4 * q + 3]) + bb[q].w);
+        v[4 * q + 0] = gk * dd.x * sech2_fast(__uint_as_float(k.r[4 * q + 0]) + bb.x);
+        v[4 * q + 1] = gk * dd.y * sech2_fast(__uint_as_float(k.r[4 * q + 1]) + bb.y);
+        v[4 * q + 2] = gk * dd.z * sech2_fast(__uint_as_float(k.r[4 * q + 2]) + bb.z);
+        v[4 * q + 3] = gk * dd.w * sech2_fast(__uint_as_float(k.r[4 * q + 3]) + bb.w);
     }
 #pragma unroll
     for (int j8 = 0; j8 < W / 8; ++j8) {
@@ -724,11 +753,27 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
                     }
                 }
                 const int colbase = hl * a.Cp;
-                int c0 = c_begin;
-                for (; c0 + 32 <= c_end; c0 += 32)
-                    bwd_chunk<32>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0, gk, gs_s, row, colbase + c0);
-                for (; c0 + 8 <= c_end; c0 += 8)
-                    bwd_chunk<8>(lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0, gk, gs_s, row, colbase + c0);
+                const int n32 = (c_end - c_begin) / 32;
+                {
+                    TcChunk<32> A, Bk;
+                    if (n32 > 0) issue32(A, 0);
+                    for (int j = 0; j < n32; j += 2) {
+                        tmem_wait_ld<32>(A.r);
+                        if (j + 1 < n32) issue32(Bk, j + 1);
+                        bwd_finish<32>(A, gk, gs_s, row, colbase + c_begin + 32 * j);
+                        if (j + 1 < n32) {
+                            tmem_wait_ld<32>(Bk.r);
+                            if (j + 2 < n32) issue32(A, j + 2);
+                            bwd_finish<32>(Bk, gk, gs_s, row, colbase + c_begin + 32 * (j + 1));
+                        }
+                    }
+                }
+                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
+                    TcChunk<8> T;
+                    chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dx_s + 4u * c0);
+                    tmem_wait_ld<8>(T.r);
+                    bwd_finish<8>(T, gk, gs_s, row, colbase + c0);
+                }
             }
             fence_async_smem();     // generic-proxy writes of G (and reads of dX/dt) before the async-proxy MMA / TMA
             tc_fence_before();
@@ -754,15 +799,35 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
             tc_fence_after();
             // ---- epilogue 2: partial input gradient of this h-group ----
             {
-                const int kb = cg * (KP / kCg), ke = kb + KP / kCg;
-                float* prow = a.P + ((size_t)g * a.B + (size_t)b) * a.DFP;
-                for (int k0 = kb; k0 < ke; k0 += 16) {
-                    float v[16];
-                    tmem_ld16(lane_addr + (uint32_t)k0, v);
+                const int kb = cg * (KP / kCg), ke = kb + KP / kCg;      // 64 (8 warps) or 32 (16 warps) columns
+                if (a.p_transposed) {
+                    // P^T[g][k][b]: the 32 lanes of a warp (= consecutive rows) write 128 contiguous bytes per column
+                    float* pcol = a.P + ((size_t)g * 128 + kb) * a.B + (size_t)b;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32_issue(lane_addr + (uint32_t)kb, r0);
+                    tmem_wait_ld<32>(r0);
+                    if (ke - kb > 32) tmem_ld32_issue(lane_addr + (uint32_t)kb + 32u, r1);
                     if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(prow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; ++j) pcol[(size_t)j * a.B] = __uint_as_float(r0[j]);
+                    }
+                    if (ke - kb > 32) {
+                        tmem_wait_ld<32>(r1);
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) pcol[(size_t)(32 + j) * a.B] = __uint_as_float(r1[j]);
+                        }
+                    }
+                } else {
+                    float* prow = a.P + ((size_t)g * a.B + (size_t)b) * a.DFP;
+                    for (int k0 = kb; k0 < ke; k0 += 16) {
+                        float v[16];
+                        tmem_ld16(lane_addr + (uint32_t)k0, v);
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(prow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
                     }
                 }
             }

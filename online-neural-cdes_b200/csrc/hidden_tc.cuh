@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_fwd_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------------
 // Backward of the hidden layers.
 //
-// p_reduce: dL/d(a_F) = sum over the h-groups of the final-layer kernel's partials P[g][b][k], times act'(a_F), rounded to
+// p_reduce: dL/d(a_F) = sum over the h-groups of the final-layer kernel's partials P^T[g][k][b], times act'(a_F), rounded to
 // a bf16 row-major record — the first operand tile of the tensor-core chain.  Batch-split over every SM (the 64-way sum is
 // 33 MB of L2 reads per stage: this part must not sit on 8 SMs).
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,36 +224,55 @@ __device__ __forceinline__ float act_grad_bf(float out, int act) {
 
 struct PReduceArgs {
     int B, n_hg, DFP, act;         // act: activation of the last hidden layer
-    const float* P;                // [n_hg][B][DFP], DFP == 128
+    const float* P;                // P^T [n_hg][128 k][B]
     const __nv_bfloat16* aF;       // [Bp][128] output of the last hidden layer (saved record)
     __nv_bfloat16* dpre;           // [Bp][128]
 };
 
+// CTA (x, y) = 128 rows x 8 columns: thread = (column = warp, 4 consecutive rows = lane), so every load is a float4 and a warp
+// reads 512 contiguous bytes of P^T[g][k][.]; the 64 groups are summed in registers, the 128 x 8 tile is transposed through
+// shared memory and leaves as one 16-byte bf16 store per row.
 __global__ void __launch_bounds__(256) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
+    __shared__ float tile[128][9];
     pdl_trigger();
     pdl_wait();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, float4 of k)
-    const int64_t b = idx >> 5;
-    const int k4 = (int)(idx & 31);
-    if (b >= a.B) return;
-    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)b * 128) + k4;
-    const size_t gs = (size_t)a.B * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * 128;
+    const int k0 = blockIdx.y * 8;
+    const int64_t bq = b0 + lane * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bq + 3 < a.B) {
+        const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)(k0 + warp) * a.B + bq);
+        const size_t gs = (size_t)128 * a.B / 4;
 #pragma unroll 16
-    for (int g = 0; g < a.n_hg; ++g) {
-        const float4 v = __ldg(p + (size_t)g * gs);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        for (int g = 0; g < a.n_hg; ++g) {
+            const float4 v = __ldg(p + (size_t)g * gs);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    } else {
+        for (int r = 0; r < 4; ++r) {
+            if (bq + r >= a.B) break;
+            float acc = 0.f;
+            for (int g = 0; g < a.n_hg; ++g) acc += __ldg(a.P + ((size_t)g * 128 + k0 + warp) * a.B + bq + r);
+            (&s.x)[r] = acc;
+        }
     }
-    const uint2 ab = *reinterpret_cast<const uint2*>(a.aF + (size_t)b * 128 + k4 * 4);
-    const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ab.x));
-    const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ab.y));
-    s.x *= act_grad_bf(a01.x, a.act); s.y *= act_grad_bf(a01.y, a.act);
-    s.z *= act_grad_bf(a23.x, a.act); s.w *= act_grad_bf(a23.y, a.act);
-    __nv_bfloat162 o01 = __floats2bfloat162_rn(s.x, s.y), o23 = __floats2bfloat162_rn(s.z, s.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&o01);
-    o.y = *reinterpret_cast<uint32_t*>(&o23);
-    *reinterpret_cast<uint2*>(a.dpre + (size_t)b * 128 + k4 * 4) = o;
+    tile[lane * 4 + 0][warp] = s.x; tile[lane * 4 + 1][warp] = s.y; tile[lane * 4 + 2][warp] = s.z; tile[lane * 4 + 3][warp] = s.w;
+    __syncthreads();
+    if (threadIdx.x < 128 && b0 + threadIdx.x < a.B) {
+        const int64_t b = b0 + threadIdx.x;
+        const uint4 av = *reinterpret_cast<const uint4*>(a.aF + (size_t)b * 128 + k0);
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(tile[threadIdx.x][2 * j] * act_grad_bf(a2.x, a.act),
+                                                      tile[threadIdx.x][2 * j + 1] * act_grad_bf(a2.y, a.act));
+            o[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(a.dpre + (size_t)b * 128 + k0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -912,6 +912,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     if (tc_hid) {
                         // dL/dk_i = c_i dt gy1 + sum over later stages q of d(stage input q)/dk_i * dz_q; the dz_q live in gkT[q]
                         ta.gy1T = gyT;
+                        ta.p_transposed = 1;
                         ta.n_dz = 0;
                         if (p->method == NCDE_RK4_38) {
                             ta.gcoef = (i == 0 || i == 3) ? dt * 0.125f : 3.f * (dt * 0.125f);
@@ -945,7 +946,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             if (tc_hid) {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 pr.aF = (const __nv_bfloat16*)(stage + pl.abl_off[pl.F]);
-                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div((int64_t)pl.B * 32, 256)), dim3(256), 0, st, pr));
+                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(256), 0, st, pr));
                 thb.rec = (int)(s * NS + i);
                 thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
                 NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads), tc_hid_bwd_smem_bytes(),
