@@ -352,7 +352,8 @@ def main():
                     "ms_per_step": float(te.item()) * 1e3, "loss": loss_value},
             "gpu_launches": gpu_launches,
             "clocks": clocks,
-            "roofline": {"kernel": "field_bwd_kernel (final-layer dgrad+wgrad, one RK stage)", "bound": "tensor",
+            "roofline": {"kernel": ("tc_field_bwd_kernel<8>" if args.precision == "bf16" else "field_bwd_kernel") +
+                                   " (final-layer recompute + dgrad + wgrad of one RK stage)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tensor_tflops"]) if achieved else None, "traffic": traffic,
                          "peak_source": peaks["source"], "flops_per_launch": flops_bwd,
