@@ -46,6 +46,9 @@ struct TcFieldArgs {
     // backward of the all-tensor-core path: dL/dk of this stage is formed on the fly from the gradient of the step result and
     // the stage-input gradients of the LATER stages (rk_common.py:106-114 transposed), so no gk arrays are read-modify-written:
     //     gk[b,h] = gcoef * gy1[b,h] + sum_q dzcoef[q] * dz_q[b,h]
+    int prefetch;              // fixed-grid solves: the saved records this launch reads (dX/dt; in the backward pass also the
+                               // activations) are older than the predecessor kernel, so their first tiles — and in the backward
+                               // kernel the first recompute MMA — are issued ahead of griddepcontrol.wait, under the predecessor
     int p_transposed;          // P is written as P^T[g][k][b] (coalesced; consumed by p_reduce) instead of [g][b][k]
     const float* gy1T;         // [H][Bp] or null (then gkT is read)
     float gcoef;
@@ -329,7 +332,9 @@ template <int W>
 __device__ __forceinline__ float fwd_finish(const TcChunk<W>& k) {
     float4 bb[W / 4], dd[W / 4];
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) { bb[q] = lds128(k.b3_s + 16u * q); dd[q] = lds128(k.dx_s + 16u * q); }
+    for (int q = 0; q < W / 4; ++q) {
+        bb[q] = lds128(k.b3_s + 16u * q); dd[q] = lds128(k.dx_s + 16u * q);
+    }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
@@ -412,10 +417,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
         tma_load_3d(Ws, &maps.W, w_bar, 0, g * Npad, 0);
         tma_load_3d(Ws + (size_t)Npad * 128, &maps.W, w_bar, 64, g * Npad, 0);
     }
+    const int64_t row_begin = (int64_t)bt * a.Bt;
+    const bool pre = a.prefetch != 0 && a.ctrl == nullptr;
+    if (producer && pre) {
+        // dX/dt of the first two tiles: written by dx_all before the stage loop began
+        for (int i = 0; i < 2; ++i) {
+            const int64_t b0 = row_begin + (int64_t)i * kTcM;
+            if (b0 < a.B && b0 < row_begin + a.Bt) {
+                mbar_expect_tx(full_x + i, x_bytes);
+                tma_load_3d(dXs + (size_t)i * x_bytes, &maps.X, full_x + i, 0, (int)b0, a.rec_x);
+            }
+        }
+    }
     pdl_trigger();
     pdl_wait();  // the activation tiles come from hidden_fwd
 
-    const int64_t row_begin = (int64_t)bt * a.Bt;
     int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
     if (a.ctrl && a.ctrl->done) row_end = row_begin;
     const int nt = row_end > row_begin ? (int)((row_end - row_begin + kTcM - 1) / kTcM) : 0;
@@ -428,6 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
                 mbar_expect_tx(full_a + b, a_bytes);
                 tma_load_3d(As + (size_t)b * a_bytes, &maps.A, full_a + b, 0, b0, a.rec_a);
                 tma_load_3d(As + (size_t)b * a_bytes + a_bytes / 2, &maps.A, full_a + b, 64, b0, a.rec_a);
+                if (pre && i < 2) return;   // already in flight
                 mbar_expect_tx(full_x + b, x_bytes);
                 tma_load_3d(dXs + (size_t)b * x_bytes, &maps.X, full_x + b, 0, b0, a.rec_x);
             };
@@ -647,10 +664,24 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
         tma_load_3d(Ws, &maps.W, w_bar, 0, g * Npad, 0);
         tma_load_3d(Ws + (size_t)Npad * 128, &maps.W, w_bar, 64, g * Npad, 0);
     }
+    const int64_t row_begin = (int64_t)bt * a.Bt;
+    const bool pre = a.prefetch != 0 && a.ctrl == nullptr && row_begin < a.B;
+    if (producer && pre) {
+        // first tile: activations and dX/dt are saved records of the forward pass, the recompute MMA needs nothing else
+        mbar_expect_tx(full_a, a_bytes);
+        tma_load_3d(As, &maps.A, full_a, 0, (int)row_begin, a.rec_a);
+        tma_load_3d(As + a_bytes / 2, &maps.A, full_a, 64, (int)row_begin, a.rec_a);
+        mbar_expect_tx(full_x, x_bytes);
+        tma_load_3d(dXs, &maps.X, full_x, 0, (int)row_begin, a.rec_x);
+        mbar_wait(w_bar, 0);
+        mbar_wait(full_a, 0);
+        tc_fence_after();
+        issue_gemm_kmajor(tmem_base, smem_u32(As), kTcM, smem_u32(Ws), Npad, Npad, KP, false);
+        umma_commit(pre_bar);
+    }
     pdl_trigger();
     pdl_wait();  // gk comes from the previous kernels
 
-    const int64_t row_begin = (int64_t)bt * a.Bt;
     int64_t row_end = min((int64_t)a.B, row_begin + a.Bt);
     if (a.ctrl && a.ctrl->done) row_end = row_begin;
     const int nt = row_end > row_begin ? (int)((row_end - row_begin + kTcM - 1) / kTcM) : 0;
@@ -667,17 +698,21 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
                 mbar_expect_tx(full_x, x_bytes);
                 tma_load_3d(dXs, &maps.X, full_x, 0, (int)(row_begin + (int64_t)i * kTcM), a.rec_x);
             };
-            load_A(0);
-            load_X(0);
-            mbar_wait(w_bar, 0);
+            if (!pre) {
+                load_A(0);
+                load_X(0);
+                mbar_wait(w_bar, 0);
+            }
             for (int i = 0; i < nt; ++i) {
                 const uint32_t ph = (uint32_t)i & 1u;
                 const uint32_t As_i = smem_u32(As);
-                mbar_wait(full_a, ph);
-                if (i > 0) mbar_wait(done2, ph ^ 1u);        // epilogue 2 of tile i-1 has read P out of the accumulator
-                tc_fence_after();
-                issue_gemm_kmajor(tmem_base, As_i, kTcM, smem_u32(Ws), Npad, Npad, KP, false);
-                umma_commit(pre_bar);
+                if (!(pre && i == 0)) {   // tile 0 of a prefetching launch was issued ahead of the dependency
+                    mbar_wait(full_a, ph);
+                    if (i > 0) mbar_wait(done2, ph ^ 1u);    // epilogue 2 of tile i-1 has read P out of the accumulator
+                    tc_fence_after();
+                    issue_gemm_kmajor(tmem_base, As_i, kTcM, smem_u32(Ws), Npad, Npad, KP, false);
+                    umma_commit(pre_bar);
+                }
                 mbar_wait(g_ready, ph);                      // G tile of tile i written by all 8 warps; dX/dt tile no longer needed
                 tc_fence_after();
                 if (i + 1 < nt) load_X(i + 1);

@@ -697,6 +697,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = dx_stage;
                     ta.koutT = kT[i];
+                    ta.prefetch = 1;   // dX/dt of every stage was written by dx_all before this loop
                     { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
@@ -909,6 +910,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     ta.abf = (const __nv_bfloat16*)(stage + pl.abf_off);
                     ta.dXT = stage + pl.dx_off;
                     ta.gkT = gkT[i];
+                    ta.prefetch = 1;   // activations and dX/dt are records saved by the forward pass
                     if (tc_hid) {
                         // dL/dk_i = c_i dt gy1 + sum over later stages q of d(stage input q)/dk_i * dz_q; the dz_q live in gkT[q]
                         ta.gy1T = gyT;
