@@ -223,8 +223,8 @@ __device__ __forceinline__ float act_grad_bf(float out, int act) {
 }
 
 struct PReduceArgs {
-    int B, n_hg, DFP, act;         // act: activation of the last hidden layer
-    const float* P;                // P^T [n_hg][128 k][B]
+    int B, Bp, n_hg, DFP, act;     // act: activation of the last hidden layer
+    const float* P;                // P^T [n_hg][128 k][Bp]
     const __nv_bfloat16* aF;       // [Bp][128] output of the last hidden layer (saved record)
     __nv_bfloat16* dpre;           // [Bp][128]
 };
@@ -239,22 +239,15 @@ __global__ void __launch_bounds__(256) p_reduce_kernel(const __grid_constant__ P
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t b0 = (int64_t)blockIdx.x * 128;
     const int k0 = blockIdx.y * 8;
-    const int64_t bq = b0 + lane * 4;
+    const int64_t bq = b0 + lane * 4;      // < Bp: the row pitch of P^T covers the padded batch, padded rows are never used
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bq + 3 < a.B) {
-        const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)(k0 + warp) * a.B + bq);
-        const size_t gs = (size_t)128 * a.B / 4;
+    if (bq < a.B) {
+        const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)(k0 + warp) * a.Bp + bq);
+        const size_t gs = (size_t)128 * a.Bp / 4;
 #pragma unroll 16
         for (int g = 0; g < a.n_hg; ++g) {
             const float4 v = __ldg(p + (size_t)g * gs);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-    } else {
-        for (int r = 0; r < 4; ++r) {
-            if (bq + r >= a.B) break;
-            float acc = 0.f;
-            for (int g = 0; g < a.n_hg; ++g) acc += __ldg(a.P + ((size_t)g * 128 + k0 + warp) * a.B + bq + r);
-            (&s.x)[r] = acc;
         }
     }
     tile[lane * 4 + 0][warp] = s.x; tile[lane * 4 + 1][warp] = s.y; tile[lane * 4 + 2][warp] = s.z; tile[lane * 4 + 3][warp] = s.w;

@@ -342,7 +342,7 @@ static size_t bwd_workspace_floats(const Plan& pl) {
     size_t per = 256 / 4;
     size_t n = pl.wpack_floats + per;
     n += (size_t)(1 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
-    n += (size_t)pl.n_hg * pl.B * pl.DFP + per;
+    n += (size_t)pl.n_hg * pl.Bp * pl.DFP + per;
     for (int l = 0; l < pl.F; ++l) n += (size_t)pl.n_stages * ((size_t)pl.Dp4[l + 1] * pl.Bp + per);
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
     n += (size_t)pl.n_bt * pl.Np + per;
@@ -765,7 +765,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     float* gyT = cv.take(nHB);
     float* gkT[NCDE_MAX_STAGES] = {};
     for (int i = 0; i < NS; ++i) gkT[i] = cv.take(nHB);
-    float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
+    float* P = cv.take((size_t)pl.n_hg * pl.Bp * pl.DFP);
     float* dpreT[NCDE_MAX_STAGES][NCDE_MAX_LAYERS] = {};
     for (int i = 0; i < NS; ++i)
         for (int l = 0; l < pl.F; ++l) dpreT[i][l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
@@ -840,7 +840,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             thb.dWacc[l] = dWh_acc + (size_t)pl.first_of_slot[l] * 128 * 128;
             thb.dbacc[l] = dbh_acc + (size_t)pl.first_of_slot[l] * 128;
         }
-        pr.B = pl.B; pr.n_hg = pl.n_hg; pr.DFP = pl.DFP; pr.act = m.act[pl.F - 1]; pr.P = P; pr.dpre = (__nv_bfloat16*)dpre_rec;
+        pr.B = pl.B; pr.Bp = pl.Bp; pr.n_hg = pl.n_hg; pr.DFP = pl.DFP; pr.act = m.act[pl.F - 1]; pr.P = P; pr.dpre = (__nv_bfloat16*)dpre_rec;
     }
     rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_wgrad_kernel, 36 * 1024);
@@ -1237,7 +1237,7 @@ static size_t adjoint_workspace_floats(const ncde_problem_t* p, const Plan& pl) 
     size_t n = pl.wpack_floats + per;
     n += (size_t)(3 + 2 * 4) * (nHB + per);            // y, a, a_stage, kf[4], ka[4]
     n += pl.stage_floats + per;
-    n += (size_t)pl.n_hg * pl.B * pl.DFP + per;
+    n += (size_t)pl.n_hg * pl.Bp * pl.DFP + per;
     for (int l = 0; l < pl.F; ++l) n += (size_t)pl.Dp4[l + 1] * pl.Bp + per;
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per + (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
@@ -1288,7 +1288,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     float* kf[4]; float* ka[4];
     for (int i = 0; i < 4; ++i) { kf[i] = cv.take(nHB); ka[i] = cv.take(nHB); }
     float* stage = cv.take(pl.stage_floats);
-    float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
+    float* P = cv.take((size_t)pl.n_hg * pl.Bp * pl.DFP);
     float* dpreT[NCDE_MAX_LAYERS] = {};
     for (int l = 0; l < pl.F; ++l) dpreT[l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
     const size_t nW3 = (size_t)pl.n_bt * pl.Np * pl.DFP, nb3 = (size_t)pl.n_bt * pl.Np;
@@ -1547,7 +1547,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     float* kf[7]; float* ka[7];
     for (int i = 0; i < 7; ++i) { kf[i] = cv.take(nHB); ka[i] = cv.take(nHB); }
     float* stage = cv.take(pl.stage_floats);
-    float* P = cv.take((size_t)pl.n_hg * pl.B * pl.DFP);
+    float* P = cv.take((size_t)pl.n_hg * pl.Bp * pl.DFP);
     float* dpreT[NCDE_MAX_LAYERS] = {};
     for (int l = 0; l < pl.F; ++l) dpreT[l] = cv.take((size_t)pl.Dp4[l + 1] * pl.Bp);
     const size_t nW3 = (size_t)pl.n_bt * pl.Np * pl.DFP, nb3 = (size_t)pl.n_bt * pl.Np;
