@@ -49,7 +49,7 @@ struct TcFieldArgs {
     int prefetch;              // fixed-grid solves: the saved records this launch reads (dX/dt; in the backward pass also the
                                // activations) are older than the predecessor kernel, so their first tiles — and in the backward
                                // kernel the first recompute MMA — are issued ahead of griddepcontrol.wait, under the predecessor
-    int p_transposed;          // P is written as P^T[g][k][Bp] (coalesced; consumed by p_reduce) instead of [g][b][k]
+    int p_transposed;          // P is written as bf16 P^T[g][k][Bp] (coalesced; consumed by p_reduce) instead of fp32 [g][b][k]
     const float* gy1T;         // [H][Bp] or null (then gkT is read)
     float gcoef;
     int n_dz;
@@ -836,21 +836,23 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
             {
                 const int kb = cg * (KP / kCg), ke = kb + KP / kCg;      // 64 (8 warps) or 32 (16 warps) columns
                 if (a.p_transposed) {
-                    // P^T[g][k][b]: the 32 lanes of a warp (= consecutive rows) write 128 contiguous bytes per column
-                    float* pcol = a.P + ((size_t)g * 128 + kb) * a.Bp + (size_t)b;   // row pitch Bp: float4-aligned for p_reduce
+                    // P^T[g][k][b] in bf16 (the consumer rounds the 64-group sum to bf16 anyway; the partials are summed in fp32):
+                    // the 32 lanes of a warp (= consecutive rows) write 64 contiguous bytes per column; row pitch Bp keeps
+                    // p_reduce's 16-byte loads aligned
+                    __nv_bfloat16* pcol = reinterpret_cast<__nv_bfloat16*>(a.P) + ((size_t)g * 128 + kb) * a.Bp + (size_t)b;
                     uint32_t r0[32], r1[32];
                     tmem_ld32_issue(lane_addr + (uint32_t)kb, r0);
                     tmem_wait_ld<32>(r0);
                     if (ke - kb > 32) tmem_ld32_issue(lane_addr + (uint32_t)kb + 32u, r1);
                     if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) pcol[(size_t)j * a.Bp] = __uint_as_float(r0[j]);
+                        for (int j = 0; j < 32; ++j) pcol[(size_t)j * a.Bp] = __float2bfloat16(__uint_as_float(r0[j]));
                     }
                     if (ke - kb > 32) {
                         tmem_wait_ld<32>(r1);
                         if (row_ok) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) pcol[(size_t)(32 + j) * a.Bp] = __uint_as_float(r1[j]);
+                            for (int j = 0; j < 32; ++j) pcol[(size_t)(32 + j) * a.Bp] = __float2bfloat16(__uint_as_float(r1[j]));
                         }
                     }
                 } else {

@@ -224,33 +224,42 @@ __device__ __forceinline__ float act_grad_bf(float out, int act) {
 
 struct PReduceArgs {
     int B, Bp, n_hg, DFP, act;     // act: activation of the last hidden layer
-    const float* P;                // P^T [n_hg][128 k][Bp]
+    const float* P;                // bf16 P^T [n_hg][128 k][Bp] (a float buffer reinterpreted)
     const __nv_bfloat16* aF;       // [Bp][128] output of the last hidden layer (saved record)
     __nv_bfloat16* dpre;           // [Bp][128]
 };
 
-// CTA (x, y) = 128 rows x 8 columns: thread = (column = warp, 4 consecutive rows = lane), so every load is a float4 and a warp
-// reads 512 contiguous bytes of P^T[g][k][.]; the 64 groups are summed in registers, the 128 x 8 tile is transposed through
-// shared memory and leaves as one 16-byte bf16 store per row.
-__global__ void __launch_bounds__(256) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
+// CTA (x, y) = 128 rows x 8 columns, 128 threads: thread = (column = tid / 16, 8 consecutive rows), so every load is 16 bytes
+// (8 bf16 partials) and a half-warp reads 256 contiguous bytes of P^T[g][k][.]; the 64 groups are summed in fp32 registers, the
+// 128 x 8 tile is transposed through shared memory and leaves as one 16-byte bf16 store per row.
+__global__ void __launch_bounds__(128) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
     __shared__ float tile[128][9];
     pdl_trigger();
     pdl_wait();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = threadIdx.x >> 4, rg = threadIdx.x & 15;
     const int64_t b0 = (int64_t)blockIdx.x * 128;
     const int k0 = blockIdx.y * 8;
-    const int64_t bq = b0 + lane * 4;      // < Bp: the row pitch of P^T covers the padded batch, padded rows are never used
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t bq = b0 + rg * 8;        // < Bp: the row pitch of P^T covers the padded batch, padded rows are never used
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
     if (bq < a.B) {
-        const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)(k0 + warp) * a.Bp + bq);
-        const size_t gs = (size_t)128 * a.Bp / 4;
+        const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.P) + (size_t)(k0 + col) * a.Bp + bq);
+        const size_t gs = (size_t)128 * a.Bp / 8;
 #pragma unroll 16
         for (int g = 0; g < a.n_hg; ++g) {
-            const float4 v = __ldg(p + (size_t)g * gs);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            const uint4 v = __ldg(p + (size_t)g * gs);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                s[2 * j] += f.x;
+                s[2 * j + 1] += f.y;
+            }
         }
     }
-    tile[lane * 4 + 0][warp] = s.x; tile[lane * 4 + 1][warp] = s.y; tile[lane * 4 + 2][warp] = s.z; tile[lane * 4 + 3][warp] = s.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[rg * 8 + j][col] = s[j];
     __syncthreads();
     if (threadIdx.x < 128 && b0 + threadIdx.x < a.B) {
         const int64_t b = b0 + threadIdx.x;

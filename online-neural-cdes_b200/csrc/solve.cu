@@ -948,7 +948,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             if (tc_hid) {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 pr.aF = (const __nv_bfloat16*)(stage + pl.abl_off[pl.F]);
-                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(256), 0, st, pr));
+                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(128), 0, st, pr));
                 thb.rec = (int)(s * NS + i);
                 thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
                 NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads), tc_hid_bwd_smem_bytes(),
