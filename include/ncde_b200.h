@@ -103,6 +103,14 @@ int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, 
 int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx, const void* wscale, void* out, int64_t n_series,
                         int64_t Lp, int d, int depth, int W, void* stream);
 
+/* Linear / rectilinear hybrid, compaction step (src/ncde/interpolation.py:224-253): `full` (n_series, K, C) is the
+ * rectilinear path of the series whose linear channels were filled beforehand; linear channels (chan_kind 0) are shifted up
+ * by one row, a row is kept only if a time / rectilinear channel (chan_kind 1) differs from the previous row, and each series is
+ * padded to K rows by repeating its last kept row.  counts (device int32[n_series]) receives the kept rows per series; the
+ * caller slices `out` to max(counts) rows (the reference's pad_sequence + forward_fill). */
+int ncde_hybrid_compact(int dtype, const void* full, const int32_t* chan_kind, void* out, int32_t* counts, int64_t n_series,
+                        int64_t K, int64_t C, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * The solve: z_t = z_0 + int f_theta(z_s) dX_s, replacing torchcde.cdeint -> torchdiffeq.odeint[_adjoint]
  * (modules/torchcde/torchcde/solver.py:102-238; modules/torchdiffeq/torchdiffeq/_impl/solvers.py:48-119,

@@ -410,6 +410,49 @@ extern "C" int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx,
     return NCDE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Linear / rectilinear hybrid (src/ncde/interpolation.py:186-253, steps after the two linear_interpolation_coeffs calls):
+// shift the linearly interpolated channels up by one row, keep a row only if a time / rectilinear channel differs from
+// the previous row, pad every series to the common length by repeating its last kept row (= NaN padding + forward fill).
+// One CTA per series walks the rows in order; lanes = channels, so every row is one coalesced access.
+//   chan_kind[c] = 1: time or rectilinear channel (decides whether a row is kept), 0: linear channel (shifted)
+//   out (n_series, K, C): rows [0, counts[s]) are the kept rows, the rest repeats the last one; the caller slices to max(counts)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void hybrid_compact_kernel(const T* __restrict__ full, const int32_t* __restrict__ chan_kind, T* __restrict__ out,
+                                      int32_t* __restrict__ counts, int64_t K, int64_t C) {
+    const int64_t s = blockIdx.x;
+    const T* fs = full + s * K * C;
+    T* os = out + s * K * C;
+    int pos = 0;
+    for (int64_t r = 0; r < K; ++r) {
+        int differs = r == 0;
+        if (r > 0)
+            for (int64_t c = threadIdx.x; c < C; c += blockDim.x)
+                if (chan_kind[c] == 1 && fs[(r - 1) * C + c] != fs[r * C + c]) differs = 1;   // NaN != NaN counts as a change, like `deltas != 0`
+        if (__syncthreads_or(differs)) {
+            const int64_t rs = r + 1 < K ? r + 1 : K - 1;
+            for (int64_t c = threadIdx.x; c < C; c += blockDim.x) os[(int64_t)pos * C + c] = fs[(chan_kind[c] == 0 ? rs : r) * C + c];
+            ++pos;
+        }
+    }
+    __syncthreads();
+    for (int64_t r = pos; r < K; ++r)
+        for (int64_t c = threadIdx.x; c < C; c += blockDim.x) os[r * C + c] = os[(int64_t)(pos - 1) * C + c];
+    if (threadIdx.x == 0) counts[s] = pos;
+}
+
+extern "C" int ncde_hybrid_compact(int dtype, const void* full, const int32_t* chan_kind, void* out, int32_t* counts,
+                                   int64_t n_series, int64_t K, int64_t C, void* stream) {
+    NCDE_REQUIRE(full && chan_kind && out && counts && K >= 1 && C >= 1, NCDE_ERR_INVALID, "hybrid_compact: bad arguments");
+    NCDE_REQUIRE(n_series < (1ll << 31), NCDE_ERR_UNSUPPORTED, "hybrid_compact: too many series");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (hybrid_compact_kernel<T><<<(unsigned)n_series, 128, 0, st>>>((const T*)full, chan_kind, (T*)out, counts, K, C)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
 extern "C" size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t L, int64_t C) {
     size_t el = dtype == NCDE_F64 ? 8 : 4;
     size_t n = (size_t)n_series * (size_t)C * (size_t)L;

@@ -682,6 +682,32 @@ def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, opti
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Linear / rectilinear hybrid (src/ncde/interpolation.py:186-253)
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def prepare_linear_rectilinear_hybrid(data, rectilinear_indices, time_index=0):
+    """Restatement with explicit loops for the row selection (the reference uses pad_sequence + forward_fill).
+    Mutates `data` like the reference."""
+    tr = [time_index] + list(rectilinear_indices)
+    non_rect = [c for c in range(data.size(-1)) if c not in tr]
+    data[..., non_rect] = linear_interpolation_coeffs(data[..., non_rect], initial_value_if_nan=0.0)
+    full = linear_interpolation_coeffs(data, rectilinear=0, initial_value_if_nan=0.0)
+    if len(non_rect) > 0:
+        full[..., non_rect] = torch.cat([full[..., 1:, non_rect], full[..., -1:, non_rect]], -2)
+    rows = []
+    for series in full:
+        keep = [0]
+        for r in range(1, series.size(0)):
+            if bool((series[r - 1, tr] != series[r, tr]).any()):
+                keep.append(r)
+        rows.append(series[keep])
+    longest = max(r.size(0) for r in rows)
+    out = torch.stack([torch.cat([r, r[-1:].expand(longest - r.size(0), -1)], 0) for r in rows])
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Log-ODE transform (tcde/log_ode.py).  The reference calls the third-party `signatory` extension for the log-signature
 # itself; signatory is neither vendored nor pinned (SURVEY section 8c), so THIS PART OF THE ORACLE IS "PARITY UNPINNED":
 # depth <= 2 log-signatures are restated from the published definition (Signatory's default "words" mode: level 1 =
