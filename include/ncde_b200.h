@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NCDE_ABI_VERSION 1
+#define NCDE_ABI_VERSION 2
 #define NCDE_MAX_LAYERS 8
 #define NCDE_MAX_STAGES 7
 
@@ -111,6 +111,18 @@ int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx, const void
 int ncde_hybrid_compact(int dtype, const void* full, const int32_t* chan_kind, void* out, int32_t* counts, int64_t n_series,
                         int64_t K, int64_t C, void* stream);
 
+/* SmoothLinearInterpolation (src/ncde/interpolation.py:6-183; unit knot spacing, as the reference requires): coefficients of
+ * the cubic (terms = 4: A,B,C,D) or quintic (terms = 6: A..F) that replaces the linear piece on [k, k + eps) after every
+ * interior knot so that the first (and second) derivatives are continuous -> out (n_series, K-2, C, terms).
+ * _setup_cubic_matching_coefficients / _setup_quintic_matching_coefficients (:146-183). */
+int ncde_smooth_matching_coeffs(int dtype, const void* coeffs, void* out, int64_t n_series, int64_t K, int64_t C, double eps,
+                                int terms, void* stream);
+/* evaluate (deriv = 0) / derivative (deriv = 1) of the smoothed path at n_t times -> out (n_series, n_t, C)
+ * (SmoothLinearInterpolation._interpret_t / evaluate / derivative, :72-123). */
+int ncde_path_eval_smooth(int dtype, const void* coeffs, const void* derivs, const void* knots, const void* match, int terms,
+                          double eps, int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv, void* out,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * The solve: z_t = z_0 + int f_theta(z_s) dX_s, replacing torchcde.cdeint -> torchdiffeq.odeint[_adjoint]
  * (modules/torchcde/torchcde/solver.py:102-238; modules/torchdiffeq/torchdiffeq/_impl/solvers.py:48-119,
@@ -138,6 +150,11 @@ typedef struct ncde_path {
     const float* knots;  /* device (K) */
     const float* coeffs; /* device; LINEAR (B,K,C), CUBIC (B,K-1,4C) */
     const float* derivs; /* device; LINEAR (B,K-1,C) precomputed by ncde_linear_derivs, or NULL; CUBIC NULL */
+    /* LINEAR only, optional (SmoothLinearInterpolation, src/ncde/interpolation.py:6-123): polynomial pieces that replace the
+     * linear ones on [t_k, t_k + match_eps) for every interior knot k = 1..K-2 */
+    const float* match;  /* device (B, K-2, C, match_terms) from ncde_smooth_matching_coeffs, or NULL */
+    int32_t match_terms; /* 4: cubic (first derivatives matched), 6: quintic (second derivatives too) */
+    float match_eps;     /* gradient_matching_eps */
 } ncde_path_t;
 
 /* Fixed-grid schedule, built by the host exactly as torchdiffeq does (solvers.py:77-119): everything here lives

@@ -453,6 +453,108 @@ extern "C" int ncde_hybrid_compact(int dtype, const void* full, const int32_t* c
     return NCDE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SmoothLinearInterpolation — src/ncde/interpolation.py:6-183.  The scalar factors (1/eps^2, 1/(3 eps^2), ...) are Python
+// doubles in the reference and are rounded to the tensor dtype when they multiply it; they arrive here as doubles and are
+// cast the same way.  Operation order follows the reference expression by expression (this file is compiled with -fmad=false).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void smooth_matching_kernel(const T* __restrict__ coeffs, T* __restrict__ out, int64_t n_series, int64_t K, int64_t C,
+                                       double eps_d, int terms) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * (K - 2) * C) return;
+    const int64_t c = tid % C, k = (tid / C) % (K - 2), s = tid / (C * (K - 2));
+    const T* cs = coeffs + s * K * C + c;
+    const T prev = cs[k * C], x = cs[(k + 1) * C], next = cs[(k + 2) * C];
+    const T eps = (T)eps_d;
+    const T x_eps = x + eps * (next - x);
+    const T delta_prev = x - prev, delta_next = next - x;
+    T* o = out + tid * terms;
+    if (terms == 4) {
+        const T Cc = delta_prev, D = x;
+        const T B = (T)(1.0 / (eps_d * eps_d)) * ((T)3 * (x_eps - Cc * eps - D) - eps * (delta_next - Cc));
+        const T A = (T)(1.0 / (3.0 * (eps_d * eps_d))) * (delta_next - Cc - (T)2 * B * eps);
+        o[0] = A; o[1] = B; o[2] = Cc; o[3] = D;
+    } else {
+        const T D = (T)0, E = delta_prev, F = x;
+        const T Cc = (T)(1.0 / (eps_d * eps_d * eps_d)) * ((T)10 * (x_eps - E * eps - F) - (T)4 * eps * (delta_next - E));
+        const T B = (T)(1.0 / (2.0 * (eps_d * eps_d * eps_d))) * ((T)2 * (delta_next - E) - (T)3 * Cc * (T)(eps_d * eps_d));
+        const T A = -(T)(1.0 / (10.0 * (eps_d * eps_d))) * ((T)6 * B * eps + (T)3 * Cc);
+        o[0] = A; o[1] = B; o[2] = Cc; o[3] = D; o[4] = E; o[5] = F;
+    }
+}
+
+// polynomial of the matching region, highest power first (interpolation.py:126-143): sum_i m[i] t^(terms-1-i), or its derivative
+template <typename T>
+__device__ __forceinline__ T smooth_poly(const T* __restrict__ m, int terms, T t, int deriv) {
+    T acc = 0;
+    if (deriv) {
+        for (int i = 0; i < terms - 1; ++i) {
+            const int pw = terms - 1 - i;          // term pw * t^(pw-1)
+            T tp = 1;
+            for (int q = 0; q < pw - 1; ++q) tp *= t;
+            acc += m[i] * ((T)pw * tp);
+        }
+    } else {
+        for (int i = 0; i < terms; ++i) {
+            const int pw = terms - 1 - i;
+            T tp = 1;
+            for (int q = 0; q < pw; ++q) tp *= t;
+            acc += m[i] * tp;
+        }
+    }
+    return acc;
+}
+
+template <typename T>
+__global__ void path_eval_smooth_kernel(const T* __restrict__ coeffs, const T* __restrict__ derivs, const T* __restrict__ knots,
+                                        const T* __restrict__ match, int terms, T eps, int64_t n_series, int64_t K, int64_t C,
+                                        const T* __restrict__ tq, int64_t n_t, int deriv, T* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * n_t * C) return;
+    const int64_t c = tid % C, q = (tid / C) % n_t, s = tid / (C * n_t);
+    const T t = tq[q];
+    const int idx = knot_index<T>(knots, (int)K, t);
+    const T frac = t - knots[idx];
+    T r;
+    if (match && idx > 0 && frac < eps) {
+        r = smooth_poly<T>(match + ((s * (K - 2) + idx - 1) * C + c) * terms, terms, frac, deriv);
+    } else if (deriv) {
+        r = derivs[(s * (K - 1) + idx) * C + c];
+    } else {
+        const T lo = coeffs[(s * K + idx) * C + c], hi = coeffs[(s * K + idx + 1) * C + c];
+        r = lo + frac * (hi - lo) / (knots[idx + 1] - knots[idx]);
+    }
+    out[tid] = r;
+}
+
+extern "C" int ncde_smooth_matching_coeffs(int dtype, const void* coeffs, void* out, int64_t n_series, int64_t K, int64_t C,
+                                           double eps, int terms, void* stream) {
+    NCDE_REQUIRE(coeffs && out && K >= 3 && C >= 1, NCDE_ERR_INVALID, "smooth_matching_coeffs: bad arguments");
+    NCDE_REQUIRE(terms == 4 || terms == 6, NCDE_ERR_INVALID, "smooth_matching_coeffs: terms must be 4 (cubic) or 6 (quintic)");
+    NCDE_REQUIRE(eps > 0 && eps <= 1, NCDE_ERR_INVALID, "gradient_matching_eps must be in (0, 1]");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (smooth_matching_kernel<T><<<grid_for(n_series * (K - 2) * C, 256), 256, 0, st>>>(
+                              (const T*)coeffs, (T*)out, n_series, K, C, eps, terms)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_path_eval_smooth(int dtype, const void* coeffs, const void* derivs, const void* knots, const void* match,
+                                     int terms, double eps, int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t,
+                                     int deriv, void* out, void* stream) {
+    NCDE_REQUIRE(coeffs && derivs && knots && tq && out && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval_smooth: bad arguments");
+    NCDE_REQUIRE(!match || terms == 4 || terms == 6, NCDE_ERR_INVALID, "path_eval_smooth: terms must be 4 or 6");
+    if (n_series == 0 || n_t == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (path_eval_smooth_kernel<T><<<grid_for(n_series * n_t * C, 256), 256, 0, st>>>(
+                              (const T*)coeffs, (const T*)derivs, (const T*)knots, (const T*)match, terms, (T)eps, n_series, K, C,
+                              (const T*)tq, n_t, deriv, (T*)out)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
 extern "C" size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t L, int64_t C) {
     size_t el = dtype == NCDE_F64 ? 8 : 4;
     size_t n = (size_t)n_series * (size_t)C * (size_t)L;

@@ -601,6 +601,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     if (rc != NCDE_OK) return rc;
     ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
     ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    ha.path.match = p->path.match; ha.path.match_terms = p->path.match_terms; ha.path.match_eps = p->path.match_eps;
     for (int i = 0; i < NS; ++i) ha.kT[i] = kT[i];
 
     FieldArgs fa;
@@ -1090,6 +1091,7 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     if (rc != NCDE_OK) return rc;
     ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
     ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    ha.path.match = p->path.match; ha.path.match_terms = p->path.match_terms; ha.path.match_eps = p->path.match_eps;
     for (int i = 0; i < 7; ++i) ha.kT[i] = kT[i];
     ha.combine = COMBINE_LINEAR;
     ha.yT = yT;
@@ -1323,6 +1325,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
     ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
     ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    ha.path.match = p->path.match; ha.path.match_terms = p->path.match_terms; ha.path.match_eps = p->path.match_eps;
     for (int i = 0; i < NS; ++i) ha.kT[i] = kf[i];
     ha.yT = yT; ha.KP = pl.KP; ha.comb_sign = -1.f;
     for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
@@ -1595,6 +1598,7 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     ha.w_in_smem = pl.w_in_smem; ha.wsm_floats = (int)round_up(pl.wt_floats, 4);
     ha.path.kind = p->path.kind; ha.path.K = (int)p->path.K; ha.path.knots = p->path.knots;
     ha.path.coeffs = p->path.coeffs; ha.path.derivs = p->path.derivs;
+    ha.path.match = p->path.match; ha.path.match_terms = p->path.match_terms; ha.path.match_eps = p->path.match_eps;
     for (int i = 0; i < 7; ++i) ha.kT[i] = kf[i];
     ha.yT = yT; ha.KP = pl.KP; ha.comb_sign = -1.f; ha.combine = COMBINE_LINEAR; ha.ctrl = ctrl;
     for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];

@@ -25,6 +25,9 @@ struct PathArgs {
     const float* coeffs;
     const float* derivs;
     float t;  // stage time, already cast to fp32 (torchdiffeq/_impl/misc.py:181)
+    const float* match;   // SmoothLinearInterpolation: (B, K-2, C, match_terms) or null
+    int match_terms;
+    float match_eps;
 };
 
 // ---- adaptive (dopri5) control state, resident in device memory; every time-like scalar is fp64 like the
@@ -243,6 +246,18 @@ __global__ void aug_advance_kernel(float* __restrict__ s, const float* k0, const
 // (torchcde/interpolation_linear.py:231-234, interpolation_cubic.py:331-336)
 __device__ __forceinline__ float path_derivative(const PathArgs& p, int idx, float frac, int64_t b, int c, int C) {
     if (p.kind == NCDE_PATH_LINEAR) {
+        if (p.match && idx > 0 && frac < p.match_eps) {
+            // gradient-matching region after an interior knot (src/ncde/interpolation.py:72-143): derivative of the polynomial
+            const float* m = p.match + (((int64_t)b * (p.K - 2) + idx - 1) * C + c) * p.match_terms;
+            float acc = 0.f;
+            for (int i = 0; i < p.match_terms - 1; ++i) {
+                const int pw = p.match_terms - 1 - i;
+                float tp = 1.f;
+                for (int q = 0; q < pw - 1; ++q) tp = __fmul_rn(tp, frac);
+                acc = __fadd_rn(acc, __fmul_rn(m[i], __fmul_rn((float)pw, tp)));
+            }
+            return acc;
+        }
         if (p.derivs) return p.derivs[((int64_t)b * (p.K - 1) + idx) * C + c];
         const float* cs = p.coeffs + (int64_t)b * p.K * C;
         return __fdiv_rn(__fsub_rn(cs[(int64_t)(idx + 1) * C + c], cs[(int64_t)idx * C + c]),

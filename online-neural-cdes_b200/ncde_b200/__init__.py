@@ -6,10 +6,14 @@ import torchcde_b200 as torchcde
 
 from .vector_fields import VECTOR_FIELDS, OriginalVectorField  # noqa: F401
 
+from .interpolation import SmoothLinearInterpolation  # noqa: E402
+
 SPLINES = {
     "cubic": torchcde.NaturalCubicSpline,
     "linear": torchcde.LinearInterpolation,
     "rectilinear": torchcde.LinearInterpolation,
+    "linear_cubic_smoothing": SmoothLinearInterpolation,
+    "linear_quintic_smoothing": SmoothLinearInterpolation,
 }
 
 
@@ -46,10 +50,16 @@ class NeuralCDE(nn.Module):
         if self.initial_dim > 0:
             self.initial_linear = nn.Linear(self.initial_dim, self.hidden_dim)
         assert self.interpolation in SPLINES.keys(), "Unrecognised interpolation scheme {}".format(self.interpolation)
-        if interpolation_eps == 1:
-            interpolation_eps = None
-        assert interpolation_eps is None
-        self.spline = SPLINES[self.interpolation]
+        # src/ncde/ncde.py:112-126
+        if interpolation in ("linear_cubic_smoothing", "linear_quintic_smoothing"):
+            match_second = "quintic" in interpolation
+            self.spline = lambda coeffs: SmoothLinearInterpolation(coeffs, gradient_matching_eps=interpolation_eps,
+                                                                   match_second_derivatives=match_second)
+        else:
+            if interpolation_eps == 1:
+                interpolation_eps = None
+            assert interpolation_eps is None
+            self.spline = SPLINES[self.interpolation]
 
         assert self.solver in ["rk4", "dopri5"]
         self.atol = 1e-5

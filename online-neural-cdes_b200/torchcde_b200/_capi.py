@@ -40,7 +40,10 @@ class Path(ctypes.Structure):
                 ("K", ctypes.c_int64),
                 ("knots", ctypes.c_void_p),
                 ("coeffs", ctypes.c_void_p),
-                ("derivs", ctypes.c_void_p)]
+                ("derivs", ctypes.c_void_p),
+                ("match", ctypes.c_void_p),
+                ("match_terms", ctypes.c_int32),
+                ("match_eps", ctypes.c_float)]
 
 
 class FixedGrid(ctypes.Structure):
@@ -71,7 +74,7 @@ _lib = None
 # every symbol include/ncde_b200.h declares; tests check that the library exports all of them
 SYMBOLS = ["ncde_version", "ncde_last_error", "ncde_abi_version", "ncde_forward_fill", "ncde_rectilinear_prepare",
            "ncde_linear_fill_missing", "ncde_cubic_scratch_bytes", "ncde_natural_cubic_coeffs", "ncde_linear_derivs",
-           "ncde_path_eval", "ncde_logsig_windows", "ncde_hybrid_compact", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
+           "ncde_path_eval", "ncde_logsig_windows", "ncde_hybrid_compact", "ncde_smooth_matching_coeffs", "ncde_path_eval_smooth", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
            "ncde_solve_bwd", "ncde_solve_adaptive_fwd", "ncde_solve_adjoint_workspace_bytes",
            "ncde_solve_adjoint_bwd", "ncde_solve_adjoint_adaptive_workspace_bytes",
            "ncde_solve_adjoint_adaptive_bwd", "ncde_profile_enable", "ncde_profile_read"]
@@ -103,6 +106,8 @@ def lib():
     L.ncde_path_eval.argtypes = [i32, i32, vp, vp, vp, i64, i64, i64, vp, i64, i32, vp, vp, vp]
     L.ncde_logsig_windows.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
     L.ncde_hybrid_compact.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.ncde_smooth_matching_coeffs.argtypes = [i32, vp, vp, i64, i64, i64, ctypes.c_double, i32, vp]
+    L.ncde_path_eval_smooth.argtypes = [i32, vp, vp, vp, vp, i32, ctypes.c_double, i64, i64, i64, vp, i64, i32, vp, vp]
     L.ncde_solve_saved_bytes.argtypes = [ctypes.POINTER(Problem), i32]
     L.ncde_solve_saved_bytes.restype = sz
     L.ncde_solve_workspace_bytes.argtypes = [ctypes.POINTER(Problem), i32]
@@ -126,7 +131,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("ncde_abi_version",):
             fn.restype = i32
-    if L.ncde_abi_version() != 1:
+    if L.ncde_abi_version() != 2:
         raise RuntimeError("libncde_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -123,6 +123,16 @@ def _build_problem(X, spec, B, H, C, method, precision, sched):
         p.path.K = coeffs.size(-2)
         p.path.derivs = derivs.data_ptr()
         keep.append(derivs)
+        if getattr(X, "gradient_matching_eps", None) is not None:   # SmoothLinearInterpolation (ncde_b200.interpolation)
+            if coeffs.dtype != torch.float32:
+                raise NotImplementedError("gradient matching inside cdeint needs float32 coefficients")
+            if method == "dopri5":
+                raise NotImplementedError("SmoothLinearInterpolation with method='dopri5' is not implemented")
+            match = X.gradient_matching_coeffs.detach().contiguous()
+            keep.append(match)
+            p.path.match = match.data_ptr()
+            p.path.match_terms = X.match_terms
+            p.path.match_eps = float(X.gradient_matching_eps)
     else:
         p.path.kind = _capi.PATH_CUBIC
         coeffs = X._coeffs.detach().contiguous()

@@ -707,6 +707,58 @@ def prepare_linear_rectilinear_hybrid(data, rectilinear_indices, time_index=0):
     return out
 
 
+class SmoothLinearPath(LinearPath):
+    """src/ncde/interpolation.py:6-183: linear interpolation with cubic / quintic gradient-matching regions
+    [t_k, t_k + eps) after every interior knot (unit knot spacing; one batch dimension)."""
+
+    def __init__(self, coeffs, gradient_matching_eps=None, match_second_derivatives=False):
+        super().__init__(coeffs)
+        self.eps = gradient_matching_eps
+        if self.eps is not None:
+            eps = self.eps
+            x = coeffs[..., 1:-1, :]
+            x_eps = x + eps * (coeffs[..., 2:, :] - x)
+            delta_prev = coeffs[..., 1:-1, :] - coeffs[..., :-2, :]
+            delta_next = coeffs[..., 2:, :] - coeffs[..., 1:-1, :]
+            if match_second_derivatives:   # :164-183
+                D = torch.zeros_like(x)
+                E = delta_prev
+                F = x
+                C = (1 / eps ** 3) * (10 * (x_eps - E * eps - F) - 4 * eps * (delta_next - E))
+                B = (1 / (2 * eps ** 3)) * (2 * (delta_next - E) - 3 * C * eps ** 2)
+                A = -(1 / (10 * eps ** 2)) * (6 * B * eps + 3 * C)
+                self.match = torch.stack([A, B, C, D, E, F], -1)
+            else:                          # :146-161
+                C = delta_prev
+                D = x
+                B = (1 / eps ** 2) * (3 * (x_eps - C * eps - D) - eps * (delta_next - C))
+                A = (1 / (3 * eps ** 2)) * (delta_next - C - 2 * B * eps)
+                self.match = torch.stack([A, B, C, D], -1)
+
+    def _poly(self, index, frac, derivative):
+        m = self.match[:, index - 1]            # (B, C, terms), highest power first
+        n = m.size(-1)
+        if derivative:
+            powers = torch.stack([i * frac ** (i - 1) for i in range(1, n)]).flip(0)
+            return (m[..., :-1] * powers).sum(-1)
+        powers = torch.stack([frac ** i for i in range(n)]).flip(0)
+        return (m * powers).sum(-1)
+
+    def evaluate(self, t):
+        t = torch.as_tensor(t, dtype=self.derivs.dtype)
+        frac, index = self._locate(t)
+        if self.eps is not None and t.dim() == 0 and 0 < int(index) and bool(frac < self.eps):
+            return self._poly(int(index), frac, False)
+        return super().evaluate(t)
+
+    def derivative(self, t):
+        t = torch.as_tensor(t, dtype=self.derivs.dtype)
+        frac, index = self._locate(t)
+        if self.eps is not None and t.dim() == 0 and 0 < int(index) and bool(frac < self.eps):
+            return self._poly(int(index), frac, True)
+        return super().derivative(t)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Log-ODE transform (tcde/log_ode.py).  The reference calls the third-party `signatory` extension for the log-signature
 # itself; signatory is neither vendored nor pinned (SURVEY section 8c), so THIS PART OF THE ORACLE IS "PARITY UNPINNED":
