@@ -278,38 +278,35 @@ __global__ void __launch_bounds__(128) p_reduce_kernel(const __grid_constant__ P
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// tc_hidden_bwd: CTA = one 128-row batch tile; for l = F-1 .. 0, with dpre_l (gradient w.r.t. the pre-activation of layer
-// l) and a_l (its input) as bf16 operand tiles in shared memory:
-//   dgrad   da_l[b][i]   = dpre_l . W_l           (A = dpre_l K-major, B = W_l MN-major)        -> TMEM cols [0, 128)
-//   wgrad   dW_l^T[i][o] = a_l^T . dpre_l         (both MN-major, K = batch rows)               -> TMEM cols [128 (l+1), +128)
-//   bias    db_l[o]      = column sums of the dpre_l tile (CUDA cores, while the tensor core works)
-//   epi     l > 0: dpre_{l-1} = da_l * act'(a_l) -> bf16 operand tile of the next level
+// tc_hidden_bwd: CTA = one 128-row batch tile; the input-gradient chain of the hidden layers, l = F-1 .. 0, with dpre_l
+// (gradient w.r.t. the pre-activation of layer l) as a bf16 operand tile in shared memory:
+//   dgrad   da_l[b][i] = dpre_l . W_l              (A = dpre_l K-major, B = W_l MN-major)        -> TMEM cols [0, 128)
+//   epi     l > 0: dpre_{l-1} = da_l * act'(a_l) -> bf16 operand tile of the next level, also TMA-stored to the dpre record
 //           l = 0: dz = da_0 -> fp32 feature-major dL/d(stage input); the RK adjoint combination happens where it is consumed
-// The weight gradients stay in TMEM until the end of the CTA and are then added to the global accumulators with
-// reductions (layers sharing a parameter slot simply add into the same accumulator).  Warp 8 is the producer (TMA + MMA).
+// The weight gradients are NOT formed here: dpre_l of every stage is kept as a record (p_reduce writes the top one) and one
+// split-K kernel at the end of the backward pass contracts them with the saved activations (tc_hidden_wgrad), which takes
+// the wgrad MMAs, the bias column sums and 32 k reductions per CTA off the sequential stage chain.
+// Warp 8 is the producer (TMA + MMA).
 // ---------------------------------------------------------------------------------------------------------------
 struct TcHiddenBwdMaps {
     CUtensorMap W;                        // as in the forward kernel
     CUtensorMap act[kTcHidMaxLayers];     // act[l]: saved input of layer l
-    CUtensorMap dpre;                     // {128, B, 1}: output of p_reduce
+    CUtensorMap dpre;                     // {128, B, n_rec * F}: record (rec * F + l) = dpre_l of stage rec
 };
 
 struct TcHiddenBwdArgs {
     int B, Bp, H, F, rec;
     int act[kTcHidMaxLayers];             // activation of layer l (act[l-1] is the one a_l went through)
-    float* dWacc[kTcHidMaxLayers];        // [128 out][128 in] fp32 accumulator of layer l's parameter slot
-    float* dbacc[kTcHidMaxLayers];        // [128]
     float* dz_out;                        // [H][Bp] fp32: dL/d(stage input) of this stage
 };
 
-struct TcHidBwdSmem { uint32_t Wt, At, Dt, bsum, bars, total; };
+struct TcHidBwdSmem { uint32_t Wt, At, Dt, bars, total; };
 __host__ __device__ inline TcHidBwdSmem tc_hid_bwd_layout() {
     TcHidBwdSmem L;
     uint32_t o = 0;
     L.Wt = o; o += 2 * kTcHidTile;
     L.At = o; o += 2 * kTcHidTile;
     L.Dt = o; o += 2 * kTcHidTile;
-    L.bsum = o; o += 8 * 128 * 4;
     L.bars = o; o += 16 * 8;
     L.total = o;
     return L;
@@ -322,26 +319,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcHidBwdSmem L = tc_hid_bwd_layout();
     uint8_t* Wt = smem + L.Wt;     // weights of level l in buffer l & 1
-    uint8_t* At = smem + L.At;     // a_l in buffer l & 1
+    uint8_t* At = smem + L.At;     // a_l in buffer l & 1 (levels l > 0 only: act' needs it)
     uint8_t* Dt = smem + L.Dt;     // dpre_l in buffer l & 1
-    float* bsum = reinterpret_cast<float*>(smem + L.bsum);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* w_full = bars;          // [2]
     uint64_t* a_full = bars + 2;      // [2]
     uint64_t* d_full = bars + 4;      // TMA: dpre_{F-1}
     uint64_t* dg_bar = bars + 5;      // dgrad of the level complete
-    uint64_t* lvl_bar = bars + 6;     // every MMA of the level complete (operand buffers free)
-    uint64_t* dp_ready = bars + 7;    // epilogue -> producer: dpre_{l-1} tile written (8 warp arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* dp_ready = bars + 6;    // epilogue -> producer: dpre_{l-1} tile written (8 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = blockIdx.x * kTcM;
     const int F = a.F;
 
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(w_full + i, 1); mbar_init(a_full + i, 1); }
-        mbar_init(d_full, 1); mbar_init(dg_bar, 1); mbar_init(lvl_bar, 1); mbar_init(dp_ready, 8);
+        mbar_init(d_full, 1); mbar_init(dg_bar, 1); mbar_init(dp_ready, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -355,6 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
         tma_load_3d(dst + kTcHidTile / 2, &maps.W, w_full + (l & 1), 64, 0, l);
     };
     auto load_A = [&](int l) {   // saved records: written by the forward pass, older than every kernel of the backward pass
+        if (l == 0) return;      // level 0 has no activation derivative to apply
         uint8_t* dst = At + (size_t)(l & 1) * kTcHidTile;
         mbar_expect_tx(a_full + (l & 1), kTcHidTile);
         tma_load_3d(dst, &maps.act[l], a_full + (l & 1), 0, b0, a.rec);
@@ -367,33 +363,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
         if (F > 1) { load_W(F - 2); load_A(F - 2); }
     }
     pdl_trigger();
-    pdl_wait();   // dpre_{F-1} comes from p_reduce; gy / gk from the previous kernels
+    pdl_wait();   // dpre_{F-1} comes from p_reduce
 
-    // phase bookkeeping: level index n = F-1-l counts 0, 1, ... ; buffers are indexed by l & 1, barrier phases by use count
     if (warp == 8) {
         if (lane == 0) {
             uint8_t* d_top = Dt + (size_t)((F - 1) & 1) * kTcHidTile;
             mbar_expect_tx(d_full, kTcHidTile);
-            tma_load_3d(d_top, &maps.dpre, d_full, 0, b0, 0);
-            tma_load_3d(d_top + kTcHidTile / 2, &maps.dpre, d_full, 64, b0, 0);
+            tma_load_3d(d_top, &maps.dpre, d_full, 0, b0, a.rec * F + F - 1);
+            tma_load_3d(d_top + kTcHidTile / 2, &maps.dpre, d_full, 64, b0, a.rec * F + F - 1);
             uint32_t use_w[2] = {0, 0};
             for (int l = F - 1, n = 0; l >= 0; --l, ++n) {
                 const int bf = l & 1;
                 if (n == 0) mbar_wait(d_full, 0);
                 else {
-                    mbar_wait(dp_ready, (uint32_t)(n - 1) & 1u);   // dpre_l written; every warp is done with a_{l+1}
+                    mbar_wait(dp_ready, (uint32_t)(n - 1) & 1u);   // dpre_l written (and fenced); every warp is done with a_{l+1}
+                    // keep dpre_l for the weight-gradient kernel
+                    tma_store_3d(&maps.dpre, Dt + (size_t)bf * kTcHidTile, 0, b0, a.rec * F + l);
+                    tma_store_3d(&maps.dpre, Dt + (size_t)bf * kTcHidTile + kTcHidTile / 2, 64, b0, a.rec * F + l);
+                    bulk_commit();
                     if (l - 1 >= 0) {
-                        // buffers of level l+1 are free once its MMAs have completed too: prefetch level l-1 into them
-                        mbar_wait(lvl_bar, (uint32_t)(n - 1) & 1u);
+                        // the weight / activation buffers of level l+1 are free (its dgrad completed before its epilogue ran)
                         load_W(l - 1); load_A(l - 1);
                     }
                 }
                 mbar_wait(w_full + bf, use_w[bf] & 1u);
-                mbar_wait(a_full + bf, use_w[bf] & 1u);
                 ++use_w[bf];
                 tc_fence_after();
-                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile), w_s = smem_u32(Wt + (size_t)bf * kTcHidTile),
-                               a_s = smem_u32(At + (size_t)bf * kTcHidTile);
+                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile), w_s = smem_u32(Wt + (size_t)bf * kTcHidTile);
                 {   // dgrad: D[128 b x 128 i] = dpre_l (K-major over o) . W_l (MN-major: N = i contiguous, K = o rows)
                     const uint32_t idesc = make_idesc(kTcM, 128, 0, 1);
                     for (int ks = 0; ks < 8; ++ks) {
@@ -402,17 +398,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
                                   ks > 0 ? 1u : 0u);
                     }
                 }
+                // the epilogue of this level overwrites the tile the store of level l+1's output... no: it writes buffer (l-1)&1,
+                // whose previous content dpre_{l+1} was stored two levels ago: that store must be done reading shared memory
+                bulk_wait_read<1>();
                 umma_commit(dg_bar);
-                {   // wgrad: D[128 i x 128 o] = a_l^T (MN-major: M = i contiguous, K = b rows) . dpre_l (MN-major: N = o contiguous)
-                    const uint32_t idesc = make_idesc(128, 128, 1, 1);
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t off = (uint32_t)ks * 2048u;
-                        umma_bf16(tmem_base + 128u * (uint32_t)(l + 1), make_sdesc(a_s + off, 128u * 128u, 1024),
-                                  make_sdesc(d_s + off, 128u * 128u, 1024), idesc, ks > 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit(lvl_bar);
             }
+            bulk_wait<0>();   // the records must be complete when the CTA exits
         }
     } else {
         const int wg = warp >> 2;
@@ -423,41 +414,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
         uint32_t use_a[2] = {0, 0};
         for (int l = F - 1, n = 0; l >= 0; --l, ++n) {
             const int bf = l & 1;
-            // ---- bias gradient: column sums of the dpre_l tile (16 chunks of 8 columns x 8 row slices of 16 rows) ----
-            if (n == 0) mbar_wait(d_full, 0);
-            else named_bar_sync(1, kTcEpiThreads);      // every warp has written its rows of dpre_l
-            if (lane < 16) {
-                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile);
-                float bacc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
-#pragma unroll 4
-                for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-                    uint32_t w4[4];
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
-                                 : "r"(d_s + sw128_off(r, lane, kTcM)));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
-                        bacc[2 * j] += f.x;
-                        bacc[2 * j + 1] += f.y;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bsum[warp * 128 + lane * 8 + j] = bacc[j];
-            }
-            named_bar_sync(1, kTcEpiThreads);
-            if (tid < 128) {
-                float sacc = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) sacc += bsum[w * 128 + tid];
-                if (a.dbacc[l]) atomicAdd(a.dbacc[l] + tid, sacc);
-            }
-            // ---- epilogue of the level ----
             mbar_wait(dg_bar, (uint32_t)n & 1u);
             tc_fence_after();
             if (l > 0) {
-                mbar_wait(a_full + bf, use_a[bf] & 1u);   // a_l landed (the producer waited on it too; this makes it visible here)
+                mbar_wait(a_full + bf, use_a[bf] & 1u);
+                ++use_a[bf];
                 const uint32_t a_s = smem_u32(At + (size_t)bf * kTcHidTile);
                 const uint32_t dst = smem_u32(Dt + (size_t)((l - 1) & 1) * kTcHidTile);
                 const int act = a.act[l - 1];
@@ -505,18 +466,148 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
                 }
                 tc_fence_before();
             }
-            ++use_a[bf];
         }
-        // ---- weight gradients: TMEM (lanes = i, columns = o) -> global accumulators [o][i] ----
-        mbar_wait(lvl_bar, (uint32_t)(F - 1) & 1u);
-        tc_fence_after();
-        for (int l = 0; l < F; ++l) {
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tc_hidden_wgrad: weight and bias gradients of the hidden layers for a WHOLE backward pass in one launch.
+//   dW_l^T[i][o] = sum over (stage, batch tile) units of  a_l^T . dpre_l       (both operands MN-major, K = the 128 rows of a unit)
+// CTA (l, split) owns a contiguous range of units, streams their two bf16 tiles through a 2-stage TMA pipeline,
+// accumulates in ONE TMEM accumulator over the whole range and adds it to the global accumulator at the end (split-K);
+// the bias gradient is the column sum of the dpre tiles, taken by the CUDA cores while the tensor core works.
+// ---------------------------------------------------------------------------------------------------------------
+struct TcHiddenWgradMaps {
+    CUtensorMap act[kTcHidMaxLayers];     // act[l]: saved input of layer l, {128, B, n_rec}
+    CUtensorMap dpre;                     // {128, B, n_rec * F}
+};
+struct TcHiddenWgradArgs {
+    int F, n_rec, n_mt, n_split;
+    float* dWacc[kTcHidMaxLayers];        // [128 out][128 in] fp32 accumulator of layer l's parameter slot
+    float* dbacc[kTcHidMaxLayers];        // [128]
+};
+static inline size_t tc_hid_wgrad_smem_bytes() { return 1024 + 4 * kTcHidTile + 8 * 128 * 4 + 16 * 8; }
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_wgrad_kernel(const __grid_constant__ TcHiddenWgradArgs a,
+                                                                        const __grid_constant__ TcHiddenWgradMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* At = smem;                          // 2 x a_l tile
+    uint8_t* Dt = smem + 2 * kTcHidTile;         // 2 x dpre_l tile
+    float* bsum = reinterpret_cast<float*>(smem + 4 * kTcHidTile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kTcHidTile + 8 * 128 * 4);
+    uint64_t* full = bars;            // [2] both tiles of a unit landed
+    uint64_t* mma_done = bars + 2;    // [2] the unit's MMAs completed
+    uint64_t* read_done = bars + 4;   // [2] the unit's column sums were taken (8 warp arrivals)
+    uint64_t* fin_bar = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l = blockIdx.x, sp = blockIdx.y;
+    const int64_t U = (int64_t)a.n_rec * a.n_mt;
+    const int64_t u_begin = sp * U / a.n_split, u_end = (sp + 1) * U / a.n_split;
+    const int n = (int)(u_end - u_begin);
+
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full + i, 1); mbar_init(mma_done + i, 1); mbar_init(read_done + i, 8); }
+        mbar_init(fin_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();   // the dpre records of the last stages come from the kernels just before this one
+
+    if (warp == 8) {
+        if (lane == 0 && n > 0) {
+            auto load = [&](int j) {
+                const int64_t u = u_begin + j;
+                const int rec = (int)(u / a.n_mt), b0 = (int)(u % a.n_mt) * kTcM;
+                const int bf = j & 1;
+                mbar_expect_tx(full + bf, 2 * kTcHidTile);
+                tma_load_3d(At + (size_t)bf * kTcHidTile, &maps.act[l], full + bf, 0, b0, rec);
+                tma_load_3d(At + (size_t)bf * kTcHidTile + kTcHidTile / 2, &maps.act[l], full + bf, 64, b0, rec);
+                tma_load_3d(Dt + (size_t)bf * kTcHidTile, &maps.dpre, full + bf, 0, b0, rec * a.F + l);
+                tma_load_3d(Dt + (size_t)bf * kTcHidTile + kTcHidTile / 2, &maps.dpre, full + bf, 64, b0, rec * a.F + l);
+            };
+            load(0);
+            if (n > 1) load(1);
+            const uint32_t idesc = make_idesc(128, 128, 1, 1);
+            for (int j = 0; j < n; ++j) {
+                const int bf = j & 1;
+                mbar_wait(full + bf, (uint32_t)(j >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t a_s = smem_u32(At + (size_t)bf * kTcHidTile), d_s = smem_u32(Dt + (size_t)bf * kTcHidTile);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t off = (uint32_t)ks * 2048u;
+                    umma_bf16(tmem_base, make_sdesc(a_s + off, 128u * 128u, 1024), make_sdesc(d_s + off, 128u * 128u, 1024), idesc,
+                              (ks > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(mma_done + bf);
+                if (j + 2 < n) {
+                    mbar_wait(mma_done + bf, (uint32_t)(j >> 1) & 1u);
+                    mbar_wait(read_done + bf, (uint32_t)(j >> 1) & 1u);
+                    load(j + 2);
+                }
+            }
+            umma_commit(fin_bar);
+        }
+    } else {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        float bacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const int bf = j & 1;
+            mbar_wait(full + bf, (uint32_t)(j >> 1) & 1u);
+            if (lane < 16) {   // 16 chunks of 8 columns x 8 row slices of 16 rows
+                const uint32_t d_s = smem_u32(Dt + (size_t)bf * kTcHidTile);
+#pragma unroll 4
+                for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+                    uint32_t w4[4];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                                 : "r"(d_s + sw128_off(r, lane, kTcM)));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                        bacc[2 * q] += f.x;
+                        bacc[2 * q + 1] += f.y;
+                    }
+                }
+            }
+            fence_async_smem();   // generic-proxy reads before the next TMA write into this buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(read_done + bf);
+        }
+        if (n > 0) {
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[warp * 128 + lane * 8 + j] = bacc[j];
+            }
+            named_bar_sync(1, kTcEpiThreads);
+            if (tid < 128 && a.dbacc[l]) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sacc += bsum[w * 128 + tid];
+                atomicAdd(a.dbacc[l] + tid, sacc);
+            }
+            mbar_wait(fin_bar, 0);
+            tc_fence_after();
             float* acc = a.dWacc[l];
-            const int i = row;
+            const int i = row;   // TMEM lanes = input feature i, columns = output feature o
 #pragma unroll
             for (int o0 = wg * 64; o0 < wg * 64 + 64; o0 += 32) {
                 uint32_t r[32];
-                tmem_ld32_issue(lane_addr + 128u * (uint32_t)(l + 1) + (uint32_t)o0, r);
+                tmem_ld32_issue(lane_addr + (uint32_t)o0, r);
                 tmem_wait_ld<32>(r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) atomicAdd(acc + (size_t)(o0 + j) * 128 + i, __uint_as_float(r[j]));
@@ -526,11 +617,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
     tc_fence_before();
     __syncwarp();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-// gW[o][i] += acc[o][i], gb[o] += accb[o] from the padded accumulators (launched once per layer, in order, so layers that
-// share a parameter tensor add into it one after the other)
 // gy += dz_0 + ... + dz_{n-1}: every stage input depends on y with unit Jacobian
 __global__ void gy_accumulate_kernel(float* __restrict__ gyT, const float* dz0, const float* dz1, const float* dz2, const float* dz3,
                                      int n_dz, int64_t n) {

@@ -338,7 +338,7 @@ static size_t fwd_workspace_extra_floats(const Plan& pl, int64_t n_steps, int ne
     if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * pl.Cp * pl.Bp + per;  // dX/dt of every stage
     return n;
 }
-static size_t bwd_workspace_floats(const Plan& pl) {
+static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps) {
     size_t per = 256 / 4;
     size_t n = pl.wpack_floats + per;
     n += (size_t)(1 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
@@ -347,7 +347,8 @@ static size_t bwd_workspace_floats(const Plan& pl) {
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
     n += (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
-    if (pl.tc_hid) n += (size_t)pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per;   // dpre record, weight-gradient accumulators
+    if (pl.tc_hid)   // dpre records of every stage and hidden layer (consumed by tc_hidden_wgrad), weight-gradient accumulators
+        n += (size_t)(n_steps > 0 ? n_steps : 1) * pl.n_stages * pl.F * pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per;
     return n;
 }
 
@@ -537,7 +538,7 @@ extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backwa
     Plan pl;
     if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
-    size_t fl = backward ? bwd_workspace_floats(pl)
+    size_t fl = backward ? bwd_workspace_floats(pl, p->grid.n_steps)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
 }
@@ -752,7 +753,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     if (rc != NCDE_OK) return rc;
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
-    NCDE_REQUIRE(workspace_bytes >= bwd_workspace_floats(pl) * 4, NCDE_ERR_WORKSPACE,
+    NCDE_REQUIRE(workspace_bytes >= bwd_workspace_floats(pl, p->grid.n_steps) * 4, NCDE_ERR_WORKSPACE,
                  "solve_bwd: workspace of %zu bytes is too small", workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     int64_t launches = 0;
@@ -774,7 +775,8 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     float* db3acc = cv.take((size_t)pl.n_bt * pl.Np);
     // all-tensor-core path: one bf16 record for dL/d(pre-activation of the last hidden layer), padded fp32 accumulators
     const bool tc_hid = pl.tc_hid && pl.F > 0;
-    float* dpre_rec = tc_hid ? cv.take((size_t)pl.Bp * 64) : nullptr;
+    const int64_t n_rec_all = g.n_steps * NS;
+    float* dpre_rec = tc_hid ? cv.take((size_t)(n_rec_all > 0 ? n_rec_all : 1) * pl.F * pl.Bp * 64) : nullptr;   // [rec][layer][Bp][128] bf16
     float* dWh_acc = tc_hid ? cv.take((size_t)pl.F * 128 * 128) : nullptr;
     float* dbh_acc = tc_hid ? cv.take((size_t)pl.F * 128) : nullptr;
 
@@ -828,20 +830,16 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             rc = make_map(&hbm.act[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const float*)saved + pl.abl_off[l], 128, (uint64_t)pl.B,
                           (uint64_t)(n_rec < 1 ? 1 : n_rec), 256, n_rec > 1 ? pl.stage_floats * 4 : 0, 64, kTcM, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc == NCDE_OK)
-            rc = make_map(&hbm.dpre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dpre_rec, 128, (uint64_t)pl.B, 1, 256, 0, 64, kTcM,
-                          CU_TENSOR_MAP_SWIZZLE_128B);
+            rc = make_map(&hbm.dpre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dpre_rec, 128, (uint64_t)pl.B,
+                          (uint64_t)(n_rec < 1 ? 1 : n_rec) * pl.F, 256, (size_t)pl.Bp * 256, 64, kTcM, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_bwd_kernel, tc_hid_bwd_smem_bytes());
+        if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_wgrad_kernel, tc_hid_wgrad_smem_bytes());
         if (rc != NCDE_OK) return rc;
         NCDE_CUDA_OK(cudaMemsetAsync(dWh_acc, 0, (size_t)pl.F * (128 * 128) * 4, st));
         NCDE_CUDA_OK(cudaMemsetAsync(dbh_acc, 0, (size_t)pl.F * 128 * 4, st));
         thb.B = pl.B; thb.Bp = pl.Bp; thb.H = pl.H; thb.F = pl.F;
-        for (int l = 0; l < pl.F; ++l) {
-            thb.act[l] = m.act[l];
-            // layers that share a parameter slot add into the accumulator of the first of them
-            thb.dWacc[l] = dWh_acc + (size_t)pl.first_of_slot[l] * 128 * 128;
-            thb.dbacc[l] = dbh_acc + (size_t)pl.first_of_slot[l] * 128;
-        }
-        pr.B = pl.B; pr.Bp = pl.Bp; pr.n_hg = pl.n_hg; pr.DFP = pl.DFP; pr.act = m.act[pl.F - 1]; pr.P = P; pr.dpre = (__nv_bfloat16*)dpre_rec;
+        for (int l = 0; l < pl.F; ++l) thb.act[l] = m.act[l];
+        pr.B = pl.B; pr.Bp = pl.Bp; pr.n_hg = pl.n_hg; pr.DFP = pl.DFP; pr.act = m.act[pl.F - 1]; pr.P = P;
     }
     rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_wgrad_kernel, 36 * 1024);
@@ -949,6 +947,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             if (tc_hid) {
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 pr.aF = (const __nv_bfloat16*)(stage + pl.abl_off[pl.F]);
+                pr.dpre = (__nv_bfloat16*)dpre_rec + ((size_t)(s * NS + i) * pl.F + (pl.F - 1)) * pl.Bp * 128;
                 NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(128), 0, st, pr));
                 thb.rec = (int)(s * NS + i);
                 thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
@@ -989,6 +988,29 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             }
         }
         j_hi = j_lo;
+    }
+    if (tc_hid && n_rec_all > 0) {
+        // weight / bias gradients of the hidden layers for the whole pass: one split-K launch over every (stage, batch tile)
+        TcHiddenWgradMaps wm;
+        TcHiddenWgradArgs wga;
+        memset(&wm, 0, sizeof(wm));
+        memset(&wga, 0, sizeof(wga));
+        for (int l = 0; l < pl.F; ++l) wm.act[l] = hbm.act[l];
+        wm.dpre = hbm.dpre;
+        wga.F = pl.F; wga.n_rec = (int)n_rec_all; wga.n_mt = (int)ceil_div(pl.B, kTcM);
+        const int64_t units = n_rec_all * wga.n_mt;
+        int n_split = kNumSMs / pl.F;
+        wga.n_split = (int)(n_split > units ? units : n_split);
+        for (int l = 0; l < pl.F; ++l) {
+            // layers that share a parameter slot add into the accumulator of the first of them
+            wga.dWacc[l] = dWh_acc + (size_t)pl.first_of_slot[l] * 128 * 128;
+            wga.dbacc[l] = dbh_acc + (size_t)pl.first_of_slot[l] * 128;
+        }
+        {
+            ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
+            NCDE_CUDA_OK(launch_pdl(tc_hidden_wgrad_kernel, dim3(pl.F, wga.n_split), dim3(kTcThreads), tc_hid_wgrad_smem_bytes(), st, wga, wm));
+        }
+        ++launches;
     }
     if (tc_hid) {
         for (int l = 0; l < pl.F; ++l) {
