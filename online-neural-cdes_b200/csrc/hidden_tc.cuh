@@ -232,13 +232,13 @@ struct PReduceArgs {
 // CTA (x, y) = 128 rows x 8 columns, 128 threads: thread = (column = tid / 16, 8 consecutive rows), so every load is 16 bytes
 // (8 bf16 partials) and a half-warp reads 256 contiguous bytes of P^T[g][k][.]; the 64 groups are summed in fp32 registers, the
 // 128 x 8 tile is transposed through shared memory and leaves as one 16-byte bf16 store per row.
-__global__ void __launch_bounds__(128) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
-    __shared__ float tile[128][9];
-    pdl_trigger();
-    pdl_wait();
-    const int col = threadIdx.x >> 4, rg = threadIdx.x & 15;
-    const int64_t b0 = (int64_t)blockIdx.x * 128;
-    const int k0 = blockIdx.y * 8;
+// one 128-row x 8-column slice of the reduction by threads 0..127 of a CTA; `tile` is [128][9] floats of shared memory;
+// `sync128` synchronises exactly these 128 threads
+template <typename Sync>
+__device__ __forceinline__ void p_reduce_slice(const PReduceArgs& a, int tile_idx, int col_block, int tid, float (*tile)[9], Sync sync128) {
+    const int col = tid >> 4, rg = tid & 15;
+    const int64_t b0 = (int64_t)tile_idx * 128;
+    const int k0 = col_block * 8;
     const int64_t bq = b0 + rg * 8;        // < Bp: the row pitch of P^T covers the padded batch, padded rows are never used
     float s[8];
 #pragma unroll
@@ -260,21 +260,28 @@ __global__ void __launch_bounds__(128) p_reduce_kernel(const __grid_constant__ P
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) tile[rg * 8 + j][col] = s[j];
-    __syncthreads();
-    if (threadIdx.x < 128 && b0 + threadIdx.x < a.B) {
-        const int64_t b = b0 + threadIdx.x;
+    sync128();
+    if (b0 + tid < a.B) {
+        const int64_t b = b0 + tid;
         const uint4 av = *reinterpret_cast<const uint4*>(a.aF + (size_t)b * 128 + k0);
         const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(tile[threadIdx.x][2 * j] * act_grad_bf(a2.x, a.act),
-                                                      tile[threadIdx.x][2 * j + 1] * act_grad_bf(a2.y, a.act));
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(tile[tid][2 * j] * act_grad_bf(a2.x, a.act), tile[tid][2 * j + 1] * act_grad_bf(a2.y, a.act));
             o[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(a.dpre + (size_t)b * 128 + k0) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+}
+
+// stand-alone launch (kept for A/B runs: NCDE_NO_FUSED_PREDUCE=1)
+__global__ void __launch_bounds__(128) p_reduce_kernel(const __grid_constant__ PReduceArgs a) {
+    __shared__ float tile[128][9];
+    pdl_trigger();
+    pdl_wait();
+    p_reduce_slice(a, blockIdx.x, blockIdx.y, threadIdx.x, tile, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -298,6 +305,10 @@ struct TcHiddenBwdArgs {
     int B, Bp, H, F, rec;
     int act[kTcHidMaxLayers];             // activation of layer l (act[l-1] is the one a_l went through)
     float* dz_out;                        // [H][Bp] fp32: dL/d(stage input) of this stage
+    // fused 64-way reduction (grid.y = 16 column blocks per batch tile; block y = 0 of each tile then runs the GEMM chain)
+    PReduceArgs pr;                       // pr.P == null: the top dpre record was written by a separate p_reduce launch
+    int* tile_count;                      // per batch tile: column blocks finished so far (monotonic over the stages of a pass)
+    int count_target;                     // 16 x (stages processed so far, this one included)
 };
 
 struct TcHidBwdSmem { uint32_t Wt, At, Dt, bars, total; };
@@ -332,17 +343,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = blockIdx.x * kTcM;
     const int F = a.F;
+    const bool fused = a.pr.P != nullptr;
+    const bool leader = blockIdx.y == 0;        // the one CTA per batch tile that runs the GEMM chain
+    __shared__ float red_tile[128][9];
 
-    if (warp == 0) tmem_alloc(tmem_slot, 128);
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(w_full + i, 1); mbar_init(a_full + i, 1); }
-        mbar_init(d_full, 1); mbar_init(dg_bar, 1); mbar_init(dp_ready, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (leader) {
+        if (warp == 0) tmem_alloc(tmem_slot, 128);
+        if (tid == 0) {
+            for (int i = 0; i < 2; ++i) { mbar_init(w_full + i, 1); mbar_init(a_full + i, 1); }
+            mbar_init(d_full, 1); mbar_init(dg_bar, 1); mbar_init(dp_ready, 8);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        tc_fence_before();
     }
-    tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = leader ? *tmem_slot : 0u;
     auto load_W = [&](int l) {
         uint8_t* dst = Wt + (size_t)(l & 1) * kTcHidTile;
         mbar_expect_tx(w_full + (l & 1), kTcHidTile);
@@ -356,17 +372,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
         tma_load_3d(dst, &maps.act[l], a_full + (l & 1), 0, b0, a.rec);
         tma_load_3d(dst + kTcHidTile / 2, &maps.act[l], a_full + (l & 1), 64, b0, a.rec);
     };
-    const bool producer = warp == 8 && lane == 0;
+    const bool producer = leader && warp == 8 && lane == 0;
     if (producer) {
         tma_prefetch_desc(&maps.dpre);
         load_W(F - 1); load_A(F - 1);
         if (F > 1) { load_W(F - 2); load_A(F - 2); }
     }
     pdl_trigger();
-    pdl_wait();   // dpre_{F-1} comes from p_reduce
+    pdl_wait();   // the partials P come from the final-layer kernel (or dpre_{F-1} from a separate p_reduce launch)
+
+    if (fused) {
+        // phase 1, every CTA: one 128 x 8 slice of  dpre_{F-1} = (sum_g P_g) * act'(a_F)  -> the stage's dpre record, then a
+        // release on the tile's counter; the leader's producer thread acquires it before its TMA reads the assembled tile
+        if (tid < 128) {
+            p_reduce_slice(a.pr, blockIdx.x, blockIdx.y, tid, red_tile, [] { named_bar_sync(2, 128); });
+            __threadfence();
+            named_bar_sync(2, 128);
+            if (tid == 0) atomicAdd(a.tile_count + blockIdx.x, 1);
+        }
+        if (!leader) return;
+    }
 
     if (warp == 8) {
         if (lane == 0) {
+            if (fused) {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.tile_count + blockIdx.x) : "memory");
+                } while (seen < a.count_target);
+                asm volatile("fence.proxy.async;" ::: "memory");   // the TMA (async proxy) read comes after the generic-proxy acquire
+            }
             uint8_t* d_top = Dt + (size_t)((F - 1) & 1) * kTcHidTile;
             mbar_expect_tx(d_full, kTcHidTile);
             tma_load_3d(d_top, &maps.dpre, d_full, 0, b0, a.rec * F + F - 1);

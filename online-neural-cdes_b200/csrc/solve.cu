@@ -348,7 +348,8 @@ static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps) {
     n += (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
     if (pl.tc_hid)   // dpre records of every stage and hidden layer (consumed by tc_hidden_wgrad), weight-gradient accumulators
-        n += (size_t)(n_steps > 0 ? n_steps : 1) * pl.n_stages * pl.F * pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per;
+        n += (size_t)(n_steps > 0 ? n_steps : 1) * pl.n_stages * pl.F * pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per +
+             (size_t)(pl.Bp / 128) + per;
     return n;
 }
 
@@ -777,6 +778,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     const bool tc_hid = pl.tc_hid && pl.F > 0;
     const int64_t n_rec_all = g.n_steps * NS;
     float* dpre_rec = tc_hid ? cv.take((size_t)(n_rec_all > 0 ? n_rec_all : 1) * pl.F * pl.Bp * 64) : nullptr;   // [rec][layer][Bp][128] bf16
+    int* tile_count = tc_hid ? (int*)cv.take((size_t)(pl.Bp / 128)) : nullptr;   // fused reduction: column blocks done per batch tile
     float* dWh_acc = tc_hid ? cv.take((size_t)pl.F * 128 * 128) : nullptr;
     float* dbh_acc = tc_hid ? cv.take((size_t)pl.F * 128) : nullptr;
 
@@ -835,6 +837,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_bwd_kernel, tc_hid_bwd_smem_bytes());
         if (rc == NCDE_OK) rc = opt_in_smem(tc_hidden_wgrad_kernel, tc_hid_wgrad_smem_bytes());
         if (rc != NCDE_OK) return rc;
+        NCDE_CUDA_OK(cudaMemsetAsync(tile_count, 0, (size_t)(pl.Bp / 128) * sizeof(int), st));
         NCDE_CUDA_OK(cudaMemsetAsync(dWh_acc, 0, (size_t)pl.F * (128 * 128) * 4, st));
         NCDE_CUDA_OK(cudaMemsetAsync(dbh_acc, 0, (size_t)pl.F * 128 * 4, st));
         thb.B = pl.B; thb.Bp = pl.Bp; thb.H = pl.H; thb.F = pl.F;
@@ -882,6 +885,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     const unsigned ew_grid = (unsigned)ceil_div((int64_t)nHB, 256);
     const float third = 0.3333333432674408f;
 
+    int stages_done = 0;     // fused reduction: target of the per-tile counters
     int64_t j_hi = g.n_out;  // outputs [j_lo, j_hi) belong to the current step
     for (int64_t s = g.n_steps - 1; s >= 0; --s) {
         int64_t j_lo = j_hi;
@@ -948,12 +952,24 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 pr.aF = (const __nv_bfloat16*)(stage + pl.abl_off[pl.F]);
                 pr.dpre = (__nv_bfloat16*)dpre_rec + ((size_t)(s * NS + i) * pl.F + (pl.F - 1)) * pl.Bp * 128;
-                NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(128), 0, st, pr));
                 thb.rec = (int)(s * NS + i);
                 thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
-                NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads), tc_hid_bwd_smem_bytes(),
-                                        st, thb, hbm));
-                launches += 2;
+                static const bool fused_reduce = getenv("NCDE_NO_FUSED_PREDUCE") == nullptr;
+                if (fused_reduce) {
+                    // one launch: 16 CTAs per batch tile reduce the partials, the first of them then runs the GEMM chain
+                    thb.pr = pr;
+                    thb.tile_count = tile_count;
+                    thb.count_target = 16 * (++stages_done);
+                    NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM), 16), dim3(kTcThreads),
+                                            tc_hid_bwd_smem_bytes(), st, thb, hbm));
+                    launches += 1;
+                } else {
+                    NCDE_CUDA_OK(launch_pdl(p_reduce_kernel, dim3((unsigned)ceil_div(pl.B, 128), 16), dim3(128), 0, st, pr));
+                    thb.pr.P = nullptr;
+                    NCDE_CUDA_OK(launch_pdl(tc_hidden_bwd_kernel, dim3((unsigned)ceil_div(pl.B, kTcM)), dim3(kTcThreads),
+                                            tc_hid_bwd_smem_bytes(), st, thb, hbm));
+                    launches += 2;
+                }
                 continue;
             }
             {
