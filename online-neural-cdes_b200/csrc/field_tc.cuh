@@ -43,6 +43,12 @@ struct TcFieldArgs {
     const float* kT[NCDE_MAX_STAGES];   // stage derivatives incl. the one this launch writes (koutT)
     int next_combine;
     float dt;
+    // last stage of a step (all-tensor-core path): the epilogue also advances the state, y_{n+1} = y_n + RK combination
+    // (fixed_grid.py:6-29, rk_common.py:114; same operation order as advance_kernel), and emits it
+    float* adv_ynewT;          // [H][Bp] or null: nothing to advance
+    __nv_bfloat16* adv_ybf;    // bf16 record [Bp][128] of y_{n+1} (input of the next step's first stage) or null
+    float* adv_emit;           // (B, H) row-major slice of z_out that receives y_{n+1}, or null
+    int adv_method;
     // backward of the all-tensor-core path: dL/dk of this stage is formed on the fly from the gradient of the step result and
     // the stage-input gradients of the LATER stages (rk_common.py:106-114 transposed), so no gk arrays are read-modify-written:
     //     gk[b,h] = gcoef * gy1[b,h] + sum_q dzcoef[q] * dz_q[b,h]
@@ -356,6 +362,29 @@ __device__ __forceinline__ float fwd_finish(const TcChunk<W>& k) {
 //   done[b]                epilogue finished (8 warp arrivals) -> accumulator b and dX buffer b free
 // Epilogue: thread = one TMEM lane (batch row); the two warp-groups split the columns.
 // ---------------------------------------------------------------------------------------------------------------
+// what the forward epilogue does with one finished k[b, h]: store it (feature-major, coalesced over the lanes = rows), emit the
+// next stage's input record, or — after the last stage of a step — advance the state and emit it
+__device__ __forceinline__ void tc_fwd_finish_element(const TcFieldArgs& a, int h, int64_t b, float k) {
+    const size_t off = (size_t)h * a.Bp + b;
+    a.koutT[off] = k;
+    if (a.zs_out)   // this thread's store above is visible to its own loads
+        a.zs_out[(size_t)b * 128 + h] = __float2bfloat16(__fadd_rn(a.yT[off], stage_increment(a.next_combine, a.dt, a.kT, nullptr, off)));
+    if (a.adv_ynewT) {
+        const float y = a.yT[off];
+        float yn;
+        if (a.adv_method == NCDE_RK4_38) {   // (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+            float s = __fadd_rn(a.kT[0][off], __fmul_rn(3.f, __fadd_rn(a.kT[1][off], a.kT[2][off])));
+            s = __fadd_rn(s, k);
+            yn = __fadd_rn(y, __fmul_rn(__fmul_rn(s, a.dt), 0.125f));
+        } else {                             // Euler: y0 + dt * f0
+            yn = __fadd_rn(y, __fmul_rn(a.dt, k));
+        }
+        a.adv_ynewT[off] = yn;
+        if (a.adv_ybf) a.adv_ybf[(size_t)b * 128 + h] = __float2bfloat16(yn);
+        if (a.adv_emit) a.adv_emit[(size_t)b * a.H + h] = yn;
+    }
+}
+
 struct TcFwdSmem {   // byte offsets from the 1024-aligned base
     uint32_t Ws, As, dXs, b3s, part, bars, total;
 };
@@ -512,23 +541,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_field_fwd_kernel(const __gri
                 }
                 if (a.Hg >= 2) {
                     const int h = g * a.Hg + hl;
-                    if (h < a.H && b0 + row < a.B) {
-                        const size_t off = (size_t)h * a.Bp + b0 + row;
-                        a.koutT[off] = acc;   // k^T[h][b], coalesced over the lanes
-                        if (a.zs_out)   // this thread's store above is visible to its own loads
-                            a.zs_out[(size_t)(b0 + row) * 128 + h] =
-                                __float2bfloat16(__fadd_rn(a.yT[off], stage_increment(a.next_combine, a.dt, a.kT, nullptr, off)));
-                    }
+                    if (h < a.H && b0 + row < a.B) tc_fwd_finish_element(a, h, b0 + row, acc);
                 } else {
                     if (wg == 0) part[row] = acc;
                     named_bar_sync(1, kTcEpiThreads);
-                    if (wg == 1 && g < a.H && b0 + row < a.B) {
-                        const size_t off = (size_t)g * a.Bp + b0 + row;
-                        a.koutT[off] = acc + part[row];
-                        if (a.zs_out)
-                            a.zs_out[(size_t)(b0 + row) * 128 + g] =
-                                __float2bfloat16(__fadd_rn(a.yT[off], stage_increment(a.next_combine, a.dt, a.kT, nullptr, off)));
-                    }
+                    if (wg == 1 && g < a.H && b0 + row < a.B) tc_fwd_finish_element(a, g, b0 + row, acc + part[row]);
                     named_bar_sync(1, kTcEpiThreads);
                 }
             }

@@ -306,6 +306,13 @@ struct TcHiddenBwdArgs {
     int act[kTcHidMaxLayers];             // activation of layer l (act[l-1] is the one a_l went through)
     float* dz_out;                        // [H][Bp] fp32: dL/d(stage input) of this stage
     // fused 64-way reduction (grid.y = 16 column blocks per batch tile; block y = 0 of each tile then runs the GEMM chain)
+    // last backward stage of a step: instead of dz this launch writes the gradient of the step's start state,
+    //   gy <- gy + dz + sum of the other stages' dz [+ gout_scale * grad_out of the output that sits at this time point]
+    float* gy_io;                         // [H][Bp] or null
+    const float* dz_other[NCDE_MAX_STAGES];
+    int n_other;
+    const float* gout;                    // (B, H) row-major or null
+    float gout_scale;
     PReduceArgs pr;                       // pr.P == null: the top dpre record was written by a separate p_reduce launch
     int* tile_count;                      // per batch tile: column blocks finished so far (monotonic over the stages of a pass)
     int count_target;                     // 16 x (stages processed so far, this one included)
@@ -494,9 +501,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_hidden_bwd_kernel(const __gr
                     tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
                     tmem_wait_ld<32>(r);
                     if (row_ok) {
+                        if (a.gy_io) {
+                            // loads of 8 features are issued together, then the stores (a store between them would order every
+                            // later load behind it: the compiler cannot rule out aliasing)
+                            const float* d1 = a.n_other > 0 ? a.dz_other[0] : nullptr;
+                            const float* d2 = a.n_other > 1 ? a.dz_other[1] : nullptr;
+                            const float* d3 = a.n_other > 2 ? a.dz_other[2] : nullptr;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < a.H) a.dz_out[(size_t)(c0 + j) * a.Bp + b] = __uint_as_float(r[j]);
+                            for (int j0 = 0; j0 < 32; j0 += 8) {
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int h = c0 + j0 + j;
+                                    const size_t off = (size_t)h * a.Bp + b;
+                                    float gsum = 0.f;
+                                    if (h < a.H) {
+                                        gsum = __ldg(a.gy_io + off) + __uint_as_float(r[j0 + j]);
+                                        if (d1) gsum += __ldg(d1 + off);
+                                        if (d2) gsum += __ldg(d2 + off);
+                                        if (d3) gsum += __ldg(d3 + off);
+                                    }
+                                    v[j] = gsum;
+                                }
+                                if (a.gout) {
+                                    const float* gp = a.gout + (size_t)b * a.H + c0 + j0;   // 8 consecutive features of this row
+                                    if (c0 + j0 + 8 <= a.H && (a.H & 3) == 0) {
+                                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp)), g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+                                        v[0] = fmaf(a.gout_scale, g0.x, v[0]); v[1] = fmaf(a.gout_scale, g0.y, v[1]);
+                                        v[2] = fmaf(a.gout_scale, g0.z, v[2]); v[3] = fmaf(a.gout_scale, g0.w, v[3]);
+                                        v[4] = fmaf(a.gout_scale, g1.x, v[4]); v[5] = fmaf(a.gout_scale, g1.y, v[5]);
+                                        v[6] = fmaf(a.gout_scale, g1.z, v[6]); v[7] = fmaf(a.gout_scale, g1.w, v[7]);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j)
+                                            if (c0 + j0 + j < a.H) v[j] = fmaf(a.gout_scale, __ldg(gp + j), v[j]);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (c0 + j0 + j < a.H) a.gy_io[(size_t)(c0 + j0 + j) * a.Bp + b] = v[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < a.H) a.dz_out[(size_t)(c0 + j) * a.Bp + b] = __uint_as_float(r[j]);
+                        }
                     }
                 }
                 tc_fence_before();

@@ -659,8 +659,14 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     static const int rk4_combine[4] = {COMBINE_Y, COMBINE_RK4_S2, COMBINE_RK4_S3, COMBINE_RK4_S4};
     int cur = 0;
     int64_t j_out = 1;
+    static const bool fuse_steps = getenv("NCDE_NO_STEP_FUSION") == nullptr;
     for (int64_t s = 0; s < g.n_steps; ++s) {
         const float dt = g.dt[s];
+        // outputs emitted by this step; the last stage's kernel can advance the state itself when there is at most one and it
+        // is the plain end-of-step state
+        int64_t n_emit_step = 0;
+        while (j_out + n_emit_step < g.n_out && g.out_step[j_out + n_emit_step] == s) ++n_emit_step;
+        const bool fuse_adv = fuse_steps && pl.tc_hid && (n_emit_step == 0 || (n_emit_step == 1 && g.out_mode[j_out] == 1));
         for (int i = 0; i < NS; ++i) {
             float* stage = need_grad ? (float*)saved + (size_t)(s * NS + i) * pl.stage_floats : scratch_stage;
             ha.combine = p->method == NCDE_RK4_38 ? rk4_combine[i] : COMBINE_Y;
@@ -686,6 +692,13 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                 for (int j = 0; j < NS; ++j) ta.kT[j] = kT[j];
                 ta.next_combine = emit && p->method == NCDE_RK4_38 ? rk4_combine[i + 1] : COMBINE_Y;
                 ta.dt = dt;
+                ta.adv_ynewT = nullptr; ta.adv_ybf = nullptr; ta.adv_emit = nullptr;
+                if (fuse_adv && i == NS - 1) {
+                    ta.adv_ynewT = yT[cur ^ 1];
+                    ta.adv_ybf = s + 1 < g.n_steps ? a0_of(need_grad ? (s + 1) * NS : 0) : nullptr;
+                    ta.adv_emit = n_emit_step == 1 ? z_out + (size_t)j_out * pl.B * pl.H : nullptr;
+                    ta.adv_method = p->method;
+                }
             } else {
                 ProfScope ps(NCDE_PROF_HIDDEN_FWD, st);
                 NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
@@ -710,6 +723,11 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                     ++launches;
                 }
             }
+        }
+        if (fuse_adv) {   // y_{n+1} was written (and emitted) by the last stage's final-layer kernel
+            j_out += n_emit_step;
+            cur ^= 1;
+            continue;
         }
         AdvanceArgs aa;
         memset(&aa, 0, sizeof(aa));
@@ -886,12 +904,39 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     const float third = 0.3333333432674408f;
 
     int stages_done = 0;     // fused reduction: target of the per-tile counters
+    static const bool fuse_steps = getenv("NCDE_NO_STEP_FUSION") == nullptr;
+    bool pre_injected = false;   // the output gradients that enter before this step's stages were already added by the previous step's last kernel
     int64_t j_hi = g.n_out;  // outputs [j_lo, j_hi) belong to the current step
     for (int64_t s = g.n_steps - 1; s >= 0; --s) {
         int64_t j_lo = j_hi;
         while (j_lo - 1 >= 1 && g.out_step[j_lo - 1] == s) --j_lo;
         const float dt = g.dt[s];
-        for (int64_t j = j_lo; j < j_hi; ++j) {
+        // All-tensor-core path: the last backward stage of the step (stage 0) writes gy <- gy + sum_i dz_i itself, and — when this
+        // step injects nothing afterwards and the next (earlier) step injects at most one output gradient beforehand — that one too.
+        // (measured: folding this elementwise work into the 8-CTA chain kernel costs 18 us per step against 8 us for the two wide
+        //  elementwise launches it replaces, so it is off unless NCDE_FOLD_GY is set)
+        static const bool fold_gy_enabled = getenv("NCDE_FOLD_GY") != nullptr;
+        bool fold_gy = fuse_steps && tc_hid && fold_gy_enabled;
+        const float* fold_gout = nullptr;
+        float fold_scale = 0.f;
+        bool fold_next_pre = false;
+        if (fold_gy) {
+            bool after_any = false;
+            for (int64_t j = j_lo; j < j_hi; ++j)
+                if (g.out_mode[j] == 0 || (g.out_mode[j] == 2 && g.out_slope[j] != 1.f)) after_any = true;
+            if (!after_any && s > 0) {
+                int64_t k_lo = j_lo;
+                while (k_lo - 1 >= 1 && g.out_step[k_lo - 1] == s - 1) --k_lo;
+                int n_pre = 0;
+                for (int64_t j = k_lo; j < j_lo; ++j) {
+                    const float sc = g.out_mode[j] == 1 ? 1.f : (g.out_mode[j] == 2 ? g.out_slope[j] : 0.f);
+                    if (sc != 0.f) { ++n_pre; fold_gout = grad_out + (size_t)j * pl.B * pl.H; fold_scale = sc; }
+                }
+                if (n_pre <= 1) fold_next_pre = true;
+                else { fold_gout = nullptr; fold_scale = 0.f; }
+            }
+        }
+        for (int64_t j = j_lo; j < j_hi && !pre_injected; ++j) {
             const float sc = g.out_mode[j] == 1 ? 1.f : (g.out_mode[j] == 2 ? g.out_slope[j] : 0.f);
             if (sc != 0.f) {
                 NCDE_CUDA_OK(launch_pdl(add_out_grad_kernel, tg, tb, 0, st, gyT, grad_out + (size_t)j * pl.B * pl.H, sc, pl.B, pl.Bp, pl.H));
@@ -954,6 +999,13 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 pr.dpre = (__nv_bfloat16*)dpre_rec + ((size_t)(s * NS + i) * pl.F + (pl.F - 1)) * pl.Bp * 128;
                 thb.rec = (int)(s * NS + i);
                 thb.dz_out = gkT[i];   // the stage-input gradient of stage i takes the place of the (unused) gk_i array
+                thb.gy_io = nullptr; thb.gout = nullptr; thb.n_other = 0;
+                if (fold_gy && i == 0) {
+                    thb.gy_io = gyT;
+                    for (int q = 1; q < NS; ++q) thb.dz_other[thb.n_other++] = gkT[q];
+                    thb.gout = fold_next_pre ? fold_gout : nullptr;
+                    thb.gout_scale = fold_scale;
+                }
                 static const bool fused_reduce = getenv("NCDE_NO_FUSED_PREDUCE") == nullptr;
                 if (fused_reduce) {
                     // one launch: 16 CTAs per batch tile reduce the partials, the first of them then runs the GEMM chain
@@ -978,11 +1030,12 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             }
             ++launches;
         }
-        if (tc_hid) {
+        if (tc_hid && !fold_gy) {
             NCDE_CUDA_OK(launch_pdl(gy_accumulate_kernel, dim3(ew_grid), dim3(256), 0, st, gyT, (const float*)gkT[0], (const float*)gkT[1],
                                     (const float*)gkT[2], (const float*)gkT[3], NS, (int64_t)nHB));
             ++launches;
         }
+        pre_injected = fold_gy && fold_next_pre;
         if (pl.F > 0 && !tc_hid) {
             // hidden weight gradients of all stages of this step in one launch (off the sequential chain)
             wa.n_stage = NS;
