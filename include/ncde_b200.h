@@ -94,6 +94,13 @@ int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, 
                    int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv, void* out,
                    int64_t* index_out, void* stream);
 
+/* Backward of ncde_path_eval with respect to the coefficients (what autograd does through
+ * LinearInterpolation / NaturalCubicSpline .evaluate/.derivative in the reference, e.g. for h0 = Linear(X.evaluate(0)) of a
+ * stacked Neural CDE, src/ncde/ncde.py:179-181).  grad_out (n_series, n_t, C); grad_coeffs has the shape of coeffs and is
+ * ACCUMULATED into (caller zero-initialises).  One thread per (series, channel) walks the query times in order: no atomics. */
+int ncde_path_eval_bwd(int kind, int dtype, const void* knots, int64_t n_series, int64_t K, int64_t C, const void* tq,
+                       int64_t n_t, int deriv, const void* grad_out, void* grad_coeffs, void* stream);
+
 /* Log-ODE transform, depth 1 or 2: log-signatures of the piecewise-linear path x (n_series, Lp, d) over W windows
  * (window w = rows idx[w]..idx[w+1], idx a device int32[W+1]), cumulatively summed, with the first row set to x[:,0,:] padded
  * with zeros -> out (n_series, W+1, d + d(d-1)/2).  Channel order as Signatory's "words" mode.  wscale (device, W values of
@@ -192,6 +199,8 @@ typedef struct ncde_problem {
  * inputs, hidden activations, path derivatives per stage) and must stay alive until ncde_solve_bwd;
  * `workspace` is scratch valid for one call. */
 size_t ncde_solve_saved_bytes(const ncde_problem_t* p, int need_grad);
+/* backward: 0 = forward pass, 1 = ncde_solve_bwd, 2 = ncde_solve_bwd with grad_coeffs != NULL (returns 0 if that is
+ * not supported for this problem). */
 size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward);
 
 /* Forward.  z0 (B,H) device; z_out (T,B,H) device (torchdiffeq's layout; cdeint returns its (B,T,H) permuted
@@ -216,7 +225,10 @@ int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0, float* z_o
 /* Backward of the fixed-grid solve (discretise-then-optimise: the exact gradient autograd produces through the
  * reference's step loop).  grad_out (T,B,H).  Writes grad_z0 (B,H); ACCUMULATES into gW[l]/gbias[l] (torch
  * layout, one pointer per layer; layers sharing a slot must pass the same pointer).  grad_coeffs (nullable):
- * gradient w.r.t. path.coeffs, same shape, accumulated. */
+ * gradient w.r.t. path.coeffs — what autograd sends into X's coefficient buffer through X.derivative(t) at every stage
+ * (modules/torchcde/torchcde/solver.py:128-132; interpolation_linear.py:198,231-234; interpolation_cubic.py:331-336) —
+ * same shape as path.coeffs, ACCUMULATED (the caller zero-initialises).  This is what stacked Neural CDEs need
+ * (src/ncde/stacked.py:120-128; modules/torchcde/test/test_tricks.py:54-106).  fp32 precision, un-smoothed paths. */
 int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, const void* saved, float* grad_z0,
                    float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
                    size_t workspace_bytes, int64_t* launches, void* stream);

@@ -161,6 +161,52 @@ __global__ void path_eval_kernel(int kind, const T* __restrict__ coeffs, const T
     out[tid] = r;
 }
 
+// gradient of path_eval_kernel w.r.t. the coefficients; thread = (series, channel), sequential over the query times
+template <typename T>
+__global__ void path_eval_bwd_kernel(int kind, const T* __restrict__ knots, int64_t n_series, int64_t K, int64_t C,
+                                     const T* __restrict__ tq, int64_t n_t, int deriv, const T* __restrict__ grad_out,
+                                     T* __restrict__ grad_coeffs) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t c = tid % C, s = tid / C;
+    for (int64_t q = 0; q < n_t; ++q) {
+        const T t = tq[q];
+        const int idx = knot_index<T>(knots, (int)K, t);
+        const T frac = t - knots[idx];
+        const T g = grad_out[(s * n_t + q) * C + c];
+        if (kind == NCDE_PATH_LINEAR) {
+            const T width = knots[idx + 1] - knots[idx];
+            T* lo = grad_coeffs + (s * K + idx) * C + c;
+            if (deriv) {
+                const T v = g / width;
+                lo[0] = lo[0] - v;
+                lo[C] = lo[C] + v;
+            } else {
+                // r = lo + frac * (hi - lo) / width
+                const T v = g * frac / width;
+                lo[0] = lo[0] + (g - v);
+                lo[C] = lo[C] + v;
+            }
+        } else {
+            T* row = grad_coeffs + (s * (K - 1) + idx) * 4 * C;
+            if (deriv) {
+                // r = b + (two_c + three_d * frac) * frac
+                const T gi = g * frac;
+                row[C + c] = row[C + c] + g;
+                row[2 * C + c] = row[2 * C + c] + gi;
+                row[3 * C + c] = row[3 * C + c] + gi * frac;
+            } else {
+                // r = a + (b + (0.5 * two_c + three_d * frac / 3) * frac) * frac
+                const T g1 = g * frac, g2 = g1 * frac;
+                row[c] = row[c] + g;
+                row[C + c] = row[C + c] + g1;
+                row[2 * C + c] = row[2 * C + c] + T(0.5) * g2;
+                row[3 * C + c] = row[3 * C + c] + g2 * frac / T(3);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // natural cubic spline coefficients — interpolation_cubic.py:7-190, misc.py:13-67 (Thomas algorithm)
 // One thread per scalar series; scratch arrays are laid out [L][n_threads] so every sweep step is coalesced.
@@ -341,6 +387,20 @@ extern "C" int ncde_path_eval(int kind, int dtype, const void* coeffs, const voi
     DISPATCH_DTYPE(dtype, (path_eval_kernel<T><<<grid_for(n_series * n_t * C, 256), 256, 0, st>>>(
                               kind, (const T*)coeffs, (const T*)derivs, (const T*)knots, n_series, K, C,
                               (const T*)tq, n_t, deriv, (T*)out, index_out)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+extern "C" int ncde_path_eval_bwd(int kind, int dtype, const void* knots, int64_t n_series, int64_t K, int64_t C,
+                                  const void* tq, int64_t n_t, int deriv, const void* grad_out, void* grad_coeffs,
+                                  void* stream) {
+    NCDE_REQUIRE(knots && tq && grad_out && grad_coeffs && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval_bwd: bad arguments");
+    NCDE_REQUIRE(kind == NCDE_PATH_LINEAR || kind == NCDE_PATH_CUBIC, NCDE_ERR_INVALID, "path_eval_bwd: bad kind");
+    if (n_series == 0 || n_t == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_DTYPE(dtype, (path_eval_bwd_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(
+                              kind, (const T*)knots, n_series, K, C, (const T*)tq, n_t, deriv, (const T*)grad_out,
+                              (T*)grad_coeffs)));
     NCDE_CUDA_OK(cudaGetLastError());
     return NCDE_OK;
 }

@@ -315,6 +315,45 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     return NCDE_OK;
 }
 
+// Tiling of the path-gradient launch: field_fwd_kernel on the problem with h and c exchanged (see
+// pack_final_swapped_kernel): "hidden rows" = the C channels, "channels" = the H hidden rows padded to 4.
+struct SwapPlan {
+    int Hp, Hg, S, n_hg, Np, n_bt, Bt, TM;
+    size_t smem, w3t_floats, b3p_floats;
+};
+static int make_swap_plan(const Plan& pl, SwapPlan* sp) {
+    memset(sp, 0, sizeof(*sp));
+    sp->Hp = (int)round_up(pl.H, 4);
+    NCDE_REQUIRE(sp->Hp <= 128, NCDE_ERR_UNSUPPORTED, "solve_bwd: path gradients need hidden width <= 128, got %d", pl.H);
+    double best = -1.0;
+    const int hg_max = pl.C < 128 / sp->Hp ? pl.C : 128 / sp->Hp;
+    for (int hg = hg_max; hg >= 1; --hg) {
+        const int S = hg * sp->Hp, NT = S / 4;
+        if (fwd_smem_floats(pl.DF, S) * 4 > kSmemLimit) continue;
+        const int n_hg = (int)ceil_div(pl.C, hg);
+        int n_bt = kNumSMs / n_hg;
+        const int max_bt = (int)ceil_div(pl.B, kChunk);
+        n_bt = n_bt < 1 ? 1 : (n_bt > max_bt ? max_bt : n_bt);
+        const int TM = NT > 16 ? 8 : 4;
+        const int thr = NT * (kChunk / TM);
+        const double util = (thr > kThreads ? kThreads : thr) / (double)kThreads;
+        const int ctas = n_hg * n_bt;
+        const double score = (ctas > kNumSMs ? kNumSMs : ctas) / (double)kNumSMs * util;
+        if (score > best + 1e-9) {
+            best = score;
+            sp->Hg = hg; sp->S = S; sp->n_hg = n_hg; sp->TM = TM;
+            sp->Bt = (int)round_up(ceil_div(pl.B, n_bt), kChunk);
+            sp->n_bt = (int)ceil_div(pl.B, sp->Bt);
+        }
+    }
+    NCDE_REQUIRE(best > 0, NCDE_ERR_UNSUPPORTED, "solve_bwd: no path-gradient tiling fits shared memory (H=%d, width=%d)", pl.H, pl.DF);
+    sp->Np = sp->n_hg * sp->S;
+    sp->smem = fwd_smem_floats(pl.DF, sp->S) * 4;
+    sp->w3t_floats = round_up((size_t)pl.DF * sp->Np, 64);
+    sp->b3p_floats = round_up(sp->Np, 64);
+    return NCDE_OK;
+}
+
 struct Carver {
     char* base; size_t used, cap;
     float* take(size_t floats) {
@@ -338,10 +377,12 @@ static size_t fwd_workspace_extra_floats(const Plan& pl, int64_t n_steps, int ne
     if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * pl.Cp * pl.Bp + per;  // dX/dt of every stage
     return n;
 }
-static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps) {
+static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps, const SwapPlan* sp = nullptr) {
     size_t per = 256 / 4;
     size_t n = pl.wpack_floats + per;
-    n += (size_t)(1 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
+    n += (size_t)(1 + pl.n_stages) * (round_up(pl.H, 4) * (size_t)pl.Bp + per);
+    if (sp)   // path gradient: swapped final-layer pack, dL/d(dX/dt) of every stage of one step
+        n += sp->w3t_floats + sp->b3p_floats + 2 * per + (size_t)pl.n_stages * ((size_t)pl.C * pl.Bp + per);
     n += (size_t)pl.n_hg * pl.Bp * pl.DFP + per;
     for (int l = 0; l < pl.F; ++l) n += (size_t)pl.n_stages * ((size_t)pl.Dp4[l + 1] * pl.Bp + per);
     n += (size_t)pl.n_bt * pl.Np * pl.DFP + per;
@@ -539,7 +580,9 @@ extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backwa
     Plan pl;
     if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
-    size_t fl = backward ? bwd_workspace_floats(pl, p->grid.n_steps)
+    SwapPlan sp;
+    if (backward == 2 && (pl.tc || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
+    size_t fl = backward ? bwd_workspace_floats(pl, p->grid.n_steps, backward == 2 ? &sp : nullptr)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
 }
@@ -766,13 +809,21 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                               float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
                               size_t workspace_bytes, int64_t* launches_out, void* stream) {
     NCDE_REQUIRE(p && grad_out && saved && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID, "solve_bwd: null pointer");
-    NCDE_REQUIRE(grad_coeffs == nullptr, NCDE_ERR_UNSUPPORTED, "solve_bwd: gradient w.r.t. the control path is not implemented");
     Plan pl;
     int rc = make_plan(p, &pl, true);
     if (rc != NCDE_OK) return rc;
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
-    NCDE_REQUIRE(workspace_bytes >= bwd_workspace_floats(pl, p->grid.n_steps) * 4, NCDE_ERR_WORKSPACE,
+    SwapPlan sp;
+    if (grad_coeffs) {
+        NCDE_REQUIRE(!pl.tc, NCDE_ERR_UNSUPPORTED,
+                     "solve_bwd: the gradient w.r.t. the control path is implemented for precision fp32 only");
+        NCDE_REQUIRE(p->path.match == nullptr, NCDE_ERR_UNSUPPORTED,
+                     "solve_bwd: the gradient w.r.t. the control path is not implemented for gradient-matched (smoothed) paths");
+        rc = make_swap_plan(pl, &sp);
+        if (rc != NCDE_OK) return rc;
+    }
+    NCDE_REQUIRE(workspace_bytes >= bwd_workspace_floats(pl, p->grid.n_steps, grad_coeffs ? &sp : nullptr) * 4, NCDE_ERR_WORKSPACE,
                  "solve_bwd: workspace of %zu bytes is too small", workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     int64_t launches = 0;
@@ -783,9 +834,18 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
 
     Carver cv{(char*)workspace, 0, workspace_bytes};
     float* wpack = cv.take(pl.wpack_floats);
-    float* gyT = cv.take(nHB);
+    const size_t nHBp = round_up(pl.H, 4) * (size_t)pl.Bp;   // rows H..Hp-1: zero padding read by the path-gradient launch
+    float* gyT = cv.take(nHBp);
     float* gkT[NCDE_MAX_STAGES] = {};
-    for (int i = 0; i < NS; ++i) gkT[i] = cv.take(nHB);
+    for (int i = 0; i < NS; ++i) gkT[i] = cv.take(nHBp);
+    float* W3Ts = nullptr;
+    float* b3ps = nullptr;
+    float* gdXT[NCDE_MAX_STAGES] = {};
+    if (grad_coeffs) {
+        W3Ts = cv.take(sp.w3t_floats);
+        b3ps = cv.take(sp.b3p_floats);
+        for (int i = 0; i < NS; ++i) gdXT[i] = cv.take((size_t)pl.C * pl.Bp);
+    }
     float* P = cv.take((size_t)pl.n_hg * pl.Bp * pl.DFP);
     float* dpreT[NCDE_MAX_STAGES][NCDE_MAX_LAYERS] = {};
     for (int i = 0; i < NS; ++i)
@@ -824,6 +884,28 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     TcFieldArgs ta;
     fill_tc_args(ta, pl, wpack);
     ta.P = P; ta.dW3acc = dW3acc; ta.db3acc = db3acc;
+    // path gradient: the forward final-layer kernel on the (h <-> c)-exchanged problem, one launch per stage
+    FieldArgs fs;
+    PathGradArgs pg;
+    memset(&fs, 0, sizeof(fs));
+    memset(&pg, 0, sizeof(pg));
+    if (grad_coeffs) {
+        const int64_t n = (int64_t)sp.Np * pl.DF;
+        pack_final_swapped_kernel<<<(unsigned)ceil_div(n > sp.Np ? n : sp.Np, 256), 256, 0, st>>>(
+            m.W[pl.F], m.bias[pl.F], W3Ts, b3ps, pl.H, pl.C, sp.Hp, pl.DF, sp.Np);
+        ++launches;
+        if (sp.Hp > pl.H)
+            for (int i = 0; i < NS; ++i)
+                NCDE_CUDA_OK(cudaMemsetAsync(gkT[i] + nHB, 0, (nHBp - nHB) * 4, st));
+        fs.B = pl.B; fs.Bp = pl.Bp; fs.H = pl.C; fs.Cp = sp.Hp; fs.DF = pl.DF; fs.DFP = pl.DFP; fs.S = sp.S; fs.Hg = sp.Hg;
+        fs.n_hg = sp.n_hg; fs.Np = sp.Np; fs.Bt = sp.Bt;
+        fs.W3T = W3Ts; fs.b3p = b3ps;
+        rc = sp.TM == 8 ? opt_in_smem(field_fwd_kernel<8>, sp.smem) : opt_in_smem(field_fwd_kernel<4>, sp.smem);
+        if (rc != NCDE_OK) return rc;
+        pg.B = pl.B; pg.Bp = pl.Bp; pg.C = pl.C; pg.n_stage = NS; pg.kind = p->path.kind; pg.K = (int)p->path.K;
+        pg.knots = p->path.knots; pg.grad_coeffs = grad_coeffs;
+        for (int i = 0; i < NS; ++i) pg.gdXT[i] = gdXT[i];
+    }
 
     HiddenBwdArgs hb;
     memset(&hb, 0, sizeof(hb));
@@ -982,6 +1064,16 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     ++launches;
                 }
             }
+            if (grad_coeffs) {
+                // dL/d(dX/dt)[b,c] = sum_h tanh(pre[b,h,c]) gk_i[b,h]
+                fs.actT = stage + pl.act_off[pl.F];
+                fs.dXT = gkT[i];
+                fs.koutT = gdXT[i];
+                const dim3 sg(sp.n_hg, sp.n_bt);
+                if (sp.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, sg, dim3(kThreads), sp.smem, st, fs));
+                else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, sg, dim3(kThreads), sp.smem, st, fs));
+                ++launches;
+            }
             for (int l = 0; l <= pl.F; ++l) hb.actT[l] = stage + pl.act_off[l];
             for (int l = 0; l < pl.F; ++l) hb.dpreT[l] = dpreT[i][l];
             // d(stage input)/d(k_j): rk_common.py:111-113
@@ -1028,6 +1120,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                 ProfScope ps(NCDE_PROF_HIDDEN_BWD, st);
                 NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
             }
+            ++launches;
+        }
+        if (grad_coeffs) {
+            for (int i = 0; i < NS; ++i) pg.t[i] = g.stage_t[s * NS + i];
+            NCDE_CUDA_OK(launch_pdl(path_grad_kernel, dim3((unsigned)ceil_div(pl.B, 32)), dim3(256), 0, st, pg));
             ++launches;
         }
         if (tc_hid && !fold_gy) {

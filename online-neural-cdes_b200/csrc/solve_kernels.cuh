@@ -365,6 +365,94 @@ __global__ void pack_final_kernel(const float* __restrict__ W, const float* __re
     }
 }
 
+// Final layer packed with the roles of h and c exchanged: n' = c*Hp + h (h padded to Hp, c padded to n_cg*Cg rows-of-Hp).
+// With this packing field_fwd_kernel, called with (H', C', dX') = (C, H, gk), computes
+//     gdX[b, c] = sum_h tanh( act[b,:] . W3[(h,c),:] + b3[(h,c)] ) * gk[b, h],
+// the gradient of the f(z).dX/dt contraction (torchcde/solver.py:132) w.r.t. dX/dt — the same code that computes k[b,h]
+// in the forward pass, so the path gradient needs no kernel of its own and no atomics.
+__global__ void pack_final_swapped_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ W3T,
+                                          float* __restrict__ b3p, int H, int C, int Hp, int DF, int Np) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)Np * DF;
+    if (idx < total) {
+        const int n = (int)(idx / DF), k = (int)(idx % DF);
+        const int c = n / Hp, h = n % Hp;
+        W3T[(int64_t)k * Np + n] = (h < H && c < C) ? W[((int64_t)h * C + c) * DF + k] : 0.f;
+    }
+    if (idx < Np) {
+        const int c = (int)idx / Hp, h = (int)idx % Hp;
+        b3p[idx] = (bias && h < H && c < C) ? bias[(int64_t)h * C + c] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// path_grad: chain rule from dL/d(dX/dt) at the stage times of ONE solver step to the path coefficients, i.e. the
+// backward of LinearInterpolation.derivative (derivs = (c[1:] - c[:-1]) / (t[1:] - t[:-1]) gathered at the knot index,
+// torchcde/interpolation_linear.py:198,231-234) or of NaturalCubicSpline.derivative (b + (2c + 3d f) f,
+// interpolation_cubic.py:331-336).  CTA = 32 batch rows; the feature-major gradient tile is transposed through shared
+// memory so that reads (batch contiguous) and the read-modify-write of grad_coeffs (channels contiguous) are both
+// coalesced.  One thread owns one (row, channel) for every stage of the step, launches are stream ordered: no atomics,
+// deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+struct PathGradArgs {
+    int B, Bp, C, n_stage, kind, K;
+    const float* knots;
+    float t[NCDE_MAX_STAGES];
+    const float* gdXT[NCDE_MAX_STAGES];  // [C][Bp]
+    float* grad_coeffs;                  // LINEAR (B,K,C) | CUBIC (B,K-1,4C)
+};
+
+__global__ void __launch_bounds__(256) path_grad_kernel(const __grid_constant__ PathGradArgs a) {
+    __shared__ float tile[32][129];
+    __shared__ int s_idx[NCDE_MAX_STAGES];
+    __shared__ float s_frac[NCDE_MAX_STAGES], s_width[NCDE_MAX_STAGES];
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    if (tid < a.n_stage) {
+        const float t = a.t[tid];
+        const int idx = knot_index<float>(a.knots, a.K, t);
+        s_idx[tid] = idx;
+        s_frac[tid] = __fsub_rn(t, a.knots[idx]);
+        s_width[tid] = __fsub_rn(a.knots[idx + 1], a.knots[idx]);
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < a.C; c0 += 128) {
+        const int cw = min(128, a.C - c0);
+        for (int st = 0; st < a.n_stage; ++st) {
+            const float* __restrict__ src = a.gdXT[st];
+            for (int i = tid; i < cw * 32; i += 256) {
+                const int c = i / 32, r = i % 32;
+                const int64_t b = b0 + r;
+                tile[r][c] = b < a.B ? src[(size_t)(c0 + c) * a.Bp + b] : 0.f;
+            }
+            __syncthreads();
+            const int idx = s_idx[st];
+            const float frac = s_frac[st], width = s_width[st];
+            for (int i = tid; i < 32 * cw; i += 256) {
+                const int r = i / cw, c = c0 + i % cw;
+                const int64_t b = b0 + r;
+                if (b >= a.B) continue;
+                const float g = tile[r][c - c0];
+                if (a.kind == NCDE_PATH_LINEAR) {
+                    const float q = __fdiv_rn(g, width);
+                    float* p = a.grad_coeffs + ((size_t)b * a.K + idx) * a.C + c;
+                    p[0] = __fsub_rn(p[0], q);
+                    p[a.C] = __fadd_rn(p[a.C], q);
+                } else {
+                    float* row = a.grad_coeffs + ((size_t)b * (a.K - 1) + idx) * 4 * a.C;
+                    const float gi = __fmul_rn(g, frac);
+                    row[a.C + c] = __fadd_rn(row[a.C + c], g);
+                    row[2 * a.C + c] = __fadd_rn(row[2 * a.C + c], gi);
+                    row[3 * a.C + c] = __fadd_rn(row[3 * a.C + c], __fmul_rn(gi, frac));
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // (B,H) row-major <-> [H][Bp] feature-major
 __global__ void to_feature_major_kernel(const float* __restrict__ src, float* __restrict__ dstT, int B, int Bp, int H) {
     __shared__ float tile[32][33];

@@ -123,3 +123,6 @@ class NeuralCDE(nn.Module):
                                  vector_field_type=self.vector_field_type, method=self.solver, atol=self.atol,
                                  rtol=self.rtol, options=options)
         return self._make_outputs(hidden)
+
+
+from .stacked import StackedNeuralCDE  # noqa: E402,F401

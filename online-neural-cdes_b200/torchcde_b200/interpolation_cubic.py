@@ -88,17 +88,16 @@ class NaturalCubicSpline(interpolation_base.InterpolationBase):
         t = torch.as_tensor(t, dtype=self._coeffs.dtype, device=self._coeffs.device)
         coeffs = self._coeffs.detach().contiguous()
         C = self._channels
-        K = coeffs.size(-2) + 1
-        n = coeffs.numel() // ((K - 1) * 4 * C) if coeffs.numel() else 0
         tq = t.detach().reshape(-1).contiguous()
-        out = torch.empty(*coeffs.shape[:-2], tq.numel(), C, dtype=coeffs.dtype, device=coeffs.device)
-        index = torch.empty(tq.numel(), dtype=torch.int64, device=coeffs.device) if want_index else None
         knots = self._t.detach().to(coeffs.dtype).contiguous()
-        _capi.check(_capi.lib().ncde_path_eval(_capi.PATH_CUBIC, _capi.dtype_code(coeffs), coeffs.data_ptr(), None,
-                                               knots.data_ptr(), n, K, C, tq.data_ptr(), tq.numel(), int(deriv),
-                                               out.data_ptr(), _capi.ptr(index), _capi.stream_ptr(coeffs.device)))
         if want_index:
+            index = torch.empty(tq.numel(), dtype=torch.int64, device=coeffs.device)
+            interpolation_base.path_eval_raw(_capi.PATH_CUBIC, coeffs, None, knots, tq, deriv, C, index)
             return index.reshape(t.shape)
+        if self._coeffs.requires_grad and torch.is_grad_enabled():
+            out = interpolation_base.PathEvalGrad.apply(self._coeffs, _capi.PATH_CUBIC, None, knots, tq, bool(deriv), C)
+        else:
+            out = interpolation_base.path_eval_raw(_capi.PATH_CUBIC, coeffs, None, knots, tq, deriv, C)
         return out.reshape(*coeffs.shape[:-2], *t.shape, C)
 
     def evaluate(self, t):

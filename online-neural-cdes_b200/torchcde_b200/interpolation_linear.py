@@ -111,14 +111,14 @@ class LinearInterpolation(interpolation_base.InterpolationBase):
     def _eval(self, t, deriv):
         t = torch.as_tensor(t, dtype=self._derivs.dtype, device=self._derivs.device)
         coeffs = self._coeffs.detach().contiguous()
-        n, K, C = _flatten(coeffs)
+        C = coeffs.size(-1)
         tq = t.detach().reshape(-1).contiguous()
-        out = torch.empty(*coeffs.shape[:-2], tq.numel(), C, dtype=coeffs.dtype, device=coeffs.device)
         knots = self._t.detach().to(coeffs.dtype).contiguous()
-        _capi.check(_capi.lib().ncde_path_eval(_capi.PATH_LINEAR, _capi.dtype_code(coeffs), coeffs.data_ptr(),
-                                               self._derivs.data_ptr(), knots.data_ptr(), n, K, C, tq.data_ptr(),
-                                               tq.numel(), int(deriv), out.data_ptr(), None,
-                                               _capi.stream_ptr(coeffs.device)))
+        if self._coeffs.requires_grad and torch.is_grad_enabled():
+            out = interpolation_base.PathEvalGrad.apply(self._coeffs, _capi.PATH_LINEAR, self._derivs, knots, tq,
+                                                        bool(deriv), C)
+        else:
+            out = interpolation_base.path_eval_raw(_capi.PATH_LINEAR, coeffs, self._derivs, knots, tq, deriv, C)
         return out.reshape(*coeffs.shape[:-2], *t.shape, C)
 
     def evaluate(self, t):

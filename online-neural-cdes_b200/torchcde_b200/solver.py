@@ -186,6 +186,7 @@ class _FixedSolve(torch.autograd.Function):
         ctx.X, ctx.spec, ctx.method, ctx.precision, ctx.sched = X, spec, method, precision, sched
         ctx.saved_buf = saved
         ctx.shape = (B, H, C)
+        ctx.coeffs_shape = coeffs_for_graph.shape
         ctx.n_params = len(params)
         return z_out
 
@@ -194,8 +195,7 @@ class _FixedSolve(torch.autograd.Function):
         B, H, C = ctx.shape
         spec = ctx.spec
         dev = grad_out.device
-        if ctx.needs_input_grad[6]:
-            raise NotImplementedError("gradients with respect to the control path coefficients are not implemented")
+        want_path_grad = ctx.needs_input_grad[6]
         problem, keep = _build_problem(ctx.X, spec, B, H, C, ctx.method, ctx.precision, ctx.sched)
         L = _capi.lib()
         g = grad_out.contiguous()
@@ -214,15 +214,19 @@ class _FixedSolve(torch.autograd.Function):
             j = first_of_slot.setdefault(spec.slots[i], i)
             gW[i] = by_layer_w[j].data_ptr()
             gb[i] = by_layer_b[j].data_ptr() if j in by_layer_b else None
-        wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 1)
-        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        # gradient w.r.t. the path coefficients (stacked CDEs, test_tricks.py:54-106): accumulated by the library into zeros
+        grad_coeffs = torch.zeros_like(ctx.X._coeffs, memory_format=torch.contiguous_format) if want_path_grad else None
+        wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 2 if want_path_grad else 1)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
         launches = ctypes.c_int64(0)
         _capi.check(L.ncde_solve_bwd(ctypes.byref(problem), g.data_ptr(), ctx.saved_buf.data_ptr(), grad_z0.data_ptr(),
-                                     gW, gb, None, work.data_ptr(), wbytes, ctypes.byref(launches),
+                                     gW, gb, _capi.ptr(grad_coeffs), work.data_ptr(), wbytes, ctypes.byref(launches),
                                      _capi.stream_ptr(dev)))
         last_launches["bwd"] = launches.value
         ctx.saved_buf = None
-        return (None, None, None, None, None, grad_z0, None) + tuple(grads)
+        if want_path_grad:
+            grad_coeffs = grad_coeffs.reshape(ctx.coeffs_shape)
+        return (None, None, None, None, None, grad_z0, grad_coeffs) + tuple(grads)
 
 
 class _AdjointFixedSolve(torch.autograd.Function):
@@ -257,8 +261,6 @@ class _AdjointFixedSolve(torch.autograd.Function):
         spec, t_host = ctx.spec, ctx.t_host
         adj_method, adj_options = ctx.adj
         dev = grad_out.device
-        if ctx.needs_input_grad[8]:
-            raise NotImplementedError("gradients with respect to the control path coefficients are not implemented")
         # backward schedule, last interval first, built in reversed time exactly like _check_inputs does (misc.py:262-283)
         T = int(t_host.numel())
         scheds = []
@@ -374,6 +376,25 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         if w.dtype != torch.float32:
             raise NotImplementedError("vector field parameters must be float32")
 
+    if coeffs.requires_grad and torch.is_grad_enabled():
+        if adjoint:
+            # solver.py:201-221: path buffers that need gradients must be listed in adjoint_params, else they get none
+            listed = [id(q) for q in (kwargs.get('adjoint_params') or ())]
+            if any(id(buf) in listed for buf in X.buffers()):
+                raise NotImplementedError("gradients with respect to the control path through the continuous adjoint "
+                                          "are not implemented; use adjoint=False")
+            warnings.warn("One of the inputs to the control path X requires gradients but is not listed in "
+                          "`options['adjoint_params']`. This is probably a mistake: it will not receive a gradient "
+                          "when using the adjoint vector_field_type. Either have the input not require gradients (if "
+                          "that was unintended), or include it (and every other parameter needing gradients) in "
+                          "`adjoint_params`.")
+            coeffs = coeffs.detach()
+        else:
+            if precision != 'fp32':
+                raise NotImplementedError("gradients with respect to the control path need options['precision']='fp32'")
+            if getattr(X, "gradient_matching_eps", None) is not None:
+                raise NotImplementedError("gradients with respect to a gradient-matched (smoothed) control path are "
+                                          "not implemented")
     if method == 'dopri5':
         from . import adaptive
         out = adaptive.solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs)
