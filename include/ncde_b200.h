@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NCDE_ABI_VERSION 2
+#define NCDE_ABI_VERSION 3
 #define NCDE_MAX_LAYERS 8
 #define NCDE_MAX_STAGES 7
 
@@ -36,6 +36,12 @@ enum ncde_dtype { NCDE_F32 = 0, NCDE_F64 = 1 };
 enum ncde_path_kind { NCDE_PATH_LINEAR = 0, NCDE_PATH_CUBIC = 1 };
 enum ncde_method { NCDE_EULER = 0, NCDE_RK4_38 = 1, NCDE_DOPRI5 = 2 };
 enum ncde_act { NCDE_ACT_NONE = 0, NCDE_ACT_RELU = 1, NCDE_ACT_TANH = 2 };
+/* how the control enters the vector field (`vector_field_type` of torchcde.cdeint, modules/torchcde/torchcde/solver.py:112-137):
+ * MATMUL      dz/dt = f(z) . dX/dt                 f: H -> H*C, contracted with the path derivative
+ * EVALUATE    dz/dt = f([z, X(t)])                 f: H+C -> H, no contraction
+ * DERIVATIVE  dz/dt = f([z, dX/dt(t)])             f: H+C -> H, no contraction
+ * EVALUATE / DERIVATIVE run on the fixed-grid fp32 path (ncde_solve_fwd / ncde_solve_bwd). */
+enum ncde_vf_type { NCDE_VF_MATMUL = 0, NCDE_VF_EVALUATE = 1, NCDE_VF_DERIVATIVE = 2 };
 /* arithmetic of the final (H*C-wide) layer: fp32 FFMA, or bf16 tcgen05 tensor-core tiles with fp32 accumulate */
 enum ncde_precision { NCDE_PREC_FP32 = 0, NCDE_PREC_BF16 = 1 };
 
@@ -193,6 +199,7 @@ typedef struct ncde_problem {
     ncde_path_t path;
     ncde_fixed_grid_t grid;   /* EULER / RK4_38 */
     ncde_adaptive_t adaptive; /* DOPRI5 */
+    int32_t vf_type;          /* ncde_vf_type; for EVALUATE / DERIVATIVE mlp.in_dim[0] == H + C and the last layer has H outputs */
 } ncde_problem_t;
 
 /* Byte sizes of the two caller-provided device buffers: `saved` carries what the backward pass needs (stage

@@ -82,7 +82,8 @@ struct TcMapSet {
 constexpr int kNumSMs = 148;
 
 struct Plan {
-    int B, Bp, H, C, Cp, F, DF, DFP, Dmax;
+    int B, Bp, H, C, Cp, F, DF, DFP, Dmax;   // C / Cp: channels of the f(z).dX/dt contraction (1 / 4 when vf != MATMUL)
+    int vf, PC;                              // ncde_vf_type; channels of the control path
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
@@ -124,14 +125,29 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
                  NCDE_MAX_LAYERS);
     NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38 || p->method == NCDE_DOPRI5, NCDE_ERR_UNSUPPORTED,
                  "solve: unknown method %d", p->method);
-    pl->B = (int)p->B; pl->H = p->H; pl->C = p->C;
+    NCDE_REQUIRE(p->vf_type >= NCDE_VF_MATMUL && p->vf_type <= NCDE_VF_DERIVATIVE, NCDE_ERR_INVALID,
+                 "vector_field_type string not recognised");
+    pl->vf = p->vf_type; pl->PC = p->C;
+    if (pl->vf) {
+        // f([z, X(t)]) / f([z, dX/dt(t)]) (torchcde/solver.py:123-126): the control is part of the first layer's input and the
+        // final layer is a plain H-wide tanh layer, run by the field kernels as a contraction over ONE channel with dX/dt = 1
+        NCDE_REQUIRE(p->precision == NCDE_PREC_FP32, NCDE_ERR_UNSUPPORTED,
+                     "solve: vector_field_type evaluate / derivative runs on the fp32 path only");
+        NCDE_REQUIRE(p->method != NCDE_DOPRI5, NCDE_ERR_UNSUPPORTED,
+                     "solve: vector_field_type evaluate / derivative is implemented for the fixed-grid solvers only");
+        NCDE_REQUIRE(p->path.match == nullptr, NCDE_ERR_UNSUPPORTED,
+                     "solve: vector_field_type evaluate / derivative is not implemented for gradient-matched paths");
+        NCDE_REQUIRE(fixed_path, NCDE_ERR_UNSUPPORTED,
+                     "solve: vector_field_type evaluate / derivative is not implemented for the continuous adjoint (use adjoint=False)");
+    }
+    pl->B = (int)p->B; pl->H = p->H; pl->C = pl->vf ? 1 : p->C;
     pl->Bp = (int)round_up(p->B, kTcM);
     // channels padded to 4 (float4 epilogues) or 8 (tensor-core path: 16-byte bf16 chunks per h)
-    pl->Cp = (int)round_up(p->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
+    pl->Cp = (int)round_up(pl->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
     pl->F = m.n_layers - 1;
     pl->n_stages = p->method == NCDE_RK4_38 ? 4 : (p->method == NCDE_DOPRI5 ? 7 : 1);
-    NCDE_REQUIRE(m.in_dim[0] == p->H, NCDE_ERR_INVALID, "solve: first layer must take H=%d inputs, takes %d", p->H,
-                 m.in_dim[0]);
+    NCDE_REQUIRE(m.in_dim[0] == p->H + (pl->vf ? p->C : 0), NCDE_ERR_INVALID, "solve: first layer must take %d inputs, takes %d",
+                 p->H + (pl->vf ? p->C : 0), m.in_dim[0]);
     for (int l = 0; l < m.n_layers; ++l) {
         NCDE_REQUIRE(m.W[l] != nullptr, NCDE_ERR_INVALID, "solve: layer %d has no weight", l);
         NCDE_REQUIRE(m.in_dim[l] >= 1 && m.out_dim[l] >= 1, NCDE_ERR_INVALID, "solve: layer %d has empty shape", l);
@@ -142,8 +158,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
         pl->D[l] = m.in_dim[l];
         pl->Dp4[l] = (int)round_up(m.in_dim[l], 4);
     }
-    NCDE_REQUIRE(m.out_dim[pl->F] == p->H * p->C, NCDE_ERR_INVALID,
-                 "solve: final layer must produce H*C=%d outputs, produces %d", p->H * p->C, m.out_dim[pl->F]);
+    NCDE_REQUIRE(m.out_dim[pl->F] == p->H * pl->C, NCDE_ERR_INVALID,
+                 "solve: final layer must produce %d outputs, produces %d", p->H * pl->C, m.out_dim[pl->F]);
     NCDE_REQUIRE(m.act[pl->F] == NCDE_ACT_TANH, NCDE_ERR_UNSUPPORTED, "solve: final activation must be tanh");
     pl->DF = pl->D[pl->F];
     pl->DFP = (int)round_up(pl->DF, 16);
@@ -369,18 +385,20 @@ static size_t fwd_workspace_floats(const Plan& pl, int need_saved_scratch) {
     size_t n = pl.wpack_floats + per;
     n += (size_t)(2 + pl.n_stages) * ((size_t)pl.H * pl.Bp + per);
     if (need_saved_scratch) n += pl.stage_floats + per;
+    if (pl.vf) n += 4 * (size_t)pl.Bp + per;   // the constant "dX/dt" = (1, 0, 0, 0) of the one-channel contraction
     return n;
 }
 static size_t fwd_workspace_extra_floats(const Plan& pl, int64_t n_steps, int need_saved_scratch) {
     size_t per = 256 / 4;
     size_t n = (size_t)n_steps * pl.n_stages + per;                                  // device copy of the stage times
-    if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * pl.Cp * pl.Bp + per;  // dX/dt of every stage
+    if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * (pl.vf ? pl.PC : pl.Cp) * pl.Bp + per;  // dX/dt (vf: X or dX/dt) of every stage
     return n;
 }
 static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps, const SwapPlan* sp = nullptr) {
     size_t per = 256 / 4;
     size_t n = pl.wpack_floats + per;
     n += (size_t)(1 + pl.n_stages) * (round_up(pl.H, 4) * (size_t)pl.Bp + per);
+    if (pl.vf) n += 4 * (size_t)pl.Bp + per;
     if (sp)   // path gradient: swapped final-layer pack, dL/d(dX/dt) of every stage of one step
         n += sp->w3t_floats + sp->b3p_floats + 2 * per + (size_t)pl.n_stages * ((size_t)pl.C * pl.Bp + per);
     n += (size_t)pl.n_hg * pl.Bp * pl.DFP + per;
@@ -581,7 +599,7 @@ extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backwa
     if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
     SwapPlan sp;
-    if (backward == 2 && (pl.tc || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
+    if (backward == 2 && (pl.tc || pl.vf || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
     size_t fl = backward ? bwd_workspace_floats(pl, p->grid.n_steps, backward == 2 ? &sp : nullptr)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
@@ -616,7 +634,13 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     float* scratch_stage = need_grad ? nullptr : cv.take(pl.stage_floats);
     const int64_t n_st_total = g.n_steps * NS;
     float* d_stage_t = cv.take((size_t)(n_st_total > 0 ? n_st_total : 1));
-    float* dx_all = need_grad ? nullptr : cv.take((size_t)n_st_total * pl.Cp * pl.Bp);
+    const int dx_rows = pl.vf ? pl.PC : pl.Cp;   // rows per stage of the path-only precompute
+    float* dx_all = need_grad ? nullptr : cv.take((size_t)n_st_total * dx_rows * pl.Bp);
+    float* e0 = pl.vf ? cv.take(4 * (size_t)pl.Bp) : nullptr;
+    if (e0) {
+        fill_e0_kernel<<<(unsigned)ceil_div(4 * (int64_t)pl.Bp, 256), 256, 0, st>>>(e0, pl.Bp);
+        ++launches;
+    }
 
     rc = pack_weights(p, pl, wpack, 0, st, &launches);
     if (rc != NCDE_OK) return rc;
@@ -666,6 +690,13 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         da.dx_base = need_grad ? (float*)saved + pl.dx_off : dx_all;
         da.stage_stride = need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp;
         da.row_major = use_tc ? 1 : 0;
+        if (pl.vf) {
+            // X(t) or dX/dt(t) goes straight into rows H.. of the first layer's (saved) input record
+            da.C = da.Cp = pl.PC;
+            da.value = pl.vf == NCDE_VF_EVALUATE;
+            da.dx_base = need_grad ? (float*)saved + pl.act_off[0] + (size_t)pl.H * pl.Bp : dx_all;
+            da.stage_stride = need_grad ? pl.stage_floats : (size_t)pl.PC * pl.Bp;
+        }
         NCDE_REQUIRE(n_st_total <= 2147483647 && ceil_div(pl.B, 32) <= 65535, NCDE_ERR_UNSUPPORTED, "solve_fwd: grid too large");
         dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
         ++launches;
@@ -716,8 +747,13 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             ha.dt = dt;
             ha.yT = yT[cur];
             for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
-            float* dx_stage = need_grad ? stage + pl.dx_off : dx_all + (size_t)(s * NS + i) * pl.Cp * pl.Bp;
+            float* dx_stage = need_grad ? stage + pl.dx_off : dx_all + (size_t)(s * NS + i) * dx_rows * pl.Bp;
             ha.dXT = nullptr;  // precomputed by dx_all_kernel
+            if (pl.vf) {
+                ha.n_u = pl.PC;
+                ha.uT = need_grad ? stage + pl.act_off[0] + (size_t)pl.H * pl.Bp : dx_stage;
+                dx_stage = e0;
+            }
             ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
             ha.path.t = g.stage_t[s * NS + i];
             if (pl.tc_hid) {
@@ -816,6 +852,8 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     if (rc != NCDE_OK) return rc;
     SwapPlan sp;
     if (grad_coeffs) {
+        NCDE_REQUIRE(!pl.vf, NCDE_ERR_UNSUPPORTED,
+                     "solve_bwd: the gradient w.r.t. the control path is implemented for vector_field_type matmul only");
         NCDE_REQUIRE(!pl.tc, NCDE_ERR_UNSUPPORTED,
                      "solve_bwd: the gradient w.r.t. the control path is implemented for precision fp32 only");
         NCDE_REQUIRE(p->path.match == nullptr, NCDE_ERR_UNSUPPORTED,
@@ -838,6 +876,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     float* gyT = cv.take(nHBp);
     float* gkT[NCDE_MAX_STAGES] = {};
     for (int i = 0; i < NS; ++i) gkT[i] = cv.take(nHBp);
+    float* e0 = pl.vf ? cv.take(4 * (size_t)pl.Bp) : nullptr;
     float* W3Ts = nullptr;
     float* b3ps = nullptr;
     float* gdXT[NCDE_MAX_STAGES] = {};
@@ -874,6 +913,10 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         if (rc != NCDE_OK) return rc;
     }
 
+    if (e0) {
+        fill_e0_kernel<<<(unsigned)ceil_div(4 * (int64_t)pl.Bp, 256), 256, 0, st>>>(e0, pl.Bp);
+        ++launches;
+    }
     NCDE_CUDA_OK(cudaMemsetAsync(gyT, 0, nHB * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, (size_t)pl.n_bt * pl.Np * pl.DFP * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(db3acc, 0, (size_t)pl.n_bt * pl.Np * 4, st));
@@ -1032,7 +1075,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         for (int i = NS - 1; i >= 0; --i) {
             const float* stage = (const float*)saved + (size_t)(s * NS + i) * pl.stage_floats;
             fa.actT = stage + pl.act_off[pl.F];
-            fa.dXT = stage + pl.dx_off;
+            fa.dXT = pl.vf ? e0 : stage + pl.dx_off;
             fa.gkT = gkT[i];
             {
                 ProfScope ps(NCDE_PROF_FIELD_BWD, st);

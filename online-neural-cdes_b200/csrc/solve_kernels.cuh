@@ -66,6 +66,10 @@ struct HiddenFwdArgs {
     const float* yT;
     const float* kT[NCDE_MAX_STAGES];
     float* actT[NCDE_MAX_LAYERS + 1];  // actT[l] = [D[l] (padded to 4)][Bp], l = 0..F, for THIS stage
+    // vector_field_type evaluate / derivative: rows H..H+n_u-1 of the first layer's input are X(t) / dX/dt(t), read from
+    // uT [n_u][Bp] (precomputed for every stage by dx_all_kernel; may alias those rows of actT[0])
+    const float* uT;
+    int n_u;
     float* dXT;                        // [Cp][Bp]  (tensor-core path, dx_row_major: [Bp][Cp])
     int dx_row_major;
     float* ddXT;                       // [Cp][Bp] or null: d2X/dt2 (cubic paths; time-gradient component of the adjoint)
@@ -269,6 +273,29 @@ __device__ __forceinline__ float path_derivative(const PathArgs& p, int idx, flo
     return __fadd_rn(bb, __fmul_rn(inner, frac));
 }
 
+// X(t) for one (row, channel) — LinearInterpolation.evaluate / NaturalCubicSpline.evaluate in the reference's operation
+// order (torchcde/interpolation_linear.py:221-229, interpolation_cubic.py:324-329); un-smoothed paths only
+__device__ __forceinline__ float path_value(const PathArgs& p, int idx, float frac, int64_t b, int c, int C) {
+    if (p.kind == NCDE_PATH_LINEAR) {
+        const float* cs = p.coeffs + (int64_t)b * p.K * C;
+        const float lo = cs[(int64_t)idx * C + c], hi = cs[(int64_t)(idx + 1) * C + c];
+        const float width = __fsub_rn(p.knots[idx + 1], p.knots[idx]);
+        return __fadd_rn(lo, __fdiv_rn(__fmul_rn(frac, __fsub_rn(hi, lo)), width));
+    }
+    const float* row = p.coeffs + ((int64_t)b * (p.K - 1) + idx) * 4 * C;
+    const float aa = row[c], bb = row[C + c], two_c = row[2 * C + c], three_d = row[3 * C + c];
+    float inner = __fadd_rn(__fmul_rn(0.5f, two_c), __fdiv_rn(__fmul_rn(three_d, frac), 3.f));
+    inner = __fadd_rn(bb, __fmul_rn(inner, frac));
+    return __fadd_rn(aa, __fmul_rn(inner, frac));
+}
+
+// the constant "path derivative" of the one-channel contraction that vector_field_type evaluate / derivative run through the
+// field kernels with: channel 0 = 1, padding channels = 0
+__global__ void fill_e0_kernel(float* __restrict__ e0, int Bp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * (int64_t)Bp) e0[i] = i < Bp ? 1.f : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // dx_all: dX/dt at EVERY stage time of the fixed grid in one launch (it depends on the path only, not on the state,
 // so it is taken off the sequential stage chain).  CTA (stage, 32-row tile): knot lookup once (bucketize - 1 clamp,
@@ -282,6 +309,7 @@ struct DxAllArgs {
     float* dx_base;            // first stage's dXT
     size_t stage_stride;       // floats between consecutive stages' dXT
     int row_major;             // tensor-core path: [Bp][Cp] instead of [Cp][Bp]
+    int value;                 // X(t) instead of dX/dt(t) (vector_field_type evaluate)
 };
 
 __global__ void __launch_bounds__(256) dx_all_kernel(const __grid_constant__ DxAllArgs a) {
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(256) dx_all_kernel(const __grid_constant__ DxA
             const int r = i / cw, c = c0 + i % cw;
             const int64_t b = b0 + r;
             float v = 0.f;
-            if (b < a.B && c < a.C) v = path_derivative(a.path, idxk, frac, b, c, a.C);
+            if (b < a.B && c < a.C) v = a.value ? path_value(a.path, idxk, frac, b, c, a.C) : path_derivative(a.path, idxk, frac, b, c, a.C);
             if (a.row_major) { if (b < a.B) out[(size_t)b * a.Cp + c] = v; }
             else tile[r][c - c0] = v;
         }
@@ -584,6 +612,19 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             a.actT[0][off] = v;
         }
         buf0[h * R + r] = v;
+    }
+    if (a.n_u) {
+        float* __restrict__ dst = a.actT[0] + (size_t)a.H * a.Bp;
+        for (int idx = tid; idx < a.n_u * R; idx += kThreads) {
+            const int c = idx / R, r = idx % R;
+            const int64_t b = b0 + r;
+            float v = 0.f;
+            if (b < a.B) {
+                v = a.uT[(size_t)c * a.Bp + b];
+                if (dst != a.uT) dst[(size_t)c * a.Bp + b] = v;
+            }
+            buf0[(a.H + c) * R + r] = v;
+        }
     }
     // 2. dX/dt at the stage time -> dXT[c][b] (zero in the padded channels); skipped when dx_all_kernel already did it
     if (a.dXT) {

@@ -20,6 +20,7 @@ PATH_LINEAR, PATH_CUBIC = 0, 1
 EULER, RK4_38, DOPRI5 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1
+VF_MATMUL, VF_EVALUATE, VF_DERIVATIVE = 0, 1, 2
 FLAG_NAN_TIME, FLAG_NONFINITE, FLAG_DT_UNDERFLOW, FLAG_MAX_STEPS = 1, 2, 4, 8
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -66,7 +67,8 @@ class Adaptive(ctypes.Structure):
 class Problem(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int64), ("H", ctypes.c_int32), ("C", ctypes.c_int32),
                 ("method", ctypes.c_int32), ("precision", ctypes.c_int32),
-                ("mlp", Mlp), ("path", Path), ("grid", FixedGrid), ("adaptive", Adaptive)]
+                ("mlp", Mlp), ("path", Path), ("grid", FixedGrid), ("adaptive", Adaptive),
+                ("vf_type", ctypes.c_int32)]
 
 
 _lib = None
@@ -132,7 +134,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("ncde_abi_version",):
             fn.restype = i32
-    if L.ncde_abi_version() != 2:
+    if L.ncde_abi_version() != 3:
         raise RuntimeError("libncde_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -53,14 +53,15 @@ class MlpSpec:
         return out
 
     def reference_forward(self, z, hidden, channels):
-        """The same map written with torch ops; used only to validate a lowering once, never on the solve path."""
+        """The same map written with torch ops; used only to validate a lowering once, never on the solve path.
+        ``channels`` None: vector_field_type evaluate / derivative (the output is the (B, H) state derivative itself)."""
         for w, b, a in zip(self.weights, self.biases, self.acts):
             z = torch.nn.functional.linear(z, w, b)
             if a == _capi.ACT_RELU:
                 z = z.relu()
             elif a == _capi.ACT_TANH:
                 z = z.tanh()
-        return z.view(-1, hidden, channels)
+        return z.view(-1, hidden) if channels is None else z.view(-1, hidden, channels)
 
 
 def _from_sequential(mods):
@@ -139,19 +140,22 @@ def _from_fx(func):
 _CACHE = {}
 
 
-def lower(func, hidden, channels):
-    """Return the MlpSpec of ``func``; validated once per module object against func itself."""
+def lower(func, hidden, channels, vector_field_type="matmul"):
+    """Return the MlpSpec of ``func``; validated once per module object against func itself.  For vector_field_type
+    'evaluate' / 'derivative' (torchcde/solver.py:123-126) func maps [z, X(t) | dX/dt(t)]: (B, H+C) -> (B, H)."""
     key = id(func)
+    matmul = vector_field_type == "matmul"
     hit = _CACHE.get(key)
-    if hit is not None and hit[0]() is func and hit[2] == (hidden, channels):
+    if hit is not None and hit[0]() is func and hit[2] == (hidden, channels, vector_field_type):
         return hit[1]
     nfe_before = getattr(func, "nfe", None)
     if hasattr(func, "ncde_mlp_spec"):
         layers = [[w, b, _ACT[a] if isinstance(a, str) else a] for (w, b, a) in func.ncde_mlp_spec()]
     elif isinstance(getattr(func, "net_to_hh", None), torch.nn.Sequential) and \
             isinstance(getattr(func, "tanh_output_layer", None), torch.nn.Sequential):
-        if getattr(func, "vector_field_type", "matmul") != "matmul":
-            raise NotImplementedError("only vector_field_type='matmul' vector fields are supported")
+        if getattr(func, "vector_field_type", vector_field_type) != vector_field_type:
+            raise ValueError("the vector field was built for vector_field_type='{}' but cdeint was called with '{}'".format(
+                func.vector_field_type, vector_field_type))
         layers = _from_sequential(list(func.net_to_hh) + list(func.tanh_output_layer))
     elif isinstance(func, torch.nn.Module):
         layers = _from_fx(func)
@@ -160,17 +164,21 @@ def lower(func, hidden, channels):
     if not layers:
         raise NotImplementedError("vector field has no Linear layer")
     spec = MlpSpec([tuple(l) for l in layers])
-    if spec.weights[0].shape[1] != hidden or spec.weights[-1].shape[0] != hidden * channels:
-        raise ValueError("vector field maps {} -> {} but the solve needs {} -> {}*{}".format(
-            spec.weights[0].shape[1], spec.weights[-1].shape[0], hidden, hidden, channels))
+    spec.vector_field_type = vector_field_type
+    spec.channels = channels
+    d_in = hidden if matmul else hidden + channels
+    d_out = hidden * channels if matmul else hidden
+    if spec.weights[0].shape[1] != d_in or spec.weights[-1].shape[0] != d_out:
+        raise ValueError("vector field maps {} -> {} but the solve (vector_field_type='{}') needs {} -> {}".format(
+            spec.weights[0].shape[1], spec.weights[-1].shape[0], vector_field_type, d_in, d_out))
     if spec.acts[-1] != _capi.ACT_TANH:
         raise NotImplementedError("the vector field must end in tanh (as every vector field of the reference does)")
     # one-off structural validation on three probe rows
     with torch.no_grad():
         w0 = spec.weights[0]
-        probe = torch.linspace(-1.0, 1.0, 3 * hidden, dtype=w0.dtype, device=w0.device).view(3, hidden)
+        probe = torch.linspace(-1.0, 1.0, 3 * d_in, dtype=w0.dtype, device=w0.device).view(3, d_in)
         want = func(torch.zeros((), dtype=w0.dtype, device=w0.device), probe)
-        got = spec.reference_forward(probe, hidden, channels)
+        got = spec.reference_forward(probe, hidden, channels if matmul else None)
         if want.shape != got.shape or not torch.allclose(want, got, rtol=1e-4, atol=1e-5):
             raise NotImplementedError("vector field could not be lowered to a Linear/activation chain faithfully")
     if nfe_before is not None:
@@ -180,5 +188,5 @@ def lower(func, hidden, channels):
         ref = weakref.ref(func)
     except TypeError:
         ref = (lambda f: (lambda: f))(func)
-    _CACHE[key] = (ref, spec, (hidden, channels))
+    _CACHE[key] = (ref, spec, (hidden, channels, vector_field_type))
     return spec

@@ -95,9 +95,13 @@ def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+_VF_TYPES = {"matmul": _capi.VF_MATMUL, "evaluate": _capi.VF_EVALUATE, "derivative": _capi.VF_DERIVATIVE}
+
+
 def _build_problem(X, spec, B, H, C, method, precision, sched):
     p = _capi.Problem()
     p.B, p.H, p.C = B, H, C
+    p.vf_type = _VF_TYPES[getattr(spec, "vector_field_type", "matmul")]
     p.method = _METHODS[method]
     p.precision = precision
     m = p.mlp
@@ -161,7 +165,7 @@ class _FixedSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, spec, method, precision, sched, z0, coeffs_for_graph, *params):
         B, H = z0.shape
-        C = spec.weights[-1].shape[0] // H
+        C = spec.channels
         dev = z0.device
         problem, keep = _build_problem(X, spec, B, H, C, method, precision, sched)
         L = _capi.lib()
@@ -237,7 +241,7 @@ class _AdjointFixedSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, spec, method, precision, sched, adj, t_host, z0, coeffs_for_graph, *params):
         B, H = z0.shape
-        C = spec.weights[-1].shape[0] // H
+        C = spec.channels
         dev = z0.device
         problem, keep = _build_problem(X, spec, B, H, C, method, precision, sched)
         L = _capi.lib()
@@ -321,8 +325,6 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
     """
     if vector_field_type not in ['matmul', 'evaluate', 'derivative']:
         raise ValueError("vector_field_type string not recognised")
-    if vector_field_type != 'matmul':
-        raise NotImplementedError("vector_field_type='{}' is not implemented by the fused solve".format(vector_field_type))
     if not isinstance(X, (LinearInterpolation, NaturalCubicSpline)):
         raise NotImplementedError("X must be a torchcde_b200 LinearInterpolation or NaturalCubicSpline")
     if not isinstance(z0, torch.Tensor):
@@ -370,7 +372,22 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         raise ValueError("batch dimensions of z0 {} and of the control path {} differ".format(
             tuple(batch_shape), tuple(coeffs.shape[:-2])))
     C = coeffs.shape[-1] // (4 if isinstance(X, NaturalCubicSpline) else 1)
-    spec = lowering.lower(func, H, C)
+    spec = lowering.lower(func, H, C, vector_field_type)
+    if vector_field_type != 'matmul':
+        # f([z, X(t)]) / f([z, dX/dt(t)]) (solver.py:123-126): fixed-grid fp32 solves, gradients by backpropagation through the steps
+        if method == 'dopri5':
+            raise NotImplementedError("vector_field_type='{}' is implemented for the fixed-grid solvers (euler, rk4) "
+                                      "only".format(vector_field_type))
+        if adjoint:
+            raise NotImplementedError("vector_field_type='{}' is not implemented for the continuous adjoint; pass "
+                                      "adjoint=False".format(vector_field_type))
+        if precision != 'fp32':
+            raise NotImplementedError("vector_field_type='{}' runs in fp32 only".format(vector_field_type))
+        if getattr(X, "gradient_matching_eps", None) is not None:
+            raise NotImplementedError("vector_field_type='{}' is not implemented for gradient-matched paths".format(
+                vector_field_type))
+        if coeffs.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("gradients with respect to the control path need vector_field_type='matmul'")
     for w in spec.weights:
         _capi.require_cuda(w)
         if w.dtype != torch.float32:

@@ -656,14 +656,19 @@ class _Adjoint(torch.autograd.Function):
 
 
 def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, options=None, stats=None,
-           adjoint_rtol=None, adjoint_atol=None, adjoint_options=None):
-    """tcde/solver.py:140-238 for a single batch dimension, 'matmul' vector fields and tensor state:
-    g(t, z) = func(t, z) @ dX/dt(t); returns (B, len(t), H).  Defaults atol=1e-6 / rtol=1e-4 (:193-196);
+           adjoint_rtol=None, adjoint_atol=None, adjoint_options=None, vector_field_type="matmul"):
+    """tcde/solver.py:140-238 for a single batch dimension and tensor state:
+    'matmul': g(t, z) = func(t, z) @ dX/dt(t); 'evaluate' / 'derivative': g(t, z) = func(t, [z, X(t) | dX/dt(t)])
+    (tcde/solver.py:112-137); returns (B, len(t), H).  Defaults atol=1e-6 / rtol=1e-4 (:193-196);
     adjoint_* default to the forward values with `norm` dropped (tdeq/adjoint.py:159-171)."""
+    if vector_field_type not in ("matmul", "evaluate", "derivative"):
+        raise ValueError("vector_field_type string not recognised")
     atol = 1e-6 if atol is None else atol
     rtol = 1e-4 if rtol is None else rtol
 
     def g(tt, z):
+        if vector_field_type != "matmul":
+            return func(tt, torch.cat([z, getattr(X, vector_field_type)(tt)], -1))
         return (func(tt, z) @ X.derivative(tt).unsqueeze(-1)).squeeze(-1)
 
     if adjoint:
@@ -839,20 +844,25 @@ class SharedMLPField(torch.nn.Module):
     """src/ncde/vector_fields/base.py:64-69,83-104 — note the *same* Linear object is repeated for every middle
     layer, so its weight gradient accumulates over the repeats."""
 
-    def __init__(self, input_dim, hidden_dim, hidden_hidden_dim, num_layers):
+    def __init__(self, input_dim, hidden_dim, hidden_hidden_dim, num_layers, vector_field_type="matmul"):
         super().__init__()
         self.input_dim, self.hidden_dim = input_dim, hidden_dim
-        layers = [torch.nn.Linear(hidden_dim, hidden_hidden_dim), torch.nn.ReLU()]
+        # base.py:56-60: evaluate / derivative fields take [z, control] and return the state derivative directly
+        self.matmul = vector_field_type == "matmul"
+        self.vector_field_type = vector_field_type
+        initial_dim = hidden_dim if self.matmul else hidden_dim + input_dim
+        output_dim = hidden_dim * input_dim if self.matmul else hidden_dim
+        layers = [torch.nn.Linear(initial_dim, hidden_hidden_dim), torch.nn.ReLU()]
         if num_layers > 1:
             layers += [torch.nn.Linear(hidden_hidden_dim, hidden_hidden_dim), torch.nn.ReLU()] * (num_layers - 1)
         self.net_to_hh = torch.nn.Sequential(*layers)
-        self.tanh_output_layer = torch.nn.Sequential(torch.nn.Linear(hidden_hidden_dim, hidden_dim * input_dim),
-                                                     torch.nn.Tanh())
+        self.tanh_output_layer = torch.nn.Sequential(torch.nn.Linear(hidden_hidden_dim, output_dim), torch.nn.Tanh())
         self.nfe = 0
 
     def forward(self, t, h):
         self.nfe += 1
-        return self.tanh_output_layer(self.net_to_hh(h)).view(-1, self.hidden_dim, self.input_dim)
+        out = self.tanh_output_layer(self.net_to_hh(h))
+        return out.view(-1, self.hidden_dim, self.input_dim) if self.matmul else out
 
 
 class ToyField(torch.nn.Module):
