@@ -155,6 +155,12 @@ typedef struct ncde_mlp {
     int32_t slot[NCDE_MAX_LAYERS];
     const float* W[NCDE_MAX_LAYERS];    /* device, (out_dim, in_dim) row-major — torch.nn.Linear layout */
     const float* bias[NCDE_MAX_LAYERS]; /* device, (out_dim) or NULL */
+    /* Optional multiplicative gate on the last layer (MinimalGatedVectorField, src/ncde/vector_fields/gating.py:7-32):
+     * output = sigmoid(W_gate a + bias_gate) * tanh(W[last] a + bias[last]), W_gate shaped like W[last].  NULL: no gate.
+     * Needs n_layers < NCDE_MAX_LAYERS: ncde_solve_bwd accumulates the gate's gradients into gW[n_layers] / gbias[n_layers].
+     * Fixed-grid fp32 path (ncde_solve_fwd / ncde_solve_bwd), at most 64 channels. */
+    const float* W_gate;
+    const float* bias_gate;
 } ncde_mlp_t;
 
 typedef struct ncde_path {

@@ -84,6 +84,7 @@ constexpr int kNumSMs = 148;
 struct Plan {
     int B, Bp, H, C, Cp, F, DF, DFP, Dmax;   // C / Cp: channels of the f(z).dX/dt contraction (1 / 4 when vf != MATMUL)
     int vf, PC;                              // ncde_vf_type; channels of the control path
+    int gated;                               // sigmoid-gated final layer: Cp = 2 * (C padded to 2) interleaved columns per h
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
@@ -144,6 +145,15 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     pl->Bp = (int)round_up(p->B, kTcM);
     // channels padded to 4 (float4 epilogues) or 8 (tensor-core path: 16-byte bf16 chunks per h)
     pl->Cp = (int)round_up(pl->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
+    pl->gated = m.W_gate != nullptr;
+    if (pl->gated) {
+        NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_path, NCDE_ERR_UNSUPPORTED,
+                     "solve: gated vector fields run on the fixed-grid fp32 path only (no adaptive solver, no continuous adjoint)");
+        NCDE_REQUIRE(m.n_layers < NCDE_MAX_LAYERS, NCDE_ERR_UNSUPPORTED, "solve: gated vector fields take at most %d layers",
+                     NCDE_MAX_LAYERS - 1);
+        pl->Cp = 2 * (int)round_up(pl->C, 2);   // (sigmoid, tanh) column pairs
+        NCDE_REQUIRE(pl->Cp <= 128, NCDE_ERR_UNSUPPORTED, "solve: gated vector fields support at most 64 channels, got %d", pl->C);
+    }
     pl->F = m.n_layers - 1;
     pl->n_stages = p->method == NCDE_RK4_38 ? 4 : (p->method == NCDE_DOPRI5 ? 7 : 1);
     NCDE_REQUIRE(m.in_dim[0] == p->H + (pl->vf ? p->C : 0), NCDE_ERR_INVALID, "solve: first layer must take %d inputs, takes %d",
@@ -439,7 +449,7 @@ static int pack_weights(const ncde_problem_t* p, const Plan& pl, float* wpack, i
     } else {
         const int64_t n = (int64_t)pl.Np * pl.DFP;
         pack_final_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
-            m.W[pl.F], m.bias[pl.F], wpack + pl.off_W3T, with_rowmajor ? wpack + pl.off_W3R : nullptr,
+            m.W[pl.F], m.bias[pl.F], m.W_gate, m.bias_gate, wpack + pl.off_W3T, with_rowmajor ? wpack + pl.off_W3R : nullptr,
             wpack + pl.off_b3p, pl.H, pl.C, pl.Cp, pl.DF, pl.DFP, pl.Np);
     }
     ++*launches;
@@ -552,6 +562,31 @@ static void fill_field_args(FieldArgs& fa, const Plan& pl, const float* wpack) {
     fa.W3T = wpack + pl.off_W3T; fa.W3R = wpack + pl.off_W3R; fa.b3p = wpack + pl.off_b3p;
 }
 
+// fp32 final-layer launches of the fixed-grid path (plain or sigmoid-gated epilogue)
+static int opt_in_field(const Plan& pl, bool backward) {
+    if (backward) {
+        if (pl.gated) return pl.TM == 8 ? opt_in_smem(field_bwd_kernel<8, true>, pl.bwd_smem) : opt_in_smem(field_bwd_kernel<4, true>, pl.bwd_smem);
+        return pl.TM == 8 ? opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem) : opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
+    }
+    if (pl.gated) return pl.TM == 8 ? opt_in_smem(field_fwd_kernel<8, true>, pl.fwd_smem) : opt_in_smem(field_fwd_kernel<4, true>, pl.fwd_smem);
+    return pl.TM == 8 ? opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem) : opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem);
+}
+static cudaError_t launch_field(const Plan& pl, const FieldArgs& fa, bool backward, cudaStream_t st) {
+    const dim3 fg(pl.n_hg, pl.n_bt);
+    if (backward) {
+        if (pl.gated)
+            return pl.TM == 8 ? launch_pdl(field_bwd_kernel<8, true>, fg, dim3(kThreads), pl.bwd_smem, st, fa)
+                              : launch_pdl(field_bwd_kernel<4, true>, fg, dim3(kThreads), pl.bwd_smem, st, fa);
+        return pl.TM == 8 ? launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa)
+                          : launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa);
+    }
+    if (pl.gated)
+        return pl.TM == 8 ? launch_pdl(field_fwd_kernel<8, true>, fg, dim3(kThreads), pl.fwd_smem, st, fa)
+                          : launch_pdl(field_fwd_kernel<4, true>, fg, dim3(kThreads), pl.fwd_smem, st, fa);
+    return pl.TM == 8 ? launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa)
+                      : launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa);
+}
+
 }  // namespace ncde
 
 using namespace ncde;
@@ -599,7 +634,7 @@ extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backwa
     if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
     SwapPlan sp;
-    if (backward == 2 && (pl.tc || pl.vf || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
+    if (backward == 2 && (pl.tc || pl.vf || pl.gated || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
     size_t fl = backward ? bwd_workspace_floats(pl, p->grid.n_steps, backward == 2 ? &sp : nullptr)
                          : fwd_workspace_floats(pl, 1) + fwd_workspace_extra_floats(pl, p->grid.n_steps, 1);
     return fl * 4 + 4096;
@@ -647,8 +682,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
 
     const bool use_tc = pl.tc != 0;
     if (use_tc) rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem);
-    else if (pl.TM == 8) rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem);
-    else rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem);
+    else rc = opt_in_field(pl, false);
     if (rc != NCDE_OK) return rc;
 
     const dim3 tb(32, 8), tg((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
@@ -796,9 +830,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                     { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
-                    const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
-                    else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                    NCDE_CUDA_OK(launch_field(pl, fa, false, st));
                     ++launches;
                 }
             }
@@ -852,8 +884,8 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     if (rc != NCDE_OK) return rc;
     SwapPlan sp;
     if (grad_coeffs) {
-        NCDE_REQUIRE(!pl.vf, NCDE_ERR_UNSUPPORTED,
-                     "solve_bwd: the gradient w.r.t. the control path is implemented for vector_field_type matmul only");
+        NCDE_REQUIRE(!pl.vf && !pl.gated, NCDE_ERR_UNSUPPORTED,
+                     "solve_bwd: the gradient w.r.t. the control path is implemented for un-gated vector_field_type matmul only");
         NCDE_REQUIRE(!pl.tc, NCDE_ERR_UNSUPPORTED,
                      "solve_bwd: the gradient w.r.t. the control path is implemented for precision fp32 only");
         NCDE_REQUIRE(p->path.match == nullptr, NCDE_ERR_UNSUPPORTED,
@@ -903,8 +935,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;
     if (use_tc) rc = (pl.bwd_ew == 16 ? opt_in_smem(tc_field_bwd_kernel<16>, pl.bwd_smem) : opt_in_smem(tc_field_bwd_kernel<8>, pl.bwd_smem));
-    else if (pl.TM == 8) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem);
-    else rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem);
+    else rc = opt_in_field(pl, true);
     if (rc != NCDE_OK) return rc;
     TcMapSet ms;
     if (use_tc && g.n_steps > 0) {
@@ -1101,9 +1132,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                     { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                     ++launches;
                 } else {
-                    const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
-                    else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+                    NCDE_CUDA_OK(launch_field(pl, fa, true, st));
                     ++launches;
                 }
             }
@@ -1240,10 +1269,22 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     ++launches;
     {
         const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
-        unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[pl.F], gbias[pl.F], pl.H,
-                                                                             pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF, pl.DFP,
-                                                                             pl.Np, pl.n_bt);
-        ++launches;
+        if (pl.gated) {
+            // interleaved columns: 2c = sigmoid head (gradients go to gW[n_layers] / gbias[n_layers]), 2c + 1 = tanh head
+            NCDE_REQUIRE(gW[m.n_layers] != nullptr, NCDE_ERR_INVALID, "solve_bwd: gW[n_layers] (gate) is null");
+            unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[m.n_layers], gbias[m.n_layers],
+                                                                                 pl.H, pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF,
+                                                                                 pl.DFP, pl.Np, pl.n_bt, 2, 0);
+            unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[pl.F], gbias[pl.F], pl.H,
+                                                                                 pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF, pl.DFP,
+                                                                                 pl.Np, pl.n_bt, 2, 1);
+            launches += 2;
+        } else {
+            unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[pl.F], gbias[pl.F], pl.H,
+                                                                                 pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF, pl.DFP,
+                                                                                 pl.Np, pl.n_bt);
+            ++launches;
+        }
     }
     NCDE_CUDA_OK(cudaGetLastError());
     if (launches_out) *launches_out = launches;

@@ -374,8 +374,12 @@ __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// final layer: n = h*Cp + c (c padded to Cp, h padded to n_hg*Hg); W3T[k*Np + n], W3R[n*DFP + k], b3p[n]
-__global__ void pack_final_kernel(const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ W3T,
+// final layer: n = h*Cp + c (c padded to Cp, h padded to n_hg*Hg); W3T[k*Np + n], W3R[n*DFP + k], b3p[n].
+// Gated final layer (Wg != null; MinimalGatedVectorField, src/ncde/vector_fields/gating.py:7-32): the sigmoid head and the tanh
+// head are interleaved column by column, n = h*Cp + 2c + {0: sigmoid head Wg, 1: tanh head W}, so that one thread of the
+// field kernels owns both pre-activations of a (h, c) entry and the GEMMs themselves are unchanged.
+__global__ void pack_final_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ Wg,
+                                  const float* __restrict__ biasg, float* __restrict__ W3T,
                                   float* __restrict__ W3R, float* __restrict__ b3p, int H, int C, int Cp, int DF,
                                   int DFP, int Np) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,13 +387,17 @@ __global__ void pack_final_kernel(const float* __restrict__ W, const float* __re
     if (idx < total) {
         int n = (int)(idx / DFP), k = (int)(idx % DFP);
         int h = n / Cp, c = n % Cp;
-        float v = (h < H && c < C && k < DF) ? W[((int64_t)h * C + c) * DF + k] : 0.f;
+        const float* src = W;
+        if (Wg) { src = (c & 1) ? W : Wg; c >>= 1; }
+        float v = (h < H && c < C && k < DF) ? src[((int64_t)h * C + c) * DF + k] : 0.f;
         if (W3R) W3R[idx] = v;
         if (k < DF) W3T[(int64_t)k * Np + n] = v;
     }
     if (idx < Np) {
         int h = (int)idx / Cp, c = (int)idx % Cp;
-        b3p[idx] = (bias && h < H && c < C) ? bias[(int64_t)h * C + c] : 0.f;
+        const float* src = bias;
+        if (Wg) { src = (c & 1) ? bias : biasg; c >>= 1; }
+        b3p[idx] = (src && h < H && c < C) ? src[(int64_t)h * C + c] : 0.f;
     }
 }
 
@@ -709,7 +717,9 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
 // The (B, H*C) matrix of the reference (src/ncde/vector_fields/base.py:99-104, torchcde/solver.py:132) is never
 // materialised.  Thread (nt, mt) owns 4 consecutive n (= 4 channels of one h) x TM rows.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TM>
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+template <int TM, bool GATED = false>
 __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_constant__ FieldArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
@@ -770,6 +780,18 @@ __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_consta
             float part[TM];
 #pragma unroll
             for (int i = 0; i < TM; ++i) part[i] = 0.f;
+            if (GATED) {
+                // columns (2c, 2c+1) = (sigmoid head, tanh head) of entry (h, c): M = sigmoid(z) * tanh(r)  (gating.py:30-32)
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const float* dxrow = a.dXT + (size_t)(c0 / 2 + pr) * a.Bp + b0 + mt * TM;
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const float mv = sigmoidf_(acc[i][2 * pr] + bias[2 * pr]) * tanhf(acc[i][2 * pr + 1] + bias[2 * pr + 1]);
+                        part[i] = fmaf(mv, __ldg(dxrow + i), part[i]);
+                    }
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float* dxrow = a.dXT + (size_t)(c0 + j) * a.Bp + b0 + mt * TM;
@@ -871,7 +893,7 @@ __global__ void rk_bwd_begin_kernel(const float* __restrict__ gyT, float* gk0, f
 //   db3[(h,c)]   += sum_b G
 //   P_g[b,:]      = sum_{(h,c) in group} G * W3[(h,c),:]   (partial of dL/d act; summed over groups by hidden_bwd)
 // ---------------------------------------------------------------------------------------------------------------
-template <int TM>
+template <int TM, bool GATED = false>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ FieldArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
@@ -975,6 +997,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
                 }
             }
             // G = gk * dX * (1 - tanh^2), zero outside the batch
+            if (GATED) {
+                // M = s * t with s = sigmoid(z), t = tanh(r):  dz = gk dX t s (1 - s),  dr = gk dX s (1 - t^2)
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const float* dxrow = a.dXT + (size_t)(c0 / 2 + pr) * a.Bp + b0 + mt * TM;
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const int m = mt * TM + i;
+                        const float sg = sigmoidf_(acc[i][2 * pr] + bias[2 * pr]);
+                        const float t = tanhf(acc[i][2 * pr + 1] + bias[2 * pr + 1]);
+                        float dm = gks[hl_of_nt * kChunk + m] * __ldg(dxrow + i);
+                        if (b0 + m >= a.B) dm = 0.f;
+                        acc[i][2 * pr] = dm * t * sg * (1.f - sg);
+                        acc[i][2 * pr + 1] = dm * sg * (1.f - t * t);
+                    }
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float* dxrow = a.dXT + (size_t)(c0 + j) * a.Bp + b0 + mt * TM;
@@ -1321,23 +1360,24 @@ __host__ __device__ inline int64_t packed_n(int h, int c, int Cp, int Hg, int Np
     return (int64_t)(h / Hg) * Npad + (int64_t)(h % Hg) * Cp + c;
 }
 
+// cmul / coff: packed column of channel c is c * cmul + coff (gated final layer: cmul 2, coff 0 sigmoid head / 1 tanh head)
 __global__ void unpack_final_grad_kernel(const float* __restrict__ dW3acc, const float* __restrict__ db3acc,
                                          float* __restrict__ gW, float* __restrict__ gb, int H, int C, int Cp, int Hg,
-                                         int Npad, int DF, int DFP, int Np, int n_bt) {
+                                         int Npad, int DF, int DFP, int Np, int n_bt, int cmul = 1, int coff = 0) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)H * C * DF;
     if (idx < total) {
         const int k = (int)(idx % DF);
         const int hc = (int)(idx / DF);
         const int h = hc / C, c = hc % C;
-        const int64_t n = packed_n(h, c, Cp, Hg, Npad);
+        const int64_t n = packed_n(h, c * cmul + coff, Cp, Hg, Npad);
         float s = 0.f;
         for (int bt = 0; bt < n_bt; ++bt) s += dW3acc[((size_t)bt * Np + n) * DFP + k];
         gW[idx] += s;
     }
     if (gb && idx < (int64_t)H * C) {
         const int h = (int)idx / C, c = (int)idx % C;
-        const int64_t n = packed_n(h, c, Cp, Hg, Npad);
+        const int64_t n = packed_n(h, c * cmul + coff, Cp, Hg, Npad);
         float s = 0.f;
         for (int bt = 0; bt < n_bt; ++bt) s += db3acc[(size_t)bt * Np + n];
         gb[idx] += s;

@@ -4,7 +4,8 @@ from torch import nn
 
 import torchcde_b200 as torchcde
 
-from .vector_fields import VECTOR_FIELDS, OriginalVectorField  # noqa: F401
+from .vector_fields import (VECTOR_FIELDS, GRUGatedVectorField, MinimalGatedVectorField,  # noqa: F401
+                            OriginalVectorField)
 
 from .interpolation import SmoothLinearInterpolation  # noqa: E402
 

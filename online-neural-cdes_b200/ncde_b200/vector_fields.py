@@ -1,4 +1,4 @@
-"""Vector fields of the Neural CDE model (mirrors src/ncde/vector_fields/base.py of the reference).
+"""Vector fields of the Neural CDE model (mirrors src/ncde/vector_fields/base.py and gating.py of the reference).
 
 The modules only hold parameters and define the architecture; inside ``torchcde_b200.cdeint`` they are lowered to an
 MLP descriptor and evaluated by the fused CUDA kernels, never called per stage.
@@ -7,12 +7,12 @@ import torch
 from torch import nn
 
 
-class OriginalVectorField(nn.Module):
-    """f_theta: R^H -> R^{H x C}:  Linear(H, HH) + ReLU, (num_layers - 1) x [Linear(HH, HH) + ReLU], Linear(HH, H*C) +
-    tanh, view(-1, H, C).  With vector_field_type 'evaluate' / 'derivative' (base.py:56-60): R^{H+C} -> R^H, no view.
+class BaseVectorField(nn.Module):
+    """Common part (base.py:7-92): ``net_to_hh`` = Linear(initial_dim, HH) + ReLU, (num_layers - 1) x [Linear(HH, HH) + ReLU].
 
     Like the reference (base.py:64-69) the middle layers are ONE Linear module repeated, so they share weights and
     their gradient accumulates over the repeats.  ``nfe`` counts vector-field evaluations (base.py:61,90).
+    With vector_field_type 'evaluate' / 'derivative' (base.py:56-60) the field maps R^{H+C} -> R^H and is not reshaped.
     """
 
     def __init__(self, input_dim, hidden_dim, hidden_hidden_dim=15, num_layers=1, sparsity=None,
@@ -38,15 +38,62 @@ class OriginalVectorField(nn.Module):
             for _ in range(num_layers - 1):
                 mods += [shared, nn.ReLU()]
         self.net_to_hh = nn.Sequential(*mods)
-        self.tanh_output_layer = nn.Sequential(nn.Linear(hidden_hidden_dim, self.output_dim), nn.Tanh())
+        self.additional_network_initialisation()
+
+    def additional_network_initialisation(self):
+        raise NotImplementedError
+
+    def _forward(self, h):
+        raise NotImplementedError
 
     def forward(self, t, h):
         """Eager definition (used once to validate the lowering; the solve never calls it)."""
-        out = self.tanh_output_layer(self.net_to_hh(h))
+        out = self._forward(h)
         if self.matmul:
             out = out.view(-1, self.hidden_dim, self.input_dim)
         self.nfe += 1
         return out
 
 
-VECTOR_FIELDS = {"original": OriginalVectorField}
+class OriginalVectorField(BaseVectorField):
+    """f_theta: net_to_hh, then Linear(HH, H*C) + tanh (base.py:94-104)."""
+
+    def additional_network_initialisation(self):
+        self.tanh_output_layer = nn.Sequential(nn.Linear(self.hidden_hidden_dim, self.output_dim), nn.Tanh())
+
+    def _forward(self, h):
+        return self.tanh_output_layer(self.net_to_hh(h))
+
+
+class MinimalGatedVectorField(BaseVectorField):
+    """sigmoid(Linear_z(hh)) * tanh(Linear_r(hh)) with hh = net_to_hh(h) (gating.py:7-32).  Lowered to a gated last layer
+    (ncde_mlp_t.W_gate): both heads are one interleaved GEMM inside the final-layer kernels."""
+
+    def additional_network_initialisation(self):
+        assert self.sparsity is None, "sparsity not implemented for gated methods"
+        self.sigmoid_net = nn.Sequential(nn.Linear(self.hidden_hidden_dim, self.output_dim), nn.Sigmoid())
+        self.tanh_net = nn.Sequential(nn.Linear(self.hidden_hidden_dim, self.output_dim), nn.Tanh())
+
+    def _forward(self, h):
+        hh = self.net_to_hh(h)
+        return self.sigmoid_net(hh) * self.tanh_net(hh)
+
+
+class GRUGatedVectorField(BaseVectorField):
+    """GRU-style gating (gating.py:35-61).  Parameter layout only (state_dict compatible with the reference): the fused solve does
+    not implement it yet — ``cdeint`` raises NotImplementedError when given this field."""
+
+    def additional_network_initialisation(self):
+        assert self.sparsity is None, "sparsity not implemented for gated methods"
+        self.reset_net = nn.Sequential(nn.Linear(self.initial_dim, self.initial_dim), nn.Sigmoid())
+        self.sigmoid_net = nn.Sequential(nn.Linear(self.hidden_hidden_dim, self.output_dim), nn.Sigmoid())
+        self.tanh_net = nn.Sequential(nn.Linear(self.hidden_hidden_dim, self.output_dim), nn.Tanh())
+
+    def _forward(self, h):
+        inner = self.net_to_hh(h)
+        reset = self.net_to_hh(self.reset_net(h) * h)
+        return self.sigmoid_net(inner) * self.tanh_net(reset)
+
+
+# src/ncde/ncde.py:23-29 ('sparse' / 'low-rank' are commented out there too: they need the un-vendored `sparselinear`)
+VECTOR_FIELDS = {"original": OriginalVectorField, "minimal": MinimalGatedVectorField, "gru": GRUGatedVectorField}

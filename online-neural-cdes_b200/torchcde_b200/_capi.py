@@ -33,7 +33,9 @@ class Mlp(ctypes.Structure):
                 ("act", ctypes.c_int32 * MAX_LAYERS),
                 ("slot", ctypes.c_int32 * MAX_LAYERS),
                 ("W", ctypes.c_void_p * MAX_LAYERS),
-                ("bias", ctypes.c_void_p * MAX_LAYERS)]
+                ("bias", ctypes.c_void_p * MAX_LAYERS),
+                ("W_gate", ctypes.c_void_p),
+                ("bias_gate", ctypes.c_void_p)]
 
 
 class Path(ctypes.Structure):

@@ -24,7 +24,11 @@ _ACT = {"none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "tanh": _capi.ACT_TANH}
 class MlpSpec:
     """layers: list of (weight, bias_or_None, activation_code); slot[i] identifies shared parameters."""
 
-    def __init__(self, layers):
+    def __init__(self, layers, gate=None):
+        # gate: (weight, bias_or_None) of a sigmoid head multiplying the (tanh) last layer — MinimalGatedVectorField
+        self.gate = gate
+        if gate is not None and len(layers) >= _capi.MAX_LAYERS:
+            raise NotImplementedError("gated vector fields take at most {} Linear layers".format(_capi.MAX_LAYERS - 1))
         if not 1 <= len(layers) <= _capi.MAX_LAYERS:
             raise NotImplementedError("vector fields with {} Linear layers are not supported (max {})".format(
                 len(layers), _capi.MAX_LAYERS))
@@ -50,17 +54,25 @@ class MlpSpec:
                 out.append((w, "W", i))
                 if b is not None:
                     out.append((b, "b", i))
+        if self.gate is not None:   # the gate's gradients are returned in slot n_layers (ncde_b200.h, ncde_mlp_t.W_gate)
+            out.append((self.gate[0], "W", len(self.weights)))
+            if self.gate[1] is not None:
+                out.append((self.gate[1], "b", len(self.weights)))
         return out
 
     def reference_forward(self, z, hidden, channels):
         """The same map written with torch ops; used only to validate a lowering once, never on the solve path.
         ``channels`` None: vector_field_type evaluate / derivative (the output is the (B, H) state derivative itself)."""
-        for w, b, a in zip(self.weights, self.biases, self.acts):
+        last = len(self.weights) - 1
+        for i, (w, b, a) in enumerate(zip(self.weights, self.biases, self.acts)):
+            zin = z
             z = torch.nn.functional.linear(z, w, b)
             if a == _capi.ACT_RELU:
                 z = z.relu()
             elif a == _capi.ACT_TANH:
                 z = z.tanh()
+            if i == last and self.gate is not None:
+                z = torch.nn.functional.linear(zin, self.gate[0], self.gate[1]).sigmoid() * z
         return z.view(-1, hidden) if channels is None else z.view(-1, hidden, channels)
 
 
@@ -149,6 +161,10 @@ def lower(func, hidden, channels, vector_field_type="matmul"):
     if hit is not None and hit[0]() is func and hit[2] == (hidden, channels, vector_field_type):
         return hit[1]
     nfe_before = getattr(func, "nfe", None)
+    gate = None
+    if hasattr(func, "reset_net"):
+        raise NotImplementedError("GRU-gated vector fields (src/ncde/vector_fields/gating.py:35-61) are not implemented by the "
+                                  "fused solve; 'original' and 'minimal' are")
     if hasattr(func, "ncde_mlp_spec"):
         layers = [[w, b, _ACT[a] if isinstance(a, str) else a] for (w, b, a) in func.ncde_mlp_spec()]
     elif isinstance(getattr(func, "net_to_hh", None), torch.nn.Sequential) and \
@@ -157,13 +173,27 @@ def lower(func, hidden, channels, vector_field_type="matmul"):
             raise ValueError("the vector field was built for vector_field_type='{}' but cdeint was called with '{}'".format(
                 func.vector_field_type, vector_field_type))
         layers = _from_sequential(list(func.net_to_hh) + list(func.tanh_output_layer))
+    elif isinstance(getattr(func, "net_to_hh", None), torch.nn.Sequential) and \
+            isinstance(getattr(func, "sigmoid_net", None), torch.nn.Sequential) and \
+            isinstance(getattr(func, "tanh_net", None), torch.nn.Sequential):
+        # MinimalGatedVectorField (gating.py:7-32): sigmoid_net(hh) * tanh_net(hh)
+        if getattr(func, "vector_field_type", vector_field_type) != vector_field_type:
+            raise ValueError("the vector field was built for vector_field_type='{}' but cdeint was called with '{}'".format(
+                func.vector_field_type, vector_field_type))
+        layers = _from_sequential(list(func.net_to_hh) + list(func.tanh_net))
+        sig = list(func.sigmoid_net)
+        if len(sig) != 2 or not isinstance(sig[0], torch.nn.Linear) or not isinstance(sig[1], torch.nn.Sigmoid):
+            raise NotImplementedError("sigmoid_net must be Linear + Sigmoid")
+        gate = (sig[0].weight, sig[0].bias)
     elif isinstance(func, torch.nn.Module):
         layers = _from_fx(func)
     else:
         raise NotImplementedError("func must be an nn.Module that is a Linear/activation chain (no eager fallback)")
     if not layers:
         raise NotImplementedError("vector field has no Linear layer")
-    spec = MlpSpec([tuple(l) for l in layers])
+    spec = MlpSpec([tuple(l) for l in layers], gate)
+    if gate is not None and gate[0].shape != spec.weights[-1].shape:
+        raise ValueError("the gate of the vector field must have the shape of its last layer")
     spec.vector_field_type = vector_field_type
     spec.channels = channels
     d_in = hidden if matmul else hidden + channels

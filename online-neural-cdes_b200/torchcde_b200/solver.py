@@ -120,6 +120,14 @@ def _build_problem(X, spec, B, H, C, method, precision, sched):
             m.bias[i] = bd.data_ptr()
         else:
             m.bias[i] = None
+    if getattr(spec, "gate", None) is not None:
+        gw = spec.gate[0].detach().contiguous()
+        keep.append(gw)
+        m.W_gate = gw.data_ptr()
+        if spec.gate[1] is not None:
+            gbias = spec.gate[1].detach().contiguous()
+            keep.append(gbias)
+            m.bias_gate = gbias.data_ptr()
     if isinstance(X, LinearInterpolation):
         p.path.kind = _capi.PATH_LINEAR
         coeffs = X._coeffs.detach().contiguous()
@@ -218,6 +226,9 @@ class _FixedSolve(torch.autograd.Function):
             j = first_of_slot.setdefault(spec.slots[i], i)
             gW[i] = by_layer_w[j].data_ptr()
             gb[i] = by_layer_b[j].data_ptr() if j in by_layer_b else None
+        if getattr(spec, "gate", None) is not None:   # gate gradients: slot n_layers
+            gW[n] = by_layer_w[n].data_ptr()
+            gb[n] = by_layer_b[n].data_ptr() if n in by_layer_b else None
         # gradient w.r.t. the path coefficients (stacked CDEs, test_tricks.py:54-106): accumulated by the library into zeros
         grad_coeffs = torch.zeros_like(ctx.X._coeffs, memory_format=torch.contiguous_format) if want_path_grad else None
         wbytes = L.ncde_solve_workspace_bytes(ctypes.byref(problem), 2 if want_path_grad else 1)
@@ -392,6 +403,13 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         _capi.require_cuda(w)
         if w.dtype != torch.float32:
             raise NotImplementedError("vector field parameters must be float32")
+    if getattr(spec, "gate", None) is not None:
+        # MinimalGatedVectorField: fixed-grid fp32 solves, gradients by backpropagation through the steps
+        if method == 'dopri5' or adjoint or precision != 'fp32':
+            raise NotImplementedError("gated vector fields are implemented for method euler / rk4, adjoint=False and "
+                                      "precision fp32")
+        if coeffs.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("gradients with respect to the control path are not implemented for gated vector fields")
 
     if coeffs.requires_grad and torch.is_grad_enabled():
         if adjoint:

@@ -865,6 +865,23 @@ class SharedMLPField(torch.nn.Module):
         return out.view(-1, self.hidden_dim, self.input_dim) if self.matmul else out
 
 
+class MinimalGatedField(SharedMLPField):
+    """src/ncde/vector_fields/gating.py:7-32: sigmoid(Linear_z(hh)) * tanh(Linear_r(hh)), hh = net_to_hh(h)."""
+
+    def __init__(self, input_dim, hidden_dim, hidden_hidden_dim, num_layers, vector_field_type="matmul"):
+        super().__init__(input_dim, hidden_dim, hidden_hidden_dim, num_layers, vector_field_type)
+        out_dim = self.tanh_output_layer[0].out_features
+        del self.tanh_output_layer
+        self.sigmoid_net = torch.nn.Sequential(torch.nn.Linear(hidden_hidden_dim, out_dim), torch.nn.Sigmoid())
+        self.tanh_net = torch.nn.Sequential(torch.nn.Linear(hidden_hidden_dim, out_dim), torch.nn.Tanh())
+
+    def forward(self, t, h):
+        self.nfe += 1
+        hh = self.net_to_hh(h)
+        out = self.sigmoid_net(hh) * self.tanh_net(hh)
+        return out.view(-1, self.hidden_dim, self.input_dim) if self.matmul else out
+
+
 class ToyField(torch.nn.Module):
     """experiments/sim_bm_toy_example.py:10-30."""
 

@@ -1,0 +1,151 @@
+"""Gated vector fields: MinimalGatedVectorField — sigmoid(Linear_z(hh)) * tanh(Linear_r(hh))
+(src/ncde/vector_fields/gating.py:7-32) — in all three vector_field_type modes (the reference's `sparsity` ablation,
+experiments/configurations/configurations.json5: vector_field x vector_field_type, adjoint false).
+
+Golden vectors: tests/golden/gated.pt from the REAL reference (tests/golden/make_gated_golden.py).  CPU tests pin the oracle and
+the lowering; GPU tests compare the CUDA path (C ABI: ncde_mlp_t.W_gate) with the golden vectors and the oracle.
+Tolerance: relative max-norm 1e-5 (fp32).
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import cde_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gated.pt")
+TOL = 1e-5
+CASES = ["min_matmul_lin_rk4", "min_matmul_cub_rk4_half", "min_matmul_rect_euler", "min_eval_lin_rk4", "min_deriv_cub_rk4",
+         "min_matmul_wide"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLDEN)
+
+
+def rel(a, b):
+    a = a.detach().cpu()
+    b = b.detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(gold, name):
+    rec = gold[name]
+    d = rec["dims"]
+    func = O.MinimalGatedField(d["C"], d["H"], d["HH"], d["n"], vector_field_type=rec["vector_field_type"])
+    func.load_state_dict(rec["state_dict"])
+    X = O.CubicPath(rec["coeffs"]) if rec["interp"] == "cubic" else O.LinearPath(rec["coeffs"])
+    z0 = rec["z0"].clone().requires_grad_(True)
+    out = O.cdeint(X, func, z0, rec["t"], adjoint=False, method=rec["method"], options=dict(rec["options"]),
+                   vector_field_type=rec["vector_field_type"])
+    (out * rec["w"]).sum().backward()
+    assert rel(out, rec["out"]) <= 1e-6
+    assert rel(z0.grad, rec["grad_z0"]) <= 1e-5
+    for n, p in func.named_parameters():
+        assert rel(p.grad, rec["grads"][n]) <= 1e-5, n
+
+
+def test_lowering_of_gated_fields(gold):
+    """MinimalGatedVectorField lowers to an MLP with a gate on its last layer; the GRU-gated field is refused loudly."""
+    import ncde_b200
+    from torchcde_b200 import lowering
+    for name in CASES:
+        rec = gold[name]
+        d = rec["dims"]
+        f = ncde_b200.VECTOR_FIELDS["minimal"](d["C"], d["H"], d["HH"], d["n"], vector_field_type=rec["vector_field_type"])
+        missing, unexpected = f.load_state_dict(rec["state_dict"])
+        assert not missing and not unexpected
+        spec = lowering.lower(f, d["H"], d["C"], rec["vector_field_type"])
+        assert spec.gate is not None and spec.gate[0] is f.sigmoid_net[0].weight
+        assert spec.weights[-1] is f.tanh_net[0].weight
+        kinds = [(k, i) for _, k, i in spec.unique_params]
+        assert kinds[-2:] == [("W", len(spec.weights)), ("b", len(spec.weights))]
+    gru = ncde_b200.VECTOR_FIELDS["gru"](3, 4, 5, 2)
+    assert gru(None, torch.zeros(2, 4)).shape == (2, 4, 3)
+    with pytest.raises(NotImplementedError):
+        lowering.lower(gru, 4, 3)
+
+
+@pytest.fixture(scope="module")
+def tc():
+    import torchcde_b200
+    assert torch.cuda.is_available()
+    return torchcde_b200
+
+
+def _run_cuda(tc, rec, **kw):
+    import ncde_b200
+    d = rec["dims"]
+    func = ncde_b200.MinimalGatedVectorField(d["C"], d["H"], d["HH"], d["n"], vector_field_type=rec["vector_field_type"])
+    func.load_state_dict(rec["state_dict"])
+    func = func.cuda()
+    coeffs = rec["coeffs"].cuda()
+    X = tc.NaturalCubicSpline(coeffs) if rec["interp"] == "cubic" else tc.LinearInterpolation(coeffs)
+    z0 = rec["z0"].cuda().requires_grad_(True)
+    args = dict(adjoint=False, vector_field_type=rec["vector_field_type"], method=rec["method"], options=dict(rec["options"]))
+    args.update(kw)
+    out = tc.cdeint(X, func, z0, rec["t"].cuda(), **args)
+    (out * rec["w"].cuda()).sum().backward()
+    torch.cuda.synchronize()
+    return out, z0.grad, {n: p.grad for n, p in func.named_parameters()}, func
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_golden_gated(tc, gold, name):
+    rec = gold[name]
+    out, gz0, grads, func = _run_cuda(tc, rec)
+    assert rel(out, rec["out"]) <= TOL
+    assert rel(gz0, rec["grad_z0"]) <= TOL
+    assert sorted(grads) == sorted(rec["grads"])
+    for n, g in rec["grads"].items():
+        assert rel(grads[n], g) <= TOL, n
+    assert func.nfe == rec["nfe"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [("matmul", 96, 20, 4, 64, 64, 3, "linear"), ("matmul", 67, 9, 7, 19, 23, 2, "cubic"),
+                                   ("matmul", 80, 10, 64, 64, 48, 3, "linear"), ("evaluate", 72, 12, 100, 128, 128, 3, "linear")])
+def test_gated_against_oracle(tc, shape):
+    vft, B, K, C, H, HH, n, interp = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, K, C, generator=g).cumsum(-2) * 0.2
+    x[..., 0] = torch.arange(K, dtype=torch.float32)
+    torch.manual_seed(6)
+    func = O.MinimalGatedField(C, H, HH, n, vector_field_type=vft)
+    z0 = torch.randn(B, H, generator=g) * 0.5
+    cref = O.natural_cubic_coeffs(x) if interp == "cubic" else x.clone()
+    w = torch.randn(B, K, H, generator=g)
+    Xr = O.CubicPath(cref) if interp == "cubic" else O.LinearPath(cref)
+    z0r = z0.clone().requires_grad_(True)
+    oref = O.cdeint(Xr, func, z0r, Xr.grid_points, adjoint=False, method="rk4", options={"step_size": 1}, vector_field_type=vft)
+    (oref * w).sum().backward()
+    gref = {k: p.grad.clone() for k, p in func.named_parameters()}
+    for p in func.parameters():
+        p.grad = None
+    fc = func.cuda()
+    c = cref.cuda()
+    X = tc.NaturalCubicSpline(c) if interp == "cubic" else tc.LinearInterpolation(c)
+    z0c = z0.cuda().requires_grad_(True)
+    out = tc.cdeint(X, fc, z0c, X.grid_points, adjoint=False, vector_field_type=vft, method="rk4", options={"step_size": 1})
+    (out * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel(out, oref) <= TOL
+    assert rel(z0c.grad, z0r.grad) <= TOL
+    for k, p in fc.named_parameters():
+        assert rel(p.grad, gref[k]) <= TOL, k
+
+
+@pytest.mark.gpu
+def test_gated_unsupported_combinations_are_loud(tc, gold):
+    rec = gold["min_matmul_lin_rk4"]
+    for bad in (dict(adjoint=True), dict(method="dopri5"), dict(options={"step_size": 1.0, "precision": "bf16"})):
+        with pytest.raises(NotImplementedError):
+            _run_cuda(tc, rec, **bad)
+    import ncde_b200
+    gru = ncde_b200.GRUGatedVectorField(3, 6, 8, 2).cuda()
+    X = tc.LinearInterpolation(rec["coeffs"].cuda())
+    with pytest.raises(NotImplementedError):
+        tc.cdeint(X, gru, rec["z0"].cuda(), rec["t"].cuda(), adjoint=False, method="rk4")
