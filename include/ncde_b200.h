@@ -100,6 +100,27 @@ int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, 
                    int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv, void* out,
                    int64_t* index_out, void* stream);
 
+/* Ragged batches (offline preprocessing and loader, get_data/transformers.py:50-85, get_data/common.py:59-80,
+ * experiments/ingredients/loader.py:100-113,190-196).  x: (n_series, Lmax, C) with series s occupying its first lengths[s]
+ * rows (lengths: device int32, every entry >= 2; the remaining rows are ignored).  One call does for ALL series what the reference
+ * does in a Python loop per series:
+ *   initial_nan_to_zero: missing values of the first row become 0 (transformers.py:52-55);
+ *   NCDE_RAGGED_LINEAR       out (n, Lmax, C):       linear_interpolation_coeffs(d)                 knots t = 0..L_s-1
+ *   NCDE_RAGGED_RECTILINEAR  out (n, 2Lmax-1, Cout): linear_interpolation_coeffs(d, rectilinear=time_index)
+ *                            intensity != 0 appends C-1 channels (Cout = 2C-1, time_index must be 0): the running count of
+ *                            observations of channels 1..C-1, duplicated like the values (loader.py:100-113; a first-row value
+ *                            that is missing or exactly 0 does not count, as there)
+ *   NCDE_RAGGED_CUBIC        out (n, Lmax-1, 4C):    natural_cubic_coeffs(d)
+ *   pad != 0: rows past a series' own K_s = L_s | 2L_s-1 | L_s-1 repeat its last row — what PadRaggedTensors + ForwardFill give
+ *   when the loader batches the coefficient lists (loader.py:190-196); pad == 0 leaves them NaN.
+ * Results for the valid rows are bit-identical to the per-series reference calls.  flags: NCDE_FLAG_NAN_TIME as in
+ * ncde_rectilinear_prepare.  scratch: device, ncde_ragged_scratch_bytes(). */
+enum ncde_ragged_method { NCDE_RAGGED_LINEAR = 0, NCDE_RAGGED_RECTILINEAR = 1, NCDE_RAGGED_CUBIC = 2 };
+size_t ncde_ragged_scratch_bytes(int method, int dtype, int64_t n_series, int64_t Lmax, int64_t C);
+int ncde_ragged_interpolate(int method, int dtype, const void* x, const int32_t* lengths, void* out, int64_t n_series,
+                            int64_t Lmax, int64_t C, int time_index, int initial_nan_to_zero, int intensity, int pad,
+                            void* scratch, int32_t* flags, void* stream);
+
 /* Backward of ncde_path_eval with respect to the coefficients (what autograd does through
  * LinearInterpolation / NaturalCubicSpline .evaluate/.derivative in the reference, e.g. for h0 = Linear(X.evaluate(0)) of a
  * stacked Neural CDE, src/ncde/ncde.py:179-181).  grad_out (n_series, n_t, C); grad_coeffs has the shape of coeffs and is

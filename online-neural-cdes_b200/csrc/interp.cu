@@ -62,13 +62,9 @@ __global__ void rectilinear_kernel(const T* __restrict__ x, T* __restrict__ out,
 // ---------------------------------------------------------------------------------------------------------------
 // linear fill of missing values, in place — torchcde/interpolation_linear.py:13-84
 // ---------------------------------------------------------------------------------------------------------------
+// one scalar series xs[0], xs[C], ..., xs[(L-1)*C] (C = element stride between consecutive rows)
 template <typename T>
-__global__ void linear_fill_kernel(T* __restrict__ x, const T* __restrict__ t, int64_t n_series, int64_t L,
-                                   int64_t C) {
-    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n_series * C) return;
-    int64_t s = tid / C, c = tid % C;
-    T* xs = x + s * L * C + c;
+__device__ void linear_fill_series(T* xs, int64_t C, int64_t L, const T* __restrict__ t) {
     int64_t first = -1, last = -1;
     for (int64_t i = 0; i < L; ++i) {
         if (!is_nan(xs[i * C])) { if (first < 0) first = i; last = i; }
@@ -100,6 +96,15 @@ __global__ void linear_fill_kernel(T* __restrict__ x, const T* __restrict__ t, i
         p = n;
         i = n + 1;
     }
+}
+
+template <typename T>
+__global__ void linear_fill_kernel(T* __restrict__ x, const T* __restrict__ t, int64_t n_series, int64_t L,
+                                   int64_t C) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    int64_t s = tid / C, c = tid % C;
+    linear_fill_series<T>(x + s * L * C + c, C, L, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -212,15 +217,9 @@ __global__ void path_eval_bwd_kernel(int kind, const T* __restrict__ knots, int6
 // One thread per scalar series; scratch arrays are laid out [L][n_threads] so every sweep step is coalesced.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void cubic_coeffs_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out,
-                                    int64_t n_series, int64_t L, int64_t C, int version, T* __restrict__ s_x,
-                                    T* __restrict__ s_d, T* __restrict__ s_r, int32_t* __restrict__ s_i) {
-    const int64_t N = n_series * C;
-    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= N) return;
-    int64_t s = tid / C, c = tid % C;
-    const T* xs = x + s * L * C + c;
-    T* os = out + s * (L - 1) * 4 * C + c;
+__device__ void cubic_series(const T* __restrict__ xs, T* __restrict__ os, int64_t L, int64_t C, int version,
+                             const T* __restrict__ t, T* __restrict__ s_x, T* __restrict__ s_d, T* __restrict__ s_r,
+                             int32_t* __restrict__ s_i, int64_t N, int64_t tid) {
 #define SX(i) s_x[(int64_t)(i) * N + tid]
 #define SD(i) s_d[(int64_t)(i) * N + tid]
 #define SR(i) s_r[(int64_t)(i) * N + tid]
@@ -318,6 +317,114 @@ __global__ void cubic_coeffs_kernel(const T* __restrict__ x, const T* __restrict
 #undef SI
 }
 
+template <typename T>
+__global__ void cubic_coeffs_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out,
+                                    int64_t n_series, int64_t L, int64_t C, int version, T* __restrict__ s_x,
+                                    T* __restrict__ s_d, T* __restrict__ s_r, int32_t* __restrict__ s_i) {
+    const int64_t N = n_series * C;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= N) return;
+    int64_t s = tid / C, c = tid % C;
+    cubic_series<T>(x + s * L * C + c, out + s * (L - 1) * 4 * C + c, L, C, version, t, s_x, s_d, s_r, s_i, N, tid);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ragged batches: n series of different lengths packed into one NaN-padded (n, Lmax, C) tensor, series s
+// having lengths[s] valid rows.  What the reference does with a Python loop over the series
+// (get_data/transformers.py:50-85: d[:1][isnan] = 0, then linear_interpolation_coeffs / natural_cubic_coeffs per series) and,
+// later, per batch (experiments/ingredients/loader.py:100-113 intensity channels, :190-196 PadRaggedTensors + ForwardFill)
+// runs here as one launch per stage over all series; thread = (series, channel) as above.
+// ---------------------------------------------------------------------------------------------------------------
+// work = x with the first row's missing values set to zero ("causality", transformers.py:52-55); t = 0, 1, 2, ...
+template <typename T>
+__global__ void ragged_init_kernel(const T* __restrict__ x, T* __restrict__ work, T* __restrict__ t, int64_t n_series,
+                                   int64_t Lmax, int64_t C, int64_t Kmax, int init_zero) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < Kmax) t[tid] = (T)tid;
+    if (tid >= n_series * Lmax * C) return;
+    T v = x[tid];
+    if (init_zero && (tid / C) % Lmax == 0 && is_nan(v)) v = T(0);
+    work[tid] = v;
+}
+
+// rows [K, Kmax) of a finished series: repeat its last row (PadRaggedTensors + ForwardFill, loader.py:190-196) or NaN
+template <typename T>
+__device__ void ragged_tail(T* os, int64_t stride, int64_t K, int64_t Kmax, int pad) {
+    const T fill = pad ? os[(K - 1) * stride] : (T)NAN;
+    for (int64_t i = K; i < Kmax; ++i) os[i * stride] = fill;
+}
+
+template <typename T>
+__global__ void ragged_linear_kernel(const T* __restrict__ work, const int32_t* __restrict__ lengths, const T* __restrict__ t,
+                                     T* __restrict__ out, int64_t n_series, int64_t Lmax, int64_t C, int pad) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    const T* xs = work + s * Lmax * C + c;
+    T* os = out + s * Lmax * C + c;
+    for (int64_t i = 0; i < L; ++i) os[i * C] = xs[i * C];
+    linear_fill_series<T>(os, C, L, t);
+    ragged_tail<T>(os, C, L, Lmax, pad);
+}
+
+// rectilinear (time channel 0 .. time_index) + optional observation-intensity channels: channel C + c - 1 of the output counts
+// the observations of channel c >= 1 up to each row (loader.py:100-113: a first-row value that is missing OR exactly zero does
+// not count; rows duplicated like the values, last one dropped)
+template <typename T>
+__global__ void ragged_rectilinear_kernel(const T* __restrict__ x, const T* __restrict__ work,
+                                          const int32_t* __restrict__ lengths, const T* __restrict__ t, T* __restrict__ out,
+                                          int64_t n_series, int64_t Lmax, int64_t C, int64_t Cout, int time_index,
+                                          int pad, int32_t* __restrict__ flags) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    const int64_t Kmax = 2 * Lmax - 1, K = 2 * L - 1;
+    const T* xs = work + s * Lmax * C + c;
+    T* os = out + s * Kmax * Cout + c;
+    const bool is_time = (c == time_index);
+    T last = xs[0];
+    bool bad_time = false;
+    for (int64_t i = 0; i < L; ++i) {
+        T v = xs[i * C];
+        if (is_nan(v)) bad_time = bad_time || is_time; else last = v;
+        if (is_time) {
+            os[(2 * i) * Cout] = last;
+            if (i > 0) os[(2 * i - 1) * Cout] = last;
+        } else {
+            os[(2 * i) * Cout] = last;
+            if (i < L - 1) os[(2 * i + 1) * Cout] = last;
+        }
+    }
+    if (bad_time && flags) atomicOr(flags, NCDE_FLAG_NAN_TIME);
+    linear_fill_series<T>(os, Cout, K, t);
+    ragged_tail<T>(os, Cout, K, Kmax, pad);
+    if (Cout > C && c >= 1) {
+        const T* xr = x + s * Lmax * C + c;
+        T* oi = out + s * Kmax * Cout + C + (c - 1);
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < L; ++i) {
+            const T v = xr[i * C];
+            if (!is_nan(v) && !(i == 0 && v == T(0))) ++cnt;
+            oi[(2 * i) * Cout] = (T)cnt;
+            if (i < L - 1) oi[(2 * i + 1) * Cout] = (T)cnt;
+        }
+        ragged_tail<T>(oi, Cout, K, Kmax, pad);
+    }
+}
+
+template <typename T>
+__global__ void ragged_cubic_kernel(const T* __restrict__ work, const int32_t* __restrict__ lengths, const T* __restrict__ t,
+                                    T* __restrict__ out, int64_t n_series, int64_t Lmax, int64_t C, int pad,
+                                    T* __restrict__ s_x, T* __restrict__ s_d, T* __restrict__ s_r, int32_t* __restrict__ s_i) {
+    const int64_t N = n_series * C;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= N) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    T* os = out + s * (Lmax - 1) * 4 * C + c;
+    cubic_series<T>(work + s * Lmax * C + c, os, L, C, 1, t, s_x, s_d, s_r, s_i, N, tid);
+    for (int q = 0; q < 4; ++q) ragged_tail<T>(os + q * C, 4 * C, L - 1, Lmax - 1, pad);
+}
+
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)ceil_div(n, block); }
 
 }  // namespace ncde
@@ -387,6 +494,63 @@ extern "C" int ncde_path_eval(int kind, int dtype, const void* coeffs, const voi
     DISPATCH_DTYPE(dtype, (path_eval_kernel<T><<<grid_for(n_series * n_t * C, 256), 256, 0, st>>>(
                               kind, (const T*)coeffs, (const T*)derivs, (const T*)knots, n_series, K, C,
                               (const T*)tq, n_t, deriv, (T*)out, index_out)));
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+static size_t ragged_scratch_layout(int dtype, int method, int64_t n, int64_t Lmax, int64_t C, size_t* off_t, size_t* off_cubic) {
+    const size_t el = dtype == NCDE_F64 ? 8 : 4;
+    size_t off = round_up((size_t)n * Lmax * C * el, 256);          // work copy
+    *off_t = off;
+    off += round_up((size_t)(2 * Lmax) * el, 256);                  // t = 0, 1, ...
+    *off_cubic = off;
+    if (method == NCDE_RAGGED_CUBIC) off += ncde_cubic_scratch_bytes(dtype, n, Lmax, C);
+    return off + 256;
+}
+
+extern "C" size_t ncde_ragged_scratch_bytes(int method, int dtype, int64_t n_series, int64_t Lmax, int64_t C) {
+    size_t a, b;
+    return ragged_scratch_layout(dtype, method, n_series, Lmax, C, &a, &b);
+}
+
+extern "C" int ncde_ragged_interpolate(int method, int dtype, const void* x, const int32_t* lengths, void* out,
+                                       int64_t n_series, int64_t Lmax, int64_t C, int time_index, int initial_nan_to_zero,
+                                       int intensity, int pad, void* scratch, int32_t* flags, void* stream) {
+    NCDE_REQUIRE(x && lengths && out && scratch, NCDE_ERR_INVALID, "ragged_interpolate: null pointer");
+    NCDE_REQUIRE(method == NCDE_RAGGED_LINEAR || method == NCDE_RAGGED_RECTILINEAR || method == NCDE_RAGGED_CUBIC,
+                 NCDE_ERR_INVALID, "ragged_interpolate: unknown method %d", method);
+    NCDE_REQUIRE(n_series >= 0 && Lmax >= 2 && C >= 1, NCDE_ERR_INVALID, "Must have a time dimension of size at least 2.");
+    NCDE_REQUIRE(method != NCDE_RAGGED_RECTILINEAR || (time_index >= 0 && time_index < C), NCDE_ERR_INVALID,
+                 "Time index must be in [0, %lld], was given %d.", (long long)C - 1, time_index);
+    NCDE_REQUIRE(!intensity || (method == NCDE_RAGGED_RECTILINEAR && time_index == 0), NCDE_ERR_INVALID,
+                 "ragged_interpolate: intensity channels belong to the rectilinear scheme with the time channel first");
+    if (n_series == 0) return NCDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t off_t, off_cubic;
+    ragged_scratch_layout(dtype, method, n_series, Lmax, C, &off_t, &off_cubic);
+    const int64_t Kmax = 2 * Lmax;
+    const int64_t n_init = n_series * Lmax * C > Kmax ? n_series * Lmax * C : Kmax;
+    DISPATCH_DTYPE(dtype, {
+        T* work = (T*)scratch;
+        T* t = (T*)((char*)scratch + off_t);
+        ragged_init_kernel<T><<<grid_for(n_init, 256), 256, 0, st>>>((const T*)x, work, t, n_series, Lmax, C, Kmax,
+                                                                      initial_nan_to_zero);
+        if (method == NCDE_RAGGED_LINEAR) {
+            ragged_linear_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(work, lengths, t, (T*)out, n_series, Lmax, C, pad);
+        } else if (method == NCDE_RAGGED_RECTILINEAR) {
+            const int64_t Cout = C + (intensity ? C - 1 : 0);
+            ragged_rectilinear_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>((const T*)x, work, lengths, t, (T*)out, n_series,
+                                                                                      Lmax, C, Cout, time_index, pad, flags);
+        } else {
+            const size_t n = (size_t)n_series * (size_t)C * (size_t)Lmax;
+            T* sx = (T*)((char*)scratch + off_cubic);
+            T* sd = sx + n;
+            T* sr = sd + n;
+            int32_t* si = (int32_t*)(sr + n);
+            ragged_cubic_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(work, lengths, t, (T*)out, n_series, Lmax, C, pad,
+                                                                                sx, sd, sr, si);
+        }
+    });
     NCDE_CUDA_OK(cudaGetLastError());
     return NCDE_OK;
 }

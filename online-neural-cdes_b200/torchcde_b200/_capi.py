@@ -21,6 +21,7 @@ EULER, RK4_38, DOPRI5 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1
 VF_MATMUL, VF_EVALUATE, VF_DERIVATIVE = 0, 1, 2
+RAGGED_LINEAR, RAGGED_RECTILINEAR, RAGGED_CUBIC = 0, 1, 2
 FLAG_NAN_TIME, FLAG_NONFINITE, FLAG_DT_UNDERFLOW, FLAG_MAX_STEPS = 1, 2, 4, 8
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -78,7 +79,7 @@ _lib = None
 # every symbol include/ncde_b200.h declares; tests check that the library exports all of them
 SYMBOLS = ["ncde_version", "ncde_last_error", "ncde_abi_version", "ncde_forward_fill", "ncde_rectilinear_prepare",
            "ncde_linear_fill_missing", "ncde_cubic_scratch_bytes", "ncde_natural_cubic_coeffs", "ncde_linear_derivs",
-           "ncde_path_eval", "ncde_path_eval_bwd", "ncde_logsig_windows", "ncde_hybrid_compact", "ncde_smooth_matching_coeffs", "ncde_path_eval_smooth", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
+           "ncde_path_eval", "ncde_ragged_scratch_bytes", "ncde_ragged_interpolate", "ncde_path_eval_bwd", "ncde_logsig_windows", "ncde_hybrid_compact", "ncde_smooth_matching_coeffs", "ncde_path_eval_smooth", "ncde_solve_saved_bytes", "ncde_solve_workspace_bytes", "ncde_solve_fwd",
            "ncde_solve_bwd", "ncde_solve_adaptive_fwd", "ncde_solve_adjoint_workspace_bytes",
            "ncde_solve_adjoint_bwd", "ncde_solve_adjoint_adaptive_workspace_bytes",
            "ncde_solve_adjoint_adaptive_bwd", "ncde_profile_enable", "ncde_profile_read"]
@@ -108,6 +109,9 @@ def lib():
     L.ncde_natural_cubic_coeffs.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, vp, vp]
     L.ncde_linear_derivs.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp]
     L.ncde_path_eval.argtypes = [i32, i32, vp, vp, vp, i64, i64, i64, vp, i64, i32, vp, vp, vp]
+    L.ncde_ragged_scratch_bytes.argtypes = [i32, i32, i64, i64, i64]
+    L.ncde_ragged_scratch_bytes.restype = sz
+    L.ncde_ragged_interpolate.argtypes = [i32, i32, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp]
     L.ncde_path_eval_bwd.argtypes = [i32, i32, vp, i64, i64, i64, vp, i64, i32, vp, vp, vp]
     L.ncde_logsig_windows.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
     L.ncde_hybrid_compact.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, vp]
