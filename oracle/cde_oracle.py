@@ -687,6 +687,52 @@ def cdeint(X, func, z0, t, adjoint=True, method=None, rtol=None, atol=None, opti
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Offline preprocessing over ragged series (get_data/transformers.py:7-85; experiments/ingredients/loader.py:100-113,181-202)
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def interpolation_transform(data, method="linear", initial_nan_to_zero=True):
+    """get_data/transformers.py:50-85: per series, zero the first row's missing values IN PLACE, then linear / rectilinear /
+    cubic coefficients ('linear_forward_fill' takes the linear branch there as well)."""
+    if initial_nan_to_zero:
+        for d in data:
+            d[:1, :][torch.isnan(d[:1, :])] = 0.0
+    rect = 0 if method == "rectilinear" else None
+
+    def one(d):
+        if method == "cubic":
+            return natural_cubic_coeffs(d)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return linear_interpolation_coeffs(d, rectilinear=rect)
+
+    if isinstance(data, torch.Tensor):
+        return one(data)
+    return [one(d) for d in data]
+
+
+def rectilinear_intensity(rect_coeffs, raw_zeroed):
+    """experiments/ingredients/loader.py:100-113 for one series: append, to its rectilinear coefficients, the running count of
+    observations of channels 1.. taken from the raw series whose first-row gaps were zeroed (a first-row zero counts as missing),
+    duplicated like the values and cut by one row."""
+    tdata = raw_zeroed.clone()
+    tdata[0, :][tdata[0, :] == 0] = float("nan")
+    counts = (~tdata[:, 1:].isnan()).cumsum(0).repeat_interleave(2, 0)[:-1]
+    return torch.cat([rect_coeffs, counts.to(rect_coeffs.dtype)], dim=1)
+
+
+def padded_batches(sorted_coeffs, batch_size):
+    """experiments/ingredients/loader.py:181-202: per batch, pad with NaN to the longest series (PadRaggedTensors) and forward
+    fill (ForwardFill)."""
+    out = []
+    for i in range(0, len(sorted_coeffs), batch_size):
+        chunk = sorted_coeffs[i:i + batch_size]
+        padded = torch.nn.utils.rnn.pad_sequence(chunk, batch_first=True, padding_value=float("nan"))
+        out.append(forward_fill(padded))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Linear / rectilinear hybrid (src/ncde/interpolation.py:186-253)
 # ----------------------------------------------------------------------------------------------------------------
 
