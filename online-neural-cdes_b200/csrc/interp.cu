@@ -4,6 +4,8 @@
 // length axis; consecutive threads own consecutive channels, so every step of the walk is a coalesced row access.
 // Compiled with -fmad=false: the reference evaluates each torch op with its own rounding (no fused
 // multiply-add), and matching that is what makes the outputs bit-identical to the reference on the same inputs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ncde {
@@ -217,7 +219,7 @@ __global__ void path_eval_bwd_kernel(int kind, const T* __restrict__ knots, int6
 // One thread per scalar series; scratch arrays are laid out [L][n_threads] so every sweep step is coalesced.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void cubic_series(const T* __restrict__ xs, T* __restrict__ os, int64_t L, int64_t C, int version,
+__device__ void cubic_series(const T* xs, int64_t XS, T* __restrict__ os, int64_t L, int64_t C, int version,
                              const T* __restrict__ t, T* __restrict__ s_x, T* __restrict__ s_d, T* __restrict__ s_r,
                              int32_t* __restrict__ s_i, int64_t N, int64_t tid) {
 #define SX(i) s_x[(int64_t)(i) * N + tid]
@@ -227,7 +229,7 @@ __device__ void cubic_series(const T* __restrict__ xs, T* __restrict__ os, int64
     // 1. observed points after end imputation (version 0: ends only; version 1: fill outward from first/last)
     int64_t first = -1, last = -1;
     for (int64_t i = 0; i < L; ++i) {
-        if (!is_nan(xs[i * C])) { if (first < 0) first = i; last = i; }
+        if (!is_nan(xs[i * XS])) { if (first < 0) first = i; last = i; }
     }
     if (first < 0) {
         for (int64_t i = 0; i < L - 1; ++i) {
@@ -235,10 +237,10 @@ __device__ void cubic_series(const T* __restrict__ xs, T* __restrict__ os, int64
         }
         return;
     }
-    const T x_first = xs[first * C], x_last = xs[last * C];
+    const T x_first = xs[first * XS], x_last = xs[last * XS];
     int m = 0;
     for (int64_t i = 0; i < L; ++i) {
-        T v = xs[i * C];
+        T v = xs[i * XS];
         bool have = !is_nan(v);
         if (!have) {
             if (version == 0) {
@@ -325,7 +327,7 @@ __global__ void cubic_coeffs_kernel(const T* __restrict__ x, const T* __restrict
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= N) return;
     int64_t s = tid / C, c = tid % C;
-    cubic_series<T>(x + s * L * C + c, out + s * (L - 1) * 4 * C + c, L, C, version, t, s_x, s_d, s_r, s_i, N, tid);
+    cubic_series<T>(x + s * L * C + c, C, out + s * (L - 1) * 4 * C + c, L, C, version, t, s_x, s_d, s_r, s_i, N, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -345,6 +347,12 @@ __global__ void ragged_init_kernel(const T* __restrict__ x, T* __restrict__ work
     T v = x[tid];
     if (init_zero && (tid / C) % Lmax == 0 && is_nan(v)) v = T(0);
     work[tid] = v;
+}
+
+template <typename T>
+__global__ void arange_kernel(T* __restrict__ t, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = (T)i;
 }
 
 // rows [K, Kmax) of a finished series: repeat its last row (PadRaggedTensors + ForwardFill, loader.py:190-196) or NaN
@@ -421,7 +429,183 @@ __global__ void ragged_cubic_kernel(const T* __restrict__ work, const int32_t* _
     if (tid >= N) return;
     const int64_t s = tid / C, c = tid % C, L = lengths[s];
     T* os = out + s * (Lmax - 1) * 4 * C + c;
-    cubic_series<T>(work + s * Lmax * C + c, os, L, C, 1, t, s_x, s_d, s_r, s_i, N, tid);
+    cubic_series<T>(work + s * Lmax * C + c, C, os, L, C, 1, t, s_x, s_d, s_r, s_i, N, tid);
+    for (int q = 0; q < 4; ++q) ragged_tail<T>(os + q * C, 4 * C, L - 1, Lmax - 1, pad);
+}
+
+// Branch-uniform restatement of linear_fill_series for a series held in a shared-memory column: a forward pass records, per
+// row, the previous observation (16-bit index column `prev`), a backward pass carries the next one in registers and writes the
+// interpolated value.  Every lane runs the same L iterations (the gap-chasing while-loops of linear_fill_series diverge within a
+// warp because each (series, channel) has its own gap pattern).  Same operands, same expression, same rounding as above:
+// results are bit-identical.  L < 65535.
+template <typename T>
+__device__ void linear_fill_uniform(T* col, int stride, unsigned short* prev, int64_t L, const T* __restrict__ t) {
+    int first = -1, p = -1;
+    bool any_nan = false;
+    for (int i = 0; i < (int)L; ++i) {
+        const bool obs = !is_nan(col[(int64_t)i * stride]);
+        if (obs) { if (first < 0) first = i; p = i; } else any_nan = true;
+        prev[(int64_t)i * stride] = (unsigned short)(p < 0 ? 0xFFFF : p);
+    }
+    const int last = p;
+    if (first < 0) {  // nothing observed: constant zero path
+        for (int i = 0; i < (int)L; ++i) col[(int64_t)i * stride] = T(0);
+        return;
+    }
+    if (!any_nan) return;
+    const T x_first = col[(int64_t)first * stride], x_last = col[(int64_t)last * stride];
+    int n = (int)L - 1;   // next observed point; the right end counts as one (imputed with the last observation)
+    T xn = x_last;
+    for (int j = (int)L - 1; j >= 0; --j) {
+        const T v = col[(int64_t)j * stride];
+        const bool obs = !is_nan(v);
+        T r = v;
+        if (!obs) {
+            if (j == (int)L - 1) r = x_last;
+            else if (j == 0) r = x_first;
+            else {
+                int pi = prev[(int64_t)j * stride];
+                T xp;
+                if (pi == 0xFFFF) { pi = 0; xp = x_first; } else xp = col[(int64_t)pi * stride];
+                const T tp = t[pi], tn = t[n];
+                const T ratio = (t[j] - tp) / (tn - tp);
+                r = xp + ratio * (xn - xp);
+            }
+            col[(int64_t)j * stride] = r;
+        } else {
+            n = j; xn = v;
+        }
+    }
+}
+
+// fixed-length linear fill through shared memory (ncde_linear_fill_missing fast path): sm = [L][blockDim] values + 16-bit indices
+template <typename T>
+__global__ void linear_fill_staged_kernel(T* __restrict__ x, const T* __restrict__ t, int64_t n_series, int64_t L, int64_t C) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* col = reinterpret_cast<T*>(sm_raw) + threadIdx.x;
+    unsigned short* prev = reinterpret_cast<unsigned short*>(sm_raw + (size_t)L * blockDim.x * sizeof(T)) + threadIdx.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t s = tid / C, c = tid % C;
+    T* xs = x + s * L * C + c;
+    int64_t i = 0;
+    for (; i + 8 <= L; i += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = xs[(i + u) * C];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) col[(i + u) * blockDim.x] = v[u];
+    }
+    for (; i < L; ++i) col[i * blockDim.x] = xs[i * C];
+    linear_fill_uniform<T>(col, blockDim.x, prev, L, t);
+    for (i = 0; i < L; ++i) xs[i * C] = col[i * blockDim.x];
+}
+
+// ---- shared-memory staged variants (the fast path) -----------------------------------------------------------------------------
+// The walks above chase one dependent global load per row.  Here a thread first pulls its whole series into a shared-memory
+// column with independent (unrolled, coalesced 128-byte-per-warp) loads — first-row zeroing applied on the way, so the work
+// copy of ragged_init_kernel is not needed — runs the same device functions on shared memory, and streams the result out with
+// independent stores.  HBM traffic: raw set read once, coefficients written once.  sm: [Lmax][blockDim.x] (+ the same again for
+// the rectilinear scheme's second operand is not needed: values are written straight from the forward-filled column).
+template <typename T>
+__device__ __forceinline__ void stage_series(const T* __restrict__ xs, int64_t C, int64_t L, T* col, int stride, int init_zero) {
+    int64_t i = 0;
+    for (; i + 8 <= L; i += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = xs[(i + u) * C];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) col[(i + u) * stride] = v[u];
+    }
+    for (; i < L; ++i) col[i * stride] = xs[i * C];
+    if (init_zero && is_nan(col[0])) col[0] = T(0);
+}
+
+template <typename T>
+__global__ void ragged_linear_staged_kernel(const T* __restrict__ x, const int32_t* __restrict__ lengths, const T* __restrict__ t,
+                                            T* __restrict__ out, int64_t n_series, int64_t Lmax, int64_t C, int init_zero, int pad) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* col = reinterpret_cast<T*>(sm_raw) + threadIdx.x;
+    const int stride = blockDim.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    unsigned short* prev = reinterpret_cast<unsigned short*>(sm_raw + (size_t)Lmax * blockDim.x * sizeof(T)) + threadIdx.x;
+    stage_series<T>(x + s * Lmax * C + c, C, L, col, stride, init_zero);
+    linear_fill_uniform<T>(col, stride, prev, L, t);
+    T* os = out + s * Lmax * C + c;
+    const T fill = pad ? col[(L - 1) * stride] : (T)NAN;
+    for (int64_t i = 0; i < Lmax; ++i) os[i * C] = i < L ? col[i * stride] : fill;
+}
+
+template <typename T>
+__global__ void ragged_rectilinear_staged_kernel(const T* __restrict__ x, const int32_t* __restrict__ lengths,
+                                                 const T* __restrict__ t, T* __restrict__ out, int64_t n_series, int64_t Lmax,
+                                                 int64_t C, int64_t Cout, int time_index, int init_zero, int pad,
+                                                 int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* col = reinterpret_cast<T*>(sm_raw) + threadIdx.x;
+    const int stride = blockDim.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_series * C) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    const int64_t Kmax = 2 * Lmax - 1, K = 2 * L - 1;
+    const T* xr = x + s * Lmax * C + c;
+    stage_series<T>(xr, C, L, col, stride, 0);
+    T* os = out + s * Kmax * Cout + c;
+    // observation counts first (they need the raw values: loader.py:100-113), then forward fill in place
+    if (Cout > C && c >= 1) {
+        T* oi = out + s * Kmax * Cout + C + (c - 1);
+        int64_t cnt = 0;
+        T lastc = T(0);
+        for (int64_t i = 0; i < L; ++i) {
+            const T v = col[i * stride];
+            if (!is_nan(v) && !(i == 0 && v == T(0))) ++cnt;
+            lastc = (T)cnt;
+            oi[(2 * i) * Cout] = lastc;
+            if (i < L - 1) oi[(2 * i + 1) * Cout] = lastc;
+        }
+        const T fill = pad ? lastc : (T)NAN;
+        for (int64_t i = K; i < Kmax; ++i) oi[i * Cout] = fill;
+    }
+    if (init_zero && is_nan(col[0])) col[0] = T(0);
+    const bool is_time = (c == time_index);
+    const bool lead_nan = is_nan(col[0]);
+    T last = col[0];
+    bool bad_time = false;
+    for (int64_t i = 0; i < L; ++i) {
+        const T v = col[i * stride];
+        if (is_nan(v)) bad_time = bad_time || is_time; else last = v;
+        col[i * stride] = last;
+    }
+    if (bad_time && flags) atomicOr(flags, NCDE_FLAG_NAN_TIME);
+    // value channels: out[2i] = out[2i+1] = ffill[i]; time channel: out[2i] = t[i], out[2i+1] = t[i+1]
+    for (int64_t i = 0; i < L; ++i) {
+        const T v = col[i * stride];
+        os[(2 * i) * Cout] = v;
+        if (is_time) { if (i > 0) os[(2 * i - 1) * Cout] = v; }
+        else if (i < L - 1) os[(2 * i + 1) * Cout] = v;
+    }
+    // a series that starts with missing values (only possible without the first-row rule) is back-filled by the generic path
+    if (lead_nan) linear_fill_series<T>(os, Cout, K, t);
+    const T fill = pad ? os[(K - 1) * Cout] : (T)NAN;
+    for (int64_t i = K; i < Kmax; ++i) os[i * Cout] = fill;
+}
+
+template <typename T>
+__global__ void ragged_cubic_staged_kernel(const T* __restrict__ x, const int32_t* __restrict__ lengths, const T* __restrict__ t,
+                                           T* __restrict__ out, int64_t n_series, int64_t Lmax, int64_t C, int init_zero, int pad,
+                                           T* __restrict__ s_x, T* __restrict__ s_d, T* __restrict__ s_r, int32_t* __restrict__ s_i) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* col = reinterpret_cast<T*>(sm_raw) + threadIdx.x;
+    const int stride = blockDim.x;
+    const int64_t N = n_series * C;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= N) return;
+    const int64_t s = tid / C, c = tid % C, L = lengths[s];
+    stage_series<T>(x + s * Lmax * C + c, C, L, col, stride, init_zero);
+    T* os = out + s * (Lmax - 1) * 4 * C + c;
+    cubic_series<T>(col, stride, os, L, C, 1, t, s_x, s_d, s_r, s_i, N, tid);
     for (int q = 0; q < 4; ++q) ragged_tail<T>(os + q * C, 4 * C, L - 1, Lmax - 1, pad);
 }
 
@@ -465,6 +649,16 @@ extern "C" int ncde_linear_fill_missing(int dtype, void* x, const void* t, int64
     NCDE_REQUIRE(x && t && n_series >= 0 && L >= 2 && C >= 1, NCDE_ERR_INVALID, "linear_fill_missing: bad arguments");
     if (n_series == 0) return NCDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool allow_staged = getenv("NCDE_RAGGED_NO_STAGING") == nullptr;
+    const size_t smem = (size_t)L * 128 * ((dtype == NCDE_F64 ? 8 : 4) + 2);
+    if (allow_staged && smem <= 200 * 1024 && L < 65535) {
+        DISPATCH_DTYPE(dtype, {
+            NCDE_CUDA_OK(cudaFuncSetAttribute(linear_fill_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            linear_fill_staged_kernel<T><<<grid_for(n_series * C, 128), 128, smem, st>>>((T*)x, (const T*)t, n_series, L, C);
+        });
+        NCDE_CUDA_OK(cudaGetLastError());
+        return NCDE_OK;
+    }
     DISPATCH_DTYPE(dtype, (linear_fill_kernel<T><<<grid_for(n_series * C, 128), 128, 0, st>>>(
                               (T*)x, (const T*)t, n_series, L, C)));
     NCDE_CUDA_OK(cudaGetLastError());
@@ -530,6 +724,40 @@ extern "C" int ncde_ragged_interpolate(int method, int dtype, const void* x, con
     ragged_scratch_layout(dtype, method, n_series, Lmax, C, &off_t, &off_cubic);
     const int64_t Kmax = 2 * Lmax;
     const int64_t n_init = n_series * Lmax * C > Kmax ? n_series * Lmax * C : Kmax;
+    static const bool allow_staged = getenv("NCDE_RAGGED_NO_STAGING") == nullptr;   // A/B switch for tools/bench_ragged.py
+    const size_t el = dtype == NCDE_F64 ? 8 : 4;
+    const int bs = 128;
+    const size_t smem = (size_t)Lmax * bs * el;
+    // measured (profiles/README.md): staging pays for linear (0.59 -> 0.32 ms before the uniform fill) and rectilinear
+    // (0.54 -> 0.19 ms); the cubic kernel is bound by its Thomas-sweep scratch, not by the input walk (1.29 -> 1.59 ms), so it stays
+    if (allow_staged && method != NCDE_RAGGED_CUBIC && smem + (size_t)Lmax * bs * 2 <= 200 * 1024 && Lmax < 65535) {
+        DISPATCH_DTYPE(dtype, {
+            T* t = (T*)((char*)scratch + off_t);
+            arange_kernel<T><<<grid_for(Kmax, 256), 256, 0, st>>>(t, Kmax);
+            if (method == NCDE_RAGGED_LINEAR) {
+                const size_t smem_l = smem + (size_t)Lmax * bs * 2;   // + the 16-bit previous-observation column
+                NCDE_CUDA_OK(cudaFuncSetAttribute(ragged_linear_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                ragged_linear_staged_kernel<T><<<grid_for(n_series * C, bs), bs, smem_l, st>>>((const T*)x, lengths, t, (T*)out, n_series,
+                                                                                             Lmax, C, initial_nan_to_zero, pad);
+            } else if (method == NCDE_RAGGED_RECTILINEAR) {
+                const int64_t Cout = C + (intensity ? C - 1 : 0);
+                NCDE_CUDA_OK(cudaFuncSetAttribute(ragged_rectilinear_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ragged_rectilinear_staged_kernel<T><<<grid_for(n_series * C, bs), bs, smem, st>>>(
+                    (const T*)x, lengths, t, (T*)out, n_series, Lmax, C, Cout, time_index, initial_nan_to_zero, pad, flags);
+            } else {
+                const size_t n = (size_t)n_series * (size_t)C * (size_t)Lmax;
+                T* sx = (T*)((char*)scratch + off_cubic);
+                T* sd = sx + n;
+                T* sr = sd + n;
+                int32_t* si = (int32_t*)(sr + n);
+                NCDE_CUDA_OK(cudaFuncSetAttribute(ragged_cubic_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ragged_cubic_staged_kernel<T><<<grid_for(n_series * C, bs), bs, smem, st>>>((const T*)x, lengths, t, (T*)out, n_series, Lmax,
+                                                                                            C, initial_nan_to_zero, pad, sx, sd, sr, si);
+            }
+        });
+        NCDE_CUDA_OK(cudaGetLastError());
+        return NCDE_OK;
+    }
     DISPATCH_DTYPE(dtype, {
         T* work = (T*)scratch;
         T* t = (T*)((char*)scratch + off_t);

@@ -3,8 +3,8 @@ reference (oracle restatement of get_data/transformers.py:50-85) timed beside it
 
     python tools/bench_ragged.py            -> one JSON line per method
 
-Algorithmic bytes per launch: the raw set is read once (n*Lmax*C*4, the init pass) and the coefficients written once
-(linear: same size; rectilinear: 2x; cubic: 4x), plus one extra read+write of the work copy: HBM-bound copy/scan work.
+Algorithmic bytes per launch: the raw set read once (n*Lmax*C*4) and the coefficients written once (linear: same size;
+rectilinear: 2x; cubic: 4x): HBM-bound copy/scan work.  NCDE_RAGGED_NO_STAGING=1 selects the un-staged kernels (A/B).
 """
 import json, os, sys, time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -59,7 +59,7 @@ for method in ("linear", "rectilinear", "cubic"):
         ts.append(a.elapsed_time(b))
     ms = sorted(ts)[len(ts) // 2]
     raw_bytes = n * Lmax * C * 4
-    alg = raw_bytes * 3 + out.numel() * 4      # read raw, write + read work copy, write coefficients
+    alg = raw_bytes + out.numel() * 4          # the raw set read once, the coefficients written once
     # reference-style CPU loop on a bounded sample
     m = 256
     sample = [x[i, :int(lengths[i])].clone() for i in range(m)]
@@ -67,7 +67,7 @@ for method in ("linear", "rectilinear", "cubic"):
     O.interpolation_transform(sample, method)
     cpu_s = time.perf_counter() - t0
     line = {"metric": "ragged_interpolation_series_per_sec", "method": method, "value": n / (ms / 1e3), "unit": "series/s",
-            "ms_per_launch_set": ms, "config": {"workload": "cfg5_raw_set", "series": n, "max_length": Lmax, "channels": C,
+            "ms_per_launch_set": ms, "staged": os.environ.get("NCDE_RAGGED_NO_STAGING") is None, "config": {"workload": "cfg5_raw_set", "series": n, "max_length": Lmax, "channels": C,
                                                 "missing": 0.75, "l2": "256 MB flush between timed calls"},
             "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": (alg / (ms / 1e3) / 1e9 / hbm) if hbm else None, "algorithmic_bytes": alg},
