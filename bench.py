@@ -288,7 +288,7 @@ def main():
     # ---- per-kernel timing: the same K steps again with every stage kernel bracketed by CUDA events on the launching
     # stream.  A separate pass because an event between two kernels removes their programmatic-dependent-launch overlap,
     # which would slow the timed region above; the per-kernel durations are what the roofline uses. ----
-    _capi.profile_enable(["field_fwd", "field_bwd", "hidden_fwd", "hidden_bwd", "hidden_wgrad"])
+    _capi.profile_enable(["field_fwd", "field_bwd", "hidden_fwd", "hidden_bwd", "hidden_wgrad", "other"])
     barrier()
     pe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     pe[0].record()
@@ -338,6 +338,23 @@ def main():
             traffic = json.load(open(tpath)).get(args.precision, {}).get("field_bwd_dram_bytes_per_launch")
         kernel_ms = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()
                      if v[1]}
+        # HBM streams of the path (north_star: achieved GB/s for the path-derivative and state streams).  dx_all: one launch per
+        # solve gathers dX/dt for every stage (reads B*C*4 per stage from derivs, writes B*Cp*4); records: what the forward pass
+        # saves per stage for the backward pass and the backward pass reads back.
+        n_stage_total = (K - 1) * 4
+        Cp = -(-cfg["C"] // (8 if args.precision == "bf16" else 4)) * (8 if args.precision == "bf16" else 4)
+        dx_bytes = n_stage_total * B * (cfg["C"] + Cp) * 4
+        dx_ms, dx_n = prof.get("other", (0.0, 0))
+        rec_bytes_per_series = ((cfg["n_layers"] + 1) * 256 + 4 * Cp) if args.precision == "bf16" else \
+            4 * (cfg["H"] + cfg["n_layers"] * cfg["HH"] + Cp)
+        rec_bytes = 2 * n_stage_total * B * rec_bytes_per_series   # written forward, read backward
+        hbm_streams = {
+            "peak_GBps": peaks.get("hbm_gbs"),
+            "dx_all": {"algorithmic_bytes_per_launch": dx_bytes, "avg_launch_us": dx_ms / max(dx_n, 1) * 1e3,
+                       "achieved_GBps": (dx_bytes / (dx_ms / max(dx_n, 1) * 1e-3) / 1e9) if dx_n else None,
+                       "timing": "CUDA events around the launch, same pass as roofline"},
+            "stage_records": {"bytes_per_step": rec_bytes, "GBps_over_step": rec_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "note": "spread over the whole sequential step: never the bound"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -363,6 +380,7 @@ def main():
                          "field_fwd": {"achieved": flops_fwd / avg_fwd / 1e12 if fwd_n else None,
                                        "avg_launch_us": avg_fwd * 1e6, "flops_per_launch": flops_fwd}},
             "kernel_ms": kernel_ms,
+            "hbm_streams": hbm_streams,
             "algorithmic_tflops": 12.0 * eval_flops_per_sample() * units_per_step / (ms_per_step * 1e-3) / 1e12,
         }
         if world == 1 and not args.no_cpu_baseline:

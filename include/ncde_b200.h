@@ -297,7 +297,7 @@ int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const float* y_out,
  * ---------------------------------------------------------------------------------------------------------- */
 enum ncde_prof_class {
     NCDE_PROF_HIDDEN_FWD = 0, NCDE_PROF_FIELD_FWD = 1, NCDE_PROF_FIELD_BWD = 2, NCDE_PROF_HIDDEN_BWD = 3,
-    NCDE_PROF_HIDDEN_WGRAD = 4, NCDE_PROF_OTHER = 5, NCDE_PROF_CLASSES = 6
+    NCDE_PROF_HIDDEN_WGRAD = 4, NCDE_PROF_OTHER = 5 /* dx_all: dX/dt of every stage, one launch per solve */, NCDE_PROF_CLASSES = 6
 };
 int ncde_profile_enable(int class_mask);
 int ncde_profile_read(double* ms, int64_t* count);

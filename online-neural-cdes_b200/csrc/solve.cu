@@ -732,7 +732,10 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             da.stage_stride = need_grad ? pl.stage_floats : (size_t)pl.PC * pl.Bp;
         }
         NCDE_REQUIRE(n_st_total <= 2147483647 && ceil_div(pl.B, 32) <= 65535, NCDE_ERR_UNSUPPORTED, "solve_fwd: grid too large");
-        dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
+        {
+            ProfScope ps(NCDE_PROF_OTHER, st);   // the path-derivative stream (bench.py reports its achieved HBM GB/s)
+            dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
+        }
         ++launches;
     }
 
