@@ -35,7 +35,10 @@ enum ncde_status {
 enum ncde_dtype { NCDE_F32 = 0, NCDE_F64 = 1 };
 enum ncde_path_kind { NCDE_PATH_LINEAR = 0, NCDE_PATH_CUBIC = 1 };
 enum ncde_method { NCDE_EULER = 0, NCDE_RK4_38 = 1, NCDE_DOPRI5 = 2 };
-enum ncde_act { NCDE_ACT_NONE = 0, NCDE_ACT_RELU = 1, NCDE_ACT_TANH = 2 };
+/* NCDE_ACT_GATE_IN (hidden layers only, out_dim == 2 * in_dim): out[i] = pre[i] for i < in_dim, out[in_dim + i] =
+ * sigmoid(pre[in_dim + i]) * in[i] — with W = [I ; W_f] this layer turns x into [x ; sigmoid(W_f x + b_f) * x], the reset-gated
+ * second input of GRUGatedVectorField (src/ncde/vector_fields/gating.py:35-61).  Fixed-grid fp32 path. */
+enum ncde_act { NCDE_ACT_NONE = 0, NCDE_ACT_RELU = 1, NCDE_ACT_TANH = 2, NCDE_ACT_GATE_IN = 3 };
 /* how the control enters the vector field (`vector_field_type` of torchcde.cdeint, modules/torchcde/torchcde/solver.py:112-137):
  * MATMUL      dz/dt = f(z) . dX/dt                 f: H -> H*C, contracted with the path derivative
  * EVALUATE    dz/dt = f([z, X(t)])                 f: H+C -> H, no contraction

@@ -164,7 +164,13 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
         if (l > 0)
             NCDE_REQUIRE(m.in_dim[l] == m.out_dim[l - 1], NCDE_ERR_INVALID, "solve: layer %d input %d != previous output %d",
                          l, m.in_dim[l], m.out_dim[l - 1]);
-        NCDE_REQUIRE(m.act[l] >= NCDE_ACT_NONE && m.act[l] <= NCDE_ACT_TANH, NCDE_ERR_INVALID, "solve: bad activation");
+        NCDE_REQUIRE(m.act[l] >= NCDE_ACT_NONE && m.act[l] <= NCDE_ACT_GATE_IN, NCDE_ERR_INVALID, "solve: bad activation");
+        if (m.act[l] == NCDE_ACT_GATE_IN) {
+            NCDE_REQUIRE(l < m.n_layers - 1 && m.out_dim[l] == 2 * m.in_dim[l], NCDE_ERR_INVALID,
+                         "solve: a gate-in layer must be a hidden layer with out_dim == 2 * in_dim");
+            NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_path, NCDE_ERR_UNSUPPORTED,
+                         "solve: gate-in layers (GRU-gated vector fields) run on the fixed-grid fp32 path only");
+        }
         pl->D[l] = m.in_dim[l];
         pl->Dp4[l] = (int)round_up(m.in_dim[l], 4);
     }

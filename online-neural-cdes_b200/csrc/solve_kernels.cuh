@@ -158,6 +158,7 @@ struct WgradArgs {
 // ---------------------------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == NCDE_ACT_RELU) return v > 0.f ? v : 0.f;   // clamp_min(0): NaN stays NaN either way is irrelevant here
     if (act == NCDE_ACT_TANH) return tanhf(v);
@@ -685,8 +686,17 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
             if (a.w_in_smem) acc = matvec4<true>(wsm + a.wsm_off[l] + o, ld, in + q * 4, R, Din, acc);
             else acc = matvec4<false>(a.WT[l] + o, ld, in + q * 4, R, Din, acc);
             const int act = a.act[l];
-            acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
-            acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+            if (act == NCDE_ACT_GATE_IN) {
+                // rows [0, Din) pass the input through (identity block of W), rows [Din, 2 Din) are sigmoid(W_f x + b_f) * x
+                if (o >= Din) {
+                    const float4 xi = *reinterpret_cast<const float4*>(in + (o - Din) * R + q * 4);
+                    acc.x = sigmoidf_(acc.x) * xi.x; acc.y = sigmoidf_(acc.y) * xi.y;
+                    acc.z = sigmoidf_(acc.z) * xi.z; acc.w = sigmoidf_(acc.w) * xi.w;
+                }
+            } else {
+                acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
+                acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+            }
             *reinterpret_cast<float4*>(out + o * R + q * 4) = acc;
         }
         __syncthreads();
@@ -717,8 +727,6 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
 // The (B, H*C) matrix of the reference (src/ncde/vector_fields/base.py:99-104, torchcde/solver.py:132) is never
 // materialised.  Thread (nt, mt) owns 4 consecutive n (= 4 channels of one h) x TM rows.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
-
 template <int TM, bool GATED = false>
 __global__ void __launch_bounds__(kThreads) field_fwd_kernel(const __grid_constant__ FieldArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -1203,8 +1211,20 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
             const int64_t b = b0 + r;
             float v = 0.f;
             if (b < a.B) {
-                v = cur[idx] * act_grad_from_output(outs[idx], act);
+                if (act == NCDE_ACT_GATE_IN && o >= Din) {
+                    // out = s * x with s = sigmoid(pre):  d/dpre = g x s (1 - s);  the direct d/dx = g s is stashed in the free
+                    // rows [Din, 2 Din) of the other buffer and added to the input gradient after the matrix product below
+                    const float x = l == 0 ? a.actT[0][(size_t)(o - Din) * a.Bp + b] : acts[((size_t)(l - 1) * a.Dmax + (o - Din)) * R + r];
+                    const float sg = x != 0.f ? outs[idx] / x : 0.f;
+                    const float g = cur[idx];
+                    nxt[idx] = g * sg;
+                    v = (g * x) * ((1.f - sg) * sg);
+                } else {
+                    v = cur[idx] * act_grad_from_output(outs[idx], act);
+                }
                 dpreT[(size_t)o * a.Bp + b] = v;
+            } else if (act == NCDE_ACT_GATE_IN && o >= Din) {
+                nxt[idx] = 0.f;
             }
             cur[idx] = v;
         }
@@ -1219,6 +1239,10 @@ __global__ void __launch_bounds__(kThreads) hidden_bwd_kernel(const __grid_const
             *reinterpret_cast<float4*>(nxt + i * R + q * 4) = acc;
         }
         __syncthreads();
+        if (act == NCDE_ACT_GATE_IN) {
+            for (int idx = tid; idx < Din * R; idx += kThreads) nxt[idx] += nxt[Din * R + idx];
+            __syncthreads();
+        }
         float* t = cur; cur = nxt; nxt = t;
     }
     // 3. RK adjoint update with dzs = cur[h][r]  (or, for the continuous adjoint, just hand dzs out)

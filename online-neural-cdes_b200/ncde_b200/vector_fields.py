@@ -80,8 +80,9 @@ class MinimalGatedVectorField(BaseVectorField):
 
 
 class GRUGatedVectorField(BaseVectorField):
-    """GRU-style gating (gating.py:35-61).  Parameter layout only (state_dict compatible with the reference): the fused solve does
-    not implement it yet — ``cdeint`` raises NotImplementedError when given this field."""
+    """GRU-style gating (gating.py:35-61): sigmoid_net(net(h)) * tanh_net(net(reset_net(h) * h)).  Lowered to one widened chain
+    that carries both evaluations of ``net_to_hh`` side by side (torchcde_b200.lowering._lower_gru); needs
+    2 * hidden_hidden_dim <= 128."""
 
     def additional_network_initialisation(self):
         assert self.sparsity is None, "sparsity not implemented for gated methods"

@@ -18,7 +18,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 PATH_LINEAR, PATH_CUBIC = 0, 1
 EULER, RK4_38, DOPRI5 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_GATE_IN = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
 VF_MATMUL, VF_EVALUATE, VF_DERIVATIVE = 0, 1, 2
 RAGGED_LINEAR, RAGGED_RECTILINEAR, RAGGED_CUBIC = 0, 1, 2

@@ -71,6 +71,9 @@ class MlpSpec:
                 z = z.relu()
             elif a == _capi.ACT_TANH:
                 z = z.tanh()
+            elif a == _capi.ACT_GATE_IN:
+                d = zin.shape[-1]
+                z = torch.cat([z[..., :d], z[..., d:].sigmoid() * zin], -1)
             if i == last and self.gate is not None:
                 z = torch.nn.functional.linear(zin, self.gate[0], self.gate[1]).sigmoid() * z
         return z.view(-1, hidden) if channels is None else z.view(-1, hidden, channels)
@@ -150,6 +153,69 @@ def _from_fx(func):
 
 
 _CACHE = {}
+_GRU_VALIDATED = {}
+
+
+def _lower_gru(func, hidden, channels, vector_field_type):
+    """GRUGatedVectorField (src/ncde/vector_fields/gating.py:35-61):
+
+        out = sigmoid(W_z net(x) + b_z) * tanh(W_r net(sigmoid(W_f x + b_f) * x) + b_r),   net = net_to_hh (shared weights)
+
+    lowered to ONE chain that carries both evaluations of ``net`` side by side:
+        layer 0   W = [I ; W_f], gate-in activation       x -> [x ; sigmoid(W_f x + b_f) * x]
+        layer k   W = blockdiag(W_k, W_k), ReLU            [a ; a'] -> [relu(W_k a + b_k) ; relu(W_k a' + b_k)]
+        last      tanh head [0 | W_r] gated by the sigmoid head [W_z | 0]
+    The widened matrices are assembled here with differentiable concatenations of the module's parameters, on every call (the
+    parameters change every optimiser step), so autograd folds the gradients the library returns for them back into W_f, W_k
+    (both diagonal blocks, every repeat of the shared Linear), W_z and W_r; the blocks of zeros / the identity receive gradients
+    that are discarded.  Needs 2 * hidden_hidden_dim <= 128 (the final-layer kernels' input width)."""
+    if getattr(func, "vector_field_type", vector_field_type) != vector_field_type:
+        raise ValueError("the vector field was built for vector_field_type='{}' but cdeint was called with '{}'".format(
+            func.vector_field_type, vector_field_type))
+    matmul = vector_field_type == "matmul"
+    mods = list(func.net_to_hh)
+    reset, sig, tanh = list(func.reset_net), list(func.sigmoid_net), list(func.tanh_net)
+    ok = len(reset) == 2 and isinstance(reset[0], torch.nn.Linear) and isinstance(reset[1], torch.nn.Sigmoid) and \
+        len(sig) == 2 and isinstance(sig[0], torch.nn.Linear) and isinstance(sig[1], torch.nn.Sigmoid) and \
+        len(tanh) == 2 and isinstance(tanh[0], torch.nn.Linear) and isinstance(tanh[1], torch.nn.Tanh) and \
+        len(mods) % 2 == 0 and all(isinstance(m, torch.nn.Linear) for m in mods[0::2]) and \
+        all(isinstance(m, torch.nn.ReLU) for m in mods[1::2])
+    if not ok:
+        raise NotImplementedError("unexpected structure of the GRU-gated vector field")
+    wf, bf = reset[0].weight, reset[0].bias
+    d0 = wf.shape[1]
+    zeros = wf.new_zeros
+    eye = torch.eye(d0, dtype=wf.dtype, device=wf.device)
+    layers = [(torch.cat([eye, wf], 0), torch.cat([zeros(d0), bf if bf is not None else zeros(d0)]), _capi.ACT_GATE_IN)]
+    for lin in mods[0::2]:
+        b = lin.bias if lin.bias is not None else zeros(lin.out_features)
+        layers.append((torch.block_diag(lin.weight, lin.weight), torch.cat([b, b]), _capi.ACT_RELU))
+    wz, wr = sig[0].weight, tanh[0].weight
+    pad = torch.zeros_like(wz)
+    gate = (torch.cat([wz, pad], 1), sig[0].bias)
+    layers.append((torch.cat([pad, wr], 1), tanh[0].bias, _capi.ACT_TANH))
+    spec = MlpSpec(layers, gate)
+    spec.vector_field_type = vector_field_type
+    spec.channels = channels
+    d_in = hidden if matmul else hidden + channels
+    d_out = hidden * channels if matmul else hidden
+    if d0 != d_in or wr.shape[0] != d_out:
+        raise ValueError("vector field maps {} -> {} but the solve (vector_field_type='{}') needs {} -> {}".format(
+            d0, wr.shape[0], vector_field_type, d_in, d_out))
+    hit = _GRU_VALIDATED.get(id(func))
+    if hit is None or hit() is not func:
+        nfe_before = getattr(func, "nfe", None)
+        with torch.no_grad():
+            probe = torch.linspace(-1.0, 1.0, 3 * d_in, dtype=wf.dtype, device=wf.device).view(3, d_in)
+            want = func(torch.zeros((), dtype=wf.dtype, device=wf.device), probe)
+            got = spec.reference_forward(probe, hidden, channels if matmul else None)
+            if want.shape != got.shape or not torch.allclose(want, got, rtol=1e-4, atol=1e-5):
+                raise NotImplementedError("GRU-gated vector field could not be lowered faithfully")
+        if nfe_before is not None:
+            func.nfe = nfe_before
+        import weakref
+        _GRU_VALIDATED[id(func)] = weakref.ref(func)
+    return spec
 
 
 def lower(func, hidden, channels, vector_field_type="matmul"):
@@ -163,8 +229,7 @@ def lower(func, hidden, channels, vector_field_type="matmul"):
     nfe_before = getattr(func, "nfe", None)
     gate = None
     if hasattr(func, "reset_net"):
-        raise NotImplementedError("GRU-gated vector fields (src/ncde/vector_fields/gating.py:35-61) are not implemented by the "
-                                  "fused solve; 'original' and 'minimal' are")
+        return _lower_gru(func, hidden, channels, vector_field_type)
     if hasattr(func, "ncde_mlp_spec"):
         layers = [[w, b, _ACT[a] if isinstance(a, str) else a] for (w, b, a) in func.ncde_mlp_spec()]
     elif isinstance(getattr(func, "net_to_hh", None), torch.nn.Sequential) and \

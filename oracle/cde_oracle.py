@@ -928,6 +928,22 @@ class MinimalGatedField(SharedMLPField):
         return out.view(-1, self.hidden_dim, self.input_dim) if self.matmul else out
 
 
+class GRUGatedField(MinimalGatedField):
+    """src/ncde/vector_fields/gating.py:35-61: sigmoid_net(net(h)) * tanh_net(net(reset_net(h) * h))."""
+
+    def __init__(self, input_dim, hidden_dim, hidden_hidden_dim, num_layers, vector_field_type="matmul"):
+        super().__init__(input_dim, hidden_dim, hidden_hidden_dim, num_layers, vector_field_type)
+        d0 = self.net_to_hh[0].in_features
+        self.reset_net = torch.nn.Sequential(torch.nn.Linear(d0, d0), torch.nn.Sigmoid())
+
+    def forward(self, t, h):
+        self.nfe += 1
+        inner = self.net_to_hh(h)
+        reset = self.net_to_hh(self.reset_net(h) * h)
+        out = self.sigmoid_net(inner) * self.tanh_net(reset)
+        return out.view(-1, self.hidden_dim, self.input_dim) if self.matmul else out
+
+
 class ToyField(torch.nn.Module):
     """experiments/sim_bm_toy_example.py:10-30."""
 

@@ -2,7 +2,8 @@
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_gated_golden.py
 
-MinimalGatedVectorField (src/ncde/vector_fields/gating.py:7-32, imported as a package so that its relative import works) under
+MinimalGatedVectorField and GRUGatedVectorField (src/ncde/vector_fields/gating.py:7-61, imported as a package so that the
+relative import works) under
 torchcde.cdeint, all three vector_field_type modes, adjoint=False: outputs and gradients of loss = sum(out * w).
 """
 import os
@@ -23,7 +24,7 @@ _a.preprocessing = _p
 sys.modules["autots"] = _a
 sys.modules["autots.preprocessing"] = _p
 import torchcde  # noqa: E402
-from src.ncde.vector_fields.gating import MinimalGatedVectorField  # noqa: E402
+from src.ncde.vector_fields.gating import GRUGatedVectorField, MinimalGatedVectorField  # noqa: E402
 
 g = torch.Generator().manual_seed(1357)
 torch.manual_seed(17)
@@ -35,6 +36,10 @@ cases = [
     ("min_eval_lin_rk4", "evaluate", 5, 7, 3, 6, 8, 2, "linear", "rk4", 1.0, "grid"),
     ("min_deriv_cub_rk4", "derivative", 3, 8, 4, 5, 12, 2, "cubic", "rk4", 1.0, "grid"),
     ("min_matmul_wide", "matmul", 6, 5, 33, 32, 16, 2, "linear", "rk4", 1.0, "grid"),
+    ("gru_matmul_lin_rk4", "matmul", 5, 7, 3, 6, 8, 2, "linear", "rk4", 1.0, "grid"),
+    ("gru_matmul_cub_rk4_half", "matmul", 4, 6, 5, 7, 9, 3, "cubic", "rk4", 0.5, "interval"),
+    ("gru_eval_rect_euler", "evaluate", 4, 5, 4, 8, 8, 1, "rectilinear", "euler", 1.0, "grid"),
+    ("gru_deriv_lin_rk4", "derivative", 5, 7, 3, 6, 8, 2, "linear", "rk4", 1.0, "grid"),
 ]
 for (name, vft, B, K, C, H, HH, n, interp, method, step, tmode) in cases:
     x = torch.randn(B, K, C, generator=g)
@@ -47,7 +52,8 @@ for (name, vft, B, K, C, H, HH, n, interp, method, step, tmode) in cases:
     else:
         coeffs = torchcde.natural_cubic_coeffs(x)
     X = torchcde.NaturalCubicSpline(coeffs) if interp == "cubic" else torchcde.LinearInterpolation(coeffs)
-    func = MinimalGatedVectorField(input_dim=C, hidden_dim=H, hidden_hidden_dim=HH, num_layers=n, vector_field_type=vft)
+    Field = GRUGatedVectorField if name.startswith("gru") else MinimalGatedVectorField
+    func = Field(input_dim=C, hidden_dim=H, hidden_hidden_dim=HH, num_layers=n, vector_field_type=vft)
     z0 = (torch.randn(B, H, generator=g) * 0.5).requires_grad_(True)
     t = X.grid_points if tmode == "grid" else X.interval
     w = torch.randn(B, len(t), H, generator=g)
