@@ -650,11 +650,12 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                               void* workspace, size_t workspace_bytes, int32_t* flags, int64_t* stats,
                               int64_t* launches_out, void* stream) {
     (void)flags;
-    NCDE_REQUIRE(p && z0 && z_out && workspace, NCDE_ERR_INVALID, "solve_fwd: null pointer");
-    NCDE_REQUIRE(!need_grad || saved, NCDE_ERR_INVALID, "solve_fwd: need_grad requires a saved buffer");
+    NCDE_REQUIRE(p && z0 && z_out, NCDE_ERR_INVALID, "solve_fwd: null pointer");
     Plan pl;
-    int rc = make_plan(p, &pl, true);
+    int rc = make_plan(p, &pl, true);   // first: an unsupported problem reports why (its workspace size query returned 0)
     if (rc != NCDE_OK) return rc;
+    NCDE_REQUIRE(workspace, NCDE_ERR_INVALID, "solve_fwd: null workspace");
+    NCDE_REQUIRE(!need_grad || saved, NCDE_ERR_INVALID, "solve_fwd: need_grad requires a saved buffer");
     NCDE_REQUIRE(p->method != NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_fwd: use ncde_solve_adaptive_fwd for dopri5");
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;

@@ -20,9 +20,7 @@ CASES = ["min_matmul_lin_rk4", "min_matmul_cub_rk4_half", "min_matmul_rect_euler
          "min_matmul_wide", "gru_matmul_lin_rk4", "gru_matmul_cub_rk4_half", "gru_eval_rect_euler", "gru_deriv_lin_rk4"]
 
 
-# GPU cases of the GRU-gated field run once they have been confirmed on a B200 (set by the commit that confirms them)
-GRU_ON_GPU = os.environ.get("NCDE_TEST_GRU_GPU") == "1"
-GPU_CASES = [c for c in CASES if GRU_ON_GPU or not c.startswith("gru")]
+GPU_CASES = CASES
 
 
 def _oracle_field(name):
@@ -153,8 +151,6 @@ def test_golden_gated(tc, gold, name):
                                    ("gru", "derivative", 72, 10, 30, 64, 48, 3, "linear")])
 def test_gated_against_oracle(tc, shape):
     kind, vft, B, K, C, H, HH, n, interp = shape
-    if kind == "gru" and not GRU_ON_GPU:
-        pytest.skip("GRU-gated field: GPU run not confirmed yet")
     g = torch.Generator().manual_seed(31)
     x = torch.randn(B, K, C, generator=g).cumsum(-2) * 0.2
     x[..., 0] = torch.arange(K, dtype=torch.float32)
