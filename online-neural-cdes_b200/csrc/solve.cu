@@ -179,7 +179,11 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     NCDE_REQUIRE(m.act[pl->F] == NCDE_ACT_TANH, NCDE_ERR_UNSUPPORTED, "solve: final activation must be tanh");
     pl->DF = pl->D[pl->F];
     pl->DFP = (int)round_up(pl->DF, 16);
-    NCDE_REQUIRE(pl->DF <= 128, NCDE_ERR_UNSUPPORTED, "solve: final-layer input width %d > 128 not supported", pl->DF);
+    // fp32 kernels take final-layer inputs up to 256 wide (the reference's hyper-parameter search reaches 196,
+    // experiments/configurations/configurations.json5:35); the tensor-core tiles are built for K <= 128
+    NCDE_REQUIRE(pl->DF <= (p->precision == NCDE_PREC_BF16 ? 128 : 256), NCDE_ERR_UNSUPPORTED,
+                 "solve: final-layer input width %d > %d not supported for this precision", pl->DF,
+                 p->precision == NCDE_PREC_BF16 ? 128 : 256);
     NCDE_REQUIRE(pl->Cp <= 128, NCDE_ERR_UNSUPPORTED, "solve: %d input channels > 128 not supported", p->C);
     int dmax = pl->Cp;
     for (int l = 0; l <= pl->F; ++l) dmax = pl->Dp4[l] > dmax ? pl->Dp4[l] : dmax;
@@ -264,6 +268,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     // hidden tiling
     int R = (int)round_up(ceil_div(pl->B, kNumSMs), 4);
     R = R < 4 ? 4 : (R > 32 ? 32 : R);
+    while (R > 4 && (size_t)2 * pl->Dmax * R * 4 > 48 * 1024) R -= 4;   // wide layers: fewer rows per CTA instead of failing
     pl->R = R;
     pl->n_rt = (int)ceil_div(pl->B, R);
     pl->hid_smem = (size_t)2 * pl->Dmax * R * 4;

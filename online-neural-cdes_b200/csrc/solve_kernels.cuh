@@ -949,9 +949,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         for (int q = 0; q < 16; ++q) accw[j][q] = 0.f;
     float accb[4] = {0.f, 0.f, 0.f, 0.f};
 
-    // dgrad mapping: thread (kd, md) owns 4 m x 8 k, k = {kd*4+j} U {DFP/2 + kd*4 + j}
+    // dgrad mapping: thread (kd, md) owns 4 m x 8 k per k-chunk, k = {kc*4+j} U {DFP/2 + kc*4 + j}, kc = kd, kd + 16, ...
+    // (one chunk per thread up to DFP = 128; wider final-layer inputs loop)
     const int KD = DFP / 8;
-    const int kd = tid % KD, md = tid / KD;
+    const int KDT = KD < 16 ? KD : 16;
+    const int kd = tid % KDT, md = tid / KDT;
     const bool dg_active = md < kChunk / 4;
     pdl_trigger();
     pdl_wait();  // gk comes from the previous kernels
@@ -1069,7 +1071,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
             }
         }
         // input gradient partial: P[b][k] = sum_n G[n][m] * W3[n][k]
-        if (dg_active) {
+        if (dg_active)
+        for (int kc = kd; kc < KD; kc += KDT) {
             float accp[4][8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1078,8 +1081,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 #pragma unroll 2
             for (int n = 0; n < S; ++n) {
                 const float4 gv = *reinterpret_cast<const float4*>(Gn + n * kGnStride + md * 4);
-                const float4 w0 = *reinterpret_cast<const float4*>(Wr + n * DFP + kd * 4);
-                const float4 w1 = *reinterpret_cast<const float4*>(Wr + n * DFP + DFP / 2 + kd * 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wr + n * DFP + kc * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wr + n * DFP + DFP / 2 + kc * 4);
                 const float gi[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1094,8 +1097,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
                 const int64_t b = b0 + md * 4 + i;
                 if (b < a.B) {
                     float* prow = a.P + ((size_t)g * a.B + b) * DFP;
-                    *reinterpret_cast<float4*>(prow + kd * 4) = make_float4(accp[i][0], accp[i][1], accp[i][2], accp[i][3]);
-                    *reinterpret_cast<float4*>(prow + DFP / 2 + kd * 4) =
+                    *reinterpret_cast<float4*>(prow + kc * 4) = make_float4(accp[i][0], accp[i][1], accp[i][2], accp[i][3]);
+                    *reinterpret_cast<float4*>(prow + DFP / 2 + kc * 4) =
                         make_float4(accp[i][4], accp[i][5], accp[i][6], accp[i][7]);
                 }
             }

@@ -82,7 +82,7 @@ class MinimalGatedVectorField(BaseVectorField):
 class GRUGatedVectorField(BaseVectorField):
     """GRU-style gating (gating.py:35-61): sigmoid_net(net(h)) * tanh_net(net(reset_net(h) * h)).  Lowered to one widened chain
     that carries both evaluations of ``net_to_hh`` side by side (torchcde_b200.lowering._lower_gru); needs
-    2 * hidden_hidden_dim <= 128."""
+    2 * hidden_hidden_dim <= 256."""
 
     def additional_network_initialisation(self):
         assert self.sparsity is None, "sparsity not implemented for gated methods"

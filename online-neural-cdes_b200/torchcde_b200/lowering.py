@@ -168,7 +168,7 @@ def _lower_gru(func, hidden, channels, vector_field_type):
     The widened matrices are assembled here with differentiable concatenations of the module's parameters, on every call (the
     parameters change every optimiser step), so autograd folds the gradients the library returns for them back into W_f, W_k
     (both diagonal blocks, every repeat of the shared Linear), W_z and W_r; the blocks of zeros / the identity receive gradients
-    that are discarded.  Needs 2 * hidden_hidden_dim <= 128 (the final-layer kernels' input width)."""
+    that are discarded.  Needs 2 * hidden_hidden_dim <= 256 (the final-layer kernels' input width)."""
     if getattr(func, "vector_field_type", vector_field_type) != vector_field_type:
         raise ValueError("the vector field was built for vector_field_type='{}' but cdeint was called with '{}'".format(
             func.vector_field_type, vector_field_type))

@@ -186,7 +186,7 @@ def test_gated_unsupported_combinations_are_loud(tc, gold):
         with pytest.raises(NotImplementedError):
             _run_cuda(tc, rec, **bad)
     import ncde_b200
-    gru = ncde_b200.GRUGatedVectorField(3, 6, 100, 2).cuda()   # 2 * hidden_hidden_dim > 128: wider than the final-layer kernels take
+    gru = ncde_b200.GRUGatedVectorField(3, 6, 160, 2).cuda()   # 2 * hidden_hidden_dim > 256: wider than the final-layer kernels take
     X = tc.LinearInterpolation(rec["coeffs"].cuda())
     with pytest.raises(NotImplementedError):
         tc.cdeint(X, gru, rec["z0"].cuda(), rec["t"].cuda(), adjoint=False, method="rk4", options={"step_size": 1.0})

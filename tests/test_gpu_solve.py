@@ -217,3 +217,37 @@ def test_batch_dims_and_errors(tc):
         tc.cdeint(X, func, z0, t.cuda(), adjoint=False, method="rk5")
     with pytest.warns(UserWarning):
         tc.cdeint(X, func, z0, t.cuda(), adjoint=False, method="rk4", options={"step_size": 1, "bogus": 2})
+
+
+@pytest.mark.parametrize("dims", [(160, 196, 5, 3), (256, 144, 3, 2)])
+def test_wide_layers_fp32(tc, dims):
+    """Widths beyond 128 — the reference's hyper-parameter search draws hidden_dim up to 256 and hidden_hidden_dim up to 196
+    (experiments/configurations/configurations.json5:34-35) — run on the fp32 path; the tensor-core tiles refuse them loudly."""
+    H, HH, C, n = dims
+    B, K = 40, 6
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(B, K, C, generator=g).cumsum(-2) * 0.2
+    x[..., 0] = torch.arange(K, dtype=torch.float32)
+    torch.manual_seed(12)
+    func = O.SharedMLPField(C, H, HH, n)
+    z0 = torch.randn(B, H, generator=g) * 0.5
+    w = torch.randn(B, K, H, generator=g)
+    Xr = O.LinearPath(x)
+    z0r = z0.clone().requires_grad_(True)
+    oref = O.cdeint(Xr, func, z0r, Xr.grid_points, adjoint=False, method="rk4", options={"step_size": 1})
+    (oref * w).sum().backward()
+    gref = {k: p.grad.clone() for k, p in func.named_parameters()}
+    for p in func.parameters():
+        p.grad = None
+    fc = func.cuda()
+    X = tc.LinearInterpolation(x.cuda())
+    z0c = z0.cuda().requires_grad_(True)
+    out = tc.cdeint(X, fc, z0c, X.grid_points, adjoint=False, method="rk4", options={"step_size": 1})
+    (out * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel(out, oref) <= TOL_FP32
+    assert rel(z0c.grad, z0r.grad) <= TOL_FP32
+    for k, p in fc.named_parameters():
+        assert rel(p.grad, gref[k]) <= TOL_FP32, k
+    with pytest.raises(NotImplementedError):
+        tc.cdeint(X, fc, z0c, X.grid_points, adjoint=False, method="rk4", options={"step_size": 1, "precision": "bf16"})
