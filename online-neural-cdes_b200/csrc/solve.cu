@@ -117,7 +117,10 @@ static size_t fwd_smem_floats(int DF, int S) {
     return (size_t)DF * S + (size_t)DF * kChunk + (size_t)(S / 4) * kChunk;
 }
 
-static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false) {
+// fixed_path: the stored-stage fixed-grid forward / backward (all-tensor-core records allowed);
+// fixed_adjoint: the fixed-grid continuous adjoint (same CUDA-core kernels, so evaluate / derivative and gated fields are allowed)
+static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false, bool fixed_adjoint = false) {
+    const bool fixed_kernels = fixed_path || fixed_adjoint;
     memset(pl, 0, sizeof(*pl));
     const ncde_mlp_t& m = p->mlp;
     NCDE_REQUIRE(p->B >= 1 && p->H >= 1 && p->C >= 1, NCDE_ERR_INVALID, "solve: B, H, C must be positive");
@@ -138,8 +141,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
                      "solve: vector_field_type evaluate / derivative is implemented for the fixed-grid solvers only");
         NCDE_REQUIRE(p->path.match == nullptr, NCDE_ERR_UNSUPPORTED,
                      "solve: vector_field_type evaluate / derivative is not implemented for gradient-matched paths");
-        NCDE_REQUIRE(fixed_path, NCDE_ERR_UNSUPPORTED,
-                     "solve: vector_field_type evaluate / derivative is not implemented for the continuous adjoint (use adjoint=False)");
+        NCDE_REQUIRE(fixed_kernels, NCDE_ERR_UNSUPPORTED,
+                     "solve: vector_field_type evaluate / derivative is implemented for the fixed-grid solvers only");
     }
     pl->B = (int)p->B; pl->H = p->H; pl->C = pl->vf ? 1 : p->C;
     pl->Bp = (int)round_up(p->B, kTcM);
@@ -147,8 +150,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
     pl->Cp = (int)round_up(pl->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
     pl->gated = m.W_gate != nullptr;
     if (pl->gated) {
-        NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_path, NCDE_ERR_UNSUPPORTED,
-                     "solve: gated vector fields run on the fixed-grid fp32 path only (no adaptive solver, no continuous adjoint)");
+        NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_kernels, NCDE_ERR_UNSUPPORTED,
+                     "solve: gated vector fields run on the fixed-grid fp32 path only (no adaptive solver)");
         NCDE_REQUIRE(m.n_layers < NCDE_MAX_LAYERS, NCDE_ERR_UNSUPPORTED, "solve: gated vector fields take at most %d layers",
                      NCDE_MAX_LAYERS - 1);
         pl->Cp = 2 * (int)round_up(pl->C, 2);   // (sigmoid, tanh) column pairs
@@ -168,7 +171,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false)
         if (m.act[l] == NCDE_ACT_GATE_IN) {
             NCDE_REQUIRE(l < m.n_layers - 1 && m.out_dim[l] == 2 * m.in_dim[l], NCDE_ERR_INVALID,
                          "solve: a gate-in layer must be a hidden layer with out_dim == 2 * in_dim");
-            NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_path, NCDE_ERR_UNSUPPORTED,
+            NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_kernels, NCDE_ERR_UNSUPPORTED,
                          "solve: gate-in layers (GRU-gated vector fields) run on the fixed-grid fp32 path only");
         }
         pl->D[l] = m.in_dim[l];
@@ -1517,6 +1520,10 @@ static void theta_layout(const ncde_problem_t* p, const Plan& pl, float* const* 
         tl->off_W[l] = off; off += round_up((size_t)p->mlp.out_dim[l] * p->mlp.in_dim[l], 64);
         if (gbias[l]) { tl->off_b[l] = off; off += round_up((size_t)p->mlp.out_dim[l], 64); } else tl->off_b[l] = (size_t)-1;
     }
+    if (pl.gated) {   // the sigmoid head of a gated final layer: slot F + 1, shaped like the last layer
+        tl->off_W[n] = off; off += round_up((size_t)p->mlp.out_dim[pl.F] * p->mlp.in_dim[pl.F], 64);
+        if (gbias[n]) { tl->off_b[n] = off; off += round_up((size_t)p->mlp.out_dim[pl.F], 64); } else tl->off_b[n] = (size_t)-1;
+    }
     tl->total = off;
 }
 
@@ -1532,13 +1539,15 @@ static size_t adjoint_workspace_floats(const ncde_problem_t* p, const Plan& pl) 
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
     size_t ntheta = 0;
     for (int l = 0; l <= pl.F; ++l) ntheta += round_up((size_t)p->mlp.out_dim[l] * p->mlp.in_dim[l], 64) + round_up(p->mlp.out_dim[l], 64);
+    if (pl.gated) ntheta += round_up((size_t)p->mlp.out_dim[pl.F] * p->mlp.in_dim[pl.F], 64) + round_up(p->mlp.out_dim[pl.F], 64);
+    if (pl.vf) n += 4 * (size_t)pl.Bp + per;
     n += 5 * (ntheta + per);
     return n;
 }
 
 extern "C" size_t ncde_solve_adjoint_workspace_bytes(const ncde_problem_t* p) {
     Plan pl;
-    if (!p || make_plan(p, &pl) != NCDE_OK) return 0;
+    if (!p || make_plan(p, &pl, false, true) != NCDE_OK) return 0;
     return adjoint_workspace_floats(p, pl) * 4 + 4096;
 }
 
@@ -1552,7 +1561,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                  "solve_adjoint_bwd: only fixed-grid adjoint methods (euler, rk4) are implemented");
     NCDE_REQUIRE(n_out >= 1, NCDE_ERR_INVALID, "solve_adjoint_bwd: no outputs");
     Plan pl;
-    int rc = make_plan(p, &pl);
+    int rc = make_plan(p, &pl, false, true);
     if (rc != NCDE_OK) return rc;
     NCDE_REQUIRE(workspace_bytes >= adjoint_workspace_floats(p, pl) * 4, NCDE_ERR_WORKSPACE,
                  "solve_adjoint_bwd: workspace of %zu bytes is too small", workspace_bytes);
@@ -1567,10 +1576,16 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     const ncde_mlp_t& m = p->mlp;
     const int NS = pl.n_stages;
     const size_t nHB = (size_t)pl.H * pl.Bp;
-    for (int l = 0; l <= pl.F; ++l) NCDE_REQUIRE(gW[l] != nullptr, NCDE_ERR_INVALID, "solve_adjoint_bwd: gW[%d] is null", l);
+    for (int l = 0; l <= pl.F + (pl.gated ? 1 : 0); ++l)
+        NCDE_REQUIRE(gW[l] != nullptr, NCDE_ERR_INVALID, "solve_adjoint_bwd: gW[%d] is null", l);
 
     Carver cv{(char*)workspace, 0, workspace_bytes};
     float* wpack = cv.take(pl.wpack_floats);
+    float* e0 = pl.vf ? cv.take(4 * (size_t)pl.Bp) : nullptr;
+    if (e0) {
+        fill_e0_kernel<<<(unsigned)ceil_div(4 * (int64_t)pl.Bp, 256), 256, 0, (cudaStream_t)stream>>>(e0, pl.Bp);
+        ++launches;
+    }
     float* yT = cv.take(nHB);
     float* aT = cv.take(nHB);
     float* a_stage = cv.take(nHB);
@@ -1593,8 +1608,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;
     if (use_tc) { rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem); if (rc == NCDE_OK) rc = (pl.bwd_ew == 16 ? opt_in_smem(tc_field_bwd_kernel<16>, pl.bwd_smem) : opt_in_smem(tc_field_bwd_kernel<8>, pl.bwd_smem)); }
-    else if (pl.TM == 8) { rc = opt_in_smem(field_fwd_kernel<8>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<8>, pl.bwd_smem); }
-    else { rc = opt_in_smem(field_fwd_kernel<4>, pl.fwd_smem); if (rc == NCDE_OK) rc = opt_in_smem(field_bwd_kernel<4>, pl.bwd_smem); }
+    else { rc = opt_in_field(pl, false); if (rc == NCDE_OK) rc = opt_in_field(pl, true); }
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_fwd_kernel, pl.hid_smem_fwd);
     if (rc == NCDE_OK) rc = opt_in_smem(hidden_bwd_kernel, pl.hid_smem_bwd);
     if (rc != NCDE_OK) return rc;
@@ -1617,11 +1631,14 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     ha.yT = yT; ha.KP = pl.KP; ha.comb_sign = -1.f;
     for (int l = 0; l <= pl.F; ++l) ha.actT[l] = stage + pl.act_off[l];
     ha.dXT = stage + pl.dx_off;
+    if (pl.vf) {   // X(t) / dX/dt(t) is evaluated by hidden_fwd into the first layer's input; the contraction runs against dX/dt = 1
+        ha.dXT = nullptr; ha.vf = pl.vf; ha.n_u = pl.PC; ha.uT = nullptr;
+    }
     ha.abf = use_tc ? (__nv_bfloat16*)(stage + pl.abf_off) : nullptr;
 
     FieldArgs fa;
     fill_field_args(fa, pl, wpack);
-    fa.actT = stage + pl.act_off[pl.F]; fa.dXT = stage + pl.dx_off;
+    fa.actT = stage + pl.act_off[pl.F]; fa.dXT = pl.vf ? e0 : stage + pl.dx_off;
     fa.P = P; fa.dW3acc = dW3acc; fa.db3acc = db3acc; fa.gkT = a_stage;
     TcFieldArgs ta;
     fill_tc_args(ta, pl, wpack);
@@ -1700,9 +1717,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                     { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
                 } else {
                     fa.koutT = kf[sg];
-                    const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
-                    else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                    NCDE_CUDA_OK(launch_field(pl, fa, false, st));
                 }
                 // adjoint stage input a_s = a + increment(ka)
                 AugCombineArgs ca;
@@ -1720,11 +1735,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                     NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
                 }
                 if (use_tc) { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
-                else {
-                    const dim3 fg(pl.n_hg, pl.n_bt);
-                    if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
-                    else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
-                }
+                else NCDE_CUDA_OK(launch_field(pl, fa, true, st));
                 hb.dz_out = ka[sg];
                 NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
                 launches += 2;
@@ -1742,10 +1753,17 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                 }
                 {
                     const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
+                    if (pl.gated) {   // interleaved columns: 2c = sigmoid head (slot F + 1), 2c + 1 = tanh head (slot F)
+                        unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+                            dW3acc, db3acc, ktheta[sg] + tl.off_W[pl.F + 1],
+                            tl.off_b[pl.F + 1] == (size_t)-1 ? nullptr : ktheta[sg] + tl.off_b[pl.F + 1], pl.H, pl.C, pl.Cp, pl.Hg,
+                            pl.Npad, pl.DF, pl.DFP, pl.Np, pl.n_bt, 2, 0);
+                        ++launches;
+                    }
                     unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
                         dW3acc, db3acc, ktheta[sg] + tl.off_W[pl.F],
                         tl.off_b[pl.F] == (size_t)-1 ? nullptr : ktheta[sg] + tl.off_b[pl.F], pl.H, pl.C, pl.Cp, pl.Hg, pl.Npad,
-                        pl.DF, pl.DFP, pl.Np, pl.n_bt);
+                        pl.DF, pl.DFP, pl.Np, pl.n_bt, pl.gated ? 2 : 1, pl.gated ? 1 : 0);
                     ++launches;
                 }
             }
@@ -1763,15 +1781,16 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
     }
     from_feature_major_kernel<<<tg, tb, 0, st>>>(aT, nullptr, grad_z0, pl.B, pl.Bp, pl.H);
     ++launches;
-    for (int l = 0; l <= pl.F; ++l) {
+    for (int l = 0; l <= pl.F + (pl.gated ? 1 : 0); ++l) {
         bool first = true;
         for (int j = 0; j < l; ++j) if (gW[j] == gW[l]) first = false;
         if (!first) continue;
-        const int64_t nw = (int64_t)m.out_dim[l] * m.in_dim[l];
+        const int ls = l > pl.F ? pl.F : l;   // the gate (slot F + 1) is shaped like the last layer
+        const int64_t nw = (int64_t)m.out_dim[ls] * m.in_dim[ls];
         axpy_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, st>>>(gW[l], theta + tl.off_W[l], nw);
         ++launches;
         if (gbias[l]) {
-            axpy_kernel<<<(unsigned)ceil_div((int64_t)m.out_dim[l], 256), 256, 0, st>>>(gbias[l], theta + tl.off_b[l], m.out_dim[l]);
+            axpy_kernel<<<(unsigned)ceil_div((int64_t)m.out_dim[ls], 256), 256, 0, st>>>(gbias[l], theta + tl.off_b[l], m.out_dim[ls]);
             ++launches;
         }
     }

@@ -70,6 +70,7 @@ struct HiddenFwdArgs {
     // uT [n_u][Bp] (precomputed for every stage by dx_all_kernel; may alias those rows of actT[0])
     const float* uT;
     int n_u;
+    int vf;                            // ncde_vf_type; with vf != 0 and uT == null the control rows are evaluated here, at the stage time
     float* dXT;                        // [Cp][Bp]  (tensor-core path, dx_row_major: [Bp][Cp])
     int dx_row_major;
     float* ddXT;                       // [Cp][Bp] or null: d2X/dt2 (cubic paths; time-gradient component of the adjoint)
@@ -622,7 +623,22 @@ __global__ void __launch_bounds__(kThreads) hidden_fwd_kernel(const __grid_const
         }
         buf0[h * R + r] = v;
     }
-    if (a.n_u) {
+    if (a.n_u && !a.uT) {
+        // continuous adjoint: the stage times are not known ahead of the launch loop's state, evaluate X(t) / dX/dt(t) in place
+        const int idxk = knot_index<float>(a.path.knots, a.path.K, t_stage);
+        const float frac = __fsub_rn(t_stage, a.path.knots[idxk]);
+        float* __restrict__ dst = a.actT[0] + (size_t)a.H * a.Bp;
+        for (int idx = tid; idx < R * a.n_u; idx += kThreads) {
+            const int r = idx / a.n_u, c = idx % a.n_u;
+            const int64_t b = b0 + r;
+            float v = 0.f;
+            if (b < a.B) {
+                v = a.vf == NCDE_VF_EVALUATE ? path_value(a.path, idxk, frac, b, c, a.n_u) : path_derivative(a.path, idxk, frac, b, c, a.n_u);
+                dst[(size_t)c * a.Bp + b] = v;
+            }
+            buf0[(a.H + c) * R + r] = v;
+        }
+    } else if (a.n_u) {
         float* __restrict__ dst = a.actT[0] + (size_t)a.H * a.Bp;
         for (int idx = tid; idx < a.n_u * R; idx += kThreads) {
             const int c = idx / R, r = idx % R;

@@ -311,6 +311,10 @@ class _AdjointFixedSolve(torch.autograd.Function):
             j = first_of_slot.setdefault(spec.slots[i], i)
             gW[i] = by_layer_w[j].data_ptr()
             gb[i] = by_layer_b[j].data_ptr() if j in by_layer_b else None
+        if getattr(spec, "gate", None) is not None:   # gate gradients: slot n_layers
+            n = len(spec.weights)
+            gW[n] = by_layer_w[n].data_ptr()
+            gb[n] = by_layer_b[n].data_ptr() if n in by_layer_b else None
         wbytes = L.ncde_solve_adjoint_workspace_bytes(ctypes.byref(problem))
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
         launches = ctypes.c_int64(0)
@@ -385,13 +389,11 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
     C = coeffs.shape[-1] // (4 if isinstance(X, NaturalCubicSpline) else 1)
     spec = lowering.lower(func, H, C, vector_field_type)
     if vector_field_type != 'matmul':
-        # f([z, X(t)]) / f([z, dX/dt(t)]) (solver.py:123-126): fixed-grid fp32 solves, gradients by backpropagation through the steps
+        # f([z, X(t)]) / f([z, dX/dt(t)]) (solver.py:123-126): fixed-grid fp32 solves; gradients by backpropagation through the
+        # steps or by the fixed-grid continuous adjoint
         if method == 'dopri5':
             raise NotImplementedError("vector_field_type='{}' is implemented for the fixed-grid solvers (euler, rk4) "
                                       "only".format(vector_field_type))
-        if adjoint:
-            raise NotImplementedError("vector_field_type='{}' is not implemented for the continuous adjoint; pass "
-                                      "adjoint=False".format(vector_field_type))
         if precision != 'fp32':
             raise NotImplementedError("vector_field_type='{}' runs in fp32 only".format(vector_field_type))
         if getattr(X, "gradient_matching_eps", None) is not None:
@@ -404,10 +406,9 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         if w.dtype != torch.float32:
             raise NotImplementedError("vector field parameters must be float32")
     if getattr(spec, "gate", None) is not None:
-        # MinimalGatedVectorField: fixed-grid fp32 solves, gradients by backpropagation through the steps
-        if method == 'dopri5' or adjoint or precision != 'fp32':
-            raise NotImplementedError("gated vector fields are implemented for method euler / rk4, adjoint=False and "
-                                      "precision fp32")
+        # gated fields: fixed-grid fp32 solves (backpropagation through the steps or the fixed-grid continuous adjoint)
+        if method == 'dopri5' or precision != 'fp32':
+            raise NotImplementedError("gated vector fields are implemented for method euler / rk4 and precision fp32")
         if coeffs.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError("gradients with respect to the control path are not implemented for gated vector fields")
 

@@ -182,7 +182,7 @@ def test_gated_against_oracle(tc, shape):
 @pytest.mark.gpu
 def test_gated_unsupported_combinations_are_loud(tc, gold):
     rec = dict(gold["min_matmul_lin_rk4"], name="min_matmul_lin_rk4")
-    for bad in (dict(adjoint=True), dict(method="dopri5"), dict(options={"step_size": 1.0, "precision": "bf16"})):
+    for bad in (dict(method="dopri5"), dict(options={"step_size": 1.0, "precision": "bf16"})):
         with pytest.raises(NotImplementedError):
             _run_cuda(tc, rec, **bad)
     import ncde_b200
@@ -190,3 +190,62 @@ def test_gated_unsupported_combinations_are_loud(tc, gold):
     X = tc.LinearInterpolation(rec["coeffs"].cuda())
     with pytest.raises(NotImplementedError):
         tc.cdeint(X, gru, rec["z0"].cuda(), rec["t"].cuda(), adjoint=False, method="rk4", options={"step_size": 1.0})
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the same modes under the fixed-grid continuous adjoint (adjoint=True is NeuralCDE's default, src/ncde/ncde.py:60)
+# ---------------------------------------------------------------------------------------------------------------
+ADJ_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adjoint_modes.pt")
+ADJ_CASES = ["orig_eval_lin_rk4", "orig_deriv_cub_rk4_half", "min_matmul_lin_rk4", "min_eval_rect_euler", "gru_matmul_lin_rk4",
+             "gru_deriv_lin_rk4"]
+
+
+@pytest.fixture(scope="module")
+def adj_gold():
+    return torch.load(ADJ_GOLDEN)
+
+
+def _adj_fields():
+    import ncde_b200
+    return {"orig": (O.SharedMLPField, ncde_b200.OriginalVectorField), "min": (O.MinimalGatedField, ncde_b200.MinimalGatedVectorField),
+            "gru": (O.GRUGatedField, ncde_b200.GRUGatedVectorField)}
+
+
+@pytest.mark.parametrize("name", ADJ_CASES)
+def test_oracle_adjoint_modes_match_reference(adj_gold, name):
+    rec = adj_gold[name]
+    d = rec["dims"]
+    func = _adj_fields()[rec["kind"]][0](d["C"], d["H"], d["HH"], d["n"], vector_field_type=rec["vector_field_type"])
+    func.load_state_dict(rec["state_dict"])
+    X = O.CubicPath(rec["coeffs"]) if rec["interp"] == "cubic" else O.LinearPath(rec["coeffs"])
+    z0 = rec["z0"].clone().requires_grad_(True)
+    out = O.cdeint(X, func, z0, rec["t"], adjoint=True, method=rec["method"], options=dict(rec["options"]),
+                   vector_field_type=rec["vector_field_type"])
+    (out * rec["w"]).sum().backward()
+    assert rel(out, rec["out"]) <= 1e-6
+    assert rel(z0.grad, rec["grad_z0"]) <= 1e-5
+    for n, p in func.named_parameters():
+        assert rel(p.grad, rec["grads"][n]) <= 1e-5, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ADJ_CASES)
+def test_golden_adjoint_modes(tc, adj_gold, name):
+    rec = adj_gold[name]
+    d = rec["dims"]
+    func = _adj_fields()[rec["kind"]][1](d["C"], d["H"], d["HH"], d["n"], vector_field_type=rec["vector_field_type"])
+    func.load_state_dict(rec["state_dict"])
+    func = func.cuda()
+    coeffs = rec["coeffs"].cuda()
+    X = tc.NaturalCubicSpline(coeffs) if rec["interp"] == "cubic" else tc.LinearInterpolation(coeffs)
+    z0 = rec["z0"].cuda().requires_grad_(True)
+    out = tc.cdeint(X, func, z0, rec["t"].cuda(), adjoint=True, vector_field_type=rec["vector_field_type"], method=rec["method"],
+                    options=dict(rec["options"]))
+    (out * rec["w"].cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel(out, rec["out"]) <= TOL
+    assert rel(z0.grad, rec["grad_z0"]) <= TOL
+    grads = {n: p.grad for n, p in func.named_parameters()}
+    assert sorted(grads) == sorted(rec["grads"])
+    for n, g in rec["grads"].items():
+        assert rel(grads[n], g) <= TOL, n

@@ -152,6 +152,6 @@ def test_vector_field_type_no_grad_forward_and_loud_errors(tc, gold):
         tc.cdeint(X, func, rec["z0"].cuda(), rec["t"].cuda(), adjoint=False, vector_field_type="nonsense")
     with pytest.raises(ValueError):   # field built for another mode
         tc.cdeint(X, func, rec["z0"].cuda(), rec["t"].cuda(), adjoint=False, vector_field_type="derivative", method="rk4")
-    for bad in (dict(adjoint=True), dict(method="dopri5"), dict(options={"step_size": 1.0, "precision": "bf16"})):
+    for bad in (dict(method="dopri5"), dict(options={"step_size": 1.0, "precision": "bf16"})):
         with pytest.raises(NotImplementedError):
             _run_cuda(tc, rec, **bad)
