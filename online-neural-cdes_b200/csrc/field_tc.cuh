@@ -55,6 +55,8 @@ struct TcFieldArgs {
     int prefetch;              // fixed-grid solves: the saved records this launch reads (dX/dt; in the backward pass also the
                                // activations) are older than the predecessor kernel, so their first tiles — and in the backward
                                // kernel the first recompute MMA — are issued ahead of griddepcontrol.wait, under the predecessor
+    int gk_early;              // form gk (global loads of gy / dz) BEFORE waiting for the accumulators instead of after (NCDE_GK_EARLY=1;
+                               // experimental: 17 % of the backward kernel's stall samples sit on those loads, profiles/README.md)
     int p_transposed;          // P is written as bf16 P^T[g][k][Bp] (coalesced; consumed by p_reduce) instead of fp32 [g][b][k]
     const float* gy1T;         // [H][Bp] or null (then gkT is read)
     float gcoef;
@@ -628,7 +630,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_layout(int Npad, int CpB, int EW) {
 // EW = number of epilogue warps (8 or 16; with 16, four warps share each TMEM lane quarter and split the columns).  Measured on
 // cfg 5: 8 warps 36.8 us per launch, 16 warps 40.6 us — the epilogue is not occupancy-bound, so 8 is the default (NCDE_BWD_EW=16
 // selects the other instantiation for A/B runs).
-template <int EW>
+template <int EW, bool GKE = false>   // GKE: form gk before waiting for the accumulators (experimental, see TcFieldArgs::gk_early)
 __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __grid_constant__ TcFieldArgs a,
                                                                        const __grid_constant__ TcMaps maps) {
     constexpr int kEpi = EW * 32, kAll = EW * 32 + 32, kCg = EW / 4;
@@ -787,6 +789,21 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
             const int64_t b0 = row_begin + (int64_t)i * kTcM;
             const int64_t b = b0 + row;
             const bool row_ok = b < a.B;
+            // gk of this thread's (at most 4) units, loaded while the recompute MMA of the tile is still in flight
+            float gk_pre[4] = {0.f, 0.f, 0.f, 0.f};
+            if (GKE && a.gy1T) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int u = u_begin + k4;
+                    const int h = g * a.Hg + u / P;
+                    if (u < u_end && row_ok && h < a.H) {
+                        const size_t off = (size_t)h * a.Bp + b;
+                        float gk = a.gcoef * __ldg(a.gy1T + off);
+                        for (int q = 0; q < a.n_dz; ++q) gk = fmaf(a.dzcoef[q], __ldg(a.dzT[q] + off), gk);
+                        gk_pre[k4] = gk;
+                    }
+                }
+            }
             mbar_wait(full_x, ph);
             mbar_wait(pre_bar, ph);
             tc_fence_after();
@@ -795,7 +812,10 @@ __global__ void __launch_bounds__(EW * 32 + 32, 1) tc_field_bwd_kernel(const __g
                 const int hl = u / P, c_begin = (u % P) * cw, c_end = min(a.Cp, c_begin + cw);
                 const int h = g * a.Hg + hl;
                 float gk = 0.f;
-                if (row_ok && h < a.H) {
+                if (GKE && a.gy1T && u - u_begin < 4) {
+                    const int k4 = u - u_begin;
+                    gk = k4 == 0 ? gk_pre[0] : (k4 == 1 ? gk_pre[1] : (k4 == 2 ? gk_pre[2] : gk_pre[3]));
+                } else if (row_ok && h < a.H) {
                     const size_t off = (size_t)h * a.Bp + b;
                     if (a.gy1T) {
                         gk = a.gcoef * __ldg(a.gy1T + off);

@@ -565,6 +565,11 @@ static int launch_tc_bwd(const Plan& pl, TcFieldArgs& ta, const TcMapSet& ms, cu
     if (pl.bwd_ew == 16)
         NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel<16>, dim3(pl.n_hg, pl.n_bt), dim3(16 * 32 + 32), pl.bwd_smem, st, ta, ms.maps));
     else
+        if (ta.gk_early) {   // experimental variant (NCDE_GK_EARLY=1), separate instantiation so that the default kernel's code is untouched
+            static bool opted = false;
+            if (!opted) { const int rc_o = opt_in_smem(tc_field_bwd_kernel<8, true>, pl.bwd_smem); if (rc_o != NCDE_OK) return rc_o; opted = true; }
+            NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel<8, true>, dim3(pl.n_hg, pl.n_bt), dim3(8 * 32 + 32), pl.bwd_smem, st, ta, ms.maps));
+        } else
         NCDE_CUDA_OK(launch_pdl(tc_field_bwd_kernel<8>, dim3(pl.n_hg, pl.n_bt), dim3(8 * 32 + 32), pl.bwd_smem, st, ta, ms.maps));
     return NCDE_OK;
 }
@@ -1137,6 +1142,10 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
                         // dL/dk_i = c_i dt gy1 + sum over later stages q of d(stage input q)/dk_i * dz_q; the dz_q live in gkT[q]
                         ta.gy1T = gyT;
                         ta.p_transposed = 1;
+                        {
+                            static const bool gk_early = getenv("NCDE_GK_EARLY") != nullptr;
+                            ta.gk_early = gk_early ? 1 : 0;
+                        }
                         ta.n_dz = 0;
                         if (p->method == NCDE_RK4_38) {
                             ta.gcoef = (i == 0 || i == 3) ? dt * 0.125f : 3.f * (dt * 0.125f);
