@@ -399,7 +399,7 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         if getattr(X, "gradient_matching_eps", None) is not None:
             raise NotImplementedError("vector_field_type='{}' is not implemented for gradient-matched paths".format(
                 vector_field_type))
-        if coeffs.requires_grad and torch.is_grad_enabled():
+        if coeffs.requires_grad and torch.is_grad_enabled() and not adjoint:   # (with adjoint=True the path gets no gradient: below)
             raise NotImplementedError("gradients with respect to the control path need vector_field_type='matmul'")
     for w in spec.weights:
         _capi.require_cuda(w)
@@ -409,7 +409,7 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         # gated fields: fixed-grid fp32 solves (backpropagation through the steps or the fixed-grid continuous adjoint)
         if method == 'dopri5' or precision != 'fp32':
             raise NotImplementedError("gated vector fields are implemented for method euler / rk4 and precision fp32")
-        if coeffs.requires_grad and torch.is_grad_enabled():
+        if coeffs.requires_grad and torch.is_grad_enabled() and not adjoint:
             raise NotImplementedError("gradients with respect to the control path are not implemented for gated vector fields")
 
     if coeffs.requires_grad and torch.is_grad_enabled():
