@@ -57,8 +57,59 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built):
     assert b"forward_fill" in built.ncde_last_error()
     assert built.ncde_rectilinear_prepare(0, 1, 1, 1, 2, 3, 7, None, None) == _capi.ERR_INVALID
     assert built.ncde_natural_cubic_coeffs(0, 1, 1, 1, 1, 1, 3, 1, 1, None) == _capi.ERR_INVALID
+    # entry points added with the widened rows: argument validation happens before any CUDA call
+    assert built.ncde_ragged_interpolate(0, 0, None, None, None, 1, 4, 3, 0, 1, 0, 0, None, None, None) == _capi.ERR_INVALID
+    assert built.ncde_ragged_interpolate(7, 0, 1, 1, 1, 1, 4, 3, 0, 1, 0, 0, 1, None, None) == _capi.ERR_INVALID
+    assert b"unknown method" in built.ncde_last_error()
+    assert built.ncde_ragged_interpolate(1, 0, 1, 1, 1, 1, 4, 3, 5, 1, 0, 0, 1, None, None) == _capi.ERR_INVALID   # time index 5 of 3 channels
+    assert built.ncde_ragged_interpolate(0, 0, 1, 1, 1, 1, 4, 3, 0, 1, 1, 0, 1, None, None) == _capi.ERR_INVALID   # intensity needs rectilinear
+    assert built.ncde_ragged_scratch_bytes(2, 0, 10, 8, 3) > built.ncde_ragged_scratch_bytes(0, 0, 10, 8, 3) > 0
+    assert built.ncde_path_eval_bwd(0, 0, None, 1, 4, 3, None, 1, 0, None, None, None) == _capi.ERR_INVALID
+    assert built.ncde_path_eval_bwd(5, 0, 1, 1, 4, 3, 1, 1, 0, 1, 1, None) == _capi.ERR_INVALID
     with pytest.raises(ValueError):
         _capi.check(_capi.ERR_INVALID)
+
+
+def test_problem_validation_without_a_gpu(built):
+    """make_plan rejects malformed / unsupported problems before touching the device: the workspace query returns 0 and the
+    solve entry point reports why (mapped to ValueError / NotImplementedError by _capi.check)."""
+    import ctypes
+    from torchcde_b200 import _capi
+
+    def problem(H=8, C=3, HH=8, vf=0, gated=False, precision=0, method=1, act0=1):
+        p = _capi.Problem()
+        p.B, p.H, p.C, p.method, p.precision, p.vf_type = 4, H, C, method, precision, vf
+        d0 = H + (C if vf else 0)
+        out = H if vf else H * C
+        m = p.mlp
+        m.n_layers = 2
+        m.in_dim[0], m.out_dim[0], m.act[0] = d0, HH, act0
+        m.in_dim[1], m.out_dim[1], m.act[1] = HH, out, _capi.ACT_TANH
+        m.W[0] = m.W[1] = 1          # never dereferenced by the checks exercised here
+        if gated:
+            m.W_gate = 1
+        p.grid.n_steps = 0
+        return p
+
+    ok = problem()
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(ok), 0) > 0
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(ok), 1) > 0
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(ok), 2) > 0          # with the path gradient
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(problem(vf=1)), 1) > 0
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(problem(vf=1)), 2) == 0   # path gradient needs matmul
+    assert built.ncde_solve_workspace_bytes(ctypes.byref(problem(gated=True)), 1) > 0
+    assert built.ncde_solve_adjoint_workspace_bytes(ctypes.byref(problem(vf=2, gated=True))) > 0
+    for bad, exc in [(problem(vf=1, precision=1), NotImplementedError),      # evaluate mode on bf16 tiles
+                     (problem(gated=True, precision=1), NotImplementedError),
+                     (problem(vf=3), ValueError),
+                     (problem(HH=300), NotImplementedError),                   # final-layer input wider than 256
+                     (problem(act0=_capi.ACT_GATE_IN), ValueError)]:          # gate-in layer needs out_dim == 2 * in_dim
+        assert built.ncde_solve_workspace_bytes(ctypes.byref(bad), 0) == 0
+        rc = built.ncde_solve_fwd(ctypes.byref(bad), 1, 1, None, 0, None, 0, None, None, None, None)
+        with pytest.raises(exc):
+            _capi.check(rc)
+    # adaptive / adaptive-adjoint entry points refuse the fixed-grid-only modes
+    assert built.ncde_solve_adjoint_adaptive_workspace_bytes(ctypes.byref(problem(vf=1, method=2))) == 0
 
 
 def test_product_refuses_cpu_tensors(built):
