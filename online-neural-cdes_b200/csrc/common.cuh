@@ -28,6 +28,25 @@ void set_error(const char* fmt, ...);
         }                                 \
     } while (0)
 
+// Every entry point runs on the device that owns its buffers, whatever the caller's current device is, and restores the
+// caller's device on return (a model on cuda:1 called while cuda:0 is current must not launch on cuda:0).
+struct DeviceGuard {
+    int prev = -1, target = -1;
+    explicit DeviceGuard(const void* device_ptr) {
+        cudaPointerAttributes at;
+        if (device_ptr && cudaPointerGetAttributes(&at, device_ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            target = at.device;
+            if (cudaGetDevice(&prev) == cudaSuccess && prev != target) cudaSetDevice(target);
+            else prev = -1;
+        } else {
+            cudaGetLastError();   // a host pointer on an old driver reports an error: not ours to surface
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -622,6 +622,7 @@ using namespace ncde;
 
 extern "C" int ncde_forward_fill(int dtype, const void* x, void* out, int64_t n_series, int64_t L, int64_t C,
                                  void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && out && n_series >= 0 && L >= 1 && C >= 1, NCDE_ERR_INVALID, "forward_fill: bad arguments");
     if (n_series == 0) return NCDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -633,6 +634,7 @@ extern "C" int ncde_forward_fill(int dtype, const void* x, void* out, int64_t n_
 
 extern "C" int ncde_rectilinear_prepare(int dtype, const void* x, void* out, int64_t n_series, int64_t L,
                                         int64_t C, int time_index, int32_t* flags, void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && out && n_series >= 0 && L >= 1 && C >= 1, NCDE_ERR_INVALID, "rectilinear: bad arguments");
     NCDE_REQUIRE(time_index >= 0 && time_index < C, NCDE_ERR_INVALID, "Time index must be in [0, %lld], was given %d.",
                  (long long)C - 1, time_index);
@@ -646,6 +648,7 @@ extern "C" int ncde_rectilinear_prepare(int dtype, const void* x, void* out, int
 
 extern "C" int ncde_linear_fill_missing(int dtype, void* x, const void* t, int64_t n_series, int64_t L, int64_t C,
                                         void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && t && n_series >= 0 && L >= 2 && C >= 1, NCDE_ERR_INVALID, "linear_fill_missing: bad arguments");
     if (n_series == 0) return NCDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -667,6 +670,7 @@ extern "C" int ncde_linear_fill_missing(int dtype, void* x, const void* t, int64
 
 extern "C" int ncde_linear_derivs(int dtype, const void* coeffs, const void* t, void* derivs, int64_t n_series,
                                   int64_t K, int64_t C, void* stream) {
+    ncde::DeviceGuard device_guard(coeffs);
     NCDE_REQUIRE(coeffs && t && derivs && K >= 2 && C >= 1, NCDE_ERR_INVALID, "linear_derivs: bad arguments");
     if (n_series == 0) return NCDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -679,6 +683,7 @@ extern "C" int ncde_linear_derivs(int dtype, const void* coeffs, const void* t, 
 extern "C" int ncde_path_eval(int kind, int dtype, const void* coeffs, const void* derivs, const void* knots,
                               int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t, int deriv,
                               void* out, int64_t* index_out, void* stream) {
+    ncde::DeviceGuard device_guard(coeffs);
     NCDE_REQUIRE(coeffs && knots && tq && out && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval: bad arguments");
     NCDE_REQUIRE(kind == NCDE_PATH_LINEAR || kind == NCDE_PATH_CUBIC, NCDE_ERR_INVALID, "path_eval: bad kind");
     NCDE_REQUIRE(!(kind == NCDE_PATH_LINEAR && deriv && !derivs), NCDE_ERR_INVALID,
@@ -710,6 +715,7 @@ extern "C" size_t ncde_ragged_scratch_bytes(int method, int dtype, int64_t n_ser
 extern "C" int ncde_ragged_interpolate(int method, int dtype, const void* x, const int32_t* lengths, void* out,
                                        int64_t n_series, int64_t Lmax, int64_t C, int time_index, int initial_nan_to_zero,
                                        int intensity, int pad, void* scratch, int32_t* flags, void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && lengths && out && scratch, NCDE_ERR_INVALID, "ragged_interpolate: null pointer");
     NCDE_REQUIRE(method == NCDE_RAGGED_LINEAR || method == NCDE_RAGGED_RECTILINEAR || method == NCDE_RAGGED_CUBIC,
                  NCDE_ERR_INVALID, "ragged_interpolate: unknown method %d", method);
@@ -786,6 +792,7 @@ extern "C" int ncde_ragged_interpolate(int method, int dtype, const void* x, con
 extern "C" int ncde_path_eval_bwd(int kind, int dtype, const void* knots, int64_t n_series, int64_t K, int64_t C,
                                   const void* tq, int64_t n_t, int deriv, const void* grad_out, void* grad_coeffs,
                                   void* stream) {
+    ncde::DeviceGuard device_guard(knots);
     NCDE_REQUIRE(knots && tq && grad_out && grad_coeffs && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval_bwd: bad arguments");
     NCDE_REQUIRE(kind == NCDE_PATH_LINEAR || kind == NCDE_PATH_CUBIC, NCDE_ERR_INVALID, "path_eval_bwd: bad kind");
     if (n_series == 0 || n_t == 0) return NCDE_OK;
@@ -851,6 +858,7 @@ __global__ void logsig_windows_kernel(const T* __restrict__ x, const int32_t* __
 
 extern "C" int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx, const void* wscale, void* out, int64_t n_series,
                                    int64_t Lp, int d, int depth, int W, void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && idx && out && Lp >= 1 && d >= 1 && W >= 0, NCDE_ERR_INVALID, "logsig_windows: bad arguments");
     NCDE_REQUIRE(depth == 1 || depth == 2, NCDE_ERR_UNSUPPORTED, "logsig_windows: depth %d is not implemented (1 and 2 are)", depth);
     if (n_series == 0) return NCDE_OK;
@@ -896,6 +904,7 @@ __global__ void hybrid_compact_kernel(const T* __restrict__ full, const int32_t*
 
 extern "C" int ncde_hybrid_compact(int dtype, const void* full, const int32_t* chan_kind, void* out, int32_t* counts,
                                    int64_t n_series, int64_t K, int64_t C, void* stream) {
+    ncde::DeviceGuard device_guard(full);
     NCDE_REQUIRE(full && chan_kind && out && counts && K >= 1 && C >= 1, NCDE_ERR_INVALID, "hybrid_compact: bad arguments");
     NCDE_REQUIRE(n_series < (1ll << 31), NCDE_ERR_UNSUPPORTED, "hybrid_compact: too many series");
     if (n_series == 0) return NCDE_OK;
@@ -982,6 +991,7 @@ __global__ void path_eval_smooth_kernel(const T* __restrict__ coeffs, const T* _
 
 extern "C" int ncde_smooth_matching_coeffs(int dtype, const void* coeffs, void* out, int64_t n_series, int64_t K, int64_t C,
                                            double eps, int terms, void* stream) {
+    ncde::DeviceGuard device_guard(coeffs);
     NCDE_REQUIRE(coeffs && out && K >= 3 && C >= 1, NCDE_ERR_INVALID, "smooth_matching_coeffs: bad arguments");
     NCDE_REQUIRE(terms == 4 || terms == 6, NCDE_ERR_INVALID, "smooth_matching_coeffs: terms must be 4 (cubic) or 6 (quintic)");
     NCDE_REQUIRE(eps > 0 && eps <= 1, NCDE_ERR_INVALID, "gradient_matching_eps must be in (0, 1]");
@@ -996,6 +1006,7 @@ extern "C" int ncde_smooth_matching_coeffs(int dtype, const void* coeffs, void* 
 extern "C" int ncde_path_eval_smooth(int dtype, const void* coeffs, const void* derivs, const void* knots, const void* match,
                                      int terms, double eps, int64_t n_series, int64_t K, int64_t C, const void* tq, int64_t n_t,
                                      int deriv, void* out, void* stream) {
+    ncde::DeviceGuard device_guard(coeffs);
     NCDE_REQUIRE(coeffs && derivs && knots && tq && out && K >= 2 && C >= 1, NCDE_ERR_INVALID, "path_eval_smooth: bad arguments");
     NCDE_REQUIRE(!match || terms == 4 || terms == 6, NCDE_ERR_INVALID, "path_eval_smooth: terms must be 4 or 6");
     if (n_series == 0 || n_t == 0) return NCDE_OK;
@@ -1015,6 +1026,7 @@ extern "C" size_t ncde_cubic_scratch_bytes(int dtype, int64_t n_series, int64_t 
 
 extern "C" int ncde_natural_cubic_coeffs(int dtype, const void* x, const void* t, void* out, int64_t n_series,
                                          int64_t L, int64_t C, int version, void* scratch, void* stream) {
+    ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && t && out && scratch, NCDE_ERR_INVALID, "natural_cubic_coeffs: null pointer");
     NCDE_REQUIRE(L >= 2 && C >= 1 && (version == 0 || version == 1), NCDE_ERR_INVALID,
                  "Must have a time dimension of size at least 2.");

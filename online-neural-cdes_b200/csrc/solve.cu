@@ -662,6 +662,7 @@ extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backwa
 extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void* saved, int need_grad,
                               void* workspace, size_t workspace_bytes, int32_t* flags, int64_t* stats,
                               int64_t* launches_out, void* stream) {
+    ncde::DeviceGuard device_guard(z0);
     (void)flags;
     NCDE_REQUIRE(p && z0 && z_out, NCDE_ERR_INVALID, "solve_fwd: null pointer");
     Plan pl;
@@ -899,6 +900,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
 extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, const void* saved, float* grad_z0,
                               float* const* gW, float* const* gbias, float* grad_coeffs, void* workspace,
                               size_t workspace_bytes, int64_t* launches_out, void* stream) {
+    ncde::DeviceGuard device_guard(grad_out);
     NCDE_REQUIRE(p && grad_out && saved && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID, "solve_bwd: null pointer");
     Plan pl;
     int rc = make_plan(p, &pl, true);
@@ -1326,6 +1328,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0, float* z_out, void* workspace,
                                        size_t workspace_bytes, int64_t* stats, int64_t* launches_out, void* stream) {
+    ncde::DeviceGuard device_guard(z0);
     NCDE_REQUIRE(p && z0 && z_out && workspace, NCDE_ERR_INVALID, "solve_adaptive_fwd: null pointer");
     NCDE_REQUIRE(p->method == NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_adaptive_fwd: method must be dopri5");
     Plan pl;
@@ -1564,6 +1567,7 @@ extern "C" int ncde_solve_adjoint_bwd(const ncde_problem_t* p, const int64_t* in
                                       const float* y_out, const float* grad_out, float* grad_z0, float* const* gW,
                                       float* const* gbias, void* workspace, size_t workspace_bytes, int64_t* launches_out,
                                       void* stream) {
+    ncde::DeviceGuard device_guard(workspace);
     NCDE_REQUIRE(p && interval_steps && y_out && grad_out && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID,
                  "solve_adjoint_bwd: null pointer");
     NCDE_REQUIRE(p->method == NCDE_EULER || p->method == NCDE_RK4_38, NCDE_ERR_UNSUPPORTED,
@@ -1837,6 +1841,7 @@ extern "C" size_t ncde_solve_adjoint_adaptive_workspace_bytes(const ncde_problem
 extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const float* y_out, const float* grad_out,
                                                float* grad_z0, float* const* gW, float* const* gbias, void* workspace,
                                                size_t workspace_bytes, int64_t* stats, int64_t* launches_out, void* stream) {
+    ncde::DeviceGuard device_guard(y_out);
     NCDE_REQUIRE(p && y_out && grad_out && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID,
                  "solve_adjoint_adaptive_bwd: null pointer");
     NCDE_REQUIRE(p->method == NCDE_DOPRI5, NCDE_ERR_INVALID, "solve_adjoint_adaptive_bwd: method must be dopri5");

@@ -161,12 +161,17 @@ class _AdjointAdaptiveSolve(torch.autograd.Function):
         return (None, None, None, None, None, None, None, grad_z0, None) + tuple(grads)
 
 
-def solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs):
+def solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs, coeffs=None):
+    """``coeffs``: the coefficient tensor cdeint prepared for the autograd graph (detached when the path is not listed in
+    adjoint_params, solver.py:201-221); defaults to X._coeffs."""
     from . import solver as S
     options = dict(options)
     precision = options.pop("precision", S.default_precision)
     _check_options(options)
-    needs_grad = torch.is_grad_enabled() and (z0.requires_grad or any(w.requires_grad for w in spec.weights))
+    if coeffs is None:
+        coeffs = X._coeffs
+    needs_grad = torch.is_grad_enabled() and (z0.requires_grad or coeffs.requires_grad or
+                                              any(p.requires_grad for p, _, _ in spec.unique_params))
     batch_shape = z0.shape[:-1]
     H = z0.shape[-1]
     Xf = X if len(batch_shape) == 1 else S._flatten_path(X)
@@ -197,5 +202,5 @@ def solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs):
         _check_options(adj_options)
     params = [p for p, _, _ in spec.unique_params]
     out = _AdjointAdaptiveSolve.apply(Xf, spec, precision, (kwargs["rtol"], kwargs["atol"], options),
-                                      (adj_rtol, adj_atol, adj_options), t_host, func, z0f, X._coeffs, *params)
+                                      (adj_rtol, adj_atol, adj_options), t_host, func, z0f, coeffs, *params)
     return out.reshape(T, *batch_shape, H)

@@ -45,8 +45,6 @@ class NaturalCubicSpline(interpolation_base.InterpolationBase):
         _capi.require_cuda(coeffs)
         if t is None:
             t = misc.default_times(coeffs.size(-2) + 1, coeffs.dtype, coeffs.device)
-        elif not hasattr(t, "_ncde_host"):
-            misc.attach_host(t, t.detach().cpu())
         t_dev = t.to(coeffs.device)
         if t_dev is not t:
             misc.attach_host(t_dev, misc.host_values(t))
@@ -74,6 +72,11 @@ class NaturalCubicSpline(interpolation_base.InterpolationBase):
     @property
     def _three_d(self):
         return self._coeffs[..., 3 * self._channels:]
+
+    @property
+    def _t_host(self):
+        """Host mirror of the knots; refreshed when the buffer was edited in place or reloaded."""
+        return misc.host_values(self._t)
 
     @property
     def grid_points(self):

@@ -83,8 +83,6 @@ class LinearInterpolation(interpolation_base.InterpolationBase):
         _capi.require_cuda(coeffs)
         if t is None:
             t = misc.default_times(coeffs.size(-2), coeffs.dtype, coeffs.device)
-        elif not hasattr(t, "_ncde_host"):
-            misc.attach_host(t, t.detach().cpu())
         t_dev = t.to(coeffs.device)
         if t_dev is not t:
             misc.attach_host(t_dev, misc.host_values(t))
@@ -94,10 +92,15 @@ class LinearInterpolation(interpolation_base.InterpolationBase):
         tt = t_dev.detach().to(coeffs_c.dtype).contiguous()
         _capi.check(_capi.lib().ncde_linear_derivs(_capi.dtype_code(coeffs_c), coeffs_c.data_ptr(), tt.data_ptr(),
                                                    derivs.data_ptr(), n, K, C, _capi.stream_ptr(coeffs_c.device)))
-        self._t_host = misc.host_values(t_dev)
+        misc.host_values(t_dev)   # mirror the knots on the host once (keyed on storage + version)
         self.register_buffer('_t', t_dev)
         self.register_buffer('_coeffs', coeffs)
         self.register_buffer('_derivs', derivs)
+
+    @property
+    def _t_host(self):
+        """Host mirror of the knots; refreshed when the buffer was edited in place or reloaded."""
+        return misc.host_values(self._t)
 
     @property
     def grid_points(self):

@@ -13,15 +13,20 @@ def cheap_stack(tensors, dim):
 
 def host_values(t):
     """Host copy of a small 1-D time tensor.  Tensors created by this package carry a host mirror so the hot path
-    never has to synchronise the stream to read them."""
+    never has to synchronise the stream to read them.  The mirror is keyed on the tensor's storage and version
+    counter: an in-place edit (or a load_state_dict into a path module) invalidates it and costs one D2H copy."""
     h = getattr(t, "_ncde_host", None)
-    if h is None:
+    key = (t.data_ptr(), t._version)
+    if h is None or getattr(t, "_ncde_host_key", key) != key:
         h = t.detach().cpu()
+        if h is not t:   # a CPU tensor is its own mirror: nothing to cache
+            t._ncde_host, t._ncde_host_key = h, key
     return h
 
 
 def attach_host(t, host):
     t._ncde_host = host
+    t._ncde_host_key = (t.data_ptr(), t._version)
     return t
 
 
@@ -85,23 +90,23 @@ def forward_fill(x, fill_index=-2):
 
 
 class TupleControl(torch.nn.Module):
-    """torchcde/misc.py:129-166.  Kept for API completeness; the reference fork's cdeint never reaches the tuple
-    code path (solver.py:198-199 hard-codes is_tensor=True)."""
+    """Several controls over one interval presented as a single control whose evaluate / derivative return tuples
+    (the API of torchcde/misc.py:129-166).  The reference fork's cdeint never takes the tuple branch
+    (solver.py:198-199 fixes is_tensor=True) and neither does this package's; the class exists so code that builds one
+    still imports."""
 
     def __init__(self, *controls):
-        super(TupleControl, self).__init__()
-        if len(controls) == 0:
+        super().__init__()
+        if not controls:
             raise ValueError("Expected one or more controls to batch together.")
-        self._interval = controls[0].interval
-        grid_points = controls[0].grid_points
-        same = True
-        for control in controls[1:]:
-            if (control.interval != self._interval).any():
-                raise ValueError("Can only batch togehter controls over the same interval.")
-            if same and (control.grid_points.shape != grid_points.shape or
-                         (control.grid_points != grid_points).any()):
-                same = False
-        self._grid_points = grid_points if same else None
+        first = controls[0]
+        for other in controls[1:]:
+            if not torch.equal(torch.as_tensor(other.interval), torch.as_tensor(first.interval)):
+                raise ValueError("Can only batch together controls over the same interval.")
+        shared = all(o.grid_points.shape == first.grid_points.shape and torch.equal(o.grid_points, first.grid_points)
+                     for o in controls[1:])
+        self._interval = first.interval
+        self._grid_points = first.grid_points if shared else None
         self.controls = torch.nn.ModuleList(controls)
 
     @property
@@ -115,7 +120,7 @@ class TupleControl(torch.nn.Module):
         return self._grid_points
 
     def evaluate(self, t):
-        return tuple(control.evaluate(t) for control in self.controls)
+        return tuple(c.evaluate(t) for c in self.controls)
 
     def derivative(self, t):
-        return tuple(control.derivative(t) for control in self.controls)
+        return tuple(c.derivative(t) for c in self.controls)

@@ -238,7 +238,7 @@ class _FixedSolve(torch.autograd.Function):
                                      gW, gb, _capi.ptr(grad_coeffs), work.data_ptr(), wbytes, ctypes.byref(launches),
                                      _capi.stream_ptr(dev)))
         last_launches["bwd"] = launches.value
-        ctx.saved_buf = None
+        # the stage records stay on ctx until autograd frees the graph: a second backward (retain_graph=True) is legal
         if want_path_grad:
             grad_coeffs = grad_coeffs.reshape(ctx.coeffs_shape)
         return (None, None, None, None, None, grad_z0, grad_coeffs) + tuple(grads)
@@ -335,8 +335,9 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
     ``options['precision']`` in {'fp32', 'bf16'} selects the arithmetic of the final-layer tiles.
 
     Differences, all loud: ``X`` must be a ``LinearInterpolation`` or ``NaturalCubicSpline`` of this package,
-    ``func`` must lower to a Linear/activation chain (see ``lowering``), ``vector_field_type`` must be 'matmul',
-    tensors must live on a CUDA device.
+    ``func`` must lower to a Linear/activation chain (see ``lowering``), tensors must live on a CUDA device.
+    ``vector_field_type`` 'matmul', 'evaluate' and 'derivative' are implemented (the latter two on the fixed-grid
+    solvers).
     """
     if vector_field_type not in ['matmul', 'evaluate', 'derivative']:
         raise ValueError("vector_field_type string not recognised")
@@ -433,7 +434,7 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
                                           "not implemented")
     if method == 'dopri5':
         from . import adaptive
-        out = adaptive.solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs)
+        out = adaptive.solve(X, func, spec, z0, t, t_host, adjoint, options, kwargs, coeffs=coeffs)
     else:
         unused = {k: v for k, v in options.items() if k not in ('step_size', 'grid_constructor', 'perturb', 'interp')}
         if options.get('interp', 'linear') != 'linear':

@@ -1,0 +1,145 @@
+"""The configuration bench.py measures (BASELINE.json configs[4]: 72 hourly steps -> 143 rectilinear knots, 100 channels,
+hidden = hidden-hidden = 128, 3-layer vector field, 3/8-rule RK4 step 1, online outputs, backprop through the solver) at
+its FULL length, every precision mode of the product against the ORACLE (oracle/cde_oracle.py, pinned to the real
+reference by tests/test_oracle_golden.py) — not against another mode of the product.
+
+Bounds, relative max-norm, written per mode in BOUNDS below:
+    fp32     states 1e-5, gradients 1e-5 (rows excluded only under the rule of tests/parity_util.py)
+    fp16x3   states 1e-4, gradients 1e-3   (split-precision tensor-core tiles: fp16 hi + lo operand pairs, 3 MMAs per GEMM)
+    bf16     states 1e-2, gradients 1.5e-1 (single bf16 tensor-core tiles; 568 chained stages)
+"""
+import copy
+
+import pytest
+import torch
+
+import parity_util as PU
+from oracle import cde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BOUNDS = {"fp32": (1e-5, 1e-5), "fp16x3": (1e-4, 1e-3), "bf16": (1e-2, 1.5e-1)}
+
+
+def _modes():
+    from torchcde_b200 import solver
+    return [m for m in ("fp32", "fp16x3", "bf16") if m in solver._PRECISIONS]
+
+
+def _problem(B, seed):
+    import bench
+    cfg = bench.CFG
+    x, _, _ = bench.synth_batch(B, seed)
+    cref = O.linear_interpolation_coeffs(x.clone(), rectilinear=0)
+    torch.manual_seed(3)
+    func = O.SharedMLPField(cfg["C"], cfg["H"], cfg["HH"], cfg["n_layers"])
+    g = torch.Generator().manual_seed(4)
+    z0 = torch.randn(B, cfg["H"], generator=g) * 0.5
+    w = torch.randn(B, cref.shape[1], cfg["H"], generator=g)
+    return x, cref, func, z0, w
+
+
+@pytest.fixture(scope="module")
+def oracle_run():
+    B = 128
+    x, cref, func, z0, w = _problem(B, 7)
+    assert cref.shape == (B, 143, 100)
+    o32 = PU.oracle_solve(func, "linear", cref, z0, w, True, margins=True)
+    return dict(x=x, cref=cref, func=func, z0=z0, w=w, o32=o32)
+
+
+def _gpu(run, precision, row_mask=None):
+    import torchcde_b200 as tc
+    fd = copy.deepcopy(run["func"]).cuda()
+    c = tc.linear_interpolation_coeffs(run["x"].clone().cuda(), rectilinear=0)
+    assert torch.equal(c.cpu(), run["cref"])
+    X = tc.LinearInterpolation(c)
+    z = run["z0"].cuda().requires_grad_(True)
+    w = run["w"].clone()
+    if row_mask is not None:
+        w[row_mask] = 0
+    out = tc.cdeint(X, fd, z, X.grid_points, adjoint=False, method="rk4", options={"step_size": 1, "precision": precision})
+    (out * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    return out.detach().cpu(), z.grad.cpu(), {n: p.grad.cpu() for n, p in fd.named_parameters()}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "bf16"])
+def test_cfg5_full_length_against_oracle(oracle_run, precision):
+    if precision not in _modes():
+        pytest.skip("precision mode %s not built" % precision)
+    tol_state, tol_grad = BOUNDS[precision]
+    oref, gz_ref, gref, margins = oracle_run["o32"]
+    out, gz, got = _gpu(oracle_run, precision)
+    assert torch.isfinite(out).all()
+    e_state = PU.rel(out, oref)
+    assert e_state <= tol_state, e_state
+    if precision == "fp32":
+        gz64 = PU.oracle_solve(oracle_run["func"], "linear", oracle_run["cref"], oracle_run["z0"], oracle_run["w"], True,
+                               dtype=torch.float64)[1]
+        bad = PU.excluded_rows(gz, gz_ref, gz64, out, oref, margins, tol_grad)
+        if bad.any():
+            _, gz_ref, gref, _ = PU.oracle_solve(oracle_run["func"], "linear", oracle_run["cref"], oracle_run["z0"],
+                                                 oracle_run["w"], True, row_mask=bad)
+            out, gz, got = _gpu(oracle_run, precision, row_mask=bad)
+    errs = {"z0": PU.rel(gz, gz_ref)}
+    for n in gref:
+        errs[n] = PU.rel(got[n], gref[n])
+    print("cfg5 full length, %s: state %.2e, gradients %s" % (precision, e_state, {k: "%.1e" % v for k, v in errs.items()}))
+    assert max(errs.values()) <= tol_grad, errs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "bf16"])
+def test_training_equivalence_cfg1(precision):
+    """50 Adam steps of the toy configuration (BASELINE.json configs[0]: Brownian paths, rectilinear, RK4, hidden 32,
+    width 128, experiments/sim_bm_toy_example.py): the loss curve of the product must track the oracle's within a stated
+    band of the initial loss — 1e-3 for fp32 / fp16x3, 3e-2 for bf16 tiles."""
+    if precision not in _modes():
+        pytest.skip("precision mode %s not built" % precision)
+    import torchcde_b200 as tc
+    band = {"fp32": 1e-3, "fp16x3": 1e-3, "bf16": 3e-2}[precision]
+    B, L, C, H = 128, 3, 2, 32
+    g = torch.Generator().manual_seed(21)
+    dt = 1.0 / (L - 1)
+    incr = torch.randn(B, L - 1, 1, generator=g) * dt ** 0.5
+    bm = torch.cat([torch.zeros(B, 1, 1), incr.cumsum(1)], 1)
+    x = torch.cat([torch.linspace(0, 1, L).view(1, L, 1).expand(B, L, 1), bm], -1)
+    target = bm[:, -1, 0]
+    cref = O.linear_interpolation_coeffs(x.clone(), rectilinear=0)
+    torch.manual_seed(2)
+    func0 = O.ToyField(C, H, width=128)
+    init0 = torch.nn.Linear(C, H)
+    read0 = torch.nn.Linear(H, 1)
+
+    def train(gpu):
+        func, init, read = copy.deepcopy(func0), copy.deepcopy(init0), copy.deepcopy(read0)
+        if gpu:
+            func, init, read = func.cuda(), init.cuda(), read.cuda()
+            c = cref.cuda()
+            X = tc.LinearInterpolation(c)
+            y = target.cuda()
+        else:
+            X = O.LinearPath(cref)
+            y = target
+        opt = torch.optim.Adam(list(func.parameters()) + list(init.parameters()) + list(read.parameters()), lr=3e-3)
+        losses = []
+        for _ in range(50):
+            opt.zero_grad()
+            z0 = init(X.evaluate(X.interval[0]))
+            if gpu:
+                zT = tc.cdeint(X, func, z0, X.interval, adjoint=False, method="rk4",
+                               options={"step_size": 0.25, "precision": precision})[:, -1]
+            else:
+                zT = O.cdeint(X, func, z0, X.interval, adjoint=False, method="rk4", options={"step_size": 0.25})[:, -1]
+            loss = ((read(zT).squeeze(-1) - y) ** 2).mean()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return torch.tensor(losses)
+
+    ref = train(False)
+    got = train(True)
+    assert ref[-1] < 0.8 * ref[0], "the oracle run must actually train"
+    dev = (got - ref).abs().max() / ref[0]
+    print("training equivalence, %s: max |loss - oracle loss| / loss0 = %.2e (final %.4f vs %.4f)" % (precision, dev, got[-1], ref[-1]))
+    assert dev <= band, (float(dev), got.tolist()[-5:], ref.tolist()[-5:])

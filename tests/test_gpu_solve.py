@@ -96,7 +96,8 @@ def _config_case(name):
     return x, func, z0, interp, online
 
 
-def _solve_pair(tc, name, row_mask=None):
+def _solve_pair(tc, name, row_mask=None, want64=False):
+    import parity_util as PU
     x, func, z0, interp, online = _config_case(name)
     g = torch.Generator().manual_seed(11)
     if interp == "rectilinear":
@@ -105,17 +106,13 @@ def _solve_pair(tc, name, row_mask=None):
         cref = O.linear_interpolation_coeffs(x.clone())
     else:
         cref = O.natural_cubic_coeffs(x.clone())
-    Xr = O.CubicPath(cref) if interp == "cubic" else O.LinearPath(cref)
-    t = Xr.grid_points if online else Xr.interval
-    w = torch.randn(x.shape[0], len(t), z0.shape[1], generator=g)
+    kind = "cubic" if interp == "cubic" else "linear"
+    n_t = cref.shape[1] + (1 if interp == "cubic" else 0) if online else 2
+    w = torch.randn(x.shape[0], n_t, z0.shape[1], generator=g)
     if row_mask is not None:
         w[row_mask] = 0
-    z0r = z0.clone().requires_grad_(True)
-    oref = O.cdeint(Xr, func, z0r, t, adjoint=False, method="rk4", options={"step_size": 1})
-    (oref * w).sum().backward()
-    gref = {n: p.grad.clone() for n, p in func.named_parameters()}
-    for p in func.parameters():
-        p.grad = None
+    oref, gz_ref, gref, margins = PU.oracle_solve(func, kind, cref, z0, w, online, margins=True)
+    gz64 = PU.oracle_solve(func, kind, cref, z0, w, online, dtype=torch.float64)[1] if want64 else None
     xd = x.clone().cuda()
     if interp == "rectilinear":
         c = tc.linear_interpolation_coeffs(xd, rectilinear=0)
@@ -126,30 +123,30 @@ def _solve_pair(tc, name, row_mask=None):
     assert torch.equal(c.cpu(), cref)
     X = tc.NaturalCubicSpline(c) if interp == "cubic" else tc.LinearInterpolation(c)
     fd = func.cuda()
+    for p in fd.parameters():
+        p.grad = None
     z0d = z0.cuda().requires_grad_(True)
     out = tc.cdeint(X, fd, z0d, X.grid_points if online else X.interval, adjoint=False, method="rk4",
                     options={"step_size": 1})
     (out * w.cuda()).sum().backward()
     got = {n: p.grad.cpu() for n, p in fd.named_parameters()}
     func.cpu()
-    return oref.detach(), z0r.grad, gref, out.detach().cpu(), z0d.grad.cpu(), got
+    return oref, gz_ref, gref, out.detach().cpu(), z0d.grad.cpu(), got, margins, gz64
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2_linear", "cfg2_rect", "cfg4", "cfg5", "odd_shapes"])
 def test_config_shapes_against_oracle(tc, name):
     """Hidden states must agree to 1e-5.  Gradients must agree to 1e-5 too, except for isolated batch rows whose
-    backward pass crosses a ReLU whose pre-activation is within rounding distance of zero: there the reference's own
-    fp32 gradient differs from its fp64 gradient by 1e-4..1e-3 (tools/diag_rows.py measures both), so no fp32
-    implementation with a different summation order can match it.  Rows are independent, so such rows are found from
-    the per-row z0 gradient, required to be rare, masked out of the loss, and everything is compared again."""
-    oref, gz_ref, gref, out, gz, got = _solve_pair(tc, name)
+    backward pass crosses a ReLU whose pre-activation is within rounding distance of zero IN THE ORACLE'S OWN RUN
+    (tests/parity_util.py states the rule: the exclusion is tied to an oracle-side margin, rows must be rare, and the GPU
+    may not have more rows beyond 1e-5 of the fp64 gradient than the reference's own fp32 arithmetic has).  Rows are
+    independent, so excluded rows are masked out of the loss and everything is compared again."""
+    import parity_util as PU
+    oref, gz_ref, gref, out, gz, got, margins, gz64 = _solve_pair(tc, name, want64=True)
     assert rel(out, oref) <= TOL_FP32
-    scale = gz_ref.abs().max()
-    row_err = (gz - gz_ref).abs().amax(1) / scale
-    bad = row_err > TOL_FP32
-    assert int(bad.sum()) <= max(1, out.shape[0] // 50), (int(bad.sum()), float(row_err.max()))
+    bad = PU.excluded_rows(gz, gz_ref, gz64, out, oref, margins, TOL_FP32)
     if bad.any():
-        oref, gz_ref, gref, out, gz, got = _solve_pair(tc, name, row_mask=bad)
+        oref, gz_ref, gref, out, gz, got, _, _ = _solve_pair(tc, name, row_mask=bad)
     errs = {"z0": rel(gz, gz_ref)}
     for n in gref:
         errs[n] = rel(got[n], gref[n])
