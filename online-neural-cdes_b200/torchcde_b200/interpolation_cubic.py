@@ -51,7 +51,7 @@ class NaturalCubicSpline(interpolation_base.InterpolationBase):
         channels = coeffs.size(-1) // 4
         if channels * 4 != coeffs.size(-1):
             raise ValueError("Passed invalid coeffs.")
-        self._t_host = misc.host_values(t_dev)
+        misc.host_values(t_dev)   # mirror the knots on the host once (keyed on storage + version)
         self._channels = channels
         self.register_buffer('_t', t_dev)
         self.register_buffer('_coeffs', coeffs)
