@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NCDE_ABI_VERSION 3
+#define NCDE_ABI_VERSION 4
 #define NCDE_MAX_LAYERS 8
 #define NCDE_MAX_STAGES 7
 
@@ -45,8 +45,11 @@ enum ncde_act { NCDE_ACT_NONE = 0, NCDE_ACT_RELU = 1, NCDE_ACT_TANH = 2, NCDE_AC
  * DERIVATIVE  dz/dt = f([z, dX/dt(t)])             f: H+C -> H, no contraction
  * EVALUATE / DERIVATIVE run on the fixed-grid fp32 path (ncde_solve_fwd / ncde_solve_bwd). */
 enum ncde_vf_type { NCDE_VF_MATMUL = 0, NCDE_VF_EVALUATE = 1, NCDE_VF_DERIVATIVE = 2 };
-/* arithmetic of the final (H*C-wide) layer: fp32 FFMA, or bf16 tcgen05 tensor-core tiles with fp32 accumulate */
-enum ncde_precision { NCDE_PREC_FP32 = 0, NCDE_PREC_BF16 = 1 };
+/* arithmetic of the vector-field GEMMs: fp32 FFMA; bf16 tcgen05 tensor-core tiles with fp32 accumulate; or BF16X3, the
+ * parity-grade tensor-core mode: every operand is a (hi, lo) pair of bf16 tiles and every GEMM is three tcgen05 MMAs
+ * hi*hi + lo*hi + hi*lo into one fp32 accumulator (16 mantissa bits per operand, bf16 exponent range).  BF16X3 runs on the
+ * persistent fixed-grid kernels only (euler / rk4, vector_field_type matmul, outputs on grid points). */
+enum ncde_precision { NCDE_PREC_FP32 = 0, NCDE_PREC_BF16 = 1, NCDE_PREC_BF16X3 = 2 };
 
 /* device status words written by kernels (read them after synchronising the stream) */
 enum ncde_flag_bits {
@@ -300,7 +303,8 @@ int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const float* y_out,
  * ---------------------------------------------------------------------------------------------------------- */
 enum ncde_prof_class {
     NCDE_PROF_HIDDEN_FWD = 0, NCDE_PROF_FIELD_FWD = 1, NCDE_PROF_FIELD_BWD = 2, NCDE_PROF_HIDDEN_BWD = 3,
-    NCDE_PROF_HIDDEN_WGRAD = 4, NCDE_PROF_OTHER = 5 /* dx_all: dX/dt of every stage, one launch per solve */, NCDE_PROF_CLASSES = 6
+    NCDE_PROF_HIDDEN_WGRAD = 4, NCDE_PROF_OTHER = 5 /* dx_all: dX/dt of every stage, one launch per solve */,
+    NCDE_PROF_SOLVE_FWD = 6, NCDE_PROF_SOLVE_BWD = 7 /* the persistent whole-pass kernels */, NCDE_PROF_CLASSES = 8
 };
 int ncde_profile_enable(int class_mask);
 int ncde_profile_read(double* ms, int64_t* count);

@@ -1,0 +1,1408 @@
+// Persistent fixed-grid solve on the tensor cores: ONE kernel per pass (forward / backward) runs every RK stage of every step.
+//
+// A CDE solve is sequential in time but the series of a batch are independent, so nothing forces all rows through stage s
+// before any row enters stage s+1.  The grid is one CTA per SM with two roles:
+//   field CTA (g, p)   owns h-group g of the final layer for its whole life: the W3 slice stays in shared memory and (backward)
+//                      the slice's weight gradient stays in TMEM for the WHOLE pass; it streams the 128-row batch tiles
+//                      p, p + n_part, ... through the warp-specialised tcgen05 pipeline of field_tc.cuh, stage after stage.
+//   hidden CTA j       owns batch tiles j, j + n_hid, ...: the hidden layers of the vector field (forward) / their input-gradient
+//                      chain (backward) as 128x128x128 MMAs chained out of shared memory.
+// The two roles hand tiles to each other through per-tile counters in global memory (release / acquire at gpu scope): a
+// field CTA may start stage s+1 of tile t as soon as the hidden CTA has produced that tile's activations, while other tiles
+// are still in stage s.  No kernel boundary, TMEM allocation, weight load or pipeline fill per stage.
+//
+// NSP = 1: bf16 operand tiles.  NSP = 2 ("bf16x3"): every MMA operand is a (hi, lo) pair of bf16 tiles, hi = bf16(x),
+// lo = bf16(x - hi), and every GEMM is three MMAs hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator: 16 mantissa bits per
+// operand instead of 8, with bf16's full exponent range (gradients need it; an fp16 split does not have it).
+//
+// dX/dt is read by the epilogue threads straight from global memory (thread = batch row, 16-byte loads, one chunk ahead of its
+// use, L2-prefetched a unit ahead by the producer): the tile has no reuse inside a CTA beyond the Hg hidden rows of its
+// h-group, which L1 serves, and not staging it frees 54-108 KB of shared memory for operand tiles.
+#pragma once
+#include "hidden_tc.cuh"
+
+namespace ncde {
+
+constexpr int kPsThreads = 320;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), warp 9 = signaller
+constexpr int kPsEpi = 256;
+constexpr long long kPsSpinLimit = 6000000000ll;   // ~3 s at 2 GHz: a protocol error traps instead of hanging the GPU
+
+struct PsMaps {
+    CUtensorMap W3;                              // {128 k, n_hg * Npad, NSP}            box {64, Npad, 1}
+    CUtensorMap Wh;                              // {128 in, 128 out, NSP, F}            box {64, 128, 1, 1}
+    CUtensorMap act[kTcHidMaxLayers + 1];        // act[l]: bf16 input of layer l, {128, B, NSP, n_rec}, box {64, 128, 1, 1}
+    CUtensorMap dpre;                            // backward: {128, B, NSP, n_rec * F}
+};
+
+struct PsArgs {
+    int B, Bp, H, Cp, Hg, n_hg, Npad, F;
+    int n_mt, n_part, n_field, n_hid;
+    int NS, n_steps, method, need_grad, NA, w_resident;
+    int act[kTcHidMaxLayers];
+    const float* dt;            // device [n_steps]
+    const int* emit_idx;        // device [n_steps]: output slot that receives the state at the end of step s, or -1
+    float* z_out;               // (n_out, B, H) row-major
+    const float* grad_out;      // backward: (n_out, B, H)
+    float* yT[2];               // forward: state ping-pong [H][Bp];  backward: yT[0] = gy
+    float* kT[NCDE_MAX_STAGES]; // forward: stage derivatives;  backward: dz of the stages of the current step
+    const float* b3;            // [n_hg][Npad]
+    const float* bias_h;        // [F][128]
+    __nv_bfloat16* rec0;        // saved records: record r at rec0 + r * rec_stride (bf16 elements); layer l input at + act_off[l]
+    size_t rec_stride;          // bf16 elements between stage records (forward without gradient: one scratch record, index 0)
+    size_t act_off[kTcHidMaxLayers + 1];   // bf16-element offset of layer l's input inside a record; part p at + p * Bp * 128
+    const float* dx0;           // dX/dt records [rec][Bp][Cp] fp32
+    size_t dx_stride;           // floats between records
+    // backward
+    float* dAT;                 // [n_mt][128 k][128 rows] fp32: sum over the h-groups of dL/d(final-layer input) of the tile in flight
+    float* dW3acc;              // [n_part][n_hg * Npad][128]
+    float* db3acc;              // [n_part][n_hg * Npad]
+    __nv_bfloat16* dpre0;       // dpre records [rec * F + l][NSP][Bp][128]
+    // synchronisation words (zeroed before the launch)
+    int* cnt_f;                 // [n_mt] field -> hidden: arrivals of field CTAs (monotonic)
+    int* flag_h;                // [n_mt] hidden -> field: stages completed by the hidden CTA (monotonic)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void ps_spin_ge(const int* p, int target) {
+    if (ld_acquire_gpu(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(p) < target) {
+        __nanosleep(40);
+        if (clock64() - t0 > kPsSpinLimit) __trap();
+    }
+}
+// bounded mbarrier wait (same reason: trap, never hang)
+__device__ __forceinline__ void ps_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > 40000000u) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 ldg128_nc(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// (hi, lo) bf16 split of two floats, packed
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h2);
+}
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h2);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = pack_bf16x2(a - hf.x, b - hf.y);
+}
+template <bool EXACT>
+__device__ __forceinline__ float ps_tanh(float x) {
+    if (EXACT) { float t, q; tanh_sech2(x, t, q); return t; }
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool EXACT>
+__device__ __forceinline__ float ps_sech2(float x) {
+    if (EXACT) { float t, q; tanh_sech2(x, t, q); return q; }
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return fmaf(-y, y, 1.f);
+}
+
+// D[128 x N] (+)= A . B^T for NSP-part operands, both K-major swizzled tiles [rows][128] (two 64-column blocks): hi*hi (+ lo*hi + hi*lo)
+template <int NSP>
+__device__ __forceinline__ void ps_gemm_kmajor(uint32_t d_tmem, uint32_t a_s, uint32_t a_part_bytes, int a_rows, uint32_t b_s,
+                                               uint32_t b_part_bytes, int b_rows, int N) {
+    issue_gemm_kmajor(d_tmem, a_s, a_rows, b_s, b_rows, N, kTcKP, false);
+    if (NSP == 2) {
+        issue_gemm_kmajor(d_tmem, a_s + a_part_bytes, a_rows, b_s, b_rows, N, kTcKP, true);
+        issue_gemm_kmajor(d_tmem, a_s, a_rows, b_s + b_part_bytes, b_rows, N, kTcKP, true);
+    }
+}
+
+// one W-column chunk of a final-layer epilogue for TMEM lane `row`: accumulator values in flight (tcgen05.ld) and this row's dX/dt
+// values in flight (ld.global) until ps_chunk_wait
+template <int W>
+struct PsChunk {
+    uint32_t r[W];
+    float4 dd[W / 4];
+    uint32_t b3_s;
+};
+template <int W>
+__device__ __forceinline__ void ps_chunk_issue(PsChunk<W>& k, uint32_t taddr, uint32_t b3_s, const float* dx, bool row_ok) {
+    tmem_ldw_issue<W>(taddr, k.r);
+    k.b3_s = b3_s;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) k.dd[q] = row_ok ? ldg128_nc(dx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int W, bool EXACT>
+__device__ __forceinline__ float ps_fwd_finish(const PsChunk<W>& k) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 bb = lds128(k.b3_s + 16u * q);
+        const float4 dd = k.dd[q];
+        acc0 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb.x), dd.x, acc0);
+        acc1 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb.y), dd.y, acc1);
+        acc2 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb.z), dd.z, acc2);
+        acc3 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb.w), dd.w, acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+}
+
+// unit i of a field CTA -> (global stage index q, batch tile t)
+struct PsUnit { int q, t; };
+__device__ __forceinline__ PsUnit ps_unit_fwd(int i, int n_my, int part, int n_part) {
+    PsUnit u;
+    u.q = i / n_my;
+    u.t = part + (i - u.q * n_my) * n_part;
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory layouts (byte offsets from the 1024-aligned base)
+// ---------------------------------------------------------------------------------------------------------------
+struct PsFieldFwdSmem { uint32_t Ws, As, b3s, part, bars, total; };
+__host__ __device__ inline PsFieldFwdSmem ps_field_fwd_layout(int Npad, int NSP, int NA) {
+    PsFieldFwdSmem L;
+    uint32_t o = 0;
+    L.Ws = o; o += (uint32_t)NSP * (uint32_t)Npad * 256u;
+    o = (o + 1023u) & ~1023u;
+    L.As = o; o += (uint32_t)NA * (uint32_t)NSP * kTcHidTile;
+    L.b3s = o; o += (uint32_t)Npad * 4;
+    L.part = o; o += kTcM * 4;
+    o = (o + 15u) & ~15u;
+    L.bars = o; o += 24 * 8;
+    L.total = o;
+    return L;
+}
+struct PsHidFwdSmem { uint32_t Wt, At, bias, bars, total; };
+__host__ __device__ inline PsHidFwdSmem ps_hid_fwd_layout(int NSP, int NW) {
+    PsHidFwdSmem L;
+    uint32_t o = 0;
+    L.Wt = o; o += (uint32_t)NW * (uint32_t)NSP * kTcHidTile;
+    L.At = o; o += 2u * (uint32_t)NSP * kTcHidTile;
+    L.bias = o; o += kTcHidMaxLayers * 128 * 4;
+    L.bars = o; o += 24 * 8;
+    L.total = o;
+    return L;
+}
+// weight buffers of the hidden role: all F layers resident when they fit next to the activation tiles, else a ring
+__host__ __device__ inline int ps_hid_nw(int NSP, int F, bool* resident) {
+    const uint32_t budget = 220u * 1024u;
+    const uint32_t fixed = 2u * NSP * kTcHidTile + kTcHidMaxLayers * 512 + 1024 + 24 * 8;
+    const int fit = (int)((budget - fixed) / ((uint32_t)NSP * kTcHidTile));
+    if (fit >= F) { *resident = true; return F; }
+    *resident = false;
+    return fit >= 2 ? 2 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward, field role
+// ---------------------------------------------------------------------------------------------------------------
+// what the forward epilogue does with one finished k[b, h] of global stage q (cf. tc_fwd_finish_element)
+template <int NSP>
+__device__ __forceinline__ void ps_fwd_finish_element(const PsArgs& a, int q, int s, int ist, float dt, int emit_slot, int h, int64_t b, float k) {
+    const size_t off = (size_t)h * a.Bp + b;
+    const int cur = s & 1;
+    const float* yT = a.yT[cur];
+    a.kT[ist][off] = k;
+    const size_t part_stride = (size_t)a.Bp * 128;
+    if (ist + 1 < a.NS) {
+        // input of the next stage of this step (rk_common.py:106-114)
+        const int combine = a.method == NCDE_RK4_38 ? (ist + 1) : COMBINE_Y;   // COMBINE_RK4_S2.. = 1..3
+        const float z = __fadd_rn(yT[off], stage_increment(combine, dt, a.kT, nullptr, off));
+        __nv_bfloat16* zr = a.rec0 + (a.need_grad ? (size_t)(q + 1) * a.rec_stride : 0) + a.act_off[0] + (size_t)b * 128 + h;
+        const __nv_bfloat16 hi = __float2bfloat16(z);
+        zr[0] = hi;
+        if (NSP == 2) zr[part_stride] = __float2bfloat16(z - __bfloat162float(hi));
+    } else {
+        const float y = yT[off];
+        float yn;
+        if (a.method == NCDE_RK4_38) {   // (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+            float sm = __fadd_rn(a.kT[0][off], __fmul_rn(3.f, __fadd_rn(a.kT[1][off], a.kT[2][off])));
+            sm = __fadd_rn(sm, k);
+            yn = __fadd_rn(y, __fmul_rn(__fmul_rn(sm, dt), 0.125f));
+        } else {
+            yn = __fadd_rn(y, __fmul_rn(dt, k));
+        }
+        a.yT[cur ^ 1][off] = yn;
+        if (s + 1 < a.n_steps) {
+            __nv_bfloat16* zr = a.rec0 + (a.need_grad ? (size_t)(q + 1) * a.rec_stride : 0) + a.act_off[0] + (size_t)b * 128 + h;
+            const __nv_bfloat16 hi = __float2bfloat16(yn);
+            zr[0] = hi;
+            if (NSP == 2) zr[part_stride] = __float2bfloat16(yn - __bfloat162float(hi));
+        }
+        if (emit_slot >= 0) a.z_out[((size_t)emit_slot * a.B + b) * a.H + h] = yn;
+    }
+}
+
+template <int NSP>
+__device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int g, int part) {
+    constexpr bool EXACT = NSP == 2;
+    const int Npad = a.Npad, NA = a.NA;
+    const PsFieldFwdSmem L = ps_field_fwd_layout(Npad, NSP, NA);
+    const uint32_t w_part = (uint32_t)Npad * 256u;
+    uint8_t* Ws = smem + L.Ws;
+    uint8_t* As = smem + L.As;
+    float* b3s = reinterpret_cast<float*>(smem + L.b3s);
+    float* partial = reinterpret_cast<float*>(smem + L.part);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* full_a = bars;          // [2]
+    uint64_t* mma_bar = bars + 2;     // [2]
+    uint64_t* done = bars + 4;        // [2]
+    uint64_t* w_bar = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    volatile int* sig_done = reinterpret_cast<volatile int*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t acc_stride = tc_tmem_cols(Npad);
+    const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
+    const int n_q = a.n_steps * a.NS;
+    const int n_units = n_my * n_q;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 2 * acc_stride);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full_a + i, 1); mbar_init(mma_bar + i, 1); mbar_init(done + i, 8); }
+        mbar_init(w_bar, 1);
+        *sig_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < Npad; i += kPsThreads) b3s[i] = a.b3[(size_t)g * Npad + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && n_units > 0) {
+            tma_prefetch_desc(&maps.act[a.F]);
+            mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
+            for (int p = 0; p < NSP; ++p) {
+                tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
+                tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+            }
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
+                const int b = i & 1, ba = NA == 2 ? b : 0;
+                if (i >= NA) ps_wait(mma_bar + ((i - NA) & 1), (uint32_t)((i - NA) >> 1) & 1u);   // activation buffer free
+                ps_spin_ge(a.flag_h + u.t, u.q + 1);            // the hidden CTA has written the tile's final-layer input of stage q
+                fence_proxy_async_all();
+                uint8_t* dst = As + (size_t)ba * NSP * kTcHidTile;
+                const int rec = a.need_grad ? u.q : 0;
+                mbar_expect_tx(full_a + ba, (uint32_t)NSP * kTcHidTile);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.act[a.F], full_a + ba, 0, u.t * kTcM, p, rec);
+                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a + ba, 64, u.t * kTcM, p, rec);
+                }
+                if (i + 1 < n_units) {   // dX/dt tile of the next unit -> L2 (the epilogue threads read it with plain loads)
+                    const PsUnit un = ps_unit_fwd(i + 1, n_my, part, a.n_part);
+                    const int rows = min(kTcM, a.B - un.t * kTcM);
+                    l2_prefetch_bulk(a.dx0 + (size_t)un.q * a.dx_stride + (size_t)un.t * kTcM * a.Cp, (uint32_t)rows * a.Cp * 4u);
+                }
+                if (i >= 2) {
+                    ps_wait(done + b, (uint32_t)((i - 2) >> 1) & 1u);        // accumulator b drained by the epilogue of unit i-2
+                    while (*sig_done < i - 1) {}                              // ... and that unit was signalled (keeps the signaller in phase)
+                }
+                if (i == 0) ps_wait(w_bar, 0);
+                ps_wait(full_a + ba, (uint32_t)(i / NA) & 1u);
+                tc_fence_after();
+                ps_gemm_kmajor<NSP>(tmem_base + (uint32_t)b * acc_stride, smem_u32(dst), kTcHidTile, kTcM, smem_u32(Ws), w_part, Npad, Npad);
+                umma_commit(mma_bar + b);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
+                ps_wait(done + (i & 1), (uint32_t)(i >> 1) & 1u);
+                __threadfence();
+                red_release_gpu_add(a.cnt_f + u.t, 1);
+                *sig_done = i + 1;
+            }
+        }
+    } else {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        int h_begin, h_end, c_begin, c_end;
+        if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
+        else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+        const uint32_t b3_s = smem_u32(b3s);
+        const int n32 = (c_end - c_begin) / 32;
+        for (int i = 0; i < n_units; ++i) {
+            const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
+            const int b = i & 1;
+            const int s = u.q / a.NS, ist = u.q - s * a.NS;
+            const float dt = __ldg(a.dt + s);
+            const int emit_slot = __ldg(a.emit_idx + s);
+            const int64_t b0 = (int64_t)u.t * kTcM;
+            const bool row_ok = b0 + row < a.B;
+            const float* dxrow = a.dx0 + (size_t)u.q * a.dx_stride + (size_t)(b0 + row) * a.Cp;
+            ps_wait(mma_bar + b, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int hl = h_begin; hl < h_end; ++hl) {
+                float acc = 0.f;
+                const int colbase = hl * a.Cp;
+#define PS_ISSUE32(k, j) ps_chunk_issue<32>(k, lane_addr + (uint32_t)(colbase + c_begin + 32 * (j)), b3_s + 4u * (colbase + c_begin + 32 * (j)), \
+                                            dxrow + c_begin + 32 * (j), row_ok)
+                {
+                    PsChunk<32> A, Bk;
+                    if (n32 > 0) PS_ISSUE32(A, 0);
+                    for (int j = 0; j < n32; j += 2) {
+                        tmem_wait_ld<32>(A.r);
+                        if (j + 1 < n32) PS_ISSUE32(Bk, j + 1);
+                        acc += ps_fwd_finish<32, EXACT>(A);
+                        if (j + 1 < n32) {
+                            tmem_wait_ld<32>(Bk.r);
+                            if (j + 2 < n32) PS_ISSUE32(A, j + 2);
+                            acc += ps_fwd_finish<32, EXACT>(Bk);
+                        }
+                    }
+                }
+                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
+                    PsChunk<8> T;
+                    ps_chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dxrow + c0, row_ok);
+                    tmem_wait_ld<8>(T.r);
+                    acc += ps_fwd_finish<8, EXACT>(T);
+                }
+                if (a.Hg >= 2) {
+                    const int h = g * a.Hg + hl;
+                    if (h < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, h, b0 + row, acc);
+                } else {
+                    if (wg == 0) partial[row] = acc;
+                    named_bar_sync(1, kPsEpi);
+                    if (wg == 1 && g < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, g, b0 + row, acc + partial[row]);
+                    named_bar_sync(1, kPsEpi);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done + b);
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * acc_stride);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward, hidden role: z_q tile -> hidden layers -> input of the final layer; every layer input is kept as a record
+// ---------------------------------------------------------------------------------------------------------------
+template <int NSP>
+__device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int j) {
+    bool resident;
+    const int NW = ps_hid_nw(NSP, a.F, &resident);
+    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW);
+    constexpr uint32_t kOp = (uint32_t)NSP * kTcHidTile;     // one operand (all parts)
+    uint8_t* Wt = smem + L.Wt;
+    uint8_t* At = smem + L.At;
+    float* bias_s = reinterpret_cast<float*>(smem + L.bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* w_full = bars;          // [NW <= 8]
+    uint64_t* a_full = bars + 8;
+    uint64_t* mma_bar = bars + 9;
+    uint64_t* a_ready = bars + 10;    // epilogue -> producer: operand tile of the next layer written (8 warp arrivals)
+    uint64_t* out_done = bars + 11;   // epilogue -> producer: final-layer input written to global memory (8 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = a.F;
+    const int n_my = j < a.n_mt ? (a.n_mt - j + a.n_hid - 1) / a.n_hid : 0;
+    const int n_q = a.n_steps * a.NS;
+    const int n_units = n_my * n_q;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(w_full + i, 1);
+        mbar_init(a_full, 1); mbar_init(mma_bar, 1); mbar_init(a_ready, 8); mbar_init(out_done, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < F * 128; i += kPsThreads) bias_s[i] = a.bias_h[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && n_units > 0) {
+            auto load_W = [&](int l, int buf) {
+                uint8_t* dst = Wt + (size_t)buf * kOp;
+                mbar_expect_tx(w_full + buf, kOp);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
+                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                }
+            };
+            tma_prefetch_desc(&maps.act[0]);
+            if (resident) { for (int l = 0; l < F; ++l) load_W(l, l); }
+            else { for (int w = 0; w < NW && w < F; ++w) load_W(w, w); }     // uses 0 .. NW-1 of the first unit
+            int use = 0;               // layer uses so far (ring position when streaming)
+            for (int i = 0; i < n_units; ++i) {
+                const int q = i / n_my, t = j + (i - q * n_my) * a.n_hid;
+                const int b0 = t * kTcM;
+                const int rec = a.need_grad ? q : 0;
+                if (q > 0) ps_spin_ge(a.cnt_f + t, a.n_hg * q);      // every h-group wrote its columns of the stage input
+                fence_proxy_async_all();
+                bulk_wait_read<0>();                                  // no store of the previous unit still reads At[0]
+                mbar_expect_tx(a_full, kOp);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(At + (size_t)p * kTcHidTile, &maps.act[0], a_full, 0, b0, p, rec);
+                    tma_load_4d(At + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[0], a_full, 64, b0, p, rec);
+                }
+                for (int l = 0; l < F; ++l, ++use) {
+                    uint8_t* a_tile = At + (size_t)(l & 1) * kOp;
+                    if (l == 0) ps_wait(a_full, (uint32_t)i & 1u);
+                    else {
+                        ps_wait(a_ready, (uint32_t)(i * (F - 1) + l - 1) & 1u);
+                        if (a.need_grad) {
+                            for (int p = 0; p < NSP; ++p) {
+                                tma_store_4d(&maps.act[l], a_tile + (size_t)p * kTcHidTile, 0, b0, p, rec);
+                                tma_store_4d(&maps.act[l], a_tile + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, rec);
+                            }
+                            bulk_commit();
+                        }
+                    }
+                    const int buf = resident ? l : use % NW;
+                    if (resident) { if (i == 0) ps_wait(w_full + buf, 0); }
+                    else ps_wait(w_full + buf, (uint32_t)(use / NW) & 1u);
+                    tc_fence_after();
+                    ps_gemm_kmajor<NSP>(tmem_base, smem_u32(a_tile), kTcHidTile, kTcM, smem_u32(Wt + (size_t)buf * kOp), kTcHidTile, 128, 128);
+                    // the epilogue of this layer overwrites the tile the previous store read from
+                    bulk_wait_read<1>();
+                    umma_commit(mma_bar);
+                    if (!resident) {
+                        // next use of this buffer: layer use + NW (the layer sequence is periodic with period F)
+                        const int64_t total_uses = (int64_t)n_units * F;
+                        if ((int64_t)use + NW < total_uses) {
+                            ps_wait(mma_bar, (uint32_t)use & 1u);     // the MMAs that read the buffer have completed
+                            load_W((use + NW) % F, buf);
+                        }
+                    }
+                }
+                ps_wait(out_done, (uint32_t)i & 1u);
+                __threadfence();
+                st_release_gpu(a.flag_h + t, q + 1);
+            }
+            bulk_wait<0>();
+        }
+    } else if (warp < 8) {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int use = 0;
+        for (int i = 0; i < n_units; ++i) {
+            const int q = i / n_my, t = j + (i - q * n_my) * a.n_hid;
+            const int64_t b = (int64_t)t * kTcM + row;
+            const bool row_ok = b < a.B;
+            const int rec = a.need_grad ? q : 0;
+            for (int l = 0; l < F; ++l, ++use) {
+                ps_wait(mma_bar, (uint32_t)use & 1u);
+                tc_fence_after();
+                const bool last = l == F - 1;
+                const uint32_t dst = smem_u32(At + (size_t)((l + 1) & 1) * kOp);
+                __nv_bfloat16* gdst = a.rec0 + (size_t)rec * a.rec_stride + a.act_off[F] + (size_t)b * 128;
+                const uint32_t bias_a = smem_u32(bias_s + l * 128);
+                const int act = a.act[l];
+#pragma unroll
+                for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+                    float4 bb[8];
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) bb[qq] = lds128(bias_a + 4u * c0 + 16u * qq);
+                    tmem_wait_ld<32>(r);
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        float v[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float4 bq = bb[j8 * 2 + (jj >> 2)];
+                            const float bj = (jj & 3) == 0 ? bq.x : ((jj & 3) == 1 ? bq.y : ((jj & 3) == 2 ? bq.z : bq.w));
+                            v[jj] = apply_act(__uint_as_float(r[j8 * 8 + jj]) + bj, act);
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            if (NSP == 2) split_bf16x2(v[2 * jj], v[2 * jj + 1], hi[jj], lo[jj]);
+                            else hi[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
+                        }
+                        if (!last) {
+                            const uint32_t o = sw128_off(row, (c0 >> 3) + j8, kTcM);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                            if (NSP == 2)
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kTcHidTile + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                        } else if (row_ok) {
+                            *reinterpret_cast<uint4*>(gdst + c0 + j8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (NSP == 2)
+                                *reinterpret_cast<uint4*>(gdst + (size_t)a.Bp * 128 + c0 + j8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (!last) {
+                    fence_async_smem();     // generic-proxy writes before the async-proxy MMA / TMA store
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_ready);
+                } else {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(out_done);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+static inline size_t ps_fwd_smem_bytes(int Npad, int NSP, int NA, int F) {
+    bool res;
+    const int NW = ps_hid_nw(NSP, F, &res);
+    const size_t f = ps_field_fwd_layout(Npad, NSP, NA).total, h = ps_hid_fwd_layout(NSP, NW).total;
+    return 1024 + (f > h ? f : h);
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(kPsThreads, 1) persist_fwd_kernel(const __grid_constant__ PsArgs a, const __grid_constant__ PsMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int bid = blockIdx.x;
+    if (bid < a.n_field) ps_field_fwd<NSP>(a, maps, smem, bid % a.n_hg, bid / a.n_hg);
+    else ps_hidden_fwd<NSP>(a, maps, smem, bid - a.n_field);
+}
+
+
+// ===============================================================================================================
+// backward pass
+// ===============================================================================================================
+// One W-column chunk of epilogue 1 for TMEM lane `row` (after tmem_wait_ld): G = gk * dX * sech^2(pre + b3) -> bf16 (hi, lo) into the
+// swizzled G tile(s) (16-byte stores, n0 is a multiple of 8).
+template <int W, int NSP, bool EXACT>
+__device__ __forceinline__ void ps_bwd_finish(const PsChunk<W>& k, float gk, uint32_t gs_s, uint32_t g_part_bytes, int row, int n0) {
+    float v[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 bb = lds128(k.b3_s + 16u * q);
+        const float4 dd = k.dd[q];
+        // gk is zero for padded rows and their dX/dt loads are predicated to zero: no NaN can enter the G tile
+        v[4 * q + 0] = gk * dd.x * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb.x);
+        v[4 * q + 1] = gk * dd.y * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb.y);
+        v[4 * q + 2] = gk * dd.z * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb.z);
+        v[4 * q + 3] = gk * dd.w * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb.w);
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < W / 8; ++j8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (NSP == 2) split_bf16x2(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1], hi[j], lo[j]);
+            else hi[j] = pack_bf16x2(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1]);
+        }
+        const uint32_t o = sw128_off(row, (n0 >> 3) + j8, kTcM);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        if (NSP == 2)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + g_part_bytes + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+}
+
+struct PsFieldBwdSmem { uint32_t Ws, As, Gs, b3s, bsum, bars, g_part, total; };
+__host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP) {
+    PsFieldBwdSmem L;
+    const uint32_t NP64 = ((uint32_t)Npad + 63u) & ~63u;
+    uint32_t o = 0;
+    L.Ws = o; o += (uint32_t)NSP * (uint32_t)Npad * 256u;
+    o = (o + 1023u) & ~1023u;
+    L.As = o; o += (uint32_t)NSP * kTcHidTile;
+    L.g_part = kTcM * NP64 * 2;
+    L.Gs = o; o += (uint32_t)NSP * L.g_part;
+    L.b3s = o; o += (uint32_t)Npad * 4;
+    L.bsum = o; o += 8u * (uint32_t)Npad * 4;
+    o = (o + 15u) & ~15u;
+    L.bars = o; o += 24 * 8;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ PsUnit ps_unit_bwd(int i, int n_my, int part, int n_part, int n_q) {
+    PsUnit u;
+    const int qi = i / n_my;
+    u.q = n_q - 1 - qi;
+    u.t = part + (i - qi * n_my) * n_part;
+    return u;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// backward of one RK stage for one batch tile (cf. tc_field_bwd_kernel): MMA1 recompute pre -> epilogue 1 G -> dgrad P, wgrad
+// dW^T (stays in TMEM for the whole pass) -> epilogue 2: P summed over the h-groups with red.global into the tile's fp32 dA^T
+template <int NSP>
+__device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int g, int part) {
+    constexpr bool EXACT = NSP == 2;
+    constexpr int EW = 8, kCg = 2, KP = kTcKP;
+    const int Npad = a.Npad;
+    const PsFieldBwdSmem L = ps_field_bwd_layout(Npad, NSP);
+    const uint32_t w_part = (uint32_t)Npad * 256u;
+    uint8_t* Ws = smem + L.Ws;
+    uint8_t* As = smem + L.As;
+    uint8_t* Gs = smem + L.Gs;
+    float* b3s = reinterpret_cast<float*>(smem + L.b3s);
+    float* bsum = reinterpret_cast<float*>(smem + L.bsum);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* full_a = bars;
+    uint64_t* wg_bar = bars + 1;
+    uint64_t* dep_bar = bars + 2;     // producer -> epilogue: the dz / gy inputs of the unit are visible
+    uint64_t* pre_bar = bars + 3;
+    uint64_t* g_ready = bars + 4;
+    uint64_t* dg_bar = bars + 5;
+    uint64_t* done2 = bars + 6;
+    uint64_t* fin_bar = bars + 7;
+    uint64_t* w_bar = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    volatile int* sig_done = reinterpret_cast<volatile int*>(bars + 10);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
+    const int n_q = a.n_steps * a.NS;
+    const int n_units = n_my * n_q;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(dep_bar, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, EW);
+        mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
+        *sig_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < Npad; i += kPsThreads) b3s[i] = a.b3[(size_t)g * Npad + i];
+    const int S = a.Hg * a.Cp;                          // valid columns (multiple of 8); [S, Npad) is zero padding
+    if (S < Npad && tid < kTcM)
+        for (int p = 0; p < NSP; ++p) *reinterpret_cast<uint4*>(Gs + (size_t)p * L.g_part + sw128_off(tid, S >> 3, kTcM)) = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && n_units > 0) {
+            tma_prefetch_desc(&maps.act[a.F]);
+            mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
+            for (int p = 0; p < NSP; ++p) {
+                tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
+                tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+            }
+            auto load_A = [&](int i) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                mbar_expect_tx(full_a, (uint32_t)NSP * kTcHidTile);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
+                    tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
+                }
+                const int rows = min(kTcM, a.B - u.t * kTcM);
+                l2_prefetch_bulk(a.dx0 + (size_t)u.q * a.dx_stride + (size_t)u.t * kTcM * a.Cp, (uint32_t)rows * a.Cp * 4u);
+            };
+            load_A(0);
+            ps_wait(w_bar, 0);
+            const uint32_t As_s = smem_u32(As), Ws_s = smem_u32(Ws), Gs_s = smem_u32(Gs);
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                const uint32_t ph = (uint32_t)i & 1u;
+                ps_wait(full_a, ph);
+                if (i > 0) ps_wait(done2, ph ^ 1u);             // epilogue 2 of the previous unit has read P out of the accumulator
+                tc_fence_after();
+                ps_gemm_kmajor<NSP>(tmem_base, As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
+                umma_commit(pre_bar);
+                // the gradients this unit's gk is formed from: the hidden CTA has finished every later stage of the tile
+                ps_spin_ge(a.flag_h + u.t, n_q - 1 - u.q);
+                mbar_arrive(dep_bar);
+                ps_wait(g_ready, ph);                            // G tile written by all 8 warps
+                tc_fence_after();
+                {   // dgrad: D[128 x KP] = G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows)
+                    const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
+                    bool first = true;
+                    for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
+                        const uint32_t g_s = Gs_s + (pr == 1 ? L.g_part : 0u), w_s = Ws_s + (pr == 2 ? w_part : 0u);
+                        for (int ks = 0; ks < Npad / 16; ++ks) {
+                            const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
+                            umma_bf16(tmem_base, make_sdesc(g_s + a_off, 16, 1024), make_sdesc(w_s + (uint32_t)ks * 2048u, (uint32_t)Npad * 128u, 1024),
+                                      idesc, first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                }
+                umma_commit(dg_bar);
+                {   // wgrad: D[KP x Npad] += A^T (MN-major: M = k contiguous, K = m rows) . G (MN-major: N = n contiguous)
+                    const uint32_t idesc = make_idesc(KP, Npad, 1, 1);
+                    for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
+                        const uint32_t a_s = As_s + (pr == 1 ? kTcHidTile : 0u), g_s = Gs_s + (pr == 2 ? L.g_part : 0u);
+                        for (int ks = 0; ks < kTcM / 16; ++ks) {
+                            const uint32_t off = (uint32_t)ks * 2048u;
+                            umma_bf16(tmem_base + kTcDwCol, make_sdesc(a_s + off, (uint32_t)kTcM * 128u, 1024),
+                                      make_sdesc(g_s + off, (uint32_t)kTcM * 128u, 1024), idesc, (ks > 0 || pr > 0 || i > 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                if (i + 1 < n_units) {
+                    umma_commit(wg_bar);
+                    ps_wait(wg_bar, ph);                         // activation tile free once wgrad(i) has completed
+                    while (*sig_done < i) {}                     // keeps the signaller within one unit of the pipeline
+                    load_A(i + 1);
+                }
+            }
+            umma_commit(fin_bar);
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                ps_wait(done2, (uint32_t)i & 1u);
+                __threadfence();
+                red_release_gpu_add(a.cnt_f + u.t, 1);
+                *sig_done = i + 1;
+            }
+        }
+    } else {
+        const int cg = warp >> 2;                    // column group
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int P = a.Hg >= kCg ? 1 : kCg / a.Hg;
+        const int U = a.Hg * P;
+        const int u_begin = cg * U / kCg, u_end = (cg + 1) * U / kCg;
+        const int cw = (((a.Cp + P - 1) / P) + 7) & ~7;
+        const int col_begin = (cg * Npad / kCg) & ~15;
+        const int col_end = cg == kCg - 1 ? Npad : (((cg + 1) * Npad / kCg) & ~15);
+        const int n_chunk8 = Npad >> 3;                     // <= 30
+        float bacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+        const uint32_t b3_s = smem_u32(b3s), gs_s = smem_u32(Gs);
+        const float third = 0.3333333432674408f;
+
+        for (int i = 0; i < n_units; ++i) {
+            const PsUnit un = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+            const uint32_t ph = (uint32_t)i & 1u;
+            const int s = un.q / a.NS, ist = un.q - s * a.NS;
+            const float dt = __ldg(a.dt + s);
+            const int64_t b0 = (int64_t)un.t * kTcM;
+            const int64_t b = b0 + row;
+            const bool row_ok = b < a.B;
+            const float* dxrow = a.dx0 + (size_t)un.q * a.dx_stride + (size_t)b * a.Cp;
+            float* gy_new = a.yT[s & 1];
+            const float* gy_old = a.yT[(s + 1) & 1];
+            ps_wait(dep_bar, ph);
+            ps_wait(pre_bar, ph);
+            tc_fence_after();
+            // ---- epilogue 1 ----
+            for (int u = u_begin; u < u_end; ++u) {
+                const int hl = u / P, c_begin = (u % P) * cw, c_end = min(a.Cp, c_begin + cw);
+                const int h = g * a.Hg + hl;
+                float gk = 0.f;
+                if (row_ok && h < a.H) {
+                    const size_t off = (size_t)h * a.Bp + b;
+                    if (ist == a.NS - 1) {
+                        // first backward stage of step s: the gradient of the step's end state = the one carried over from step s+1
+                        // + the stage-input gradients of step s+1 (unit Jacobian w.r.t. the state) + the output gradient at this point
+                        float gy = gy_old[off];
+                        if (s + 1 < a.n_steps)
+                            for (int q2 = 0; q2 < a.NS; ++q2) gy += __ldcg(a.kT[q2] + off);
+                        const int slot = __ldg(a.emit_idx + s);
+                        if (slot >= 0) gy += __ldg(a.grad_out + ((size_t)slot * a.B + b) * a.H + h);
+                        gy_new[off] = gy;
+                        gk = (a.method == NCDE_RK4_38 ? dt * 0.125f : dt) * gy;
+                    } else {
+                        // rk_common.py:106-114 transposed: dL/dk_i = c_i dt gy + sum over later stages q of d(stage input q)/dk_i * dz_q
+                        const float gy = gy_new[off];
+                        const float c8 = dt * 0.125f;
+                        gk = ((ist == 0) ? c8 : 3.f * c8) * gy;
+                        if (ist == 0) {
+                            gk = fmaf(dt * third, __ldcg(a.kT[1] + off), gk);
+                            gk = fmaf(-(dt * third), __ldcg(a.kT[2] + off), gk);
+                            gk = fmaf(dt, __ldcg(a.kT[3] + off), gk);
+                        } else if (ist == 1) {
+                            gk = fmaf(dt, __ldcg(a.kT[2] + off), gk);
+                            gk = fmaf(-dt, __ldcg(a.kT[3] + off), gk);
+                        } else {
+                            gk = fmaf(dt, __ldcg(a.kT[3] + off), gk);
+                        }
+                    }
+                }
+                const int colbase = hl * a.Cp;
+                const int n32 = (c_end - c_begin) / 32;
+#define PS_ISSUE32B(k, j) ps_chunk_issue<32>(k, lane_addr + (uint32_t)(colbase + c_begin + 32 * (j)), b3_s + 4u * (colbase + c_begin + 32 * (j)), \
+                                             dxrow + c_begin + 32 * (j), row_ok)
+                {
+                    PsChunk<32> A, Bk;
+                    if (n32 > 0) PS_ISSUE32B(A, 0);
+                    for (int j = 0; j < n32; j += 2) {
+                        tmem_wait_ld<32>(A.r);
+                        if (j + 1 < n32) PS_ISSUE32B(Bk, j + 1);
+                        ps_bwd_finish<32, NSP, EXACT>(A, gk, gs_s, L.g_part, row, colbase + c_begin + 32 * j);
+                        if (j + 1 < n32) {
+                            tmem_wait_ld<32>(Bk.r);
+                            if (j + 2 < n32) PS_ISSUE32B(A, j + 2);
+                            ps_bwd_finish<32, NSP, EXACT>(Bk, gk, gs_s, L.g_part, row, colbase + c_begin + 32 * (j + 1));
+                        }
+                    }
+                }
+                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
+                    PsChunk<8> T;
+                    ps_chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dxrow + c0, row_ok);
+                    tmem_wait_ld<8>(T.r);
+                    ps_bwd_finish<8, NSP, EXACT>(T, gk, gs_s, L.g_part, row, colbase + c0);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_ready);
+            // bias gradient from the G tile while the tensor core works: every warp needs ALL rows -> epilogue-wide barrier
+            named_bar_sync(1, kPsEpi);
+            if (lane < n_chunk8) {
+#pragma unroll 4
+                for (int r = warp * (kTcM / EW); r < (warp + 1) * (kTcM / EW); ++r) {
+                    for (int p = 0; p < NSP; ++p) {
+                        uint32_t w4[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                                     : "r"(gs_s + (uint32_t)p * L.g_part + sw128_off(r, lane, kTcM)));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                            bacc[2 * j] += f.x;
+                            bacc[2 * j + 1] += f.y;
+                        }
+                    }
+                }
+            }
+            ps_wait(dg_bar, ph);
+            tc_fence_after();
+            // ---- epilogue 2: this h-group's share of dL/d(final-layer input), summed over the groups in L2 ----
+            {
+                const int kb = cg * (KP / kCg);
+                float* dcol = a.dAT + ((size_t)un.t * 128 + kb) * 128 + row;
+                uint32_t r0[32], r1[32];
+                tmem_ld32_issue(lane_addr + (uint32_t)kb, r0);
+                tmem_wait_ld<32>(r0);
+                tmem_ld32_issue(lane_addr + (uint32_t)kb + 32u, r1);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red_add_f32(dcol + (size_t)j * 128, __uint_as_float(r0[j]));
+                }
+                tmem_wait_ld<32>(r1);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red_add_f32(dcol + (size_t)(32 + j) * 128, __uint_as_float(r1[j]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done2);
+        }
+        // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [part][g*Npad + n][k];  bias gradient ----
+        if (n_units > 0) {
+            if (lane < n_chunk8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[warp * Npad + lane * 8 + j] = bacc[j];
+            }
+            ps_wait(fin_bar, 0);
+            tc_fence_after();
+            named_bar_sync(1, kPsEpi);
+            const int k = row;
+            for (int n0 = col_begin; n0 < col_end; n0 += 16) {
+                float v[16];
+                tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    a.dW3acc[(((size_t)part * a.n_hg + g) * Npad + n0 + j) * 128 + k] = v[j];
+            }
+            for (int n = tid; n < Npad; n += kPsEpi) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < EW; ++w) sacc += bsum[w * Npad + n];
+                a.db3acc[((size_t)part * a.n_hg + g) * Npad + n] = sacc;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// backward, hidden role: sum of the h-group partials (dA^T, fp32, L2) x act' -> dpre_{F-1}; input-gradient chain l = F-1 .. 0 on the
+// tensor core; dz -> global.  dpre_l of every stage is kept as a record for the weight-gradient kernel.
+template <int NSP>
+__device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int j) {
+    bool resident;
+    const int NW = ps_hid_nw(NSP, a.F, &resident);
+    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW);
+    constexpr uint32_t kOp = (uint32_t)NSP * kTcHidTile;
+    uint8_t* Wt = smem + L.Wt;
+    uint8_t* Dt = smem + L.At;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* w_full = bars;          // [NW <= 8]
+    uint64_t* top_bar = bars + 8;     // producer -> epilogue: all h-groups have added their partials for this unit
+    uint64_t* dg_bar = bars + 9;
+    uint64_t* dp_ready = bars + 10;   // epilogue -> producer: dpre tile written (8 warp arrivals)
+    uint64_t* out_done = bars + 11;   // epilogue -> producer: dz written (8 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = a.F;
+    const int n_my = j < a.n_mt ? (a.n_mt - j + a.n_hid - 1) / a.n_hid : 0;
+    const int n_q = a.n_steps * a.NS;
+    const int n_units = n_my * n_q;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(w_full + i, 1);
+        mbar_init(top_bar, 1); mbar_init(dg_bar, 1); mbar_init(dp_ready, 8); mbar_init(out_done, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && n_units > 0) {
+            auto load_W = [&](int l, int buf) {
+                uint8_t* dst = Wt + (size_t)buf * kOp;
+                mbar_expect_tx(w_full + buf, kOp);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
+                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                }
+            };
+            tma_prefetch_desc(&maps.dpre);
+            // layer order of the chain: F-1, F-2, ..., 0, F-1, ...   use u -> layer F-1 - (u % F)
+            if (resident) { for (int l = 0; l < F; ++l) load_W(l, l); }
+            else { for (int w = 0; w < NW && w < F; ++w) load_W(F - 1 - w, w); }
+            int use = 0;
+            for (int i = 0; i < n_units; ++i) {
+                const int qi = i / n_my, q = n_q - 1 - qi, t = j + (i - qi * n_my) * a.n_hid;
+                const int b0 = t * kTcM;
+                ps_spin_ge(a.cnt_f + t, a.n_hg * (qi + 1));          // every h-group has added its partial of stage q
+                mbar_arrive(top_bar);
+                for (int l = F - 1, n = 0; l >= 0; --l, ++n, ++use) {
+                    const int bf = l & 1;
+                    ps_wait(dp_ready, (uint32_t)(i * F + n) & 1u);        // dpre_l written (and fenced)
+                    uint8_t* d_tile = Dt + (size_t)bf * kOp;
+                    for (int p = 0; p < NSP; ++p) {                       // keep dpre_l for the weight-gradient kernel
+                        tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile, 0, b0, p, q * F + l);
+                        tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, q * F + l);
+                    }
+                    bulk_commit();
+                    const int buf = resident ? l : use % NW;
+                    if (resident) { if (i == 0) ps_wait(w_full + buf, 0); }
+                    else ps_wait(w_full + buf, (uint32_t)(use / NW) & 1u);
+                    tc_fence_after();
+                    {   // dgrad: D[128 b x 128 i] = dpre_l (K-major over o) . W_l (MN-major: N = i contiguous, K = o rows)
+                        const uint32_t idesc = make_idesc(kTcM, 128, 0, 1);
+                        const uint32_t d_s = smem_u32(d_tile), w_s = smem_u32(Wt + (size_t)buf * kOp);
+                        bool first = true;
+                        for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
+                            const uint32_t ds = d_s + (pr == 1 ? kTcHidTile : 0u), ws = w_s + (pr == 2 ? kTcHidTile : 0u);
+                            for (int ks = 0; ks < 8; ++ks) {
+                                const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
+                                umma_bf16(tmem_base, make_sdesc(ds + a_off, 16, 1024), make_sdesc(ws + (uint32_t)ks * 2048u, 128u * 128u, 1024), idesc,
+                                          first ? 0u : 1u);
+                                first = false;
+                            }
+                        }
+                    }
+                    // the epilogue of this level writes buffer (l-1)&1, whose previous content was stored one level ago
+                    bulk_wait_read<1>();
+                    umma_commit(dg_bar);
+                    if (!resident) {
+                        const int64_t total_uses = (int64_t)n_units * F;
+                        if ((int64_t)use + NW < total_uses) {
+                            ps_wait(dg_bar, (uint32_t)use & 1u);
+                            load_W(F - 1 - ((use + NW) % F), buf);
+                        }
+                    }
+                }
+                ps_wait(out_done, (uint32_t)i & 1u);
+                bulk_wait_read<0>();     // the next unit's top tile overwrites a buffer the last store may still read
+                __threadfence();
+                st_release_gpu(a.flag_h + t, qi + 1);
+            }
+            bulk_wait<0>();
+        }
+    } else if (warp < 8) {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int use = 0;
+        for (int i = 0; i < n_units; ++i) {
+            const int qi = i / n_my, q = n_q - 1 - qi, t = j + (i - qi * n_my) * a.n_hid;
+            const int s = q / a.NS, ist = q - s * a.NS;
+            const int64_t b = (int64_t)t * kTcM + row;
+            const bool row_ok = b < a.B;
+            const __nv_bfloat16* recq = a.rec0 + (size_t)q * a.rec_stride;
+            // ---- top: dpre_{F-1} = (sum over the h-groups of P) * act'(a_F) ----
+            ps_wait(top_bar, (uint32_t)i & 1u);
+            {
+                float* dcol = a.dAT + ((size_t)t * 128 + wg * 64) * 128 + row;
+                const __nv_bfloat16* arow = recq + a.act_off[F] + (size_t)b * 128 + wg * 64;
+                const uint32_t dst = smem_u32(Dt + (size_t)((F - 1) & 1) * kOp);
+                const int act = a.act[F - 1];
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float v[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) v[jj] = __ldcg(dcol + (size_t)(c8 * 8 + jj) * 128);
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) __stcg(dcol + (size_t)(c8 * 8 + jj) * 128, 0.f);   // ready for the tile's next stage
+                    uint4 av = make_uint4(0, 0, 0, 0), al = make_uint4(0, 0, 0, 0);
+                    if (row_ok) {
+                        av = __ldg(reinterpret_cast<const uint4*>(arow + c8 * 8));
+                        if (NSP == 2 && act == NCDE_ACT_TANH) al = __ldg(reinterpret_cast<const uint4*>(arow + (size_t)a.Bp * 128 + c8 * 8));
+                    }
+                    const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, lw[4] = {al.x, al.y, al.z, al.w};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[jj]));
+                        const float2 l2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[jj]));
+                        a2.x += l2.x; a2.y += l2.y;
+                        const float g0 = row_ok ? v[2 * jj] * act_grad_bf(a2.x, act) : 0.f;
+                        const float g1 = row_ok ? v[2 * jj + 1] * act_grad_bf(a2.y, act) : 0.f;
+                        if (NSP == 2) split_bf16x2(g0, g1, hi[jj], lo[jj]);
+                        else hi[jj] = pack_bf16x2(g0, g1);
+                    }
+                    const uint32_t o = sw128_off(row, wg * 8 + c8, kTcM);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    if (NSP == 2)
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kTcHidTile + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dp_ready);
+            }
+            for (int l = F - 1; l >= 0; --l, ++use) {
+                ps_wait(dg_bar, (uint32_t)use & 1u);
+                tc_fence_after();
+                if (l > 0) {
+                    const __nv_bfloat16* arow = recq + a.act_off[l] + (size_t)b * 128;
+                    const uint32_t dst = smem_u32(Dt + (size_t)((l - 1) & 1) * kOp);
+                    const int act = a.act[l - 1];
+#pragma unroll
+                    for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+                        uint4 av[4], al[4];
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            av[qq] = row_ok ? __ldg(reinterpret_cast<const uint4*>(arow + c0 + qq * 8)) : make_uint4(0, 0, 0, 0);
+                            al[qq] = (NSP == 2 && act == NCDE_ACT_TANH && row_ok)
+                                         ? __ldg(reinterpret_cast<const uint4*>(arow + (size_t)a.Bp * 128 + c0 + qq * 8)) : make_uint4(0, 0, 0, 0);
+                        }
+                        tmem_wait_ld<32>(r);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const uint32_t aw[4] = {av[qq].x, av[qq].y, av[qq].z, av[qq].w}, lw[4] = {al[qq].x, al[qq].y, al[qq].z, al[qq].w};
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[jj]));
+                                const float2 l2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[jj]));
+                                a2.x += l2.x; a2.y += l2.y;
+                                const float g0 = row_ok ? __uint_as_float(r[8 * qq + 2 * jj]) * act_grad_bf(a2.x, act) : 0.f;
+                                const float g1 = row_ok ? __uint_as_float(r[8 * qq + 2 * jj + 1]) * act_grad_bf(a2.y, act) : 0.f;
+                                if (NSP == 2) split_bf16x2(g0, g1, hi[jj], lo[jj]);
+                                else hi[jj] = pack_bf16x2(g0, g1);
+                            }
+                            const uint32_t o = sw128_off(row, (c0 >> 3) + qq, kTcM);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                            if (NSP == 2)
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kTcHidTile + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                        }
+                    }
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dp_ready);
+                } else {
+                    // dz of stage `ist`, feature-major fp32: plain stores, coalesced over the lanes (= rows)
+                    float* dz = a.kT[ist];
+#pragma unroll
+                    for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+                        tmem_wait_ld<32>(r);
+                        if (row_ok) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj)
+                                if (c0 + jj < a.H) dz[(size_t)(c0 + jj) * a.Bp + b] = __uint_as_float(r[jj]);
+                        }
+                    }
+                    tc_fence_before();
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(out_done);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+static inline size_t ps_bwd_smem_bytes(int Npad, int NSP, int F) {
+    bool res;
+    const int NW = ps_hid_nw(NSP, F, &res);
+    const size_t f = ps_field_bwd_layout(Npad, NSP).total, h = ps_hid_fwd_layout(NSP, NW).total;
+    return 1024 + (f > h ? f : h);
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(kPsThreads, 1) persist_bwd_kernel(const __grid_constant__ PsArgs a, const __grid_constant__ PsMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int bid = blockIdx.x;
+    if (bid < a.n_field) ps_field_bwd<NSP>(a, maps, smem, bid % a.n_hg, bid / a.n_hg);
+    else ps_hidden_bwd<NSP>(a, maps, smem, bid - a.n_field);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// packing for the persistent path: bf16 (hi [, lo]) operand tiles
+// ---------------------------------------------------------------------------------------------------------------
+// final layer: Wp[part][g][nl][k], k contiguous, zero padded (cf. pack_final_bf16_kernel)
+__global__ void ps_pack_final_kernel(const float* __restrict__ W, const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wp,
+                                     float* __restrict__ b3, int H, int C, int Cp, int Hg, int n_hg, int Npad, int DF, int NSP) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)n_hg * Npad * 128;
+    if (idx < total) {
+        const int k = (int)(idx & 127);
+        const int nl = (int)((idx >> 7) % Npad);
+        const int g = (int)(idx / ((int64_t)128 * Npad));
+        const int hl = nl / Cp, c = nl % Cp, h = g * Hg + hl;
+        float v = 0.f;
+        if (hl < Hg && h < H && c < C && k < DF) v = W[((int64_t)h * C + c) * DF + k];
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        Wp[idx] = hi;
+        if (NSP == 2) Wp[total + idx] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+    if (idx < (int64_t)n_hg * Npad) {
+        const int nl = (int)(idx % Npad), g = (int)(idx / Npad);
+        const int hl = nl / Cp, c = nl % Cp, h = g * Hg + hl;
+        b3[idx] = (bias && hl < Hg && h < H && c < C) ? bias[(int64_t)h * C + c] : 0.f;
+    }
+}
+// hidden layer l: Wh[l][part][o][i] zero padded to 128 x 128; bh[l][o]
+__global__ void ps_pack_hidden_kernel(const float* __restrict__ W, const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wh,
+                                      float* __restrict__ bh, int Dout, int Din, int NSP) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 128 * 128) {
+        const int o = idx >> 7, i = idx & 127;
+        const float v = (o < Dout && i < Din) ? W[(size_t)o * Din + i] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        Wh[idx] = hi;
+        if (NSP == 2) Wh[128 * 128 + idx] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+    if (idx < 128) bh[idx] = (bias && idx < Dout) ? bias[idx] : 0.f;
+}
+// z0 (B, H) fp32 row-major -> stage-input record 0: bf16 parts [NSP][Bp][128], feature padding zeroed
+__global__ void ps_z0_record_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int Bp, int H, int NSP) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (int64_t)B * 128) {
+        const int h = (int)(idx & 127);
+        const int64_t b = idx >> 7;
+        const float v = h < H ? src[b * H + h] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        dst[idx] = hi;
+        if (NSP == 2) dst[(size_t)Bp * 128 + idx] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight and bias gradients of the hidden layers for a whole backward pass (cf. tc_hidden_wgrad_kernel), (hi, lo) operands:
+//   dW_l^T[i][o] = sum over (stage, batch tile) units of  a_l^T . dpre_l     (hi*hi + lo*hi + hi*lo)
+// ---------------------------------------------------------------------------------------------------------------
+struct PsWgradArgs {
+    int F, n_rec, n_mt, n_split;
+    float* dWacc[kTcHidMaxLayers];
+    float* dbacc[kTcHidMaxLayers];
+};
+static inline size_t ps_wgrad_smem_bytes(int NSP) {
+    const int NST = NSP == 1 ? 2 : 1;
+    return 1024 + (size_t)NST * 2 * NSP * kTcHidTile + 8 * 128 * 4 + 16 * 8;
+}
+template <int NSP>
+__global__ void __launch_bounds__(kTcThreads, 1) ps_hidden_wgrad_kernel(const __grid_constant__ PsWgradArgs a, const __grid_constant__ PsMaps maps) {
+    constexpr int NST = NSP == 1 ? 2 : 1;                 // pipeline stages
+    constexpr uint32_t kOp = (uint32_t)NSP * kTcHidTile;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* At = smem;                          // NST x a_l operand
+    uint8_t* Dt = smem + NST * kOp;              // NST x dpre_l operand
+    float* bsum = reinterpret_cast<float*>(smem + 2 * NST * kOp);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * NST * kOp + 8 * 128 * 4);
+    uint64_t* full = bars;            // [2]
+    uint64_t* mma_done = bars + 2;    // [2]
+    uint64_t* read_done = bars + 4;   // [2]
+    uint64_t* fin_bar = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l = blockIdx.x, sp = blockIdx.y;
+    const int64_t U = (int64_t)a.n_rec * a.n_mt;
+    const int64_t u_begin = sp * U / a.n_split, u_end = (sp + 1) * U / a.n_split;
+    const int n = (int)(u_end - u_begin);
+
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full + i, 1); mbar_init(mma_done + i, 1); mbar_init(read_done + i, 8); }
+        mbar_init(fin_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && n > 0) {
+            auto load = [&](int j) {
+                const int64_t u = u_begin + j;
+                const int rec = (int)(u / a.n_mt), b0 = (int)(u % a.n_mt) * kTcM;
+                const int bf = j % NST;
+                mbar_expect_tx(full + bf, 2 * kOp);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_4d(At + (size_t)bf * kOp + (size_t)p * kTcHidTile, &maps.act[l], full + bf, 0, b0, p, rec);
+                    tma_load_4d(At + (size_t)bf * kOp + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[l], full + bf, 64, b0, p, rec);
+                    tma_load_4d(Dt + (size_t)bf * kOp + (size_t)p * kTcHidTile, &maps.dpre, full + bf, 0, b0, p, rec * a.F + l);
+                    tma_load_4d(Dt + (size_t)bf * kOp + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.dpre, full + bf, 64, b0, p, rec * a.F + l);
+                }
+            };
+            for (int j = 0; j < NST && j < n; ++j) load(j);
+            const uint32_t idesc = make_idesc(128, 128, 1, 1);
+            for (int j = 0; j < n; ++j) {
+                const int bf = j % NST;
+                const uint32_t ph = (uint32_t)(j / NST) & 1u;
+                mbar_wait(full + bf, ph);
+                tc_fence_after();
+                const uint32_t a_s = smem_u32(At + (size_t)bf * kOp), d_s = smem_u32(Dt + (size_t)bf * kOp);
+                for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
+                    const uint32_t as = a_s + (pr == 1 ? kTcHidTile : 0u), ds = d_s + (pr == 2 ? kTcHidTile : 0u);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t off = (uint32_t)ks * 2048u;
+                        umma_bf16(tmem_base, make_sdesc(as + off, 128u * 128u, 1024), make_sdesc(ds + off, 128u * 128u, 1024), idesc,
+                                  (ks > 0 || pr > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(mma_done + bf);
+                if (j + NST < n) {
+                    mbar_wait(mma_done + bf, ph);
+                    mbar_wait(read_done + bf, ph);
+                    load(j + NST);
+                }
+            }
+            umma_commit(fin_bar);
+        }
+    } else {
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        float bacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const int bf = j % NST;
+            mbar_wait(full + bf, (uint32_t)(j / NST) & 1u);
+            if (lane < 16) {   // 16 chunks of 8 columns x 8 row slices of 16 rows
+                for (int p = 0; p < NSP; ++p) {
+                    const uint32_t d_s = smem_u32(Dt + (size_t)bf * kOp + (size_t)p * kTcHidTile);
+#pragma unroll 4
+                    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+                        uint32_t w4[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                                     : "r"(d_s + sw128_off(r, lane, kTcM)));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                            bacc[2 * q] += f.x;
+                            bacc[2 * q + 1] += f.y;
+                        }
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(read_done + bf);
+        }
+        if (n > 0) {
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[warp * 128 + lane * 8 + j] = bacc[j];
+            }
+            named_bar_sync(1, kTcEpiThreads);
+            if (tid < 128 && a.dbacc[l]) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sacc += bsum[w * 128 + tid];
+                atomicAdd(a.dbacc[l] + tid, sacc);
+            }
+            mbar_wait(fin_bar, 0);
+            tc_fence_after();
+            float* acc = a.dWacc[l];
+            const int i = row;   // TMEM lanes = input feature i, columns = output feature o
+#pragma unroll
+            for (int o0 = wg * 64; o0 < wg * 64 + 64; o0 += 32) {
+                uint32_t r[32];
+                tmem_ld32_issue(lane_addr + (uint32_t)o0, r);
+                tmem_wait_ld<32>(r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(acc + (size_t)(o0 + j) * 128 + i, __uint_as_float(r[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// gy_final = gy + sum of the stage-input gradients of the first step (the persistent backward kernel leaves this last sum open)
+__global__ void ps_gy_final_kernel(float* __restrict__ gyT, const float* dz0, const float* dz1, const float* dz2, const float* dz3,
+                                   int n_dz, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = gyT[i] + dz0[i];
+    if (n_dz > 1) g += dz1[i];
+    if (n_dz > 2) g += dz2[i];
+    if (n_dz > 3) g += dz3[i];
+    gyT[i] = g;
+}
+
+}  // namespace ncde

@@ -7,6 +7,7 @@
 #include "solve_kernels.cuh"
 #include "field_tc.cuh"
 #include "hidden_tc.cuh"
+#include "persist_tc.cuh"
 #include "adaptive_kernels.cuh"
 
 namespace ncde {
@@ -73,6 +74,28 @@ static int make_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, cons
     NCDE_REQUIRE(r == CUDA_SUCCESS, NCDE_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return NCDE_OK;
 }
+// rank-4 bf16 tensor {128 inner, rows, parts, recs} with the 128-byte swizzle, box {64, box_rows, 1, 1} (persistent kernels:
+// operand tiles whose (hi, lo) parts and stage records sit at fixed strides)
+static int make_map4(CUtensorMap* m, const void* base, uint64_t rows, uint64_t parts, uint64_t recs, uint64_t part_stride_bytes,
+                     uint64_t rec_stride_bytes, uint32_t box_rows) {
+    EncodeTiledFn enc;
+    int rc = get_encoder(&enc);
+    if (rc != NCDE_OK) return rc;
+    if (recs < 1) recs = 1;
+    const cuuint64_t dims[4] = {128, rows, parts, recs};
+    if (!part_stride_bytes) part_stride_bytes = 256 * rows;
+    if (!rec_stride_bytes) rec_stride_bytes = part_stride_bytes * parts;
+    const cuuint64_t strides[3] = {256, part_stride_bytes, rec_stride_bytes};
+    const cuuint32_t box[4] = {64, box_rows, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    NCDE_REQUIRE(((uintptr_t)base & 15) == 0 && (strides[1] & 15) == 0 && (strides[2] & 15) == 0, NCDE_ERR_INVALID,
+                 "TMA descriptor: misaligned tensor");
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NCDE_REQUIRE(r == CUDA_SUCCESS, NCDE_ERR_CUDA, "cuTensorMapEncodeTiled (rank 4) failed with code %d", (int)r);
+    return NCDE_OK;
+}
 // The activation / dX records of one solve sit at a fixed stride; launches address them by record index.
 struct TcMapSet {
     TcMaps maps;
@@ -88,6 +111,7 @@ struct Plan {
     int D[NCDE_MAX_LAYERS + 1];
     int Dp4[NCDE_MAX_LAYERS + 1];
     int Hg, S, n_hg, Np, n_bt, Bt, TM;
+    int ns;                   // operand parts of the tensor-core tiles: 1 = bf16, 2 = bf16x3 (hi, lo)
     int tc_hid;               // hidden layers on the tensor cores too (fixed-grid bf16 path): bf16 row-major activation records
     size_t abl_off[NCDE_MAX_LAYERS + 1];   // tc_hid: record offset (floats) of the bf16 [Bp][128] input of layer l
     size_t off_Wh, off_bh;    // tc_hid: packed bf16 hidden weights [F][128][128], fp32 biases [F][128]
@@ -119,7 +143,7 @@ static size_t fwd_smem_floats(int DF, int S) {
 
 // fixed_path: the stored-stage fixed-grid forward / backward (all-tensor-core records allowed);
 // fixed_adjoint: the fixed-grid continuous adjoint (same CUDA-core kernels, so evaluate / derivative and gated fields are allowed)
-static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false, bool fixed_adjoint = false) {
+static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false, bool fixed_adjoint = false, bool for_bwd = false) {
     const bool fixed_kernels = fixed_path || fixed_adjoint;
     memset(pl, 0, sizeof(*pl));
     const ncde_mlp_t& m = p->mlp;
@@ -147,7 +171,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
     pl->B = (int)p->B; pl->H = p->H; pl->C = pl->vf ? 1 : p->C;
     pl->Bp = (int)round_up(p->B, kTcM);
     // channels padded to 4 (float4 epilogues) or 8 (tensor-core path: 16-byte bf16 chunks per h)
-    pl->Cp = (int)round_up(pl->C, p->precision == NCDE_PREC_BF16 ? 8 : 4);
+    pl->Cp = (int)round_up(pl->C, p->precision != NCDE_PREC_FP32 ? 8 : 4);
     pl->gated = m.W_gate != nullptr;
     if (pl->gated) {
         NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 && fixed_kernels, NCDE_ERR_UNSUPPORTED,
@@ -184,16 +208,23 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
     pl->DFP = (int)round_up(pl->DF, 16);
     // fp32 kernels take final-layer inputs up to 256 wide (the reference's hyper-parameter search reaches 196,
     // experiments/configurations/configurations.json5:35); the tensor-core tiles are built for K <= 128
-    NCDE_REQUIRE(pl->DF <= (p->precision == NCDE_PREC_BF16 ? 128 : 256), NCDE_ERR_UNSUPPORTED,
+    NCDE_REQUIRE(pl->DF <= (p->precision != NCDE_PREC_FP32 ? 128 : 256), NCDE_ERR_UNSUPPORTED,
                  "solve: final-layer input width %d > %d not supported for this precision", pl->DF,
-                 p->precision == NCDE_PREC_BF16 ? 128 : 256);
+                 p->precision != NCDE_PREC_FP32 ? 128 : 256);
     NCDE_REQUIRE(pl->Cp <= 128, NCDE_ERR_UNSUPPORTED, "solve: %d input channels > 128 not supported", p->C);
     int dmax = pl->Cp;
     for (int l = 0; l <= pl->F; ++l) dmax = pl->Dp4[l] > dmax ? pl->Dp4[l] : dmax;
     NCDE_REQUIRE(dmax <= 1024, NCDE_ERR_UNSUPPORTED, "solve: layer width %d > 1024 not supported", dmax);
     pl->Dmax = dmax;
 
-    pl->tc = p->precision == NCDE_PREC_BF16;
+    pl->tc = p->precision != NCDE_PREC_FP32;
+    pl->ns = p->precision == NCDE_PREC_BF16X3 ? 2 : 1;
+    if (pl->ns == 2) {
+        NCDE_REQUIRE(fixed_path && !pl->vf && !pl->gated, NCDE_ERR_UNSUPPORTED,
+                     "solve: precision bf16x3 runs on the fixed-grid solvers (euler / rk4, backprop through the steps) with "
+                     "vector_field_type matmul only");
+        NCDE_REQUIRE(m.n_layers >= 2, NCDE_ERR_UNSUPPORTED, "solve: precision bf16x3 needs at least one hidden layer");
+    }
     if (!pl->tc) {
         // field tiling (fp32 kernels): h-groups x batch tiles
         double best = -1.0;
@@ -242,8 +273,14 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
                 if (hg > pl->H) continue;
                 const int npad = (int)round_up(hg * pl->Cp, 16);
                 if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
-                if (tc_bwd_smem_bytes(npad, pl->CpB, pl->bwd_ew) > kSmemLimit) continue;
-                if (tc_fwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
+                if (pl->ns == 2) {
+                    // bf16x3 runs on the persistent kernels only: the pass at hand decides (weights are re-packed per pass)
+                    if (for_bwd ? ps_bwd_smem_bytes(npad, 2, m.n_layers - 1) > kSmemLimit
+                                : ps_fwd_smem_bytes(npad, 2, 1, m.n_layers - 1) > kSmemLimit) continue;
+                } else {
+                    if (tc_bwd_smem_bytes(npad, pl->CpB, pl->bwd_ew) > kSmemLimit) continue;
+                    if (tc_fwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
+                }
                 const int n_hg = (int)ceil_div(pl->H, hg);
                 int n_bt = kNumSMs / n_hg;
                 n_bt = n_bt < 1 ? 1 : (n_bt > n_mt ? n_mt : n_bt);
@@ -301,7 +338,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
     if (pl->tc_hid) {
         // records of the all-tensor-core path: bf16 [Bp][128] input of every layer (the last one feeds the final layer), dX/dt
         off = 0;
-        for (int l = 0; l <= pl->F; ++l) { pl->abl_off[l] = off; off += (size_t)pl->Bp * 64; }
+        for (int l = 0; l <= pl->F; ++l) { pl->abl_off[l] = off; off += (size_t)pl->ns * pl->Bp * 64; }
         pl->abf_off = pl->abl_off[pl->F];
         pl->dx_off = off; off += (size_t)pl->Cp * pl->Bp;
         pl->stage_floats = off;
@@ -349,7 +386,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
     pl->off_W3T = off; off += round_up((size_t)pl->DF * pl->Np, 64);
     pl->off_W3R = off; off += round_up((size_t)pl->Np * pl->DFP, 64);
     pl->off_b3p = off; off += round_up(pl->Np, 64);
-    pl->off_Wh = off; off += (size_t)pl->F * 128 * 64;
+    if (pl->ns == 2) { off = round_up(off, 64); pl->off_W3T = off; off += round_up((size_t)2 * pl->Np * 64, 64); }   // bf16x3: [2][Np][128] bf16
+    pl->off_Wh = off; off += (size_t)pl->ns * pl->F * 128 * 64;
     pl->off_bh = off; off += (size_t)pl->F * 128;
     pl->wpack_floats = off;
     return NCDE_OK;
@@ -412,9 +450,11 @@ static size_t fwd_workspace_floats(const Plan& pl, int need_saved_scratch) {
     if (pl.vf) n += 4 * (size_t)pl.Bp + per;   // the constant "dX/dt" = (1, 0, 0, 0) of the one-channel contraction
     return n;
 }
+static size_t ps_workspace_floats(const Plan& pl, int64_t n_steps, bool bwd);
 static size_t fwd_workspace_extra_floats(const Plan& pl, int64_t n_steps, int need_saved_scratch) {
     size_t per = 256 / 4;
-    size_t n = (size_t)n_steps * pl.n_stages + per;                                  // device copy of the stage times
+    size_t n = (size_t)n_steps * pl.n_stages + per;
+    if (pl.tc_hid) n += ps_workspace_floats(pl, n_steps, false);                                  // device copy of the stage times
     if (need_saved_scratch) n += (size_t)n_steps * pl.n_stages * (pl.vf ? pl.PC : pl.Cp) * pl.Bp + per;  // dX/dt (vf: X or dX/dt) of every stage
     return n;
 }
@@ -431,8 +471,8 @@ static size_t bwd_workspace_floats(const Plan& pl, int64_t n_steps, const SwapPl
     n += (size_t)pl.n_bt * pl.Np + per;
     n += (size_t)pl.wg_split * (pl.wr_floats + 64 * pl.F) + (size_t)pl.wg_split * pl.F * 1024 + 2 * per;
     if (pl.tc_hid)   // dpre records of every stage and hidden layer (consumed by tc_hidden_wgrad), weight-gradient accumulators
-        n += (size_t)(n_steps > 0 ? n_steps : 1) * pl.n_stages * pl.F * pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per +
-             (size_t)(pl.Bp / 128) + per;
+        n += (size_t)(n_steps > 0 ? n_steps : 1) * pl.n_stages * pl.F * pl.ns * pl.Bp * 64 + per + (size_t)pl.F * (128 * 128 + 128) + 2 * per +
+             (size_t)(pl.Bp / 128) + per + ps_workspace_floats(pl, n_steps, true);
     return n;
 }
 
@@ -606,6 +646,121 @@ static cudaError_t launch_field(const Plan& pl, const FieldArgs& fa, bool backwa
                       : launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// persistent whole-pass kernels (persist_tc.cuh): grid shape, eligibility, packing, descriptors
+// ---------------------------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // every CTA must be resident: the roles wait for each other
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+struct PsPlan { int n_mt, n_part, n_field, n_hid, NA; size_t smem; };
+
+static int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = kNumSMs;
+    }
+    return sms;
+}
+
+// every output is the state at the end of a step, at most one per step (online outputs on the grid, terminal output)
+static bool ps_outputs_on_grid(const ncde_fixed_grid_t& g) {
+    int64_t prev = -1;
+    for (int64_t j = 1; j < g.n_out; ++j) {
+        if (g.out_mode[j] != 1 || g.out_step[j] == prev) return false;
+        prev = g.out_step[j];
+    }
+    return true;
+}
+
+static bool ps_eligible(const ncde_problem_t* p, const Plan& pl, bool bwd, PsPlan* pp) {
+    static const bool disabled = getenv("NCDE_NO_PERSIST") != nullptr;
+    if ((disabled && pl.ns == 1) || !pl.tc_hid || pl.F < 1 || p->grid.n_steps < 1 || pl.vf || pl.gated) return false;
+    if (!ps_outputs_on_grid(p->grid)) return false;
+    const int sms = device_sm_count();
+    pp->n_mt = pl.Bp / kTcM;
+    pp->n_hid = pp->n_mt < 16 ? pp->n_mt : 16;
+    while (pp->n_hid > 1 && pl.n_hg + pp->n_hid > sms) --pp->n_hid;
+    if (pl.n_hg + pp->n_hid > sms) return false;
+    pp->n_part = (sms - pp->n_hid) / pl.n_hg;
+    if (pp->n_part > pp->n_mt) pp->n_part = pp->n_mt;
+    pp->n_field = pp->n_part * pl.n_hg;
+    pp->NA = 1;
+    if (bwd) pp->smem = ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F);
+    else {
+        pp->NA = ps_fwd_smem_bytes(pl.Npad, pl.ns, 2, pl.F) <= kSmemLimit ? 2 : 1;
+        pp->smem = ps_fwd_smem_bytes(pl.Npad, pl.ns, pp->NA, pl.F);
+    }
+    return pp->smem <= kSmemLimit && (int64_t)p->grid.n_steps * pl.n_stages * pp->n_mt < (1ll << 30);
+}
+// synchronisation words + device copies of dt / emit slots, in floats
+static size_t ps_workspace_floats(const Plan& pl, int64_t n_steps, bool bwd) {
+    size_t n = 2 * (size_t)(n_steps > 0 ? n_steps : 1) + 2 * (size_t)(pl.Bp / kTcM) + 4 * 64;
+    if (bwd) n += (size_t)(pl.Bp / kTcM) * 128 * 128 + 64 + (size_t)pl.H * pl.Bp + 64;   // dA^T tiles, second gy buffer
+    return n;
+}
+
+static int ps_pack(const ncde_problem_t* p, const Plan& pl, float* wpack, cudaStream_t st, int64_t* launches) {
+    const ncde_mlp_t& m = p->mlp;
+    for (int l = 0; l < pl.F; ++l) {
+        ps_pack_hidden_kernel<<<64, 256, 0, st>>>(m.W[l], m.bias[l], (__nv_bfloat16*)(wpack + pl.off_Wh) + (size_t)l * pl.ns * 128 * 128,
+                                                  wpack + pl.off_bh + (size_t)l * 128, m.out_dim[l], m.in_dim[l], pl.ns);
+        ++*launches;
+    }
+    const int64_t n = (int64_t)pl.Np * 128;
+    ps_pack_final_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(m.W[pl.F], m.bias[pl.F], (__nv_bfloat16*)(wpack + pl.off_W3T),
+                                                                     wpack + pl.off_b3p, pl.H, pl.C, pl.Cp, pl.Hg, pl.n_hg, pl.Npad, pl.DF, pl.ns);
+    ++*launches;
+    NCDE_CUDA_OK(cudaGetLastError());
+    return NCDE_OK;
+}
+
+// descriptors: packed weights, the bf16 activation records (rec0 = first record, stride in floats), dpre records (backward)
+static int ps_build_maps(const Plan& pl, const float* wpack, PsMaps* pm, const float* rec0, size_t rec_stride_floats, int64_t n_rec,
+                         const float* dpre0) {
+    memset(pm, 0, sizeof(*pm));
+    int rc = make_map(&pm->W3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_W3T, 128, (uint64_t)pl.Np, (uint64_t)pl.ns, 256,
+                      (uint64_t)pl.Np * 256, 64, (uint32_t)pl.Npad, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == NCDE_OK) rc = make_map4(&pm->Wh, wpack + pl.off_Wh, 128, (uint64_t)pl.ns, (uint64_t)pl.F, 128 * 256, (uint64_t)pl.ns * 128 * 256, 128);
+    for (int l = 0; l <= pl.F && rc == NCDE_OK; ++l)
+        rc = make_map4(&pm->act[l], rec0 + pl.abl_off[l], (uint64_t)pl.B, (uint64_t)pl.ns, (uint64_t)n_rec, (uint64_t)pl.Bp * 256,
+                       n_rec > 1 ? rec_stride_floats * 4 : 0, kTcM);
+    if (rc == NCDE_OK && dpre0)
+        rc = make_map4(&pm->dpre, dpre0, (uint64_t)pl.B, (uint64_t)pl.ns, (uint64_t)n_rec * pl.F, (uint64_t)pl.Bp * 256,
+                       (uint64_t)pl.ns * pl.Bp * 256, kTcM);
+    return rc;
+}
+
+static void ps_fill_args(PsArgs& a, const ncde_problem_t* p, const Plan& pl, const PsPlan& pp, const float* wpack) {
+    memset(&a, 0, sizeof(a));
+    a.B = pl.B; a.Bp = pl.Bp; a.H = pl.H; a.Cp = pl.Cp; a.Hg = pl.Hg; a.n_hg = pl.n_hg; a.Npad = pl.Npad; a.F = pl.F;
+    a.n_mt = pp.n_mt; a.n_part = pp.n_part; a.n_field = pp.n_field; a.n_hid = pp.n_hid;
+    a.NS = pl.n_stages; a.n_steps = (int)p->grid.n_steps; a.method = p->method; a.NA = pp.NA;
+    for (int l = 0; l < pl.F; ++l) a.act[l] = p->mlp.act[l];
+    a.b3 = wpack + pl.off_b3p;
+    a.bias_h = wpack + pl.off_bh;
+    for (int l = 0; l <= pl.F; ++l) a.act_off[l] = pl.abl_off[l] * 2;
+}
+// host copy of "which output slot receives the state at the end of step s"
+static void ps_emit_slots(const ncde_fixed_grid_t& g, std::vector<int>* slots) {
+    slots->assign((size_t)(g.n_steps > 0 ? g.n_steps : 1), -1);
+    for (int64_t j = 1; j < g.n_out; ++j) (*slots)[(size_t)g.out_step[j]] = (int)j;
+}
+
 }  // namespace ncde
 
 using namespace ncde;
@@ -650,7 +805,7 @@ static size_t adaptive_workspace_floats(const Plan& pl, int64_t n_out) {
 
 extern "C" size_t ncde_solve_workspace_bytes(const ncde_problem_t* p, int backward) {
     Plan pl;
-    if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5) != NCDE_OK) return 0;
+    if (!p || make_plan(p, &pl, p->method != NCDE_DOPRI5, false, backward != 0) != NCDE_OK) return 0;
     if (p->method == NCDE_DOPRI5) return backward ? 0 : adaptive_workspace_floats(pl, p->adaptive.n_out) * 4 + 4096;
     SwapPlan sp;
     if (backward == 2 && (pl.tc || pl.vf || pl.gated || make_swap_plan(pl, &sp) != NCDE_OK)) return 0;   // with the path gradient (fp32 path only)
@@ -676,7 +831,7 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
     NCDE_REQUIRE(workspace_bytes >= (fwd_workspace_floats(pl, !need_grad) +
                                      fwd_workspace_extra_floats(pl, p->grid.n_steps, !need_grad)) * 4,
                  NCDE_ERR_WORKSPACE, "solve_fwd: workspace of %zu bytes is too small", workspace_bytes);
-    NCDE_REQUIRE(p->precision == NCDE_PREC_FP32 || p->precision == NCDE_PREC_BF16, NCDE_ERR_INVALID, "solve_fwd: bad precision");
+    NCDE_REQUIRE(p->precision >= NCDE_PREC_FP32 && p->precision <= NCDE_PREC_BF16X3, NCDE_ERR_INVALID, "solve_fwd: bad precision");
     cudaStream_t st = (cudaStream_t)stream;
     int64_t launches = 0;
     const ncde_fixed_grid_t& g = p->grid;
@@ -698,11 +853,17 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         ++launches;
     }
 
-    rc = pack_weights(p, pl, wpack, 0, st, &launches);
+    float* ps_ws = pl.tc_hid ? cv.take(ps_workspace_floats(pl, g.n_steps, false)) : nullptr;
+    PsPlan pp;
+    const bool persist = ps_eligible(p, pl, false, &pp);
+    NCDE_REQUIRE(persist || pl.ns == 1, NCDE_ERR_UNSUPPORTED,
+                 "solve_fwd: precision bf16x3 needs hidden layers of width <= 128 and every output time on a grid point");
+    rc = persist ? ps_pack(p, pl, wpack, st, &launches) : pack_weights(p, pl, wpack, 0, st, &launches);
     if (rc != NCDE_OK) return rc;
 
     const bool use_tc = pl.tc != 0;
-    if (use_tc) rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem);
+    if (persist) rc = NCDE_OK;
+    else if (use_tc) rc = opt_in_smem(tc_field_fwd_kernel, pl.fwd_smem);
     else rc = opt_in_field(pl, false);
     if (rc != NCDE_OK) return rc;
 
@@ -758,6 +919,55 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
             dx_all_kernel<<<dim3((unsigned)n_st_total, (unsigned)ceil_div(pl.B, 32)), 256, 0, st>>>(da);
         }
         ++launches;
+    }
+
+    if (persist) {
+        // ONE launch runs every stage of every step (persist_tc.cuh)
+        float* const rec0p = need_grad ? (float*)saved : scratch_stage;
+        const int64_t n_rec = need_grad ? n_st_total : 1;
+        float* d_dt = ps_ws;
+        int* d_emit = (int*)(ps_ws + round_up(g.n_steps, 64));
+        int* sync = d_emit + round_up(g.n_steps, 64);
+        std::vector<int> slots;
+        ps_emit_slots(g, &slots);
+        NCDE_CUDA_OK(cudaMemcpyAsync(d_dt, g.dt, (size_t)g.n_steps * 4, cudaMemcpyHostToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(d_emit, slots.data(), (size_t)g.n_steps * 4, cudaMemcpyHostToDevice, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(sync, 0, (size_t)2 * pp.n_mt * sizeof(int), st));
+        // feature padding (and, for the stage-input records, every column until the kernels write them) must be zero
+        NCDE_CUDA_OK(cudaMemset2DAsync(rec0p + pl.abl_off[0], (need_grad ? pl.stage_floats : (size_t)pl.ns * pl.Bp * 64) * 4, 0,
+                                       (size_t)pl.ns * pl.Bp * 256, (size_t)n_rec, st));
+        ps_z0_record_kernel<<<(unsigned)ceil_div((int64_t)pl.B * 128, 256), 256, 0, st>>>(z0, (__nv_bfloat16*)(rec0p + pl.abl_off[0]), pl.B,
+                                                                                         pl.Bp, pl.H, pl.ns);
+        ++launches;
+        PsMaps pm;
+        rc = ps_build_maps(pl, wpack, &pm, rec0p, pl.stage_floats, n_rec, nullptr);
+        if (rc != NCDE_OK) return rc;
+        PsArgs pa;
+        ps_fill_args(pa, p, pl, pp, wpack);
+        pa.need_grad = need_grad ? 1 : 0;
+        pa.dt = d_dt; pa.emit_idx = d_emit; pa.z_out = z_out;
+        pa.yT[0] = yT[0]; pa.yT[1] = yT[1];
+        for (int i = 0; i < NS; ++i) pa.kT[i] = kT[i];
+        pa.rec0 = (__nv_bfloat16*)rec0p;
+        pa.rec_stride = need_grad ? pl.stage_floats * 2 : 0;
+        pa.dx0 = need_grad ? (const float*)saved + pl.dx_off : dx_all;
+        pa.dx_stride = need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp;
+        pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
+        const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
+        {
+            ProfScope ps(NCDE_PROF_SOLVE_FWD, st);
+            if (pl.ns == 2) {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(persist_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+                NCDE_CUDA_OK(launch_coop(persist_fwd_kernel<2>, grid, dim3(kPsThreads), pp.smem, st, pa, pm));
+            } else {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(persist_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+                NCDE_CUDA_OK(launch_coop(persist_fwd_kernel<1>, grid, dim3(kPsThreads), pp.smem, st, pa, pm));
+            }
+        }
+        ++launches;
+        NCDE_CUDA_OK(cudaGetLastError());
+        if (launches_out) *launches_out = launches;
+        return NCDE_OK;
     }
 
     TcMapSet ms;
@@ -903,7 +1113,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     ncde::DeviceGuard device_guard(grad_out);
     NCDE_REQUIRE(p && grad_out && saved && grad_z0 && gW && gbias && workspace, NCDE_ERR_INVALID, "solve_bwd: null pointer");
     Plan pl;
-    int rc = make_plan(p, &pl, true);
+    int rc = make_plan(p, &pl, true, false, true);
     if (rc != NCDE_OK) return rc;
     rc = validate_grid(p, pl);
     if (rc != NCDE_OK) return rc;
@@ -951,11 +1161,109 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
     // all-tensor-core path: one bf16 record for dL/d(pre-activation of the last hidden layer), padded fp32 accumulators
     const bool tc_hid = pl.tc_hid && pl.F > 0;
     const int64_t n_rec_all = g.n_steps * NS;
-    float* dpre_rec = tc_hid ? cv.take((size_t)(n_rec_all > 0 ? n_rec_all : 1) * pl.F * pl.Bp * 64) : nullptr;   // [rec][layer][Bp][128] bf16
+    float* dpre_rec = tc_hid ? cv.take((size_t)(n_rec_all > 0 ? n_rec_all : 1) * pl.F * pl.ns * pl.Bp * 64) : nullptr;   // [rec][layer][part][Bp][128] bf16
     int* tile_count = tc_hid ? (int*)cv.take((size_t)(pl.Bp / 128)) : nullptr;   // fused reduction: column blocks done per batch tile
     float* dWh_acc = tc_hid ? cv.take((size_t)pl.F * 128 * 128) : nullptr;
     float* dbh_acc = tc_hid ? cv.take((size_t)pl.F * 128) : nullptr;
 
+    float* ps_ws = pl.tc_hid ? cv.take(ps_workspace_floats(pl, g.n_steps, true)) : nullptr;
+    PsPlan pp;
+    const bool persist = !grad_coeffs && ps_eligible(p, pl, true, &pp);
+    NCDE_REQUIRE(persist || pl.ns == 1, NCDE_ERR_UNSUPPORTED,
+                 "solve_bwd: precision bf16x3 needs hidden layers of width <= 128 and every output time on a grid point");
+    if (persist) {
+        // ONE launch runs the backward pass of every stage (persist_tc.cuh), then the hidden weight gradients in one split-K launch
+        const int64_t n_rec = n_rec_all;
+        float* d_dt = ps_ws;
+        int* d_emit = (int*)(ps_ws + round_up(g.n_steps, 64));
+        int* sync = d_emit + round_up(g.n_steps, 64);
+        float* dAT = (float*)(sync + round_up(2 * pp.n_mt, 64));
+        float* gy2 = dAT + (size_t)pp.n_mt * 128 * 128 + 64;
+        std::vector<int> slots;
+        ps_emit_slots(g, &slots);
+        NCDE_CUDA_OK(cudaMemcpyAsync(d_dt, g.dt, (size_t)g.n_steps * 4, cudaMemcpyHostToDevice, st));
+        NCDE_CUDA_OK(cudaMemcpyAsync(d_emit, slots.data(), (size_t)g.n_steps * 4, cudaMemcpyHostToDevice, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(sync, 0, (size_t)2 * pp.n_mt * sizeof(int), st));
+        NCDE_CUDA_OK(cudaMemsetAsync(dAT, 0, (size_t)pp.n_mt * 128 * 128 * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(gyT, 0, nHB * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(gy2, 0, nHB * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, (size_t)pp.n_part * pl.Np * 128 * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(db3acc, 0, (size_t)pp.n_part * pl.Np * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(dWh_acc, 0, (size_t)pl.F * (128 * 128) * 4, st));
+        NCDE_CUDA_OK(cudaMemsetAsync(dbh_acc, 0, (size_t)pl.F * 128 * 4, st));
+        rc = ps_pack(p, pl, wpack, st, &launches);
+        if (rc != NCDE_OK) return rc;
+        PsMaps pm;
+        rc = ps_build_maps(pl, wpack, &pm, (const float*)saved, pl.stage_floats, n_rec, dpre_rec);
+        if (rc != NCDE_OK) return rc;
+        PsArgs pa;
+        ps_fill_args(pa, p, pl, pp, wpack);
+        pa.need_grad = 1;
+        pa.dt = d_dt; pa.emit_idx = d_emit; pa.grad_out = grad_out;
+        pa.yT[0] = gyT; pa.yT[1] = gy2;
+        for (int i = 0; i < NS; ++i) pa.kT[i] = gkT[i];
+        pa.rec0 = (__nv_bfloat16*)const_cast<void*>(saved);
+        pa.rec_stride = pl.stage_floats * 2;
+        pa.dx0 = (const float*)saved + pl.dx_off;
+        pa.dx_stride = pl.stage_floats;
+        pa.dAT = dAT; pa.dW3acc = dW3acc; pa.db3acc = db3acc; pa.dpre0 = (__nv_bfloat16*)dpre_rec;
+        pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
+        const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
+        {
+            ProfScope ps(NCDE_PROF_SOLVE_BWD, st);
+            if (pl.ns == 2) {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(persist_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+                NCDE_CUDA_OK(launch_coop(persist_bwd_kernel<2>, grid, dim3(kPsThreads), pp.smem, st, pa, pm));
+            } else {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(persist_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+                NCDE_CUDA_OK(launch_coop(persist_bwd_kernel<1>, grid, dim3(kPsThreads), pp.smem, st, pa, pm));
+            }
+        }
+        ++launches;
+        ps_gy_final_kernel<<<(unsigned)ceil_div((int64_t)nHB, 256), 256, 0, st>>>(gyT, gkT[0], gkT[1], gkT[2], gkT[3], NS, (int64_t)nHB);
+        ++launches;
+        {
+            PsWgradArgs wga;
+            memset(&wga, 0, sizeof(wga));
+            wga.F = pl.F; wga.n_rec = (int)n_rec; wga.n_mt = pp.n_mt;
+            const int64_t units = n_rec * wga.n_mt;
+            const int n_split = device_sm_count() / pl.F;
+            wga.n_split = (int)(n_split > units ? units : n_split);
+            for (int l = 0; l < pl.F; ++l) {
+                wga.dWacc[l] = dWh_acc + (size_t)pl.first_of_slot[l] * 128 * 128;
+                wga.dbacc[l] = dbh_acc + (size_t)pl.first_of_slot[l] * 128;
+            }
+            ProfScope ps(NCDE_PROF_HIDDEN_WGRAD, st);
+            if (pl.ns == 2) {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(ps_hidden_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_wgrad_smem_bytes(2)));
+                ps_hidden_wgrad_kernel<2><<<dim3(pl.F, wga.n_split), kTcThreads, ps_wgrad_smem_bytes(2), st>>>(wga, pm);
+            } else {
+                NCDE_CUDA_OK(cudaFuncSetAttribute(ps_hidden_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_wgrad_smem_bytes(1)));
+                ps_hidden_wgrad_kernel<1><<<dim3(pl.F, wga.n_split), kTcThreads, ps_wgrad_smem_bytes(1), st>>>(wga, pm);
+            }
+        }
+        ++launches;
+        for (int l = 0; l < pl.F; ++l) {
+            if (pl.first_of_slot[l] != l) continue;
+            const int n = m.out_dim[l] * m.in_dim[l];
+            unpack_hidden_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dWh_acc + (size_t)l * 128 * 128, dbh_acc + (size_t)l * 128,
+                                                                                gW[l], gbias[l], m.out_dim[l], m.in_dim[l]);
+            ++launches;
+        }
+        const dim3 tbp(32, 8), tgp((unsigned)ceil_div(pl.B, 32), (unsigned)ceil_div(pl.H, 32));
+        from_feature_major_kernel<<<tgp, tbp, 0, st>>>(gyT, grad_out, grad_z0, pl.B, pl.Bp, pl.H);
+        ++launches;
+        NCDE_REQUIRE(gW[pl.F] != nullptr, NCDE_ERR_INVALID, "solve_bwd: gW of the final layer is null");
+        {
+            const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
+            unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dW3acc, db3acc, gW[pl.F], gbias[pl.F], pl.H, pl.C, pl.Cp,
+                                                                                 pl.Hg, pl.Npad, pl.DF, 128, pl.Np, pp.n_part);
+            ++launches;
+        }
+        NCDE_CUDA_OK(cudaGetLastError());
+        if (launches_out) *launches_out = launches;
+        return NCDE_OK;
+    }
     rc = pack_weights(p, pl, wpack, 1, st, &launches);
     if (rc != NCDE_OK) return rc;
     const bool use_tc = pl.tc != 0;

@@ -19,7 +19,7 @@ F32, F64 = 0, 1
 PATH_LINEAR, PATH_CUBIC = 0, 1
 EULER, RK4_38, DOPRI5 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_GATE_IN = 0, 1, 2, 3
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 VF_MATMUL, VF_EVALUATE, VF_DERIVATIVE = 0, 1, 2
 RAGGED_LINEAR, RAGGED_RECTILINEAR, RAGGED_CUBIC = 0, 1, 2
 FLAG_NAN_TIME, FLAG_NONFINITE, FLAG_DT_UNDERFLOW, FLAG_MAX_STEPS = 1, 2, 4, 8
@@ -84,7 +84,7 @@ SYMBOLS = ["ncde_version", "ncde_last_error", "ncde_abi_version", "ncde_forward_
            "ncde_solve_adjoint_bwd", "ncde_solve_adjoint_adaptive_workspace_bytes",
            "ncde_solve_adjoint_adaptive_bwd", "ncde_profile_enable", "ncde_profile_read"]
 
-PROF_CLASSES = ["hidden_fwd", "field_fwd", "field_bwd", "hidden_bwd", "hidden_wgrad", "other"]
+PROF_CLASSES = ["hidden_fwd", "field_fwd", "field_bwd", "hidden_bwd", "hidden_wgrad", "other", "solve_fwd", "solve_bwd"]
 
 
 def lib():
@@ -140,7 +140,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("ncde_abi_version",):
             fn.restype = i32
-    if L.ncde_abi_version() != 3:
+    if L.ncde_abi_version() != 4:
         raise RuntimeError("libncde_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -20,7 +20,7 @@ from .interpolation_linear import LinearInterpolation
 _METHODS = {"euler": _capi.EULER, "rk4": _capi.RK4_38, "dopri5": _capi.DOPRI5}
 _ALL_TORCHDIFFEQ_METHODS = ("dopri8", "dopri5", "bosh3", "fehlberg2", "adaptive_heun", "euler", "midpoint", "rk4",
                             "explicit_adams", "implicit_adams", "fixed_adams", "scipy_solver")
-_PRECISIONS = {"fp32": _capi.PREC_FP32, "bf16": _capi.PREC_BF16}
+_PRECISIONS = {"fp32": _capi.PREC_FP32, "bf16": _capi.PREC_BF16, "bf16x3": _capi.PREC_BF16X3}
 
 _THIRD = 1 / 3
 _TWO_THIRDS = 2 / 3

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(built, name), "library does not export " + name
     assert sorted(_capi.SYMBOLS) == declared
-    assert built.ncde_abi_version() == 3
+    assert built.ncde_abi_version() == 4
     assert b"sm_100a" in built.ncde_version()
 
 

@@ -5,7 +5,7 @@ reference by tests/test_oracle_golden.py) — not against another mode of the pr
 
 Bounds, relative max-norm, written per mode in BOUNDS below:
     fp32     states 1e-5, gradients 1e-5 (rows excluded only under the rule of tests/parity_util.py)
-    fp16x3   states 1e-4, gradients 1e-3   (split-precision tensor-core tiles: fp16 hi + lo operand pairs, 3 MMAs per GEMM)
+    bf16x3   states 1e-4, gradients 1e-3   (split-precision tensor-core tiles: bf16 hi + lo operand pairs, 3 MMAs per GEMM)
     bf16     states 1e-2, gradients 1.5e-1 (single bf16 tensor-core tiles; 568 chained stages)
 """
 import copy
@@ -18,12 +18,12 @@ from oracle import cde_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-BOUNDS = {"fp32": (1e-5, 1e-5), "fp16x3": (1e-4, 1e-3), "bf16": (1e-2, 1.5e-1)}
+BOUNDS = {"fp32": (1e-5, 1e-5), "bf16x3": (1e-4, 1e-3), "bf16": (1e-2, 1.5e-1)}
 
 
 def _modes():
     from torchcde_b200 import solver
-    return [m for m in ("fp32", "fp16x3", "bf16") if m in solver._PRECISIONS]
+    return [m for m in ("fp32", "bf16x3", "bf16") if m in solver._PRECISIONS]
 
 
 def _problem(B, seed):
@@ -64,7 +64,7 @@ def _gpu(run, precision, row_mask=None):
     return out.detach().cpu(), z.grad.cpu(), {n: p.grad.cpu() for n, p in fd.named_parameters()}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 def test_cfg5_full_length_against_oracle(oracle_run, precision):
     if precision not in _modes():
         pytest.skip("precision mode %s not built" % precision)
@@ -89,15 +89,15 @@ def test_cfg5_full_length_against_oracle(oracle_run, precision):
     assert max(errs.values()) <= tol_grad, errs
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 def test_training_equivalence_cfg1(precision):
     """50 Adam steps of the toy configuration (BASELINE.json configs[0]: Brownian paths, rectilinear, RK4, hidden 32,
     width 128, experiments/sim_bm_toy_example.py): the loss curve of the product must track the oracle's within a stated
-    band of the initial loss — 1e-3 for fp32 / fp16x3, 3e-2 for bf16 tiles."""
+    band of the initial loss — 1e-3 for fp32 / bf16x3, 3e-2 for bf16 tiles."""
     if precision not in _modes():
         pytest.skip("precision mode %s not built" % precision)
     import torchcde_b200 as tc
-    band = {"fp32": 1e-3, "fp16x3": 1e-3, "bf16": 3e-2}[precision]
+    band = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 3e-2}[precision]
     B, L, C, H = 128, 3, 2, 32
     g = torch.Generator().manual_seed(21)
     dt = 1.0 / (L - 1)
