@@ -23,7 +23,7 @@
 
 namespace ncde {
 
-constexpr int kPsThreads = 320;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), warp 9 = signaller
+constexpr int kPsThreads = 352;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), 9 = signaller, 10 = dX/dt loader
 constexpr int kPsEpi = 256;
 constexpr long long kPsSpinLimit = 6000000000ll;   // ~3 s at 2 GHz: a protocol error traps instead of hanging the GPU
 
@@ -32,12 +32,13 @@ struct PsMaps {
     CUtensorMap Wh;                              // {128 in, 128 out, NSP, F}            box {64, 128, 1, 1}
     CUtensorMap act[kTcHidMaxLayers + 1];        // act[l]: bf16 input of layer l, {128, B, NSP, n_rec}, box {64, 128, 1, 1}
     CUtensorMap dpre;                            // backward: {128, B, NSP, n_rec * F}
+    CUtensorMap X;                               // dX/dt records fp32 {Cp, B, n_rec}, box {36, 128, 1}, no swizzle
 };
 
 struct PsArgs {
     int B, Bp, H, Cp, Hg, n_hg, Npad, F;
     int n_mt, n_part, n_field, n_hid;
-    int NS, n_steps, method, need_grad, NA, w_resident;
+    int NS, n_steps, method, need_grad, NA, NX;    // NA: activation buffers of the forward field role; NX: dX/dt chunk slots
     int act[kTcHidMaxLayers];
     const float* dt;            // device [n_steps]
     const int* emit_idx;        // device [n_steps]: output slot that receives the state at the end of step s, or -1
@@ -60,7 +61,16 @@ struct PsArgs {
     // synchronisation words (zeroed before the launch)
     int* cnt_f;                 // [n_mt] field -> hidden: arrivals of field CTAs (monotonic)
     int* flag_h;                // [n_mt] hidden -> field: stages completed by the hidden CTA (monotonic)
+    unsigned long long* trace;  // debug (NCDE_PS_TRACE): [stage][16] globaltimer stamps of tile 0's hand-offs, or null
 };
+constexpr int kPsTraceStages = 48;
+__device__ __forceinline__ void ps_trace(const PsArgs& a, int t, int g, int q, int ev) {
+    if (a.trace && t == 0 && g == 0 && q < kPsTraceStages) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        a.trace[q * 16 + ev] = ns;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -79,7 +89,7 @@ __device__ __forceinline__ void ps_spin_ge(const int* p, int target) {
     if (ld_acquire_gpu(p) >= target) return;
     const long long t0 = clock64();
     while (ld_acquire_gpu(p) < target) {
-        __nanosleep(40);
+        __nanosleep(20);
         if (clock64() - t0 > kPsSpinLimit) __trap();
     }
 }
@@ -105,6 +115,13 @@ __device__ __forceinline__ float4 ldg128_nc(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+}
+// the n floats at p (one batch row of dX/dt, 16-byte aligned) -> L1, one request per 128-byte line
+__device__ __forceinline__ void ps_prefetch_row(const float* p, int n) {
+    const char* c = reinterpret_cast<const char*>(p);
+    const char* e = c + (size_t)n * 4;
+    for (const char* q = reinterpret_cast<const char*>((uintptr_t)c & ~(uintptr_t)127); q < e; q += 128)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
 }
 // (hi, lo) bf16 split of two floats, packed
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -143,34 +160,59 @@ __device__ __forceinline__ void ps_gemm_kmajor(uint32_t d_tmem, uint32_t a_s, ui
     }
 }
 
-// one W-column chunk of a final-layer epilogue for TMEM lane `row`: accumulator values in flight (tcgen05.ld) and this row's dX/dt
-// values in flight (ld.global) until ps_chunk_wait
-template <int W>
-struct PsChunk {
-    uint32_t r[W];
-    float4 dd[W / 4];
-    uint32_t b3_s;
-};
-template <int W>
-__device__ __forceinline__ void ps_chunk_issue(PsChunk<W>& k, uint32_t taddr, uint32_t b3_s, const float* dx, bool row_ok) {
-    tmem_ldw_issue<W>(taddr, k.r);
-    k.b3_s = b3_s;
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) k.dd[q] = row_ok ? ldg128_nc(dx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+// dX/dt reaches the epilogue threads through a ring of chunk slots in shared memory: slot = [128 rows][36 floats] (32 channels + 4 of
+// padding: a 144-byte pitch keeps the per-row LDS.128 of consecutive lanes on distinct banks), filled by the loader warp with one TMA
+// box per chunk, in exactly the order the epilogue consumes them (unit after unit, h after h, chunk after chunk).
+constexpr int kPsXPitch = 36;
+constexpr uint32_t kPsXSlot = kTcM * kPsXPitch * 4;     // 18432 bytes
+constexpr int kPsMaxSlots = 8;
+
+// 16 accumulator columns of TMEM lane `row` in flight
+struct PsHalf { uint32_t r[16]; };
+__device__ __forceinline__ void ps_half_issue(PsHalf& k, uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(k.r[0]), "=r"(k.r[1]), "=r"(k.r[2]), "=r"(k.r[3]), "=r"(k.r[4]), "=r"(k.r[5]), "=r"(k.r[6]), "=r"(k.r[7]),
+                   "=r"(k.r[8]), "=r"(k.r[9]), "=r"(k.r[10]), "=r"(k.r[11]), "=r"(k.r[12]), "=r"(k.r[13]), "=r"(k.r[14]), "=r"(k.r[15])
+                 : "r"(taddr) : "memory");
 }
-template <int W, bool EXACT>
-__device__ __forceinline__ float ps_fwd_finish(const PsChunk<W>& k) {
+// sum_j tanh(D[row][j] + b3[j]) * dX[row][j] over the first nv (0, 8 or 16) columns of the half
+template <bool EXACT>
+__device__ __forceinline__ float ps_fwd_half(const PsHalf& k, int nv, uint32_t b3_s, uint32_t x_s) {
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (nv == 16) {   // the common case, branch-free: every load first, then the arithmetic
+        float4 bb[4], dd[4];
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-        const float4 bb = lds128(k.b3_s + 16u * q);
-        const float4 dd = k.dd[q];
-        acc0 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb.x), dd.x, acc0);
-        acc1 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb.y), dd.y, acc1);
-        acc2 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb.z), dd.z, acc2);
-        acc3 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb.w), dd.w, acc3);
+        for (int q = 0; q < 4; ++q) { bb[q] = lds128(b3_s + 16u * q); dd[q] = lds128(x_s + 16u * q); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc0 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb[q].x), dd[q].x, acc0);
+            acc1 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb[q].y), dd[q].y, acc1);
+            acc2 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb[q].z), dd[q].z, acc2);
+            acc3 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb[q].w), dd[q].w, acc3);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * q < nv) {
+                const float4 bb = lds128(b3_s + 16u * q), dd = lds128(x_s + 16u * q);
+                acc0 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb.x), dd.x, acc0);
+                acc1 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb.y), dd.y, acc1);
+                acc2 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb.z), dd.z, acc2);
+                acc3 = fmaf(ps_tanh<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb.w), dd.w, acc3);
+            }
+        }
     }
     return (acc0 + acc1) + (acc2 + acc3);
+}
+// the chunk sequence of one unit, identical for the loader and every epilogue warp: n_pass passes over nch chunks
+struct PsXSeq {
+    int n_pass, nch;
+};
+__device__ __forceinline__ PsXSeq ps_xseq(int Hg, int Cp) {
+    PsXSeq q;
+    q.n_pass = Hg >= 2 ? Hg - Hg / 2 : 1;      // hidden rows per warp-group (the larger share when Hg is odd)
+    q.nch = (Cp + 31) / 32;
+    return q;
 }
 
 // unit i of a field CTA -> (global stage index q, batch tile t)
@@ -185,39 +227,48 @@ __device__ __forceinline__ PsUnit ps_unit_fwd(int i, int n_my, int part, int n_p
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory layouts (byte offsets from the 1024-aligned base)
 // ---------------------------------------------------------------------------------------------------------------
-struct PsFieldFwdSmem { uint32_t Ws, As, b3s, part, bars, total; };
-__host__ __device__ inline PsFieldFwdSmem ps_field_fwd_layout(int Npad, int NSP, int NA) {
+struct PsFieldFwdSmem { uint32_t Ws, As, Xs, b3s, part, bars, total; };
+__host__ __device__ inline PsFieldFwdSmem ps_field_fwd_layout(int Npad, int NSP, int NA, int NX) {
     PsFieldFwdSmem L;
     uint32_t o = 0;
     L.Ws = o; o += (uint32_t)NSP * (uint32_t)Npad * 256u;
     o = (o + 1023u) & ~1023u;
     L.As = o; o += (uint32_t)NA * (uint32_t)NSP * kTcHidTile;
+    L.Xs = o; o += (uint32_t)NX * kPsXSlot;
     L.b3s = o; o += (uint32_t)Npad * 4;
     L.part = o; o += kTcM * 4;
     o = (o + 15u) & ~15u;
-    L.bars = o; o += 24 * 8;
+    L.bars = o; o += 40 * 8;
     L.total = o;
     return L;
 }
 struct PsHidFwdSmem { uint32_t Wt, At, bias, bars, total; };
-__host__ __device__ inline PsHidFwdSmem ps_hid_fwd_layout(int NSP, int NW) {
+__host__ __device__ inline PsHidFwdSmem ps_hid_fwd_layout(int NSP, int NW, int n_op = 1) {
     PsHidFwdSmem L;
     uint32_t o = 0;
     L.Wt = o; o += (uint32_t)NW * (uint32_t)NSP * kTcHidTile;
-    L.At = o; o += 2u * (uint32_t)NSP * kTcHidTile;
+    L.At = o; o += (uint32_t)n_op * (uint32_t)NSP * kTcHidTile;
     L.bias = o; o += kTcHidMaxLayers * 128 * 4;
     L.bars = o; o += 24 * 8;
     L.total = o;
     return L;
 }
 // weight buffers of the hidden role: all F layers resident when they fit next to the activation tiles, else a ring
-__host__ __device__ inline int ps_hid_nw(int NSP, int F, bool* resident) {
+__host__ __device__ inline int ps_hid_nw(int NSP, int F, bool* resident, int n_op = 1) {
     const uint32_t budget = 220u * 1024u;
-    const uint32_t fixed = 2u * NSP * kTcHidTile + kTcHidMaxLayers * 512 + 1024 + 24 * 8;
+    const uint32_t fixed = (uint32_t)n_op * NSP * kTcHidTile + kTcHidMaxLayers * 512 + 1024 + 24 * 8;
     const int fit = (int)((budget - fixed) / ((uint32_t)NSP * kTcHidTile));
     if (fit >= F) { *resident = true; return F; }
     *resident = false;
     return fit >= 2 ? 2 : 1;
+}
+
+// operand tiles of the forward hidden role: two (no wait between a record store and the next epilogue) when the resident weights
+// leave room, else one (the epilogue overwrites the tile the MMA has finished reading, after the record store has read it)
+__host__ __device__ inline int ps_hid_fwd_nop(int NSP, int F) {
+    bool res;
+    ps_hid_nw(NSP, F, &res, 2);
+    return res ? 2 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -263,11 +314,12 @@ __device__ __forceinline__ void ps_fwd_finish_element(const PsArgs& a, int q, in
 template <int NSP>
 __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int g, int part) {
     constexpr bool EXACT = NSP == 2;
-    const int Npad = a.Npad, NA = a.NA;
-    const PsFieldFwdSmem L = ps_field_fwd_layout(Npad, NSP, NA);
+    const int Npad = a.Npad, NA = a.NA, NX = a.NX;
+    const PsFieldFwdSmem L = ps_field_fwd_layout(Npad, NSP, NA, NX);
     const uint32_t w_part = (uint32_t)Npad * 256u;
     uint8_t* Ws = smem + L.Ws;
     uint8_t* As = smem + L.As;
+    uint8_t* Xs = smem + L.Xs;
     float* b3s = reinterpret_cast<float*>(smem + L.b3s);
     float* partial = reinterpret_cast<float*>(smem + L.part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -277,16 +329,20 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* w_bar = bars + 6;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
     volatile int* sig_done = reinterpret_cast<volatile int*>(bars + 8);
+    uint64_t* x_full = bars + 10;     // [NX <= 8]
+    uint64_t* x_free = bars + 18;     // [NX <= 8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t acc_stride = tc_tmem_cols(Npad);
     const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
     const int n_q = a.n_steps * a.NS;
     const int n_units = n_my * n_q;
+    const PsXSeq xq = ps_xseq(a.Hg, a.Cp);
 
     if (warp == 0) tmem_alloc(tmem_slot, 2 * acc_stride);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(full_a + i, 1); mbar_init(mma_bar + i, 1); mbar_init(done + i, 8); }
+        for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
         mbar_init(w_bar, 1);
         *sig_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -310,6 +366,7 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const int b = i & 1, ba = NA == 2 ? b : 0;
                 if (i >= NA) ps_wait(mma_bar + ((i - NA) & 1), (uint32_t)((i - NA) >> 1) & 1u);   // activation buffer free
                 ps_spin_ge(a.flag_h + u.t, u.q + 1);            // the hidden CTA has written the tile's final-layer input of stage q
+                ps_trace(a, u.t, g, u.q, 0);
                 fence_proxy_async_all();
                 uint8_t* dst = As + (size_t)ba * NSP * kTcHidTile;
                 const int rec = a.need_grad ? u.q : 0;
@@ -318,17 +375,13 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.act[a.F], full_a + ba, 0, u.t * kTcM, p, rec);
                     tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a + ba, 64, u.t * kTcM, p, rec);
                 }
-                if (i + 1 < n_units) {   // dX/dt tile of the next unit -> L2 (the epilogue threads read it with plain loads)
-                    const PsUnit un = ps_unit_fwd(i + 1, n_my, part, a.n_part);
-                    const int rows = min(kTcM, a.B - un.t * kTcM);
-                    l2_prefetch_bulk(a.dx0 + (size_t)un.q * a.dx_stride + (size_t)un.t * kTcM * a.Cp, (uint32_t)rows * a.Cp * 4u);
-                }
                 if (i >= 2) {
                     ps_wait(done + b, (uint32_t)((i - 2) >> 1) & 1u);        // accumulator b drained by the epilogue of unit i-2
                     while (*sig_done < i - 1) {}                              // ... and that unit was signalled (keeps the signaller in phase)
                 }
                 if (i == 0) ps_wait(w_bar, 0);
                 ps_wait(full_a + ba, (uint32_t)(i / NA) & 1u);
+                ps_trace(a, u.t, g, u.q, 1);
                 tc_fence_after();
                 ps_gemm_kmajor<NSP>(tmem_base + (uint32_t)b * acc_stride, smem_u32(dst), kTcHidTile, kTcM, smem_u32(Ws), w_part, Npad, Npad);
                 umma_commit(mma_bar + b);
@@ -339,19 +392,37 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
                 ps_wait(done + (i & 1), (uint32_t)(i >> 1) & 1u);
-                __threadfence();
-                red_release_gpu_add(a.cnt_f + u.t, 1);
+                red_release_gpu_add(a.cnt_f + u.t, 1);      // release: cumulative over the epilogue warps' writes (ordered by the mbarrier)
+                ps_trace(a, u.t, g, u.q, 4);
                 *sig_done = i + 1;
+            }
+        }
+    } else if (warp == 10) {
+        // dX/dt loader: the records were written before the launch, so it simply runs NX chunks ahead of the epilogue
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.X);
+            int slot = 0;
+            uint32_t lap = 0;          // completed laps of the ring
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
+                for (int p = 0; p < xq.n_pass; ++p)
+                    for (int j = 0; j < xq.nch; ++j) {
+                        if (lap > 0) ps_wait(x_free + slot, (lap - 1) & 1u);
+                        mbar_expect_tx(x_full + slot, kPsXSlot);
+                        tma_load_3d(Xs + (size_t)slot * kPsXSlot, &maps.X, x_full + slot, 32 * j, u.t * kTcM, u.q);
+                        if (++slot == NX) { slot = 0; ++lap; }
+                    }
             }
         }
     } else {
         const int wg = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
-        int h_begin, h_end, c_begin, c_end;
-        if (a.Hg >= 2) { h_begin = wg == 0 ? 0 : a.Hg / 2; h_end = wg == 0 ? a.Hg / 2 : a.Hg; c_begin = 0; c_end = a.Cp; }
-        else { const int half = ((a.Cp / 2 + 7) / 8) * 8; h_begin = 0; h_end = 1; c_begin = wg == 0 ? 0 : half; c_end = wg == 0 ? half : a.Cp; }
+        const int h_begin = a.Hg >= 2 ? (wg == 0 ? 0 : a.Hg / 2) : 0;
+        const int h_end = a.Hg >= 2 ? (wg == 0 ? a.Hg / 2 : a.Hg) : 1;
         const uint32_t b3_s = smem_u32(b3s);
-        const int n32 = (c_end - c_begin) / 32;
+        const uint32_t xs_row = smem_u32(Xs) + (uint32_t)row * (kPsXPitch * 4);
+        int slot = 0;
+        uint32_t lap = 0;
         for (int i = 0; i < n_units; ++i) {
             const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
             const int b = i & 1;
@@ -360,38 +431,47 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             const int emit_slot = __ldg(a.emit_idx + s);
             const int64_t b0 = (int64_t)u.t * kTcM;
             const bool row_ok = b0 + row < a.B;
-            const float* dxrow = a.dx0 + (size_t)u.q * a.dx_stride + (size_t)(b0 + row) * a.Cp;
             ps_wait(mma_bar + b, (uint32_t)(i >> 1) & 1u);
+            if (tid == 0) ps_trace(a, u.t, g, u.q, 2);
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)((warp & 3) * 32) << 16);
-            for (int hl = h_begin; hl < h_end; ++hl) {
-                float acc = 0.f;
+            // my chunks of the unit's sequence: Hg >= 2 -> every chunk of my own hidden rows; Hg == 1 -> the chunks of my parity
+            PsHalf HA, HB;
+            {   // pre-issue the first half of my first chunk
+                const int j0 = a.Hg >= 2 ? 0 : wg;
+                if (h_begin < h_end && j0 < xq.nch) ps_half_issue(HA, lane_addr + (uint32_t)(h_begin * a.Cp + 32 * j0));
+            }
+            for (int p = 0; p < xq.n_pass; ++p) {
+                const int hl = h_begin + p;
+                const bool pass_ok = hl < h_end;
                 const int colbase = hl * a.Cp;
-#define PS_ISSUE32(k, j) ps_chunk_issue<32>(k, lane_addr + (uint32_t)(colbase + c_begin + 32 * (j)), b3_s + 4u * (colbase + c_begin + 32 * (j)), \
-                                            dxrow + c_begin + 32 * (j), row_ok)
-                {
-                    PsChunk<32> A, Bk;
-                    if (n32 > 0) PS_ISSUE32(A, 0);
-                    for (int j = 0; j < n32; j += 2) {
-                        tmem_wait_ld<32>(A.r);
-                        if (j + 1 < n32) PS_ISSUE32(Bk, j + 1);
-                        acc += ps_fwd_finish<32, EXACT>(A);
-                        if (j + 1 < n32) {
-                            tmem_wait_ld<32>(Bk.r);
-                            if (j + 2 < n32) PS_ISSUE32(A, j + 2);
-                            acc += ps_fwd_finish<32, EXACT>(Bk);
+                float acc = 0.f;
+                for (int j = 0; j < xq.nch; ++j) {
+                    ps_wait(x_full + slot, lap & 1u);
+                    const bool mine = pass_ok && (a.Hg >= 2 || (j & 1) == wg);
+                    if (mine) {
+                        const int c = 32 * j;
+                        const int nv0 = min(16, a.Cp - c), nv1 = max(0, min(16, a.Cp - c - 16));
+                        const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlot;
+                        tmem_wait_ld<16>(HA.r);
+                        if (nv1 > 0) ps_half_issue(HB, lane_addr + (uint32_t)(colbase + c + 16));
+                        acc += ps_fwd_half<EXACT>(HA, nv0, b3_s + 4u * (colbase + c), xs);
+                        tmem_wait_ld<16>(HB.r);
+                        {   // first half of my next chunk in this unit
+                            int pn = p, jn = j + (a.Hg >= 2 ? 1 : 2);
+                            if (jn >= xq.nch) { pn = p + 1; jn = a.Hg >= 2 ? 0 : wg; }
+                            if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch)
+                                ps_half_issue(HA, lane_addr + (uint32_t)((h_begin + pn) * a.Cp + 32 * jn));
                         }
+                        acc += ps_fwd_half<EXACT>(HB, nv1, b3_s + 4u * (colbase + c + 16), xs + 64u);
                     }
-                }
-                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
-                    PsChunk<8> T;
-                    ps_chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dxrow + c0, row_ok);
-                    tmem_wait_ld<8>(T.r);
-                    acc += ps_fwd_finish<8, EXACT>(T);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_free + slot);
+                    if (++slot == NX) { slot = 0; ++lap; }
                 }
                 if (a.Hg >= 2) {
                     const int h = g * a.Hg + hl;
-                    if (h < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, h, b0 + row, acc);
+                    if (pass_ok && h < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, h, b0 + row, acc);
                 } else {
                     if (wg == 0) partial[row] = acc;
                     named_bar_sync(1, kPsEpi);
@@ -401,6 +481,7 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             }
             tc_fence_before();
             __syncwarp();
+            if (tid == 0) ps_trace(a, u.t, g, u.q, 3);
             if (lane == 0) mbar_arrive(done + b);
         }
     }
@@ -411,13 +492,15 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward, hidden role: z_q tile -> hidden layers -> input of the final layer; every layer input is kept as a record
+// forward, hidden role: z_q tile -> hidden layers -> input of the final layer; every layer input is kept as a record.
+// ONE operand buffer: the epilogue of layer l overwrites the tile MMA l has finished reading with the input of layer l+1.
 // ---------------------------------------------------------------------------------------------------------------
 template <int NSP>
 __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int j) {
     bool resident;
-    const int NW = ps_hid_nw(NSP, a.F, &resident);
-    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW);
+    const int n_op = ps_hid_fwd_nop(NSP, a.F);
+    const int NW = ps_hid_nw(NSP, a.F, &resident, n_op);
+    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW, n_op);
     constexpr uint32_t kOp = (uint32_t)NSP * kTcHidTile;     // one operand (all parts)
     uint8_t* Wt = smem + L.Wt;
     uint8_t* At = smem + L.At;
@@ -426,8 +509,7 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     uint64_t* w_full = bars;          // [NW <= 8]
     uint64_t* a_full = bars + 8;
     uint64_t* mma_bar = bars + 9;
-    uint64_t* a_ready = bars + 10;    // epilogue -> producer: operand tile of the next layer written (8 warp arrivals)
-    uint64_t* out_done = bars + 11;   // epilogue -> producer: final-layer input written to global memory (8 warp arrivals)
+    uint64_t* a_ready = bars + 10;    // epilogue -> producer: output of the layer written over the operand tile (8 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -439,7 +521,7 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     if (warp == 0) tmem_alloc(tmem_slot, 128);
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(w_full + i, 1);
-        mbar_init(a_full, 1); mbar_init(mma_bar, 1); mbar_init(a_ready, 8); mbar_init(out_done, 8);
+        mbar_init(a_full, 1); mbar_init(mma_bar, 1); mbar_init(a_ready, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < F * 128; i += kPsThreads) bias_s[i] = a.bias_h[i];
@@ -458,6 +540,14 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
                 }
             };
+            auto store_A = [&](int l, int b0, int rec) {   // the operand tile = input of layer l -> its record
+                const uint8_t* src = At + (size_t)((l & 1) % n_op) * kOp;
+                for (int p = 0; p < NSP; ++p) {
+                    tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile, 0, b0, p, rec);
+                    tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, rec);
+                }
+                bulk_commit();
+            };
             tma_prefetch_desc(&maps.act[0]);
             if (resident) { for (int l = 0; l < F; ++l) load_W(l, l); }
             else { for (int w = 0; w < NW && w < F; ++w) load_W(w, w); }     // uses 0 .. NW-1 of the first unit
@@ -467,36 +557,31 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 const int b0 = t * kTcM;
                 const int rec = a.need_grad ? q : 0;
                 if (q > 0) ps_spin_ge(a.cnt_f + t, a.n_hg * q);      // every h-group wrote its columns of the stage input
+                ps_trace(a, t, 0, q, 5);
                 fence_proxy_async_all();
-                bulk_wait_read<0>();                                  // no store of the previous unit still reads At[0]
+                bulk_wait_read<0>();      // no record store of the previous unit still reads the first tile
                 mbar_expect_tx(a_full, kOp);
                 for (int p = 0; p < NSP; ++p) {
                     tma_load_4d(At + (size_t)p * kTcHidTile, &maps.act[0], a_full, 0, b0, p, rec);
                     tma_load_4d(At + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[0], a_full, 64, b0, p, rec);
                 }
                 for (int l = 0; l < F; ++l, ++use) {
-                    uint8_t* a_tile = At + (size_t)(l & 1) * kOp;
-                    if (l == 0) ps_wait(a_full, (uint32_t)i & 1u);
+                    if (l == 0) { ps_wait(a_full, (uint32_t)i & 1u); ps_trace(a, t, 0, q, 6); }
                     else {
-                        ps_wait(a_ready, (uint32_t)(i * (F - 1) + l - 1) & 1u);
-                        if (a.need_grad) {
-                            for (int p = 0; p < NSP; ++p) {
-                                tma_store_4d(&maps.act[l], a_tile + (size_t)p * kTcHidTile, 0, b0, p, rec);
-                                tma_store_4d(&maps.act[l], a_tile + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, rec);
-                            }
-                            bulk_commit();
-                        }
+                        ps_wait(a_ready, (uint32_t)(i * F + l - 1) & 1u);
+                        if (a.need_grad) store_A(l, b0, rec);
                     }
                     const int buf = resident ? l : use % NW;
                     if (resident) { if (i == 0) ps_wait(w_full + buf, 0); }
                     else ps_wait(w_full + buf, (uint32_t)(use / NW) & 1u);
                     tc_fence_after();
-                    ps_gemm_kmajor<NSP>(tmem_base, smem_u32(a_tile), kTcHidTile, kTcM, smem_u32(Wt + (size_t)buf * kOp), kTcHidTile, 128, 128);
-                    // the epilogue of this layer overwrites the tile the previous store read from
-                    bulk_wait_read<1>();
+                    ps_gemm_kmajor<NSP>(tmem_base, smem_u32(At + (size_t)((l & 1) % n_op) * kOp), kTcHidTile, kTcM,
+                                        smem_u32(Wt + (size_t)buf * kOp), kTcHidTile, 128, 128);
+                    // the epilogue of this layer writes tile (l+1)&1: one buffer -> the record store just issued reads it; two buffers ->
+                    // the store of the previous layer does
+                    if (n_op == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
                     umma_commit(mma_bar);
                     if (!resident) {
-                        // next use of this buffer: layer use + NW (the layer sequence is periodic with period F)
                         const int64_t total_uses = (int64_t)n_units * F;
                         if ((int64_t)use + NW < total_uses) {
                             ps_wait(mma_bar, (uint32_t)use & 1u);     // the MMAs that read the buffer have completed
@@ -504,11 +589,14 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                         }
                     }
                 }
-                ps_wait(out_done, (uint32_t)i & 1u);
-                __threadfence();
+                ps_wait(a_ready, (uint32_t)(i * F + F - 1) & 1u);     // input of the final layer written
+                store_A(F, b0, rec);
+                bulk_wait<0>();                                        // ... and complete in global memory
+                ps_trace(a, t, 0, q, 11);
+                fence_proxy_async_all();
                 st_release_gpu(a.flag_h + t, q + 1);
+                ps_trace(a, t, 0, q, 12);
             }
-            bulk_wait<0>();
         }
     } else if (warp < 8) {
         const int wg = warp >> 2;
@@ -517,16 +605,12 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
         int use = 0;
         for (int i = 0; i < n_units; ++i) {
             const int q = i / n_my, t = j + (i - q * n_my) * a.n_hid;
-            const int64_t b = (int64_t)t * kTcM + row;
-            const bool row_ok = b < a.B;
-            const int rec = a.need_grad ? q : 0;
             for (int l = 0; l < F; ++l, ++use) {
                 ps_wait(mma_bar, (uint32_t)use & 1u);
+                if (tid == 0) ps_trace(a, t, 0, q, 7 + 2 * (l > 0));
                 tc_fence_after();
-                const bool last = l == F - 1;
-                const uint32_t dst = smem_u32(At + (size_t)((l + 1) & 1) * kOp);
-                __nv_bfloat16* gdst = a.rec0 + (size_t)rec * a.rec_stride + a.act_off[F] + (size_t)b * 128;
                 const uint32_t bias_a = smem_u32(bias_s + l * 128);
+                const uint32_t dst = smem_u32(At + (size_t)(((l + 1) & 1) % n_op) * kOp);
                 const int act = a.act[l];
 #pragma unroll
                 for (int c0 = wg * 64; c0 < wg * 64 + 64; c0 += 32) {
@@ -551,28 +635,17 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                             if (NSP == 2) split_bf16x2(v[2 * jj], v[2 * jj + 1], hi[jj], lo[jj]);
                             else hi[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
                         }
-                        if (!last) {
-                            const uint32_t o = sw128_off(row, (c0 >> 3) + j8, kTcM);
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                            if (NSP == 2)
-                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kTcHidTile + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-                        } else if (row_ok) {
-                            *reinterpret_cast<uint4*>(gdst + c0 + j8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            if (NSP == 2)
-                                *reinterpret_cast<uint4*>(gdst + (size_t)a.Bp * 128 + c0 + j8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        }
+                        const uint32_t o = sw128_off(row, (c0 >> 3) + j8, kTcM);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                        if (NSP == 2)
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kTcHidTile + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                     }
                 }
                 tc_fence_before();
-                if (!last) {
-                    fence_async_smem();     // generic-proxy writes before the async-proxy MMA / TMA store
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready);
-                } else {
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(out_done);
-                }
+                if (tid == 0) ps_trace(a, t, 0, q, 8 + 2 * (l > 0));
+                fence_async_smem();     // generic-proxy writes before the async-proxy MMA / TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
             }
         }
     }
@@ -582,10 +655,11 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-static inline size_t ps_fwd_smem_bytes(int Npad, int NSP, int NA, int F) {
+static inline size_t ps_fwd_smem_bytes(int Npad, int NSP, int NA, int F, int NX) {
     bool res;
-    const int NW = ps_hid_nw(NSP, F, &res);
-    const size_t f = ps_field_fwd_layout(Npad, NSP, NA).total, h = ps_hid_fwd_layout(NSP, NW).total;
+    const int n_op = ps_hid_fwd_nop(NSP, F);
+    const int NW = ps_hid_nw(NSP, F, &res, n_op);
+    const size_t f = ps_field_fwd_layout(Npad, NSP, NA, NX).total, h = ps_hid_fwd_layout(NSP, NW, n_op).total;
     return 1024 + (f > h ? f : h);
 }
 
@@ -602,38 +676,40 @@ __global__ void __launch_bounds__(kPsThreads, 1) persist_fwd_kernel(const __grid
 // ===============================================================================================================
 // backward pass
 // ===============================================================================================================
-// One W-column chunk of epilogue 1 for TMEM lane `row` (after tmem_wait_ld): G = gk * dX * sech^2(pre + b3) -> bf16 (hi, lo) into the
-// swizzled G tile(s) (16-byte stores, n0 is a multiple of 8).
-template <int W, int NSP, bool EXACT>
-__device__ __forceinline__ void ps_bwd_finish(const PsChunk<W>& k, float gk, uint32_t gs_s, uint32_t g_part_bytes, int row, int n0) {
-    float v[W];
+// The first nv (0, 8 or 16) columns of a half-chunk of epilogue 1 for TMEM lane `row`: G = gk * dX * sech^2(pre + b3) -> bf16 (hi, lo)
+// into the swizzled G tile(s) (16-byte stores, n0 is a multiple of 8).
+template <int NSP, bool EXACT>
+__device__ __forceinline__ void ps_bwd_half(const PsHalf& k, int nv, float gk, uint32_t b3_s, uint32_t x_s, uint32_t gs_s, uint32_t g_part_bytes,
+                                            int row, int n0) {
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-        const float4 bb = lds128(k.b3_s + 16u * q);
-        const float4 dd = k.dd[q];
-        // gk is zero for padded rows and their dX/dt loads are predicated to zero: no NaN can enter the G tile
-        v[4 * q + 0] = gk * dd.x * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 0]) + bb.x);
-        v[4 * q + 1] = gk * dd.y * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 1]) + bb.y);
-        v[4 * q + 2] = gk * dd.z * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 2]) + bb.z);
-        v[4 * q + 3] = gk * dd.w * ps_sech2<EXACT>(__uint_as_float(k.r[4 * q + 3]) + bb.w);
-    }
+    for (int j8 = 0; j8 < 2; ++j8) {
+        if (8 * j8 < nv) {
+            float v[8];
 #pragma unroll
-    for (int j8 = 0; j8 < W / 8; ++j8) {
-        uint32_t hi[4], lo[4];
+            for (int q = 0; q < 2; ++q) {
+                const float4 bb = lds128(b3_s + 32u * j8 + 16u * q), dd = lds128(x_s + 32u * j8 + 16u * q);
+                // gk is zero for padded rows and dX/dt rows beyond the batch are zero-filled by TMA: no NaN can enter the G tile
+                v[4 * q + 0] = gk * dd.x * ps_sech2<EXACT>(__uint_as_float(k.r[8 * j8 + 4 * q + 0]) + bb.x);
+                v[4 * q + 1] = gk * dd.y * ps_sech2<EXACT>(__uint_as_float(k.r[8 * j8 + 4 * q + 1]) + bb.y);
+                v[4 * q + 2] = gk * dd.z * ps_sech2<EXACT>(__uint_as_float(k.r[8 * j8 + 4 * q + 2]) + bb.z);
+                v[4 * q + 3] = gk * dd.w * ps_sech2<EXACT>(__uint_as_float(k.r[8 * j8 + 4 * q + 3]) + bb.w);
+            }
+            uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (NSP == 2) split_bf16x2(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1], hi[j], lo[j]);
-            else hi[j] = pack_bf16x2(v[j8 * 8 + 2 * j], v[j8 * 8 + 2 * j + 1]);
+            for (int j = 0; j < 4; ++j) {
+                if (NSP == 2) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                else hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+            const uint32_t o = sw128_off(row, (n0 >> 3) + j8, kTcM);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            if (NSP == 2)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + g_part_bytes + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
-        const uint32_t o = sw128_off(row, (n0 >> 3) + j8, kTcM);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + o), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-        if (NSP == 2)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(gs_s + g_part_bytes + o), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
     }
 }
 
-struct PsFieldBwdSmem { uint32_t Ws, As, Gs, b3s, bsum, bars, g_part, total; };
-__host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP) {
+struct PsFieldBwdSmem { uint32_t Ws, As, Gs, Xs, b3s, bsum, bars, g_part, total; };
+__host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP, int NX) {
     PsFieldBwdSmem L;
     const uint32_t NP64 = ((uint32_t)Npad + 63u) & ~63u;
     uint32_t o = 0;
@@ -642,10 +718,11 @@ __host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP)
     L.As = o; o += (uint32_t)NSP * kTcHidTile;
     L.g_part = kTcM * NP64 * 2;
     L.Gs = o; o += (uint32_t)NSP * L.g_part;
+    L.Xs = o; o += (uint32_t)NX * kPsXSlot;
     L.b3s = o; o += (uint32_t)Npad * 4;
     L.bsum = o; o += 8u * (uint32_t)Npad * 4;
     o = (o + 15u) & ~15u;
-    L.bars = o; o += 24 * 8;
+    L.bars = o; o += 40 * 8;
     L.total = o;
     return L;
 }
@@ -667,12 +744,13 @@ template <int NSP>
 __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int g, int part) {
     constexpr bool EXACT = NSP == 2;
     constexpr int EW = 8, kCg = 2, KP = kTcKP;
-    const int Npad = a.Npad;
-    const PsFieldBwdSmem L = ps_field_bwd_layout(Npad, NSP);
+    const int Npad = a.Npad, NX = a.NX;
+    const PsFieldBwdSmem L = ps_field_bwd_layout(Npad, NSP, NX);
     const uint32_t w_part = (uint32_t)Npad * 256u;
     uint8_t* Ws = smem + L.Ws;
     uint8_t* As = smem + L.As;
     uint8_t* Gs = smem + L.Gs;
+    uint8_t* Xs = smem + L.Xs;
     float* b3s = reinterpret_cast<float*>(smem + L.b3s);
     float* bsum = reinterpret_cast<float*>(smem + L.bsum);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -687,6 +765,9 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* w_bar = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     volatile int* sig_done = reinterpret_cast<volatile int*>(bars + 10);
+    uint64_t* x_full = bars + 12;     // [NX <= 8]
+    uint64_t* x_free = bars + 20;     // [NX <= 8]
+    const PsXSeq xq = ps_xseq(a.Hg, a.Cp);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
@@ -697,6 +778,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     if (tid == 0) {
         mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(dep_bar, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, EW);
         mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
+        for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
         *sig_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -725,8 +807,6 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
                     tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
                 }
-                const int rows = min(kTcM, a.B - u.t * kTcM);
-                l2_prefetch_bulk(a.dx0 + (size_t)u.q * a.dx_stride + (size_t)u.t * kTcM * a.Cp, (uint32_t)rows * a.Cp * 4u);
             };
             load_A(0);
             ps_wait(w_bar, 0);
@@ -735,12 +815,14 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);
+                ps_trace(a, u.t, g, n_q - 1 - u.q, 1);
                 if (i > 0) ps_wait(done2, ph ^ 1u);             // epilogue 2 of the previous unit has read P out of the accumulator
                 tc_fence_after();
                 ps_gemm_kmajor<NSP>(tmem_base, As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
                 umma_commit(pre_bar);
                 // the gradients this unit's gk is formed from: the hidden CTA has finished every later stage of the tile
                 ps_spin_ge(a.flag_h + u.t, n_q - 1 - u.q);
+                ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
                 mbar_arrive(dep_bar);
                 ps_wait(g_ready, ph);                            // G tile written by all 8 warps
                 tc_fence_after();
@@ -783,19 +865,36 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 ps_wait(done2, (uint32_t)i & 1u);
-                __threadfence();
                 red_release_gpu_add(a.cnt_f + u.t, 1);
+                ps_trace(a, u.t, g, n_q - 1 - u.q, 6);
                 *sig_done = i + 1;
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.X);
+            int slot = 0;
+            uint32_t lap = 0;          // completed laps of the ring
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                for (int p = 0; p < xq.n_pass; ++p)
+                    for (int j = 0; j < xq.nch; ++j) {
+                        if (lap > 0) ps_wait(x_free + slot, (lap - 1) & 1u);
+                        mbar_expect_tx(x_full + slot, kPsXSlot);
+                        tma_load_3d(Xs + (size_t)slot * kPsXSlot, &maps.X, x_full + slot, 32 * j, u.t * kTcM, u.q);
+                        if (++slot == NX) { slot = 0; ++lap; }
+                    }
             }
         }
     } else {
         const int cg = warp >> 2;                    // column group
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int P = a.Hg >= kCg ? 1 : kCg / a.Hg;
-        const int U = a.Hg * P;
-        const int u_begin = cg * U / kCg, u_end = (cg + 1) * U / kCg;
-        const int cw = (((a.Cp + P - 1) / P) + 7) & ~7;
+        const int h_begin = a.Hg >= 2 ? (cg == 0 ? 0 : a.Hg / 2) : 0;
+        const int h_end = a.Hg >= 2 ? (cg == 0 ? a.Hg / 2 : a.Hg) : 1;
+        const uint32_t xs_row = smem_u32(Xs) + (uint32_t)row * (kPsXPitch * 4);
+        int slot = 0;
+        uint32_t lap = 0;
         const int col_begin = (cg * Npad / kCg) & ~15;
         const int col_end = cg == kCg - 1 ? Npad : (((cg + 1) * Npad / kCg) & ~15);
         const int n_chunk8 = Npad >> 3;                     // <= 30
@@ -813,18 +912,24 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             const int64_t b0 = (int64_t)un.t * kTcM;
             const int64_t b = b0 + row;
             const bool row_ok = b < a.B;
-            const float* dxrow = a.dx0 + (size_t)un.q * a.dx_stride + (size_t)b * a.Cp;
             float* gy_new = a.yT[s & 1];
             const float* gy_old = a.yT[(s + 1) & 1];
             ps_wait(dep_bar, ph);
             ps_wait(pre_bar, ph);
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 2);
             tc_fence_after();
             // ---- epilogue 1 ----
-            for (int u = u_begin; u < u_end; ++u) {
-                const int hl = u / P, c_begin = (u % P) * cw, c_end = min(a.Cp, c_begin + cw);
+            PsHalf HA, HB;
+            {
+                const int j0 = a.Hg >= 2 ? 0 : cg;
+                if (h_begin < h_end && j0 < xq.nch) ps_half_issue(HA, lane_addr + (uint32_t)(h_begin * a.Cp + 32 * j0));
+            }
+            for (int p = 0; p < xq.n_pass; ++p) {
+                const int hl = h_begin + p;
+                const bool pass_ok = hl < h_end;
                 const int h = g * a.Hg + hl;
                 float gk = 0.f;
-                if (row_ok && h < a.H) {
+                if (pass_ok && row_ok && h < a.H) {
                     const size_t off = (size_t)h * a.Bp + b;
                     if (ist == a.NS - 1) {
                         // first backward stage of step s: the gradient of the step's end state = the one carried over from step s+1
@@ -854,33 +959,34 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     }
                 }
                 const int colbase = hl * a.Cp;
-                const int n32 = (c_end - c_begin) / 32;
-#define PS_ISSUE32B(k, j) ps_chunk_issue<32>(k, lane_addr + (uint32_t)(colbase + c_begin + 32 * (j)), b3_s + 4u * (colbase + c_begin + 32 * (j)), \
-                                             dxrow + c_begin + 32 * (j), row_ok)
-                {
-                    PsChunk<32> A, Bk;
-                    if (n32 > 0) PS_ISSUE32B(A, 0);
-                    for (int j = 0; j < n32; j += 2) {
-                        tmem_wait_ld<32>(A.r);
-                        if (j + 1 < n32) PS_ISSUE32B(Bk, j + 1);
-                        ps_bwd_finish<32, NSP, EXACT>(A, gk, gs_s, L.g_part, row, colbase + c_begin + 32 * j);
-                        if (j + 1 < n32) {
-                            tmem_wait_ld<32>(Bk.r);
-                            if (j + 2 < n32) PS_ISSUE32B(A, j + 2);
-                            ps_bwd_finish<32, NSP, EXACT>(Bk, gk, gs_s, L.g_part, row, colbase + c_begin + 32 * (j + 1));
+                for (int j = 0; j < xq.nch; ++j) {
+                    ps_wait(x_full + slot, lap & 1u);
+                    const bool mine = pass_ok && (a.Hg >= 2 || (j & 1) == cg);
+                    if (mine) {
+                        const int c = 32 * j;
+                        const int nv0 = min(16, a.Cp - c), nv1 = max(0, min(16, a.Cp - c - 16));
+                        const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlot;
+                        tmem_wait_ld<16>(HA.r);
+                        if (nv1 > 0) ps_half_issue(HB, lane_addr + (uint32_t)(colbase + c + 16));
+                        ps_bwd_half<NSP, EXACT>(HA, nv0, gk, b3_s + 4u * (colbase + c), xs, gs_s, L.g_part, row, colbase + c);
+                        tmem_wait_ld<16>(HB.r);
+                        {
+                            int pn = p, jn = j + (a.Hg >= 2 ? 1 : 2);
+                            if (jn >= xq.nch) { pn = p + 1; jn = a.Hg >= 2 ? 0 : cg; }
+                            if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch)
+                                ps_half_issue(HA, lane_addr + (uint32_t)((h_begin + pn) * a.Cp + 32 * jn));
                         }
+                        ps_bwd_half<NSP, EXACT>(HB, nv1, gk, b3_s + 4u * (colbase + c + 16), xs + 64u, gs_s, L.g_part, row, colbase + c + 16);
                     }
-                }
-                for (int c0 = c_begin + 32 * n32; c0 + 8 <= c_end; c0 += 8) {
-                    PsChunk<8> T;
-                    ps_chunk_issue<8>(T, lane_addr + (uint32_t)(colbase + c0), b3_s + 4u * (colbase + c0), dxrow + c0, row_ok);
-                    tmem_wait_ld<8>(T.r);
-                    ps_bwd_finish<8, NSP, EXACT>(T, gk, gs_s, L.g_part, row, colbase + c0);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_free + slot);
+                    if (++slot == NX) { slot = 0; ++lap; }
                 }
             }
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 3);
             if (lane == 0) mbar_arrive(g_ready);
             // bias gradient from the G tile while the tensor core works: every warp needs ALL rows -> epilogue-wide barrier
             named_bar_sync(1, kPsEpi);
@@ -901,6 +1007,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 }
             }
             ps_wait(dg_bar, ph);
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 4);
             tc_fence_after();
             // ---- epilogue 2: this h-group's share of dL/d(final-layer input), summed over the groups in L2 ----
             {
@@ -922,6 +1029,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             }
             tc_fence_before();
             __syncwarp();
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 5);
             if (lane == 0) mbar_arrive(done2);
         }
         // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [part][g*Npad + n][k];  bias gradient ----
@@ -960,8 +1068,8 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
 template <int NSP>
 __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem, int j) {
     bool resident;
-    const int NW = ps_hid_nw(NSP, a.F, &resident);
-    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW);
+    const int NW = ps_hid_nw(NSP, a.F, &resident, 2);
+    const PsHidFwdSmem L = ps_hid_fwd_layout(NSP, NW, 2);
     constexpr uint32_t kOp = (uint32_t)NSP * kTcHidTile;
     uint8_t* Wt = smem + L.Wt;
     uint8_t* Dt = smem + L.At;
@@ -1009,6 +1117,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 const int qi = i / n_my, q = n_q - 1 - qi, t = j + (i - qi * n_my) * a.n_hid;
                 const int b0 = t * kTcM;
                 ps_spin_ge(a.cnt_f + t, a.n_hg * (qi + 1));          // every h-group has added its partial of stage q
+                ps_trace(a, t, 0, qi, 7);
                 mbar_arrive(top_bar);
                 for (int l = F - 1, n = 0; l >= 0; --l, ++n, ++use) {
                     const int bf = l & 1;
@@ -1050,8 +1159,8 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 }
                 ps_wait(out_done, (uint32_t)i & 1u);
                 bulk_wait_read<0>();     // the next unit's top tile overwrites a buffer the last store may still read
-                __threadfence();
                 st_release_gpu(a.flag_h + t, qi + 1);
+                ps_trace(a, t, 0, qi, 13);
             }
             bulk_wait<0>();
         }
@@ -1104,10 +1213,12 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 }
                 fence_async_smem();
                 __syncwarp();
+                if (tid == 0) ps_trace(a, t, 0, qi, 8);
                 if (lane == 0) mbar_arrive(dp_ready);
             }
             for (int l = F - 1; l >= 0; --l, ++use) {
                 ps_wait(dg_bar, (uint32_t)use & 1u);
+                if (tid == 0) ps_trace(a, t, 0, qi, l == 0 ? 11 : 9);
                 tc_fence_after();
                 if (l > 0) {
                     const __nv_bfloat16* arow = recq + a.act_off[l] + (size_t)b * 128;
@@ -1148,6 +1259,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
+                    if (tid == 0) ps_trace(a, t, 0, qi, 10);
                     if (lane == 0) mbar_arrive(dp_ready);
                 } else {
                     // dz of stage `ist`, feature-major fp32: plain stores, coalesced over the lanes (= rows)
@@ -1164,7 +1276,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                         }
                     }
                     tc_fence_before();
-                    __threadfence();
+                    if (tid == 0) ps_trace(a, t, 0, qi, 12);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(out_done);
                 }
@@ -1177,10 +1289,10 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-static inline size_t ps_bwd_smem_bytes(int Npad, int NSP, int F) {
+static inline size_t ps_bwd_smem_bytes(int Npad, int NSP, int F, int NX) {
     bool res;
-    const int NW = ps_hid_nw(NSP, F, &res);
-    const size_t f = ps_field_bwd_layout(Npad, NSP).total, h = ps_hid_fwd_layout(NSP, NW).total;
+    const int NW = ps_hid_nw(NSP, F, &res, 2);
+    const size_t f = ps_field_bwd_layout(Npad, NSP, NX).total, h = ps_hid_fwd_layout(NSP, NW, 2).total;
     return 1024 + (f > h ? f : h);
 }
 

@@ -275,8 +275,8 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
                 if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
                 if (pl->ns == 2) {
                     // bf16x3 runs on the persistent kernels only: the pass at hand decides (weights are re-packed per pass)
-                    if (for_bwd ? ps_bwd_smem_bytes(npad, 2, m.n_layers - 1) > kSmemLimit
-                                : ps_fwd_smem_bytes(npad, 2, 1, m.n_layers - 1) > kSmemLimit) continue;
+                    if (for_bwd ? ps_bwd_smem_bytes(npad, 2, m.n_layers - 1, 2) > kSmemLimit
+                                : ps_fwd_smem_bytes(npad, 2, 1, m.n_layers - 1, 2) > kSmemLimit) continue;
                 } else {
                     if (tc_bwd_smem_bytes(npad, pl->CpB, pl->bwd_ew) > kSmemLimit) continue;
                     if (tc_fwd_smem_bytes(npad, pl->CpB) > kSmemLimit) continue;
@@ -665,7 +665,7 @@ static inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-struct PsPlan { int n_mt, n_part, n_field, n_hid, NA; size_t smem; };
+struct PsPlan { int n_mt, n_part, n_field, n_hid, NA, NX; size_t smem; };
 
 static int device_sm_count() {
     static int sms = 0;
@@ -699,11 +699,21 @@ static bool ps_eligible(const ncde_problem_t* p, const Plan& pl, bool bwd, PsPla
     pp->n_part = (sms - pp->n_hid) / pl.n_hg;
     if (pp->n_part > pp->n_mt) pp->n_part = pp->n_mt;
     pp->n_field = pp->n_part * pl.n_hg;
+    // shared memory: operand tiles first, then as many dX/dt chunk slots as fit (at least 2; more = the loader runs further ahead)
     pp->NA = 1;
-    if (bwd) pp->smem = ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F);
-    else {
-        pp->NA = ps_fwd_smem_bytes(pl.Npad, pl.ns, 2, pl.F) <= kSmemLimit ? 2 : 1;
-        pp->smem = ps_fwd_smem_bytes(pl.Npad, pl.ns, pp->NA, pl.F);
+    const int nch = (pl.Cp + 31) / 32;
+    const int want = 2 * nch < kPsMaxSlots ? 2 * nch : kPsMaxSlots;     // two whole tiles' worth is as far ahead as it is useful to run
+    if (bwd) {
+        pp->NX = 2;
+        while (pp->NX < want && ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX + 1) <= kSmemLimit) ++pp->NX;
+        pp->smem = ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX);
+    } else {
+        pp->NX = 2;
+        const int need = nch < kPsMaxSlots ? nch : kPsMaxSlots;        // one tile's worth of slots before a second activation buffer
+        while (pp->NX < need && ps_fwd_smem_bytes(pl.Npad, pl.ns, 1, pl.F, pp->NX + 1) <= kSmemLimit) ++pp->NX;
+        if (ps_fwd_smem_bytes(pl.Npad, pl.ns, 2, pl.F, pp->NX) <= kSmemLimit) pp->NA = 2;
+        while (pp->NX < want && ps_fwd_smem_bytes(pl.Npad, pl.ns, pp->NA, pl.F, pp->NX + 1) <= kSmemLimit) ++pp->NX;
+        pp->smem = ps_fwd_smem_bytes(pl.Npad, pl.ns, pp->NA, pl.F, pp->NX);
     }
     return pp->smem <= kSmemLimit && (int64_t)p->grid.n_steps * pl.n_stages * pp->n_mt < (1ll << 30);
 }
@@ -731,7 +741,7 @@ static int ps_pack(const ncde_problem_t* p, const Plan& pl, float* wpack, cudaSt
 
 // descriptors: packed weights, the bf16 activation records (rec0 = first record, stride in floats), dpre records (backward)
 static int ps_build_maps(const Plan& pl, const float* wpack, PsMaps* pm, const float* rec0, size_t rec_stride_floats, int64_t n_rec,
-                         const float* dpre0) {
+                         const float* dpre0, const float* dx0, size_t dx_stride_floats, int64_t n_dx) {
     memset(pm, 0, sizeof(*pm));
     int rc = make_map(&pm->W3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_W3T, 128, (uint64_t)pl.Np, (uint64_t)pl.ns, 256,
                       (uint64_t)pl.Np * 256, 64, (uint32_t)pl.Npad, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -739,6 +749,9 @@ static int ps_build_maps(const Plan& pl, const float* wpack, PsMaps* pm, const f
     for (int l = 0; l <= pl.F && rc == NCDE_OK; ++l)
         rc = make_map4(&pm->act[l], rec0 + pl.abl_off[l], (uint64_t)pl.B, (uint64_t)pl.ns, (uint64_t)n_rec, (uint64_t)pl.Bp * 256,
                        n_rec > 1 ? rec_stride_floats * 4 : 0, kTcM);
+    if (rc == NCDE_OK)   // dX/dt records, row-major [B][Cp] fp32; one box = 128 rows x (32 + 4) channels, rows / channels beyond the tensor read 0
+        rc = make_map(&pm->X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dx0, (uint64_t)pl.Cp, (uint64_t)pl.B, (uint64_t)(n_dx < 1 ? 1 : n_dx),
+                      (uint64_t)pl.Cp * 4, n_dx > 1 ? dx_stride_floats * 4 : 0, kPsXPitch, kTcM, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc == NCDE_OK && dpre0)
         rc = make_map4(&pm->dpre, dpre0, (uint64_t)pl.B, (uint64_t)pl.ns, (uint64_t)n_rec * pl.F, (uint64_t)pl.Bp * 256,
                        (uint64_t)pl.ns * pl.Bp * 256, kTcM);
@@ -749,7 +762,7 @@ static void ps_fill_args(PsArgs& a, const ncde_problem_t* p, const Plan& pl, con
     memset(&a, 0, sizeof(a));
     a.B = pl.B; a.Bp = pl.Bp; a.H = pl.H; a.Cp = pl.Cp; a.Hg = pl.Hg; a.n_hg = pl.n_hg; a.Npad = pl.Npad; a.F = pl.F;
     a.n_mt = pp.n_mt; a.n_part = pp.n_part; a.n_field = pp.n_field; a.n_hid = pp.n_hid;
-    a.NS = pl.n_stages; a.n_steps = (int)p->grid.n_steps; a.method = p->method; a.NA = pp.NA;
+    a.NS = pl.n_stages; a.n_steps = (int)p->grid.n_steps; a.method = p->method; a.NA = pp.NA; a.NX = pp.NX;
     for (int l = 0; l < pl.F; ++l) a.act[l] = p->mlp.act[l];
     a.b3 = wpack + pl.off_b3p;
     a.bias_h = wpack + pl.off_bh;
@@ -855,7 +868,10 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
 
     float* ps_ws = pl.tc_hid ? cv.take(ps_workspace_floats(pl, g.n_steps, false)) : nullptr;
     PsPlan pp;
-    const bool persist = ps_eligible(p, pl, false, &pp);
+    // the saved records of a persistent forward pass are read by the persistent backward pass only (dX/dt is kept feature-major):
+    // with gradients, both passes must qualify (bf16x3 has no other path and reports what is missing)
+    PsPlan pp_other;
+    const bool persist = ps_eligible(p, pl, false, &pp) && (!need_grad || pl.ns == 2 || ps_eligible(p, pl, true, &pp_other));
     NCDE_REQUIRE(persist || pl.ns == 1, NCDE_ERR_UNSUPPORTED,
                  "solve_fwd: precision bf16x3 needs hidden layers of width <= 128 and every output time on a grid point");
     rc = persist ? ps_pack(p, pl, wpack, st, &launches) : pack_weights(p, pl, wpack, 0, st, &launches);
@@ -940,7 +956,8 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
                                                                                          pl.Bp, pl.H, pl.ns);
         ++launches;
         PsMaps pm;
-        rc = ps_build_maps(pl, wpack, &pm, rec0p, pl.stage_floats, n_rec, nullptr);
+        rc = ps_build_maps(pl, wpack, &pm, rec0p, pl.stage_floats, n_rec, nullptr, need_grad ? (const float*)saved + pl.dx_off : dx_all,
+                           need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp, n_st_total);
         if (rc != NCDE_OK) return rc;
         PsArgs pa;
         ps_fill_args(pa, p, pl, pp, wpack);
@@ -953,6 +970,11 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         pa.dx0 = need_grad ? (const float*)saved + pl.dx_off : dx_all;
         pa.dx_stride = need_grad ? pl.stage_floats : (size_t)pl.Cp * pl.Bp;
         pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
+        static const bool trace_on = getenv("NCDE_PS_TRACE") != nullptr;   // debug: stamps of tile 0's hand-offs, dumped to stderr
+        if (trace_on) {
+            NCDE_CUDA_OK(cudaMalloc(&pa.trace, kPsTraceStages * 16 * 8));
+            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, kPsTraceStages * 16 * 8, st));
+        }
         const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
         {
             ProfScope ps(NCDE_PROF_SOLVE_FWD, st);
@@ -966,6 +988,18 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         }
         ++launches;
         NCDE_CUDA_OK(cudaGetLastError());
+        if (trace_on) {
+            std::vector<unsigned long long> h(kPsTraceStages * 16);
+            NCDE_CUDA_OK(cudaStreamSynchronize(st));
+            NCDE_CUDA_OK(cudaMemcpy(h.data(), pa.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(pa.trace);
+            const unsigned long long t0 = h[5];
+            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q) {
+                fprintf(stderr, "pstrace fwd q=%d", q);
+                for (int e = 0; e < 13; ++e) fprintf(stderr, " %lld", h[q * 16 + e] ? (long long)(h[q * 16 + e] - t0) : -1ll);
+                fprintf(stderr, "\n");
+            }
+        }
         if (launches_out) *launches_out = launches;
         return NCDE_OK;
     }
@@ -1168,7 +1202,8 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
 
     float* ps_ws = pl.tc_hid ? cv.take(ps_workspace_floats(pl, g.n_steps, true)) : nullptr;
     PsPlan pp;
-    const bool persist = !grad_coeffs && ps_eligible(p, pl, true, &pp);
+    PsPlan pp_other;
+    const bool persist = !grad_coeffs && ps_eligible(p, pl, true, &pp) && (pl.ns == 2 || ps_eligible(p, pl, false, &pp_other));
     NCDE_REQUIRE(persist || pl.ns == 1, NCDE_ERR_UNSUPPORTED,
                  "solve_bwd: precision bf16x3 needs hidden layers of width <= 128 and every output time on a grid point");
     if (persist) {
@@ -1194,7 +1229,8 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         rc = ps_pack(p, pl, wpack, st, &launches);
         if (rc != NCDE_OK) return rc;
         PsMaps pm;
-        rc = ps_build_maps(pl, wpack, &pm, (const float*)saved, pl.stage_floats, n_rec, dpre_rec);
+        rc = ps_build_maps(pl, wpack, &pm, (const float*)saved, pl.stage_floats, n_rec, dpre_rec, (const float*)saved + pl.dx_off,
+                           pl.stage_floats, n_rec);
         if (rc != NCDE_OK) return rc;
         PsArgs pa;
         ps_fill_args(pa, p, pl, pp, wpack);
@@ -1208,6 +1244,11 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         pa.dx_stride = pl.stage_floats;
         pa.dAT = dAT; pa.dW3acc = dW3acc; pa.db3acc = db3acc; pa.dpre0 = (__nv_bfloat16*)dpre_rec;
         pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
+        static const bool trace_on = getenv("NCDE_PS_TRACE") != nullptr;
+        if (trace_on) {
+            NCDE_CUDA_OK(cudaMalloc(&pa.trace, kPsTraceStages * 16 * 8));
+            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, kPsTraceStages * 16 * 8, st));
+        }
         const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
         {
             ProfScope ps(NCDE_PROF_SOLVE_BWD, st);
@@ -1220,6 +1261,18 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
             }
         }
         ++launches;
+        if (trace_on) {
+            std::vector<unsigned long long> h(kPsTraceStages * 16);
+            NCDE_CUDA_OK(cudaStreamSynchronize(st));
+            NCDE_CUDA_OK(cudaMemcpy(h.data(), pa.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(pa.trace);
+            const unsigned long long t0 = h[1];
+            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q) {
+                fprintf(stderr, "pstrace bwd q=%d", q);
+                for (int e = 0; e < 14; ++e) fprintf(stderr, " %lld", h[q * 16 + e] ? (long long)(h[q * 16 + e] - t0) : -1ll);
+                fprintf(stderr, "\n");
+            }
+        }
         ps_gy_final_kernel<<<(unsigned)ceil_div((int64_t)nHB, 256), 256, 0, st>>>(gyT, gkT[0], gkT[1], gkT[2], gkT[3], NS, (int64_t)nHB);
         ++launches;
         {
