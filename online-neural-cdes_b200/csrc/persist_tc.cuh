@@ -767,6 +767,11 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     volatile int* sig_done = reinterpret_cast<volatile int*>(bars + 10);
     uint64_t* x_full = bars + 12;     // [NX <= 8]
     uint64_t* x_free = bars + 20;     // [NX <= 8]
+    uint64_t* pre_bar2 = bars + 28;   // second recompute accumulator (Npad <= 128)
+    // TMEM columns.  Npad <= 128: two recompute accumulators (pre of unit i+1 is formed while the epilogues of unit i run) at 0 and
+    // 384, P at 128, dW^T at 256.  Wider h-groups: one accumulator at 0 that P re-uses, dW^T at 256.
+    const bool pre2 = Npad <= 128;
+    const uint32_t p_col = pre2 ? 128u : 0u;
     const PsXSeq xq = ps_xseq(a.Hg, a.Cp);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -776,7 +781,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(dep_bar, 1); mbar_init(pre_bar, 1); mbar_init(g_ready, EW);
+        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(dep_bar, 1); mbar_init(pre_bar, 1); mbar_init(pre_bar2, 1); mbar_init(g_ready, EW);
         mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
         for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
         *sig_done = 0;
@@ -816,15 +821,18 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);
                 ps_trace(a, u.t, g, n_q - 1 - u.q, 1);
-                if (i > 0) ps_wait(done2, ph ^ 1u);             // epilogue 2 of the previous unit has read P out of the accumulator
+                // one accumulator: epilogue 2 of the previous unit must have read P out of it; two: accumulator i & 1 was released by
+                // epilogue 1 of unit i-2 (g_ready of unit i-1 was awaited below, so that one is long complete)
+                if (!pre2 && i > 0) ps_wait(done2, ph ^ 1u);
                 tc_fence_after();
-                ps_gemm_kmajor<NSP>(tmem_base, As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
-                umma_commit(pre_bar);
+                ps_gemm_kmajor<NSP>(tmem_base + ((pre2 && (i & 1)) ? 384u : 0u), As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
+                umma_commit((pre2 && (i & 1)) ? pre_bar2 : pre_bar);
                 // the gradients this unit's gk is formed from: the hidden CTA has finished every later stage of the tile
                 ps_spin_ge(a.flag_h + u.t, n_q - 1 - u.q);
                 ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
                 mbar_arrive(dep_bar);
                 ps_wait(g_ready, ph);                            // G tile written by all 8 warps
+                if (pre2 && i > 0) ps_wait(done2, ph ^ 1u);      // P of the previous unit has been read out
                 tc_fence_after();
                 {   // dgrad: D[128 x KP] = G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows)
                     const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
@@ -833,7 +841,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         const uint32_t g_s = Gs_s + (pr == 1 ? L.g_part : 0u), w_s = Ws_s + (pr == 2 ? w_part : 0u);
                         for (int ks = 0; ks < Npad / 16; ++ks) {
                             const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                            umma_bf16(tmem_base, make_sdesc(g_s + a_off, 16, 1024), make_sdesc(w_s + (uint32_t)ks * 2048u, (uint32_t)Npad * 128u, 1024),
+                            umma_bf16(tmem_base + p_col, make_sdesc(g_s + a_off, 16, 1024), make_sdesc(w_s + (uint32_t)ks * 2048u, (uint32_t)Npad * 128u, 1024),
                                       idesc, first ? 0u : 1u);
                             first = false;
                         }
@@ -915,18 +923,12 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             float* gy_new = a.yT[s & 1];
             const float* gy_old = a.yT[(s + 1) & 1];
             ps_wait(dep_bar, ph);
-            ps_wait(pre_bar, ph);
-            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 2);
-            tc_fence_after();
-            // ---- epilogue 1 ----
-            PsHalf HA, HB;
-            {
-                const int j0 = a.Hg >= 2 ? 0 : cg;
-                if (h_begin < h_end && j0 < xq.nch) ps_half_issue(HA, lane_addr + (uint32_t)(h_begin * a.Cp + 32 * j0));
-            }
-            for (int p = 0; p < xq.n_pass; ++p) {
+            // dL/dk of this thread's (row, h) entries: formed as soon as the inputs are visible, before the recompute MMA is awaited
+            float gkv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
                 const int hl = h_begin + p;
-                const bool pass_ok = hl < h_end;
+                const bool pass_ok = p < xq.n_pass && hl < h_end;
                 const int h = g * a.Hg + hl;
                 float gk = 0.f;
                 if (pass_ok && row_ok && h < a.H) {
@@ -958,6 +960,24 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         }
                     }
                 }
+                gkv[p] = gk;
+            }
+            if (pre2) ps_wait((i & 1) ? pre_bar2 : pre_bar, (uint32_t)(i >> 1) & 1u);
+            else ps_wait(pre_bar, ph);
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 2);
+            tc_fence_after();
+            const uint32_t pre_addr = lane_addr + ((pre2 && (i & 1)) ? 384u : 0u);
+            // ---- epilogue 1 ----
+            PsHalf HA, HB;
+            {
+                const int j0 = a.Hg >= 2 ? 0 : cg;
+                if (h_begin < h_end && j0 < xq.nch) ps_half_issue(HA, pre_addr + (uint32_t)(h_begin * a.Cp + 32 * j0));
+            }
+            for (int p = 0; p < xq.n_pass; ++p) {
+                const int hl = h_begin + p;
+                const bool pass_ok = hl < h_end;
+                const int h = g * a.Hg + hl;
+                const float gk = p == 0 ? gkv[0] : (p == 1 ? gkv[1] : (p == 2 ? gkv[2] : gkv[3]));
                 const int colbase = hl * a.Cp;
                 for (int j = 0; j < xq.nch; ++j) {
                     ps_wait(x_full + slot, lap & 1u);
@@ -967,14 +987,14 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         const int nv0 = min(16, a.Cp - c), nv1 = max(0, min(16, a.Cp - c - 16));
                         const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlot;
                         tmem_wait_ld<16>(HA.r);
-                        if (nv1 > 0) ps_half_issue(HB, lane_addr + (uint32_t)(colbase + c + 16));
+                        if (nv1 > 0) ps_half_issue(HB, pre_addr + (uint32_t)(colbase + c + 16));
                         ps_bwd_half<NSP, EXACT>(HA, nv0, gk, b3_s + 4u * (colbase + c), xs, gs_s, L.g_part, row, colbase + c);
                         tmem_wait_ld<16>(HB.r);
                         {
                             int pn = p, jn = j + (a.Hg >= 2 ? 1 : 2);
                             if (jn >= xq.nch) { pn = p + 1; jn = a.Hg >= 2 ? 0 : cg; }
                             if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch)
-                                ps_half_issue(HA, lane_addr + (uint32_t)((h_begin + pn) * a.Cp + 32 * jn));
+                                ps_half_issue(HA, pre_addr + (uint32_t)((h_begin + pn) * a.Cp + 32 * jn));
                         }
                         ps_bwd_half<NSP, EXACT>(HB, nv1, gk, b3_s + 4u * (colbase + c + 16), xs + 64u, gs_s, L.g_part, row, colbase + c + 16);
                     }
@@ -1014,9 +1034,9 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const int kb = cg * (KP / kCg);
                 float* dcol = a.dAT + ((size_t)un.t * 128 + kb) * 128 + row;
                 uint32_t r0[32], r1[32];
-                tmem_ld32_issue(lane_addr + (uint32_t)kb, r0);
+                tmem_ld32_issue(lane_addr + p_col + (uint32_t)kb, r0);
                 tmem_wait_ld<32>(r0);
-                tmem_ld32_issue(lane_addr + (uint32_t)kb + 32u, r1);
+                tmem_ld32_issue(lane_addr + p_col + (uint32_t)kb + 32u, r1);
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) red_add_f32(dcol + (size_t)j * 128, __uint_as_float(r0[j]));

@@ -269,8 +269,10 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
         // the padded dX/dt row pitch is dropped (bank conflicts instead of no fit) when shared memory is too tight for it
         for (int attempt = 0; attempt < 2 && best < 0; ++attempt) {
             if (attempt == 1) pl->CpB = pl->Cp;
+            static const char* force_hg = getenv("NCDE_TC_HG");   // experiments: fix the number of hidden rows per h-group
             for (int hg = 8; hg >= 1; --hg) {
                 if (hg > pl->H) continue;
+                if (force_hg && atoi(force_hg) > 0 && hg != atoi(force_hg) && atoi(force_hg) <= pl->H) continue;
                 const int npad = (int)round_up(hg * pl->Cp, 16);
                 if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
                 if (pl->ns == 2) {
