@@ -805,50 +805,83 @@ extern "C" int ncde_path_eval_bwd(int kind, int dtype, const void* knots, int64_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Depth-<=2 log-signatures over windows of a piecewise-linear path, cumulatively summed (log-ODE transform).
+// Depth-<=3 log-signatures over windows of a piecewise-linear path, cumulatively summed (log-ODE transform).
 // Replaces the signatory.Logsignature(depth) + stack + cumsum part of torchcde.log_ode._logsignature_windows
 // (modules/torchcde/torchcde/log_ode.py:49-70).  x is the filled path (n_series, Lp, d); window w covers rows
 // idx[w] .. idx[w+1] inclusive.  Output row 0 is the "first increment" x[:, 0, :] padded with zeros (:53-55), row w+1 the
-// running sum of the window log-signatures.  Channel order = Signatory's default "words" mode: the d increments, then the
-// Levy areas of the Lyndon words (i, j), i < j, in lexicographic order:
-//     A_ij = 1/2 sum_k [ (x_k - x_0)_i (x_{k+1} - x_k)_j - (x_k - x_0)_j (x_{k+1} - x_k)_i ]
-// One thread per (series, output channel) walks the windows in order, so the cumulative sum needs no second pass.
+// running sum of the window log-signatures.  Channel order = Signatory's default "words" mode: the coefficients of
+// log(signature), taken in the tensor algebra, at the Lyndon words of length 1, 2, 3 (each length in lexicographic order):
+//   length 1  (i)       the increment
+//   length 2  (i, j), i < j                                  L2_ij  = S2_ij - S1_i S1_j / 2            (= the Levy area)
+//   length 3  (i, j, k), j >= i, k > i                       L3_ijk = S3_ijk - (S1_i S2_jk + S2_ij S1_k) / 2 + S1_i S1_j S1_k / 3
+// with S the signature of the window, built segment by segment with Chen's identity (exp of a linear segment D is
+// 1 + D + D(x)D / 2 + D(x)D(x)D / 6):  S3_ijk += S2_ij D_k + S1_i D_j D_k / 2 + D_i D_j D_k / 6,  S2_ij += S1_i D_j + D_i D_j / 2.
+// One thread per (series, output channel) carries only the signature entries its word needs and walks the windows in order,
+// so the cumulative sum needs no second pass.
 // wscale (device, W entries, nullable) multiplies each window's log-signature before the sum (_version 0: window duration).
 // ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int logsig_channels(int d, int depth) {
+    int ch = d;
+    if (depth >= 2) ch += d * (d - 1) / 2;
+    if (depth >= 3) ch += (d * d * d - d) / 3;
+    return ch;
+}
 template <typename T>
 __global__ void logsig_windows_kernel(const T* __restrict__ x, const int32_t* __restrict__ idx, const T* __restrict__ wscale,
                                       T* __restrict__ out, int64_t n_series, int64_t Lp, int d, int depth, int W) {
-    const int ch = depth >= 2 ? d + d * (d - 1) / 2 : d;
+    const int ch = logsig_channels(d, depth);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n_series * ch) return;
     const int64_t s = tid / ch;
     const int c = (int)(tid % ch);
     const T* xs = x + s * Lp * d;
     T* os = out + s * (int64_t)(W + 1) * ch;
-    int i = c, j = -1;
-    if (c >= d) {   // Lyndon word (i, j): c - d = i (2d - i - 1) / 2 + (j - i - 1)
+    const int n2 = d * (d - 1) / 2;
+    int len = 1, i = c, j = 0, k = 0;
+    if (c >= d + n2) {          // Lyndon word (i, j, k): first letter i has (d - i)(d - 1 - i) words: j in [i, d), k in (i, d)
+        len = 3;
+        int r = c - d - n2;
+        i = 0;
+        while (r >= (d - i) * (d - 1 - i)) { r -= (d - i) * (d - 1 - i); ++i; }
+        j = i + r / (d - 1 - i);
+        k = i + 1 + r % (d - 1 - i);
+    } else if (c >= d) {        // Lyndon word (i, j): c - d = i (2d - i - 1) / 2 + (j - i - 1)
+        len = 2;
         int r = c - d;
         i = 0;
         while (r >= d - 1 - i) { r -= d - 1 - i; ++i; }
         j = i + 1 + r;
     }
-    T run = j < 0 ? xs[i] : (T)0;
+    T run = len == 1 ? xs[i] : (T)0;
     os[c] = run;
     for (int w = 0; w < W; ++w) {
         const int lo = idx[w], hi = idx[w + 1];
         T v;
-        if (j < 0) {
+        if (len == 1) {
             v = xs[(int64_t)hi * d + i] - xs[(int64_t)lo * d + i];
-        } else {
+        } else if (len == 2) {
             const T x0i = xs[(int64_t)lo * d + i], x0j = xs[(int64_t)lo * d + j];
             T acc = 0;
             T pi = x0i, pj = x0j;
-            for (int k = lo; k < hi; ++k) {
-                const T ni = xs[(int64_t)(k + 1) * d + i], nj = xs[(int64_t)(k + 1) * d + j];
+            for (int q = lo; q < hi; ++q) {
+                const T ni = xs[(int64_t)(q + 1) * d + i], nj = xs[(int64_t)(q + 1) * d + j];
                 acc += (pi - x0i) * (nj - pj) - (pj - x0j) * (ni - pi);
                 pi = ni; pj = nj;
             }
             v = (T)0.5 * acc;
+        } else {
+            T pi = xs[(int64_t)lo * d + i], pj = xs[(int64_t)lo * d + j], pk = xs[(int64_t)lo * d + k];
+            T s1i = 0, s1j = 0, s1k = 0, s2ij = 0, s2jk = 0, s3 = 0;
+            for (int q = lo; q < hi; ++q) {
+                const T ni = xs[(int64_t)(q + 1) * d + i], nj = xs[(int64_t)(q + 1) * d + j], nk = xs[(int64_t)(q + 1) * d + k];
+                const T di = ni - pi, dj = nj - pj, dk = nk - pk;
+                s3 += s2ij * dk + s1i * dj * dk * (T)0.5 + di * dj * dk * (T)(1.0 / 6.0);
+                s2ij += s1i * dj + di * dj * (T)0.5;
+                s2jk += s1j * dk + dj * dk * (T)0.5;
+                s1i += di; s1j += dj; s1k += dk;
+                pi = ni; pj = nj; pk = nk;
+            }
+            v = s3 - (T)0.5 * (s1i * s2jk + s2ij * s1k) + s1i * s1j * s1k * (T)(1.0 / 3.0);
         }
         if (wscale) v *= wscale[w];
         run += v;
@@ -860,9 +893,10 @@ extern "C" int ncde_logsig_windows(int dtype, const void* x, const int32_t* idx,
                                    int64_t Lp, int d, int depth, int W, void* stream) {
     ncde::DeviceGuard device_guard(x);
     NCDE_REQUIRE(x && idx && out && Lp >= 1 && d >= 1 && W >= 0, NCDE_ERR_INVALID, "logsig_windows: bad arguments");
-    NCDE_REQUIRE(depth == 1 || depth == 2, NCDE_ERR_UNSUPPORTED, "logsig_windows: depth %d is not implemented (1 and 2 are)", depth);
+    NCDE_REQUIRE(depth >= 1 && depth <= 3, NCDE_ERR_UNSUPPORTED, "logsig_windows: depth %d is not implemented (1, 2 and 3 are)", depth);
+    NCDE_REQUIRE(d <= 1024, NCDE_ERR_UNSUPPORTED, "logsig_windows: %d channels > 1024 not supported", d);
     if (n_series == 0) return NCDE_OK;
-    const int ch = depth >= 2 ? d + d * (d - 1) / 2 : d;
+    const int ch = logsig_channels(d, depth);
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_DTYPE(dtype, (logsig_windows_kernel<T><<<grid_for(n_series * ch, 128), 128, 0, st>>>(
                               (const T*)x, idx, (const T*)wscale, (T*)out, n_series, Lp, d, depth, W)));

@@ -1,9 +1,10 @@
-"""Log-ODE transform: log-signatures over windows (depth 1 and 2) on the GPU.
+"""Log-ODE transform: log-signatures over windows (depth 1, 2 and 3) on the GPU.
 
 Mirrors torchcde/log_ode.py of the reference (`logsig_windows`, the deprecated `logsignature_windows`).  The reference
 delegates the log-signature itself to the third-party `signatory` extension (un-vendored, un-pinned: SURVEY §8c); here
-depths 1 and 2 are computed by `ncde_logsig_windows` (csrc/interp.cu) in Signatory's default "words" channel order —
-increments, then the Levy areas of the Lyndon words (i, j), i < j.  Deeper log-signatures raise NotImplementedError.
+depths 1 to 3 are computed by `ncde_logsig_windows` (csrc/interp.cu) in Signatory's default "words" channel order — the
+coefficients of log(signature) at the Lyndon words of length 1 (increments), 2 ((i, j), i < j: the Levy areas) and 3
+((i, j, k), j >= i, k > i).  Deeper log-signatures raise NotImplementedError.
 The window bookkeeping follows log_ode.py:15-47 line by line (it decides which rows exist, so it must not drift);
 missing values and the inserted window boundaries are filled through `linear_interpolation_coeffs` as in :47.
 """
@@ -15,12 +16,11 @@ from . import misc
 
 
 def logsignature_channels(in_channels, depth):
-    """signatory.logsignature_channels for depth <= 2: d + d (d - 1) / 2."""
-    if depth == 1:
-        return in_channels
-    if depth == 2:
-        return in_channels + in_channels * (in_channels - 1) // 2
-    raise NotImplementedError("log-signatures of depth {} are not implemented (depth 1 and 2 are)".format(depth))
+    """signatory.logsignature_channels for depth <= 3 (Witt's formula: d, d (d - 1) / 2, (d^3 - d) / 3 Lyndon words)."""
+    d = in_channels
+    if depth not in (1, 2, 3):
+        raise NotImplementedError("log-signatures of depth {} are not implemented (depth 1, 2 and 3 are)".format(depth))
+    return d + (d * (d - 1) // 2 if depth >= 2 else 0) + ((d ** 3 - d) // 3 if depth >= 3 else 0)
 
 
 def _logsignature_windows(x, depth, window_length, t, _version):

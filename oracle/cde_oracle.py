@@ -813,22 +813,76 @@ class SmoothLinearPath(LinearPath):
 # ----------------------------------------------------------------------------------------------------------------
 # Log-ODE transform (tcde/log_ode.py).  The reference calls the third-party `signatory` extension for the log-signature
 # itself; signatory is neither vendored nor pinned, so THIS PART OF THE ORACLE IS "PARITY UNPINNED":
-# depth <= 2 log-signatures are restated from the published definition (Signatory's default "words" mode: level 1 =
-# increments, level 2 = coefficients of the Lyndon words (i, j), i < j, of log S = Levy areas) and checked through the
-# algebraic identity the reference's own test uses (modules/torchcde/test/test_log_ode.py:6-30).
+# depth <= 3 log-signatures are restated from the published definition (Signatory's default "words" mode: the coefficients of
+# log S, taken in the tensor algebra, at the Lyndon words of each length) and pinned by three independent checks in
+# tests/test_logsig.py: the algebraic identity the reference's own test uses (modules/torchcde/test/test_log_ode.py:6-30), a
+# brute-force double / triple sum over segment pairs, and the Baker-Campbell-Hausdorff series for two-segment paths.
 # ----------------------------------------------------------------------------------------------------------------
 
 
 def logsignature_channels(d, depth):
-    if depth == 1:
-        return d
-    if depth == 2:
-        return d + d * (d - 1) // 2
-    raise NotImplementedError("depth {}".format(depth))
+    """Number of Lyndon words of length <= depth over d letters (Witt): d, d (d - 1) / 2, (d^3 - d) / 3."""
+    if depth not in (1, 2, 3):
+        raise NotImplementedError("depth {}".format(depth))
+    return d + (d * (d - 1) // 2 if depth >= 2 else 0) + ((d ** 3 - d) // 3 if depth >= 3 else 0)
+
+
+def lyndon_words(d, length):
+    """Lyndon words of the given length over {0..d-1} in lexicographic order, by the definition: strictly smaller than every
+    proper rotation."""
+    import itertools
+    out = []
+    for w in itertools.product(range(d), repeat=length):
+        if all(w < w[r:] + w[:r] for r in range(1, length)):
+            out.append(w)
+    return out
+
+
+def signature_levels(path, depth):
+    """Signature of piecewise-linear paths (..., m+1, d) in the tensor algebra, level by level, with Chen's identity:
+    S <- S (x) exp(D) per segment, exp(D) = 1 + D + D(x)D/2 + D(x)D(x)D/6.  Returns [S1 (..., d), S2 (..., d, d), S3 (..., d, d, d)]."""
+    inc = path[..., 1:, :] - path[..., :-1, :]
+    batch = path.shape[:-2]
+    d = path.size(-1)
+    S1 = torch.zeros(*batch, d, dtype=path.dtype)
+    S2 = torch.zeros(*batch, d, d, dtype=path.dtype)
+    S3 = torch.zeros(*batch, d, d, d, dtype=path.dtype)
+    for m in range(inc.size(-2)):
+        D = inc[..., m, :]
+        E2 = 0.5 * D.unsqueeze(-1) * D.unsqueeze(-2)
+        E3 = E2.unsqueeze(-1) * D.unsqueeze(-2).unsqueeze(-2) / 3.0
+        if depth >= 3:
+            S3 = S3 + S2.unsqueeze(-1) * D.unsqueeze(-2).unsqueeze(-2) + S1.unsqueeze(-1).unsqueeze(-1) * E2.unsqueeze(-3) + E3
+        if depth >= 2:
+            S2 = S2 + S1.unsqueeze(-1) * D.unsqueeze(-2) + E2
+        S1 = S1 + D
+    return [S1, S2, S3][:depth]
+
+
+def logsignature_words(path, depth):
+    """Log-signature in Signatory's default "words" mode: log(S) = X - X^2/2 + X^3/3 (X = S - 1) computed in the tensor algebra,
+    then the coefficients of the Lyndon words of length 1..depth, each length in lexicographic order."""
+    S = signature_levels(path, depth)
+    d = path.size(-1)
+    out = [S[0]]
+    if depth >= 2:
+        L2 = S[1] - 0.5 * S[0].unsqueeze(-1) * S[0].unsqueeze(-2)
+        w = lyndon_words(d, 2)
+        if w:
+            ii = torch.tensor(w)
+            out.append(L2[..., ii[:, 0], ii[:, 1]])
+    if depth >= 3:
+        L3 = S[2] - 0.5 * (S[0].unsqueeze(-1).unsqueeze(-1) * S[1].unsqueeze(-3) + S[1].unsqueeze(-1) * S[0].unsqueeze(-2).unsqueeze(-2)) \
+            + S[0].unsqueeze(-1).unsqueeze(-1) * S[0].unsqueeze(-1).unsqueeze(-3) * S[0].unsqueeze(-2).unsqueeze(-2) / 3.0
+        w = lyndon_words(d, 3)
+        if w:
+            ii = torch.tensor(w)
+            out.append(L3[..., ii[:, 0], ii[:, 1], ii[:, 2]])
+    return torch.cat(out, dim=-1)
 
 
 def logsignature_depth2(path, depth):
-    """Log-signature of piecewise-linear paths (..., m+1, d) via the full level-2 signature:
+    """Depth <= 2 through the closed form (kept as a second, independent route for the tests): level 2 = Levy areas
     S2 = sum_k [ (x_k - x_0) (x) D_k + 1/2 D_k (x) D_k ],  logsig_2 = 1/2 (S2 - S2^T) upper triangle, row-major."""
     inc = path[..., 1:, :] - path[..., :-1, :]
     lvl1 = path[..., -1, :] - path[..., 0, :]
@@ -873,7 +927,7 @@ def logsig_windows(x, depth, window_length, t=None, _version=1):
     first[..., :x.size(-1)] = x[..., 0, :]
     pieces = [first]
     for index, next_index, time, next_time in zip(new_t_indices[:-1], new_t_indices[1:], new_t[:-1], new_t[1:]):
-        ls = logsignature_depth2(x[..., index:next_index + 1, :], depth)
+        ls = logsignature_words(x[..., index:next_index + 1, :], depth)
         if _version == 0:
             ls = ls * (next_time - time)
         pieces.append(ls)

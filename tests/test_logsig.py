@@ -1,15 +1,54 @@
-"""Log-ODE transform.  The reference's log-signature comes from the un-vendored `signatory` extension, so the
-oracle's restatement is "parity unpinned"; what pins it is the algebraic identity of the reference's own test
-(modules/torchcde/test/test_log_ode.py:6-30): the derivative of the linearly interpolated transformed path at a window
-mid-point equals the log-signature of that window — checked here against an independent brute-force Levy area."""
+"""Log-ODE transform, depth 1 to 3.  The reference's log-signature comes from the un-vendored `signatory` extension,
+so no output of the reference itself can be minted here; the oracle's restatement (tensor-algebra log of the Chen signature,
+coefficients at the Lyndon words = Signatory's default "words" mode) is pinned by three independent routes instead:
+  * the algebraic identity of the reference's own test (modules/torchcde/test/test_log_ode.py:6-30): the derivative of the linearly
+    interpolated transformed path at a window mid-point equals the log-signature of that window;
+  * brute-force iterated sums over ordered segment tuples (no Chen recursion, no tensor algebra);
+  * the Baker-Campbell-Hausdorff series for a two-segment path, log(e^a e^b) = a + b + [a,b]/2 + ([a,[a,b]] + [b,[b,a]])/12,
+    evaluated with explicit commutators of tensors — a published closed form that shares no code with either of the above."""
 import pytest
 import torch
 
 from oracle import cde_oracle as O
 
 
+def _brute_signature(path, depth):
+    """Iterated integrals of a piecewise-linear path as explicit sums over ordered tuples of segments:
+    S2_ij = sum_{k<l} D_ki D_lj + 1/2 sum_k D_ki D_kj;  S3_ijk = sum_{a<b<c} + 1/2 (a=b<c) + 1/2 (a<b=c) + 1/6 (a=b=c)."""
+    inc = (path[1:] - path[:-1]).double()
+    m, d = inc.shape
+    S1 = inc.sum(0)
+    S2 = torch.zeros(d, d, dtype=torch.float64)
+    S3 = torch.zeros(d, d, d, dtype=torch.float64)
+    for a in range(m):
+        for b in range(a, m):
+            wab = 0.5 if a == b else 1.0
+            S2 += wab * torch.outer(inc[a], inc[b])
+            if depth >= 3:
+                for c in range(b, m):
+                    if a == b == c:
+                        wt = 1.0 / 6.0
+                    elif a == b or b == c:
+                        wt = 0.5
+                    else:
+                        wt = 1.0
+                    S3 += wt * torch.einsum("i,j,k->ijk", inc[a], inc[b], inc[c])
+    return S1, S2, S3
+
+
+def _brute_logsig3(path):
+    S1, S2, S3 = _brute_signature(path, 3)
+    d = path.size(-1)
+    L2 = S2 - 0.5 * torch.outer(S1, S1)
+    L3 = S3 - 0.5 * (torch.einsum("i,jk->ijk", S1, S2) + torch.einsum("ij,k->ijk", S2, S1)) + torch.einsum("i,j,k->ijk", S1, S1, S1) / 3.0
+    out = [S1] + [L2[i, j].reshape(1) for (i, j) in O.lyndon_words(d, 2)] + [L3[i, j, k].reshape(1) for (i, j, k) in O.lyndon_words(d, 3)]
+    return torch.cat(out).to(path.dtype)
+
+
 def _brute_logsig(path, depth):
     """(m+1, d) -> depth-<=2 log-signature by explicit loops: A_ij = 1/2 sum_{k<l} (D_k,i D_l,j - D_k,j D_l,i)."""
+    if depth == 3:
+        return _brute_logsig3(path)
     inc = path[1:] - path[:-1]
     d = path.size(-1)
     out = [float(inc[:, i].sum()) for i in range(d)]
@@ -25,7 +64,44 @@ def _brute_logsig(path, depth):
     return torch.tensor(out, dtype=path.dtype)
 
 
-@pytest.mark.parametrize("depth", [1, 2])
+def test_lyndon_word_counts_and_order():
+    for d in (1, 2, 3, 5, 14):
+        assert len(O.lyndon_words(d, 1)) == d
+        assert len(O.lyndon_words(d, 2)) == d * (d - 1) // 2
+        assert len(O.lyndon_words(d, 3)) == (d ** 3 - d) // 3
+        assert O.logsignature_channels(d, 3) == d + d * (d - 1) // 2 + (d ** 3 - d) // 3
+    assert O.lyndon_words(3, 3) == [(0, 0, 1), (0, 0, 2), (0, 1, 1), (0, 1, 2), (0, 2, 1), (0, 2, 2), (1, 1, 2), (1, 2, 2)]
+
+
+def test_depth3_matches_baker_campbell_hausdorff():
+    """Two-segment path a then b: log S = a + b + [a,b]/2 + ([a,[a,b]] + [b,[b,a]])/12 with [x,y] = x(x)y - y(x)x."""
+    torch.manual_seed(0)
+    for d in (2, 3, 5):
+        a, b = torch.randn(d, dtype=torch.float64), torch.randn(d, dtype=torch.float64)
+        path = torch.stack([torch.zeros(d, dtype=torch.float64), a, a + b])
+        ab = torch.outer(a, b) - torch.outer(b, a)                                     # [a, b], level 2
+        a_ab = torch.einsum("i,jk->ijk", a, ab) - torch.einsum("ij,k->ijk", ab, a)      # [a, [a, b]]
+        b_ba = torch.einsum("i,jk->ijk", b, -ab) - torch.einsum("ij,k->ijk", -ab, b)    # [b, [b, a]]
+        L2, L3 = 0.5 * ab, (a_ab + b_ba) / 12.0
+        expect = torch.cat([a + b] + [L2[i, j].reshape(1) for (i, j) in O.lyndon_words(d, 2)] +
+                           [L3[i, j, k].reshape(1) for (i, j, k) in O.lyndon_words(d, 3)])
+        got = O.logsignature_words(path, 3)
+        assert got.shape == expect.shape and got.allclose(expect, atol=1e-13)
+
+
+def test_depth3_matches_brute_force_and_depth2_closed_form():
+    torch.manual_seed(1)
+    for m, d in [(1, 3), (4, 2), (6, 4), (3, 1)]:
+        path = torch.randn(m + 1, d, dtype=torch.float64).cumsum(0)
+        got = O.logsignature_words(path, 3)
+        assert got.allclose(_brute_logsig3(path), atol=1e-12)
+        assert O.logsignature_words(path, 2).allclose(O.logsignature_depth2(path, 2), atol=1e-13)
+    # a straight line has no area and no level-3 term
+    line = torch.linspace(0, 1, 5, dtype=torch.float64).unsqueeze(-1) * torch.randn(3, dtype=torch.float64)
+    assert O.logsignature_words(line, 3)[3:].abs().max() < 1e-14
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
 def test_oracle_identity_of_the_reference_test(depth):
     torch.manual_seed(depth)
     window_length = 4
@@ -68,7 +144,9 @@ def test_gpu_logsig_windows_matches_oracle(dtype, tol):
     import torchcde_b200 as tc
     torch.manual_seed(5)
     for shape, wl, depth, tt in [((7, 24, 14), 4, 2, None), ((2, 3, 25, 5), 2.5, 2, None), ((5, 30, 3), 7, 1, None),
-                                 ((4, 16, 6), 1.7, 2, torch.linspace(0, 9, 16)), ((1, 9, 1), 3, 2, None)]:
+                                 ((4, 16, 6), 1.7, 2, torch.linspace(0, 9, 16)), ((1, 9, 1), 3, 2, None),
+                                 ((6, 24, 14), 4, 3, None), ((2, 2, 20, 4), 2.5, 3, None), ((3, 12, 1), 3, 3, None),
+                                 ((4, 16, 5), 1.7, 3, torch.linspace(0, 9, 16))]:
         x = torch.randn(*shape, dtype=dtype)
         x[..., 0] = torch.arange(shape[-2], dtype=dtype) if shape[-1] > 1 else x[..., 0]
         if shape[-1] > 2:
@@ -82,8 +160,8 @@ def test_gpu_logsig_windows_matches_oracle(dtype, tol):
         gv, gt = tc.logsignature_windows(x.clone().cuda(), depth, wl, None if t is None else t.cuda())
         assert torch.equal(gt.cpu(), rt) and float((gv.cpu() - rv).abs().max() / rv.abs().max().clamp_min(1e-30)) <= tol
     with pytest.raises(NotImplementedError):
-        tc.logsig_windows(torch.randn(2, 8, 3).cuda(), 3, 2)
-    assert tc.logsignature_channels(14, 2) == 105
+        tc.logsig_windows(torch.randn(2, 8, 3).cuda(), 4, 2)
+    assert tc.logsignature_channels(14, 2) == 105 and tc.logsignature_channels(14, 3) == 105 + 910
 
 
 @pytest.mark.gpu
