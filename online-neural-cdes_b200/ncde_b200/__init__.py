@@ -127,3 +127,4 @@ class NeuralCDE(nn.Module):
 
 
 from .stacked import StackedNeuralCDE  # noqa: E402,F401
+from .attention import AttentionNeuralCDE, Sparsemax  # noqa: E402,F401
