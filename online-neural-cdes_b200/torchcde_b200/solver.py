@@ -30,12 +30,24 @@ default_precision = "fp32"
 
 
 class FixedSchedule:
-    """Host arrays describing the fixed grid, stage times and output map (kept alive while kernels are enqueued)."""
+    """Host arrays describing the fixed grid, stage times and output map (kept alive while kernels are enqueued).
 
-    def __init__(self, t_host, method, step_size, grid_constructor, func, z0):
-        t = t_host
+    Decreasing ``t`` follows torchdiffeq's _check_inputs (modules/torchdiffeq/torchdiffeq/_impl/misc.py:262-283): time is negated
+    (tau = -t), the grid / stages / outputs are laid out in tau, and the vector field is evaluated at -tau with its sign flipped.
+    Every step formula is linear in dt * k, so the kernels run the same arithmetic with the actual (decreasing) stage times and
+    dt = -(tau1 - tau0).  ``perturb=True`` nudges the first stage time of a step to the next float and the last one (rk4) to the
+    previous float, in the state's dtype and in tau, as _PerturbFunc does (misc.py:168-191, fixed_grid.py:9-29)."""
+
+    def __init__(self, t_host, method, step_size, grid_constructor, func, z0, perturb=False):
+        reverse = len(t_host) > 1 and bool(t_host[0] > t_host[1])
+        t = -t_host if reverse else t_host
         if step_size is None:
-            grid = t if grid_constructor is None else grid_constructor(func, z0, t)
+            if grid_constructor is None:
+                grid = t
+            elif reverse:
+                grid = -torch.as_tensor(grid_constructor(func, z0, -t))
+            else:
+                grid = grid_constructor(func, z0, t)
         else:
             if grid_constructor is not None:
                 raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
@@ -54,9 +66,16 @@ class FixedSchedule:
             stages = g0.unsqueeze(1)
         self.n_steps = int(dt.numel())
         self.n_stages = int(stages.shape[1]) if self.n_steps else (4 if method == "rk4" else 1)
-        self.stage_t = np.ascontiguousarray(stages.to(torch.float32).numpy())
-        self.dt = np.ascontiguousarray(dt.to(torch.float32).numpy())
-        # output map (solvers.py:106-117, 166-172)
+        stage_t = np.ascontiguousarray(stages.to(torch.float32).numpy())
+        if perturb and self.n_steps:
+            stage_t[:, 0] = np.nextafter(stage_t[:, 0], np.float32(np.inf))
+            if method == "rk4":
+                stage_t[:, -1] = np.nextafter(stage_t[:, -1], np.float32(-np.inf))
+        dt32 = np.ascontiguousarray(dt.to(torch.float32).numpy())
+        self.stage_t = np.ascontiguousarray(-stage_t) if reverse else stage_t
+        self.dt = np.ascontiguousarray(-dt32) if reverse else dt32
+        self.reverse = reverse
+        # output map (solvers.py:106-117, 166-172), in tau
         T = int(t.numel())
         tn, gn = t.numpy(), grid.numpy()
         out_step = np.zeros(T, dtype=np.int64)
@@ -80,15 +99,16 @@ _SCHEDULE_CACHE = {}
 def _schedule(t_host, method, options, func, z0):
     step_size = options.get("step_size")
     gc = options.get("grid_constructor")
+    perturb = bool(options.get("perturb", False))
     if gc is None:
-        key = (t_host.dtype, t_host.numpy().tobytes(), method, None if step_size is None else float(step_size))
+        key = (t_host.dtype, t_host.numpy().tobytes(), method, None if step_size is None else float(step_size), perturb)
         hit = _SCHEDULE_CACHE.get(key)
         if hit is None:
             if len(_SCHEDULE_CACHE) > 64:
                 _SCHEDULE_CACHE.clear()
-            hit = _SCHEDULE_CACHE[key] = FixedSchedule(t_host, method, step_size, None, func, z0)
+            hit = _SCHEDULE_CACHE[key] = FixedSchedule(t_host, method, step_size, None, func, z0, perturb)
         return hit
-    return FixedSchedule(t_host, method, step_size, gc, func, z0)
+    return FixedSchedule(t_host, method, step_size, gc, func, z0, perturb)
 
 
 def _np_ptr(a):
@@ -378,8 +398,10 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
     t_host = misc.host_values(t)
     diff = t_host[1:] > t_host[:-1]
     assert bool(diff.all()) or bool((~diff).all()), 't must be strictly increasing or decreasing'
-    if len(t_host) > 1 and bool(t_host[0] > t_host[1]):
-        raise NotImplementedError("decreasing integration times are not implemented")
+    decreasing = len(t_host) > 1 and bool(t_host[0] > t_host[1])
+    if decreasing and (method == 'dopri5' or adjoint):
+        raise NotImplementedError("decreasing integration times are implemented for the fixed-grid solvers (euler, rk4) with "
+                                  "adjoint=False")
 
     batch_shape = z0.shape[:-1]
     H = z0.shape[-1]
@@ -439,8 +461,8 @@ def cdeint(X, func, z0, t, adjoint=True, vector_field_type='matmul', **kwargs):
         unused = {k: v for k, v in options.items() if k not in ('step_size', 'grid_constructor', 'perturb', 'interp')}
         if options.get('interp', 'linear') != 'linear':
             raise NotImplementedError("only interp='linear' is implemented for fixed-grid output")
-        if options.get('perturb', False):
-            raise NotImplementedError("perturb=True is not implemented")
+        if options.get('perturb', False) and adjoint:
+            raise NotImplementedError("perturb=True is implemented with adjoint=False")
         if unused:
             warnings.warn('{}: Unexpected arguments {}'.format('RK4' if method == 'rk4' else 'Euler', unused))
         z0f = z0.reshape(-1, H)
