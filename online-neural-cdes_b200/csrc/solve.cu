@@ -776,6 +776,73 @@ static void ps_emit_slots(const ncde_fixed_grid_t& g, std::vector<int>* slots) {
     for (int64_t j = 1; j < g.n_out; ++j) (*slots)[(size_t)g.out_step[j]] = (int)j;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side loop of the adaptive solvers: a CUDA-graph WHILE node whose body is ONE attempt (every kernel of it reads its step
+// size, stage times and flags from the device control block, so the body's launch parameters never change) followed by a
+// one-thread kernel that sets the loop condition from ctrl->done.  The host enqueues the graph once and never looks at the
+// controller again: no event, no flag copy, no stream synchronisation (north_star: "step-accept control reduced on device with
+// no host sync").  NCDE_DOPRI_HOSTPOLL=1 keeps the round-1 chunked look-ahead loop for A/B runs.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; i < n; i += (int64_t)blockDim.x) {
+        if (i >= ((int64_t)blockIdx.x + 1) * blockDim.x * 4) break;
+        p[i] = 0.f;
+    }
+}
+__global__ void adapt_cond_kernel(cudaGraphConditionalHandle handle, const AdaptCtrl* ctrl) {
+    cudaGraphSetConditional(handle, ctrl->done ? 0u : 1u);
+}
+static bool dopri_host_poll() {
+    static const bool v = getenv("NCDE_DOPRI_HOSTPOLL") != nullptr;
+    return v;
+}
+template <typename Body>
+static int graph_while_not_done(cudaStream_t st, const AdaptCtrl* ctrl, Body&& body) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cs = nullptr;
+    int rc = NCDE_OK;
+    auto cleanup = [&]() {
+        if (exec) cudaGraphExecDestroy(exec);     // an executable graph in flight is freed on completion
+        if (graph) cudaGraphDestroy(graph);
+        if (cs) cudaStreamDestroy(cs);
+    };
+#define NCDE_GW(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            ncde::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            cleanup();                                                                                  \
+            return NCDE_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)
+    NCDE_GW(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle handle;
+    NCDE_GW(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    NCDE_GW(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    cudaGraph_t body_graph = np.conditional.phGraph_out[0];
+    NCDE_GW(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    NCDE_GW(cudaStreamBeginCaptureToGraph(cs, body_graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    rc = body(cs);
+    if (rc == NCDE_OK) adapt_cond_kernel<<<1, 1, 0, cs>>>(handle, ctrl);
+    cudaGraph_t ended = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(cs, &ended);
+    if (rc != NCDE_OK) { cleanup(); return rc; }
+    NCDE_GW(e_end);
+    NCDE_GW(cudaGraphInstantiate(&exec, graph, 0));
+    NCDE_GW(cudaGraphLaunch(exec, st));
+#undef NCDE_GW
+    cleanup();
+    return NCDE_OK;
+}
+
 }  // namespace ncde
 
 using namespace ncde;
@@ -1780,19 +1847,20 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     }
 
     // one vector-field evaluation: stage input from tab[tab_index], result into kT[k_out]
+    cudaStream_t cur = st;   // the stream the evaluation kernels go to (the capture stream while the attempt body is recorded)
     auto eval = [&](int tab_index, int k_out, float* stage_input_T) -> int {
         ha.tab_index = tab_index;
         ha.actT[0] = stage_input_T ? stage_input_T : stage + pl.act_off[0];
-        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, cur, ha));
         if (pl.F == 0) fa.actT = ha.actT[0];
         if (use_tc) {
             ta.koutT = kT[k_out];
-            { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
+            { const int rc_tc = launch_tc_fwd(pl, ta, ms, cur); if (rc_tc != NCDE_OK) return rc_tc; }
         } else {
             fa.koutT = kT[k_out];
             const dim3 fg(pl.n_hg, pl.n_bt);
-            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
-            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
+            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
         }
         launches += 2;
         return NCDE_OK;
@@ -1822,39 +1890,58 @@ extern "C" int ncde_solve_adaptive_fwd(const ncde_problem_t* p, const float* z0,
     for (int i = 0; i < 7; ++i) da.kT[i] = kT[i];
     da.out_t = d_out_t; da.z_out = z_out; da.partials = partials; da.nblocks = nblocks;
 
-    // completion polling: pinned flag + event per chunk, always one chunk of look-ahead
-    static int* h_done = nullptr;
-    static cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (!h_done) {
-        NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, 2 * sizeof(int), cudaHostAllocDefault));
-        NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-        NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    }
-    h_done[0] = h_done[1] = 0;
-    const int64_t chunk = 32;
-    int64_t enq = 0;
-    int n_chunks = 0;
-    while (enq < ad.max_attempts) {
-        const int64_t upto = enq + chunk < ad.max_attempts ? enq + chunk : ad.max_attempts;
-        for (; enq < upto; ++enq) {
-            for (int i = 1; i <= 6; ++i) {
-                rc = eval(i, i, i == 6 ? y1T : nullptr);
-                if (rc != NCDE_OK) return rc;
+    auto attempt = [&](cudaStream_t q) -> int {
+        cur = q;
+        for (int i = 1; i <= 6; ++i) {
+            const int rc_e = eval(i, i, i == 6 ? y1T : nullptr);
+            if (rc_e != NCDE_OK) { cur = st; return rc_e; }
+        }
+        cur = st;
+        NCDE_CUDA_OK(launch_pdl(dopri_err_kernel, dim3(nblocks), dim3(256), 0, q, da));
+        NCDE_CUDA_OK(launch_pdl(dopri_ctrl_kernel, dim3(1), dim3(32), 0, q, da));
+        NCDE_CUDA_OK(launch_pdl(dopri_accept_kernel, tg, tb, 0, q, da));
+        launches += 3;
+        return NCDE_OK;
+    };
+    if (!dopri_host_poll()) {
+        // the attempt loop runs on the device: one graph launch, no host synchronisation (graph_while_not_done)
+        rc = graph_while_not_done(st, ctrl, attempt);
+        if (rc != NCDE_OK) return rc;
+    } else {
+        // completion polling: pinned flag + event per chunk, always one chunk of look-ahead
+        static int* h_done = nullptr;
+        static cudaEvent_t ev[2] = {nullptr, nullptr};
+        if (!h_done) {
+            NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, 2 * sizeof(int), cudaHostAllocDefault));
+            NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+            NCDE_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        }
+        h_done[0] = h_done[1] = 0;
+        const int64_t chunk = 32;
+        int64_t enq = 0;
+        int n_chunks = 0;
+        while (enq < ad.max_attempts) {
+            const int64_t upto = enq + chunk < ad.max_attempts ? enq + chunk : ad.max_attempts;
+            for (; enq < upto; ++enq) {
+                for (int i = 1; i <= 6; ++i) {
+                    rc = eval(i, i, i == 6 ? y1T : nullptr);
+                    if (rc != NCDE_OK) return rc;
+                }
+                NCDE_CUDA_OK(launch_pdl(dopri_err_kernel, dim3(nblocks), dim3(256), 0, st, da));
+                NCDE_CUDA_OK(launch_pdl(dopri_ctrl_kernel, dim3(1), dim3(32), 0, st, da));
+                NCDE_CUDA_OK(launch_pdl(dopri_accept_kernel, tg, tb, 0, st, da));
+                launches += 3;
             }
-            NCDE_CUDA_OK(launch_pdl(dopri_err_kernel, dim3(nblocks), dim3(256), 0, st, da));
-            NCDE_CUDA_OK(launch_pdl(dopri_ctrl_kernel, dim3(1), dim3(32), 0, st, da));
-            NCDE_CUDA_OK(launch_pdl(dopri_accept_kernel, tg, tb, 0, st, da));
-            launches += 3;
+            const int slot = n_chunks & 1;
+            if (n_chunks >= 1) {
+                // wait for the flag written at the end of the PREVIOUS chunk (the chunk just enqueued keeps the GPU busy)
+                NCDE_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
+                if (h_done[slot ^ 1]) break;
+            }
+            NCDE_CUDA_OK(cudaMemcpyAsync(&h_done[slot], &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            NCDE_CUDA_OK(cudaEventRecord(ev[slot], st));
+            ++n_chunks;
         }
-        const int slot = n_chunks & 1;
-        if (n_chunks >= 1) {
-            // wait for the flag written at the end of the PREVIOUS chunk (the chunk just enqueued keeps the GPU busy)
-            NCDE_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
-            if (h_done[slot ^ 1]) break;
-        }
-        NCDE_CUDA_OK(cudaMemcpyAsync(&h_done[slot], &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-        NCDE_CUDA_OK(cudaEventRecord(ev[slot], st));
-        ++n_chunks;
     }
     if (stats) {
         // attempted, accepted, nfe are consecutive int64 fields of the control block; flags follows max_attempts
@@ -2369,32 +2456,33 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     const unsigned th_grid = (unsigned)ceil_div((int64_t)tl.total, 256);
 
     // one augmented evaluation: stage inputs from ctrl->tab[tab_index]; results into kf/ka/ktheta[k_out]
+    cudaStream_t cur = st;   // the stream the attempt kernels go to (the capture stream while the attempt body is recorded)
     auto aeval = [&](int tab_index, int k_out, float* y_stage_T) -> int {
         ha.tab_index = tab_index;
         ha.actT[0] = y_stage_T ? y_stage_T : stage + pl.act_off[0];
         hb.actT[0] = ha.actT[0];
         wa.actT[0][0] = ha.actT[0];   // the first hidden layer's input is the stage input itself
         if (pl.F == 0) { fa.actT = ha.actT[0]; }
-        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, st, ha));
+        NCDE_CUDA_OK(launch_pdl(hidden_fwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_fwd, cur, ha));
         const dim3 fg(pl.n_hg, pl.n_bt);
         if (use_tc) {
             ta.koutT = kf[k_out];
-            { const int rc_tc = launch_tc_fwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
+            { const int rc_tc = launch_tc_fwd(pl, ta, ms, cur); if (rc_tc != NCDE_OK) return rc_tc; }
         } else {
             fa.koutT = kf[k_out];
-            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
-            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+            if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
+            else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
         }
         if (has_vt) {
             // q[b,h] = sum_c F(z)[b,h,c] d2X/dt2[b,c]: the same field kernel with the second path derivative
             if (use_tc) {
                 ta.koutT = qT; ta.dXT = ddXT;
-                { const int rc_tc = launch_tc_fwd(pl, ta, ms_q, st); if (rc_tc != NCDE_OK) return rc_tc; }
+                { const int rc_tc = launch_tc_fwd(pl, ta, ms_q, cur); if (rc_tc != NCDE_OK) return rc_tc; }
                 ta.dXT = stage + pl.dx_off;
             } else {
                 fa.koutT = qT; fa.dXT = ddXT;
-                if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
-                else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, st, fa));
+                if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<8>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
+                else NCDE_CUDA_OK(launch_pdl(field_fwd_kernel<4>, fg, dim3(kThreads), pl.fwd_smem, cur, fa));
                 fa.dXT = stage + pl.dx_off;
             }
             ++launches;
@@ -2404,25 +2492,29 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
         cb.n = (int64_t)nHB; cb.combine = COMBINE_LINEAR; cb.sign = 1.f; cb.base = aT; cb.out = a_stage;
         for (int j = 0; j < 7; ++j) cb.k[j] = ka[j];
         cb.ctrl = ctrl; cb.tab_index = tab_index;
-        NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(ew_grid), dim3(256), 0, st, cb));
+        NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(ew_grid), dim3(256), 0, cur, cb));
         if (has_vt) {
             // d(vjp_t)/dtau = sum_{b,h} a[b,h] q[b,h]
-            NCDE_CUDA_OK(launch_pdl(aug_dot_kernel, dim3(1), dim3(1024), 0, st, (const AdaptCtrl*)ctrl, (const float*)a_stage,
+            NCDE_CUDA_OK(launch_pdl(aug_dot_kernel, dim3(1), dim3(1024), 0, cur, (const AdaptCtrl*)ctrl, (const float*)a_stage,
                                     (const float*)qT, pl.B, pl.Bp, pl.H, kvt[k_out]));
             ++launches;
         }
-        NCDE_CUDA_OK(cudaMemsetAsync(dW3acc, 0, nW3 * 4, st));
-        NCDE_CUDA_OK(cudaMemsetAsync(db3acc, 0, nb3 * 4, st));
-        NCDE_CUDA_OK(cudaMemsetAsync(ktheta[k_out], 0, tl.total * 4, st));
+        // zero-fills as kernels (not memset nodes): this sequence is recorded into the body of a conditional graph node
+        auto zero = [&](float* ptr, size_t n) {
+            zero_f32_kernel<<<(unsigned)ceil_div((int64_t)n, 1024), 256, 0, cur>>>(ptr, (int64_t)n);
+        };
+        zero(dW3acc, nW3);
+        zero(db3acc, nb3);
+        zero(ktheta[k_out], tl.total);
         for (int s2 = 0; s2 < wa.n_slots; ++s2) {
-            NCDE_CUDA_OK(cudaMemsetAsync(wa.gWp[s2], 0, gwp_floats[s2] * 4, st));
-            NCDE_CUDA_OK(cudaMemsetAsync(wa.gbp[s2], 0, gbp_floats[s2] * 4, st));
+            zero(wa.gWp[s2], gwp_floats[s2]);
+            zero(wa.gbp[s2], gbp_floats[s2]);
         }
-        if (use_tc) { const int rc_tc = launch_tc_bwd(pl, ta, ms, st); if (rc_tc != NCDE_OK) return rc_tc; }
-        else if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
-        else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, st, fa));
+        if (use_tc) { const int rc_tc = launch_tc_bwd(pl, ta, ms, cur); if (rc_tc != NCDE_OK) return rc_tc; }
+        else if (pl.TM == 8) NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<8>, fg, dim3(kThreads), pl.bwd_smem, cur, fa));
+        else NCDE_CUDA_OK(launch_pdl(field_bwd_kernel<4>, fg, dim3(kThreads), pl.bwd_smem, cur, fa));
         hb.dz_out = ka[k_out];
-        NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, st, hb));
+        NCDE_CUDA_OK(launch_pdl(hidden_bwd_kernel, dim3(pl.n_rt), dim3(kThreads), pl.hid_smem_bwd, cur, hb));
         launches += 5;
         if (pl.F > 0) {
             for (int s2 = 0; s2 < wa.n_slots; ++s2) {
@@ -2430,14 +2522,14 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
                 wa.gW[s2] = ktheta[k_out] + tl.off_W[l0];
                 wa.gb[s2] = tl.off_b[l0] == (size_t)-1 ? nullptr : ktheta[k_out] + tl.off_b[l0];
             }
-            NCDE_CUDA_OK(launch_pdl(hidden_wgrad_kernel, dim3(total_tiles, pl.wg_split), dim3(kThreads), 0, st, wa));
+            NCDE_CUDA_OK(launch_pdl(hidden_wgrad_kernel, dim3(total_tiles, pl.wg_split), dim3(kThreads), 0, cur, wa));
             int nmax = 0;
             for (int s2 = 0; s2 < wa.n_slots; ++s2) nmax = wa.Dout[s2] * wa.Din[s2] > nmax ? wa.Dout[s2] * wa.Din[s2] : nmax;
-            hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, st>>>(wa);
+            hidden_wgrad_reduce_kernel<<<dim3((unsigned)ceil_div(nmax, 256), wa.n_slots), 256, 0, cur>>>(wa);
             launches += 2;
         }
         const int64_t n = (int64_t)pl.H * pl.C * pl.DF;
-        unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+        unpack_final_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, cur>>>(
             dW3acc, db3acc, ktheta[k_out] + tl.off_W[pl.F],
             tl.off_b[pl.F] == (size_t)-1 ? nullptr : ktheta[k_out] + tl.off_b[pl.F], pl.H, pl.C, pl.Cp, pl.Hg, pl.Npad, pl.DF,
             pl.DFP, pl.Np, pl.n_bt);
@@ -2447,17 +2539,17 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     // mixed-norm partial sums of the initial-step selection: mode 0 -> (s0, f0), mode 1 -> (f0, f1)
     auto norms = [&](int mode, int kb) -> int {
         const int kb0 = 0;
-        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)yT,
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, mode, (const float*)yT,
                                 (const float*)kf[kb0], (const float*)kf[kb], pl.B, pl.Bp, pl.H, partials + (size_t)0 * 2 * nblocks));
-        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)aT,
+        NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, mode, (const float*)aT,
                                 (const float*)ka[kb0], (const float*)ka[kb], pl.B, pl.Bp, pl.H, partials + (size_t)1 * 2 * nblocks));
         for (size_t i = 0; i < tsegs.size(); ++i)
-            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode,
+            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, mode,
                                     (const float*)(theta + tsegs[i].off), (const float*)(ktheta[kb0] + tsegs[i].off),
                                     (const float*)(ktheta[kb] + tsegs[i].off), (int)tsegs[i].n, (int)tsegs[i].n, 1,
                                     partials + (size_t)(2 + i) * 2 * nblocks));
         if (has_vt)
-            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, mode, (const float*)vts,
+            NCDE_CUDA_OK(launch_pdl(adapt_norm_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, mode, (const float*)vts,
                                     (const float*)kvt[kb0], (const float*)kvt[kb], 1, 1, 1, partials + (size_t)(n_seg - 1) * 2 * nblocks));
         launches += n_seg;
         return NCDE_OK;
@@ -2479,9 +2571,6 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
     NCDE_CUDA_OK(cudaMemsetAsync(theta, 0, tl.total * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(vts, 0, 64 * 4, st));
     NCDE_CUDA_OK(cudaMemsetAsync(ctrl, 0, sizeof(AdaptCtrl), st));
-
-    static int* h_done = nullptr;
-    if (!h_done) NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, sizeof(int), cudaHostAllocDefault));
 
     for (int64_t iv = 0; iv + 1 < n_out; ++iv) {
         const int64_t i_hi = n_out - 1 - iv;
@@ -2507,71 +2596,85 @@ extern "C" int ncde_solve_adjoint_adaptive_bwd(const ncde_problem_t* p, const fl
             NCDE_CUDA_OK(launch_pdl(aug_init_step2_kernel, dim3(1), dim3(32), 0, st, ca));
             launches += 2;
         }
-        int64_t enq = 0;
-        bool finished = false;
-        while (enq < ad.max_attempts && !finished) {
-            for (int c4 = 0; c4 < 4 && enq < ad.max_attempts; ++c4, ++enq) {
-                for (int i = 1; i <= 6; ++i) {
-                    rc = aeval(i, i, i == 6 ? y1T : nullptr);
+        auto attempt = [&](cudaStream_t q) -> int {
+            cur = q;
+            for (int i = 1; i <= 6; ++i) {
+                const int rc_e = aeval(i, i, i == 6 ? y1T : nullptr);
+                if (rc_e != NCDE_OK) { cur = st; return rc_e; }
+            }
+            // theta candidate = theta + sum_j beta_6j dt ktheta_j (the 7th stage input of the parameter component)
+            AugCombineArgs cb;
+            memset(&cb, 0, sizeof(cb));
+            cb.n = (int64_t)tl.total; cb.combine = COMBINE_LINEAR; cb.sign = 1.f; cb.base = theta; cb.out = theta1;
+            for (int j = 0; j < 7; ++j) cb.k[j] = ktheta[j];
+            cb.ctrl = ctrl; cb.tab_index = 6;
+            NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(th_grid), dim3(256), 0, cur, cb));
+            if (has_vt) {
+                cb.n = 1; cb.base = vts; cb.out = vts + 1;
+                for (int j = 0; j < 7; ++j) cb.k[j] = kvt[j];
+                NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(1), dim3(32), 0, cur, cb));
+                ++launches;
+            }
+            // error ratio per segment
+            NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, (const float*)yT,
+                                    (const float*)y1T, (const float*)kf[0], (const float*)kf[1], (const float*)kf[2],
+                                    (const float*)kf[3], (const float*)kf[4], (const float*)kf[5], (const float*)kf[6],
+                                    (int64_t)nHB, pl.Bp, pl.B, partials));
+            NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, (const float*)aT,
+                                    (const float*)a_stage, (const float*)ka[0], (const float*)ka[1], (const float*)ka[2],
+                                    (const float*)ka[3], (const float*)ka[4], (const float*)ka[5], (const float*)ka[6],
+                                    (int64_t)nHB, pl.Bp, pl.B, partials + (size_t)1 * 2 * nblocks));
+            for (size_t i = 0; i < tsegs.size(); ++i) {
+                const size_t o = tsegs[i].off;
+                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl,
+                                        (const float*)(theta + o), (const float*)(theta1 + o), (const float*)(ktheta[0] + o),
+                                        (const float*)(ktheta[1] + o), (const float*)(ktheta[2] + o), (const float*)(ktheta[3] + o),
+                                        (const float*)(ktheta[4] + o), (const float*)(ktheta[5] + o), (const float*)(ktheta[6] + o),
+                                        tsegs[i].n, 0, 0, partials + (size_t)(2 + i) * 2 * nblocks));
+            }
+            if (has_vt)
+                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, (const float*)vts,
+                                        (const float*)(vts + 1), (const float*)kvt[0], (const float*)kvt[1], (const float*)kvt[2],
+                                        (const float*)kvt[3], (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6],
+                                        (int64_t)1, 0, 0, partials + (size_t)(n_seg - 1) * 2 * nblocks));
+            NCDE_CUDA_OK(launch_pdl(aug_ctrl_kernel, dim3(1), dim3(32), 0, cur, ca));
+            NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, yT, (const float*)y1T,
+                                    kf[0], (const float*)kf[1], (const float*)kf[2], (const float*)kf[3], (const float*)kf[4],
+                                    (const float*)kf[5], (const float*)kf[6], (float*)nullptr, (int64_t)nHB, out_tau));
+            NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, aT, (const float*)a_stage,
+                                    ka[0], (const float*)ka[1], (const float*)ka[2], (const float*)ka[3], (const float*)ka[4],
+                                    (const float*)ka[5], (const float*)ka[6], a_out, (int64_t)nHB, out_tau));
+            NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(th_grid), dim3(256), 0, cur, (const AdaptCtrl*)ctrl, theta, (const float*)theta1,
+                                    ktheta[0], (const float*)ktheta[1], (const float*)ktheta[2], (const float*)ktheta[3],
+                                    (const float*)ktheta[4], (const float*)ktheta[5], (const float*)ktheta[6], theta_out,
+                                    (int64_t)tl.total, out_tau));
+            if (has_vt) {
+                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(1), dim3(32), 0, cur, (const AdaptCtrl*)ctrl, vts, (const float*)(vts + 1),
+                                        kvt[0], (const float*)kvt[1], (const float*)kvt[2], (const float*)kvt[3],
+                                        (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6], vts + 2, (int64_t)1, out_tau));
+                ++launches;
+            }
+            launches += 7 + n_seg;
+            cur = st;
+            return NCDE_OK;
+        };
+        if (!dopri_host_poll()) {
+            rc = graph_while_not_done(st, ctrl, attempt);     // device-side loop, no host synchronisation
+            if (rc != NCDE_OK) return rc;
+        } else {
+            static int* h_done = nullptr;
+            if (!h_done) NCDE_CUDA_OK(cudaHostAlloc((void**)&h_done, sizeof(int), cudaHostAllocDefault));
+            int64_t enq = 0;
+            bool finished = false;
+            while (enq < ad.max_attempts && !finished) {
+                for (int c4 = 0; c4 < 4 && enq < ad.max_attempts; ++c4, ++enq) {
+                    rc = attempt(st);
                     if (rc != NCDE_OK) return rc;
                 }
-                // theta candidate = theta + sum_j beta_6j dt ktheta_j (the 7th stage input of the parameter component)
-                AugCombineArgs cb;
-                memset(&cb, 0, sizeof(cb));
-                cb.n = (int64_t)tl.total; cb.combine = COMBINE_LINEAR; cb.sign = 1.f; cb.base = theta; cb.out = theta1;
-                for (int j = 0; j < 7; ++j) cb.k[j] = ktheta[j];
-                cb.ctrl = ctrl; cb.tab_index = 6;
-                NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(th_grid), dim3(256), 0, st, cb));
-                if (has_vt) {
-                    cb.n = 1; cb.base = vts; cb.out = vts + 1;
-                    for (int j = 0; j < 7; ++j) cb.k[j] = kvt[j];
-                    NCDE_CUDA_OK(launch_pdl(aug_combine_kernel, dim3(1), dim3(32), 0, st, cb));
-                    ++launches;
-                }
-                // error ratio per segment
-                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)yT,
-                                        (const float*)y1T, (const float*)kf[0], (const float*)kf[1], (const float*)kf[2],
-                                        (const float*)kf[3], (const float*)kf[4], (const float*)kf[5], (const float*)kf[6],
-                                        (int64_t)nHB, pl.Bp, pl.B, partials));
-                NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)aT,
-                                        (const float*)a_stage, (const float*)ka[0], (const float*)ka[1], (const float*)ka[2],
-                                        (const float*)ka[3], (const float*)ka[4], (const float*)ka[5], (const float*)ka[6],
-                                        (int64_t)nHB, pl.Bp, pl.B, partials + (size_t)1 * 2 * nblocks));
-                for (size_t i = 0; i < tsegs.size(); ++i) {
-                    const size_t o = tsegs[i].off;
-                    NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl,
-                                            (const float*)(theta + o), (const float*)(theta1 + o), (const float*)(ktheta[0] + o),
-                                            (const float*)(ktheta[1] + o), (const float*)(ktheta[2] + o), (const float*)(ktheta[3] + o),
-                                            (const float*)(ktheta[4] + o), (const float*)(ktheta[5] + o), (const float*)(ktheta[6] + o),
-                                            tsegs[i].n, 0, 0, partials + (size_t)(2 + i) * 2 * nblocks));
-                }
-                if (has_vt)
-                    NCDE_CUDA_OK(launch_pdl(aug_err_kernel, dim3(nblocks), dim3(256), 0, st, (const AdaptCtrl*)ctrl, (const float*)vts,
-                                            (const float*)(vts + 1), (const float*)kvt[0], (const float*)kvt[1], (const float*)kvt[2],
-                                            (const float*)kvt[3], (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6],
-                                            (int64_t)1, 0, 0, partials + (size_t)(n_seg - 1) * 2 * nblocks));
-                NCDE_CUDA_OK(launch_pdl(aug_ctrl_kernel, dim3(1), dim3(32), 0, st, ca));
-                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, yT, (const float*)y1T,
-                                        kf[0], (const float*)kf[1], (const float*)kf[2], (const float*)kf[3], (const float*)kf[4],
-                                        (const float*)kf[5], (const float*)kf[6], (float*)nullptr, (int64_t)nHB, out_tau));
-                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(ew_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, aT, (const float*)a_stage,
-                                        ka[0], (const float*)ka[1], (const float*)ka[2], (const float*)ka[3], (const float*)ka[4],
-                                        (const float*)ka[5], (const float*)ka[6], a_out, (int64_t)nHB, out_tau));
-                NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(th_grid), dim3(256), 0, st, (const AdaptCtrl*)ctrl, theta, (const float*)theta1,
-                                        ktheta[0], (const float*)ktheta[1], (const float*)ktheta[2], (const float*)ktheta[3],
-                                        (const float*)ktheta[4], (const float*)ktheta[5], (const float*)ktheta[6], theta_out,
-                                        (int64_t)tl.total, out_tau));
-                if (has_vt) {
-                    NCDE_CUDA_OK(launch_pdl(aug_accept_kernel, dim3(1), dim3(32), 0, st, (const AdaptCtrl*)ctrl, vts, (const float*)(vts + 1),
-                                            kvt[0], (const float*)kvt[1], (const float*)kvt[2], (const float*)kvt[3],
-                                            (const float*)kvt[4], (const float*)kvt[5], (const float*)kvt[6], vts + 2, (int64_t)1, out_tau));
-                    ++launches;
-                }
-                launches += 7 + n_seg;
+                NCDE_CUDA_OK(cudaMemcpyAsync(h_done, &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+                NCDE_CUDA_OK(cudaStreamSynchronize(st));
+                finished = *h_done != 0;
             }
-            NCDE_CUDA_OK(cudaMemcpyAsync(h_done, &ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-            NCDE_CUDA_OK(cudaStreamSynchronize(st));
-            finished = *h_done != 0;
         }
         // interval end (adjoint.py:131-133): adjoint and parameter gradients from the dense output at t_{i-1}, the state
         // from the stored forward solution, plus the gradient arriving at t_{i-1}
