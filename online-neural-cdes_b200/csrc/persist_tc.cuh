@@ -274,40 +274,58 @@ __host__ __device__ inline int ps_hid_fwd_nop(int NSP, int F) {
 // ---------------------------------------------------------------------------------------------------------------
 // forward, field role
 // ---------------------------------------------------------------------------------------------------------------
-// what the forward epilogue does with one finished k[b, h] of global stage q (cf. tc_fwd_finish_element)
+// The RK state this thread's (row, h) entry needs when its k is finished: read at the START of the unit (the values were written
+// by this same thread in earlier units), so that the L2 latency hides behind the accumulator read-out instead of sitting between
+// the last chunk and the hand-off.
+struct PsFwdState { float y, k0, k1, k2; };
+__device__ __forceinline__ PsFwdState ps_fwd_state_load(const PsArgs& a, int s, int ist, int h, int64_t b) {
+    PsFwdState v;
+    const size_t off = (size_t)h * a.Bp + b;
+    v.y = a.yT[s & 1][off];
+    v.k0 = ist >= 1 ? a.kT[0][off] : 0.f;
+    v.k1 = ist >= 2 ? a.kT[1][off] : 0.f;
+    v.k2 = ist >= 3 ? a.kT[2][off] : 0.f;
+    return v;
+}
+// what the forward epilogue does with one finished k[b, h] of global stage q (cf. tc_fwd_finish_element; reference operation
+// order of rk_common.py:106-114, no FMA contraction)
 template <int NSP>
-__device__ __forceinline__ void ps_fwd_finish_element(const PsArgs& a, int q, int s, int ist, float dt, int emit_slot, int h, int64_t b, float k) {
+__device__ __forceinline__ void ps_fwd_finish_element(const PsArgs& a, const PsFwdState& v, int q, int s, int ist, float dt, int emit_slot,
+                                                      int h, int64_t b, float k) {
     const size_t off = (size_t)h * a.Bp + b;
     const int cur = s & 1;
-    const float* yT = a.yT[cur];
+    const float third = 0.3333333432674408f;
     a.kT[ist][off] = k;
     const size_t part_stride = (size_t)a.Bp * 128;
+    float znext;
+    bool have_next;
     if (ist + 1 < a.NS) {
-        // input of the next stage of this step (rk_common.py:106-114)
-        const int combine = a.method == NCDE_RK4_38 ? (ist + 1) : COMBINE_Y;   // COMBINE_RK4_S2.. = 1..3
-        const float z = __fadd_rn(yT[off], stage_increment(combine, dt, a.kT, nullptr, off));
-        __nv_bfloat16* zr = a.rec0 + (a.need_grad ? (size_t)(q + 1) * a.rec_stride : 0) + a.act_off[0] + (size_t)b * 128 + h;
-        const __nv_bfloat16 hi = __float2bfloat16(z);
-        zr[0] = hi;
-        if (NSP == 2) zr[part_stride] = __float2bfloat16(z - __bfloat162float(hi));
+        // input of the next stage of this step: stage i+1 reads k_1 .. k_{i+1}, of which k_{i+1} is the value just finished
+        float inc;
+        if (ist == 0) inc = __fmul_rn(__fmul_rn(dt, k), third);                                   // dt * k1 * (1/3)
+        else if (ist == 1) inc = __fmul_rn(dt, __fsub_rn(k, __fmul_rn(v.k0, third)));             // dt * (k2 - k1 * (1/3))
+        else inc = __fmul_rn(dt, __fadd_rn(__fsub_rn(v.k0, v.k1), k));                            // dt * (k1 - k2 + k3)
+        znext = __fadd_rn(v.y, inc);
+        have_next = true;
     } else {
-        const float y = yT[off];
         float yn;
         if (a.method == NCDE_RK4_38) {   // (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
-            float sm = __fadd_rn(a.kT[0][off], __fmul_rn(3.f, __fadd_rn(a.kT[1][off], a.kT[2][off])));
+            float sm = __fadd_rn(v.k0, __fmul_rn(3.f, __fadd_rn(v.k1, v.k2)));
             sm = __fadd_rn(sm, k);
-            yn = __fadd_rn(y, __fmul_rn(__fmul_rn(sm, dt), 0.125f));
+            yn = __fadd_rn(v.y, __fmul_rn(__fmul_rn(sm, dt), 0.125f));
         } else {
-            yn = __fadd_rn(y, __fmul_rn(dt, k));
+            yn = __fadd_rn(v.y, __fmul_rn(dt, k));
         }
         a.yT[cur ^ 1][off] = yn;
-        if (s + 1 < a.n_steps) {
-            __nv_bfloat16* zr = a.rec0 + (a.need_grad ? (size_t)(q + 1) * a.rec_stride : 0) + a.act_off[0] + (size_t)b * 128 + h;
-            const __nv_bfloat16 hi = __float2bfloat16(yn);
-            zr[0] = hi;
-            if (NSP == 2) zr[part_stride] = __float2bfloat16(yn - __bfloat162float(hi));
-        }
         if (emit_slot >= 0) a.z_out[((size_t)emit_slot * a.B + b) * a.H + h] = yn;
+        znext = yn;
+        have_next = s + 1 < a.n_steps;
+    }
+    if (have_next) {
+        __nv_bfloat16* zr = a.rec0 + (a.need_grad ? (size_t)(q + 1) * a.rec_stride : 0) + a.act_off[0] + (size_t)b * 128 + h;
+        const __nv_bfloat16 hi = __float2bfloat16(znext);
+        zr[0] = hi;
+        if (NSP == 2) zr[part_stride] = __float2bfloat16(znext - __bfloat162float(hi));
     }
 }
 
@@ -445,6 +463,10 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const int hl = h_begin + p;
                 const bool pass_ok = hl < h_end;
                 const int colbase = hl * a.Cp;
+                const int h_out = a.Hg >= 2 ? g * a.Hg + hl : g;
+                const bool writes = row_ok && h_out < a.H && (a.Hg >= 2 ? pass_ok : wg == 1);
+                PsFwdState sv = {0.f, 0.f, 0.f, 0.f};
+                if (writes) sv = ps_fwd_state_load(a, s, ist, h_out, b0 + row);
                 float acc = 0.f;
                 for (int j = 0; j < xq.nch; ++j) {
                     ps_wait(x_full + slot, lap & 1u);
@@ -470,12 +492,11 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     if (++slot == NX) { slot = 0; ++lap; }
                 }
                 if (a.Hg >= 2) {
-                    const int h = g * a.Hg + hl;
-                    if (pass_ok && h < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, h, b0 + row, acc);
+                    if (writes) ps_fwd_finish_element<NSP>(a, sv, u.q, s, ist, dt, emit_slot, h_out, b0 + row, acc);
                 } else {
                     if (wg == 0) partial[row] = acc;
                     named_bar_sync(1, kPsEpi);
-                    if (wg == 1 && g < a.H && row_ok) ps_fwd_finish_element<NSP>(a, u.q, s, ist, dt, emit_slot, g, b0 + row, acc + partial[row]);
+                    if (writes) ps_fwd_finish_element<NSP>(a, sv, u.q, s, ist, dt, emit_slot, h_out, b0 + row, acc + partial[row]);
                     named_bar_sync(1, kPsEpi);
                 }
             }

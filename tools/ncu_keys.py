@@ -13,12 +13,18 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
-res = {"kernel": vals[col["Kernel Name"]]}
-for k in KEYS:
-    if k in col:
-        res[k] = (vals[col[k]] + " " + units[col[k]]).strip()
+allres = []
+for vals in rows[2:]:
+    if len(vals) != len(hdr):
+        continue
+    r = {"kernel": vals[col["Kernel Name"]]}
+    for k in KEYS:
+        if k in col:
+            r[k] = (vals[col[k]] + " " + units[col[k]]).strip()
+    allres.append(r)
+res = allres[0] if len(allres) == 1 else {"kernels": allres}
 print(json.dumps(res, indent=1))
 if dst:
     json.dump(res, open(dst, "w"), indent=1)
