@@ -149,14 +149,31 @@ __device__ __forceinline__ float ps_sech2(float x) {
     return fmaf(-y, y, 1.f);
 }
 
+// MMA issue is done by ONE thread: every instruction it spends per tcgen05.mma is serial latency of the whole CTA (bf16x3 issues 45
+// MMAs per backward unit).  Descriptors are therefore built once per operand and advanced by adding the 16-byte-granular offset to
+// their address field (shared-memory addresses stay below 2^18, so the 14-bit field cannot carry), inside fully unrolled loops.
+__device__ __forceinline__ uint64_t ps_desc_advance(uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); }
+// D[128 x N] (+)= A[128 x 128] . B[N x 128]^T, both operands K-major swizzled tiles of two 64-column blocks; `first` clears D
+__device__ __forceinline__ void ps_issue_kmajor(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, int b_rows, int N, bool first) {
+    const uint32_t idesc = make_idesc(kTcM, N, 0, 0);
+    const uint64_t ad = make_sdesc(a_saddr, 16, 1024), bd = make_sdesc(b_saddr, 16, 1024);
+    const uint32_t b_blk = (uint32_t)b_rows * 128u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t ao = (uint32_t)(k >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(k & 3) * 32u;
+        const uint32_t bo = (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
+        umma_bf16(d_tmem, ps_desc_advance(ad, ao), ps_desc_advance(bd, bo), idesc, (k > 0 || !first) ? 1u : 0u);
+    }
+}
 // D[128 x N] (+)= A . B^T for NSP-part operands, both K-major swizzled tiles [rows][128] (two 64-column blocks): hi*hi (+ lo*hi + hi*lo)
 template <int NSP>
 __device__ __forceinline__ void ps_gemm_kmajor(uint32_t d_tmem, uint32_t a_s, uint32_t a_part_bytes, int a_rows, uint32_t b_s,
                                                uint32_t b_part_bytes, int b_rows, int N) {
-    issue_gemm_kmajor(d_tmem, a_s, a_rows, b_s, b_rows, N, kTcKP, false);
+    (void)a_rows;
+    ps_issue_kmajor(d_tmem, a_s, b_s, b_rows, N, true);
     if (NSP == 2) {
-        issue_gemm_kmajor(d_tmem, a_s + a_part_bytes, a_rows, b_s, b_rows, N, kTcKP, true);
-        issue_gemm_kmajor(d_tmem, a_s, a_rows, b_s + b_part_bytes, b_rows, N, kTcKP, true);
+        ps_issue_kmajor(d_tmem, a_s + a_part_bytes, b_s, b_rows, N, false);
+        ps_issue_kmajor(d_tmem, a_s, b_s + b_part_bytes, b_rows, N, false);
     }
 }
 
@@ -826,6 +843,16 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
                 tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
             }
+            // The saved records are cold (1-2 GB written by the forward pass): the tile of unit i+1 is pulled into L2 while unit i is
+            // being worked on, so that its TMA — which can only start when wgrad(i) has released the buffer — is an L2 hit.
+            auto prefetch_A = [&](int i) {
+                if (i >= n_units) return;
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                const int rows = min(kTcM, a.B - u.t * kTcM);
+                for (int p = 0; p < NSP; ++p)
+                    l2_prefetch_bulk(a.rec0 + (size_t)u.q * a.rec_stride + a.act_off[a.F] + (size_t)p * a.Bp * 128 + (size_t)u.t * kTcM * 128,
+                                     (uint32_t)rows * 256u);
+            };
             auto load_A = [&](int i) {
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 mbar_expect_tx(full_a, (uint32_t)NSP * kTcHidTile);
@@ -833,6 +860,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
                     tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
                 }
+                prefetch_A(i + 1);
             };
             load_A(0);
             ps_wait(w_bar, 0);
@@ -857,26 +885,31 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 tc_fence_after();
                 {   // dgrad: D[128 x KP] = G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows)
                     const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
-                    bool first = true;
+                    const int nks = Npad / 16;
+#pragma unroll
                     for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
-                        const uint32_t g_s = Gs_s + (pr == 1 ? L.g_part : 0u), w_s = Ws_s + (pr == 2 ? w_part : 0u);
-                        for (int ks = 0; ks < Npad / 16; ++ks) {
+                        const uint64_t gd = make_sdesc(Gs_s + (pr == 1 ? L.g_part : 0u), 16, 1024);
+                        const uint64_t wd = make_sdesc(Ws_s + (pr == 2 ? w_part : 0u), (uint32_t)Npad * 128u, 1024);
+#pragma unroll 4
+                        for (int ks = 0; ks < nks; ++ks) {
                             const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                            umma_bf16(tmem_base + p_col, make_sdesc(g_s + a_off, 16, 1024), make_sdesc(w_s + (uint32_t)ks * 2048u, (uint32_t)Npad * 128u, 1024),
-                                      idesc, first ? 0u : 1u);
-                            first = false;
+                            umma_bf16(tmem_base + p_col, ps_desc_advance(gd, a_off), ps_desc_advance(wd, (uint32_t)ks * 2048u), idesc,
+                                      (pr > 0 || ks > 0) ? 1u : 0u);
                         }
                     }
                 }
                 umma_commit(dg_bar);
                 {   // wgrad: D[KP x Npad] += A^T (MN-major: M = k contiguous, K = m rows) . G (MN-major: N = n contiguous)
                     const uint32_t idesc = make_idesc(KP, Npad, 1, 1);
+#pragma unroll
                     for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
-                        const uint32_t a_s = As_s + (pr == 1 ? kTcHidTile : 0u), g_s = Gs_s + (pr == 2 ? L.g_part : 0u);
+                        const uint64_t ad = make_sdesc(As_s + (pr == 1 ? kTcHidTile : 0u), (uint32_t)kTcM * 128u, 1024);
+                        const uint64_t gd = make_sdesc(Gs_s + (pr == 2 ? L.g_part : 0u), (uint32_t)kTcM * 128u, 1024);
+#pragma unroll
                         for (int ks = 0; ks < kTcM / 16; ++ks) {
                             const uint32_t off = (uint32_t)ks * 2048u;
-                            umma_bf16(tmem_base + kTcDwCol, make_sdesc(a_s + off, (uint32_t)kTcM * 128u, 1024),
-                                      make_sdesc(g_s + off, (uint32_t)kTcM * 128u, 1024), idesc, (ks > 0 || pr > 0 || i > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + kTcDwCol, ps_desc_advance(ad, off), ps_desc_advance(gd, off), idesc,
+                                      (ks > 0 || pr > 0 || i > 0) ? 1u : 0u);
                         }
                     }
                 }
@@ -906,6 +939,11 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             uint32_t lap = 0;          // completed laps of the ring
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                if (i + 1 < n_units) {   // next unit's dX/dt tile (cold, contiguous rows) -> L2
+                    const PsUnit un = ps_unit_bwd(i + 1, n_my, part, a.n_part, n_q);
+                    const int rows = min(kTcM, a.B - un.t * kTcM);
+                    l2_prefetch_bulk(a.dx0 + (size_t)un.q * a.dx_stride + (size_t)un.t * kTcM * a.Cp, (uint32_t)rows * a.Cp * 4u);
+                }
                 for (int p = 0; p < xq.n_pass; ++p)
                     for (int j = 0; j < xq.nch; ++j) {
                         if (lap > 0) ps_wait(x_free + slot, (lap - 1) & 1u);
@@ -1176,14 +1214,15 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     {   // dgrad: D[128 b x 128 i] = dpre_l (K-major over o) . W_l (MN-major: N = i contiguous, K = o rows)
                         const uint32_t idesc = make_idesc(kTcM, 128, 0, 1);
                         const uint32_t d_s = smem_u32(d_tile), w_s = smem_u32(Wt + (size_t)buf * kOp);
-                        bool first = true;
+#pragma unroll
                         for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
-                            const uint32_t ds = d_s + (pr == 1 ? kTcHidTile : 0u), ws = w_s + (pr == 2 ? kTcHidTile : 0u);
+                            const uint64_t dd = make_sdesc(d_s + (pr == 1 ? kTcHidTile : 0u), 16, 1024);
+                            const uint64_t wd = make_sdesc(w_s + (pr == 2 ? kTcHidTile : 0u), 128u * 128u, 1024);
+#pragma unroll
                             for (int ks = 0; ks < 8; ++ks) {
                                 const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                                umma_bf16(tmem_base, make_sdesc(ds + a_off, 16, 1024), make_sdesc(ws + (uint32_t)ks * 2048u, 128u * 128u, 1024), idesc,
-                                          first ? 0u : 1u);
-                                first = false;
+                                umma_bf16(tmem_base, ps_desc_advance(dd, a_off), ps_desc_advance(wd, (uint32_t)ks * 2048u), idesc,
+                                          (pr > 0 || ks > 0) ? 1u : 0u);
                             }
                         }
                     }
