@@ -23,7 +23,8 @@
 
 namespace ncde {
 
-constexpr int kPsThreads = 352;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), 9 = signaller, 10 = dX/dt loader
+constexpr int kPsThreads = 384;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), 9 = signaller, 10 = dX/dt loader,
+                                          // 11 = dL/dk former of the backward field role (idle elsewhere)
 constexpr int kPsEpi = 256;
 constexpr long long kPsSpinLimit = 6000000000ll;   // ~3 s at 2 GHz: a protocol error traps instead of hanging the GPU
 
@@ -61,14 +62,29 @@ struct PsArgs {
     // synchronisation words (zeroed before the launch)
     int* cnt_f;                 // [n_mt] field -> hidden: arrivals of field CTAs (monotonic)
     int* flag_h;                // [n_mt] hidden -> field: stages completed by the hidden CTA (monotonic)
-    unsigned long long* trace;  // debug (NCDE_PS_TRACE): [stage][16] globaltimer stamps of tile 0's hand-offs, or null
+    unsigned long long* trace;  // debug (NCDE_PS_TRACE): [stage][tile < 8][24] globaltimer stamps of the hand-offs of h-group trace_g, or null
+    int trace_g;
 };
-constexpr int kPsTraceStages = 48;
-__device__ __forceinline__ void ps_trace(const PsArgs& a, int t, int g, int q, int ev) {
-    if (a.trace && t == 0 && g == 0 && q < kPsTraceStages) {
+constexpr int kPsTraceStages = 48, kPsTraceTiles = 8, kPsTraceEv = 40;
+// second trace area (after the first): stamps of EVERY h-group for one (stage, tile): [g < 256][8]
+constexpr int kPsTraceAllStage = 40, kPsTraceAllTile = 0;
+__device__ __forceinline__ void ps_trace_all(const PsArgs& a, int t, int g, int q, int ev) {
+    if (a.trace && q == kPsTraceAllStage && t == kPsTraceAllTile && g >= 0 && g < 256) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        a.trace[q * 16 + ev] = ns;
+        a.trace[kPsTraceStages * kPsTraceTiles * kPsTraceEv + g * 8 + ev] = ns;
+        if (ev == 1) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.trace[kPsTraceStages * kPsTraceTiles * kPsTraceEv + g * 8 + 7] = smid + 1;
+        }
+    }
+}
+__device__ __forceinline__ void ps_trace(const PsArgs& a, int t, int g, int q, int ev) {
+    if (a.trace && t < kPsTraceTiles && (g == a.trace_g || g < 0) && q < kPsTraceStages) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        a.trace[(q * kPsTraceTiles + t) * kPsTraceEv + ev] = ns;
     }
 }
 
@@ -85,19 +101,30 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#ifdef NCDE_PS_DBG_PRINT
+#include <cassert>
+__device__ uint32_t g_ps_dbg_bars;      // shared-memory address of the barrier array of the (last initialised) field role
+#define PS_TRAP(what, v0_, v1_) do { printf("PS TIMEOUT %s blk %d tid %d : %d %d\n", what, (int)blockIdx.x, (int)threadIdx.x, (int)(v0_), (int)(v1_)); assert(0); } while (0)
+#else
+#define PS_TRAP(what, v0_, v1_) __trap()
+#endif
 __device__ __forceinline__ void ps_spin_ge(const int* p, int target) {
     if (ld_acquire_gpu(p) >= target) return;
     const long long t0 = clock64();
     while (ld_acquire_gpu(p) < target) {
         __nanosleep(20);
-        if (clock64() - t0 > kPsSpinLimit) __trap();
+        if (clock64() - t0 > kPsSpinLimit) PS_TRAP("spin", target, ld_acquire_gpu(p));
     }
 }
 // bounded mbarrier wait (same reason: trap, never hang)
 __device__ __forceinline__ void ps_wait(uint64_t* bar, uint32_t parity) {
     uint32_t n = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef NCDE_PS_DBG_PRINT
+        if (++n > 4000000u) PS_TRAP("mbar", ((int)smem_u32(bar) - (int)g_ps_dbg_bars) / 8, parity);
+#else
         if (++n > 40000000u) __trap();
+#endif
     }
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -149,6 +176,27 @@ __device__ __forceinline__ float ps_sech2(float x) {
     return fmaf(-y, y, 1.f);
 }
 
+// The producer warp can run CONVERGED (NCDE_PS_CONVERGED=1 at build time): all 32 lanes execute the loops and the waits, and each
+// single-thread instruction (tcgen05.mma, tcgen05.commit, TMA, mbarrier arrive) is issued under elect.sync, as cute's atoms do; that
+// removes the ELECT / R2UR / branch waterfall ptxas wraps around a tcgen05.mma issued from a divergent `if (lane == 0)` region.
+// Measured on cfg 5 it does NOT pay: MMA issue is back-pressured by MMA execution either way (24 MMAs of M128 N112 K16 take
+// 0.86 us in both forms: ~70 cycles each, the shared-memory operand bandwidth), and the converged form was 5 % slower overall
+// (bf16x3 backward 44.8 vs 42.2 ms).  Default: one lane runs the producer loop.
+#ifndef NCDE_PS_CONVERGED
+#define NCDE_PS_CONVERGED 0
+#endif
+constexpr bool kPsConverged = NCDE_PS_CONVERGED != 0;
+__device__ __forceinline__ bool ps_elect() {
+    if (!kPsConverged) return true;
+    uint32_t p;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void ps_syncwarp() { if (kPsConverged) __syncwarp(); }
+#define PS_LEAD(...) do { if (ps_elect()) { __VA_ARGS__; } } while (0)
+__device__ __forceinline__ void ps_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (ps_elect()) umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+}
 // MMA issue is done by ONE thread: every instruction it spends per tcgen05.mma is serial latency of the whole CTA (bf16x3 issues 45
 // MMAs per backward unit).  Descriptors are therefore built once per operand and advanced by adding the 16-byte-granular offset to
 // their address field (shared-memory addresses stay below 2^18, so the 14-bit field cannot carry), inside fully unrolled loops.
@@ -162,7 +210,7 @@ __device__ __forceinline__ void ps_issue_kmajor(uint32_t d_tmem, uint32_t a_sadd
     for (int k = 0; k < 8; ++k) {
         const uint32_t ao = (uint32_t)(k >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(k & 3) * 32u;
         const uint32_t bo = (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
-        umma_bf16(d_tmem, ps_desc_advance(ad, ao), ps_desc_advance(bd, bo), idesc, (k > 0 || !first) ? 1u : 0u);
+        ps_umma(d_tmem, ps_desc_advance(ad, ao), ps_desc_advance(bd, bo), idesc, (k > 0 || !first) ? 1u : 0u);
     }
 }
 // D[128 x N] (+)= A . B^T for NSP-part operands, both K-major swizzled tiles [rows][128] (two 64-column blocks): hi*hi (+ lo*hi + hi*lo)
@@ -183,6 +231,15 @@ __device__ __forceinline__ void ps_gemm_kmajor(uint32_t d_tmem, uint32_t a_s, ui
 constexpr int kPsXPitch = 36;
 constexpr uint32_t kPsXSlot = kTcM * kPsXPitch * 4;     // 18432 bytes
 constexpr int kPsMaxSlots = 8;
+// Backward field role with ONE hidden row per h-group (bf16x3 on wide fields: shared memory leaves room for two wide slots only, and a
+// ring without depth exposes the TMA latency of every refill): 16-channel chunks, pitch 20 floats (80 bytes: still conflict-free for the
+// per-row LDS.128), chunk j worked on by warp group j & 1 — the two groups walk the ring together, so a slot is free as soon as its chunk
+// is done, and twice as many slots fit.
+constexpr int kPsXPitchN = 20;
+constexpr uint32_t kPsXSlotN = kTcM * kPsXPitchN * 4;   // 10240 bytes
+__host__ __device__ inline bool ps_bwd_narrow(int Hg) { return Hg == 1; }
+__host__ __device__ inline int ps_bwd_xw(int Hg) { return ps_bwd_narrow(Hg) ? 16 : 32; }
+__host__ __device__ inline uint32_t ps_bwd_xslot(int Hg) { return ps_bwd_narrow(Hg) ? kPsXSlotN : kPsXSlot; }
 
 // 16 accumulator columns of TMEM lane `row` in flight
 struct PsHalf { uint32_t r[16]; };
@@ -367,7 +424,7 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* x_full = bars + 10;     // [NX <= 8]
     uint64_t* x_free = bars + 18;     // [NX <= 8]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform
     const uint32_t acc_stride = tc_tmem_cols(Npad);
     const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
     const int n_q = a.n_steps * a.NS;
@@ -389,37 +446,47 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        if (lane == 0 && n_units > 0) {
-            tma_prefetch_desc(&maps.act[a.F]);
-            mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
-            for (int p = 0; p < NSP; ++p) {
-                tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
-                tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+        if ((kPsConverged || lane == 0) && n_units > 0) {     // see ps_elect
+            if (ps_elect()) {
+                tma_prefetch_desc(&maps.act[a.F]);
+                mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
+                    tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+                }
             }
+            ps_syncwarp();
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_fwd(i, n_my, part, a.n_part);
                 const int b = i & 1, ba = NA == 2 ? b : 0;
                 if (i >= NA) ps_wait(mma_bar + ((i - NA) & 1), (uint32_t)((i - NA) >> 1) & 1u);   // activation buffer free
-                ps_spin_ge(a.flag_h + u.t, u.q + 1);            // the hidden CTA has written the tile's final-layer input of stage q
-                ps_trace(a, u.t, g, u.q, 0);
+                if (lane == 0) {
+                    ps_spin_ge(a.flag_h + u.t, u.q + 1);        // the hidden CTA has written the tile's final-layer input of stage q
+                    ps_trace(a, u.t, g, u.q, 0);
+                }
+                ps_syncwarp();
                 fence_proxy_async_all();
                 uint8_t* dst = As + (size_t)ba * NSP * kTcHidTile;
                 const int rec = a.need_grad ? u.q : 0;
-                mbar_expect_tx(full_a + ba, (uint32_t)NSP * kTcHidTile);
-                for (int p = 0; p < NSP; ++p) {
-                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.act[a.F], full_a + ba, 0, u.t * kTcM, p, rec);
-                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a + ba, 64, u.t * kTcM, p, rec);
+                if (ps_elect()) {
+                    mbar_expect_tx(full_a + ba, (uint32_t)NSP * kTcHidTile);
+                    for (int p = 0; p < NSP; ++p) {
+                        tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.act[a.F], full_a + ba, 0, u.t * kTcM, p, rec);
+                        tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a + ba, 64, u.t * kTcM, p, rec);
+                    }
                 }
+                ps_syncwarp();
                 if (i >= 2) {
                     ps_wait(done + b, (uint32_t)((i - 2) >> 1) & 1u);        // accumulator b drained by the epilogue of unit i-2
                     while (*sig_done < i - 1) {}                              // ... and that unit was signalled (keeps the signaller in phase)
                 }
                 if (i == 0) ps_wait(w_bar, 0);
                 ps_wait(full_a + ba, (uint32_t)(i / NA) & 1u);
-                ps_trace(a, u.t, g, u.q, 1);
+                if (lane == 0) ps_trace(a, u.t, g, u.q, 1);
                 tc_fence_after();
                 ps_gemm_kmajor<NSP>(tmem_base + (uint32_t)b * acc_stride, smem_u32(dst), kTcHidTile, kTcM, smem_u32(Ws), w_part, Npad, Npad);
-                umma_commit(mma_bar + b);
+                PS_LEAD(umma_commit(mma_bar + b));
+                ps_syncwarp();
             }
         }
     } else if (warp == 9) {
@@ -449,7 +516,7 @@ __device__ void ps_field_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     }
             }
         }
-    } else {
+    } else if (warp < 8) {
         const int wg = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
         const int h_begin = a.Hg >= 2 ? (wg == 0 ? 0 : a.Hg / 2) : 0;
@@ -550,7 +617,7 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     uint64_t* a_ready = bars + 10;    // epilogue -> producer: output of the layer written over the operand tile (8 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform
     const int F = a.F;
     const int n_my = j < a.n_mt ? (a.n_mt - j + a.n_hid - 1) / a.n_hid : 0;
     const int n_q = a.n_steps * a.NS;
@@ -569,24 +636,30 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        if (lane == 0 && n_units > 0) {
+        if ((kPsConverged || lane == 0) && n_units > 0) {     // see ps_elect
             auto load_W = [&](int l, int buf) {
                 uint8_t* dst = Wt + (size_t)buf * kOp;
-                mbar_expect_tx(w_full + buf, kOp);
-                for (int p = 0; p < NSP; ++p) {
-                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
-                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                if (ps_elect()) {
+                    mbar_expect_tx(w_full + buf, kOp);
+                    for (int p = 0; p < NSP; ++p) {
+                        tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
+                        tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                    }
                 }
+                ps_syncwarp();
             };
             auto store_A = [&](int l, int b0, int rec) {   // the operand tile = input of layer l -> its record
                 const uint8_t* src = At + (size_t)((l & 1) % n_op) * kOp;
-                for (int p = 0; p < NSP; ++p) {
-                    tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile, 0, b0, p, rec);
-                    tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, rec);
+                if (ps_elect()) {
+                    for (int p = 0; p < NSP; ++p) {
+                        tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile, 0, b0, p, rec);
+                        tma_store_4d(&maps.act[l], src + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, rec);
+                    }
+                    bulk_commit();
                 }
-                bulk_commit();
+                ps_syncwarp();
             };
-            tma_prefetch_desc(&maps.act[0]);
+            PS_LEAD(tma_prefetch_desc(&maps.act[0]));
             if (resident) { for (int l = 0; l < F; ++l) load_W(l, l); }
             else { for (int w = 0; w < NW && w < F; ++w) load_W(w, w); }     // uses 0 .. NW-1 of the first unit
             int use = 0;               // layer uses so far (ring position when streaming)
@@ -594,17 +667,23 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 const int q = i / n_my, t = j + (i - q * n_my) * a.n_hid;
                 const int b0 = t * kTcM;
                 const int rec = a.need_grad ? q : 0;
-                if (q > 0) ps_spin_ge(a.cnt_f + t, a.n_hg * q);      // every h-group wrote its columns of the stage input
-                ps_trace(a, t, 0, q, 5);
-                fence_proxy_async_all();
-                bulk_wait_read<0>();      // no record store of the previous unit still reads the first tile
-                mbar_expect_tx(a_full, kOp);
-                for (int p = 0; p < NSP; ++p) {
-                    tma_load_4d(At + (size_t)p * kTcHidTile, &maps.act[0], a_full, 0, b0, p, rec);
-                    tma_load_4d(At + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[0], a_full, 64, b0, p, rec);
+                if (lane == 0) {
+                    if (q > 0) ps_spin_ge(a.cnt_f + t, a.n_hg * q);      // every h-group wrote its columns of the stage input
+                    ps_trace(a, t, -1, q, 5);
                 }
+                ps_syncwarp();
+                fence_proxy_async_all();
+                if (ps_elect()) {
+                    bulk_wait_read<0>();      // no record store of the previous unit still reads the first tile
+                    mbar_expect_tx(a_full, kOp);
+                    for (int p = 0; p < NSP; ++p) {
+                        tma_load_4d(At + (size_t)p * kTcHidTile, &maps.act[0], a_full, 0, b0, p, rec);
+                        tma_load_4d(At + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[0], a_full, 64, b0, p, rec);
+                    }
+                }
+                ps_syncwarp();
                 for (int l = 0; l < F; ++l, ++use) {
-                    if (l == 0) { ps_wait(a_full, (uint32_t)i & 1u); ps_trace(a, t, 0, q, 6); }
+                    if (l == 0) { ps_wait(a_full, (uint32_t)i & 1u); if (lane == 0) ps_trace(a, t, -1, q, 6); }
                     else {
                         ps_wait(a_ready, (uint32_t)(i * F + l - 1) & 1u);
                         if (a.need_grad) store_A(l, b0, rec);
@@ -617,8 +696,11 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                                         smem_u32(Wt + (size_t)buf * kOp), kTcHidTile, 128, 128);
                     // the epilogue of this layer writes tile (l+1)&1: one buffer -> the record store just issued reads it; two buffers ->
                     // the store of the previous layer does
-                    if (n_op == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
-                    umma_commit(mma_bar);
+                    if (ps_elect()) {
+                        if (n_op == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+                        umma_commit(mma_bar);
+                    }
+                    ps_syncwarp();
                     if (!resident) {
                         const int64_t total_uses = (int64_t)n_units * F;
                         if ((int64_t)use + NW < total_uses) {
@@ -629,11 +711,14 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 }
                 ps_wait(a_ready, (uint32_t)(i * F + F - 1) & 1u);     // input of the final layer written
                 store_A(F, b0, rec);
-                bulk_wait<0>();                                        // ... and complete in global memory
-                ps_trace(a, t, 0, q, 11);
-                fence_proxy_async_all();
-                st_release_gpu(a.flag_h + t, q + 1);
-                ps_trace(a, t, 0, q, 12);
+                if (ps_elect()) {
+                    bulk_wait<0>();                                    // ... and complete in global memory
+                    ps_trace(a, t, -1, q, 11);
+                    fence_proxy_async_all();
+                    st_release_gpu(a.flag_h + t, q + 1);
+                    ps_trace(a, t, -1, q, 12);
+                }
+                ps_syncwarp();
             }
         }
     } else if (warp < 8) {
@@ -645,7 +730,7 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
             const int q = i / n_my, t = j + (i - q * n_my) * a.n_hid;
             for (int l = 0; l < F; ++l, ++use) {
                 ps_wait(mma_bar, (uint32_t)use & 1u);
-                if (tid == 0) ps_trace(a, t, 0, q, 7 + 2 * (l > 0));
+                if (tid == 0) ps_trace(a, t, -1, q, 7 + 2 * (l > 0));
                 tc_fence_after();
                 const uint32_t bias_a = smem_u32(bias_s + l * 128);
                 const uint32_t dst = smem_u32(At + (size_t)(((l + 1) & 1) % n_op) * kOp);
@@ -680,7 +765,7 @@ __device__ void ps_hidden_fwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     }
                 }
                 tc_fence_before();
-                if (tid == 0) ps_trace(a, t, 0, q, 8 + 2 * (l > 0));
+                if (tid == 0) ps_trace(a, t, -1, q, 8 + 2 * (l > 0));
                 fence_async_smem();     // generic-proxy writes before the async-proxy MMA / TMA store
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
@@ -746,8 +831,8 @@ __device__ __forceinline__ void ps_bwd_half(const PsHalf& k, int nv, float gk, u
     }
 }
 
-struct PsFieldBwdSmem { uint32_t Ws, As, Gs, Xs, b3s, bsum, bars, g_part, total; };
-__host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP, int NX) {
+struct PsFieldBwdSmem { uint32_t Ws, As, Gs, Xs, b3s, bsum, gks, bars, g_part, total; };
+__host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP, int NX, int Hg) {
     PsFieldBwdSmem L;
     const uint32_t NP64 = ((uint32_t)Npad + 63u) & ~63u;
     uint32_t o = 0;
@@ -756,9 +841,10 @@ __host__ __device__ inline PsFieldBwdSmem ps_field_bwd_layout(int Npad, int NSP,
     L.As = o; o += (uint32_t)NSP * kTcHidTile;
     L.g_part = kTcM * NP64 * 2;
     L.Gs = o; o += (uint32_t)NSP * L.g_part;
-    L.Xs = o; o += (uint32_t)NX * kPsXSlot;
+    L.Xs = o; o += (uint32_t)NX * ps_bwd_xslot(Hg);
     L.b3s = o; o += (uint32_t)Npad * 4;
-    L.bsum = o; o += 8u * (uint32_t)Npad * 4;
+    L.bsum = L.Gs;                              // per-lane-quarter column sums, staged once after the last MMA has read the G tile
+    L.gks = o; o += (uint32_t)Hg * kTcM * 4;    // dL/dk of the unit about to enter epilogue 1: [Hg][128 rows]
     o = (o + 15u) & ~15u;
     L.bars = o; o += 40 * 8;
     L.total = o;
@@ -783,7 +869,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     constexpr bool EXACT = NSP == 2;
     constexpr int EW = 8, kCg = 2, KP = kTcKP;
     const int Npad = a.Npad, NX = a.NX;
-    const PsFieldBwdSmem L = ps_field_bwd_layout(Npad, NSP, NX);
+    const PsFieldBwdSmem L = ps_field_bwd_layout(Npad, NSP, NX, a.Hg);
     const uint32_t w_part = (uint32_t)Npad * 256u;
     uint8_t* Ws = smem + L.Ws;
     uint8_t* As = smem + L.As;
@@ -794,9 +880,9 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* full_a = bars;
     uint64_t* wg_bar = bars + 1;
-    uint64_t* dep_bar = bars + 2;     // producer -> epilogue: the dz / gy inputs of the unit are visible
+    uint64_t* gk_full = bars + 2;     // dL/dk warp -> epilogue: gks holds the unit's dL/dk (and the tile's hand-off flag has been acquired)
     uint64_t* pre_bar = bars + 3;
-    uint64_t* g_ready = bars + 4;
+    uint64_t* gk_free = bars + 4;     // epilogue -> dL/dk warp: every warp has taken its dL/dk of the unit out of gks
     uint64_t* dg_bar = bars + 5;
     uint64_t* done2 = bars + 6;
     uint64_t* fin_bar = bars + 7;
@@ -806,20 +892,34 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* x_full = bars + 12;     // [NX <= 8]
     uint64_t* x_free = bars + 20;     // [NX <= 8]
     uint64_t* pre_bar2 = bars + 28;   // second recompute accumulator (Npad <= 128)
+    uint64_t* g_blk = bars + 29;      // [<= 4] epilogue -> MMA issuers: 64-column block b of the G tile written by all 8 warps
+    uint64_t* lo_bar = bars + 33;     // wgrad issuer -> producer: every MMA that reads the lo part of the activation tile has completed
+    float* gks = reinterpret_cast<float*>(smem + L.gks);
+    const int n_blk = (Npad + 63) >> 6;
     // TMEM columns.  Npad <= 128: two recompute accumulators (pre of unit i+1 is formed while the epilogues of unit i run) at 0 and
     // 384, P at 128, dW^T at 256.  Wider h-groups: one accumulator at 0 that P re-uses, dW^T at 256.
     const bool pre2 = Npad <= 128;
     const uint32_t p_col = pre2 ? 128u : 0u;
-    const PsXSeq xq = ps_xseq(a.Hg, a.Cp);
+    const bool narrow = ps_bwd_narrow(a.Hg);
+    const int xw = ps_bwd_xw(a.Hg);
+    const uint32_t xslot = ps_bwd_xslot(a.Hg);
+    PsXSeq xq = ps_xseq(a.Hg, a.Cp);
+    if (narrow) xq.nch = (a.Cp + 15) / 16;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform
     const int n_my = part < a.n_mt ? (a.n_mt - part + a.n_part - 1) / a.n_part : 0;
     const int n_q = a.n_steps * a.NS;
     const int n_units = n_my * n_q;
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
+#ifdef NCDE_PS_DBG_PRINT
+    if (tid == 0 && blockIdx.x == 0) g_ps_dbg_bars = smem_u32(bars);
+#endif
     if (tid == 0) {
-        mbar_init(full_a, 1); mbar_init(wg_bar, 1); mbar_init(dep_bar, 1); mbar_init(pre_bar, 1); mbar_init(pre_bar2, 1); mbar_init(g_ready, EW);
+        mbar_init(full_a, NSP == 2 ? 2 : 1);      // bf16x3: the two parts of the tile are loaded separately (two expect_tx arrivals)
+        mbar_init(wg_bar, 1); mbar_init(gk_full, 1); mbar_init(pre_bar, 1); mbar_init(pre_bar2, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(g_blk + i, EW);
+        mbar_init(gk_free, EW); mbar_init(lo_bar, 1);
         mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
         for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
         *sig_done = 0;
@@ -836,101 +936,132 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        if (lane == 0 && n_units > 0) {
-            tma_prefetch_desc(&maps.act[a.F]);
-            mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
-            for (int p = 0; p < NSP; ++p) {
-                tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
-                tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+        if ((kPsConverged || lane == 0) && n_units > 0) {     // see ps_elect
+            if (ps_elect()) {
+                tma_prefetch_desc(&maps.act[a.F]);
+                mbar_expect_tx(w_bar, (uint32_t)NSP * w_part);
+                for (int p = 0; p < NSP; ++p) {
+                    tma_load_3d(Ws + (size_t)p * w_part, &maps.W3, w_bar, 0, g * Npad, p);
+                    tma_load_3d(Ws + (size_t)p * w_part + (size_t)Npad * 128, &maps.W3, w_bar, 64, g * Npad, p);
+                }
             }
+            ps_syncwarp();
             // The saved records are cold (1-2 GB written by the forward pass): the tile of unit i+1 is pulled into L2 while unit i is
             // being worked on, so that its TMA — which can only start when wgrad(i) has released the buffer — is an L2 hit.
-            auto prefetch_A = [&](int i) {
-                if (i >= n_units) return;
-                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
-                const int rows = min(kTcM, a.B - u.t * kTcM);
-                for (int p = 0; p < NSP; ++p)
-                    l2_prefetch_bulk(a.rec0 + (size_t)u.q * a.rec_stride + a.act_off[a.F] + (size_t)p * a.Bp * 128 + (size_t)u.t * kTcM * 128,
-                                     (uint32_t)rows * 256u);
-            };
-            auto load_A = [&](int i) {
-                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
-                mbar_expect_tx(full_a, (uint32_t)NSP * kTcHidTile);
-                for (int p = 0; p < NSP; ++p) {
-                    tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
-                    tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
+            // parts [p0, p1) of the activation tile of unit i; full_a completes when both parts have landed (two expect_tx arrivals)
+            auto load_A = [&](int i, int p0, int p1) {
+                if (ps_elect()) {
+                    const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                    mbar_expect_tx(full_a, (uint32_t)(p1 - p0) * kTcHidTile);
+                    for (int p = p0; p < p1; ++p) {
+                        tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
+                        tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
+                    }
+                    if (p0 == 0 && i + 1 < n_units) {
+                        const PsUnit v = ps_unit_bwd(i + 1, n_my, part, a.n_part, n_q);
+                        const int rows = min(kTcM, a.B - v.t * kTcM);
+                        for (int p = 0; p < NSP; ++p)
+                            l2_prefetch_bulk(a.rec0 + (size_t)v.q * a.rec_stride + a.act_off[a.F] + (size_t)p * a.Bp * 128 + (size_t)v.t * kTcM * 128,
+                                             (uint32_t)rows * 256u);
+                    }
                 }
-                prefetch_A(i + 1);
+                ps_syncwarp();
             };
-            load_A(0);
+            if (NSP == 2) load_A(0, 1, 2);
+            load_A(0, 0, 1);
             ps_wait(w_bar, 0);
             const uint32_t As_s = smem_u32(As), Ws_s = smem_u32(Ws), Gs_s = smem_u32(Gs);
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);
-                ps_trace(a, u.t, g, n_q - 1 - u.q, 1);
+                if (lane == 0) { ps_trace(a, u.t, g, n_q - 1 - u.q, 1); ps_trace_all(a, u.t, g + part * a.n_hg, n_q - 1 - u.q, 1); }
                 // one accumulator: epilogue 2 of the previous unit must have read P out of it; two: accumulator i & 1 was released by
-                // epilogue 1 of unit i-2 (g_ready of unit i-1 was awaited below, so that one is long complete)
+                // epilogue 1 of unit i-2 (the last G block of unit i-1 was awaited below, so that one is long complete)
                 if (!pre2 && i > 0) ps_wait(done2, ph ^ 1u);
                 tc_fence_after();
                 ps_gemm_kmajor<NSP>(tmem_base + ((pre2 && (i & 1)) ? 384u : 0u), As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
-                umma_commit((pre2 && (i & 1)) ? pre_bar2 : pre_bar);
-                // the gradients this unit's gk is formed from: the hidden CTA has finished every later stage of the tile
-                ps_spin_ge(a.flag_h + u.t, n_q - 1 - u.q);
-                ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
-                mbar_arrive(dep_bar);
-                ps_wait(g_ready, ph);                            // G tile written by all 8 warps
-                if (pre2 && i > 0) ps_wait(done2, ph ^ 1u);      // P of the previous unit has been read out
-                tc_fence_after();
-                {   // dgrad: D[128 x KP] = G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows)
-                    const uint32_t idesc = make_idesc(kTcM, KP, 0, 1);
-                    const int nks = Npad / 16;
+                PS_LEAD(umma_commit((pre2 && (i & 1)) ? pre_bar2 : pre_bar));
+                ps_syncwarp();
+                if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
+                // The G tile is handed over in 64-column blocks (one 128-byte swizzle block each): the weight-gradient MMAs of block b
+                // — and, when P has its own TMEM columns, the k-steps of dgrad that read it — run under the rest of epilogue 1.
+                const uint32_t idesc_dg = make_idesc(kTcM, KP, 0, 1);
+                const int nks = Npad / 16;
+                auto issue_dgrad = [&](int blk, bool clear) {
+                    // dgrad: D[128 x KP] (+)= G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows), the (up to) four k-steps
+                    // that read block blk of G; fully unrolled, descriptors advanced from one base per operand
+                    const int nk = min(4, nks - 4 * blk);
 #pragma unroll
                     for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
-                        const uint64_t gd = make_sdesc(Gs_s + (pr == 1 ? L.g_part : 0u), 16, 1024);
-                        const uint64_t wd = make_sdesc(Ws_s + (pr == 2 ? w_part : 0u), (uint32_t)Npad * 128u, 1024);
-#pragma unroll 4
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                            umma_bf16(tmem_base + p_col, ps_desc_advance(gd, a_off), ps_desc_advance(wd, (uint32_t)ks * 2048u), idesc,
-                                      (pr > 0 || ks > 0) ? 1u : 0u);
-                        }
+                        const uint64_t gd = make_sdesc(Gs_s + (pr == 1 ? L.g_part : 0u) + (uint32_t)blk * (uint32_t)kTcM * 128u, 16, 1024);
+                        const uint64_t wd = make_sdesc(Ws_s + (pr == 2 ? w_part : 0u) + (uint32_t)blk * 8192u, (uint32_t)Npad * 128u, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk < nk)
+                                ps_umma(tmem_base + p_col, ps_desc_advance(gd, (uint32_t)kk * 32u), ps_desc_advance(wd, (uint32_t)kk * 2048u), idesc_dg,
+                                        (!clear || pr > 0 || kk > 0) ? 1u : 0u);
                     }
+                };
+                for (int blk = 0; blk < n_blk; ++blk) {
+                    ps_wait(g_blk + blk, ph);                         // block written by all 8 warps
+                    if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, blk == 0 ? 18 : 19);
+                    if (blk == 0 && pre2 && i > 0) ps_wait(done2, ph ^ 1u);      // P of the previous unit has been read out
+                    tc_fence_after();
+                    const bool last = blk == n_blk - 1;
+                    if (pre2) issue_dgrad(blk, blk == 0);
+                    else if (last) {                                  // P re-uses the columns of pre: every warp has read it out by now
+                        for (int b2 = 0; b2 < n_blk; ++b2) issue_dgrad(b2, b2 == 0);
+                    }
+                    if (last) { PS_LEAD(umma_commit(dg_bar)); if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 20); }
                 }
-                umma_commit(dg_bar);
-                {   // wgrad: D[KP x Npad] += A^T (MN-major: M = k contiguous, K = m rows) . G (MN-major: N = n contiguous)
-                    const uint32_t idesc = make_idesc(KP, Npad, 1, 1);
+                if (i + 1 < n_units) {
+                    // the activation tile is released by the wgrad issuer (warp 9): the lo part first, so that half of the next tile's
+                    // load runs under the remaining weight-gradient MMAs
+                    if (NSP == 2) { ps_wait(lo_bar, ph); load_A(i + 1, 1, 2); }
+                    ps_wait(wg_bar, ph);
+                    if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 15);
+                    while (*sig_done < i) {}                     // keeps the signaller within one unit of the pipeline
+                    load_A(i + 1, 0, 1);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // Weight-gradient issuer.  A single thread issues a tcgen05.mma every ~70 ns next to the busy epilogue warps of its scheduler, and
+        // a backward unit of bf16x3 needs 93 of them: with one issuer the MMA issue itself was the critical path of the unit (traced).
+        // The weight-gradient MMAs only meet the producer's at the G blocks and at the release of the activation tile, so they get their
+        // own thread (on another scheduler): D[KP x 64 b ..] += A^T (MN-major: M = k contiguous, K = m rows) . G block b (MN-major).
+        if ((kPsConverged || lane == 0) && n_units > 0) {
+            const uint32_t As_s = smem_u32(As), Gs_s = smem_u32(Gs);
+            for (int i = 0; i < n_units; ++i) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                const uint32_t ph = (uint32_t)i & 1u;
+                ps_wait(full_a, ph);                                  // (long complete: the producer's recompute MMAs have read the tile)
+                for (int blk = 0; blk < n_blk; ++blk) {
+                    ps_wait(g_blk + blk, ph);                         // block written by all 8 warps
+                    tc_fence_after();
+                    const bool last = blk == n_blk - 1;
+                    const int nb = min(64, Npad - 64 * blk);
+                    const uint32_t idesc = make_idesc(KP, nb, 1, 1);
+                    const uint32_t g_blk_off = (uint32_t)blk * (uint32_t)kTcM * 128u;
 #pragma unroll
-                    for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
+                    for (int pi = 0; pi < (NSP == 2 ? 3 : 1); ++pi) {
+                        const int pr = NSP == 2 ? (pi == 0 ? 1 : (pi == 1 ? 0 : 2)) : 0;     // the pair that reads A's lo part goes first
                         const uint64_t ad = make_sdesc(As_s + (pr == 1 ? kTcHidTile : 0u), (uint32_t)kTcM * 128u, 1024);
-                        const uint64_t gd = make_sdesc(Gs_s + (pr == 2 ? L.g_part : 0u), (uint32_t)kTcM * 128u, 1024);
+                        const uint64_t gd = make_sdesc(Gs_s + (pr == 2 ? L.g_part : 0u) + g_blk_off, (uint32_t)kTcM * 128u, 1024);
 #pragma unroll
                         for (int ks = 0; ks < kTcM / 16; ++ks) {
                             const uint32_t off = (uint32_t)ks * 2048u;
-                            umma_bf16(tmem_base + kTcDwCol, ps_desc_advance(ad, off), ps_desc_advance(gd, off), idesc,
-                                      (ks > 0 || pr > 0 || i > 0) ? 1u : 0u);
+                            ps_umma(tmem_base + kTcDwCol + 64u * (uint32_t)blk, ps_desc_advance(ad, off), ps_desc_advance(gd, off), idesc,
+                                    (ks > 0 || pi > 0 || i > 0) ? 1u : 0u);
                         }
+                        if (NSP == 2 && pi == 0 && last) { PS_LEAD(umma_commit(lo_bar)); }
                     }
                 }
-                if (i + 1 < n_units) {
-                    umma_commit(wg_bar);
-                    ps_wait(wg_bar, ph);                         // activation tile free once wgrad(i) has completed
-                    while (*sig_done < i) {}                     // keeps the signaller within one unit of the pipeline
-                    load_A(i + 1);
-                }
+                PS_LEAD(umma_commit(wg_bar));
+                if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 21);
             }
-            umma_commit(fin_bar);
-        }
-    } else if (warp == 9) {
-        if (lane == 0) {
-            for (int i = 0; i < n_units; ++i) {
-                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
-                ps_wait(done2, (uint32_t)i & 1u);
-                red_release_gpu_add(a.cnt_f + u.t, 1);
-                ps_trace(a, u.t, g, n_q - 1 - u.q, 6);
-                *sig_done = i + 1;
-            }
+            PS_LEAD(umma_commit(fin_bar));
         }
     } else if (warp == 10) {
         if (lane == 0) {
@@ -947,100 +1078,222 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 for (int p = 0; p < xq.n_pass; ++p)
                     for (int j = 0; j < xq.nch; ++j) {
                         if (lap > 0) ps_wait(x_free + slot, (lap - 1) & 1u);
-                        mbar_expect_tx(x_full + slot, kPsXSlot);
-                        tma_load_3d(Xs + (size_t)slot * kPsXSlot, &maps.X, x_full + slot, 32 * j, u.t * kTcM, u.q);
+                        mbar_expect_tx(x_full + slot, xslot);
+                        tma_load_3d(Xs + (size_t)slot * xslot, &maps.X, x_full + slot, xw * j, u.t * kTcM, u.q);
                         if (++slot == NX) { slot = 0; ++lap; }
                     }
             }
         }
-    } else {
+    } else if (warp == 11) {
+        // dL/dk former (one unit ahead of the epilogue warps) and signaller.  lane = row (mod 32); entries (row, h) of the tile are owned
+        // by this CTA alone, and gy is read and written by the same lane in program order.
+        const float third = 0.3333333432674408f;
+        auto signal_unit = [&](int i) {          // every epilogue warp has issued its share of unit i's partial sums
+            if (lane == 0) {
+                const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+                ps_wait(done2, (uint32_t)i & 1u);
+                red_release_gpu_add(a.cnt_f + u.t, 1);
+                ps_trace(a, u.t, g, n_q - 1 - u.q, 6); ps_trace_all(a, u.t, g + part * a.n_hg, n_q - 1 - u.q, 6);
+                *sig_done = i + 1;
+            }
+        };
+        for (int i = 0; i < n_units; ++i) {
+            const PsUnit un = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
+            const int s = un.q / a.NS, ist = un.q - s * a.NS;
+            const float dt = __ldg(a.dt + s);
+            const int64_t b0 = (int64_t)un.t * kTcM;
+            float* gy_new = a.yT[s & 1];
+            const float* gy_old = a.yT[(s + 1) & 1];
+            const int emit = __ldg(a.emit_idx + s);
+            const bool first = ist == a.NS - 1;          // first backward stage of step s
+            const bool carry = first && s + 1 < a.n_steps;
+            // the gradients this unit's dL/dk is formed from: the hidden CTA has finished every later stage of the tile (the same
+            // acquire makes the tile's zeroed dA^T visible to epilogue 2, through gk_full)
+            // With several tiles per CTA the flag of unit i was set long ago and dL/dk is formed a whole unit ahead; with one tile it
+            // depends on this CTA's own signal for unit i-1, which then has to go out first (the order below can never deadlock).
+            bool signalled = i == 0;
+            {
+                int ready = 0;
+                if (lane == 0) ready = ld_acquire_gpu(a.flag_h + un.t) >= n_q - 1 - un.q;
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (!ready && !signalled) { signal_unit(i - 1); signalled = true; }
+            }
+            if (lane == 0) { ps_spin_ge(a.flag_h + un.t, n_q - 1 - un.q); ps_trace(a, un.t, g, n_q - 1 - un.q, 16); }
+            __syncwarp();
+            if (i > 0) {      // the epilogue warps have taken the previous unit's values out of gks
+                if (lane == 0) ps_wait(gk_free, ((uint32_t)i & 1u) ^ 1u);
+                __syncwarp();
+            }
+            for (int hl = 0; hl < a.Hg; ++hl) {
+                const int h = g * a.Hg + hl;
+                const bool h_ok = h < a.H;
+                const size_t hoff = (size_t)(h_ok ? h : 0) * a.Bp;
+                // every load of the four row groups first (L2 latency once, not four times), then the arithmetic
+                float v0[kTcM / 32], v1[kTcM / 32], v2[kTcM / 32], v3[kTcM / 32], v4[kTcM / 32];
+#pragma unroll
+                for (int rr = 0; rr < kTcM / 32; ++rr) {
+                    const int64_t b = b0 + rr * 32 + lane;
+                    const size_t off = hoff + (size_t)(b < a.B ? b : a.B - 1);
+                    v0[rr] = first ? gy_old[off] : gy_new[off];      // written by this very lane (plain accesses: same-thread order)
+                    v1[rr] = v2[rr] = v3[rr] = v4[rr] = 0.f;
+                    if (first) {
+                        if (carry) {
+                            v1[rr] = __ldcg(a.kT[0] + off);
+                            if (a.NS > 1) v2[rr] = __ldcg(a.kT[1] + off);
+                            if (a.NS > 2) v3[rr] = __ldcg(a.kT[2] + off);
+                            if (a.NS > 3) v4[rr] = __ldcg(a.kT[3] + off);
+                        }
+                        if (emit >= 0) v1[rr] += __ldg(a.grad_out + ((size_t)emit * a.B + (b < a.B ? b : a.B - 1)) * a.H + (h_ok ? h : 0));
+                    } else {
+                        if (ist == 0) v1[rr] = __ldcg(a.kT[1] + off);
+                        if (ist <= 1) v2[rr] = __ldcg(a.kT[2] + off);
+                        v3[rr] = __ldcg(a.kT[3] + off);
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < kTcM / 32; ++rr) {
+                    const int row = rr * 32 + lane;
+                    const int64_t b = b0 + row;
+                    float gk = 0.f;
+                    if (b < a.B && h_ok) {
+                        if (first) {
+                            // the gradient of the step's end state = the one carried over from step s+1 + the stage-input gradients of
+                            // step s+1 (unit Jacobian w.r.t. the state) + the output gradient at this point
+                            const float gy = v0[rr] + v1[rr] + v2[rr] + v3[rr] + v4[rr];
+                            gy_new[hoff + b] = gy;
+                            gk = (a.method == NCDE_RK4_38 ? dt * 0.125f : dt) * gy;
+                        } else {
+                            // rk_common.py:106-114 transposed: dL/dk_i = c_i dt gy + sum over later stages q of d(stage input q)/dk_i * dz_q
+                            const float c8 = dt * 0.125f;
+                            gk = ((ist == 0) ? c8 : 3.f * c8) * v0[rr];
+                            if (ist == 0) {
+                                gk = fmaf(dt * third, v1[rr], gk);
+                                gk = fmaf(-(dt * third), v2[rr], gk);
+                                gk = fmaf(dt, v3[rr], gk);
+                            } else if (ist == 1) {
+                                gk = fmaf(dt, v2[rr], gk);
+                                gk = fmaf(-dt, v3[rr], gk);
+                            } else {
+                                gk = fmaf(dt, v3[rr], gk);
+                            }
+                        }
+                    }
+                    gks[hl * kTcM + row] = gk;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(gk_full); ps_trace(a, un.t, g, n_q - 1 - un.q, 17); }
+            if (!signalled) signal_unit(i - 1);
+        }
+        if (n_units > 0) signal_unit(n_units - 1);
+    } else if (warp < 8) {
         const int cg = warp >> 2;                    // column group
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int h_begin = a.Hg >= 2 ? (cg == 0 ? 0 : a.Hg / 2) : 0;
         const int h_end = a.Hg >= 2 ? (cg == 0 ? a.Hg / 2 : a.Hg) : 1;
-        const uint32_t xs_row = smem_u32(Xs) + (uint32_t)row * (kPsXPitch * 4);
+        const uint32_t xs_row = smem_u32(Xs) + (uint32_t)row * ((narrow ? kPsXPitchN : kPsXPitch) * 4);
         int slot = 0;
         uint32_t lap = 0;
         const int col_begin = (cg * Npad / kCg) & ~15;
         const int col_end = cg == kCg - 1 ? Npad : (((cg + 1) * Npad / kCg) & ~15);
-        const int n_chunk8 = Npad >> 3;                     // <= 30
+        const uint32_t b3_s = smem_u32(b3s), gs_s = smem_u32(Gs);
+        // Bias gradient = column sums of G.  Each warp sums exactly what it wrote — its 32 rows x its own 8-column chunks — right after
+        // epilogue 1, while the tensor core works on dgrad (no CTA-wide barrier, no second reader of other warps' rows).  Lane = (chunk
+        // slot, row subset); the slot -> chunk map is the same for every unit, so the running sums stay in registers for the whole pass.
+        int bs_nc;                                   // my 8-column chunks
+        if (a.Hg >= 2) bs_nc = (h_end - h_begin) * (a.Cp >> 3);
+        else { const int c8 = a.Cp >> 3; bs_nc = (c8 / 4) * 2 + max(0, min(2, c8 % 4 - 2 * cg)); }     // 16-column chunks j with j & 1 == cg
+        const int bs_S = bs_nc <= 8 ? 8 : 16;        // chunk slots per pass over the lanes (bs_nc <= 16: TMEM limits Npad / 2 to 120 columns)
+        const int bs_slot = lane % bs_S, bs_rsub = lane / bs_S, bs_R = 32 / bs_S;
+        const int bs_chunk = a.Hg >= 2 ? h_begin * (a.Cp >> 3) + bs_slot : (bs_slot >> 1) * 4 + cg * 2 + (bs_slot & 1);
+        const bool bs_on = bs_slot < bs_nc;
         float bacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
-        const uint32_t b3_s = smem_u32(b3s), gs_s = smem_u32(Gs);
-        const float third = 0.3333333432674408f;
 
         for (int i = 0; i < n_units; ++i) {
             const PsUnit un = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
             const uint32_t ph = (uint32_t)i & 1u;
-            const int s = un.q / a.NS, ist = un.q - s * a.NS;
-            const float dt = __ldg(a.dt + s);
             const int64_t b0 = (int64_t)un.t * kTcM;
             const int64_t b = b0 + row;
             const bool row_ok = b < a.B;
-            float* gy_new = a.yT[s & 1];
-            const float* gy_old = a.yT[(s + 1) & 1];
-            ps_wait(dep_bar, ph);
-            // dL/dk of this thread's (row, h) entries: formed as soon as the inputs are visible, before the recompute MMA is awaited
+            // dL/dk of this thread's (row, h) entries, formed by warp 11 while the previous unit was in its second epilogue
+            ps_wait(gk_full, ph);
+            if (lane == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 32 + warp);
             float gkv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int hl = h_begin + p;
-                const bool pass_ok = p < xq.n_pass && hl < h_end;
-                const int h = g * a.Hg + hl;
-                float gk = 0.f;
-                if (pass_ok && row_ok && h < a.H) {
-                    const size_t off = (size_t)h * a.Bp + b;
-                    if (ist == a.NS - 1) {
-                        // first backward stage of step s: the gradient of the step's end state = the one carried over from step s+1
-                        // + the stage-input gradients of step s+1 (unit Jacobian w.r.t. the state) + the output gradient at this point
-                        float gy = gy_old[off];
-                        if (s + 1 < a.n_steps)
-                            for (int q2 = 0; q2 < a.NS; ++q2) gy += __ldcg(a.kT[q2] + off);
-                        const int slot = __ldg(a.emit_idx + s);
-                        if (slot >= 0) gy += __ldg(a.grad_out + ((size_t)slot * a.B + b) * a.H + h);
-                        gy_new[off] = gy;
-                        gk = (a.method == NCDE_RK4_38 ? dt * 0.125f : dt) * gy;
-                    } else {
-                        // rk_common.py:106-114 transposed: dL/dk_i = c_i dt gy + sum over later stages q of d(stage input q)/dk_i * dz_q
-                        const float gy = gy_new[off];
-                        const float c8 = dt * 0.125f;
-                        gk = ((ist == 0) ? c8 : 3.f * c8) * gy;
-                        if (ist == 0) {
-                            gk = fmaf(dt * third, __ldcg(a.kT[1] + off), gk);
-                            gk = fmaf(-(dt * third), __ldcg(a.kT[2] + off), gk);
-                            gk = fmaf(dt, __ldcg(a.kT[3] + off), gk);
-                        } else if (ist == 1) {
-                            gk = fmaf(dt, __ldcg(a.kT[2] + off), gk);
-                            gk = fmaf(-dt, __ldcg(a.kT[3] + off), gk);
-                        } else {
-                            gk = fmaf(dt, __ldcg(a.kT[3] + off), gk);
-                        }
-                    }
-                }
-                gkv[p] = gk;
-            }
+            for (int p = 0; p < 4; ++p)
+                if (p < xq.n_pass && h_begin + p < h_end) gkv[p] = gks[(h_begin + p) * kTcM + row];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gk_free);
             if (pre2) ps_wait((i & 1) ? pre_bar2 : pre_bar, (uint32_t)(i >> 1) & 1u);
             else ps_wait(pre_bar, ph);
-            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 2);
+            if (tid == 0) { ps_trace(a, un.t, g, n_q - 1 - un.q, 2); ps_trace_all(a, un.t, g + part * a.n_hg, n_q - 1 - un.q, 2); }
             tc_fence_after();
             const uint32_t pre_addr = lane_addr + ((pre2 && (i & 1)) ? 384u : 0u);
             // ---- epilogue 1 ----
             PsHalf HA, HB;
+            int nb_done = 0;          // 64-column blocks of the G tile this warp has handed over
+            // every column of mine below `col` is written: hand over the blocks that lie entirely below it
+            auto hand_over = [&](int col) {
+                if (nb_done < n_blk && 64 * (nb_done + 1) <= col) {
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    do {
+                        if (lane == 0) mbar_arrive(g_blk + nb_done);
+                        ++nb_done;
+                    } while (nb_done < n_blk && 64 * (nb_done + 1) <= col);
+                }
+            };
+            if (narrow) {
+                // one hidden row: 16-column chunk j is warp group (j & 1)'s; four chunks per trip keep HA / HB statically named
+                const float gk = gkv[0];
+                if (cg < xq.nch) ps_half_issue(HA, pre_addr + (uint32_t)(16 * cg));
+                else hand_over(1 << 30);
+                for (int j2 = 0; j2 < xq.nch; j2 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j2 + u;
+                        if (j < xq.nch) {
+                            ps_wait(x_full + slot, lap & 1u);
+                            if ((u & 1) == cg) {
+                                const int c = 16 * j, jn = j + 2;
+                                const int nv = min(16, a.Cp - c);
+                                const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlotN;
+                                const bool more = jn < xq.nch;
+                                if (u < 2) {
+                                    tmem_wait_ld<16>(HA.r);
+                                    if (more) ps_half_issue(HB, pre_addr + (uint32_t)(16 * jn));
+                                    ps_bwd_half<NSP, EXACT>(HA, nv, gk, b3_s + 4u * c, xs, gs_s, L.g_part, row, c);
+                                } else {
+                                    tmem_wait_ld<16>(HB.r);
+                                    if (more) ps_half_issue(HA, pre_addr + (uint32_t)(16 * jn));
+                                    ps_bwd_half<NSP, EXACT>(HB, nv, gk, b3_s + 4u * c, xs, gs_s, L.g_part, row, c);
+                                }
+                                hand_over(more ? 16 * jn : (1 << 30));
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(x_free + slot);
+                            if (++slot == NX) { slot = 0; ++lap; }
+                        }
+                    }
+                }
+            } else {
             {
-                const int j0 = a.Hg >= 2 ? 0 : cg;
-                if (h_begin < h_end && j0 < xq.nch) ps_half_issue(HA, pre_addr + (uint32_t)(h_begin * a.Cp + 32 * j0));
+                const bool any = h_begin < h_end;
+                if (any) ps_half_issue(HA, pre_addr + (uint32_t)(h_begin * a.Cp));
+                hand_over(any ? h_begin * a.Cp : (1 << 30));
             }
             for (int p = 0; p < xq.n_pass; ++p) {
                 const int hl = h_begin + p;
                 const bool pass_ok = hl < h_end;
-                const int h = g * a.Hg + hl;
                 const float gk = p == 0 ? gkv[0] : (p == 1 ? gkv[1] : (p == 2 ? gkv[2] : gkv[3]));
                 const int colbase = hl * a.Cp;
                 for (int j = 0; j < xq.nch; ++j) {
                     ps_wait(x_full + slot, lap & 1u);
-                    const bool mine = pass_ok && (a.Hg >= 2 || (j & 1) == cg);
+                    const bool mine = pass_ok;
                     if (mine) {
                         const int c = 32 * j;
                         const int nv0 = min(16, a.Cp - c), nv1 = max(0, min(16, a.Cp - c - 16));
@@ -1049,44 +1302,48 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         if (nv1 > 0) ps_half_issue(HB, pre_addr + (uint32_t)(colbase + c + 16));
                         ps_bwd_half<NSP, EXACT>(HA, nv0, gk, b3_s + 4u * (colbase + c), xs, gs_s, L.g_part, row, colbase + c);
                         tmem_wait_ld<16>(HB.r);
+                        int next_col = 1 << 30;     // first column of my next chunk in this unit
                         {
-                            int pn = p, jn = j + (a.Hg >= 2 ? 1 : 2);
-                            if (jn >= xq.nch) { pn = p + 1; jn = a.Hg >= 2 ? 0 : cg; }
-                            if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch)
-                                ps_half_issue(HA, pre_addr + (uint32_t)((h_begin + pn) * a.Cp + 32 * jn));
+                            int pn = p, jn = j + 1;
+                            if (jn >= xq.nch) { pn = p + 1; jn = 0; }
+                            if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch) {
+                                next_col = (h_begin + pn) * a.Cp + 32 * jn;
+                                ps_half_issue(HA, pre_addr + (uint32_t)next_col);
+                            }
                         }
                         ps_bwd_half<NSP, EXACT>(HB, nv1, gk, b3_s + 4u * (colbase + c + 16), xs + 64u, gs_s, L.g_part, row, colbase + c + 16);
+                        hand_over(next_col);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(x_free + slot);
                     if (++slot == NX) { slot = 0; ++lap; }
                 }
             }
-            fence_async_smem();
-            tc_fence_before();
+            }
+            hand_over(1 << 30);       // (a warp without columns in this unit hands every block over here)
+            if (lane == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 24 + warp);
+            if (tid == 0) { ps_trace(a, un.t, g, n_q - 1 - un.q, 3); ps_trace_all(a, un.t, g + part * a.n_hg, n_q - 1 - un.q, 3); }
             __syncwarp();
-            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 3);
-            if (lane == 0) mbar_arrive(g_ready);
-            // bias gradient from the G tile while the tensor core works: every warp needs ALL rows -> epilogue-wide barrier
-            named_bar_sync(1, kPsEpi);
-            if (lane < n_chunk8) {
+            if (bs_on) {
+                const int r0 = (warp & 3) * 32 + bs_rsub;
 #pragma unroll 4
-                for (int r = warp * (kTcM / EW); r < (warp + 1) * (kTcM / EW); ++r) {
+                for (int r = r0; r < (warp & 3) * 32 + 32; r += bs_R) {
+#pragma unroll
                     for (int p = 0; p < NSP; ++p) {
                         uint32_t w4[4];
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
-                                     : "r"(gs_s + (uint32_t)p * L.g_part + sw128_off(r, lane, kTcM)));
+                                     : "r"(gs_s + (uint32_t)p * L.g_part + sw128_off(r, bs_chunk, kTcM)));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
-                            bacc[2 * j] += f.x;
-                            bacc[2 * j + 1] += f.y;
+                            bacc[2 * j] += __uint_as_float(w4[j] << 16);
+                            bacc[2 * j + 1] += __uint_as_float(w4[j] & 0xffff0000u);
                         }
                     }
                 }
             }
+            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 14);
             ps_wait(dg_bar, ph);
-            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 4);
+            if (tid == 0) { ps_trace(a, un.t, g, n_q - 1 - un.q, 4); ps_trace_all(a, un.t, g + part * a.n_hg, n_q - 1 - un.q, 4); }
             tc_fence_after();
             // ---- epilogue 2: this h-group's share of dL/d(final-layer input), summed over the groups in L2 ----
             {
@@ -1108,17 +1365,22 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             }
             tc_fence_before();
             __syncwarp();
-            if (tid == 0) ps_trace(a, un.t, g, n_q - 1 - un.q, 5);
+            if (tid == 0) { ps_trace(a, un.t, g, n_q - 1 - un.q, 5); ps_trace_all(a, un.t, g + part * a.n_hg, n_q - 1 - un.q, 5); }
             if (lane == 0) mbar_arrive(done2);
         }
         // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [part][g*Npad + n][k];  bias gradient ----
         if (n_units > 0) {
-            if (lane < n_chunk8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bsum[warp * Npad + lane * 8 + j] = bacc[j];
-            }
             ps_wait(fin_bar, 0);
             tc_fence_after();
+            // column sums: over the row subsets of a warp by shuffles, then over the four lane quarters through shared memory
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                for (int d = bs_S; d < 32; d <<= 1) bacc[j] += __shfl_xor_sync(0xffffffffu, bacc[j], d);
+            }
+            if (bs_on && bs_rsub == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[(warp & 3) * Npad + bs_chunk * 8 + j] = bacc[j];
+            }
             named_bar_sync(1, kPsEpi);
             const int k = row;
             for (int n0 = col_begin; n0 < col_end; n0 += 16) {
@@ -1129,10 +1391,9 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     a.dW3acc[(((size_t)part * a.n_hg + g) * Npad + n0 + j) * 128 + k] = v[j];
             }
             for (int n = tid; n < Npad; n += kPsEpi) {
-                float sacc = 0.f;
-#pragma unroll
-                for (int w = 0; w < EW; ++w) sacc += bsum[w * Npad + n];
-                a.db3acc[((size_t)part * a.n_hg + g) * Npad + n] = sacc;
+                // columns no warp owns ([Hg * Cp, Npad) padding) were never written: they are zero by construction
+                const bool owned = n < a.Hg * a.Cp;
+                a.db3acc[((size_t)part * a.n_hg + g) * Npad + n] = owned ? (bsum[n] + bsum[Npad + n]) + (bsum[2 * Npad + n] + bsum[3 * Npad + n]) : 0.f;
             }
         }
     }
@@ -1160,7 +1421,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     uint64_t* out_done = bars + 11;   // epilogue -> producer: dz written (8 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform
     const int F = a.F;
     const int n_my = j < a.n_mt ? (a.n_mt - j + a.n_hid - 1) / a.n_hid : 0;
     const int n_q = a.n_steps * a.NS;
@@ -1178,16 +1439,19 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        if (lane == 0 && n_units > 0) {
+        if ((kPsConverged || lane == 0) && n_units > 0) {     // see ps_elect
             auto load_W = [&](int l, int buf) {
                 uint8_t* dst = Wt + (size_t)buf * kOp;
-                mbar_expect_tx(w_full + buf, kOp);
-                for (int p = 0; p < NSP; ++p) {
-                    tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
-                    tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                if (ps_elect()) {
+                    mbar_expect_tx(w_full + buf, kOp);
+                    for (int p = 0; p < NSP; ++p) {
+                        tma_load_4d(dst + (size_t)p * kTcHidTile, &maps.Wh, w_full + buf, 0, 0, p, l);
+                        tma_load_4d(dst + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.Wh, w_full + buf, 64, 0, p, l);
+                    }
                 }
+                ps_syncwarp();
             };
-            tma_prefetch_desc(&maps.dpre);
+            PS_LEAD(tma_prefetch_desc(&maps.dpre));
             // layer order of the chain: F-1, F-2, ..., 0, F-1, ...   use u -> layer F-1 - (u % F)
             if (resident) { for (int l = 0; l < F; ++l) load_W(l, l); }
             else { for (int w = 0; w < NW && w < F; ++w) load_W(F - 1 - w, w); }
@@ -1195,18 +1459,24 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
             for (int i = 0; i < n_units; ++i) {
                 const int qi = i / n_my, q = n_q - 1 - qi, t = j + (i - qi * n_my) * a.n_hid;
                 const int b0 = t * kTcM;
-                ps_spin_ge(a.cnt_f + t, a.n_hg * (qi + 1));          // every h-group has added its partial of stage q
-                ps_trace(a, t, 0, qi, 7);
-                mbar_arrive(top_bar);
+                if (lane == 0) {
+                    ps_spin_ge(a.cnt_f + t, a.n_hg * (qi + 1));          // every h-group has added its partial of stage q
+                    ps_trace(a, t, -1, qi, 7);
+                    mbar_arrive(top_bar);
+                }
+                ps_syncwarp();
                 for (int l = F - 1, n = 0; l >= 0; --l, ++n, ++use) {
                     const int bf = l & 1;
                     ps_wait(dp_ready, (uint32_t)(i * F + n) & 1u);        // dpre_l written (and fenced)
                     uint8_t* d_tile = Dt + (size_t)bf * kOp;
-                    for (int p = 0; p < NSP; ++p) {                       // keep dpre_l for the weight-gradient kernel
-                        tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile, 0, b0, p, q * F + l);
-                        tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, q * F + l);
+                    if (ps_elect()) {
+                        for (int p = 0; p < NSP; ++p) {                   // keep dpre_l for the weight-gradient kernel
+                            tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile, 0, b0, p, q * F + l);
+                            tma_store_4d(&maps.dpre, d_tile + (size_t)p * kTcHidTile + kTcHidTile / 2, 64, b0, p, q * F + l);
+                        }
+                        bulk_commit();
                     }
-                    bulk_commit();
+                    ps_syncwarp();
                     const int buf = resident ? l : use % NW;
                     if (resident) { if (i == 0) ps_wait(w_full + buf, 0); }
                     else ps_wait(w_full + buf, (uint32_t)(use / NW) & 1u);
@@ -1221,14 +1491,17 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks) {
                                 const uint32_t a_off = (uint32_t)(ks >> 2) * (uint32_t)kTcM * 128u + (uint32_t)(ks & 3) * 32u;
-                                umma_bf16(tmem_base, ps_desc_advance(dd, a_off), ps_desc_advance(wd, (uint32_t)ks * 2048u), idesc,
-                                          (pr > 0 || ks > 0) ? 1u : 0u);
+                                ps_umma(tmem_base, ps_desc_advance(dd, a_off), ps_desc_advance(wd, (uint32_t)ks * 2048u), idesc,
+                                        (pr > 0 || ks > 0) ? 1u : 0u);
                             }
                         }
                     }
-                    // the epilogue of this level writes buffer (l-1)&1, whose previous content was stored one level ago
-                    bulk_wait_read<1>();
-                    umma_commit(dg_bar);
+                    if (ps_elect()) {
+                        // the epilogue of this level writes buffer (l-1)&1, whose previous content was stored one level ago
+                        bulk_wait_read<1>();
+                        umma_commit(dg_bar);
+                    }
+                    ps_syncwarp();
                     if (!resident) {
                         const int64_t total_uses = (int64_t)n_units * F;
                         if ((int64_t)use + NW < total_uses) {
@@ -1238,11 +1511,14 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     }
                 }
                 ps_wait(out_done, (uint32_t)i & 1u);
-                bulk_wait_read<0>();     // the next unit's top tile overwrites a buffer the last store may still read
-                st_release_gpu(a.flag_h + t, qi + 1);
-                ps_trace(a, t, 0, qi, 13);
+                if (ps_elect()) {
+                    bulk_wait_read<0>();     // the next unit's top tile overwrites a buffer the last store may still read
+                    st_release_gpu(a.flag_h + t, qi + 1);
+                    ps_trace(a, t, -1, qi, 13);
+                }
+                ps_syncwarp();
             }
-            bulk_wait<0>();
+            PS_LEAD(bulk_wait<0>());
         }
     } else if (warp < 8) {
         const int wg = warp >> 2;
@@ -1293,12 +1569,12 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (tid == 0) ps_trace(a, t, 0, qi, 8);
+                if (tid == 0) ps_trace(a, t, -1, qi, 8);
                 if (lane == 0) mbar_arrive(dp_ready);
             }
             for (int l = F - 1; l >= 0; --l, ++use) {
                 ps_wait(dg_bar, (uint32_t)use & 1u);
-                if (tid == 0) ps_trace(a, t, 0, qi, l == 0 ? 11 : 9);
+                if (tid == 0) ps_trace(a, t, -1, qi, l == 0 ? 11 : 9);
                 tc_fence_after();
                 if (l > 0) {
                     const __nv_bfloat16* arow = recq + a.act_off[l] + (size_t)b * 128;
@@ -1339,7 +1615,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (tid == 0) ps_trace(a, t, 0, qi, 10);
+                    if (tid == 0) ps_trace(a, t, -1, qi, 10);
                     if (lane == 0) mbar_arrive(dp_ready);
                 } else {
                     // dz of stage `ist`, feature-major fp32: plain stores, coalesced over the lanes (= rows)
@@ -1356,7 +1632,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                         }
                     }
                     tc_fence_before();
-                    if (tid == 0) ps_trace(a, t, 0, qi, 12);
+                    if (tid == 0) ps_trace(a, t, -1, qi, 12);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(out_done);
                 }
@@ -1369,10 +1645,10 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-static inline size_t ps_bwd_smem_bytes(int Npad, int NSP, int F, int NX) {
+static inline size_t ps_bwd_smem_bytes(int Npad, int NSP, int F, int NX, int Hg) {
     bool res;
     const int NW = ps_hid_nw(NSP, F, &res, 2);
-    const size_t f = ps_field_bwd_layout(Npad, NSP, NX).total, h = ps_hid_fwd_layout(NSP, NW, 2).total;
+    const size_t f = ps_field_bwd_layout(Npad, NSP, NX, Hg).total, h = ps_hid_fwd_layout(NSP, NW, 2).total;
     return 1024 + (f > h ? f : h);
 }
 
@@ -1466,7 +1742,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ps_hidden_wgrad_kernel(const __
     uint64_t* fin_bar = bars + 6;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform
     const int l = blockIdx.x, sp = blockIdx.y;
     const int64_t U = (int64_t)a.n_rec * a.n_mt;
     const int64_t u_begin = sp * U / a.n_split, u_end = (sp + 1) * U / a.n_split;

@@ -277,7 +277,7 @@ static int make_plan(const ncde_problem_t* p, Plan* pl, bool fixed_path = false,
                 if (npad > 240) continue;  // TMEM: [pre | dW^T] must fit 512 columns in the backward kernel
                 if (pl->ns == 2) {
                     // bf16x3 runs on the persistent kernels only: the pass at hand decides (weights are re-packed per pass)
-                    if (for_bwd ? ps_bwd_smem_bytes(npad, 2, m.n_layers - 1, 2) > kSmemLimit
+                    if (for_bwd ? ps_bwd_smem_bytes(npad, 2, m.n_layers - 1, 2, hg) > kSmemLimit
                                 : ps_fwd_smem_bytes(npad, 2, 1, m.n_layers - 1, 2) > kSmemLimit) continue;
                 } else {
                     if (tc_bwd_smem_bytes(npad, pl->CpB, pl->bwd_ew) > kSmemLimit) continue;
@@ -703,12 +703,13 @@ static bool ps_eligible(const ncde_problem_t* p, const Plan& pl, bool bwd, PsPla
     pp->n_field = pp->n_part * pl.n_hg;
     // shared memory: operand tiles first, then as many dX/dt chunk slots as fit (at least 2; more = the loader runs further ahead)
     pp->NA = 1;
-    const int nch = (pl.Cp + 31) / 32;
+    int nch = (pl.Cp + 31) / 32;
+    if (bwd && ps_bwd_narrow(pl.Hg)) nch = (pl.Cp + 15) / 16;
     const int want = 2 * nch < kPsMaxSlots ? 2 * nch : kPsMaxSlots;     // two whole tiles' worth is as far ahead as it is useful to run
     if (bwd) {
         pp->NX = 2;
-        while (pp->NX < want && ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX + 1) <= kSmemLimit) ++pp->NX;
-        pp->smem = ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX);
+        while (pp->NX < want && ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX + 1, pl.Hg) <= kSmemLimit) ++pp->NX;
+        pp->smem = ps_bwd_smem_bytes(pl.Npad, pl.ns, pl.F, pp->NX, pl.Hg);
     } else {
         pp->NX = 2;
         const int need = nch < kPsMaxSlots ? nch : kPsMaxSlots;        // one tile's worth of slots before a second activation buffer
@@ -743,7 +744,7 @@ static int ps_pack(const ncde_problem_t* p, const Plan& pl, float* wpack, cudaSt
 
 // descriptors: packed weights, the bf16 activation records (rec0 = first record, stride in floats), dpre records (backward)
 static int ps_build_maps(const Plan& pl, const float* wpack, PsMaps* pm, const float* rec0, size_t rec_stride_floats, int64_t n_rec,
-                         const float* dpre0, const float* dx0, size_t dx_stride_floats, int64_t n_dx) {
+                         const float* dpre0, const float* dx0, size_t dx_stride_floats, int64_t n_dx, int x_pitch = kPsXPitch) {
     memset(pm, 0, sizeof(*pm));
     int rc = make_map(&pm->W3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack + pl.off_W3T, 128, (uint64_t)pl.Np, (uint64_t)pl.ns, 256,
                       (uint64_t)pl.Np * 256, 64, (uint32_t)pl.Npad, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -753,7 +754,7 @@ static int ps_build_maps(const Plan& pl, const float* wpack, PsMaps* pm, const f
                        n_rec > 1 ? rec_stride_floats * 4 : 0, kTcM);
     if (rc == NCDE_OK)   // dX/dt records, row-major [B][Cp] fp32; one box = 128 rows x (32 + 4) channels, rows / channels beyond the tensor read 0
         rc = make_map(&pm->X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dx0, (uint64_t)pl.Cp, (uint64_t)pl.B, (uint64_t)(n_dx < 1 ? 1 : n_dx),
-                      (uint64_t)pl.Cp * 4, n_dx > 1 ? dx_stride_floats * 4 : 0, kPsXPitch, kTcM, CU_TENSOR_MAP_SWIZZLE_NONE);
+                      (uint64_t)pl.Cp * 4, n_dx > 1 ? dx_stride_floats * 4 : 0, (uint32_t)x_pitch, kTcM, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc == NCDE_OK && dpre0)
         rc = make_map4(&pm->dpre, dpre0, (uint64_t)pl.B, (uint64_t)pl.ns, (uint64_t)n_rec * pl.F, (uint64_t)pl.Bp * 256,
                        (uint64_t)pl.ns * pl.Bp * 256, kTcM);
@@ -1041,8 +1042,9 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
         static const bool trace_on = getenv("NCDE_PS_TRACE") != nullptr;   // debug: stamps of tile 0's hand-offs, dumped to stderr
         if (trace_on) {
-            NCDE_CUDA_OK(cudaMalloc(&pa.trace, kPsTraceStages * 16 * 8));
-            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, kPsTraceStages * 16 * 8, st));
+            NCDE_CUDA_OK(cudaMalloc(&pa.trace, (kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8) * 8));
+            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, (kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8) * 8, st));
+            pa.trace_g = getenv("NCDE_PS_TRACE_G") ? atoi(getenv("NCDE_PS_TRACE_G")) : 0;
         }
         const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
         {
@@ -1058,16 +1060,18 @@ extern "C" int ncde_solve_fwd(const ncde_problem_t* p, const float* z0, float* z
         ++launches;
         NCDE_CUDA_OK(cudaGetLastError());
         if (trace_on) {
-            std::vector<unsigned long long> h(kPsTraceStages * 16);
+            std::vector<unsigned long long> h(kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8);
             NCDE_CUDA_OK(cudaStreamSynchronize(st));
             NCDE_CUDA_OK(cudaMemcpy(h.data(), pa.trace, h.size() * 8, cudaMemcpyDeviceToHost));
             cudaFree(pa.trace);
             const unsigned long long t0 = h[5];
-            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q) {
-                fprintf(stderr, "pstrace fwd q=%d", q);
-                for (int e = 0; e < 13; ++e) fprintf(stderr, " %lld", h[q * 16 + e] ? (long long)(h[q * 16 + e] - t0) : -1ll);
-                fprintf(stderr, "\n");
-            }
+            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q)
+                for (int t = 0; t < kPsTraceTiles && t < pp.n_mt; ++t) {
+                    const unsigned long long* r = h.data() + ((size_t)q * kPsTraceTiles + t) * kPsTraceEv;
+                    fprintf(stderr, "pstrace fwd q=%d t=%d", q, t);
+                    for (int e = 0; e < kPsTraceEv; ++e) fprintf(stderr, " %lld", r[e] ? (long long)(r[e] - t0) : -1ll);
+                    fprintf(stderr, "\n");
+                }
         }
         if (launches_out) *launches_out = launches;
         return NCDE_OK;
@@ -1299,7 +1303,7 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         if (rc != NCDE_OK) return rc;
         PsMaps pm;
         rc = ps_build_maps(pl, wpack, &pm, (const float*)saved, pl.stage_floats, n_rec, dpre_rec, (const float*)saved + pl.dx_off,
-                           pl.stage_floats, n_rec);
+                           pl.stage_floats, n_rec, ps_bwd_narrow(pl.Hg) ? kPsXPitchN : kPsXPitch);
         if (rc != NCDE_OK) return rc;
         PsArgs pa;
         ps_fill_args(pa, p, pl, pp, wpack);
@@ -1315,8 +1319,9 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         pa.cnt_f = sync; pa.flag_h = sync + pp.n_mt;
         static const bool trace_on = getenv("NCDE_PS_TRACE") != nullptr;
         if (trace_on) {
-            NCDE_CUDA_OK(cudaMalloc(&pa.trace, kPsTraceStages * 16 * 8));
-            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, kPsTraceStages * 16 * 8, st));
+            NCDE_CUDA_OK(cudaMalloc(&pa.trace, (kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8) * 8));
+            NCDE_CUDA_OK(cudaMemsetAsync(pa.trace, 0, (kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8) * 8, st));
+            pa.trace_g = getenv("NCDE_PS_TRACE_G") ? atoi(getenv("NCDE_PS_TRACE_G")) : 0;
         }
         const dim3 grid((unsigned)(pp.n_field + pp.n_hid));
         {
@@ -1331,15 +1336,24 @@ extern "C" int ncde_solve_bwd(const ncde_problem_t* p, const float* grad_out, co
         }
         ++launches;
         if (trace_on) {
-            std::vector<unsigned long long> h(kPsTraceStages * 16);
+            std::vector<unsigned long long> h(kPsTraceStages * kPsTraceTiles * kPsTraceEv + 256 * 8);
             NCDE_CUDA_OK(cudaStreamSynchronize(st));
             NCDE_CUDA_OK(cudaMemcpy(h.data(), pa.trace, h.size() * 8, cudaMemcpyDeviceToHost));
             cudaFree(pa.trace);
             const unsigned long long t0 = h[1];
-            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q) {
-                fprintf(stderr, "pstrace bwd q=%d", q);
-                for (int e = 0; e < 14; ++e) fprintf(stderr, " %lld", h[q * 16 + e] ? (long long)(h[q * 16 + e] - t0) : -1ll);
-                fprintf(stderr, "\n");
+            for (int q = 0; q < kPsTraceStages && q < g.n_steps * NS; ++q)
+                for (int t = 0; t < kPsTraceTiles && t < pp.n_mt; ++t) {
+                    const unsigned long long* r = h.data() + ((size_t)q * kPsTraceTiles + t) * kPsTraceEv;
+                    fprintf(stderr, "pstrace bwd q=%d t=%d", q, t);
+                    for (int e = 0; e < kPsTraceEv; ++e) fprintf(stderr, " %lld", r[e] ? (long long)(r[e] - t0) : -1ll);
+                    fprintf(stderr, "\n");
+                }
+            for (int gg = 0; gg < 256; ++gg) {
+                const unsigned long long* r = h.data() + (size_t)kPsTraceStages * kPsTraceTiles * kPsTraceEv + gg * 8;
+                if (!r[1]) continue;
+                fprintf(stderr, "pstrace_all bwd g=%d", gg);
+                for (int e = 0; e < 7; ++e) fprintf(stderr, " %lld", r[e] ? (long long)(r[e] - t0) : -1ll);
+                fprintf(stderr, " %lld\n", (long long)r[7] - 1);
             }
         }
         ps_gy_final_kernel<<<(unsigned)ceil_div((int64_t)nHB, 256), 256, 0, st>>>(gyT, gkT[0], gkT[1], gkT[2], gkT[3], NS, (int64_t)nHB);

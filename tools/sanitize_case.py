@@ -12,12 +12,14 @@ for (B, L, C, H, HH, n) in [(130, 3, 100, 128, 128, 3), (70, 3, 5, 16, 32, 2)]:
     func = O.SharedMLPField(C, H, HH, n).cuda()
     coeffs = tc.linear_interpolation_coeffs(x.cuda(), rectilinear=0)
     X = tc.LinearInterpolation(coeffs)
-    for prec in ("bf16", "fp32"):
+    for prec in (sys.argv[1:2] or ["bf16", "fp32"]) if len(sys.argv) > 1 else ("bf16", "fp32"):
         z0 = (torch.randn(B, H) * 0.5).cuda().requires_grad_(True)
         out = tc.cdeint(X, func, z0, X.grid_points, adjoint=False, method="rk4", options={"step_size": 1, "precision": prec})
         out.sum().backward()
         torch.cuda.synchronize()
         print("ok", B, C, H, prec, float(out.abs().max()))
+if len(sys.argv) > 1:
+    sys.exit(0)
 x = torch.randn(6, 6, 4); x[..., 0] = torch.arange(6, dtype=torch.float32)
 Xc = tc.NaturalCubicSpline(tc.natural_cubic_coeffs(x.cuda()))
 func = O.SharedMLPField(4, 8, 8, 2).cuda()
