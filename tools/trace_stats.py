@@ -1,6 +1,6 @@
 """Summarise an NCDE_PS_TRACE dump: period per stage and the timeline of one whole stage (all traced tiles) of the traced h-group."""
 import sys, statistics as st
-NAMES = {"fwd": ["flag", "A_in", "mma", "epi_end", "signal", "h_cnt", "z_in", "L0mma", "L0epi", "L1mma", "L1epi", "stored", "released"],
+NAMES = {"fwd": ["flag", "A_in", "mma", "epi_end", "signal", "h_cnt", "z_in", "L0mma", "L0epi", "Llast_mma", "Llast_epi", "stored", "released"],
          "bwd": ["pre_issued", "A_in", "epi1_start", "epi1_end", "epi2_start", "epi2_end", "signal", "h_cnt", "top", "Lmma", "Lepi", "L0mma", "dz",
                  "released", "bias_end", "wgrad_done", "gk_flag", "gk_ready", "blk0", "blk1", "dg_issued", "wg_issued", "e22", "e23"] + ["w%d_e1end" % w for w in range(8)] + ["w%d_start" % w for w in range(8)]}
 for kind in ("fwd", "bwd"):
