@@ -1208,6 +1208,9 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
         const int bs_slot = lane % bs_S, bs_rsub = lane / bs_S, bs_R = 32 / bs_S;
         const int bs_chunk = a.Hg >= 2 ? h_begin * (a.Cp >> 3) + bs_slot : (bs_slot >> 1) * 4 + cg * 2 + (bs_slot & 1);
         const bool bs_on = bs_slot < bs_nc;
+        // one-row groups: the eight lanes of a quarter-warp read chunks of BOTH 64-column blocks, whose 16-byte positions coincide in the
+        // swizzled rows; the lanes of the second block take the row two below / above instead (position ^ 2: disjoint again)
+        const int bs_rx = (narrow && ((bs_chunk >> 3) & 1)) ? 2 : 0;
         float bacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
@@ -1332,7 +1335,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     for (int p = 0; p < NSP; ++p) {
                         uint32_t w4[4];
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
-                                     : "r"(gs_s + (uint32_t)p * L.g_part + sw128_off(r, bs_chunk, kTcM)));
+                                     : "r"(gs_s + (uint32_t)p * L.g_part + sw128_off(r ^ bs_rx, bs_chunk, kTcM)));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             bacc[2 * j] += __uint_as_float(w4[j] << 16);
