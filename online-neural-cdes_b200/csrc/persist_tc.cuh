@@ -214,10 +214,18 @@ __device__ __forceinline__ void ps_issue_kmajor(uint32_t d_tmem, uint32_t a_sadd
     }
 }
 // D[128 x N] (+)= A . B^T for NSP-part operands, both K-major swizzled tiles [rows][128] (two 64-column blocks): hi*hi (+ lo*hi + hi*lo)
-template <int NSP>
+template <int NSP, bool ROLLED = false>
 __device__ __forceinline__ void ps_gemm_kmajor(uint32_t d_tmem, uint32_t a_s, uint32_t a_part_bytes, int a_rows, uint32_t b_s,
                                                uint32_t b_part_bytes, int b_rows, int N) {
     (void)a_rows;
+    if (ROLLED) {
+        // backward field role: the operand pairs are a rolled loop — the issuing thread is back-pressured by the tensor pipe anyway, and
+        // every unrolled tcgen05.mma site costs ~13 instructions of an instruction cache the epilogue warps need (measured: -5 %)
+#pragma unroll 1
+        for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr)
+            ps_issue_kmajor(d_tmem, a_s + (pr == 1 ? a_part_bytes : 0u), b_s + (pr == 2 ? b_part_bytes : 0u), b_rows, N, pr == 0);
+        return;
+    }
     ps_issue_kmajor(d_tmem, a_s, b_s, b_rows, N, true);
     if (NSP == 2) {
         ps_issue_kmajor(d_tmem, a_s + a_part_bytes, b_s, b_rows, N, false);
@@ -980,7 +988,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 // epilogue 1 of unit i-2 (the last G block of unit i-1 was awaited below, so that one is long complete)
                 if (!pre2 && i > 0) ps_wait(done2, ph ^ 1u);
                 tc_fence_after();
-                ps_gemm_kmajor<NSP>(tmem_base + ((pre2 && (i & 1)) ? 384u : 0u), As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
+                ps_gemm_kmajor<NSP, true>(tmem_base + ((pre2 && (i & 1)) ? 384u : 0u), As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
                 PS_LEAD(umma_commit((pre2 && (i & 1)) ? pre_bar2 : pre_bar));
                 ps_syncwarp();
                 if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
@@ -992,7 +1000,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     // dgrad: D[128 x KP] (+)= G (K-major over n) . W3 (MN-major: N = k contiguous, K = n rows), the (up to) four k-steps
                     // that read block blk of G; fully unrolled, descriptors advanced from one base per operand
                     const int nk = min(4, nks - 4 * blk);
-#pragma unroll
+#pragma unroll 1
                     for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
                         const uint64_t gd = make_sdesc(Gs_s + (pr == 1 ? L.g_part : 0u) + (uint32_t)blk * (uint32_t)kTcM * 128u, 16, 1024);
                         const uint64_t wd = make_sdesc(Ws_s + (pr == 2 ? w_part : 0u) + (uint32_t)blk * 8192u, (uint32_t)Npad * 128u, 1024);
@@ -1044,7 +1052,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     const int nb = min(64, Npad - 64 * blk);
                     const uint32_t idesc = make_idesc(KP, nb, 1, 1);
                     const uint32_t g_blk_off = (uint32_t)blk * (uint32_t)kTcM * 128u;
-#pragma unroll
+#pragma unroll 1
                     for (int pi = 0; pi < (NSP == 2 ? 3 : 1); ++pi) {
                         const int pr = NSP == 2 ? (pi == 0 ? 1 : (pi == 1 ? 0 : 2)) : 0;     // the pair that reads A's lo part goes first
                         const uint64_t ad = make_sdesc(As_s + (pr == 1 ? kTcHidTile : 0u), (uint32_t)kTcM * 128u, 1024);
@@ -1236,7 +1244,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             tc_fence_after();
             const uint32_t pre_addr = lane_addr + ((pre2 && (i & 1)) ? 384u : 0u);
             // ---- epilogue 1 ----
-            PsHalf HA, HB;
+            PsHalf H, Hn;             // 16 accumulator columns being worked on / in flight from TMEM
             int nb_done = 0;          // 64-column blocks of the G tile this warp has handed over
             // every column of mine below `col` is written: hand over the blocks that lie entirely below it
             auto hand_over = [&](int col) {
@@ -1251,42 +1259,64 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 }
             };
             if (narrow) {
-                // one hidden row: 16-column chunk j is warp group (j & 1)'s; four chunks per trip keep HA / HB statically named
-                const float gk = gkv[0];
-                if (cg < xq.nch) ps_half_issue(HA, pre_addr + (uint32_t)(16 * cg));
-                else hand_over(1 << 30);
-                for (int j2 = 0; j2 < xq.nch; j2 += 4) {
+            // ONE loop over the ring slots of the unit with ONE inlined copy of the 16-column body (the epilogue code of this kernel
+            // must stay small: with a copy per accumulator buffer and per unrolled chunk the kernel outgrew the instruction cache —
+            // 17 % of its stall samples were instruction fetches).  A slot holds 32 channels of one hidden row (two halves) or, with
+            // one-row groups, 16 channels (chunk j is warp group (j & 1)'s).  The accumulator columns of my next half are loaded
+            // from TMEM while the current half is worked on; they change registers by 16 moves after the wait.
+            const int n_slots = narrow ? xq.nch : xq.n_pass * xq.nch;
+            const int nh = narrow ? 1 : 2;
+            auto half_col = [&](int sidx, int hf) -> int {     // first accumulator column of half (sidx, hf) if it is mine and not empty, else -1
+                if (narrow) return ((sidx & 1) == cg) ? 16 * sidx : -1;
+                const int p = sidx / xq.nch, j = sidx - p * xq.nch;
+                if (h_begin + p >= h_end) return -1;
+                const int c = 32 * j + 16 * hf;
+                return c < a.Cp ? (h_begin + p) * a.Cp + c : -1;
+            };
+            auto next_mine = [&](int sidx, int hf) -> int {    // first column of my next half after (sidx, hf), or 1 << 30
+                for (;;) {
+                    if (hf + 1 < nh) ++hf; else { hf = 0; ++sidx; }
+                    if (sidx >= n_slots) return 1 << 30;
+                    const int c = half_col(sidx, hf);
+                    if (c >= 0) return c;
+                }
+            };
+            {
+                const int c0 = next_mine(-1, nh - 1);
+                if (c0 < (1 << 30)) ps_half_issue(Hn, pre_addr + (uint32_t)c0);
+                hand_over(c0);
+            }
+#pragma unroll 1
+            for (int sidx = 0; sidx < n_slots; ++sidx) {
+                ps_wait(x_full + slot, lap & 1u);
+#pragma unroll 1
+                for (int hf = 0; hf < nh; ++hf) {
+                    const int col = half_col(sidx, hf);
+                    if (col >= 0) {
+                        const int p = narrow ? 0 : sidx / xq.nch;
+                        const float gk = p == 0 ? gkv[0] : (p == 1 ? gkv[1] : (p == 2 ? gkv[2] : gkv[3]));
+                        const int c_local = narrow ? col : col - (h_begin + p) * a.Cp;
+                        const int nv = min(16, a.Cp - c_local);
+                        const uint32_t xs = xs_row + (uint32_t)slot * xslot + (hf ? 64u : 0u);
+                        tmem_wait_ld<16>(Hn.r);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = j2 + u;
-                        if (j < xq.nch) {
-                            ps_wait(x_full + slot, lap & 1u);
-                            if ((u & 1) == cg) {
-                                const int c = 16 * j, jn = j + 2;
-                                const int nv = min(16, a.Cp - c);
-                                const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlotN;
-                                const bool more = jn < xq.nch;
-                                if (u < 2) {
-                                    tmem_wait_ld<16>(HA.r);
-                                    if (more) ps_half_issue(HB, pre_addr + (uint32_t)(16 * jn));
-                                    ps_bwd_half<NSP, EXACT>(HA, nv, gk, b3_s + 4u * c, xs, gs_s, L.g_part, row, c);
-                                } else {
-                                    tmem_wait_ld<16>(HB.r);
-                                    if (more) ps_half_issue(HA, pre_addr + (uint32_t)(16 * jn));
-                                    ps_bwd_half<NSP, EXACT>(HB, nv, gk, b3_s + 4u * c, xs, gs_s, L.g_part, row, c);
-                                }
-                                hand_over(more ? 16 * jn : (1 << 30));
-                            }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(x_free + slot);
-                            if (++slot == NX) { slot = 0; ++lap; }
-                        }
+                        for (int e = 0; e < 16; ++e) H.r[e] = Hn.r[e];
+                        const int next_col = next_mine(sidx, hf);
+                        if (next_col < (1 << 30)) ps_half_issue(Hn, pre_addr + (uint32_t)next_col);
+                        ps_bwd_half<NSP, EXACT>(H, nv, gk, b3_s + 4u * col, xs, gs_s, L.g_part, row, col);
+                        hand_over(next_col);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_free + slot);
+                if (++slot == NX) { slot = 0; ++lap; }
+            }
             } else {
+                // wider groups: both halves of a 32-channel chunk are mine; two named buffers, software-pipelined (the single-copy loop
+                // above was measured 17 % slower here: cfg 5 in bf16, 31.0 vs 26.6 ms per step)
             {
                 const bool any = h_begin < h_end;
-                if (any) ps_half_issue(HA, pre_addr + (uint32_t)(h_begin * a.Cp));
+                if (any) ps_half_issue(H, pre_addr + (uint32_t)(h_begin * a.Cp));
                 hand_over(any ? h_begin * a.Cp : (1 << 30));
             }
             for (int p = 0; p < xq.n_pass; ++p) {
@@ -1301,20 +1331,20 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         const int c = 32 * j;
                         const int nv0 = min(16, a.Cp - c), nv1 = max(0, min(16, a.Cp - c - 16));
                         const uint32_t xs = xs_row + (uint32_t)slot * kPsXSlot;
-                        tmem_wait_ld<16>(HA.r);
-                        if (nv1 > 0) ps_half_issue(HB, pre_addr + (uint32_t)(colbase + c + 16));
-                        ps_bwd_half<NSP, EXACT>(HA, nv0, gk, b3_s + 4u * (colbase + c), xs, gs_s, L.g_part, row, colbase + c);
-                        tmem_wait_ld<16>(HB.r);
+                        tmem_wait_ld<16>(H.r);
+                        if (nv1 > 0) ps_half_issue(Hn, pre_addr + (uint32_t)(colbase + c + 16));
+                        ps_bwd_half<NSP, EXACT>(H, nv0, gk, b3_s + 4u * (colbase + c), xs, gs_s, L.g_part, row, colbase + c);
+                        tmem_wait_ld<16>(Hn.r);
                         int next_col = 1 << 30;     // first column of my next chunk in this unit
                         {
                             int pn = p, jn = j + 1;
                             if (jn >= xq.nch) { pn = p + 1; jn = 0; }
                             if (pn < xq.n_pass && h_begin + pn < h_end && jn < xq.nch) {
                                 next_col = (h_begin + pn) * a.Cp + 32 * jn;
-                                ps_half_issue(HA, pre_addr + (uint32_t)next_col);
+                                ps_half_issue(H, pre_addr + (uint32_t)next_col);
                             }
                         }
-                        ps_bwd_half<NSP, EXACT>(HB, nv1, gk, b3_s + 4u * (colbase + c + 16), xs + 64u, gs_s, L.g_part, row, colbase + c + 16);
+                        ps_bwd_half<NSP, EXACT>(Hn, nv1, gk, b3_s + 4u * (colbase + c + 16), xs + 64u, gs_s, L.g_part, row, colbase + c + 16);
                         hand_over(next_col);
                     }
                     __syncwarp();
