@@ -901,6 +901,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* x_free = bars + 20;     // [NX <= 8]
     uint64_t* pre_bar2 = bars + 28;   // second recompute accumulator (Npad <= 128)
     uint64_t* g_blk = bars + 29;      // [<= 4] epilogue -> MMA issuers: 64-column block b of the G tile written by all 8 warps
+    uint64_t* full_lo = bars + 36;    // bf16x3: the lo part of the activation tile has landed (full_a: the hi part)
     uint64_t* lo_bar = bars + 33;     // wgrad issuer -> producer: every MMA that reads the lo part of the activation tile has completed
     float* gks = reinterpret_cast<float*>(smem + L.gks);
     const int n_blk = (Npad + 63) >> 6;
@@ -924,7 +925,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     if (tid == 0 && blockIdx.x == 0) g_ps_dbg_bars = smem_u32(bars);
 #endif
     if (tid == 0) {
-        mbar_init(full_a, NSP == 2 ? 2 : 1);      // bf16x3: the two parts of the tile are loaded separately (two expect_tx arrivals)
+        mbar_init(full_a, 1); mbar_init(full_lo, 1);   // bf16x3: the two parts of the tile are loaded separately
         mbar_init(wg_bar, 1); mbar_init(gk_full, 1); mbar_init(pre_bar, 1); mbar_init(pre_bar2, 1);
         for (int i = 0; i < 4; ++i) mbar_init(g_blk + i, EW);
         mbar_init(gk_free, EW); mbar_init(lo_bar, 1);
@@ -956,14 +957,18 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             ps_syncwarp();
             // The saved records are cold (1-2 GB written by the forward pass): the tile of unit i+1 is pulled into L2 while unit i is
             // being worked on, so that its TMA — which can only start when wgrad(i) has released the buffer — is an L2 hit.
-            // parts [p0, p1) of the activation tile of unit i; full_a completes when both parts have landed (two expect_tx arrivals)
+            // Parts [p0, p1) of the activation tile of unit i.  bf16x3: the two halves of the buffer swap roles from unit to unit — the half
+            // that the weight-gradient MMAs release first (it held the lo part, which one operand pair of three reads) receives the HI
+            // part of the next tile, so that two thirds of the next recompute GEMM run before the other half is free at all.
             auto load_A = [&](int i, int p0, int p1) {
                 if (ps_elect()) {
                     const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
-                    mbar_expect_tx(full_a, (uint32_t)(p1 - p0) * kTcHidTile);
                     for (int p = p0; p < p1; ++p) {
-                        tma_load_4d(As + (size_t)p * kTcHidTile, &maps.act[a.F], full_a, 0, u.t * kTcM, p, u.q);
-                        tma_load_4d(As + (size_t)p * kTcHidTile + kTcHidTile / 2, &maps.act[a.F], full_a, 64, u.t * kTcM, p, u.q);
+                        uint64_t* bar = p == 0 ? full_a : full_lo;
+                        uint8_t* dst = As + (size_t)(NSP == 2 ? (p ^ (i & 1)) : p) * kTcHidTile;
+                        mbar_expect_tx(bar, kTcHidTile);
+                        tma_load_4d(dst, &maps.act[a.F], bar, 0, u.t * kTcM, p, u.q);
+                        tma_load_4d(dst + kTcHidTile / 2, &maps.act[a.F], bar, 64, u.t * kTcM, p, u.q);
                     }
                     if (p0 == 0 && i + 1 < n_units) {
                         const PsUnit v = ps_unit_bwd(i + 1, n_my, part, a.n_part, n_q);
@@ -975,20 +980,32 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 }
                 ps_syncwarp();
             };
-            if (NSP == 2) load_A(0, 1, 2);
-            load_A(0, 0, 1);
+            load_A(0, 0, NSP);
             ps_wait(w_bar, 0);
             const uint32_t As_s = smem_u32(As), Ws_s = smem_u32(Ws), Gs_s = smem_u32(Gs);
             for (int i = 0; i < n_units; ++i) {
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);
-                if (lane == 0) { ps_trace(a, u.t, g, n_q - 1 - u.q, 1); ps_trace_all(a, u.t, g + part * a.n_hg, n_q - 1 - u.q, 1); }
                 // one accumulator: epilogue 2 of the previous unit must have read P out of it; two: accumulator i & 1 was released by
                 // epilogue 1 of unit i-2 (the last G block of unit i-1 was awaited below, so that one is long complete)
                 if (!pre2 && i > 0) ps_wait(done2, ph ^ 1u);
                 tc_fence_after();
-                ps_gemm_kmajor<NSP, true>(tmem_base + ((pre2 && (i & 1)) ? 384u : 0u), As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
+                {
+                    const uint32_t d0 = tmem_base + ((pre2 && (i & 1)) ? 384u : 0u);
+                    if (NSP == 2) {
+                        // hi . W_hi + hi . W_lo as soon as the hi part is there, lo . W_hi when the other half has been freed and filled
+                        const uint32_t a_hi = As_s + ((i & 1) ? kTcHidTile : 0u), a_lo = As_s + ((i & 1) ? 0u : kTcHidTile);
+#pragma unroll 1
+                        for (int w = 0; w < 2; ++w) ps_issue_kmajor(d0, a_hi, Ws_s + (w ? w_part : 0u), Npad, Npad, w == 0);
+                        ps_wait(full_lo, ph);
+                        tc_fence_after();
+                        ps_issue_kmajor(d0, a_lo, Ws_s, Npad, Npad, false);
+                    } else {
+                        ps_gemm_kmajor<NSP, true>(d0, As_s, kTcHidTile, kTcM, Ws_s, w_part, Npad, Npad);
+                    }
+                }
+                if (lane == 0) { ps_trace(a, u.t, g, n_q - 1 - u.q, 1); ps_trace_all(a, u.t, g + part * a.n_hg, n_q - 1 - u.q, 1); }
                 PS_LEAD(umma_commit((pre2 && (i & 1)) ? pre_bar2 : pre_bar));
                 ps_syncwarp();
                 if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 0);
@@ -1026,11 +1043,11 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 if (i + 1 < n_units) {
                     // the activation tile is released by the wgrad issuer (warp 9): the lo part first, so that half of the next tile's
                     // load runs under the remaining weight-gradient MMAs
-                    if (NSP == 2) { ps_wait(lo_bar, ph); load_A(i + 1, 1, 2); }
+                    while (*sig_done < i) {}                     // keeps the signaller within one unit of the pipeline
+                    if (NSP == 2) { ps_wait(lo_bar, ph); load_A(i + 1, 0, 1); }      // hi part of the next tile -> the half released first
                     ps_wait(wg_bar, ph);
                     if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 15);
-                    while (*sig_done < i) {}                     // keeps the signaller within one unit of the pipeline
-                    load_A(i + 1, 0, 1);
+                    load_A(i + 1, NSP == 2 ? 1 : 0, NSP == 2 ? 2 : 1);
                 }
             }
         }
@@ -1045,6 +1062,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const PsUnit u = ps_unit_bwd(i, n_my, part, a.n_part, n_q);
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);                                  // (long complete: the producer's recompute MMAs have read the tile)
+                if (NSP == 2) ps_wait(full_lo, ph);
                 for (int blk = 0; blk < n_blk; ++blk) {
                     ps_wait(g_blk + blk, ph);                         // block written by all 8 warps
                     tc_fence_after();
@@ -1055,7 +1073,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
 #pragma unroll 1
                     for (int pi = 0; pi < (NSP == 2 ? 3 : 1); ++pi) {
                         const int pr = NSP == 2 ? (pi == 0 ? 1 : (pi == 1 ? 0 : 2)) : 0;     // the pair that reads A's lo part goes first
-                        const uint64_t ad = make_sdesc(As_s + (pr == 1 ? kTcHidTile : 0u), (uint32_t)kTcM * 128u, 1024);
+                        const uint64_t ad = make_sdesc(As_s + ((NSP == 2 && ((pr == 1) != ((i & 1) != 0))) ? kTcHidTile : 0u), (uint32_t)kTcM * 128u, 1024);   // bf16x3: halves swap per unit
                         const uint64_t gd = make_sdesc(Gs_s + (pr == 2 ? L.g_part : 0u) + g_blk_off, (uint32_t)kTcM * 128u, 1024);
 #pragma unroll
                         for (int ks = 0; ks < kTcM / 16; ++ks) {
