@@ -43,6 +43,18 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_mn, int b_mn, in
             fence_async_smem();
         }
         __syncthreads();
+        if ((MODE == 4 || MODE == 5 || MODE == 6) && warp >= 1) {
+            // background shared-memory traffic from three warps into a scratch region above the operand tiles, for roughly as long as the batch lasts
+            const uint32_t scratch = smem_u32(smem + 140 * 1024) + (uint32_t)(tid - 32) * 16u;
+            uint32_t acc = 0;
+            const int iters = MODE == 6 ? n_mma / 4 : n_mma * 4;
+            for (int it = 0; it < iters; ++it) {
+                if (MODE == 4 || MODE == 6) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(scratch + (uint32_t)(it & 7) * 1536u), "r"(acc + it));
+                else { uint32_t v0, v1, v2, v3; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(scratch + (uint32_t)(it & 7) * 1536u)); acc += v0 ^ v3; }
+                if (MODE == 6) __nanosleep(200);
+            }
+            if (acc == 0x12345678u) out[3] = acc;
+        }
         if (issuer) {
             const uint32_t a_s = smem_u32(smem), b_s = smem_u32(smem + 64 * 1024);
             const uint32_t idesc = make_idesc(128, N, a_mn, b_mn);
@@ -82,7 +94,7 @@ static void run(long long* d, const char* name) {
     cudaFuncSetAttribute(mma_rate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int cfgs[][3] = {{0, 0, 112}, {0, 0, 208}, {0, 0, 256}, {0, 1, 128}, {1, 1, 112}, {1, 1, 64}, {1, 1, 48}, {1, 1, 208}};
     for (auto& c : cfgs) {
-        const int n_mma = 24;
+        const int n_mma = 96;
         mma_rate_kernel<MODE><<<1, 128, 200 * 1024>>>(c[0], c[1], c[2], n_mma, 20, d);
         long long h[2] = {0, 0}; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         cudaError_t e = cudaDeviceSynchronize();
@@ -91,8 +103,10 @@ static void run(long long* d, const char* name) {
     }
 }
 int main() {
-    long long* d; cudaMalloc(&d, 16);
+    long long* d; cudaMalloc(&d, 64);
     run<0>(d, "one-thread");
-    run<3>(d, "st.shared-A");
+    run<4>(d, "bg st.shared");
+    run<5>(d, "bg ld.shared");
+    run<6>(d, "bg sparse st");
     return 0;
 }
