@@ -930,7 +930,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
         for (int i = 0; i < 4; ++i) mbar_init(g_blk + i, EW);
         mbar_init(gk_free, EW); mbar_init(lo_bar, 1);
         mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
-        for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
+        for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, ps_bwd_narrow(a.Hg) ? 4 : 8); }
         *sig_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1221,6 +1221,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
         const uint32_t xs_row = smem_u32(Xs) + (uint32_t)row * ((narrow ? kPsXPitchN : kPsXPitch) * 4);
         int slot = 0;
         uint32_t lap = 0;
+        uint32_t xbase = 0;        // one-row groups: chunks of all earlier units (the ring position of a chunk follows from its number)
         const int col_begin = (cg * Npad / kCg) & ~15;
         const int col_end = cg == kCg - 1 ? Npad : (((cg + 1) * Npad / kCg) & ~15);
         const uint32_t b3_s = smem_u32(b3s), gs_s = smem_u32(Gs);
@@ -1277,58 +1278,33 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 }
             };
             if (narrow) {
-            // ONE loop over the ring slots of the unit with ONE inlined copy of the 16-column body (the epilogue code of this kernel
-            // must stay small: with a copy per accumulator buffer and per unrolled chunk the kernel outgrew the instruction cache —
-            // 17 % of its stall samples were instruction fetches).  A slot holds 32 channels of one hidden row (two halves) or, with
-            // one-row groups, 16 channels (chunk j is warp group (j & 1)'s).  The accumulator columns of my next half are loaded
-            // from TMEM while the current half is worked on; they change registers by 16 moves after the wait.
-            const int n_slots = narrow ? xq.nch : xq.n_pass * xq.nch;
-            const int nh = narrow ? 1 : 2;
-            auto half_col = [&](int sidx, int hf) -> int {     // first accumulator column of half (sidx, hf) if it is mine and not empty, else -1
-                if (narrow) return ((sidx & 1) == cg) ? 16 * sidx : -1;
-                const int p = sidx / xq.nch, j = sidx - p * xq.nch;
-                if (h_begin + p >= h_end) return -1;
-                const int c = 32 * j + 16 * hf;
-                return c < a.Cp ? (h_begin + p) * a.Cp + c : -1;
-            };
-            auto next_mine = [&](int sidx, int hf) -> int {    // first column of my next half after (sidx, hf), or 1 << 30
-                for (;;) {
-                    if (hf + 1 < nh) ++hf; else { hf = 0; ++sidx; }
-                    if (sidx >= n_slots) return 1 << 30;
-                    const int c = half_col(sidx, hf);
-                    if (c >= 0) return c;
-                }
-            };
-            {
-                const int c0 = next_mine(-1, nh - 1);
-                if (c0 < (1 << 30)) ps_half_issue(Hn, pre_addr + (uint32_t)c0);
-                hand_over(c0);
-            }
+                // One hidden row per group: 16-channel chunk j of the unit is warp group (j & 1)'s and ONLY that group's — it alone waits
+                // for the slot and releases it (x_free counts 4 arrivals in this mode), so a warp runs 3-4 hand-shakes per unit, not 7.
+                // ONE inlined copy of the 16-column body (with a copy per accumulator buffer and per unrolled chunk the kernel had outgrown
+                // the instruction cache: 17 % of its stall samples were instruction fetches): the accumulator columns of my next chunk
+                // are loaded from TMEM while the current one is worked on and change registers by 16 moves after the wait.
+                const float gk = gkv[0];
+                if (cg < xq.nch) ps_half_issue(Hn, pre_addr + (uint32_t)(16 * cg));
+                else hand_over(1 << 30);
 #pragma unroll 1
-            for (int sidx = 0; sidx < n_slots; ++sidx) {
-                ps_wait(x_full + slot, lap & 1u);
-#pragma unroll 1
-                for (int hf = 0; hf < nh; ++hf) {
-                    const int col = half_col(sidx, hf);
-                    if (col >= 0) {
-                        const int p = narrow ? 0 : sidx / xq.nch;
-                        const float gk = p == 0 ? gkv[0] : (p == 1 ? gkv[1] : (p == 2 ? gkv[2] : gkv[3]));
-                        const int c_local = narrow ? col : col - (h_begin + p) * a.Cp;
-                        const int nv = min(16, a.Cp - c_local);
-                        const uint32_t xs = xs_row + (uint32_t)slot * xslot + (hf ? 64u : 0u);
-                        tmem_wait_ld<16>(Hn.r);
+                for (int j = cg; j < xq.nch; j += 2) {
+                    const uint32_t cj = xbase + (uint32_t)j;                // running chunk number -> ring position
+                    const uint32_t xlap = cj / (uint32_t)NX, xslot_i = cj - xlap * (uint32_t)NX;
+                    ps_wait(x_full + xslot_i, xlap & 1u);
+                    const int col = 16 * j, jn = j + 2;
+                    const int nv = min(16, a.Cp - col);
+                    const uint32_t xs = xs_row + xslot_i * xslot;
+                    tmem_wait_ld<16>(Hn.r);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) H.r[e] = Hn.r[e];
-                        const int next_col = next_mine(sidx, hf);
-                        if (next_col < (1 << 30)) ps_half_issue(Hn, pre_addr + (uint32_t)next_col);
-                        ps_bwd_half<NSP, EXACT>(H, nv, gk, b3_s + 4u * col, xs, gs_s, L.g_part, row, col);
-                        hand_over(next_col);
-                    }
+                    for (int e = 0; e < 16; ++e) H.r[e] = Hn.r[e];
+                    const int next_col = jn < xq.nch ? 16 * jn : (1 << 30);
+                    if (jn < xq.nch) ps_half_issue(Hn, pre_addr + (uint32_t)next_col);
+                    ps_bwd_half<NSP, EXACT>(H, nv, gk, b3_s + 4u * col, xs, gs_s, L.g_part, row, col);
+                    hand_over(next_col);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_free + xslot_i);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(x_free + slot);
-                if (++slot == NX) { slot = 0; ++lap; }
-            }
+                xbase += (uint32_t)xq.nch;
             } else {
                 // wider groups: both halves of a 32-channel chunk are mine; two named buffers, software-pipelined (the single-copy loop
                 // above was measured 17 % slower here: cfg 5 in bf16, 31.0 vs 26.6 ms per step)
