@@ -1034,13 +1034,11 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                     if (blk == 0 && pre2 && i > 0) ps_wait(done2, ph ^ 1u);      // P of the previous unit has been read out
                     tc_fence_after();
                     const bool last = blk == n_blk - 1;
-                    // (pre2 and several blocks: the k-steps of the LAST block are issued by the weight-gradient thread, behind its MMAs —
-                    // the release of the activation tile is on the critical path of the unit, epilogue 2 has the bias pass to wait under)
-                    if (pre2) { if (!last || n_blk == 1) issue_dgrad(blk, blk == 0); }
+                    if (pre2) issue_dgrad(blk, blk == 0);
                     else if (last) {                                  // P re-uses the columns of pre: every warp has read it out by now
                         for (int b2 = 0; b2 < n_blk; ++b2) issue_dgrad(b2, b2 == 0);
                     }
-                    if (last && !(pre2 && n_blk > 1)) { PS_LEAD(umma_commit(dg_bar)); if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 20); }
+                    if (last) { PS_LEAD(umma_commit(dg_bar)); if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 20); }
                 }
                 if (i + 1 < n_units) {
                     // the activation tile is released by the wgrad issuer (warp 9): the lo part first, so that half of the next tile's
@@ -1088,24 +1086,6 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 }
                 PS_LEAD(umma_commit(wg_bar));
                 if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 21);
-                if (pre2 && n_blk > 1) {
-                    // last k-steps of dgrad (see the producer): P (+)= G block . W3; MMAs on one accumulator complete in issue order, so this
-                    // thread's commit also covers the producer's earlier k-steps
-                    const int blk = n_blk - 1, nk = min(4, Npad / 16 - 4 * blk);
-                    const uint32_t idesc_dg = make_idesc(kTcM, KP, 0, 1);
-                    const uint32_t Ws_s = smem_u32(Ws);
-#pragma unroll 1
-                    for (int pr = 0; pr < (NSP == 2 ? 3 : 1); ++pr) {
-                        const uint64_t gd = make_sdesc(Gs_s + (pr == 1 ? L.g_part : 0u) + (uint32_t)blk * (uint32_t)kTcM * 128u, 16, 1024);
-                        const uint64_t wd = make_sdesc(Ws_s + (pr == 2 ? w_part : 0u) + (uint32_t)blk * 8192u, (uint32_t)Npad * 128u, 1024);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            if (kk < nk)
-                                ps_umma(tmem_base + p_col, ps_desc_advance(gd, (uint32_t)kk * 32u), ps_desc_advance(wd, (uint32_t)kk * 2048u), idesc_dg, 1u);
-                    }
-                    PS_LEAD(umma_commit(dg_bar));
-                    if (lane == 0) ps_trace(a, u.t, g, n_q - 1 - u.q, 20);
-                }
             }
             PS_LEAD(umma_commit(fin_bar));
         }
