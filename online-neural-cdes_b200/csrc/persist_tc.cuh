@@ -869,6 +869,13 @@ __device__ __forceinline__ PsUnit ps_unit_bwd(int i, int n_my, int part, int n_p
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// four consecutive floats in one reduction (16-byte aligned): a quarter of the instructions and LSU slots of the scalar form
+__device__ __forceinline__ void red_add_f32x4(float* p, float v0, float v1, float v2, float v3) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+}
+// dA^T of a tile, summed over the h-groups in L2: [32 k-quads][128 rows][4] floats — a thread (= row) owns four consecutive k as one
+// 16-byte word, and the rows of a warp are contiguous: red.v4 / ld.cg.v4 / st.cg.v4, 512 contiguous bytes per warp instruction
+__device__ __forceinline__ size_t ps_dat_index(int kq, int row) { return ((size_t)kq * 128 + row) * 4; }
 
 // backward of one RK stage for one batch tile (cf. tc_field_bwd_kernel): MMA1 recompute pre -> epilogue 1 G -> dgrad P, wgrad
 // dW^T (stays in TMEM for the whole pass) -> epilogue 2: P summed over the h-groups with red.global into the tile's fp32 dA^T
@@ -1375,19 +1382,23 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             // ---- epilogue 2: this h-group's share of dL/d(final-layer input), summed over the groups in L2 ----
             {
                 const int kb = cg * (KP / kCg);
-                float* dcol = a.dAT + ((size_t)un.t * 128 + kb) * 128 + row;
+                float* dtile = a.dAT + (size_t)un.t * 128 * 128;
                 uint32_t r0[32], r1[32];
                 tmem_ld32_issue(lane_addr + p_col + (uint32_t)kb, r0);
                 tmem_wait_ld<32>(r0);
                 tmem_ld32_issue(lane_addr + p_col + (uint32_t)kb + 32u, r1);
                 if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) red_add_f32(dcol + (size_t)j * 128, __uint_as_float(r0[j]));
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        red_add_f32x4(dtile + ps_dat_index(kb / 4 + j4, row), __uint_as_float(r0[4 * j4]), __uint_as_float(r0[4 * j4 + 1]),
+                                      __uint_as_float(r0[4 * j4 + 2]), __uint_as_float(r0[4 * j4 + 3]));
                 }
                 tmem_wait_ld<32>(r1);
                 if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) red_add_f32(dcol + (size_t)(32 + j) * 128, __uint_as_float(r1[j]));
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        red_add_f32x4(dtile + ps_dat_index(kb / 4 + 8 + j4, row), __uint_as_float(r1[4 * j4]), __uint_as_float(r1[4 * j4 + 1]),
+                                      __uint_as_float(r1[4 * j4 + 2]), __uint_as_float(r1[4 * j4 + 3]));
                 }
             }
             tc_fence_before();
@@ -1561,7 +1572,7 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
             // ---- top: dpre_{F-1} = (sum over the h-groups of P) * act'(a_F) ----
             ps_wait(top_bar, (uint32_t)i & 1u);
             {
-                float* dcol = a.dAT + ((size_t)t * 128 + wg * 64) * 128 + row;
+                float* dtile = a.dAT + (size_t)t * 128 * 128;
                 const __nv_bfloat16* arow = recq + a.act_off[F] + (size_t)b * 128 + wg * 64;
                 const uint32_t dst = smem_u32(Dt + (size_t)((F - 1) & 1) * kOp);
                 const int act = a.act[F - 1];
@@ -1569,9 +1580,12 @@ __device__ void ps_hidden_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem
                 for (int c8 = 0; c8 < 8; ++c8) {
                     float v[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) v[jj] = __ldcg(dcol + (size_t)(c8 * 8 + jj) * 128);
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) __stcg(dcol + (size_t)(c8 * 8 + jj) * 128, 0.f);   // ready for the tile's next stage
+                    for (int j4 = 0; j4 < 2; ++j4) {
+                        float4* p4 = reinterpret_cast<float4*>(dtile + ps_dat_index(wg * 16 + c8 * 2 + j4, row));
+                        const float4 x4 = __ldcg(p4);
+                        v[4 * j4] = x4.x; v[4 * j4 + 1] = x4.y; v[4 * j4 + 2] = x4.z; v[4 * j4 + 3] = x4.w;
+                        __stcg(p4, make_float4(0.f, 0.f, 0.f, 0.f));   // ready for the tile's next stage
+                    }
                     uint4 av = make_uint4(0, 0, 0, 0), al = make_uint4(0, 0, 0, 0);
                     if (row_ok) {
                         av = __ldg(reinterpret_cast<const uint4*>(arow + c8 * 8));
