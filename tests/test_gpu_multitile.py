@@ -1,0 +1,83 @@
+"""The shard the bench measures — 1024 series = EIGHT 128-row batch tiles per GPU, cfg-5 shape at its full length — against solves
+of its parts, and through them against the single-tile solves that tests/test_gpu_cfg5_full.py pins to the oracle.
+
+Rows of a batch are independent, so the solve of the whole shard must reproduce the solves of its two 512-series halves (same tiling
+plan: the h-group width depends on the number of tiles, and with it the order of the per-row channel sums): the states exactly (the
+same per-row arithmetic wherever the row's tile sits in the sequence), the gradient of every row of z0 and the parameter gradients
+(sums over the rows) up to the order in which fp32 partial sums meet — the h-groups' shares of dL/d(input) are added in L2 with `red`,
+the weight gradients accumulate over tiles in TMEM instead of over sub-batches on the host.  The first 128-series tile is also solved
+alone (the single-tile path of the oracle tests, another plan) and must agree within the mode's stated parity bounds.
+
+With eight tiles in flight the persistent kernels run the hand-offs the single-tile tests cannot reach: a field CTA works on tile t of
+stage s while tile t' is still in stage s-1, the dL/dk warp runs a unit ahead across tiles, the dX/dt ring and the activation-buffer
+halves are reused by different tiles back to back.  Bounds (relative max-norm): gradient of z0 1e-5 (bf16x3), 2e-2 (bf16, measured 4e-3:
+the order of the fp32 `red`s differs from run to run, the sums are then ROUNDED to bf16 for the next GEMM, and a last-bit difference there
+is 2^-9 — carried through 568 stages); parameter gradients 1e-3 (bf16x3) — the final layer's weight gradient stays
+in ONE fp32 TMEM accumulator for the whole pass (4544 units here) and the tensor core's accumulation is grouping-sensitive at the 3-5e-4
+level (tools/diag_multitile.py: 1 x 1024 vs 2 x 512 tiles 4.7e-4, 2 x 512 vs 4 x 256 2.8e-4; every other parameter 1-2e-5), well inside
+what the mode's own arithmetic costs against the fp32 path (3e-3 for the shard and for a single tile alike)."""
+import copy
+
+import pytest
+import torch
+
+import parity_util as PU
+from oracle import cde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BOUNDS = {"bf16x3": 1e-5, "bf16": 2e-2}
+PARAM_BOUND = {"bf16x3": 1e-3, "bf16": 2e-2}
+MODE_BOUNDS = {"bf16x3": (1e-4, 1.5e-2), "bf16": (1e-2, 1.5e-1)}     # states, gradients: tests/test_gpu_cfg5_full.py
+
+
+def _solve(tc, func, c, z0, w, precision):
+    fd = copy.deepcopy(func).cuda()
+    X = tc.LinearInterpolation(c)
+    z = z0.clone().requires_grad_(True)
+    out = tc.cdeint(X, fd, z, X.grid_points, adjoint=False, method="rk4", options={"step_size": 1, "precision": precision})
+    (out * w).sum().backward()
+    torch.cuda.synchronize()
+    return out.detach(), z.grad.detach(), {n: p.grad.detach().clone() for n, p in fd.named_parameters()}
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_bench_shard_equals_its_parts(precision):
+    import bench
+    import torchcde_b200 as tc
+    from torchcde_b200 import solver
+    if precision not in solver._PRECISIONS:
+        pytest.skip("precision mode %s not built" % precision)
+    cfg = bench.CFG
+    B, T = 1024, 512
+    x, _, _ = bench.synth_batch(B, 11)
+    c = tc.linear_interpolation_coeffs(x.cuda(), rectilinear=0)
+    assert c.shape == (B, 143, cfg["C"])
+    torch.manual_seed(5)
+    func = O.SharedMLPField(cfg["C"], cfg["H"], cfg["HH"], cfg["n_layers"])
+    g = torch.Generator().manual_seed(6)
+    z0 = (torch.randn(B, cfg["H"], generator=g) * 0.5).cuda()
+    w = torch.randn(B, c.shape[1], cfg["H"], generator=g).cuda()
+
+    out, gz, gp = _solve(tc, func, c, z0, w, precision)
+    assert torch.isfinite(out).all() and torch.isfinite(gz).all()
+    gp_sum = {n: torch.zeros_like(v) for n, v in gp.items()}
+    for k in range(B // T):
+        rows = slice(k * T, (k + 1) * T)
+        o_k, gz_k, gp_k = _solve(tc, func, c[rows].contiguous(), z0[rows].contiguous(), w[rows].contiguous(), precision)
+        assert torch.equal(o_k, out[rows]), "states of half %d differ between the shard and the half solved alone" % k
+        e = PU.rel(gz[rows], gz_k)
+        assert e <= BOUNDS[precision], ("z0 gradient of half %d" % k, e)
+        for n in gp_sum:
+            gp_sum[n] += gp_k[n]
+    errs = {n: PU.rel(gp[n], gp_sum[n]) for n in gp}
+    print("bench shard vs its halves, %s: parameter gradients %s" % (precision, {k: "%.1e" % v for k, v in errs.items()}))
+    assert max(errs.values()) <= PARAM_BOUND[precision], errs
+    if precision == "bf16x3":
+        assert max(v for n, v in errs.items() if not n.startswith("tanh_output_layer")) <= 1e-4, errs
+    # one tile alone: the plan of the oracle-pinned single-tile tests
+    rows = slice(0, 128)
+    o_1, gz_1, _ = _solve(tc, func, c[rows].contiguous(), z0[rows].contiguous(), w[rows].contiguous(), precision)
+    e_s, e_g = PU.rel(out[rows], o_1), PU.rel(gz[rows], gz_1)
+    print("bench shard vs its first tile alone, %s: states %.1e, z0 gradient %.1e" % (precision, e_s, e_g))
+    assert e_s <= MODE_BOUNDS[precision][0] and e_g <= MODE_BOUNDS[precision][1], (e_s, e_g)
