@@ -26,6 +26,7 @@ namespace ncde {
 constexpr int kPsThreads = 384;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), 9 = signaller, 10 = dX/dt loader,
                                           // 11 = dL/dk former of the backward field role (idle elsewhere)
 constexpr int kPsEpi = 256;
+constexpr int kPsFlushUnits = 512;        // backward field role: units between two flushes of the TMEM-resident weight gradient
 constexpr long long kPsSpinLimit = 6000000000ll;   // ~3 s at 2 GHz: a protocol error traps instead of hanging the GPU
 
 struct PsMaps {
@@ -908,6 +909,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
     uint64_t* x_free = bars + 20;     // [NX <= 8]
     uint64_t* pre_bar2 = bars + 28;   // second recompute accumulator (Npad <= 128)
     uint64_t* g_blk = bars + 29;      // [<= 4] epilogue -> MMA issuers: 64-column block b of the G tile written by all 8 warps
+    uint64_t* flush_bar = bars + 38;  // epilogue -> wgrad thread: the weight-gradient accumulator has been added to the global sum (8 arrivals)
     uint64_t* full_lo = bars + 36;    // bf16x3: the lo part of the activation tile has landed (full_a: the hi part)
     uint64_t* lo_bar = bars + 33;     // wgrad issuer -> producer: every MMA that reads the lo part of the activation tile has completed
     float* gks = reinterpret_cast<float*>(smem + L.gks);
@@ -935,7 +937,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
         mbar_init(full_a, 1); mbar_init(full_lo, 1);   // bf16x3: the two parts of the tile are loaded separately
         mbar_init(wg_bar, 1); mbar_init(gk_full, 1); mbar_init(pre_bar, 1); mbar_init(pre_bar2, 1);
         for (int i = 0; i < 4; ++i) mbar_init(g_blk + i, EW);
-        mbar_init(gk_free, EW); mbar_init(lo_bar, 1);
+        mbar_init(gk_free, EW); mbar_init(lo_bar, 1); mbar_init(flush_bar, EW);
         mbar_init(dg_bar, 1); mbar_init(done2, EW); mbar_init(fin_bar, 1); mbar_init(w_bar, 1);
         for (int i = 0; i < kPsMaxSlots; ++i) { mbar_init(x_full + i, 1); mbar_init(x_free + i, ps_bwd_narrow(a.Hg) ? 4 : 8); }
         *sig_done = 0;
@@ -1070,6 +1072,10 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 const uint32_t ph = (uint32_t)i & 1u;
                 ps_wait(full_a, ph);                                  // (long complete: the producer's recompute MMAs have read the tile)
                 if (NSP == 2) ps_wait(full_lo, ph);
+                // every kPsFlushUnits units the epilogue warps add dW^T to the global fp32 sum and the accumulation starts afresh: one TMEM
+                // accumulator over a whole pass (4544 units x 24 MMAs on cfg 5) was grouping-sensitive at the 3-5e-4 level
+                const bool fresh = i % kPsFlushUnits == 0;
+                if (fresh && i > 0) ps_wait(flush_bar, (uint32_t)(i / kPsFlushUnits - 1) & 1u);
                 for (int blk = 0; blk < n_blk; ++blk) {
                     ps_wait(g_blk + blk, ph);                         // block written by all 8 warps
                     tc_fence_after();
@@ -1086,7 +1092,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                         for (int ks = 0; ks < kTcM / 16; ++ks) {
                             const uint32_t off = (uint32_t)ks * 2048u;
                             ps_umma(tmem_base + kTcDwCol + 64u * (uint32_t)blk, ps_desc_advance(ad, off), ps_desc_advance(gd, off), idesc,
-                                    (ks > 0 || pi > 0 || i > 0) ? 1u : 0u);
+                                    (ks > 0 || pi > 0 || !fresh) ? 1u : 0u);
                         }
                         if (NSP == 2 && pi == 0 && last) { PS_LEAD(umma_commit(lo_bar)); }
                     }
@@ -1235,6 +1241,19 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
         // Bias gradient = column sums of G.  Each warp sums exactly what it wrote — its 32 rows x its own 8-column chunks — right after
         // epilogue 1, while the tensor core works on dgrad (no CTA-wide barrier, no second reader of other warps' rows).  Lane = (chunk
         // slot, row subset); the slot -> chunk map is the same for every unit, so the running sums stay in registers for the whole pass.
+        // dW^T (TMEM lanes = k, columns = n) is ADDED to the global accumulator [part][g*Npad + n][k] (zeroed by the host): at the end of
+        // the pass and every kPsFlushUnits units on the way (this CTA alone owns its slice; a thread its lane k and half of the columns)
+        auto flush_dw = [&]() {
+            for (int n0 = col_begin; n0 < col_end; n0 += 16) {
+                float v[16];
+                tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float* p = a.dW3acc + (((size_t)part * a.n_hg + g) * Npad + n0 + j) * 128 + row;
+                    *p += v[j];
+                }
+            }
+        };
         int bs_nc;                                   // my 8-column chunks
         if (a.Hg >= 2) bs_nc = (h_end - h_begin) * (a.Cp >> 3);
         else { const int c8 = a.Cp >> 3; bs_nc = (c8 / 4) * 2 + max(0, min(2, c8 % 4 - 2 * cg)); }     // 16-column chunks j with j & 1 == cg
@@ -1405,6 +1424,14 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
             __syncwarp();
             if (tid == 0) { ps_trace(a, un.t, g, n_q - 1 - un.q, 5); ps_trace_all(a, un.t, g + part * a.n_hg, n_q - 1 - un.q, 5); }
             if (lane == 0) mbar_arrive(done2);
+            if ((i + 1) % kPsFlushUnits == 0 && i + 1 < n_units) {
+                ps_wait(wg_bar, ph);           // every weight-gradient MMA of the unit has completed
+                tc_fence_after();
+                flush_dw();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(flush_bar);
+            }
         }
         // ---- dW^T (TMEM lanes = k, columns = n) -> global accumulator [part][g*Npad + n][k];  bias gradient ----
         if (n_units > 0) {
@@ -1420,14 +1447,7 @@ __device__ void ps_field_bwd(const PsArgs& a, const PsMaps& maps, uint8_t* smem,
                 for (int j = 0; j < 8; ++j) bsum[(warp & 3) * Npad + bs_chunk * 8 + j] = bacc[j];
             }
             named_bar_sync(1, kPsEpi);
-            const int k = row;
-            for (int n0 = col_begin; n0 < col_end; n0 += 16) {
-                float v[16];
-                tmem_ld16(lane_addr + kTcDwCol + (uint32_t)n0, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    a.dW3acc[(((size_t)part * a.n_hg + g) * Npad + n0 + j) * 128 + k] = v[j];
-            }
+            flush_dw();
             for (int n = tid; n < Npad; n += kPsEpi) {
                 // columns no warp owns ([Hg * Cp, Npad) padding) were never written: they are zero by construction
                 const bool owned = n < a.Hg * a.Cp;

@@ -12,10 +12,9 @@ With eight tiles in flight the persistent kernels run the hand-offs the single-t
 stage s while tile t' is still in stage s-1, the dL/dk warp runs a unit ahead across tiles, the dX/dt ring and the activation-buffer
 halves are reused by different tiles back to back.  Bounds (relative max-norm): gradient of z0 1e-5 (bf16x3), 2e-2 (bf16, measured 4e-3:
 the order of the fp32 `red`s differs from run to run, the sums are then ROUNDED to bf16 for the next GEMM, and a last-bit difference there
-is 2^-9 — carried through 568 stages); parameter gradients 1e-3 (bf16x3) — the final layer's weight gradient stays
-in ONE fp32 TMEM accumulator for the whole pass (4544 units here) and the tensor core's accumulation is grouping-sensitive at the 3-5e-4
-level (tools/diag_multitile.py: 1 x 1024 vs 2 x 512 tiles 4.7e-4, 2 x 512 vs 4 x 256 2.8e-4; every other parameter 1-2e-5), well inside
-what the mode's own arithmetic costs against the fp32 path (3e-3 for the shard and for a single tile alike)."""
+is 2^-9 — carried through 568 stages); parameter gradients 1e-4 (bf16x3, measured 2e-5).  The final layer's weight gradient lives in a
+TMEM accumulator; kept there for a whole pass (4544 units here) the tensor core's accumulation was grouping-sensitive at the 3-5e-4 level
+(tools/diag_multitile.py: 1 x 1024 vs 2 x 512 tiles 4.7e-4), so it is added to the global fp32 sum every 512 units now (9e-6)."""
 import copy
 
 import pytest
@@ -27,7 +26,7 @@ from oracle import cde_oracle as O
 pytestmark = pytest.mark.gpu
 
 BOUNDS = {"bf16x3": 1e-5, "bf16": 2e-2}
-PARAM_BOUND = {"bf16x3": 1e-3, "bf16": 2e-2}
+PARAM_BOUND = {"bf16x3": 1e-4, "bf16": 2e-2}
 MODE_BOUNDS = {"bf16x3": (1e-4, 1.5e-2), "bf16": (1e-2, 1.5e-1)}     # states, gradients: tests/test_gpu_cfg5_full.py
 
 
@@ -73,8 +72,6 @@ def test_bench_shard_equals_its_parts(precision):
     errs = {n: PU.rel(gp[n], gp_sum[n]) for n in gp}
     print("bench shard vs its halves, %s: parameter gradients %s" % (precision, {k: "%.1e" % v for k, v in errs.items()}))
     assert max(errs.values()) <= PARAM_BOUND[precision], errs
-    if precision == "bf16x3":
-        assert max(v for n, v in errs.items() if not n.startswith("tanh_output_layer")) <= 1e-4, errs
     # one tile alone: the plan of the oracle-pinned single-tile tests
     rows = slice(0, 128)
     o_1, gz_1, _ = _solve(tc, func, c[rows].contiguous(), z0[rows].contiguous(), w[rows].contiguous(), precision)
