@@ -3,8 +3,9 @@
 // A CDE solve is sequential in time but the series of a batch are independent, so nothing forces all rows through stage s
 // before any row enters stage s+1.  The grid is one CTA per SM with two roles:
 //   field CTA (g, p)   owns h-group g of the final layer for its whole life: the W3 slice stays in shared memory and (backward)
-//                      the slice's weight gradient stays in TMEM for the WHOLE pass; it streams the 128-row batch tiles
-//                      p, p + n_part, ... through the warp-specialised tcgen05 pipeline of field_tc.cuh, stage after stage.
+//                      the slice's weight gradient stays in TMEM across the pass (added to the global fp32 sum every kPsFlushUnits
+//                      units); it streams the 128-row batch tiles p, p + n_part, ... through a warp-specialised tcgen05 pipeline,
+//                      stage after stage.
 //   hidden CTA j       owns batch tiles j, j + n_hid, ...: the hidden layers of the vector field (forward) / their input-gradient
 //                      chain (backward) as 128x128x128 MMAs chained out of shared memory.
 // The two roles hand tiles to each other through per-tile counters in global memory (release / acquire at gpu scope): a
@@ -15,16 +16,17 @@
 // lo = bf16(x - hi), and every GEMM is three MMAs hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator: 16 mantissa bits per
 // operand instead of 8, with bf16's full exponent range (gradients need it; an fp16 split does not have it).
 //
-// dX/dt is read by the epilogue threads straight from global memory (thread = batch row, 16-byte loads, one chunk ahead of its
-// use, L2-prefetched a unit ahead by the producer): the tile has no reuse inside a CTA beyond the Hg hidden rows of its
-// h-group, which L1 serves, and not staging it frees 54-108 KB of shared memory for operand tiles.
+// Warps of a field CTA: 0-7 epilogue (thread = TMEM lane = batch row), 8 producer (TMA of the activation tile; tcgen05.mma of the
+// forward GEMM / of the recompute and dgrad), 9 signaller (forward) / weight-gradient MMA issuer (backward), 10 dX/dt loader (TMA
+// boxes into a ring of chunk slots, in the order the epilogue consumes them), 11 (backward) forms dL/dk one unit ahead and signals.
+// Backward unit = one tile of one stage: recompute -> epilogue 1 (G, handed to the tensor core in 64-column blocks) -> dgrad, wgrad ->
+// epilogue 2 (red.global.add.v4 into the tile's dA^T); what waits for what, and what was measured, is in DESIGN.md 4.1.
 #pragma once
 #include "hidden_tc.cuh"
 
 namespace ncde {
 
-constexpr int kPsThreads = 384;           // 8 epilogue warps, warp 8 = producer (TMA + MMA issue), 9 = signaller, 10 = dX/dt loader,
-                                          // 11 = dL/dk former of the backward field role (idle elsewhere)
+constexpr int kPsThreads = 384;           // 12 warps, roles above (warps 9-11 idle in the hidden CTAs, warp 11 in the forward kernel)
 constexpr int kPsEpi = 256;
 constexpr int kPsFlushUnits = 512;        // backward field role: units between two flushes of the TMEM-resident weight gradient
 constexpr long long kPsSpinLimit = 6000000000ll;   // ~3 s at 2 GHz: a protocol error traps instead of hanging the GPU
